@@ -1,0 +1,96 @@
+"""ctypes binding of libgansynth_b200.so (include/gansynth_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, this raises.  Build it with
+``python -m gansynth_b200.build`` (or ``__graft_entry__.build()``).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgansynth_b200.so")
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+_L = ctypes.c_longlong
+_F = ctypes.c_float
+
+# name -> argument types (all functions return int); mirrors include/gansynth_b200.h
+SIGNATURES = {
+    "gs_conv2d_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P],
+    "gs_conv2d_dgrad": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P],
+    "gs_conv2d_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
+    "gs_conv2d_transpose_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P],
+    "gs_conv2d_transpose_dgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
+    "gs_conv2d_transpose_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
+    "gs_dense_fwd": [_P, _P, _P, _I, _I, _I, _F, _P],
+    "gs_dense_dgrad": [_P, _P, _P, _I, _I, _I, _F, _P],
+    "gs_dense_wgrad": [_P, _P, _P, _I, _I, _I, _F, _P],
+    "gs_embedding_fwd": [_P, _P, _P, _I, _I, _F, _P],
+    "gs_embedding_bwd": [_P, _P, _P, _I, _I, _I, _F, _P],
+    "gs_lrelu": [_P, _P, _L, _P],
+    "gs_lrelu_mask_mul": [_P, _P, _P, _L, _P],
+    "gs_tanh_fwd": [_P, _P, _L, _P],
+    "gs_tanh_bwd": [_P, _P, _P, _L, _P],
+    "gs_tanh_bwd2": [_P, _P, _P, _P, _L, _P],
+    "gs_bias_act": [_P, _P, _P, _L, _I, _I, _P],
+    "gs_row_broadcast": [_P, _P, _L, _I, _P],
+    "gs_col_sum": [_P, _P, _L, _I, _P],
+    "gs_axpby": [_P, _P, _P, _F, _F, _L, _P],
+    "gs_mul": [_P, _P, _P, _F, _L, _P],
+    "gs_pixel_norm_fwd": [_P, _P, _P, _L, _I, _F, _P],
+    "gs_pixel_norm_bwd": [_P, _P, _P, _P, _L, _I, _P],
+    "gs_pixel_norm_bwd2": [_P, _P, _P, _P, _P, _L, _I, _P],
+    "gs_batch_stddev_fwd": [_P, _P, _I, _L, _I, _F, _P],
+    "gs_batch_stddev_bwd": [_P, _P, _P, _I, _L, _I, _F, _P],
+    "gs_batch_stddev_bwd2": [_P, _P, _P, _P, _P, _I, _L, _I, _F, _P],
+    "gs_upscale2d": [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
+    "gs_pool2d": [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
+    "gs_transpose_inner": [_P, _P, _I, _I, _I, _P],
+    "gs_row_dot": [_P, _P, _P, _I, _L, _P],
+    "gs_row_scale": [_P, _P, _P, _I, _L, _F, _P],
+    "gs_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _L, _F, _P],
+    "gs_spectrogram_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "gs_waveform_fwd": [_P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _P],
+}
+
+_lib = None
+
+
+class GansynthLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the shared library (once) and declares every entry point.  Raises if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GansynthLibraryError(
+            "libgansynth_b200.so is not built (%s); run `python -m gansynth_b200.build`. "
+            "There is no CPU or PyTorch fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.gs_last_error.restype = ctypes.c_char_p
+    lib.gs_last_error.argtypes = []
+    lib.gs_version.restype = _I
+    lib.gs_version.argtypes = []
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = _I
+    _lib = lib
+    return lib
+
+
+launch_count = 0
+
+
+def call(name, *args):
+    """Calls a C-ABI entry point; raises GansynthLibraryError with gs_last_error() on failure."""
+    global launch_count
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise GansynthLibraryError("%s failed (%d): %s" % (name, rc, lib.gs_last_error().decode()))
+    launch_count += 1
+    return rc

@@ -1,0 +1,472 @@
+"""Autograd layer over the CUDA kernels.
+
+Every op is a torch.autograd.Function whose backward is built from OTHER Functions of this module, so
+the R1 penalty (models.py:46-49 of the reference: gradient of D w.r.t. real images, differentiated
+again w.r.t. D's weights) and the mode-seeking term (models.py:59-62: gradient of G w.r.t. latents,
+differentiated w.r.t. G's weights) run entirely on the hand-written kernels:
+
+* the convolution trio (gather C, transposed T, weight-gradient W) is bilinear and closed under
+  differentiation, likewise the dense trio;
+* leaky-relu has zero curvature, so only its mask (recovered from the sign of the output) is reused;
+* pixel-norm, tanh and minibatch-stddev carry hand-derived second-derivative kernels.
+
+PyTorch supplies the graph bookkeeping, device memory and streams only.  `K` is the kernel backend;
+it is a CudaBackend in the product.  (tests/ swap in a torch-CPU emulation of the same primitive API to
+check this module's graph logic against the oracle without a GPU.)
+"""
+import contextlib
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from .kernels import CudaBackend
+
+K = CudaBackend()
+
+ACT_NONE, ACT_LRELU = 0, 1
+
+
+def set_backend(backend):
+    global K
+    K = backend
+
+
+_SKIP_WGRAD = False
+
+
+@contextlib.contextmanager
+def skip_weight_grads():
+    """Inside this context the layer Functions do not compute parameter gradients in their backward.
+    Used around the first-order passes of the two penalties (gradient w.r.t. images / latents only):
+    the parameter gradients of that pass are never consumed."""
+    global _SKIP_WGRAD
+    prev, _SKIP_WGRAD = _SKIP_WGRAD, True
+    try:
+        yield
+    finally:
+        _SKIP_WGRAD = prev
+
+
+# ----------------------------------------------------------------------------- convolution trio
+class ConvC(Function):
+    """y = alpha * gather_conv(x, w)  (forward form of tf.nn.conv2d, ops.py:237)."""
+
+    @staticmethod
+    def forward(ctx, x, w, ksize, stride, wswap, alpha):
+        ctx.cfg = (ksize, stride, wswap, alpha)
+        ctx.save_for_backward(x, w)
+        return K.conv_c(x, w, None, ksize, stride, wswap, alpha, ACT_NONE)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        cfg = ctx.cfg
+        dx = ConvT.apply(dy, w, *cfg) if ctx.needs_input_grad[0] else None
+        dw = ConvW.apply(x, dy, *cfg) if ctx.needs_input_grad[1] else None
+        return dx, dw, None, None, None, None
+
+
+class ConvT(Function):
+    """dx = alpha * transposed_conv(dy, w)  (input-gradient form; forward of tf.nn.conv2d_transpose)."""
+
+    @staticmethod
+    def forward(ctx, dy, w, ksize, stride, wswap, alpha):
+        ctx.cfg = (ksize, stride, wswap, alpha)
+        ctx.save_for_backward(dy, w)
+        return K.conv_t(dy, w, None, ksize, stride, wswap, alpha, ACT_NONE)
+
+    @staticmethod
+    def backward(ctx, g):
+        dy, w = ctx.saved_tensors
+        cfg = ctx.cfg
+        gdy = ConvC.apply(g, w, *cfg) if ctx.needs_input_grad[0] else None
+        gw = ConvW.apply(g, dy, *cfg) if ctx.needs_input_grad[1] else None
+        return gdy, gw, None, None, None, None
+
+
+class ConvW(Function):
+    """dw = alpha * sum_pixels x (x) dy  (filter-gradient form)."""
+
+    @staticmethod
+    def forward(ctx, x, dy, ksize, stride, wswap, alpha):
+        ctx.cfg = (ksize, stride, wswap, alpha)
+        ctx.save_for_backward(x, dy)
+        return K.conv_w(x, dy, ksize, stride, wswap, alpha)
+
+    @staticmethod
+    def backward(ctx, gw):
+        x, dy = ctx.saved_tensors
+        cfg = ctx.cfg
+        gx = ConvT.apply(dy, gw, *cfg) if ctx.needs_input_grad[0] else None
+        gdy = ConvC.apply(x, gw, *cfg) if ctx.needs_input_grad[1] else None
+        return gx, gdy, None, None, None, None
+
+
+class ConvLayer(Function):
+    """Fused layer forward: act(alpha * conv(x, w) + bias), conv in gather (`form`='c') or transposed
+    ('t') form.  The backward un-fuses into MaskMul / ColSum / the trio so it stays differentiable."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, form, ksize, stride, wswap, alpha, act):
+        fn = K.conv_c if form == "c" else K.conv_t
+        y = fn(x, w, bias, ksize, stride, wswap, alpha, act)
+        ctx.cfg = (ksize, stride, wswap, alpha)
+        ctx.form, ctx.act, ctx.has_bias = form, act, bias is not None
+        ctx.save_for_backward(x, w, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        cfg = ctx.cfg
+        dz = MaskMul.apply(dy, y) if ctx.act == ACT_LRELU else dy
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = (ConvT if ctx.form == "c" else ConvC).apply(dz, w, *cfg)
+        if ctx.needs_input_grad[1] and not _SKIP_WGRAD:
+            dw = ConvW.apply(x, dz, *cfg) if ctx.form == "c" else ConvW.apply(dz, x, *cfg)
+        if ctx.has_bias and ctx.needs_input_grad[2] and not _SKIP_WGRAD:
+            db = ColSum.apply(dz)
+        return dx, dw, db, None, None, None, None, None, None
+
+
+# ----------------------------------------------------------------------------- activations / bias
+class MaskMul(Function):
+    """v * lrelu'(.) with the mask taken from the sign of the layer OUTPUT y (same sign as the input)."""
+
+    @staticmethod
+    def forward(ctx, v, y):
+        ctx.save_for_backward(y)
+        return K.mask_mul(v, y)
+
+    @staticmethod
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        return MaskMul.apply(g, y), None
+
+
+class LeakyRelu(Function):
+    @staticmethod
+    def forward(ctx, x):
+        y = K.lrelu(x)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        return MaskMul.apply(g, y)
+
+
+class ColSum(Function):
+    """[..., C] -> [C] (bias gradient)."""
+
+    @staticmethod
+    def forward(ctx, v):
+        ctx.lead = tuple(v.shape[:-1])
+        return K.col_sum(v)
+
+    @staticmethod
+    def backward(ctx, g):
+        return RowBroadcast.apply(g, ctx.lead)
+
+
+class RowBroadcast(Function):
+    @staticmethod
+    def forward(ctx, s, lead):
+        return K.row_broadcast(s, lead)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ColSum.apply(g), None
+
+
+class BiasAct(Function):
+    """act(x + bias) on [..., C] (dense layers)."""
+
+    @staticmethod
+    def forward(ctx, x, bias, act):
+        y = K.bias_act(x, bias, act)
+        ctx.act = act
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dz = MaskMul.apply(dy, y) if ctx.act == ACT_LRELU else dy
+        db = ColSum.apply(dz) if (ctx.needs_input_grad[1] and not _SKIP_WGRAD) else None
+        return dz, db, None
+
+
+class Tanh(Function):
+    @staticmethod
+    def forward(ctx, x):
+        y = K.tanh_fwd(x)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        return TanhBwd.apply(y, dy)
+
+
+class TanhBwd(Function):
+    """dy * (1 - y^2); d/dy-out = -2 y dy u, d/d(dy) = u (1 - y^2)."""
+
+    @staticmethod
+    def forward(ctx, y, dy):
+        ctx.save_for_backward(y, dy)
+        return K.tanh_bwd(y, dy)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, u):
+        y, dy = ctx.saved_tensors
+        return K.tanh_bwd2(y, dy, u), K.tanh_bwd(y, u)
+
+
+class Axpby(Function):
+    """alpha * a + beta * b (lerp, networks.py:10-11)."""
+
+    @staticmethod
+    def forward(ctx, a, b, alpha, beta):
+        ctx.ab = (alpha, beta)
+        return K.axpby(a, b, alpha, beta)
+
+    @staticmethod
+    def backward(ctx, g):
+        alpha, beta = ctx.ab
+        return Scale.apply(g, alpha), Scale.apply(g, beta), None, None
+
+
+class Scale(Function):
+    @staticmethod
+    def forward(ctx, a, s):
+        ctx.s = s
+        return K.axpby(a, None, s, 0.0)
+
+    @staticmethod
+    def backward(ctx, g):
+        return Scale.apply(g, ctx.s), None
+
+
+# ----------------------------------------------------------------------------- pixel norm
+class PixelNorm(Function):
+    """ops.py:330-333 over the last (channel) axis."""
+
+    @staticmethod
+    def forward(ctx, a, eps):
+        y, r = K.pn_fwd(a, eps)
+        ctx.save_for_backward(a, r)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, r = ctx.saved_tensors
+        return PixelNormBwd.apply(a, r, dy), None
+
+
+class PixelNormBwd(Function):
+    """da = r dy - (r^3/C)(a.dy) a.  Symmetric in the sense J(a)^T = J(a), so d/d(dy) reuses itself;
+    d/da is the hand-derived second-order kernel (gs_pixel_norm_bwd2)."""
+
+    @staticmethod
+    def forward(ctx, a, r, dy):
+        ctx.save_for_backward(a, r, dy)
+        return K.pn_bwd(a, r, dy)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, u):
+        a, r, dy = ctx.saved_tensors
+        return K.pn_bwd2(a, r, dy, u), None, K.pn_bwd(a, r, u)
+
+
+# ----------------------------------------------------------------------------- dense trio / embedding
+class DenseF(Function):
+    @staticmethod
+    def forward(ctx, x, w, alpha):
+        ctx.alpha = alpha
+        ctx.save_for_backward(x, w)
+        return K.dense_fwd(x, w, alpha)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dx = DenseD.apply(dy, w, ctx.alpha) if ctx.needs_input_grad[0] else None
+        dw = DenseW.apply(x, dy, ctx.alpha) if (ctx.needs_input_grad[1] and not _SKIP_WGRAD) else None
+        return dx, dw, None
+
+
+class DenseD(Function):
+    @staticmethod
+    def forward(ctx, dy, w, alpha):
+        ctx.alpha = alpha
+        ctx.save_for_backward(dy, w)
+        return K.dense_dgrad(dy, w, alpha)
+
+    @staticmethod
+    def backward(ctx, g):
+        dy, w = ctx.saved_tensors
+        gdy = DenseF.apply(g, w, ctx.alpha) if ctx.needs_input_grad[0] else None
+        gw = DenseW.apply(g, dy, ctx.alpha) if ctx.needs_input_grad[1] else None
+        return gdy, gw, None
+
+
+class DenseW(Function):
+    @staticmethod
+    def forward(ctx, x, dy, alpha):
+        ctx.alpha = alpha
+        ctx.save_for_backward(x, dy)
+        return K.dense_wgrad(x, dy, alpha)
+
+    @staticmethod
+    def backward(ctx, gw):
+        x, dy = ctx.saved_tensors
+        gx = DenseD.apply(dy, gw, ctx.alpha) if ctx.needs_input_grad[0] else None
+        gdy = DenseF.apply(x, gw, ctx.alpha) if ctx.needs_input_grad[1] else None
+        return gx, gdy, None
+
+
+class Embedding(Function):
+    @staticmethod
+    def forward(ctx, table, idx, alpha):
+        ctx.alpha, ctx.rows = alpha, table.shape[0]
+        ctx.save_for_backward(idx)
+        return K.embedding_fwd(table, idx, alpha)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        if _SKIP_WGRAD or not ctx.needs_input_grad[0]:
+            return None, None, None
+        return EmbeddingBwd.apply(dy, idx, ctx.rows, ctx.alpha), None, None
+
+
+class EmbeddingBwd(Function):
+    @staticmethod
+    def forward(ctx, dy, idx, rows, alpha):
+        ctx.alpha = alpha
+        ctx.save_for_backward(idx)
+        return K.embedding_bwd(dy, idx, rows, alpha)
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        return Embedding.apply(g, idx, ctx.alpha), None, None, None
+
+
+# ----------------------------------------------------------------------------- resampling / layout
+class Upscale(Function):
+    """scale * nearest-neighbour repeat (ops.py:283-291)."""
+
+    @staticmethod
+    def forward(ctx, x, fh, fw, scale):
+        ctx.cfg = (fh, fw, scale)
+        return K.upscale(x, fh, fw, scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        return Pool.apply(g, *ctx.cfg), None, None, None
+
+
+class Pool(Function):
+    """scale * sum-pool with kernel = stride = (fh, fw); downscale2d (ops.py:294-305) is scale 1/(fh*fw)."""
+
+    @staticmethod
+    def forward(ctx, x, fh, fw, scale):
+        ctx.cfg = (fh, fw, scale)
+        return K.pool(x, fh, fw, scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        return Upscale.apply(g, *ctx.cfg), None, None, None
+
+
+class TransposeInner(Function):
+    """[n, a, b] -> [n, b, a]; NCHW <-> NHWC with (a, b) = (C, H*W)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return K.transpose_inner(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return TransposeInner.apply(g)
+
+
+def nchw_to_nhwc(x):
+    n, c, h, w = x.shape
+    return TransposeInner.apply(x.reshape(n, c, h * w)).reshape(n, h, w, c)
+
+
+def nhwc_to_nchw(x):
+    n, h, w, c = x.shape
+    return TransposeInner.apply(x.reshape(n, h * w, c)).reshape(n, c, h, w)
+
+
+# ----------------------------------------------------------------------------- per-sample reductions
+class RowDot(Function):
+    """[B, E] x [B, E] -> [B]."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.save_for_backward(a, b)
+        return K.row_dot(a, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        ga = RowScale.apply(b, g) if ctx.needs_input_grad[0] else None
+        gb = RowScale.apply(a, g) if ctx.needs_input_grad[1] else None
+        return ga, gb
+
+
+class RowScale(Function):
+    """out[b, e] = a[b, e] * s[b]."""
+
+    @staticmethod
+    def forward(ctx, a, s):
+        ctx.save_for_backward(a, s)
+        return K.row_scale(a, s, 1.0)
+
+    @staticmethod
+    def backward(ctx, u):
+        a, s = ctx.saved_tensors
+        ga = RowScale.apply(u, s) if ctx.needs_input_grad[0] else None
+        gs = RowDot.apply(u, a) if ctx.needs_input_grad[1] else None
+        return ga, gs
+
+
+# ----------------------------------------------------------------------------- minibatch stddev
+class BatchStddev(Function):
+    """x [B, E] -> statistic [B/groups] (ops.py:336-347 up to the final tile)."""
+
+    @staticmethod
+    def forward(ctx, x, groups, eps):
+        ctx.cfg = (groups, eps)
+        ctx.save_for_backward(x)
+        return K.stddev_fwd(x, groups, eps)
+
+    @staticmethod
+    def backward(ctx, df):
+        (x,) = ctx.saved_tensors
+        return BatchStddevBwd.apply(x, df, *ctx.cfg), None, None
+
+
+class BatchStddevBwd(Function):
+    @staticmethod
+    def forward(ctx, x, df, groups, eps):
+        ctx.cfg = (groups, eps)
+        ctx.save_for_backward(x, df)
+        return K.stddev_bwd(x, df, groups, eps)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, u):
+        x, df = ctx.saved_tensors
+        gx, q = K.stddev_bwd2(x, df, u, *ctx.cfg)
+        return gx, q, None, None

@@ -1,0 +1,274 @@
+"""Thin tensor-level wrappers over the C ABI: allocate outputs with torch (device memory plumbing),
+pass raw device pointers and the current CUDA stream to libgansynth_b200.so.
+
+Activations are NHWC fp32.  Every method requires CUDA tensors and fails loudly otherwise -- there is
+no CPU path in the product.
+"""
+import torch
+
+from . import _lib
+
+IMPL_AUTO, IMPL_NAIVE, IMPL_TILED = 0, 1, 2
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(*tensors):
+    out = []
+    for t in tensors:
+        if t is None:
+            out.append(None)
+            continue
+        if not t.is_cuda:
+            raise _lib.GansynthLibraryError("gansynth_b200 kernels need CUDA tensors (got %s); no CPU fallback" % t.device)
+        if t.dtype != torch.float32:
+            raise TypeError("expected float32, got %s" % t.dtype)
+        out.append(t if t.is_contiguous() else t.contiguous())
+    return out
+
+
+class CudaBackend(object):
+    """The primitive-kernel API the autograd functions in functional.py are written against."""
+
+    impl = IMPL_AUTO
+
+    # ------------------------------------------------------------------ convolution family
+    def conv_c(self, x, w, bias, ksize, stride, wswap, alpha, act):
+        x, w, bias = _chk(x, w, bias)
+        n, h, wd, ci = x.shape
+        co = w.shape[2] if wswap else w.shape[3]
+        assert (w.shape[3] if wswap else w.shape[2]) == ci, "conv_c: weight/input channel mismatch"
+        y = torch.empty((n, h // stride, wd // stride, co), device=x.device, dtype=torch.float32)
+        _lib.call("gs_conv2d_fwd", _ptr(x), _ptr(w), _ptr(bias), _ptr(y), n, h, wd, ci, co, ksize, stride,
+                  int(wswap), float(alpha), int(act), self.impl, _stream())
+        return y
+
+    def conv_t(self, dy, w, bias, ksize, stride, wswap, alpha, act):
+        dy, w, bias = _chk(dy, w, bias)
+        n, oh, ow, co = dy.shape
+        ci = w.shape[3] if wswap else w.shape[2]
+        assert (w.shape[2] if wswap else w.shape[3]) == co, "conv_t: weight/input channel mismatch"
+        h, wd = oh * stride, ow * stride
+        dx = torch.empty((n, h, wd, ci), device=dy.device, dtype=torch.float32)
+        _lib.call("gs_conv2d_dgrad", _ptr(dy), _ptr(w), _ptr(bias), _ptr(dx), n, h, wd, ci, co, ksize, stride,
+                  int(wswap), float(alpha), int(act), self.impl, _stream())
+        return dx
+
+    def conv_w(self, x, dy, ksize, stride, wswap, alpha):
+        x, dy = _chk(x, dy)
+        n, h, wd, ci = x.shape
+        co = dy.shape[3]
+        shape = (ksize, ksize, co, ci) if wswap else (ksize, ksize, ci, co)
+        dw = torch.empty(shape, device=x.device, dtype=torch.float32)
+        _lib.call("gs_conv2d_wgrad", _ptr(x), _ptr(dy), _ptr(dw), n, h, wd, ci, co, ksize, stride, int(wswap),
+                  float(alpha), self.impl, _stream())
+        return dw
+
+    # ------------------------------------------------------------------ dense / embedding
+    def dense_fwd(self, x, w, alpha):
+        x, w = _chk(x, w)
+        m, k = x.shape
+        n = w.shape[1]
+        y = torch.empty((m, n), device=x.device, dtype=torch.float32)
+        _lib.call("gs_dense_fwd", _ptr(x), _ptr(w), _ptr(y), m, k, n, float(alpha), _stream())
+        return y
+
+    def dense_dgrad(self, dy, w, alpha):
+        dy, w = _chk(dy, w)
+        m, n = dy.shape
+        k = w.shape[0]
+        dx = torch.empty((m, k), device=dy.device, dtype=torch.float32)
+        _lib.call("gs_dense_dgrad", _ptr(dy), _ptr(w), _ptr(dx), m, k, n, float(alpha), _stream())
+        return dx
+
+    def dense_wgrad(self, x, dy, alpha):
+        x, dy = _chk(x, dy)
+        m, k = x.shape
+        n = dy.shape[1]
+        dw = torch.empty((k, n), device=x.device, dtype=torch.float32)
+        _lib.call("gs_dense_wgrad", _ptr(x), _ptr(dy), _ptr(dw), m, k, n, float(alpha), _stream())
+        return dw
+
+    def embedding_fwd(self, table, idx, alpha):
+        (table,) = _chk(table)
+        idx = idx.contiguous()
+        assert idx.dtype == torch.int64 and idx.is_cuda
+        b, units = idx.shape[0], table.shape[1]
+        out = torch.empty((b, units), device=table.device, dtype=torch.float32)
+        _lib.call("gs_embedding_fwd", _ptr(table), _ptr(idx), _ptr(out), b, units, float(alpha), _stream())
+        return out
+
+    def embedding_bwd(self, dy, idx, rows, alpha):
+        (dy,) = _chk(dy)
+        idx = idx.contiguous()
+        b, units = dy.shape
+        out = torch.empty((rows, units), device=dy.device, dtype=torch.float32)
+        _lib.call("gs_embedding_bwd", _ptr(dy), _ptr(idx), _ptr(out), b, rows, units, float(alpha), _stream())
+        return out
+
+    # ------------------------------------------------------------------ elementwise
+    def _ew(self, name, *ins, extra=()):
+        ins = _chk(*ins)
+        out = torch.empty_like(ins[0])
+        _lib.call(name, *[_ptr(t) for t in ins], _ptr(out), *extra, ins[0].numel(), _stream())
+        return out
+
+    def lrelu(self, x):
+        return self._ew("gs_lrelu", x)
+
+    def mask_mul(self, v, y):
+        return self._ew("gs_lrelu_mask_mul", v, y)
+
+    def tanh_fwd(self, x):
+        return self._ew("gs_tanh_fwd", x)
+
+    def tanh_bwd(self, y, dy):
+        return self._ew("gs_tanh_bwd", y, dy)
+
+    def tanh_bwd2(self, y, dy, u):
+        return self._ew("gs_tanh_bwd2", y, dy, u)
+
+    def axpby(self, a, b, alpha, beta):
+        a, b = _chk(a, b)
+        out = torch.empty_like(a)
+        _lib.call("gs_axpby", _ptr(a), _ptr(b), _ptr(out), float(alpha), float(beta), a.numel(), _stream())
+        return out
+
+    def bias_act(self, x, bias, act):
+        x, bias = _chk(x, bias)
+        c = x.shape[-1]
+        out = torch.empty_like(x)
+        _lib.call("gs_bias_act", _ptr(x), _ptr(bias), _ptr(out), x.numel() // c, c, int(act), _stream())
+        return out
+
+    def row_broadcast(self, s, lead_shape):
+        (s,) = _chk(s)
+        c = s.numel()
+        out = torch.empty(tuple(lead_shape) + (c,), device=s.device, dtype=torch.float32)
+        _lib.call("gs_row_broadcast", _ptr(s), _ptr(out), out.numel() // c, c, _stream())
+        return out
+
+    def col_sum(self, v):
+        (v,) = _chk(v)
+        c = v.shape[-1]
+        out = torch.empty((c,), device=v.device, dtype=torch.float32)
+        _lib.call("gs_col_sum", _ptr(v), _ptr(out), v.numel() // c, c, _stream())
+        return out
+
+    # ------------------------------------------------------------------ pixel norm
+    def pn_fwd(self, a, eps):
+        (a,) = _chk(a)
+        c = a.shape[-1]
+        y = torch.empty_like(a)
+        r = torch.empty(a.shape[:-1], device=a.device, dtype=torch.float32)
+        _lib.call("gs_pixel_norm_fwd", _ptr(a), _ptr(y), _ptr(r), a.numel() // c, c, float(eps), _stream())
+        return y, r
+
+    def pn_bwd(self, a, r, dy):
+        a, r, dy = _chk(a, r, dy)
+        c = a.shape[-1]
+        da = torch.empty_like(a)
+        _lib.call("gs_pixel_norm_bwd", _ptr(a), _ptr(r), _ptr(dy), _ptr(da), a.numel() // c, c, _stream())
+        return da
+
+    def pn_bwd2(self, a, r, dy, u):
+        a, r, dy, u = _chk(a, r, dy, u)
+        c = a.shape[-1]
+        ga = torch.empty_like(a)
+        _lib.call("gs_pixel_norm_bwd2", _ptr(a), _ptr(r), _ptr(dy), _ptr(u), _ptr(ga), a.numel() // c, c, _stream())
+        return ga
+
+    # ------------------------------------------------------------------ minibatch stddev on [B, E]
+    def stddev_fwd(self, x, groups, eps):
+        (x,) = _chk(x)
+        b, e = x.shape
+        stat = torch.empty((b // groups,), device=x.device, dtype=torch.float32)
+        _lib.call("gs_batch_stddev_fwd", _ptr(x), _ptr(stat), b, e, groups, float(eps), _stream())
+        return stat
+
+    def stddev_bwd(self, x, df, groups, eps):
+        x, df = _chk(x, df)
+        b, e = x.shape
+        dx = torch.empty_like(x)
+        _lib.call("gs_batch_stddev_bwd", _ptr(x), _ptr(df), _ptr(dx), b, e, groups, float(eps), _stream())
+        return dx
+
+    def stddev_bwd2(self, x, df, u, groups, eps):
+        x, df, u = _chk(x, df, u)
+        b, e = x.shape
+        gx = torch.empty_like(x)
+        q = torch.empty((b // groups,), device=x.device, dtype=torch.float32)
+        _lib.call("gs_batch_stddev_bwd2", _ptr(x), _ptr(df), _ptr(u), _ptr(gx), _ptr(q), b, e, groups, float(eps),
+                  _stream())
+        return gx, q
+
+    # ------------------------------------------------------------------ resampling / layout
+    def upscale(self, x, fh, fw, scale):
+        (x,) = _chk(x)
+        n, h, w, c = x.shape
+        out = torch.empty((n, h * fh, w * fw, c), device=x.device, dtype=torch.float32)
+        _lib.call("gs_upscale2d", _ptr(x), _ptr(out), n, h, w, c, fh, fw, float(scale), _stream())
+        return out
+
+    def pool(self, x, fh, fw, scale):
+        (x,) = _chk(x)
+        n, hh, ww, c = x.shape
+        h, w = hh // fh, ww // fw
+        out = torch.empty((n, h, w, c), device=x.device, dtype=torch.float32)
+        _lib.call("gs_pool2d", _ptr(x), _ptr(out), n, h, w, c, fh, fw, float(scale), _stream())
+        return out
+
+    def transpose_inner(self, x):
+        """[n, a, b] -> [n, b, a]"""
+        (x,) = _chk(x)
+        n, a, b = x.shape
+        out = torch.empty((n, b, a), device=x.device, dtype=torch.float32)
+        _lib.call("gs_transpose_inner", _ptr(x), _ptr(out), n, a, b, _stream())
+        return out
+
+    # ------------------------------------------------------------------ per-sample row ops on [B, E]
+    def row_dot(self, a, b):
+        a, b = _chk(a, b)
+        rows, e = a.shape
+        out = torch.empty((rows,), device=a.device, dtype=torch.float32)
+        _lib.call("gs_row_dot", _ptr(a), _ptr(b), _ptr(out), rows, e, _stream())
+        return out
+
+    def row_scale(self, a, s, alpha=1.0):
+        a, s = _chk(a, s)
+        rows, e = a.shape
+        out = torch.empty_like(a)
+        _lib.call("gs_row_scale", _ptr(a), _ptr(s), _ptr(out), rows, e, float(alpha), _stream())
+        return out
+
+    # ------------------------------------------------------------------ optimiser
+    def adam_step(self, p, g, m, v, lr, beta1, beta2, eps, t, grad_scale=1.0):
+        for tns in (p, g, m, v):
+            assert tns.is_cuda and tns.is_contiguous() and tns.dtype == torch.float32
+        _lib.call("gs_adam_step", _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), float(beta1),
+                  float(beta2), float(eps), int(t), float(grad_scale), _stream())
+
+    # ------------------------------------------------------------------ spectral
+    def spectrogram_fwd(self, wave, consts, time_steps, frames_per_chunk):
+        (wave,) = _chk(wave)
+        b, wave_len = wave.shape
+        logmel = torch.empty((b, time_steps, 1024), device=wave.device, dtype=torch.float32)
+        inst = torch.empty_like(logmel)
+        _lib.call("gs_spectrogram_fwd", _ptr(wave), _ptr(consts["hann"]), _ptr(consts["mel_k0"]), _ptr(consts["mel_w"]),
+                  _ptr(logmel), _ptr(inst), b, wave_len, time_steps, frames_per_chunk, _stream())
+        return logmel, inst
+
+    def waveform_fwd(self, logmel, inst, consts, wave_len):
+        logmel, inst = _chk(logmel, inst)
+        b, time_steps, _ = logmel.shape
+        wave = torch.empty((b, wave_len), device=logmel.device, dtype=torch.float32)
+        _lib.call("gs_waveform_fwd", _ptr(logmel), _ptr(inst), _ptr(consts["synth_window"]), _ptr(consts["pb_j0"]),
+                  _ptr(consts["pb_cnt"]), _ptr(consts["pb_w"]), int(consts["band"]), _ptr(wave), b, wave_len,
+                  time_steps, _stream())
+        return wave

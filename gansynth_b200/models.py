@@ -1,0 +1,338 @@
+"""GANSynth model / training step on the CUDA kernels (host mirror of reference models.py:8-250:
+same constructor, `train`, `evaluate`, `generate` signatures).
+
+The reference builds one TF graph and alternates session.run(discriminator_train_op) /
+session.run(generator_train_op) (models.py:189-192), each run pulling a fresh real batch and fresh
+latents.  Here each run is an eager sub-step:
+
+  D sub-step: G forward (no graph) -> spectral forward on the real batch -> D(real), D(fake) ->
+              softplus losses + R1 penalty (double backward through D) -> grads of D vars -> [all-reduce]
+              -> fused TF-Adam on the flat D buffer.
+  G sub-step: G forward -> D(fake) -> softplus loss + mode-seeking term (double backward through G) ->
+              grads of G vars -> [all-reduce] -> fused TF-Adam on the flat G buffer; global_step += 1.
+
+Data parallel (new design): one process per GPU, identical replicas, rank-local batch (and
+rank-local batch_stddev groups), one NCCL all-reduce of the flat gradient buffer per sub-step.
+"""
+import glob
+import os
+import time
+
+import numpy as np
+import torch
+
+from . import functional as F
+from . import ops
+from . import spectral_ops
+
+
+class GlobalStep(object):
+    """Host-side tf.train global step: an int that can be divided into a lazily evaluated level."""
+
+    def __init__(self):
+        self.value = 0
+
+    def __int__(self):
+        return int(self.value)
+
+    def __float__(self):
+        return float(self.value)
+
+    def __truediv__(self, other):
+        return lambda: float(self.value) / float(other)
+
+
+_global_step = None
+
+
+def get_or_create_global_step():
+    global _global_step
+    if _global_step is None:
+        _global_step = GlobalStep()
+    return _global_step
+
+
+def reset_global_step():
+    global _global_step
+    _global_step = None
+
+
+def _to_device(x, device, dtype=torch.float32):
+    if torch.is_tensor(x):
+        return x.to(device=device, dtype=dtype, non_blocking=True)
+    return torch.as_tensor(np.asarray(x)).to(device=device, dtype=dtype, non_blocking=True)
+
+
+def _select_logits(logits, labels):
+    """models.py:39-40: tf.gather_nd(logits, tf.where(labels)) -> the logit of the true class, [B]."""
+    return logits.gather(1, torch.argmax(labels, dim=1, keepdim=True))[:, 0]
+
+
+class GANSynth(object):
+
+    def __init__(self, generator, discriminator, real_input_fn, fake_input_fn, spectral_params, hyper_params,
+                 device="cuda", process_group=None):
+        self.generator = generator
+        self.discriminator = discriminator
+        self.real_input_fn = real_input_fn
+        self.fake_input_fn = fake_input_fn
+        self.spectral_params = dict(spectral_params)
+        self.hyper_params = hyper_params
+        self.device = torch.device(device)
+        self.process_group = process_group
+        self.global_step = get_or_create_global_step()
+        self.store = ops.default_store()
+        self._opt = None
+        self.generator_loss = None
+        self.discriminator_loss = None
+        # last evaluated tensors, named like the reference attributes (models.py:91-108)
+        self.real_waveforms = self.fake_waveforms = None
+        self.real_images = self.fake_images = None
+        self.real_labels = self.fake_labels = None
+        self.real_features = self.fake_features = None
+        self.real_logits = self.fake_logits = None
+
+    # ------------------------------------------------------------------ inputs
+    def _next_real(self):
+        waveforms, labels = self.real_input_fn()
+        return _to_device(waveforms, self.device), _to_device(labels, self.device)
+
+    def _next_latents(self):
+        return _to_device(self.fake_input_fn(), self.device)
+
+    def real_images_from_waveforms(self, waveforms):
+        """models.py:27-28."""
+        mag, inst = spectral_ops.convert_to_spectrogram(waveforms, **self.spectral_params)
+        return torch.stack([mag, inst], dim=1)
+
+    # ------------------------------------------------------------------ losses
+    def discriminator_loss_fn(self, real_images, labels, latents):
+        """models.py:25-54, 65."""
+        hp = self.hyper_params
+        with torch.no_grad():
+            fake_images = self.generator(latents, labels)
+        real_images = real_images.detach().requires_grad_(True)
+        real_features, real_logits = self.discriminator(real_images, labels)
+        fake_features, fake_logits = self.discriminator(fake_images, labels)
+        real_logits = _select_logits(real_logits, labels)
+        fake_logits = _select_logits(fake_logits, labels)
+        losses = torch.nn.functional.softplus(-real_logits) + torch.nn.functional.softplus(fake_logits)
+        if hp["real_gradient_penalty_weight"]:
+            with F.skip_weight_grads():
+                (grads,) = torch.autograd.grad(real_logits, real_images, grad_outputs=torch.ones_like(real_logits),
+                                               create_graph=True)
+            flat = grads.reshape(grads.shape[0], -1)
+            losses = losses + F.RowDot.apply(flat, flat) * hp["real_gradient_penalty_weight"]
+        if hp.get("fake_gradient_penalty_weight"):
+            raise NotImplementedError("fake_gradient_penalty_weight != 0 is not on the reference path "
+                                      "(gan_synth_main.py:87)")
+        self.real_images, self.fake_images = real_images.detach(), fake_images
+        self.real_features, self.fake_features = real_features.detach(), fake_features.detach()
+        self.real_logits, self.fake_logits = real_logits.detach(), fake_logits.detach()
+        return losses.mean()
+
+    def generator_loss_fn(self, labels, latents):
+        """models.py:25, 34, 57-64."""
+        hp = self.hyper_params
+        latents = latents.detach().requires_grad_(True)
+        fake_images = self.generator(latents, labels)
+        fake_features, fake_logits = self.discriminator(fake_images, labels)
+        fake_logits = _select_logits(fake_logits, labels)
+        losses = torch.nn.functional.softplus(-fake_logits)
+        if hp["mode_seeking_loss_weight"]:
+            with F.skip_weight_grads():
+                (lg,) = torch.autograd.grad(fake_images, latents, grad_outputs=self._ones_like(fake_images),
+                                            create_graph=True)
+            losses = losses + hp["mode_seeking_loss_weight"] / (F.RowDot.apply(lg, lg) + 1.0e-6)
+        self.fake_images = fake_images.detach()
+        self.fake_features, self.fake_logits = fake_features.detach(), fake_logits.detach()
+        return losses.mean()
+
+    def _ones_like(self, t):
+        key = (tuple(t.shape), t.device)
+        if getattr(self, "_ones_key", None) != key:
+            self._ones_key, self._ones = key, torch.ones_like(t)
+        return self._ones
+
+    # ------------------------------------------------------------------ optimiser state
+    def _ensure_optimizers(self, labels, latents):
+        if self._opt is not None:
+            return
+        # touch both networks once so that every variable exists, then pack them into flat buffers
+        with torch.no_grad():
+            pg = getattr(self.generator, "__self__", None)
+            if pg is not None and hasattr(pg, "_ensure_variables"):
+                pg._ensure_variables("generator", latents.shape[1], labels.shape[1])
+                pg._ensure_variables("discriminator", 0, labels.shape[1])
+            else:
+                self.discriminator(self.generator(latents, labels), labels)
+        self._opt = {}
+        for scope in ("generator", "discriminator"):
+            flat = self.store.pack(scope)
+            self._opt[scope] = dict(flat=flat, grad=torch.zeros_like(flat), m=torch.zeros_like(flat),
+                                    v=torch.zeros_like(flat), t=0)
+
+    def _set_trainable(self, scope):
+        for n, v in self.store.vars.items():
+            v.requires_grad_(n.startswith(scope + "/"))
+
+    def _apply(self, scope, loss):
+        """minimize(loss, var_list=scope variables) (models.py:81-89) with TF-Adam semantics."""
+        hp = self.hyper_params
+        st = self._opt[scope]
+        variables = list(self.store.trainable_variables(scope).values())
+        grads = torch.autograd.grad(loss, variables, allow_unused=True)
+        off = 0
+        gflat = st["grad"]
+        for v, g in zip(variables, grads):
+            k = v.numel()
+            if g is None:
+                gflat[off:off + k].zero_()
+            else:
+                gflat[off:off + k].copy_(g.reshape(-1))
+            off += k
+        scale = 1.0
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            world = torch.distributed.get_world_size(self.process_group)
+            if world > 1:
+                torch.distributed.all_reduce(gflat, group=self.process_group)
+                scale = 1.0 / world
+        st["t"] += 1
+        F.K.adam_step(st["flat"], gflat, st["m"], st["v"], hp[scope + "_learning_rate"], hp[scope + "_beta1"],
+                      hp[scope + "_beta2"], 1.0e-8, st["t"], scale)
+
+    # ------------------------------------------------------------------ sub-steps (one session.run each)
+    def discriminator_step(self, real_waveforms=None, labels=None, latents=None):
+        if real_waveforms is None:
+            real_waveforms, labels = self._next_real()
+        if latents is None:
+            latents = self._next_latents()
+        self._ensure_optimizers(labels, latents)
+        self._set_trainable("discriminator")
+        self.real_waveforms, self.real_labels, self.fake_labels = real_waveforms, labels, labels
+        real_images = self.real_images_from_waveforms(real_waveforms)
+        loss = self.discriminator_loss_fn(real_images, labels, latents)
+        self._apply("discriminator", loss)
+        self.discriminator_loss = loss.detach()
+        return self.discriminator_loss
+
+    def generator_step(self, labels=None, latents=None):
+        if labels is None:
+            _, labels = self._next_real()
+        if latents is None:
+            latents = self._next_latents()
+        self._ensure_optimizers(labels, latents)
+        self._set_trainable("generator")
+        self.real_labels = self.fake_labels = labels
+        loss = self.generator_loss_fn(labels, latents)
+        self._apply("generator", loss)
+        self.generator_loss = loss.detach()
+        self.global_step.value += 1
+        return self.generator_loss
+
+    def train_step(self):
+        """One iteration of the reference hot loop (models.py:189-192)."""
+        d = self.discriminator_step()
+        g = self.generator_step()
+        return d, g
+
+    # ------------------------------------------------------------------ checkpoints
+    def _checkpoint_state(self):
+        state = dict(global_step=int(self.global_step.value), variables=self.store.state())
+        if self._opt is not None:
+            state["optimizers"] = {s: dict(m=o["m"].cpu(), v=o["v"].cpu(), t=o["t"]) for s, o in self._opt.items()}
+        return state
+
+    def save_checkpoint(self, model_dir, max_to_keep=10):
+        os.makedirs(model_dir, exist_ok=True)
+        path = os.path.join(model_dir, "model.ckpt-%d.pt" % int(self.global_step.value))
+        torch.save(self._checkpoint_state(), path)
+        kept = sorted(glob.glob(os.path.join(model_dir, "model.ckpt-*.pt")),
+                      key=lambda p: int(p.rsplit("-", 1)[1][:-3]))
+        for old in kept[:-max_to_keep]:
+            os.remove(old)
+        return path
+
+    def restore_latest(self, model_dir, labels=None, latents=None):
+        """Implicit restore of SingularMonitoredSession(checkpoint_dir=model_dir) (models.py:120)."""
+        paths = sorted(glob.glob(os.path.join(model_dir, "model.ckpt-*.pt")),
+                       key=lambda p: int(p.rsplit("-", 1)[1][:-3]))
+        if not paths:
+            return None
+        state = torch.load(paths[-1], map_location="cpu")
+        if labels is not None:
+            self._ensure_optimizers(labels, latents)
+        self.store.load(state["variables"])
+        self.global_step.value = state["global_step"]
+        if self._opt is not None and "optimizers" in state:
+            for s, o in state["optimizers"].items():
+                self._opt[s]["m"].copy_(o["m"])
+                self._opt[s]["v"].copy_(o["v"])
+                self._opt[s]["t"] = o["t"]
+        return paths[-1]
+
+    # ------------------------------------------------------------------ reference entry points
+    def train(self, model_dir, config=None, total_steps=1000000, save_checkpoint_steps=1000, save_summary_steps=100,
+              log_tensor_steps=100):
+        """models.py:110-194: alternate D and G updates until global_step reaches total_steps or the
+        input function is exhausted (StopIteration / IndexError play the role of OutOfRangeError)."""
+        rank0 = not (torch.distributed.is_available() and torch.distributed.is_initialized()) or \
+            torch.distributed.get_rank() == 0
+        restored = False
+        iteration = 0
+        t0 = time.time()
+        while int(self.global_step.value) < total_steps:
+            try:
+                waveforms, labels = self._next_real()
+                latents = self._next_latents()
+                if not restored:
+                    self.restore_latest(model_dir, labels, latents)
+                    restored = True
+                    if int(self.global_step.value) >= total_steps:
+                        break
+                self.discriminator_step(waveforms, labels, latents)
+                self.generator_step()
+            except (StopIteration, IndexError):
+                break
+            iteration += 1
+            step = int(self.global_step.value)
+            if rank0 and log_tensor_steps and iteration % log_tensor_steps == 0:
+                print("INFO:gansynth_b200:global_step = %d, generator_loss = %.6f, discriminator_loss = %.6f (%.3f sec)"
+                      % (step, float(self.generator_loss), float(self.discriminator_loss), time.time() - t0), flush=True)
+                t0 = time.time()
+            if rank0 and save_checkpoint_steps and step % save_checkpoint_steps == 0:
+                self.save_checkpoint(model_dir)
+        if rank0:
+            self.save_checkpoint(model_dir)
+
+    def evaluate(self, model_dir, config, classifier, input_name, output_names):
+        """models.py:196-230 needs the frozen pitch-classifier graph the reference never ships; the
+        classifier network is outside this hot path."""
+        raise NotImplementedError("evaluate() needs the ResNet pitch classifier, which is outside the hot path")
+
+    def generate(self, model_dir, config=None):
+        """models.py:232-250: yields float32 numpy [B, waveform_length] until the input function ends."""
+        restored = False
+        while True:
+            try:
+                _, labels = self._next_real()
+            except (StopIteration, IndexError):
+                break
+            latents = self._next_latents()
+            if not restored:
+                pg = getattr(self.generator, "__self__", None)
+                if pg is not None and hasattr(pg, "_ensure_variables"):
+                    pg._ensure_variables("generator", latents.shape[1], labels.shape[1])
+                    pg._ensure_variables("discriminator", 0, labels.shape[1])
+                self.restore_latest(model_dir)
+                restored = True
+            yield self.generate_batch(labels, latents).cpu().numpy()
+
+    @torch.no_grad()
+    def generate_batch(self, labels, latents):
+        """z + pitch -> images -> waveforms (models.py:25, 30-31)."""
+        fake_images = self.generator(latents, labels)
+        self.fake_images = fake_images
+        mag, inst = fake_images[:, 0].contiguous(), fake_images[:, 1].contiguous()
+        self.fake_waveforms = spectral_ops.convert_to_waveform(mag, inst, **self.spectral_params)
+        return self.fake_waveforms

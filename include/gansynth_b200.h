@@ -1,0 +1,118 @@
+/* gansynth_b200 -- C ABI of the B200-native GANSynth hot path (libgansynth_b200.so, sm_100a).
+ *
+ * The reference (skmhrk1209/GANSynth @ d135d40) has no FFI: its hot path is TensorFlow-1.13 library
+ * calls made from ops.py / spectral_ops.py / models.py.  Each entry point below replaces one of those
+ * call sites (file:line given per function) and is what a host binding (ctypes here, see
+ * gansynth_b200/_lib.py and INTEGRATION.md) binds.
+ *
+ * Conventions
+ *  - every pointer is a caller-owned DEVICE pointer to contiguous fp32 (int32 / int64 where stated);
+ *    the library never frees or retains them past the call;
+ *  - activations are NHWC ([n, h, w, c], c fastest); conv weights keep the TF variable layout
+ *    [kh, kw, cin, cout] (`wswap`=1: the tensor in memory is [kh, kw, cout, cin]);
+ *  - `alpha` is the run-time equalised-learning-rate constant of get_weight (ops.py:154-160), applied
+ *    to the contraction result (before bias);
+ *  - `act`: 0 none, 1 leaky-relu(0.2) applied after the bias;
+ *  - `impl`: 0 auto, 1 naive anchor kernel, 2 tiled fp32 kernel (error if the shape is unsupported);
+ *  - `stream` is a cudaStream_t; every call is asynchronous on it, no hidden synchronisation (the
+ *    spectral entry points synchronise once, on first use, to upload twiddle tables);
+ *  - return 0 on success, negative on error; gs_last_error() gives the message (thread-local).
+ */
+#ifndef GANSYNTH_B200_H_
+#define GANSYNTH_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* gs_last_error(void);
+int gs_version(void);
+
+/* ---- convolution family: tf.nn.conv2d ops.py:237-243 (+ bias_add :245-246) and its gradients ------
+ * SAME padding as TF computes it for even sizes: 3x3 stride 1 pads (1,1); stride 2 pads (0,1).
+ * fwd  : y[n,h/s,w/s,co]  = act(alpha * sum x[n, oh*s+kh-pb, ow*s+kw-pb, ci] * W(kh,kw,ci,co) + bias[co])
+ * dgrad: dx[n,h,w,ci]     = act(alpha * sum dy[n,oh,ow,co] * W(kh,kw,ci,co) + bias[ci])   (oh*s+kh-pb = ih)
+ * wgrad: dw(kh,kw,ci,co)  = alpha * sum x[n, oh*s+kh-pb, ow*s+kw-pb, ci] * dy[n,oh,ow,co]
+ * h, w are always the spatial size of the LARGE side (x of fwd / dx of dgrad). bias may be NULL. */
+int gs_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, int n, int h, int wd, int ci, int co,
+                  int ksize, int stride, int wswap, float alpha, int act, int impl, void* stream);
+int gs_conv2d_dgrad(const float* dy, const float* w, const float* bias, float* dx, int n, int h, int wd, int ci,
+                    int co, int ksize, int stride, int wswap, float alpha, int act, int impl, void* stream);
+int gs_conv2d_wgrad(const float* x, const float* dy, float* dw, int n, int h, int wd, int ci, int co, int ksize,
+                    int stride, int wswap, float alpha, int impl, void* stream);
+
+/* ---- tf.nn.conv2d_transpose ops.py:266-276: x [n,h,w,cin], var [k,k,cin,filters] -> y [n,h*s,w*s,filters] */
+int gs_conv2d_transpose_fwd(const float* x, const float* var, const float* bias, float* y, int n, int h, int wd,
+                            int cin, int filters, int ksize, int stride, float alpha, int act, int impl, void* stream);
+int gs_conv2d_transpose_dgrad(const float* dy, const float* var, float* dx, int n, int h, int wd, int cin, int filters,
+                              int ksize, int stride, float alpha, int impl, void* stream);
+int gs_conv2d_transpose_wgrad(const float* x, const float* dy, float* dvar, int n, int h, int wd, int cin, int filters,
+                              int ksize, int stride, float alpha, int impl, void* stream);
+
+/* ---- dense: tf.matmul ops.py:197 and its gradients; w is [k, n] ---------------------------------- */
+int gs_dense_fwd(const float* x, const float* w, float* y, int m, int k, int n, float alpha, void* stream);
+int gs_dense_dgrad(const float* dy, const float* w, float* dx, int m, int k, int n, float alpha, void* stream);
+int gs_dense_wgrad(const float* x, const float* dy, float* dw, int m, int k, int n, float alpha, void* stream);
+
+/* ---- embedding: tf.nn.embedding_lookup ops.py:217; idx is int64 [b] (argmax of the one-hot labels) - */
+int gs_embedding_fwd(const float* table, const long long* idx, float* out, int b, int units, float alpha, void* stream);
+int gs_embedding_bwd(const float* dy, const long long* idx, float* dtable, int b, int rows, int units, float alpha,
+                     void* stream);
+
+/* ---- activations (networks.py: tf.nn.leaky_relu, tf.nn.tanh) and their derivative forms ---------- */
+int gs_lrelu(const float* x, float* out, long long n, void* stream);
+int gs_lrelu_mask_mul(const float* v, const float* y, float* out, long long n, void* stream); /* v * (y>0 ? 1 : 0.2) */
+int gs_tanh_fwd(const float* x, float* out, long long n, void* stream);
+int gs_tanh_bwd(const float* y, const float* dy, float* out, long long n, void* stream);        /* dy (1 - y^2) */
+int gs_tanh_bwd2(const float* y, const float* dy, const float* u, float* out, long long n, void* stream); /* -2 y dy u */
+int gs_bias_act(const float* x, const float* bias, float* out, long long rows, int c, int act, void* stream);
+int gs_row_broadcast(const float* s, float* out, long long rows, int c, void* stream);
+int gs_col_sum(const float* v, float* out, long long rows, int c, void* stream);                /* bias gradient */
+
+/* ---- lerp networks.py:10-11 and generic linear combinations ------------------------------------- */
+int gs_axpby(const float* a, const float* b, float* out, float alpha, float beta, long long n, void* stream);
+int gs_mul(const float* a, const float* b, float* out, float alpha, long long n, void* stream);
+
+/* ---- pixel_normalization ops.py:330-333 over the channel axis of [rows, c] ----------------------- */
+int gs_pixel_norm_fwd(const float* a, float* y, float* r, long long rows, int c, float eps, void* stream);
+int gs_pixel_norm_bwd(const float* a, const float* r, const float* dy, float* da, long long rows, int c, void* stream);
+int gs_pixel_norm_bwd2(const float* a, const float* r, const float* dy, const float* u, float* ga, long long rows,
+                       int c, void* stream);
+
+/* ---- batch_stddev ops.py:336-348 on [b, e]; stat is [b/groups] ---------------------------------- */
+int gs_batch_stddev_fwd(const float* x, float* stat, int b, long long e, int groups, float eps, void* stream);
+int gs_batch_stddev_bwd(const float* x, const float* df, float* dx, int b, long long e, int groups, float eps,
+                        void* stream);
+int gs_batch_stddev_bwd2(const float* x, const float* df, const float* u, float* gx, float* q, int b, long long e,
+                         int groups, float eps, void* stream);
+
+/* ---- upscale2d ops.py:283-291 / downscale2d ops.py:294-305 (NHWC), layout permutation ------------ */
+int gs_upscale2d(const float* in, float* out, int n, int h, int w, int c, int fh, int fw, float scale, void* stream);
+int gs_pool2d(const float* in, float* out, int n, int h, int w, int c, int fh, int fw, float scale, void* stream);
+int gs_transpose_inner(const float* in, float* out, int n, int a, int b, void* stream); /* [n,a,b] -> [n,b,a] */
+
+/* ---- per-sample reductions of the penalties models.py:48,61 on [rows, e] ------------------------- */
+int gs_row_dot(const float* a, const float* b, float* out, int rows, long long e, void* stream);
+int gs_row_scale(const float* a, const float* s, float* out, int rows, long long e, float alpha, void* stream);
+
+/* ---- tf.train.AdamOptimizer models.py:67-76 (epsilon outside the bias correction), t = 1-based step */
+int gs_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                 float eps, long long t, float grad_scale, void* stream);
+
+/* ---- spectral front-end, reference configuration frame 2048 / hop 512 / 1024 bins ---------------
+ * gs_spectrogram_fwd: spectral_ops.py:45-94.  wave [batch, wave_len] -> logmel, inst [batch, T, 1024].
+ *   hann [2048]; mel_k0 int32 [1024] and mel_w [6][1024]: column-sparse linear->mel matrix (first
+ *   non-zero row and up to 6 weights per mel bin).  frames_per_chunk divides T.
+ * gs_waveform_fwd: spectral_ops.py:97-149.  logmel, inst -> wave [batch, wave_len].
+ *   synth_window [2048] (hann / overlap-added hann^2); pb_j0/pb_cnt int32 [1024], pb_w [band][1024]:
+ *   banded pseudo-inverse (first mel row, row count and zero-padded weights per linear bin). */
+int gs_spectrogram_fwd(const float* wave, const float* hann, const int* mel_k0, const float* mel_w, float* logmel,
+                       float* inst, int batch, int wave_len, int time_steps, int frames_per_chunk, void* stream);
+int gs_waveform_fwd(const float* logmel, const float* inst, const float* synth_window, const int* pb_j0,
+                    const int* pb_cnt, const float* pb_w, int band, float* wave, int batch, int wave_len,
+                    int time_steps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GANSYNTH_B200_H_ */

@@ -1,0 +1,215 @@
+"""TEST INFRASTRUCTURE: a torch-CPU emulation of gansynth_b200.kernels.CudaBackend's primitive API.
+
+It lets the CPU test-suite check the host-side logic of the product (autograd Function composition in
+functional.py, network wiring, loss, optimiser bookkeeping, sparse spectral constants) against the
+oracle without a GPU.  It is never imported by the product; the product has no CPU path.
+Each method restates the contract of the C-ABI entry point of the same name (include/gansynth_b200.h).
+"""
+import math
+
+import torch
+import torch.nn.functional as TF
+
+
+def _nchw(x):
+    return x.permute(0, 3, 1, 2)
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def _act(y, act):
+    return TF.leaky_relu(y, 0.2) if act == 1 else y
+
+
+class EmuBackend(object):
+
+    def _w(self, w, wswap):
+        return w.permute(0, 1, 3, 2) if wswap else w   # -> [k, k, ci, co]
+
+    def conv_c(self, x, w, bias, ksize, stride, wswap, alpha, act):
+        wt = self._w(w, wswap).permute(3, 2, 0, 1)
+        pb = 1 if (ksize == 3 and stride == 1) else 0
+        pa = (ksize - stride) - pb if ksize == 3 else 0
+        xp = TF.pad(_nchw(x), (pb, pa, pb, pa))
+        y = TF.conv2d(xp, wt, stride=stride) * alpha
+        if bias is not None:
+            y = y + bias.view(1, -1, 1, 1)
+        return _nhwc(_act(y, act))
+
+    def conv_t(self, dy, w, bias, ksize, stride, wswap, alpha, act):
+        wt = self._w(w, wswap).permute(3, 2, 0, 1)      # [co, ci, k, k]
+        pb = 1 if (ksize == 3 and stride == 1) else 0
+        n, oh, ow, co = dy.shape
+        full = TF.conv_transpose2d(_nchw(dy), wt, stride=stride)
+        h, wd = oh * stride, ow * stride
+        full = TF.pad(full, (0, max(0, pb + wd - full.shape[3]), 0, max(0, pb + h - full.shape[2])))
+        dx = full[:, :, pb:pb + h, pb:pb + wd] * alpha
+        if bias is not None:
+            dx = dx + bias.view(1, -1, 1, 1)
+        return _nhwc(_act(dx, act))
+
+    def conv_w(self, x, dy, ksize, stride, wswap, alpha):
+        pb = 1 if (ksize == 3 and stride == 1) else 0
+        pa = (ksize - stride) - pb if ksize == 3 else 0
+        xp = TF.pad(_nchw(x), (pb, pa, pb, pa))
+        ci, co = x.shape[3], dy.shape[3]
+        dw = torch.nn.grad.conv2d_weight(xp, (co, ci, ksize, ksize), _nchw(dy).contiguous(), stride=stride)
+        dw = dw.permute(2, 3, 1, 0) * alpha             # [k, k, ci, co]
+        return (dw.permute(0, 1, 3, 2) if wswap else dw).contiguous()
+
+    def dense_fwd(self, x, w, alpha):
+        return (x @ w) * alpha
+
+    def dense_dgrad(self, dy, w, alpha):
+        return (dy @ w.t()) * alpha
+
+    def dense_wgrad(self, x, dy, alpha):
+        return (x.t() @ dy) * alpha
+
+    def embedding_fwd(self, table, idx, alpha):
+        return table[idx] * alpha
+
+    def embedding_bwd(self, dy, idx, rows, alpha):
+        out = torch.zeros(rows, dy.shape[1], dtype=dy.dtype)
+        return out.index_add_(0, idx, dy * alpha)
+
+    def lrelu(self, x):
+        return TF.leaky_relu(x, 0.2)
+
+    def mask_mul(self, v, y):
+        return v * torch.where(y > 0, torch.ones_like(y), torch.full_like(y, 0.2))
+
+    def tanh_fwd(self, x):
+        return torch.tanh(x)
+
+    def tanh_bwd(self, y, dy):
+        return dy * (1 - y * y)
+
+    def tanh_bwd2(self, y, dy, u):
+        return -2 * y * dy * u
+
+    def axpby(self, a, b, alpha, beta):
+        return alpha * a if b is None else alpha * a + beta * b
+
+    def bias_act(self, x, bias, act):
+        return _act(x if bias is None else x + bias, act)
+
+    def row_broadcast(self, s, lead_shape):
+        return s.expand(*lead_shape, s.numel()).contiguous()
+
+    def col_sum(self, v):
+        return v.reshape(-1, v.shape[-1]).sum(0)
+
+    def pn_fwd(self, a, eps):
+        r = 1.0 / torch.sqrt((a * a).mean(-1) + eps)
+        return a * r.unsqueeze(-1), r
+
+    def pn_bwd(self, a, r, dy):
+        c = a.shape[-1]
+        dot = (a * dy).sum(-1, keepdim=True)
+        r = r.unsqueeze(-1)
+        return r * dy - (r ** 3 / c) * dot * a
+
+    def pn_bwd2(self, a, r, dy, u):
+        c = a.shape[-1]
+        r = r.unsqueeze(-1)
+        ud = (u * dy).sum(-1, keepdim=True)
+        ad = (a * dy).sum(-1, keepdim=True)
+        ua = (u * a).sum(-1, keepdim=True)
+        return -(r ** 3 / c) * (ud * a + ad * u + ua * dy) + 3 * (r ** 5 / c ** 2) * ua * ad * a
+
+    def _sd(self, x, groups, eps):
+        b, e = x.shape
+        g = x.reshape(groups, b // groups, e)
+        mu = g.mean(0, keepdim=True)
+        s = torch.sqrt(((g - mu) ** 2).mean(0) + eps)
+        return g, mu, s
+
+    def stddev_fwd(self, x, groups, eps):
+        _, _, s = self._sd(x, groups, eps)
+        return s.mean(1)
+
+    def stddev_bwd(self, x, df, groups, eps):
+        g, mu, s = self._sd(x, groups, eps)
+        e = x.shape[1]
+        return (df.view(1, -1, 1) * (g - mu) / (e * groups * s)).reshape(x.shape)
+
+    def stddev_bwd2(self, x, df, u, groups, eps):
+        g, mu, s = self._sd(x, groups, eps)
+        e = x.shape[1]
+        ug = u.reshape(g.shape)
+        ubar = ug.mean(0, keepdim=True)
+        ux = (ug * (g - mu)).sum(0)
+        cm = df.view(1, -1, 1) / (e * groups)
+        gx = cm * ((ug - ubar) / s - (ux / (groups * s ** 3)) * (g - mu))
+        q = (ux / s).sum(1) / (e * groups)
+        return gx.reshape(x.shape), q
+
+    def upscale(self, x, fh, fw, scale):
+        return (x.repeat_interleave(fh, 1).repeat_interleave(fw, 2) * scale).contiguous()
+
+    def pool(self, x, fh, fw, scale):
+        n, hh, ww, c = x.shape
+        return x.reshape(n, hh // fh, fh, ww // fw, fw, c).sum((2, 4)) * scale
+
+    def transpose_inner(self, x):
+        return x.transpose(1, 2).contiguous()
+
+    def row_dot(self, a, b):
+        return (a * b).sum(1)
+
+    def row_scale(self, a, s, alpha=1.0):
+        return a * (alpha * s).unsqueeze(1)
+
+    def adam_step(self, p, g, m, v, lr, beta1, beta2, eps, t, grad_scale=1.0):
+        lr_t = lr * math.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
+        with torch.no_grad():
+            gi = g * grad_scale
+            m.mul_(beta1).add_(gi, alpha=1.0 - beta1)
+            v.mul_(beta2).add_(gi * gi, alpha=1.0 - beta2)
+            p.sub_(lr_t * m / (torch.sqrt(v) + eps))
+
+    # spectral: same sparse constants as the kernels, dense torch arithmetic
+    def spectrogram_fwd(self, wave, consts, time_steps, frames_per_chunk):
+        b, wave_len = wave.shape
+        nsamp = 512 * (time_steps - 1) + 2048
+        x = TF.pad(wave, (nsamp - wave_len, 0))
+        frames = x.unfold(-1, 2048, 512) * consts["hann"]
+        s = torch.fft.rfft(frames, n=2048)[..., 1:]
+        mag, ph = torch.abs(s), torch.atan2(s.imag + 0.0, s.real + 0.0)
+        k0, w = consts["mel_k0"].long(), consts["mel_w"]
+        mm = torch.zeros(b, time_steps, 1024)
+        pp = torch.zeros(b, time_steps, 1024)
+        for i in range(w.shape[0]):
+            idx = (k0 + i).clamp(max=1023)
+            mm = mm + mag[..., idx] * w[i]
+            pp = pp + ph[..., idx] * w[i]
+        logmel = (torch.log(mm + 1e-6) + 3.76) / 10.05
+        pi = torch.tensor(math.pi, dtype=torch.float32)
+        d = pp[:, 1:] - pp[:, :-1]
+        md = torch.remainder(d + pi, 2 * pi) - pi
+        md = torch.where((md == -pi) & (d > 0), pi.expand_as(md), md)
+        inst = torch.cat([pp[:, :1], md], 1) / pi
+        return logmel, inst
+
+    def waveform_fwd(self, logmel, inst, consts, wave_len):
+        b, t, _ = logmel.shape
+        mm = torch.exp(logmel * 10.05 - 3.76)
+        pp = torch.cumsum(inst * torch.tensor(math.pi, dtype=torch.float32), 1)
+        j0, cnt, w = consts["pb_j0"].long(), consts["pb_cnt"], consts["pb_w"]
+        mag = torch.zeros(b, t, 1024)
+        ph = torch.zeros(b, t, 1024)
+        for i in range(w.shape[0]):
+            idx = (j0 + i).clamp(max=1023)
+            mag = mag + mm[..., idx] * w[i]
+            ph = ph + pp[..., idx] * w[i]
+        s = torch.complex(mag * torch.cos(ph), mag * torch.sin(ph))
+        s = TF.pad(s, (1, 0))
+        frames = torch.fft.irfft(s, n=2048) * consts["synth_window"]
+        nsamp = 512 * (t - 1) + 2048
+        out = torch.zeros(b, nsamp)
+        for k in range(t):
+            out[:, 512 * k:512 * k + 2048] += frames[:, k]
+        return out[:, nsamp - wave_len:]
