@@ -29,7 +29,11 @@ def _chk(*tensors):
             raise _lib.GansynthLibraryError("gansynth_b200 kernels need CUDA tensors (got %s); no CPU fallback" % t.device)
         if t.dtype != torch.float32:
             raise TypeError("expected float32, got %s" % t.dtype)
-        out.append(t if t.is_contiguous() else t.contiguous())
+        if not t.is_contiguous():
+            t = t.contiguous()
+        if t.data_ptr() % 16:
+            t = t.clone()   # the float4 paths of the kernels need 16-byte aligned base pointers
+        out.append(t)
     return out
 
 

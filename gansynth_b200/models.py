@@ -180,17 +180,15 @@ class GANSynth(object):
         """minimize(loss, var_list=scope variables) (models.py:81-89) with TF-Adam semantics."""
         hp = self.hyper_params
         st = self._opt[scope]
-        variables = list(self.store.trainable_variables(scope).values())
-        grads = torch.autograd.grad(loss, variables, allow_unused=True)
-        off = 0
+        names = list(self.store.trainable_variables(scope).keys())
+        grads = torch.autograd.grad(loss, [self.store.vars[n] for n in names], allow_unused=True)
         gflat = st["grad"]
-        for v, g in zip(variables, grads):
-            k = v.numel()
+        views = self.store.unflatten(scope, gflat)
+        for n, g in zip(names, grads):
             if g is None:
-                gflat[off:off + k].zero_()
+                views[n].zero_()
             else:
-                gflat[off:off + k].copy_(g.reshape(-1))
-            off += k
+                views[n].copy_(g)
         scale = 1.0
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             world = torch.distributed.get_world_size(self.process_group)

@@ -33,6 +33,7 @@ class VariableStore(object):
         self._scope = []
         self._rng = torch.Generator().manual_seed(seed)
         self.flat = {}                # prefix -> flat parameter buffer (after pack())
+        self.offsets = {}             # prefix -> name -> (offset, numel) inside the flat buffer
 
     @contextlib.contextmanager
     def variable_scope(self, name):
@@ -69,17 +70,24 @@ class VariableStore(object):
         if scope in self.flat:
             return self.flat[scope]
         items = self.trainable_variables(scope)
-        total = sum(v.numel() for v in items.values())
-        flat = torch.empty(total, device=self.device, dtype=torch.float32)
-        off = 0
+        align = 32   # floats: every variable starts on a 128-byte boundary (float4 / TMA friendly)
+        offsets, off = OrderedDict(), 0
         for n, v in items.items():
-            k = v.numel()
-            view = flat[off:off + k].view(v.shape)
+            offsets[n] = (off, v.numel())
+            off += -(-v.numel() // align) * align
+        flat = torch.zeros(off, device=self.device, dtype=torch.float32)
+        for n, v in items.items():
+            o, k = offsets[n]
+            view = flat[o:o + k].view(v.shape)
             view.copy_(v.detach())
             self.vars[n] = view.requires_grad_(True)
-            off += k
         self.flat[scope] = flat
+        self.offsets[scope] = offsets
         return flat
+
+    def unflatten(self, scope, flat):
+        """name -> view of `flat` (a tensor laid out like the packed parameter buffer of `scope`)."""
+        return OrderedDict((n, flat[o:o + k].view(self.vars[n].shape)) for n, (o, k) in self.offsets[scope].items())
 
     def load(self, values):
         """Injects values (numpy or torch, TF layouts) by variable name."""

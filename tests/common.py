@@ -22,3 +22,13 @@ def seeded_inputs(batch, res, seed=0, latent_dim=256, num_labels=61):
 def rel_err(a, b):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def grad_close(got, want, tol):
+    """max |got - want| <= tol * max |want| per variable; an all-zero reference (inactive colour block)
+    requires an all-zero result."""
+    got, want = got.detach().double().cpu(), want.detach().double().cpu()
+    scale = float(want.abs().max())
+    if scale == 0.0:
+        return float(got.abs().max()) == 0.0
+    return float((got - want).abs().max()) <= tol * scale
