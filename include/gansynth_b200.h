@@ -112,6 +112,11 @@ int gs_waveform_fwd(const float* logmel, const float* inst, const float* synth_w
                     const int* pb_cnt, const float* pb_w, int band, float* wave, int batch, int wave_len,
                     int time_steps, void* stream);
 
+/* ---- tcgen05 self-test: one 128 x n bf16 UMMA accumulation from operands staged in the SWIZZLE_NONE
+ * core-matrix layout of the tensor-core convolution (see csrc/tc_probe.cu) ------------------------- */
+int gs_tc_probe(const float* a, const float* b, float* d, int k, int n, int rows_a, int rows_b, int shift, int gstride,
+                int mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
