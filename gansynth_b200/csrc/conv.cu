@@ -1,6 +1,9 @@
 // C-ABI entry points for the NHWC convolution family (see include/gansynth_b200.h).
 // Replaces the tf.nn.conv2d / tf.nn.conv2d_transpose call sites of the reference
 // (ops.py:237, ops.py:269) and their TF-generated gradients (models.py:47,60,81-89).
+#include <stdlib.h>
+
+#include "conv_tc.cuh"
 #include "conv_tiled.cuh"
 #include "gansynth_b200.h"
 
@@ -88,6 +91,80 @@ int launch_w(const float* big, const float* small, float* dw, int n, int h, int 
   return GS_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// tcgen05 path
+struct TcWorkspace {
+  __nv_bfloat16* buf = nullptr;
+  size_t bytes = 0;
+};
+TcWorkspace g_tc_ws;   // grow-only; calls are stream-ordered on one stream per process (see gansynth_b200.h)
+
+int tc_auto_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GS_CONV_TC");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v;
+}
+
+// shape gate of the tensor-core kernels: 3x3, contraction channels % 32, output channels % 32 and <= 256
+// (<= 128 for the four-accumulator transposed form), tile-aligned spatial size on the tiled side
+bool tc_ok(int form, int ksize, int kdim, int ndim, int th_dim, int tw_dim) {
+  if (ksize != 3 || kdim % 32 || ndim % 32 || ndim > 256) return false;
+  if (form == TC_T2 && ndim > 128) return false;
+  return th_dim % 16 == 0 && tw_dim % 8 == 0;
+}
+
+template <int FORM>
+int launch_tc(const float* x, const float* w, const float* bias, float* y, int n, int h_in, int w_in, int h_out,
+              int w_out, int kdim, int ndim, int w_is_kn, int flip, float alpha, int act, cudaStream_t st) {
+  using G = TcGeo<FORM>;
+  const size_t wbytes = (size_t)9 * kdim * ndim * 2 * sizeof(__nv_bfloat16);
+  if (g_tc_ws.bytes < wbytes) {
+    GS_CUDA(cudaStreamSynchronize(st));
+    if (g_tc_ws.buf) GS_CUDA(cudaFree(g_tc_ws.buf));
+    size_t want = wbytes < ((size_t)4 << 20) ? ((size_t)4 << 20) : wbytes;
+    GS_CUDA(cudaMalloc(&g_tc_ws.buf, want));
+    g_tc_ws.bytes = want;
+  }
+  {
+    size_t total = (size_t)9 * kdim * ndim;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > gs_num_sms() * 8) blocks = gs_num_sms() * 8;
+    conv_tc_prep_kernel<<<blocks, 256, 0, st>>>(w, g_tc_ws.buf, kdim, ndim, w_is_kn, flip);
+    GS_CHECK_LAUNCH("conv_tc_prep");
+  }
+  TcParams p;
+  p.x = x; p.wprep = g_tc_ws.buf; p.bias = bias; p.y = y;
+  p.n_img = n; p.h_in = h_in; p.w_in = w_in; p.h_out = h_out; p.w_out = w_out; p.kdim = kdim; p.ndim = ndim;
+  p.alpha = alpha; p.act = act;
+  const int th_dim = (FORM == TC_T2) ? h_in : h_out, tw_dim = (FORM == TC_T2) ? w_in : w_out;
+  p.tiles_h = th_dim / 16; p.tiles_w = tw_dim / 8; p.ntiles = n * p.tiles_h * p.tiles_w;
+  const size_t a_stage = (size_t)8 * G::P * 16, b_stage = (size_t)128 * ndim;
+  const size_t budget = 222 * 1024;
+  p.sa = (FORM == TC_C2) ? 2 : 3;
+  size_t left = budget - p.sa * a_stage;
+  p.sb = (int)(left / b_stage);
+  if (p.sb > TC_MAX_STAGES) p.sb = TC_MAX_STAGES;
+  GS_CHECK_ARG(p.sb >= 2, "conv_tc: not enough shared memory for two weight stages (ndim %d)", ndim);
+  p.nbuf = (2 * G::NACC * ndim <= 512) ? 2 : 1;
+  int cols = 32;
+  while (cols < p.nbuf * G::NACC * ndim) cols <<= 1;
+  p.tmem_cols = cols;
+  const size_t smem = p.sa * a_stage + p.sb * b_stage;
+  auto kern = conv_tc_kernel<FORM>;
+  static bool attr = false;
+  if (!attr) {
+    GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    attr = true;
+  }
+  int grid = p.ntiles < gs_num_sms() ? p.ntiles : gs_num_sms();
+  kern<<<grid, TC_THREADS, smem, st>>>(p);
+  GS_CHECK_LAUNCH("conv_tc");
+  return GS_OK;
+}
+
 }  // namespace
 
 extern "C" int gs_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, int n, int h, int wd,
@@ -99,6 +176,15 @@ extern "C" int gs_conv2d_fwd(const float* x, const float* w, const float* bias, 
   cudaStream_t st = (cudaStream_t)stream;
   bool tiled = tiled_ok(g);
   GS_CHECK_ARG(!(impl == 2 && !tiled), "conv2d_fwd: tiled kernel needs ksize 3 and channels %% 4 == 0");
+  {
+    const int form = stride == 1 ? TC_C1 : TC_C2;
+    const bool tcok = tc_ok(form, ksize, ci, co, g.oh, g.ow);
+    GS_CHECK_ARG(!(impl == 3 && !tcok), "conv2d_fwd: tensor-core kernel does not cover this shape");
+    if (impl == 3 || (impl == 0 && tcok && tc_auto_enabled())) {
+      if (stride == 1) return launch_tc<TC_C1>(x, w, bias, y, n, h, wd, g.oh, g.ow, ci, co, !g.wswap, 0, alpha, act, st);
+      return launch_tc<TC_C2>(x, w, bias, y, n, h, wd, g.oh, g.ow, ci, co, !g.wswap, 0, alpha, act, st);
+    }
+  }
   if (impl == 1 || !tiled) {
     size_t total = (size_t)n * g.oh * g.ow * co;
     conv_c_naive_kernel<<<grid_1d(total, 256), 256, 0, st>>>(x, w, bias, y, g);
@@ -123,6 +209,16 @@ extern "C" int gs_conv2d_dgrad(const float* dy, const float* w, const float* bia
   cudaStream_t st = (cudaStream_t)stream;
   bool tiled = tiled_ok(g);
   GS_CHECK_ARG(!(impl == 2 && !tiled), "conv2d_dgrad: tiled kernel needs ksize 3 and channels %% 4 == 0");
+  {
+    // contraction over co, output channels ci
+    const int form = stride == 1 ? TC_C1 : TC_T2;
+    const bool tcok = stride == 1 ? tc_ok(form, ksize, co, ci, h, wd) : tc_ok(form, ksize, co, ci, g.oh, g.ow);
+    GS_CHECK_ARG(!(impl == 3 && !tcok), "conv2d_dgrad: tensor-core kernel does not cover this shape");
+    if (impl == 3 || (impl == 0 && tcok && tc_auto_enabled())) {
+      if (stride == 1) return launch_tc<TC_C1>(dy, w, bias, dx, n, h, wd, h, wd, co, ci, g.wswap, 1, alpha, act, st);
+      return launch_tc<TC_T2>(dy, w, bias, dx, n, g.oh, g.ow, h, wd, co, ci, g.wswap, 0, alpha, act, st);
+    }
+  }
   if (impl == 1 || !tiled) {
     size_t total = (size_t)n * h * wd * ci;
     conv_t_naive_kernel<<<grid_1d(total, 256), 256, 0, st>>>(dy, w, bias, dx, g);
@@ -148,6 +244,7 @@ extern "C" int gs_conv2d_wgrad(const float* x, const float* dy, float* dw, int n
   cudaStream_t st = (cudaStream_t)stream;
   bool tiled = tiled_ok(g);
   GS_CHECK_ARG(!(impl == 2 && !tiled), "conv2d_wgrad: tiled kernel needs ksize 3 and channels %% 4 == 0");
+  if (impl == 3) impl = 0;   // no tensor-core filter-gradient kernel yet: the tiled fp32 kernel serves impl 3
   size_t nel = (size_t)ksize * ksize * ci * co;
   GS_CUDA(cudaMemsetAsync(dw, 0, nel * sizeof(float), st));
   if (impl == 1 || !tiled) {

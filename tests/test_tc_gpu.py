@@ -44,3 +44,92 @@ def test_probe_mn_major(k, n, shift, gstride):
     pix = torch.tensor([(j // 8) * gstride + j % 8 + shift for j in range(k)])
     want = _bf16(a)[pix].t() @ _bf16(b)[pix]
     assert float((got - want).abs().max()) < 1e-3 * float(want.abs().max())
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core convolution forms (impl = 3) against the torch-CPU contract; bf16x3 products carry ~16
+# mantissa bits, so the bound is 1e-4 of the largest output (measured ~1e-5).
+from common import rel_err  # noqa: E402
+from emu_backend import EmuBackend  # noqa: E402
+
+EMU = EmuBackend()
+
+
+def _rand(*shape, seed=0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+def _k3():
+    from gansynth_b200.kernels import CudaBackend
+    k = CudaBackend()
+    k.impl = 3
+    return k
+
+
+TC_FWD_CASES = [
+    # n, h, w, ci, co, stride   (h, w = large side)
+    (1, 16, 8, 32, 32, 1),
+    (2, 16, 16, 32, 32, 1),
+    (1, 32, 24, 64, 64, 1),
+    (3, 48, 40, 96, 160, 1),
+    (1, 16, 8, 256, 256, 1),
+    (1, 128, 64, 32, 32, 1),
+    (2, 32, 16, 32, 64, 2),
+    (1, 64, 32, 64, 128, 2),
+    (1, 32, 48, 128, 256, 2),
+]
+
+
+@pytest.mark.parametrize("case", TC_FWD_CASES)
+@pytest.mark.parametrize("wswap", [0, 1])
+def test_tc_gather_forms(case, wswap):
+    n, h, w, ci, co, st = case
+    k = _k3()
+    x = _rand(n, h, w, ci, seed=1)
+    wt = _rand(3, 3, co, ci, seed=3) if wswap else _rand(3, 3, ci, co, seed=3)
+    bias = _rand(co, seed=4)
+    for act, b in ((0, None), (1, bias)):
+        got = k.conv_c(x.cuda(), wt.cuda(), None if b is None else b.cuda(), 3, st, wswap, 0.37, act)
+        want = EMU.conv_c(x, wt, b, 3, st, wswap, 0.37, act)
+        assert got.shape == want.shape
+        assert rel_err(got, want) < 1e-4, (case, wswap, act, rel_err(got, want))
+
+
+TC_DGRAD_CASES = [
+    # n, h, w (large side), ci (output channels of dgrad), co (contraction), stride
+    (1, 16, 8, 32, 32, 1),
+    (2, 32, 16, 64, 32, 1),
+    (1, 16, 16, 256, 128, 1),
+    (1, 32, 16, 32, 32, 2),
+    (2, 64, 32, 32, 64, 2),
+    (1, 32, 48, 128, 256, 2),
+    (1, 64, 16, 64, 128, 2),
+]
+
+
+@pytest.mark.parametrize("case", TC_DGRAD_CASES)
+@pytest.mark.parametrize("wswap", [0, 1])
+def test_tc_transposed_forms(case, wswap):
+    n, h, w, ci, co, st = case
+    k = _k3()
+    dy = _rand(n, h // st, w // st, co, seed=2)
+    wt = _rand(3, 3, co, ci, seed=3) if wswap else _rand(3, 3, ci, co, seed=3)
+    bias = _rand(ci, seed=5)
+    for act, b in ((0, None), (1, bias)):
+        got = k.conv_t(dy.cuda(), wt.cuda(), None if b is None else b.cuda(), 3, st, wswap, 0.37, act)
+        want = EMU.conv_t(dy, wt, b, 3, st, wswap, 0.37, act)
+        assert got.shape == want.shape
+        assert rel_err(got, want) < 1e-4, (case, wswap, act, rel_err(got, want))
+
+
+def test_tc_full_size_layer_matches_fp32_tiled_kernel():
+    """The top generator layer (8 x 128 x 1024 x 32 -> 32): tensor-core vs fp32 FFMA kernel."""
+    from gansynth_b200.kernels import CudaBackend
+    x = _rand(8, 128, 1024, 32, seed=1).cuda()
+    wt = _rand(3, 3, 32, 32, seed=2).cuda()
+    b = _rand(32, seed=3).cuda()
+    k2, k3 = CudaBackend(), CudaBackend()
+    k2.impl, k3.impl = 2, 3
+    a = k2.conv_c(x, wt, b, 3, 1, 0, 0.0589, 1)
+    c = k3.conv_c(x, wt, b, 3, 1, 0, 0.0589, 1)
+    assert rel_err(c, a) < 1e-4
