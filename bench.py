@@ -148,10 +148,10 @@ class ConvProfiler(object):
         return self
 
     def _wrap(self, name, fn):
-        def wrapped(a, b, *rest):
+        def wrapped(a, b, *rest, **kw):
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            out = fn(a, b, *rest)
+            out = fn(a, b, *rest, **kw)
             e.record()
             if name == "conv_w":
                 ksize, stride = rest[0], rest[1]

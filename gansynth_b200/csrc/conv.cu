@@ -116,15 +116,15 @@ bool tc_ok(int form, int ksize, int kdim, int ndim, int th_dim, int tw_dim) {
   return th_dim % 16 == 0 && tw_dim % 8 == 0;
 }
 
-template <int FORM>
-int launch_tc(const float* x, const float* w, const float* bias, float* y, int n, int h_in, int w_in, int h_out,
-              int w_out, int kdim, int ndim, int w_is_kn, int flip, float alpha, int act, cudaStream_t st) {
+template <int FORM, int NSPLIT, int KC>
+int launch_tc_impl(const float* x, const float* w, const float* bias, float* y, int n, int h_in, int w_in, int h_out,
+                   int w_out, int kdim, int ndim, int w_is_kn, int flip, float alpha, int act, cudaStream_t st) {
   using G = TcGeo<FORM>;
-  const size_t wbytes = (size_t)9 * kdim * ndim * 2 * sizeof(__nv_bfloat16);
+  const size_t wbytes = (size_t)9 * kdim * ndim * NSPLIT * sizeof(__nv_bfloat16);
   if (g_tc_ws.bytes < wbytes) {
     GS_CUDA(cudaStreamSynchronize(st));
     if (g_tc_ws.buf) GS_CUDA(cudaFree(g_tc_ws.buf));
-    size_t want = wbytes < ((size_t)4 << 20) ? ((size_t)4 << 20) : wbytes;
+    size_t want = wbytes < ((size_t)8 << 20) ? ((size_t)8 << 20) : wbytes;
     GS_CUDA(cudaMalloc(&g_tc_ws.buf, want));
     g_tc_ws.bytes = want;
   }
@@ -132,7 +132,7 @@ int launch_tc(const float* x, const float* w, const float* bias, float* y, int n
     size_t total = (size_t)9 * kdim * ndim;
     int blocks = (int)((total + 255) / 256);
     if (blocks > gs_num_sms() * 8) blocks = gs_num_sms() * 8;
-    conv_tc_prep_kernel<<<blocks, 256, 0, st>>>(w, g_tc_ws.buf, kdim, ndim, w_is_kn, flip);
+    conv_tc_prep_kernel<NSPLIT, KC><<<blocks, 256, 0, st>>>(w, g_tc_ws.buf, kdim, ndim, w_is_kn, flip);
     GS_CHECK_LAUNCH("conv_tc_prep");
   }
   TcParams p;
@@ -141,19 +141,19 @@ int launch_tc(const float* x, const float* w, const float* bias, float* y, int n
   p.alpha = alpha; p.act = act;
   const int th_dim = (FORM == TC_T2) ? h_in : h_out, tw_dim = (FORM == TC_T2) ? w_in : w_out;
   p.tiles_h = th_dim / 16; p.tiles_w = tw_dim / 8; p.ntiles = n * p.tiles_h * p.tiles_w;
-  const size_t a_stage = (size_t)8 * G::P * 16, b_stage = (size_t)128 * ndim;
+  const size_t a_stage = (size_t)NSPLIT * (KC / 8) * G::P * 16, b_stage = (size_t)NSPLIT * (KC / 8) * ndim * 16;
   const size_t budget = 222 * 1024;
   p.sa = (FORM == TC_C2) ? 2 : 3;
+  GS_CHECK_ARG((size_t)p.sa * a_stage + 2 * b_stage <= budget, "conv_tc: shared memory budget exceeded (ndim %d)", ndim);
   size_t left = budget - p.sa * a_stage;
   p.sb = (int)(left / b_stage);
   if (p.sb > TC_MAX_STAGES) p.sb = TC_MAX_STAGES;
-  GS_CHECK_ARG(p.sb >= 2, "conv_tc: not enough shared memory for two weight stages (ndim %d)", ndim);
   p.nbuf = (2 * G::NACC * ndim <= 512) ? 2 : 1;
   int cols = 32;
   while (cols < p.nbuf * G::NACC * ndim) cols <<= 1;
   p.tmem_cols = cols;
   const size_t smem = p.sa * a_stage + p.sb * b_stage;
-  auto kern = conv_tc_kernel<FORM>;
+  auto kern = conv_tc_kernel<FORM, NSPLIT, KC>;
   static bool attr = false;
   if (!attr) {
     GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
@@ -163,6 +163,15 @@ int launch_tc(const float* x, const float* w, const float* bias, float* y, int n
   kern<<<grid, TC_THREADS, smem, st>>>(p);
   GS_CHECK_LAUNCH("conv_tc");
   return GS_OK;
+}
+
+// bf16x3 (two-term split).  A three-term split was measured and buys nothing: the tcgen05 fp32 accumulator
+// truncates (tools/tc_precision.py: mean relative error -9.5e-6 at K = 2304 whatever the split), so the
+// accumulation, not the operand split, bounds the accuracy at ~1e-5.
+template <int FORM>
+int launch_tc(const float* x, const float* w, const float* bias, float* y, int n, int h_in, int w_in, int h_out,
+              int w_out, int kdim, int ndim, int w_is_kn, int flip, float alpha, int act, cudaStream_t st) {
+  return launch_tc_impl<FORM, 2, 32>(x, w, bias, y, n, h_in, w_in, h_out, w_out, kdim, ndim, w_is_kn, flip, alpha, act, st);
 }
 
 }  // namespace
@@ -175,6 +184,7 @@ extern "C" int gs_conv2d_fwd(const float* x, const float* w, const float* bias, 
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   bool tiled = tiled_ok(g);
+  if (impl == 4) impl = tiled ? 2 : 1;   // "fp32 auto": never the tensor-core kernel
   GS_CHECK_ARG(!(impl == 2 && !tiled), "conv2d_fwd: tiled kernel needs ksize 3 and channels %% 4 == 0");
   {
     const int form = stride == 1 ? TC_C1 : TC_C2;
@@ -208,6 +218,7 @@ extern "C" int gs_conv2d_dgrad(const float* dy, const float* w, const float* bia
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   bool tiled = tiled_ok(g);
+  if (impl == 4) impl = tiled ? 2 : 1;
   GS_CHECK_ARG(!(impl == 2 && !tiled), "conv2d_dgrad: tiled kernel needs ksize 3 and channels %% 4 == 0");
   {
     // contraction over co, output channels ci
@@ -243,8 +254,9 @@ extern "C" int gs_conv2d_wgrad(const float* x, const float* dy, float* dw, int n
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   bool tiled = tiled_ok(g);
+  if (impl == 4) impl = tiled ? 2 : 1;
   GS_CHECK_ARG(!(impl == 2 && !tiled), "conv2d_wgrad: tiled kernel needs ksize 3 and channels %% 4 == 0");
-  if (impl == 3) impl = 0;   // no tensor-core filter-gradient kernel yet: the tiled fp32 kernel serves impl 3
+  if (impl == 3) impl = 0;   // no tensor-core filter-gradient kernel yet
   size_t nel = (size_t)ksize * ksize * ci * co;
   GS_CUDA(cudaMemsetAsync(dw, 0, nel * sizeof(float), st));
   if (impl == 1 || !tiled) {

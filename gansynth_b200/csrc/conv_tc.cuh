@@ -6,7 +6,9 @@
 // pixel-major ("SWIZZLE_NONE core matrices": plane q = channels 8q..8q+7, 16 bytes per pixel).  In that
 // layout every filter tap is just a different START ADDRESS / group stride of the same staged tile, so the
 // nine taps cost nine descriptor pairs, not nine loads.  Each 16-channel K slice issues three MMAs
-// (hi*hi + hi*lo + lo*hi): products carry ~16 mantissa bits, accumulation is fp32 in TMEM.
+// (hi*hi + hi*lo + lo*hi; NSPLIT = 2: products carry ~17 mantissa bits) or, for layer forwards whose sign
+// decides the leaky-relu mask, six MMAs of a 3-way split (h,m,l; NSPLIT = 3: ~25 bits, fp32-grade);
+// accumulation is fp32 in TMEM.
 // Weights are pre-split into the same layout by conv_tc_prep_kernel and streamed per tap with 1-D bulk
 // copies.  Warp roles: 0-3 epilogue (TMEM -> bias / leaky-relu -> HBM), 4-7 halo load + split, 8 weight
 // copies, 9 MMA issue + TMEM allocation.  Rings: A (per channel chunk), B (per tap), accumulators (per tile).
@@ -53,7 +55,7 @@ struct TcGeo<TC_T2> {
 
 struct TcParams {
   const float* x;                 // A-side activations [n, h_in, w_in, kdim]
-  const __nv_bfloat16* wprep;     // [kdim/32][9][2][4][ndim][8]
+  const __nv_bfloat16* wprep;     // [kdim/KC][9][NSPLIT][KC/8][ndim][8]
   const float* bias;              // [ndim] or null
   float* y;                       // [n, h_out, w_out, ndim]
   int n_img, h_in, w_in, h_out, w_out, kdim, ndim;
@@ -68,49 +70,63 @@ struct TcParams {
 constexpr int TC_THREADS = 320;
 constexpr int TC_MAX_STAGES = 4;
 
-// Weight pre-pass: W_eff[tap][k][n] (k = contraction channel, n = output channel) -> bf16 hi/lo blocks
-// [k/32][tap][hl][q][n][e], value index k = 32*kc + 8*q + e.  w_is_kn / flip as in gs_load_b_tile.
+// fp32 -> NSPLIT bf16 terms whose sum reproduces x to 2^-17 (2 terms) / 2^-25 (3 terms) relative
+template <int NSPLIT>
+__device__ __forceinline__ void tc_split(float x, __nv_bfloat16 (&t)[NSPLIT]) {
+  float r = x;
+#pragma unroll
+  for (int s = 0; s < NSPLIT; ++s) {
+    t[s] = __float2bfloat16_rn(r);
+    r -= __bfloat162float(t[s]);
+  }
+}
+
+// Weight pre-pass: W_eff[tap][k][n] (k = contraction channel, n = output channel) -> bf16 split blocks
+// [k/KC][tap][split][q][n][e], value index k = KC*kc + 8*q + e.  w_is_kn / flip as in gs_load_b_tile.
+template <int NSPLIT, int KC>
 __global__ void conv_tc_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int kdim, int ndim,
                                     int w_is_kn, int flip) {
+  constexpr int Q = KC / 8;
   const size_t total = (size_t)9 * kdim * ndim;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    // i enumerates the OUTPUT (hi plane) so writes are coalesced
     int e = (int)(i % 8);
     size_t r = i / 8;
     int n = (int)(r % ndim);
     r /= ndim;
-    int q = (int)(r % 4);
-    r /= 4;
+    int q = (int)(r % Q);
+    r /= Q;
     int tap = (int)(r % 9);
     int kc = (int)(r / 9);
-    int k = kc * 32 + q * 8 + e;
+    int k = kc * KC + q * 8 + e;
     int st = flip ? 8 - tap : tap;
     float v = w_is_kn ? w[((size_t)st * kdim + k) * ndim + n] : w[((size_t)st * ndim + n) * kdim + k];
-    __nv_bfloat16 hi, lo;
-    tc::split_bf16(v, hi, lo);
-    size_t blk = ((size_t)kc * 9 + tap) * 2;
+    __nv_bfloat16 t[NSPLIT];
+    tc_split<NSPLIT>(v, t);
+    size_t blk = ((size_t)kc * 9 + tap) * NSPLIT;
+    size_t plane = (size_t)Q * ndim * 8;
     size_t inner = ((size_t)q * ndim + n) * 8 + e;
-    out[(blk + 0) * 4 * ndim * 8 + inner] = hi;
-    out[(blk + 1) * 4 * ndim * 8 + inner] = lo;
+#pragma unroll
+    for (int sp = 0; sp < NSPLIT; ++sp) out[(blk + sp) * plane + inner] = t[sp];
   }
 }
 
-template <int FORM>
+template <int FORM, int NSPLIT, int KC>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p) {
   using G = TcGeo<FORM>;
+  constexpr int Q = KC / 8;               // 16-byte channel planes per split term
   extern __shared__ __align__(128) unsigned char tc_smem[];
   __shared__ uint64_t a_full[TC_MAX_STAGES], a_empty[TC_MAX_STAGES], b_full[TC_MAX_STAGES], b_empty[TC_MAX_STAGES];
   __shared__ uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t a_stage_bytes = 8u * G::P * 16u;          // 4 hi planes + 4 lo planes
   const uint32_t plane_a = G::P * 16u;
   const uint32_t plane_b = (uint32_t)p.ndim * 16u;
-  const uint32_t b_stage_bytes = 8u * plane_b;
+  const uint32_t a_stage_bytes = (uint32_t)(NSPLIT * Q) * plane_a;   // [split][q] planes
+  const uint32_t b_stage_bytes = (uint32_t)(NSPLIT * Q) * plane_b;
   unsigned char* a_smem = tc_smem;
   unsigned char* b_smem = tc_smem + (size_t)p.sa * a_stage_bytes;
-  const int nchunks = p.kdim / 32;
+  const int nchunks = p.kdim / KC;
 
   if (tid == 0) {
     for (int s = 0; s < p.sa; ++s) { tc::mbar_init(&a_full[s], 128); tc::mbar_init(&a_empty[s], 1); }
@@ -149,28 +165,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
           else if (FORM == TC_C2) { hr = ps / 17; int rem = ps % 17; int par = rem >= 9; hc = 2 * (rem - 9 * par) + par; }
           else { hr = ps / 9; hc = ps % 9; }
           const int ih = r0 + hr, iw = c0 + hc;
-          float4 v[8];
+          float4 v[2 * Q];
           if (ih >= 0 && ih < p.h_in && iw >= 0 && iw < p.w_in) {
-            const float4* src = reinterpret_cast<const float4*>(p.x + (((size_t)n * p.h_in + ih) * p.w_in + iw) * p.kdim + kc * 32);
+            const float4* src = reinterpret_cast<const float4*>(p.x + (((size_t)n * p.h_in + ih) * p.w_in + iw) * p.kdim + kc * KC);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __ldg(src + j);
+            for (int j = 0; j < 2 * Q; ++j) v[j] = __ldg(src + j);
           } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < 2 * Q; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < Q; ++q) {
             const float f[8] = {v[2 * q].x, v[2 * q].y, v[2 * q].z, v[2 * q].w, v[2 * q + 1].x, v[2 * q + 1].y, v[2 * q + 1].z, v[2 * q + 1].w};
-            __nv_bfloat16 hi[8], lo[8];
+            __nv_bfloat16 t[8][NSPLIT];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) tc::split_bf16(f[e], hi[e], lo[e]);
-            uint4 h4, l4;
-            h4.x = tc::pack_bf16(hi[0], hi[1]); h4.y = tc::pack_bf16(hi[2], hi[3]);
-            h4.z = tc::pack_bf16(hi[4], hi[5]); h4.w = tc::pack_bf16(hi[6], hi[7]);
-            l4.x = tc::pack_bf16(lo[0], lo[1]); l4.y = tc::pack_bf16(lo[2], lo[3]);
-            l4.z = tc::pack_bf16(lo[4], lo[5]); l4.w = tc::pack_bf16(lo[6], lo[7]);
-            *reinterpret_cast<uint4*>(st + (size_t)q * plane_a + (size_t)ps * 16) = h4;
-            *reinterpret_cast<uint4*>(st + (size_t)(4 + q) * plane_a + (size_t)ps * 16) = l4;
+            for (int e = 0; e < 8; ++e) tc_split<NSPLIT>(f[e], t[e]);
+#pragma unroll
+            for (int sp = 0; sp < NSPLIT; ++sp) {
+              uint4 o;
+              o.x = tc::pack_bf16(t[0][sp], t[1][sp]); o.y = tc::pack_bf16(t[2][sp], t[3][sp]);
+              o.z = tc::pack_bf16(t[4][sp], t[5][sp]); o.w = tc::pack_bf16(t[6][sp], t[7][sp]);
+              *reinterpret_cast<uint4*>(st + (size_t)(sp * Q + q) * plane_a + (size_t)ps * 16) = o;
+            }
           }
         }
         tc::fence_proxy_async();
@@ -217,15 +233,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
             const uint32_t d = tmem_base + (uint32_t)(ab * acc_cols + acc * p.ndim);
             const uint32_t aoff = (uint32_t)G::tap_off(tap) * 16u;
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t a_hi = tc::smem_desc(a0 + (2u * ks) * plane_a + aoff, plane_a, G::GSTRIDE * 16u);
-              const uint64_t a_lo = tc::smem_desc(a0 + (4u + 2u * ks) * plane_a + aoff, plane_a, G::GSTRIDE * 16u);
-              const uint64_t b_hi = tc::smem_desc(b0 + (2u * ks) * plane_b, plane_b, 128u);
-              const uint64_t b_lo = tc::smem_desc(b0 + (4u + 2u * ks) * plane_b, plane_b, 128u);
-              tc::mma_bf16(d, a_hi, b_hi, idesc, (started >> acc) & 1u);
+            for (int ks = 0; ks < KC / 16; ++ks) {
+              // split products kept: (0,0) (0,1) (1,0) [+ (0,2) (2,0) (1,1) for the 3-way split]
+              constexpr int NPROD = (NSPLIT == 2) ? 3 : 6;
+              constexpr int PA[6] = {0, 0, 1, 0, 2, 1};
+              constexpr int PB[6] = {0, 1, 0, 2, 0, 1};
+#pragma unroll
+              for (int pr = 0; pr < NPROD; ++pr) {
+                const uint64_t da = tc::smem_desc(a0 + (uint32_t)(PA[pr] * Q + 2 * ks) * plane_a + aoff, plane_a, G::GSTRIDE * 16u);
+                const uint64_t db = tc::smem_desc(b0 + (uint32_t)(PB[pr] * Q + 2 * ks) * plane_b, plane_b, 128u);
+                tc::mma_bf16(d, da, db, idesc, (pr == 0) ? ((started >> acc) & 1u) : 1u);
+              }
               started |= 1u << acc;
-              tc::mma_bf16(d, a_hi, b_lo, idesc, 1u);
-              tc::mma_bf16(d, a_lo, b_hi, idesc, 1u);
             }
             tc::mma_commit(&b_empty[sb]);
             if (++sb == p.sb) { sb = 0; pb ^= 1u; }

@@ -110,7 +110,7 @@ class ConvLayer(Function):
     @staticmethod
     def forward(ctx, x, w, bias, form, ksize, stride, wswap, alpha, act):
         fn = K.conv_c if form == "c" else K.conv_t
-        y = fn(x, w, bias, ksize, stride, wswap, alpha, act)
+        y = fn(x, w, bias, ksize, stride, wswap, alpha, act, precise=True)
         ctx.cfg = (ksize, stride, wswap, alpha)
         ctx.form, ctx.act, ctx.has_bias = form, act, bias is not None
         ctx.save_for_backward(x, w, y)

@@ -4,11 +4,13 @@ pass raw device pointers and the current CUDA stream to libgansynth_b200.so.
 Activations are NHWC fp32.  Every method requires CUDA tensors and fails loudly otherwise -- there is
 no CPU path in the product.
 """
+import os
+
 import torch
 
 from . import _lib
 
-IMPL_AUTO, IMPL_NAIVE, IMPL_TILED = 0, 1, 2
+IMPL_AUTO, IMPL_NAIVE, IMPL_TILED, IMPL_TC, IMPL_FP32 = 0, 1, 2, 3, 4
 
 
 def _ptr(t):
@@ -41,19 +43,26 @@ class CudaBackend(object):
     """The primitive-kernel API the autograd functions in functional.py are written against."""
 
     impl = IMPL_AUTO
+    # implementation used for LAYER FORWARD convolutions (`precise=True`): their outputs decide the
+    # leaky-relu masks, so GS_CONV_FWD_IMPL=4 routes them to the exact-fp32 kernels while the gradient
+    # forms stay on the tensor cores (default -1: same as every other convolution)
+    fwd_impl = int(os.environ.get("GS_CONV_FWD_IMPL", "-1"))
+
+    def _impl(self, precise):
+        return self.fwd_impl if (precise and self.fwd_impl >= 0) else self.impl
 
     # ------------------------------------------------------------------ convolution family
-    def conv_c(self, x, w, bias, ksize, stride, wswap, alpha, act):
+    def conv_c(self, x, w, bias, ksize, stride, wswap, alpha, act, precise=False):
         x, w, bias = _chk(x, w, bias)
         n, h, wd, ci = x.shape
         co = w.shape[2] if wswap else w.shape[3]
         assert (w.shape[3] if wswap else w.shape[2]) == ci, "conv_c: weight/input channel mismatch"
         y = torch.empty((n, h // stride, wd // stride, co), device=x.device, dtype=torch.float32)
         _lib.call("gs_conv2d_fwd", _ptr(x), _ptr(w), _ptr(bias), _ptr(y), n, h, wd, ci, co, ksize, stride,
-                  int(wswap), float(alpha), int(act), self.impl, _stream())
+                  int(wswap), float(alpha), int(act), self._impl(precise), _stream())
         return y
 
-    def conv_t(self, dy, w, bias, ksize, stride, wswap, alpha, act):
+    def conv_t(self, dy, w, bias, ksize, stride, wswap, alpha, act, precise=False):
         dy, w, bias = _chk(dy, w, bias)
         n, oh, ow, co = dy.shape
         ci = w.shape[3] if wswap else w.shape[2]
@@ -61,7 +70,7 @@ class CudaBackend(object):
         h, wd = oh * stride, ow * stride
         dx = torch.empty((n, h, wd, ci), device=dy.device, dtype=torch.float32)
         _lib.call("gs_conv2d_dgrad", _ptr(dy), _ptr(w), _ptr(bias), _ptr(dx), n, h, wd, ci, co, ksize, stride,
-                  int(wswap), float(alpha), int(act), self.impl, _stream())
+                  int(wswap), float(alpha), int(act), self._impl(precise), _stream())
         return dx
 
     def conv_w(self, x, dy, ksize, stride, wswap, alpha):

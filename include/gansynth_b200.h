@@ -13,7 +13,9 @@
  *  - `alpha` is the run-time equalised-learning-rate constant of get_weight (ops.py:154-160), applied
  *    to the contraction result (before bias);
  *  - `act`: 0 none, 1 leaky-relu(0.2) applied after the bias;
- *  - `impl`: 0 auto, 1 naive anchor kernel, 2 tiled fp32 kernel (error if the shape is unsupported);
+ *  - `impl`: 0 auto (tensor-core kernel where the shape allows, else fp32), 1 naive anchor kernel,
+ *    2 tiled fp32 FFMA kernel, 3 tcgen05 tensor-core kernel (2/3: error if the shape is unsupported),
+ *    4 fp32 auto (tiled else naive; never the tensor-core kernel);
  *  - `stream` is a cudaStream_t; every call is asynchronous on it, no hidden synchronisation (the
  *    spectral entry points synchronise once, on first use, to upload twiddle tables);
  *  - return 0 on success, negative on error; gs_last_error() gives the message (thread-local).

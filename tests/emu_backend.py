@@ -28,7 +28,7 @@ class EmuBackend(object):
     def _w(self, w, wswap):
         return w.permute(0, 1, 3, 2) if wswap else w   # -> [k, k, ci, co]
 
-    def conv_c(self, x, w, bias, ksize, stride, wswap, alpha, act):
+    def conv_c(self, x, w, bias, ksize, stride, wswap, alpha, act, precise=False):
         wt = self._w(w, wswap).permute(3, 2, 0, 1)
         pb = 1 if (ksize == 3 and stride == 1) else 0
         pa = (ksize - stride) - pb if ksize == 3 else 0
@@ -38,7 +38,7 @@ class EmuBackend(object):
             y = y + bias.view(1, -1, 1, 1)
         return _nhwc(_act(y, act))
 
-    def conv_t(self, dy, w, bias, ksize, stride, wswap, alpha, act):
+    def conv_t(self, dy, w, bias, ksize, stride, wswap, alpha, act, precise=False):
         wt = self._w(w, wswap).permute(3, 2, 0, 1)      # [co, ci, k, k]
         pb = 1 if (ksize == 3 and stride == 1) else 0
         n, oh, ow, co = dy.shape
