@@ -3,6 +3,7 @@
 // (ops.py:237, ops.py:269) and their TF-generated gradients (models.py:47,60,81-89).
 #include <stdlib.h>
 
+#include "conv1x1.cuh"
 #include "conv_tc.cuh"
 #include "conv_tiled.cuh"
 #include "gansynth_b200.h"
@@ -88,6 +89,34 @@ int launch_w(const float* big, const float* small, float* dw, int n, int h, int 
   dim3 grid((unsigned)gx, (unsigned)ya, (unsigned)zb);
   kern<<<grid, T::NT, T::SMEM, st>>>(big, small, dw, n, h, wd, adim, bdim, oh, ow, pb, out_ab, alpha, th, tw);
   GS_CHECK_LAUNCH("conv_w_tiled");
+  return GS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1x1 convolutions with 2 channels on one side (image side of the colour blocks)
+bool pow2_le32(int v) { return v >= 1 && v <= 32 && (v & (v - 1)) == 0; }
+
+// y[p][ndim] = act(alpha * x[p][kdim] . B + bias); returns 1 if handled
+int try_conv1x1(const float* x, const float* w, const float* bias, float* y, long long npix, int kdim, int ndim,
+                int w_is_kn, float alpha, int act, cudaStream_t st, bool* handled) {
+  *handled = false;
+  if (kdim == 2 && ndim % 4 == 0 && ndim <= 1024) {
+    long long total = npix * (ndim / 4);
+    int blocks = (int)((total + 256 * 4 - 1) / (256 * 4));
+    if (blocks > gs_num_sms() * 16) blocks = gs_num_sms() * 16;
+    if (blocks < 1) blocks = 1;
+    conv1x1_expand_kernel<2><<<blocks, 256, (size_t)(3 * ndim) * sizeof(float), st>>>(x, w, bias, y, npix, ndim, w_is_kn, alpha, act);
+    GS_CHECK_LAUNCH("conv1x1_expand");
+    *handled = true;
+  } else if (ndim == 2 && kdim % 4 == 0 && (pow2_le32(kdim / 4) || kdim % 128 == 0) && kdim <= 2048) {
+    int lpp = kdim / 4 > 32 ? 32 : kdim / 4;
+    long long warps = (npix + (32 / lpp) - 1) / (32 / lpp);
+    long long blocks = (warps + 7) / 8 / 4 + 1;
+    if (blocks > gs_num_sms() * 16) blocks = gs_num_sms() * 16;
+    conv1x1_reduce_kernel<2><<<(int)blocks, 256, (size_t)(2 * kdim) * sizeof(float), st>>>(x, w, bias, y, npix, kdim, w_is_kn, alpha, act);
+    GS_CHECK_LAUNCH("conv1x1_reduce");
+    *handled = true;
+  }
   return GS_OK;
 }
 
@@ -195,6 +224,11 @@ extern "C" int gs_conv2d_fwd(const float* x, const float* w, const float* bias, 
       return launch_tc<TC_C2>(x, w, bias, y, n, h, wd, g.oh, g.ow, ci, co, !g.wswap, 0, alpha, act, st);
     }
   }
+  if (impl != 1 && ksize == 1 && stride == 1) {
+    bool handled = false;
+    rc = try_conv1x1(x, w, bias, y, (long long)n * h * wd, ci, co, !g.wswap, alpha, act, st, &handled);
+    if (rc || handled) return rc;
+  }
   if (impl == 1 || !tiled) {
     size_t total = (size_t)n * g.oh * g.ow * co;
     conv_c_naive_kernel<<<grid_1d(total, 256), 256, 0, st>>>(x, w, bias, y, g);
@@ -230,6 +264,11 @@ extern "C" int gs_conv2d_dgrad(const float* dy, const float* w, const float* bia
       return launch_tc<TC_T2>(dy, w, bias, dx, n, g.oh, g.ow, h, wd, co, ci, g.wswap, 0, alpha, act, st);
     }
   }
+  if (impl != 1 && ksize == 1 && stride == 1) {
+    bool handled = false;
+    rc = try_conv1x1(dy, w, bias, dx, (long long)n * h * wd, co, ci, g.wswap, alpha, act, st, &handled);
+    if (rc || handled) return rc;
+  }
   if (impl == 1 || !tiled) {
     size_t total = (size_t)n * h * wd * ci;
     conv_t_naive_kernel<<<grid_1d(total, 256), 256, 0, st>>>(dy, w, bias, dx, g);
@@ -259,6 +298,23 @@ extern "C" int gs_conv2d_wgrad(const float* x, const float* dy, float* dw, int n
   if (impl == 3) impl = 0;   // no tensor-core filter-gradient kernel yet
   size_t nel = (size_t)ksize * ksize * ci * co;
   GS_CUDA(cudaMemsetAsync(dw, 0, nel * sizeof(float), st));
+  if (impl != 1 && ksize == 1 && stride == 1 && (ci == 2 || co == 2)) {
+    const int W = (ci == 2) ? co : ci;
+    if (W != 2 && W <= 256 && 256 % W == 0) {
+      const long long npix = (long long)n * h * wd;
+      // wide-channel index c, narrow index j -> element offset in dw ([ci][co], or [co][ci] when wswap)
+      int sc, sj;
+      if (ci == 2) { sc = g.wswap ? ci : 1; sj = g.wswap ? 1 : co; }
+      else { sc = g.wswap ? 1 : co; sj = g.wswap ? ci : 1; }
+      long long ppb = (npix + (long long)gs_num_sms() * 8 - 1) / ((long long)gs_num_sms() * 8);
+      if (ppb < 64) ppb = 64;
+      int blocks = (int)((npix + ppb - 1) / ppb);
+      if (ci == 2) conv1x1_w_kernel<2><<<blocks, 256, 0, st>>>(dy, x, dw, npix, W, sc, sj, alpha, ppb);
+      else conv1x1_w_kernel<2><<<blocks, 256, 0, st>>>(x, dy, dw, npix, W, sc, sj, alpha, ppb);
+      GS_CHECK_LAUNCH("conv1x1_w");
+      return GS_OK;
+    }
+  }
   if (impl == 1 || !tiled) {
     long long npix = (long long)n * g.oh * g.ow;
     int chunk = 512;

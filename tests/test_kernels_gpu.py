@@ -38,13 +38,17 @@ CONV_CASES = [
     (2, 2, 16, 257, 256, 3, 1),   # stddev conv: naive path
     (2, 16, 32, 32, 2, 1, 1),     # to-RGB
     (2, 16, 32, 2, 32, 1, 1),     # from-RGB
+    (3, 8, 24, 256, 2, 1, 1),     # to-RGB of a low-resolution colour block (growth path)
+    (3, 8, 24, 2, 256, 1, 1),
+    (1, 4, 8, 2, 64, 1, 1),
+    (1, 4, 8, 128, 2, 1, 1),
     (1, 40, 24, 36, 20, 3, 1),    # K remainder (36 % 8 = 4)
 ]
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
 @pytest.mark.parametrize("wswap", [0, 1])
-@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("impl", [0, 1, 2])
 def test_conv_trio(case, wswap, impl):
     n, h, w, ci, co, ks, st = case
     if impl == 2 and (ks != 3 or ci % 4 or co % 4):

@@ -51,8 +51,11 @@ for scope in ("discriminator", "generator"):
     names = list(store.trainable_variables(scope))
     grads = torch.autograd.grad(loss, [store.vars[n] for n in names], allow_unused=True)
     print("%s loss: cuda %.8f  oracle32 %.8f  oracle64 %.8f" % (scope, float(loss.detach()), float(l32), float(l64)))
-    print("%-60s %10s %10s %10s" % ("variable", "cuda/64", "ora32/64", "|g|max"))
+    print("%-60s %10s %10s %10s %10s %10s" % ("variable", "cuda/64", "ora32/64", "|g|max", "relL2", "1-cos"))
     for n, g in zip(names, grads):
         if g is None:
             continue
-        print("%-60s %10.2e %10.2e %10.2e" % (n, err(g, g64[n]), err(g32[n], g64[n]), float(g64[n].abs().max())))
+        gg, ww = g.double().cpu().reshape(-1), g64[n].reshape(-1)
+        rel = float((gg - ww).norm() / ww.norm())
+        cos = float(torch.dot(gg, ww) / (gg.norm() * ww.norm()))
+        print("%-60s %10.2e %10.2e %10.2e %10.2e %10.2e" % (n, err(g, g64[n]), err(g32[n], g64[n]), float(g64[n].abs().max()), rel, 1 - cos))
