@@ -5,6 +5,7 @@
 
 #include "conv1x1.cuh"
 #include "conv_tc.cuh"
+#include "conv_tcw.cuh"
 #include "conv_tiled.cuh"
 #include "gansynth_b200.h"
 
@@ -203,6 +204,65 @@ int launch_tc(const float* x, const float* w, const float* bias, float* y, int n
   return launch_tc_impl<FORM, 2, 32>(x, w, bias, y, n, h_in, w_in, h_out, w_out, kdim, ndim, w_is_kn, flip, alpha, act, st);
 }
 
+// filter-gradient form on the tensor cores
+bool tcw_ok(int ksize, int adim, int bdim, int sh, int sw) {
+  return ksize == 3 && adim % 32 == 0 && bdim % 32 == 0 && adim <= 256 && bdim <= 256 && sw % 8 == 0 && sh % 2 == 0;
+}
+
+int launch_tcw(const float* big, const float* small, float* dw, int n, int bh, int bw, int adim, int bdim, int sh,
+               int sw, int stride, int out_ab, float alpha, cudaStream_t st) {
+  TcwParams p;
+  p.big = big; p.small = small; p.dw = dw;
+  p.n_img = n; p.bh = bh; p.bw = bw; p.sh = sh; p.sw = sw; p.adim = adim; p.bdim = bdim; p.stride = stride;
+  p.big_is_m = adim >= bdim;
+  p.mch = p.big_is_m ? adim : bdim;
+  p.nch = p.big_is_m ? bdim : adim;
+  p.mt = p.mch < 128 ? p.mch : 128;
+  p.nt = p.nch < 128 ? p.nch : 128;
+  p.m_tiles = p.mch / p.mt;
+  p.n_tiles = p.nch / p.nt;
+  p.tap_groups = (9 * p.nt + 511) / 512;
+  p.tg = (9 + p.tap_groups - 1) / p.tap_groups;
+  int cols = 32;
+  while (cols < p.tg * p.nt) cols <<= 1;
+  p.tmem_cols = cols;
+  const size_t budget = 222 * 1024;
+  int tpr = 16;
+  size_t stage = 0, slack = 0;
+  for (;; tpr >>= 1) {
+    GS_CHECK_ARG(tpr >= 2, "conv_tcw: no tile fits shared memory (adim %d bdim %d)", adim, bdim);
+    if (sh % tpr) continue;
+    const size_t pbig = (size_t)tcw_big_pixels(tpr, stride) * 16, psmall = (size_t)tpr * 8 * 16;
+    p.m_plane = (uint32_t)(p.big_is_m ? pbig : psmall);
+    p.n_plane = (uint32_t)(p.big_is_m ? psmall : pbig);
+    p.m_bytes = (uint32_t)(2 * (p.mt / 8) * p.m_plane);
+    stage = p.m_bytes + (size_t)2 * (p.nt / 8) * p.n_plane;
+    // the M = 128 instruction reads 16 channel planes of the M operand even when mt < 128: keep that
+    // over-read inside the allocation (those accumulator rows are never drained)
+    slack = (size_t)16 * p.m_plane;
+    if (2 * stage + slack <= budget) break;
+  }
+  p.tpr = tpr;
+  p.stage_bytes = (uint32_t)stage;
+  p.stages = (int)((budget - slack) / stage);
+  if (p.stages > TCW_MAX_STAGES) p.stages = TCW_MAX_STAGES;
+  p.tiles_h = sh / tpr; p.tiles_w = sw / 8; p.ntiles = n * p.tiles_h * p.tiles_w;
+  p.out_ab = out_ab; p.alpha = alpha;
+  const int njobs = p.m_tiles * p.n_tiles * p.tap_groups;
+  int px = gs_num_sms() / njobs;
+  if (px < 1) px = 1;
+  if (px > p.ntiles) px = p.ntiles;
+  static bool attr = false;
+  if (!attr) {
+    GS_CUDA(cudaFuncSetAttribute(conv_tcw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    attr = true;
+  }
+  dim3 grid((unsigned)px, (unsigned)njobs);
+  conv_tcw_kernel<<<grid, TCW_THREADS, (size_t)p.stages * stage + slack, st>>>(p);
+  GS_CHECK_LAUNCH("conv_tcw");
+  return GS_OK;
+}
+
 }  // namespace
 
 extern "C" int gs_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, int n, int h, int wd,
@@ -295,7 +355,14 @@ extern "C" int gs_conv2d_wgrad(const float* x, const float* dy, float* dw, int n
   bool tiled = tiled_ok(g);
   if (impl == 4) impl = tiled ? 2 : 1;
   GS_CHECK_ARG(!(impl == 2 && !tiled), "conv2d_wgrad: tiled kernel needs ksize 3 and channels %% 4 == 0");
-  if (impl == 3) impl = 0;   // no tensor-core filter-gradient kernel yet
+  {
+    const bool tcok = tcw_ok(ksize, ci, co, g.oh, g.ow);
+    GS_CHECK_ARG(!(impl == 3 && !tcok), "conv2d_wgrad: tensor-core kernel does not cover this shape");
+    if (impl == 3 || (impl == 0 && tcok && tc_auto_enabled())) {
+      GS_CUDA(cudaMemsetAsync(dw, 0, (size_t)ksize * ksize * ci * co * sizeof(float), (cudaStream_t)stream));
+      return launch_tcw(x, dy, dw, n, h, wd, ci, co, g.oh, g.ow, stride, !g.wswap, alpha, (cudaStream_t)stream);
+    }
+  }
   size_t nel = (size_t)ksize * ksize * ci * co;
   GS_CUDA(cudaMemsetAsync(dw, 0, nel * sizeof(float), st));
   if (impl != 1 && ksize == 1 && stride == 1 && (ci == 2 || co == 2)) {

@@ -139,3 +139,35 @@ def test_tc_full_size_layer_matches_fp32_tiled_kernel():
     a = k2.conv_c(x, wt, b, 3, 1, 0, 0.0589, 1)
     c = k3.conv_c(x, wt, b, 3, 1, 0, 0.0589, 1)
     assert rel_err(c, a) < 1e-4
+
+
+TC_WGRAD_CASES = [
+    # n, h, w (large side), ci, co, stride
+    (1, 16, 8, 32, 32, 1),
+    (2, 32, 16, 32, 32, 1),
+    (1, 16, 16, 64, 32, 1),
+    (1, 16, 16, 32, 64, 1),
+    (2, 16, 24, 64, 64, 1),
+    (1, 8, 16, 128, 128, 1),
+    (1, 4, 16, 256, 256, 1),
+    (2, 2, 16, 256, 256, 1),
+    (1, 16, 16, 256, 128, 1),
+    (2, 32, 32, 32, 64, 2),
+    (1, 32, 16, 64, 32, 2),
+    (1, 16, 32, 128, 256, 2),
+    (1, 8, 32, 256, 256, 2),
+    (2, 128, 64, 32, 32, 1),
+]
+
+
+@pytest.mark.parametrize("case", TC_WGRAD_CASES)
+@pytest.mark.parametrize("wswap", [0, 1])
+def test_tc_filter_gradient(case, wswap):
+    n, h, w, ci, co, st = case
+    k = _k3(3)
+    x = _rand(n, h, w, ci, seed=1)
+    dy = _rand(n, h // st, w // st, co, seed=2)
+    got = k.conv_w(x.cuda(), dy.cuda(), 3, st, wswap, 0.37)
+    want = EMU.conv_w(x.double(), dy.double(), 3, st, wswap, 0.37)
+    assert got.shape == want.shape
+    assert rel_err(got, want) < 1e-4, (case, wswap, rel_err(got, want))
