@@ -306,6 +306,14 @@ def bench_ours(args):
         return
     steps_s = args.steps * world / (ms / 1e3) / world   # iterations/s of the whole job (all ranks step together)
     value = args.steps / (ms / 1e3)
+    if args.conv_table:
+        with open(args.conv_table, "w") as f:
+            f.write("%-8s %3s %5s %5s %4s %4s %2s %2s %5s %10s %9s %9s %8s\n" % (
+                "form", "n", "h", "w", "ci", "co", "k", "s", "calls", "total_ms", "avg_us", "TFLOP/s", "GB/s"))
+            for key, v in sorted(conv.items(), key=lambda kv: -kv[1]["ms"]):
+                avg = v["ms"] / v["n"]
+                f.write("%-8s %3d %5d %5d %4d %4d %2d %2d %5d %10.3f %9.1f %9.1f %8.0f\n" % (
+                    key + (v["n"], v["ms"], avg * 1e3, v["flops"] / (avg * 1e-3) / 1e12, v["bytes"] / (avg * 1e-3) / 1e9)))
     top_key, top = max(conv.items(), key=lambda kv: kv[1]["ms"])
     conv_ms = sum(v["ms"] for v in conv.values())
     avg_ms = top["ms"] / top["n"]
@@ -381,6 +389,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-spectral", action="store_true")
+    ap.add_argument("--conv-table", default=None, help="write per-shape convolution timings of the timed region here")
     args = ap.parse_args()
     if args.impl == "reference":
         bench_reference(args)

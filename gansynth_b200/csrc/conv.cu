@@ -138,12 +138,13 @@ int tc_auto_enabled() {
   return v;
 }
 
-// shape gate of the tensor-core kernels: 3x3, contraction channels % 32, output channels % 32 and <= 256
-// (<= 128 for the four-accumulator transposed form), tile-aligned spatial size on the tiled side
+// shape gate of the tensor-core kernels: 3x3, contraction / output channels % 32, output channels <= 256,
+// tile side a multiple of 16 rows (or 8 / 4 / 2 rows: images are interleaved) and of 8 columns
 bool tc_ok(int form, int ksize, int kdim, int ndim, int th_dim, int tw_dim) {
+  (void)form;
   if (ksize != 3 || kdim % 32 || ndim % 32 || ndim > 256) return false;
-  if (form == TC_T2 && ndim > 128) return false;
-  return th_dim % 16 == 0 && tw_dim % 8 == 0;
+  const bool rows_ok = (th_dim % 16 == 0) || th_dim == 8 || th_dim == 4 || th_dim == 2;
+  return rows_ok && tw_dim % 8 == 0;
 }
 
 template <int FORM, int NSPLIT, int KC>
@@ -170,17 +171,31 @@ int launch_tc_impl(const float* x, const float* w, const float* bias, float* y, 
   p.n_img = n; p.h_in = h_in; p.w_in = w_in; p.h_out = h_out; p.w_out = w_out; p.kdim = kdim; p.ndim = ndim;
   p.alpha = alpha; p.act = act;
   const int th_dim = (FORM == TC_T2) ? h_in : h_out, tw_dim = (FORM == TC_T2) ? w_in : w_out;
-  p.tiles_h = th_dim / 16; p.tiles_w = tw_dim / 8; p.ntiles = n * p.tiles_h * p.tiles_w;
-  const size_t a_stage = (size_t)NSPLIT * (KC / 8) * G::P * 16, b_stage = (size_t)NSPLIT * (KC / 8) * ndim * 16;
+  if (th_dim % 16 == 0) { p.rows = 16; p.img = 1; p.tiles_h = th_dim / 16; }
+  else { p.rows = th_dim; p.img = 16 / th_dim; p.tiles_h = 1; }
+  p.tiles_w = tw_dim / 8;
+  p.ntiles = ((n + p.img - 1) / p.img) * p.tiles_h * p.tiles_w;
+  p.pix = G::pixels(p.rows, p.img);
+  for (int t = 0; t < 9; ++t) p.tap_off[t] = G::tap_off(t, p.img);
+  // output-channel tile: all channels when there are enough pixel tiles to fill the GPU, else split so
+  // that more SMs share the layer (each CTA re-reads the same halo, the weights are partitioned)
+  int nt = ndim;
+  if (G::NACC * nt > 512) nt = 512 / G::NACC;
+  while (nt > 64 && nt % 64 == 0 && (long long)p.ntiles * (ndim / nt) < gs_num_sms()) nt /= 2;
   const size_t budget = 222 * 1024;
-  p.sa = (FORM == TC_C2) ? 2 : 3;
+  const size_t a_stage = (size_t)NSPLIT * (KC / 8) * p.pix * 16;
+  p.sa = (FORM == TC_C2 && p.img == 1) ? 2 : 3;
+  while (p.sa > 2 && (size_t)p.sa * a_stage + 2 * (size_t)NSPLIT * (KC / 8) * nt * 16 > budget) --p.sa;
+  while (nt > 32 && (size_t)p.sa * a_stage + 2 * (size_t)NSPLIT * (KC / 8) * nt * 16 > budget) nt /= 2;
+  const size_t b_stage = (size_t)NSPLIT * (KC / 8) * nt * 16;
   GS_CHECK_ARG((size_t)p.sa * a_stage + 2 * b_stage <= budget, "conv_tc: shared memory budget exceeded (ndim %d)", ndim);
-  size_t left = budget - p.sa * a_stage;
-  p.sb = (int)(left / b_stage);
+  p.nt = nt;
+  p.n_tiles = ndim / nt;
+  p.sb = (int)((budget - p.sa * a_stage) / b_stage);
   if (p.sb > TC_MAX_STAGES) p.sb = TC_MAX_STAGES;
-  p.nbuf = (2 * G::NACC * ndim <= 512) ? 2 : 1;
+  p.nbuf = (2 * G::NACC * nt <= 512) ? 2 : 1;
   int cols = 32;
-  while (cols < p.nbuf * G::NACC * ndim) cols <<= 1;
+  while (cols < p.nbuf * G::NACC * nt) cols <<= 1;
   p.tmem_cols = cols;
   const size_t smem = p.sa * a_stage + p.sb * b_stage;
   auto kern = conv_tc_kernel<FORM, NSPLIT, KC>;
@@ -189,7 +204,10 @@ int launch_tc_impl(const float* x, const float* w, const float* bias, float* y, 
     GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
     attr = true;
   }
-  int grid = p.ntiles < gs_num_sms() ? p.ntiles : gs_num_sms();
+  int gx = gs_num_sms() / p.n_tiles;
+  if (gx < 1) gx = 1;
+  if (gx > p.ntiles) gx = p.ntiles;
+  dim3 grid((unsigned)gx, (unsigned)p.n_tiles);
   kern<<<grid, TC_THREADS, smem, st>>>(p);
   GS_CHECK_LAUNCH("conv_tc");
   return GS_OK;

@@ -1,23 +1,27 @@
 // tcgen05 / TMEM implicit-GEMM 3x3 convolutions for sm_100a (NHWC fp32 in HBM, bf16x3 on the tensor cores).
 //
-// One CTA owns a 16x8 pixel tile (M = 128 accumulator rows = TMEM lanes) and ALL output channels
-// (N = Cout <= 256 accumulator columns).  For each chunk of 32 input channels the halo of the tile is read
-// from HBM once, split fp32 -> (bf16 hi, bf16 lo) and stored in shared memory as 16-byte channel vectors,
-// pixel-major ("SWIZZLE_NONE core matrices": plane q = channels 8q..8q+7, 16 bytes per pixel).  In that
-// layout every filter tap is just a different START ADDRESS / group stride of the same staged tile, so the
-// nine taps cost nine descriptor pairs, not nine loads.  Each 16-channel K slice issues three MMAs
-// (hi*hi + hi*lo + lo*hi; NSPLIT = 2: products carry ~17 mantissa bits) or, for layer forwards whose sign
-// decides the leaky-relu mask, six MMAs of a 3-way split (h,m,l; NSPLIT = 3: ~25 bits, fp32-grade);
-// accumulation is fp32 in TMEM.
+// One CTA owns 128 output pixels (M = 128 accumulator rows = TMEM lanes: 16 groups of 8 consecutive
+// columns) and NT <= 256 output channels (accumulator columns).  For each chunk of 32 input channels the
+// halo of the tile is read from HBM once, split fp32 -> (bf16 hi, bf16 lo) and stored in shared memory as
+// 16-byte channel vectors, pixel-major ("SWIZZLE_NONE core matrices": plane q = channels 8q..8q+7,
+// 16 bytes per pixel).  In that layout every filter tap is just a different START ADDRESS of the same
+// staged tile (group stride fixed), so the nine taps cost nine descriptor pairs, not nine loads.  Each
+// 16-channel K slice issues three MMAs (hi*hi + hi*lo + lo*hi); accumulation is fp32 in TMEM (the
+// accumulator truncates: ~1e-5 relative at K = 2304, tools/tc_precision.py).
 // Weights are pre-split into the same layout by conv_tc_prep_kernel and streamed per tap with 1-D bulk
-// copies.  Warp roles: 0-3 epilogue (TMEM -> bias / leaky-relu -> HBM), 4-7 halo load + split, 8 weight
-// copies, 9 MMA issue + TMEM allocation.  Rings: A (per channel chunk), B (per tap), accumulators (per tile).
+// copies (TMA engine).  Warp roles: 0-3 epilogue (TMEM -> alpha, bias, leaky-relu -> HBM), 4-7 halo load +
+// split, 8 weight copies, 9 MMA issue + TMEM allocation.  Rings: A (per channel chunk), B (per tap),
+// accumulators (per tile).
+//
+// Tiles.  Images with >= 16 rows: 16 rows x 8 columns of one image.  Smaller images (8, 4, 2 rows: the
+// 256-channel low-resolution blocks) interleave IMG = 16 / rows images row by row -- group g = row * IMG
+// + slot -- so the halo rows of different images never alias and the group stride stays uniform.
 //
 // Forms (template FORM):
 //   TC_C1  gather conv stride 1 (forward of conv2d; dgrad of stride 1 with flipped/transposed weights)
 //   TC_C2  gather conv stride 2 (forward of the down-scaling conv; dgrad of conv2d_transpose)
 //   TC_T2  transposed conv stride 2 (forward of conv2d_transpose; dgrad of the down-scaling conv):
-//          four sub-pixel phases = four accumulators fed by 4/2/2/1 taps of one 17x9 halo
+//          four sub-pixel phases = four accumulators fed by 4/2/2/1 taps of one halo
 #pragma once
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -25,32 +29,24 @@
 enum { TC_C1 = 0, TC_C2 = 1, TC_T2 = 2 };
 
 template <int FORM>
-struct TcGeo;
-template <>
-struct TcGeo<TC_C1> {
-  static constexpr int P = 18 * 10, GSTRIDE = 10, NACC = 1;
-  __device__ static int tap_off(int t) { return (t / 3) * 10 + (t % 3); }
-  __device__ static int tap_acc(int) { return 0; }
-};
-template <>
-struct TcGeo<TC_C2> {
-  // 33 input rows x 17 input columns, columns de-interleaved by parity: [row][9 even | 8 odd]
-  static constexpr int P = 33 * 17, GSTRIDE = 34, NACC = 1;
-  __device__ static int tap_off(int t) {
-    int kh = t / 3, kw = t % 3;
-    return kh * 17 + (kw & 1) * 9 + (kw >> 1);
+struct TcGeo {
+  // pixels between consecutive 8-pixel groups of the staged tile
+  static constexpr int GSTRIDE = (FORM == TC_C1) ? 10 : (FORM == TC_C2) ? 34 : 9;
+  static constexpr int NACC = (FORM == TC_T2) ? 4 : 1;
+  __host__ __device__ static constexpr int tap_acc(int t) {
+    return (FORM == TC_T2) ? (((t / 3) == 1 ? 2 : 0) + ((t % 3) == 1 ? 1 : 0)) : 0;
   }
-  __device__ static int tap_acc(int) { return 0; }
-};
-template <>
-struct TcGeo<TC_T2> {
-  // 17 rows (i0-1 .. i0+15) x 9 columns (j0-1 .. j0+7) of the small side
-  static constexpr int P = 17 * 9, GSTRIDE = 9, NACC = 4;
-  __device__ static int tap_off(int t) {
-    int kh = t / 3, kw = t % 3;
-    return ((kh == 2) ? 0 : 1) * 9 + ((kw == 2) ? 0 : 1);
+  // staged pixels for a tile of `rows` rows per image and `img` interleaved images
+  __host__ __device__ static constexpr int pixels(int rows, int img) {
+    return (FORM == TC_C1) ? (rows + 2) * img * 10 : (FORM == TC_C2) ? (rows + 1) * img * 34 : (rows + 1) * img * 9;
   }
-  __device__ static int tap_acc(int t) { return ((t / 3) == 1 ? 2 : 0) + ((t % 3) == 1 ? 1 : 0); }
+  // start offset (pixels) of tap t
+  __host__ __device__ static constexpr int tap_off(int t, int img) {
+    const int kh = t / 3, kw = t % 3;
+    if (FORM == TC_C1) return kh * img * 10 + kw;
+    if (FORM == TC_C2) return (kh == 0 ? 0 : kh == 1 ? 17 : img * 34) + (kw & 1) * 9 + (kw >> 1);
+    return ((kh == 2) ? 0 : 1) * img * 9 + ((kw == 2) ? 0 : 1);
+  }
 };
 
 struct TcParams {
@@ -61,16 +57,20 @@ struct TcParams {
   int n_img, h_in, w_in, h_out, w_out, kdim, ndim;
   float alpha;
   int act;
-  int tiles_h, tiles_w, ntiles;
+  int rows, img;                  // tile: `rows` rows of each of `img` interleaved images, 8 columns
+  int pix;                        // staged pixels per tile
+  int tiles_h, tiles_w, ntiles;   // ntiles = image groups * tiles_h * tiles_w
+  int nt, n_tiles;                // output-channel tile (grid.y)
+  int tap_off[9];
   int sa, sb;                     // ring depths
   int nbuf;                       // accumulator buffers (1 or 2)
-  int tmem_cols;                  // power of two >= nbuf * NACC * ndim
+  int tmem_cols;                  // power of two >= nbuf * NACC * nt
 };
 
 constexpr int TC_THREADS = 320;
 constexpr int TC_MAX_STAGES = 4;
 
-// fp32 -> NSPLIT bf16 terms whose sum reproduces x to 2^-17 (2 terms) / 2^-25 (3 terms) relative
+// fp32 -> NSPLIT bf16 terms whose sum reproduces x to 2^-17 (2 terms) relative
 template <int NSPLIT>
 __device__ __forceinline__ void tc_split(float x, __nv_bfloat16 (&t)[NSPLIT]) {
   float r = x;
@@ -120,13 +120,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t plane_a = G::P * 16u;
-  const uint32_t plane_b = (uint32_t)p.ndim * 16u;
+  const uint32_t plane_a = (uint32_t)p.pix * 16u;
+  const uint32_t plane_b = (uint32_t)p.nt * 16u;
   const uint32_t a_stage_bytes = (uint32_t)(NSPLIT * Q) * plane_a;   // [split][q] planes
   const uint32_t b_stage_bytes = (uint32_t)(NSPLIT * Q) * plane_b;
   unsigned char* a_smem = tc_smem;
   unsigned char* b_smem = tc_smem + (size_t)p.sa * a_stage_bytes;
   const int nchunks = p.kdim / KC;
+  const int n0 = blockIdx.y * p.nt;       // first output channel of this CTA
 
   if (tid == 0) {
     for (int s = 0; s < p.sa; ++s) { tc::mbar_init(&a_full[s], 128); tc::mbar_init(&a_empty[s], 1); }
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  const int acc_cols = G::NACC * p.ndim;   // columns per accumulator buffer
+  const int acc_cols = G::NACC * p.nt;   // columns per accumulator buffer
 
   if (warp >= 4 && warp < 8) {
     // ============================== halo load + fp32 -> bf16 hi/lo split ==============================
@@ -151,22 +152,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
       const int tw_ = t % p.tiles_w;
       t /= p.tiles_w;
       const int th_ = t % p.tiles_h;
-      const int n = t / p.tiles_h;
-      int r0, c0;   // input coordinates of halo element (0, 0)
+      const int img0 = (t / p.tiles_h) * p.img;
+      int r0, c0;   // input coordinates of staged element (row 0, column 0)
       if (FORM == TC_C1) { r0 = th_ * 16 - 1; c0 = tw_ * 8 - 1; }
       else if (FORM == TC_C2) { r0 = th_ * 32; c0 = tw_ * 16; }
       else { r0 = th_ * 16 - 1; c0 = tw_ * 8 - 1; }
       for (int kc = 0; kc < nchunks; ++kc) {
         tc::mbar_wait(&a_empty[stage], phase ^ 1u);
         unsigned char* st = a_smem + (size_t)stage * a_stage_bytes;
-        for (int ps = ct; ps < G::P; ps += 128) {
-          int hr, hc;
-          if (FORM == TC_C1) { hr = ps / 10; hc = ps % 10; }
-          else if (FORM == TC_C2) { hr = ps / 17; int rem = ps % 17; int par = rem >= 9; hc = 2 * (rem - 9 * par) + par; }
-          else { hr = ps / 9; hc = ps % 9; }
-          const int ih = r0 + hr, iw = c0 + hc;
+        for (int ps = ct; ps < p.pix; ps += 128) {
+          int hr, hc, slot;
+          if (FORM == TC_C1) { hc = ps % 10; int u = ps / 10; slot = u % p.img; hr = u / p.img; }
+          else if (FORM == TC_C2) {
+            int rem = ps % 34, u = ps / 34;
+            slot = u % p.img;
+            hr = 2 * (u / p.img) + (rem >= 17);
+            rem -= 17 * (rem >= 17);
+            int par = rem >= 9;
+            hc = 2 * (rem - 9 * par) + par;
+          } else { hc = ps % 9; int u = ps / 9; slot = u % p.img; hr = u / p.img; }
+          const int ih = r0 + hr, iw = c0 + hc, n = img0 + slot;
           float4 v[2 * Q];
-          if (ih >= 0 && ih < p.h_in && iw >= 0 && iw < p.w_in) {
+          if (n < p.n_img && ih >= 0 && ih < p.h_in && iw >= 0 && iw < p.w_in) {
             const float4* src = reinterpret_cast<const float4*>(p.x + (((size_t)n * p.h_in + ih) * p.w_in + iw) * p.kdim + kc * KC);
 #pragma unroll
             for (int j = 0; j < 2 * Q; ++j) v[j] = __ldg(src + j);
@@ -177,14 +184,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
 #pragma unroll
           for (int q = 0; q < Q; ++q) {
             const float f[8] = {v[2 * q].x, v[2 * q].y, v[2 * q].z, v[2 * q].w, v[2 * q + 1].x, v[2 * q + 1].y, v[2 * q + 1].z, v[2 * q + 1].w};
-            __nv_bfloat16 t[8][NSPLIT];
+            __nv_bfloat16 t2[8][NSPLIT];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) tc_split<NSPLIT>(f[e], t[e]);
+            for (int e = 0; e < 8; ++e) tc_split<NSPLIT>(f[e], t2[e]);
 #pragma unroll
             for (int sp = 0; sp < NSPLIT; ++sp) {
               uint4 o;
-              o.x = tc::pack_bf16(t[0][sp], t[1][sp]); o.y = tc::pack_bf16(t[2][sp], t[3][sp]);
-              o.z = tc::pack_bf16(t[4][sp], t[5][sp]); o.w = tc::pack_bf16(t[6][sp], t[7][sp]);
+              o.x = tc::pack_bf16(t2[0][sp], t2[1][sp]); o.y = tc::pack_bf16(t2[2][sp], t2[3][sp]);
+              o.z = tc::pack_bf16(t2[4][sp], t2[5][sp]); o.w = tc::pack_bf16(t2[6][sp], t2[7][sp]);
               *reinterpret_cast<uint4*>(st + (size_t)(sp * Q + q) * plane_a + (size_t)ps * 16) = o;
             }
           }
@@ -195,17 +202,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
       }
     }
   } else if (warp == 8) {
-    // ============================== weight blocks: one bulk copy per (chunk, tap) ======================
+    // ============================== weight blocks: bulk copies per (chunk, tap) =========================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      const size_t src_plane = (size_t)p.ndim * 16;          // bytes of one [n][8] plane in wprep
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         for (int kc = 0; kc < nchunks; ++kc) {
           for (int tap = 0; tap < 9; ++tap) {
             tc::mbar_wait(&b_empty[stage], phase ^ 1u);
             tc::mbar_arrive_expect_tx(&b_full[stage], b_stage_bytes);
-            const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wprep) + ((size_t)kc * 9 + tap) * b_stage_bytes;
-            tc::bulk_g2s(b_smem + (size_t)stage * b_stage_bytes, src, b_stage_bytes, &b_full[stage]);
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wprep) +
+                                       ((size_t)kc * 9 + tap) * (NSPLIT * Q) * src_plane + (size_t)n0 * 16;
+            unsigned char* dst = b_smem + (size_t)stage * b_stage_bytes;
+            if (p.nt == p.ndim) {
+              tc::bulk_g2s(dst, src, b_stage_bytes, &b_full[stage]);
+            } else {
+#pragma unroll
+              for (int pl = 0; pl < NSPLIT * Q; ++pl) tc::bulk_g2s(dst + (size_t)pl * plane_b, src + (size_t)pl * src_plane, plane_b, &b_full[stage]);
+            }
             if (++stage == p.sb) { stage = 0; phase ^= 1u; }
           }
         }
@@ -213,38 +228,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
     }
   } else if (warp == 9) {
     // ============================== MMA issue ==========================================================
+    // One thread feeds the tensor core.  With N = 32 an MMA is only ~16 cycles of tensor work, so the
+    // issue loop is kept to an add or two per MMA: descriptors are a per-stage base (start address in
+    // 16-byte units in the low word) plus tap / K-slice / split offsets.
     if (lane == 0) {
-      const uint32_t idesc = tc::idesc_bf16_f32(p.ndim, 0, 0);
+      const uint32_t idesc = tc::idesc_bf16_f32(p.nt, 0, 0);
+      const uint64_t a_desc0 = tc::smem_desc(tc::smem_u32(a_smem), plane_a, G::GSTRIDE * 16u);
+      const uint64_t b_desc0 = tc::smem_desc(tc::smem_u32(b_smem), plane_b, 128u);
+      const uint32_t a_stage16 = a_stage_bytes >> 4, b_stage16 = b_stage_bytes >> 4;
+      const uint32_t plane_a16 = plane_a >> 4, plane_b16 = plane_b >> 4;
       int sa = 0, sb = 0, ab = 0;
       uint32_t pa = 0, pb = 0, pacc = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         tc::mbar_wait(&acc_empty[ab], pacc ^ 1u);
         tc::tc_fence_after();
-        uint32_t started = 0;   // bit a: accumulator a already holds a partial sum for this tile
+        const uint32_t d0 = tmem_base + (uint32_t)(ab * acc_cols);
         for (int kc = 0; kc < nchunks; ++kc) {
           tc::mbar_wait(&a_full[sa], pa);
           tc::tc_fence_after();
-          const uint32_t a0 = tc::smem_u32(a_smem + (size_t)sa * a_stage_bytes);
+          const uint64_t a_base = a_desc0 + (uint64_t)((uint32_t)sa * a_stage16);
+          const uint32_t acc_rest = (kc > 0) ? 1u : 0u;
+#pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             tc::mbar_wait(&b_full[sb], pb);
             tc::tc_fence_after();
-            const uint32_t b0 = tc::smem_u32(b_smem + (size_t)sb * b_stage_bytes);
+            const uint64_t b_base = b_desc0 + (uint64_t)((uint32_t)sb * b_stage16);
             const int acc = G::tap_acc(tap);
-            const uint32_t d = tmem_base + (uint32_t)(ab * acc_cols + acc * p.ndim);
-            const uint32_t aoff = (uint32_t)G::tap_off(tap) * 16u;
+            const uint32_t d = d0 + (uint32_t)(acc * p.nt);
+            const uint64_t a_tap = a_base + (uint64_t)(uint32_t)p.tap_off[tap];
+            // the first tap that touches an accumulator overwrites it on the first channel chunk
+            const bool opens = (G::NACC == 1) ? (tap == 0) : (tap == 0 || tap == 1 || tap == 3 || tap == 4);
 #pragma unroll
             for (int ks = 0; ks < KC / 16; ++ks) {
-              // split products kept: (0,0) (0,1) (1,0) [+ (0,2) (2,0) (1,1) for the 3-way split]
               constexpr int NPROD = (NSPLIT == 2) ? 3 : 6;
               constexpr int PA[6] = {0, 0, 1, 0, 2, 1};
               constexpr int PB[6] = {0, 1, 0, 2, 0, 1};
 #pragma unroll
               for (int pr = 0; pr < NPROD; ++pr) {
-                const uint64_t da = tc::smem_desc(a0 + (uint32_t)(PA[pr] * Q + 2 * ks) * plane_a + aoff, plane_a, G::GSTRIDE * 16u);
-                const uint64_t db = tc::smem_desc(b0 + (uint32_t)(PB[pr] * Q + 2 * ks) * plane_b, plane_b, 128u);
-                tc::mma_bf16(d, da, db, idesc, (pr == 0) ? ((started >> acc) & 1u) : 1u);
+                const uint64_t da = a_tap + (uint64_t)((uint32_t)(PA[pr] * Q + 2 * ks) * plane_a16);
+                const uint64_t db = b_base + (uint64_t)((uint32_t)(PB[pr] * Q + 2 * ks) * plane_b16);
+                const uint32_t accum = (opens && ks == 0 && pr == 0) ? acc_rest : 1u;
+                tc::mma_bf16(d, da, db, idesc, accum);
               }
-              started |= 1u << acc;
             }
             tc::mma_commit(&b_empty[sb]);
             if (++sb == p.sb) { sb = 0; pb ^= 1u; }
@@ -262,39 +287,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
     uint32_t pacc = 0;
     const int m = warp * 32 + lane;
     const int g = m >> 3, i = m & 7;
+    const int row = g / p.img, slot = g % p.img;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       int t = tile;
       const int tw_ = t % p.tiles_w;
       t /= p.tiles_w;
       const int th_ = t % p.tiles_h;
-      const int n = t / p.tiles_h;
+      const int n = (t / p.tiles_h) * p.img + slot;
       tc::mbar_wait(&acc_full[ab], pacc);
       tc::tc_fence_after();
 #pragma unroll 1
       for (int a = 0; a < G::NACC; ++a) {
         int oy, ox;
-        if (FORM == TC_T2) { oy = 2 * (th_ * 16 + g) + (a >> 1); ox = 2 * (tw_ * 8 + i) + (a & 1); }
-        else { oy = th_ * 16 + g; ox = tw_ * 8 + i; }
-        float* dst = p.y + (((size_t)n * p.h_out + oy) * p.w_out + ox) * p.ndim;
-        const bool in_range = (oy < p.h_out) && (ox < p.w_out);
+        if (FORM == TC_T2) { oy = 2 * (th_ * 16 + row) + (a >> 1); ox = 2 * (tw_ * 8 + i) + (a & 1); }
+        else { oy = th_ * 16 + row; ox = tw_ * 8 + i; }
+        const bool in_range = (n < p.n_img) && (oy < p.h_out) && (ox < p.w_out);
+        float* dst = p.y + (((size_t)n * p.h_out + oy) * p.w_out + ox) * p.ndim + n0;
 #pragma unroll 1
-        for (int c0 = 0; c0 < p.ndim; c0 += 32) {
+        for (int c0 = 0; c0 < p.nt; c0 += 32) {
           float v[32];
-          tc::tmem_ld32(tmem_base + lane_base + (uint32_t)(ab * acc_cols + a * p.ndim + c0), v);
-          const int nvalid = p.ndim - c0;   // ndim is a multiple of 16: a chunk holds 32 or 16 valid columns
+          tc::tmem_ld32(tmem_base + lane_base + (uint32_t)(ab * acc_cols + a * p.nt + c0), v);
           if (in_range) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              if (j < nvalid) {
-                float4 o;
-                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
-                o.x = fmaf(v[j + 0], p.alpha, bv.x); o.y = fmaf(v[j + 1], p.alpha, bv.y);
-                o.z = fmaf(v[j + 2], p.alpha, bv.z); o.w = fmaf(v[j + 3], p.alpha, bv.w);
-                if (p.act == 1) { o.x = gs_lrelu(o.x); o.y = gs_lrelu(o.y); o.z = gs_lrelu(o.z); o.w = gs_lrelu(o.w); }
-                *reinterpret_cast<float4*>(dst + c0 + j) = o;
-              }
+              float4 o;
+              float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
+              o.x = fmaf(v[j + 0], p.alpha, bv.x); o.y = fmaf(v[j + 1], p.alpha, bv.y);
+              o.z = fmaf(v[j + 2], p.alpha, bv.z); o.w = fmaf(v[j + 3], p.alpha, bv.w);
+              if (p.act == 1) { o.x = gs_lrelu(o.x); o.y = gs_lrelu(o.y); o.z = gs_lrelu(o.z); o.w = gs_lrelu(o.w); }
+              *reinterpret_cast<float4*>(dst + c0 + j) = o;
             }
           }
         }

@@ -150,40 +150,43 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const TcwParam
     }
   } else if (lane == 0) {
     // ============================== MMA issue ==========================================================
+    // Descriptors = per-stage base + tap offset + k-step stride, all in 16-byte units in the low word.
     const uint32_t idesc = tc::idesc_bf16_f32(p.nt, 1, 1);
-    const uint32_t big_row = (p.stride == 1) ? 10u * 16u : 17u * 16u;   // bytes per staged row of `big`
-    const uint32_t big_lbo = (p.stride == 1) ? 160u : 544u;           // next tile row (stride 2: two staged rows)
+    const uint32_t big_lbo = (p.stride == 1) ? 160u : 544u;            // next tile row of `big`
+    const uint32_t big_step16 = (p.stride == 1) ? 20u : 68u;            // two tile rows of `big`, 16-byte units
+    const uint32_t m_step16 = p.big_is_m ? big_step16 : 16u, n_step16 = p.big_is_m ? 16u : big_step16;
+    const uint64_t m_desc0 = tc::smem_desc(tc::smem_u32(tcw_smem), p.big_is_m ? big_lbo : 128u, p.m_plane);
+    const uint64_t n_desc0 = tc::smem_desc(tc::smem_u32(tcw_smem) + p.m_bytes, p.big_is_m ? 128u : big_lbo, p.n_plane);
+    const uint32_t stage16 = p.stage_bytes >> 4;
+    const uint32_t m_lo16 = ((uint32_t)qm * p.m_plane) >> 4, n_lo16 = ((uint32_t)qn * p.n_plane) >> 4;
+    const int ksteps = p.tpr / 2;
     int stage = 0;
     uint32_t phase = 0;
-    bool first = true;
+    uint32_t accum_first = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       tc::mbar_wait(&full_m[stage], phase);
       tc::mbar_wait(&full_n[stage], phase);
       tc::tc_fence_after();
-      const uint32_t m0 = tc::smem_u32(tcw_smem + (size_t)stage * p.stage_bytes);
-      const uint32_t n0 = m0 + p.m_bytes;
+      const uint64_t m_base = m_desc0 + (uint64_t)((uint32_t)stage * stage16);
+      const uint64_t n_base = n_desc0 + (uint64_t)((uint32_t)stage * stage16);
       for (int tl = 0; tl < ntap; ++tl) {
         const int tap = tap0 + tl, kh = tap / 3, kw = tap % 3;
+        const uint32_t tap16 = (p.stride == 1) ? (uint32_t)(kh * 10 + kw) : (uint32_t)(kh * 17 + (kw & 1) * 9 + (kw >> 1));
+        uint64_t a_hi = m_base + (uint64_t)(p.big_is_m ? tap16 : 0u);
+        uint64_t b_hi = n_base + (uint64_t)(p.big_is_m ? 0u : tap16);
         const uint32_t d = tmem_base + (uint32_t)(tl * p.nt);
-        for (int j = 0; j < p.tpr / 2; ++j) {
-          // 16 pixels = tile rows 2j, 2j+1
-          uint32_t big_off;
-          if (p.stride == 1) big_off = (uint32_t)((2 * j + kh) * 10 + kw) * 16u;
-          else big_off = (uint32_t)((4 * j + kh) * 17 + (kw & 1) * 9 + (kw >> 1)) * 16u;
-          const uint32_t small_off = (uint32_t)j * 256u;
-          const uint32_t moff = p.big_is_m ? big_off : small_off, noff = p.big_is_m ? small_off : big_off;
-          const uint32_t mlbo = p.big_is_m ? big_lbo : 128u, nlbo = p.big_is_m ? 128u : big_lbo;
-          const uint64_t a_hi = tc::smem_desc(m0 + moff, mlbo, p.m_plane);
-          const uint64_t a_lo = tc::smem_desc(m0 + (uint32_t)qm * p.m_plane + moff, mlbo, p.m_plane);
-          const uint64_t b_hi = tc::smem_desc(n0 + noff, nlbo, p.n_plane);
-          const uint64_t b_lo = tc::smem_desc(n0 + (uint32_t)qn * p.n_plane + noff, nlbo, p.n_plane);
-          tc::mma_bf16(d, a_hi, b_hi, idesc, (first && j == 0) ? 0u : 1u);
-          tc::mma_bf16(d, a_hi, b_lo, idesc, 1u);
-          tc::mma_bf16(d, a_lo, b_hi, idesc, 1u);
+        uint32_t accum = accum_first;
+#pragma unroll 2
+        for (int j = 0; j < ksteps; ++j) {
+          tc::mma_bf16(d, a_hi, b_hi, idesc, accum);
+          tc::mma_bf16(d, a_hi, b_hi + n_lo16, idesc, 1u);
+          tc::mma_bf16(d, a_hi + m_lo16, b_hi, idesc, 1u);
+          accum = 1u;
+          a_hi += m_step16;
+          b_hi += n_step16;
         }
       }
-      (void)big_row;
-      first = false;
+      accum_first = 1u;
       tc::mma_commit(&empty[stage]);
       if (++stage == p.stages) { stage = 0; phase ^= 1u; }
     }

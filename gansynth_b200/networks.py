@@ -190,10 +190,18 @@ class PGGAN(object):
         def conv_block(inputs, depth):
             with variable_scope("conv_block_{}x{}".format(*resolution(depth))):
                 if depth == self.min_depth:
-                    inputs = torch.cat([inputs, batch_stddev(inputs)], dim=3)
                     with variable_scope("conv"):
-                        inputs = conv2d(inputs, filters=channels(depth), kernel_size=[3, 3], use_bias=True,
-                                        variance_scale=2.0, scale_weight=True, activation="leaky_relu")
+                        # conv2d(concat([x, batch_stddev(x)])) with the [3,3,C+1,C] variable of the reference
+                        # (networks.py:174-184), evaluated as conv(x, W[:, :, :C]) + conv(stddev, W[:, :, C:]):
+                        # the C-channel part stays on the vectorised / tensor-core kernels instead of
+                        # dragging a 257-channel tensor through the generic path.
+                        ch = channels(depth)
+                        weight, alpha = ops.get_weight([3, 3, ch + 1, ch], 2.0, True)
+                        bias = ops.get_bias([ch])
+                        stddev = batch_stddev(inputs).contiguous()
+                        main = F.ConvC.apply(inputs, weight[:, :, :ch, :].contiguous(), 3, 1, False, alpha)
+                        extra = F.ConvC.apply(stddev, weight[:, :, ch:, :].contiguous(), 3, 1, False, alpha)
+                        inputs = F.BiasAct.apply(F.Axpby.apply(main, extra, 1.0, 1.0), bias, F.ACT_LRELU)
                     with variable_scope("dense"):
                         # tf.layers.flatten of the NCHW tensor: index = c*H*W + h*W + w
                         b, h, w, c = inputs.shape

@@ -81,6 +81,13 @@ TC_FWD_CASES = [
     (2, 32, 16, 32, 64, 2),
     (1, 64, 32, 64, 128, 2),
     (1, 32, 48, 128, 256, 2),
+    # low-resolution 256-channel blocks: images interleaved row by row, output channels split over CTAs
+    (8, 2, 16, 256, 256, 1),
+    (8, 4, 32, 256, 256, 1),
+    (3, 8, 64, 256, 256, 1),
+    (8, 4, 32, 256, 256, 2),
+    (8, 16, 128, 256, 256, 2),
+    (5, 8, 16, 64, 32, 2),
 ]
 
 
@@ -109,6 +116,12 @@ TC_DGRAD_CASES = [
     (2, 64, 32, 32, 64, 2),
     (1, 32, 48, 128, 256, 2),
     (1, 64, 16, 64, 128, 2),
+    (8, 2, 16, 256, 256, 1),
+    (3, 4, 32, 256, 256, 1),
+    (8, 8, 64, 256, 256, 1),
+    (8, 4, 32, 256, 256, 2),
+    (8, 16, 128, 256, 256, 2),
+    (3, 8, 64, 64, 256, 2),
 ]
 
 
