@@ -184,20 +184,27 @@ int launch_tc_impl(const float* x, const float* w, const float* bias, float* y, 
   while (nt > 64 && nt % 64 == 0 && (long long)p.ntiles * (ndim / nt) < gs_num_sms()) nt /= 2;
   const size_t budget = 222 * 1024;
   const size_t a_stage = (size_t)NSPLIT * (KC / 8) * p.pix * 16;
-  p.sa = (FORM == TC_C2 && p.img == 1) ? 2 : 3;
-  while (p.sa > 2 && (size_t)p.sa * a_stage + 2 * (size_t)NSPLIT * (KC / 8) * nt * 16 > budget) --p.sa;
+  const size_t stg = (size_t)p.pix * KC * 4;
+  p.sa = 2;
   while (nt > 32 && (size_t)p.sa * a_stage + 2 * (size_t)NSPLIT * (KC / 8) * nt * 16 > budget) nt /= 2;
   const size_t b_stage = (size_t)NSPLIT * (KC / 8) * nt * 16;
   GS_CHECK_ARG((size_t)p.sa * a_stage + 2 * b_stage <= budget, "conv_tc: shared memory budget exceeded (ndim %d)", ndim);
   p.nt = nt;
   p.n_tiles = ndim / nt;
-  p.sb = (int)((budget - p.sa * a_stage) / b_stage);
-  if (p.sb > TC_MAX_STAGES) p.sb = TC_MAX_STAGES;
+  // shared memory: 2 operand stages + 2 weight stages first, then staging slots for the asynchronous halo
+  // prefetch (up to 3), then extra weight stages (up to 4)
+  size_t used = p.sa * a_stage + 2 * b_stage;
+  p.ds = 0;
+  while (p.ds < 3 && used + stg <= budget) { ++p.ds; used += stg; }
+  if (p.ds == 0 && used + a_stage <= budget) { ++p.sa; used += a_stage; }   // no prefetch ring: deeper operand ring
+  p.sb = 2;
+  while (p.sb < TC_MAX_STAGES && used + b_stage <= budget) { ++p.sb; used += b_stage; }
+  if (getenv("GS_TC_NO_PREFETCH")) { p.ds = 0; }
   p.nbuf = (2 * G::NACC * nt <= 512) ? 2 : 1;
   int cols = 32;
   while (cols < p.nbuf * G::NACC * nt) cols <<= 1;
   p.tmem_cols = cols;
-  const size_t smem = p.sa * a_stage + p.sb * b_stage;
+  const size_t smem = p.sa * a_stage + p.sb * b_stage + p.ds * stg;
   auto kern = conv_tc_kernel<FORM, NSPLIT, KC>;
   static bool attr = false;
   if (!attr) {
@@ -219,6 +226,9 @@ int launch_tc_impl(const float* x, const float* w, const float* bias, float* y, 
 template <int FORM>
 int launch_tc(const float* x, const float* w, const float* bias, float* y, int n, int h_in, int w_in, int h_out,
               int w_out, int kdim, int ndim, int w_is_kn, int flip, float alpha, int act, cudaStream_t st) {
+  // the stride-2 gather form stages ~4x the pixels of the others: 16-channel chunks keep a prefetch ring in budget
+  if (FORM == TC_C2)
+    return launch_tc_impl<FORM, 2, 16>(x, w, bias, y, n, h_in, w_in, h_out, w_out, kdim, ndim, w_is_kn, flip, alpha, act, st);
   return launch_tc_impl<FORM, 2, 32>(x, w, bias, y, n, h_in, w_in, h_out, w_out, kdim, ndim, w_is_kn, flip, alpha, act, st);
 }
 
@@ -232,18 +242,35 @@ int launch_tcw(const float* big, const float* small, float* dw, int n, int bh, i
   TcwParams p;
   p.big = big; p.small = small; p.dw = dw;
   p.n_img = n; p.bh = bh; p.bw = bw; p.sh = sh; p.sw = sw; p.adim = adim; p.bdim = bdim; p.stride = stride;
-  p.big_is_m = adim >= bdim;
-  p.mch = p.big_is_m ? adim : bdim;
-  p.nch = p.big_is_m ? bdim : adim;
-  p.mt = p.mch < 128 ? p.mch : 128;
-  p.nt = p.nch < 128 ? p.nch : 128;
-  p.m_tiles = p.mch / p.mt;
-  p.n_tiles = p.nch / p.nt;
-  p.tap_groups = (9 * p.nt + 511) / 512;
-  p.tg = (9 + p.tap_groups - 1) / p.tap_groups;
-  int cols = 32;
-  while (cols < p.tg * p.nt) cols <<= 1;
-  p.tmem_cols = cols;
+  p.mode_e = (adim <= 64) && !getenv("GS_TCW_NO_EXPAND");
+  if (p.mode_e) {
+    // kw-expanded: M = (kw, big channel) in tiles of 128 rows, N = small channels, one accumulator per (kh, M tile)
+    p.big_is_m = 1;
+    p.mch = 3 * adim; p.nch = bdim;
+    p.m_tiles = (3 * adim + 127) / 128;
+    p.mt = 128;
+    int nt = bdim < 128 ? bdim : 128;
+    while (3 * p.m_tiles * nt > 512) nt /= 2;
+    p.nt = nt;
+    p.n_tiles = bdim / nt;
+    p.tap_groups = 1; p.tg = 9;
+    int cols = 32;
+    while (cols < 3 * p.m_tiles * nt) cols <<= 1;
+    p.tmem_cols = cols;
+  } else {
+    p.big_is_m = adim >= bdim;
+    p.mch = p.big_is_m ? adim : bdim;
+    p.nch = p.big_is_m ? bdim : adim;
+    p.mt = p.mch < 128 ? p.mch : 128;
+    p.nt = p.nch < 128 ? p.nch : 128;
+    p.m_tiles = p.mch / p.mt;
+    p.n_tiles = p.nch / p.nt;
+    p.tap_groups = (9 * p.nt + 511) / 512;
+    p.tg = (9 + p.tap_groups - 1) / p.tap_groups;
+    int cols = 32;
+    while (cols < p.tg * p.nt) cols <<= 1;
+    p.tmem_cols = cols;
+  }
   const size_t budget = 222 * 1024;
   int tpr = 16;
   size_t stage = 0, slack = 0;
@@ -253,9 +280,10 @@ int launch_tcw(const float* big, const float* small, float* dw, int n, int bh, i
     const size_t pbig = (size_t)tcw_big_pixels(tpr, stride) * 16, psmall = (size_t)tpr * 8 * 16;
     p.m_plane = (uint32_t)(p.big_is_m ? pbig : psmall);
     p.n_plane = (uint32_t)(p.big_is_m ? psmall : pbig);
-    p.m_bytes = (uint32_t)(2 * (p.mt / 8) * p.m_plane);
+    const size_t m_planes = p.mode_e ? (size_t)2 * 3 * (adim / 8) : (size_t)2 * (p.mt / 8);
+    p.m_bytes = (uint32_t)(m_planes * p.m_plane);
     stage = p.m_bytes + (size_t)2 * (p.nt / 8) * p.n_plane;
-    // the M = 128 instruction reads 16 channel planes of the M operand even when mt < 128: keep that
+    // the M = 128 instruction reads 16 channel planes of the M operand even when fewer are staged: keep that
     // over-read inside the allocation (those accumulator rows are never drained)
     slack = (size_t)16 * p.m_plane;
     if (2 * stage + slack <= budget) break;
@@ -266,7 +294,7 @@ int launch_tcw(const float* big, const float* small, float* dw, int n, int bh, i
   if (p.stages > TCW_MAX_STAGES) p.stages = TCW_MAX_STAGES;
   p.tiles_h = sh / tpr; p.tiles_w = sw / 8; p.ntiles = n * p.tiles_h * p.tiles_w;
   p.out_ab = out_ab; p.alpha = alpha;
-  const int njobs = p.m_tiles * p.n_tiles * p.tap_groups;
+  const int njobs = p.mode_e ? p.n_tiles : p.m_tiles * p.n_tiles * p.tap_groups;
   int px = gs_num_sms() / njobs;
   if (px < 1) px = 1;
   if (px > p.ntiles) px = p.ntiles;
@@ -349,6 +377,11 @@ extern "C" int gs_conv2d_dgrad(const float* dy, const float* w, const float* bia
   }
   if (impl == 1 || !tiled) {
     size_t total = (size_t)n * h * wd * ci;
+    if (co >= 64 && total <= (size_t)gs_num_sms() * 256) {
+      conv_t_naive_warp_kernel<<<grid_1d(total * 32, 256), 256, 0, st>>>(dy, w, bias, dx, g);
+      GS_CHECK_LAUNCH("conv_t_naive_warp");
+      return GS_OK;
+    }
     conv_t_naive_kernel<<<grid_1d(total, 256), 256, 0, st>>>(dy, w, bias, dx, g);
     GS_CHECK_LAUNCH("conv_t_naive");
     return GS_OK;
@@ -403,6 +436,13 @@ extern "C" int gs_conv2d_wgrad(const float* x, const float* dy, float* dw, int n
   if (impl == 1 || !tiled) {
     long long npix = (long long)n * g.oh * g.ow;
     int chunk = 512;
+    {   // few pixels: shorter chunks so that the grid still fills the GPU
+      long long bx = (long long)(nel + 127) / 128;
+      long long want = ((long long)gs_num_sms() * 4 + bx - 1) / bx;
+      long long c2 = (npix + want - 1) / want;
+      if (c2 < 16) c2 = 16;
+      if (c2 < chunk) chunk = (int)c2;
+    }
     dim3 grid((unsigned)gs_cdiv((long long)nel, 128), (unsigned)gs_cdiv(npix, chunk));
     conv_w_naive_kernel<<<grid, 128, 0, st>>>(x, dy, dw, g, chunk);
     GS_CHECK_LAUNCH("conv_w_naive");

@@ -84,6 +84,48 @@ __global__ void conv_t_naive_kernel(const float* __restrict__ dy, const float* _
   }
 }
 
+// Same contract, one WARP per output element (lanes stride over the contraction channel co): for outputs
+// with few elements and a long contraction (the 1-channel stddev branch) the thread-per-output kernel is
+// a latency chain of thousands of dependent loads.
+__global__ void conv_t_naive_warp_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                         const float* __restrict__ bias, float* __restrict__ dx, ConvGeom g) {
+  const size_t total = (size_t)g.n * g.h * g.w * g.ci;
+  const int lane = threadIdx.x & 31;
+  const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t idx = warp; idx < total; idx += nwarps) {
+    int ci = (int)(idx % g.ci);
+    size_t p = idx / g.ci;
+    int iw = (int)(p % g.w);
+    p /= g.w;
+    int ih = (int)(p % g.h);
+    int n = (int)(p / g.h);
+    float acc = 0.0f;
+    for (int kh = 0; kh < g.ksize; ++kh) {
+      int th = ih + g.pb - kh;
+      if (th < 0 || (th % g.stride) != 0) continue;
+      int oh = th / g.stride;
+      if (oh >= g.oh) continue;
+      for (int kw = 0; kw < g.ksize; ++kw) {
+        int tw = iw + g.pb - kw;
+        if (tw < 0 || (tw % g.stride) != 0) continue;
+        int ow = tw / g.stride;
+        if (ow >= g.ow) continue;
+        const float* yp = dy + (((size_t)n * g.oh + oh) * g.ow + ow) * g.co;
+        int tap = kh * g.ksize + kw;
+        for (int co = lane; co < g.co; co += 32) acc = fmaf(yp[co], gs_wt(w, g, tap, ci, co), acc);
+      }
+    }
+    acc = gs_warp_sum(acc);
+    if (lane == 0) {
+      acc *= g.alpha;
+      if (bias) acc += bias[ci];
+      if (g.act == 1) acc = gs_lrelu(acc);
+      dx[idx] = acc;
+    }
+  }
+}
+
 // dw(kh,kw,ci,co) += alpha * sum over a pixel chunk of x[n,oh*s+kh-pb,ow*s+kw-pb,ci] * dy[n,oh,ow,co]
 // grid.x covers (tap,ci,co) in blocks of 128 threads, grid.y = pixel chunks; dw must be zeroed first.
 __global__ void conv_w_naive_kernel(const float* __restrict__ x, const float* __restrict__ dy,

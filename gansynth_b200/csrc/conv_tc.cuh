@@ -63,6 +63,7 @@ struct TcParams {
   int nt, n_tiles;                // output-channel tile (grid.y)
   int tap_off[9];
   int sa, sb;                     // ring depths
+  int ds;                         // fp32 staging slots of the asynchronous halo prefetch (0: direct loads)
   int nbuf;                       // accumulator buffers (1 or 2)
   int tmem_cols;                  // power of two >= nbuf * NACC * nt
 };
@@ -126,6 +127,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
   const uint32_t b_stage_bytes = (uint32_t)(NSPLIT * Q) * plane_b;
   unsigned char* a_smem = tc_smem;
   unsigned char* b_smem = tc_smem + (size_t)p.sa * a_stage_bytes;
+  unsigned char* stg_smem = b_smem + (size_t)p.sb * b_stage_bytes;     // [ds][pix][KC] fp32, chunks XOR-swizzled
+  const uint32_t stg_bytes = (uint32_t)p.pix * (KC * 4u);
   const int nchunks = p.kdim / KC;
   const int n0 = blockIdx.y * p.nt;       // first output channel of this CTA
 
@@ -144,62 +147,129 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
 
   if (warp >= 4 && warp < 8) {
     // ============================== halo load + fp32 -> bf16 hi/lo split ==============================
+    // The loads are the latency-critical part (one HBM round trip per tile otherwise): they are issued
+    // p.ds work items ahead as 16-byte cp.async copies into an fp32 staging ring (zero-filled outside the
+    // image).  Every thread converts exactly the pixels it copied itself, so cp.async.wait_group is the
+    // only synchronisation the staging ring needs.
     const int ct = tid - 128;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    constexpr int CH = KC / 4;                      // 16-byte chunks per pixel
+    // bank-conflict-free chunk permutation of the staging rows (128-byte rows: 8 pixels x 8 chunks;
+    // 64-byte rows: pixel pairs share a 128-byte line)
+    auto swz = [](int ps) { return (CH == 8) ? (ps & 7) : ((ps >> 1) & 3); };
+    auto coords = [&](int tile, int ps, int& n, int& ih, int& iw) {
       int t = tile;
       const int tw_ = t % p.tiles_w;
       t /= p.tiles_w;
       const int th_ = t % p.tiles_h;
       const int img0 = (t / p.tiles_h) * p.img;
-      int r0, c0;   // input coordinates of staged element (row 0, column 0)
-      if (FORM == TC_C1) { r0 = th_ * 16 - 1; c0 = tw_ * 8 - 1; }
-      else if (FORM == TC_C2) { r0 = th_ * 32; c0 = tw_ * 16; }
-      else { r0 = th_ * 16 - 1; c0 = tw_ * 8 - 1; }
-      for (int kc = 0; kc < nchunks; ++kc) {
-        tc::mbar_wait(&a_empty[stage], phase ^ 1u);
-        unsigned char* st = a_smem + (size_t)stage * a_stage_bytes;
-        for (int ps = ct; ps < p.pix; ps += 128) {
-          int hr, hc, slot;
-          if (FORM == TC_C1) { hc = ps % 10; int u = ps / 10; slot = u % p.img; hr = u / p.img; }
-          else if (FORM == TC_C2) {
-            int rem = ps % 34, u = ps / 34;
-            slot = u % p.img;
-            hr = 2 * (u / p.img) + (rem >= 17);
-            rem -= 17 * (rem >= 17);
-            int par = rem >= 9;
-            hc = 2 * (rem - 9 * par) + par;
-          } else { hc = ps % 9; int u = ps / 9; slot = u % p.img; hr = u / p.img; }
-          const int ih = r0 + hr, iw = c0 + hc, n = img0 + slot;
-          float4 v[2 * Q];
-          if (n < p.n_img && ih >= 0 && ih < p.h_in && iw >= 0 && iw < p.w_in) {
-            const float4* src = reinterpret_cast<const float4*>(p.x + (((size_t)n * p.h_in + ih) * p.w_in + iw) * p.kdim + kc * KC);
+      int hr, hc, slot;
+      if (FORM == TC_C1) { hc = ps % 10; int u = ps / 10; slot = u % p.img; hr = u / p.img; ih = th_ * 16 - 1 + hr; iw = tw_ * 8 - 1 + hc; }
+      else if (FORM == TC_C2) {
+        int rem = ps % 34, u = ps / 34;
+        slot = u % p.img;
+        hr = 2 * (u / p.img) + (rem >= 17);
+        rem -= 17 * (rem >= 17);
+        int par = rem >= 9;
+        hc = 2 * (rem - 9 * par) + par;
+        ih = th_ * 32 + hr; iw = tw_ * 16 + hc;
+      } else { hc = ps % 9; int u = ps / 9; slot = u % p.img; hr = u / p.img; ih = th_ * 16 - 1 + hr; iw = tw_ * 8 - 1 + hc; }
+      n = img0 + slot;
+    };
+    auto convert_store = [&](unsigned char* st, int ps, const float4 (&v)[CH]) {
 #pragma unroll
-            for (int j = 0; j < 2 * Q; ++j) v[j] = __ldg(src + j);
-          } else {
+      for (int q = 0; q < Q; ++q) {
+        const float f[8] = {v[2 * q].x, v[2 * q].y, v[2 * q].z, v[2 * q].w, v[2 * q + 1].x, v[2 * q + 1].y, v[2 * q + 1].z, v[2 * q + 1].w};
+        __nv_bfloat16 t2[8][NSPLIT];
 #pragma unroll
-            for (int j = 0; j < 2 * Q; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+        for (int e = 0; e < 8; ++e) tc_split<NSPLIT>(f[e], t2[e]);
 #pragma unroll
-          for (int q = 0; q < Q; ++q) {
-            const float f[8] = {v[2 * q].x, v[2 * q].y, v[2 * q].z, v[2 * q].w, v[2 * q + 1].x, v[2 * q + 1].y, v[2 * q + 1].z, v[2 * q + 1].w};
-            __nv_bfloat16 t2[8][NSPLIT];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) tc_split<NSPLIT>(f[e], t2[e]);
-#pragma unroll
-            for (int sp = 0; sp < NSPLIT; ++sp) {
-              uint4 o;
-              o.x = tc::pack_bf16(t2[0][sp], t2[1][sp]); o.y = tc::pack_bf16(t2[2][sp], t2[3][sp]);
-              o.z = tc::pack_bf16(t2[4][sp], t2[5][sp]); o.w = tc::pack_bf16(t2[6][sp], t2[7][sp]);
-              *reinterpret_cast<uint4*>(st + (size_t)(sp * Q + q) * plane_a + (size_t)ps * 16) = o;
-            }
-          }
+        for (int sp = 0; sp < NSPLIT; ++sp) {
+          uint4 o;
+          o.x = tc::pack_bf16(t2[0][sp], t2[1][sp]); o.y = tc::pack_bf16(t2[2][sp], t2[3][sp]);
+          o.z = tc::pack_bf16(t2[4][sp], t2[5][sp]); o.w = tc::pack_bf16(t2[6][sp], t2[7][sp]);
+          *reinterpret_cast<uint4*>(st + (size_t)(sp * Q + q) * plane_a + (size_t)ps * 16) = o;
         }
-        tc::fence_proxy_async();
-        tc::mbar_arrive(&a_full[stage]);
-        if (++stage == p.sa) { stage = 0; phase ^= 1u; }
       }
+    };
+    int stage = 0;
+    uint32_t phase = 0;
+    if (p.ds == 0) {
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        for (int kc = 0; kc < nchunks; ++kc) {
+          tc::mbar_wait(&a_empty[stage], phase ^ 1u);
+          unsigned char* st = a_smem + (size_t)stage * a_stage_bytes;
+          for (int ps = ct; ps < p.pix; ps += 128) {
+            int n, ih, iw;
+            coords(tile, ps, n, ih, iw);
+            float4 v[CH];
+            if (n < p.n_img && ih >= 0 && ih < p.h_in && iw >= 0 && iw < p.w_in) {
+              const float4* src = reinterpret_cast<const float4*>(p.x + (((size_t)n * p.h_in + ih) * p.w_in + iw) * p.kdim + kc * KC);
+#pragma unroll
+              for (int j = 0; j < CH; ++j) v[j] = __ldg(src + j);
+            } else {
+#pragma unroll
+              for (int j = 0; j < CH; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            convert_store(st, ps, v);
+          }
+          tc::fence_proxy_async();
+          tc::mbar_arrive(&a_full[stage]);
+          if (++stage == p.sa) { stage = 0; phase ^= 1u; }
+        }
+      }
+    } else {
+      auto issue = [&](int tile, int kc, int slot) {
+        unsigned char* sg = stg_smem + (size_t)slot * stg_bytes;
+        for (int ps = ct; ps < p.pix; ps += 128) {
+          int n, ih, iw;
+          coords(tile, ps, n, ih, iw);
+          const bool ok = n < p.n_img && ih >= 0 && ih < p.h_in && iw >= 0 && iw < p.w_in;
+          const float* src = ok ? p.x + (((size_t)n * p.h_in + ih) * p.w_in + iw) * p.kdim + kc * KC : p.x;
+#pragma unroll
+          for (int j = 0; j < CH; ++j)
+            tc::cp_async16(sg + (size_t)ps * (KC * 4) + (size_t)((j ^ swz(ps)) * 16), src + j * 4, ok ? 16u : 0u);
+        }
+      };
+      // prefetch iterator (pt, pk) runs p.ds items ahead of the convert iterator (tile, kc)
+      int pt = blockIdx.x, pk = 0, slot_pf = 0;
+      for (int i = 0; i < p.ds; ++i) {
+        if (pt < p.ntiles) {
+          issue(pt, pk, slot_pf);
+          if (++pk == nchunks) { pk = 0; pt += gridDim.x; }
+        }
+        tc::cp_async_commit();
+        if (++slot_pf == p.ds) slot_pf = 0;
+      }
+      int slot_cv = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        for (int kc = 0; kc < nchunks; ++kc) {
+          // groups are committed one per item, so "all but the newest ds-1" == the item being converted
+          if (p.ds == 1) tc::cp_async_wait<0>();
+          else if (p.ds == 2) tc::cp_async_wait<1>();
+          else tc::cp_async_wait<2>();
+          tc::mbar_wait(&a_empty[stage], phase ^ 1u);
+          unsigned char* st = a_smem + (size_t)stage * a_stage_bytes;
+          const unsigned char* sg = stg_smem + (size_t)slot_cv * stg_bytes;
+          for (int ps = ct; ps < p.pix; ps += 128) {
+            float4 v[CH];
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              v[j] = *reinterpret_cast<const float4*>(sg + (size_t)ps * (KC * 4) + (size_t)((j ^ swz(ps)) * 16));
+            convert_store(st, ps, v);
+          }
+          tc::fence_proxy_async();
+          tc::mbar_arrive(&a_full[stage]);
+          if (++stage == p.sa) { stage = 0; phase ^= 1u; }
+          // refill the slot just consumed
+          if (pt < p.ntiles) {
+            issue(pt, pk, slot_cv);
+            if (++pk == nchunks) { pk = 0; pt += gridDim.x; }
+          }
+          tc::cp_async_commit();
+          if (++slot_cv == p.ds) slot_cv = 0;
+        }
+      }
+      tc::cp_async_wait<0>();
     }
   } else if (warp == 8) {
     // ============================== weight blocks: bulk copies per (chunk, tap) =========================

@@ -10,6 +10,11 @@
 // The side with fewer channels is put on N (<= 128 per CTA); TG taps x N columns of TMEM (<= 512) are
 // accumulated over the CTA's whole pixel range and added to dw with fp32 atomics at the end.
 // grid = (pixel splits, jobs), job = (M tile, N tile, tap group).
+//
+// Thin layers (<= 64 channels on the `big` side) use the kw-EXPANDED mode instead: `big` is staged three
+// times, shifted by the column offset of kw = 0, 1, 2, as extra channel planes.  M then runs over
+// (kw, channel) = 96 or 192 rows, so a 128-row MMA is filled, the nine taps cost three MMAs (one per kh,
+// each with its own accumulator) and nothing is re-staged per tap group.
 // Warps 0-3 stage the M-side operand, 4-7 the N-side operand (fp32 -> bf16 hi/lo), warp 8 issues MMAs;
 // warps 0-7 drain TMEM at the end.
 #pragma once
@@ -22,6 +27,7 @@ struct TcwParams {
   float* dw;
   int n_img, bh, bw, sh, sw, adim, bdim, stride;
   int big_is_m;         // 1: big on M, small on N; 0: small on M, big on N
+  int mode_e;           // kw-expanded mode (big on M, M = 3 * adim rows in m_tiles tiles of 128)
   int mch, nch;         // total channels on the M / N side
   int mt, nt;           // channels per CTA tile on each side (mt <= 128, nt <= 128, multiples of 8)
   int m_tiles, n_tiles, tap_groups, tg;
@@ -73,9 +79,11 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const TcwParam
     const bool m_side = warp < 4;
     const bool is_big = m_side ? (p.big_is_m != 0) : (p.big_is_m == 0);
     const int ct = tid & 127;
-    const int q_cnt = m_side ? qm : qn;
-    const int ch0 = m_side ? m_ch0 : n_ch0;
-    const int ch_valid = m_side ? mt_valid : nt_valid;
+    const bool expand = p.mode_e && is_big;          // kw-expanded staging of `big`
+    const int q_cnt = expand ? p.adim / 8 : (m_side ? qm : qn);
+    const int ch0 = expand ? 0 : (m_side ? m_ch0 : n_ch0);
+    const int ch_valid = expand ? p.adim : (m_side ? mt_valid : nt_valid);
+    const int shift1 = (p.stride == 1) ? 1 : 9, shift2 = (p.stride == 1) ? 2 : 1;   // staged-pixel shift of kw = 1, 2
     const uint32_t plane = m_side ? p.m_plane : p.n_plane;
     const float* src_base = is_big ? p.big : p.small;
     const int cdim = is_big ? p.adim : p.bdim;
@@ -115,8 +123,23 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const TcwParam
           h4.z = tc::pack_bf16(hi[4], hi[5]); h4.w = tc::pack_bf16(hi[6], hi[7]);
           l4.x = tc::pack_bf16(lo[0], lo[1]); l4.y = tc::pack_bf16(lo[2], lo[3]);
           l4.z = tc::pack_bf16(lo[4], lo[5]); l4.w = tc::pack_bf16(lo[6], lo[7]);
-          *reinterpret_cast<uint4*>(st + (size_t)q * plane + (size_t)ps * 16) = h4;
-          *reinterpret_cast<uint4*>(st + (size_t)(q_cnt + q) * plane + (size_t)ps * 16) = l4;
+          if (!expand) {
+            *reinterpret_cast<uint4*>(st + (size_t)q * plane + (size_t)ps * 16) = h4;
+            *reinterpret_cast<uint4*>(st + (size_t)(q_cnt + q) * plane + (size_t)ps * 16) = l4;
+          } else {
+            // planes [split][kw][q]; plane kw holds the tile shifted left by the column offset of tap kw
+            const size_t lo0 = (size_t)3 * q_cnt;
+            *reinterpret_cast<uint4*>(st + (size_t)q * plane + (size_t)ps * 16) = h4;
+            *reinterpret_cast<uint4*>(st + (lo0 + q) * plane + (size_t)ps * 16) = l4;
+            if (ps >= shift1) {
+              *reinterpret_cast<uint4*>(st + (size_t)(q_cnt + q) * plane + (size_t)(ps - shift1) * 16) = h4;
+              *reinterpret_cast<uint4*>(st + (lo0 + q_cnt + q) * plane + (size_t)(ps - shift1) * 16) = l4;
+            }
+            if (ps >= shift2) {
+              *reinterpret_cast<uint4*>(st + (size_t)(2 * q_cnt + q) * plane + (size_t)(ps - shift2) * 16) = h4;
+              *reinterpret_cast<uint4*>(st + (lo0 + 2 * q_cnt + q) * plane + (size_t)(ps - shift2) * 16) = l4;
+            }
+          }
         }
       }
       tc::fence_proxy_async();
@@ -128,8 +151,32 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const TcwParam
     tc::tc_fence_after();
     const int quarter = warp & 3, half = warp >> 2;
     const int m = quarter * 32 + lane;
-    const int ncols = ntap * p.nt;
+    const int ncols = p.mode_e ? 3 * p.m_tiles * p.nt : ntap * p.nt;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    if (p.mode_e) {
+      // columns: accumulator (kh, t) at ((kh * m_tiles + t) * nt); row m of M tile t = group 16 t + m/8 of (kw, channel)
+      const int qa = p.adim / 8;
+      for (int c0 = half * 32; c0 < ncols; c0 += 64) {
+        float v[32];
+        tc::tmem_ld32(tmem_base + lane_base + (uint32_t)c0, v);
+        const int accn = c0 / p.nt, nn0 = c0 % p.nt;
+        const int kh = accn / p.m_tiles, t = accn % p.m_tiles;
+        const int gi = 16 * t + (m >> 3);
+        if (gi < 3 * qa) {
+          const int kw = gi / qa, a = (gi % qa) * 8 + (m & 7);
+          const int tap = kh * 3 + kw;
+#pragma unroll 4
+          for (int j = 0; j < 32; ++j) {
+            const int nn = nn0 + j;
+            if (nn < nt_valid) {
+              const int b = n_ch0 + nn;
+              const size_t o = p.out_ab ? ((size_t)tap * p.adim + a) * p.bdim + b : ((size_t)tap * p.bdim + b) * p.adim + a;
+              atomicAdd(p.dw + o, v[j] * p.alpha);
+            }
+          }
+        }
+      }
+    } else
     for (int c0 = half * 32; c0 < ncols; c0 += 64) {
       float v[32];
       tc::tmem_ld32(tmem_base + lane_base + (uint32_t)c0, v);
@@ -163,6 +210,38 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const TcwParam
     int stage = 0;
     uint32_t phase = 0;
     uint32_t accum_first = 0;
+    if (p.mode_e) {
+      const uint32_t split_lo16 = ((uint32_t)(3 * (p.adim / 8)) * p.m_plane) >> 4;   // hi planes -> lo planes of big
+      const uint32_t row16 = (p.stride == 1) ? 10u : 17u;                            // one staged row of `big`
+      const uint32_t mtile16 = (16u * p.m_plane) >> 4;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        tc::mbar_wait(&full_m[stage], phase);
+        tc::mbar_wait(&full_n[stage], phase);
+        tc::tc_fence_after();
+        const uint64_t m_base = m_desc0 + (uint64_t)((uint32_t)stage * stage16);
+        const uint64_t n_base = n_desc0 + (uint64_t)((uint32_t)stage * stage16);
+        for (int kh = 0; kh < 3; ++kh) {
+          for (int t = 0; t < p.m_tiles; ++t) {
+            uint64_t a_hi = m_base + (uint64_t)((uint32_t)kh * row16 + (uint32_t)t * mtile16);
+            uint64_t b_hi = n_base;
+            const uint32_t d = tmem_base + (uint32_t)((kh * p.m_tiles + t) * p.nt);
+            uint32_t accum = accum_first;
+#pragma unroll 2
+            for (int j = 0; j < ksteps; ++j) {
+              tc::mma_bf16(d, a_hi, b_hi, idesc, accum);
+              tc::mma_bf16(d, a_hi, b_hi + n_lo16, idesc, 1u);
+              tc::mma_bf16(d, a_hi + split_lo16, b_hi, idesc, 1u);
+              accum = 1u;
+              a_hi += big_step16;
+              b_hi += 16u;
+            }
+          }
+        }
+        accum_first = 1u;
+        tc::mma_commit(&empty[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    } else
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       tc::mbar_wait(&full_m[stage], phase);
       tc::mbar_wait(&full_n[stage], phase);
