@@ -273,25 +273,32 @@ int launch_tcw(const float* big, const float* small, float* dw, int n, int bh, i
   }
   const size_t budget = 222 * 1024;
   int tpr = 16;
-  size_t stage = 0, slack = 0;
+  size_t stage = 0, raw = 0, slack = 0;
+  const int m_ch = p.mode_e ? adim : p.mt, n_ch = p.nt;       // channels staged per pixel on each side
   for (;; tpr >>= 1) {
     GS_CHECK_ARG(tpr >= 2, "conv_tcw: no tile fits shared memory (adim %d bdim %d)", adim, bdim);
     if (sh % tpr) continue;
-    const size_t pbig = (size_t)tcw_big_pixels(tpr, stride) * 16, psmall = (size_t)tpr * 8 * 16;
+    const size_t pbig = (size_t)tcw_big_plane_pixels(tpr, stride, p.mode_e) * 16, psmall = (size_t)tpr * 8 * 16;
+    const size_t rbig = (size_t)tcw_big_raw_pixels(tpr, stride), rsmall = (size_t)tpr * 8;
     p.m_plane = (uint32_t)(p.big_is_m ? pbig : psmall);
     p.n_plane = (uint32_t)(p.big_is_m ? psmall : pbig);
     const size_t m_planes = p.mode_e ? (size_t)2 * 3 * (adim / 8) : (size_t)2 * (p.mt / 8);
     p.m_bytes = (uint32_t)(m_planes * p.m_plane);
     stage = p.m_bytes + (size_t)2 * (p.nt / 8) * p.n_plane;
+    p.m_raw = (uint32_t)((p.big_is_m ? rbig : rsmall) * m_ch * 4);
+    raw = p.m_raw + (p.big_is_m ? rsmall : rbig) * n_ch * 4;
     // the M = 128 instruction reads 16 channel planes of the M operand even when fewer are staged: keep that
     // over-read inside the allocation (those accumulator rows are never drained)
     slack = (size_t)16 * p.m_plane;
-    if (2 * stage + slack <= budget) break;
+    if (2 * stage + raw + slack <= budget && (tpr <= 2 || 2 * stage + 2 * raw + slack <= budget)) break;
   }
   p.tpr = tpr;
   p.stage_bytes = (uint32_t)stage;
-  p.stages = (int)((budget - slack) / stage);
-  if (p.stages > TCW_MAX_STAGES) p.stages = TCW_MAX_STAGES;
+  p.raw_bytes = (uint32_t)raw;
+  p.stages = 2; p.ds = 1;
+  size_t used = 2 * stage + raw + slack;
+  while (p.ds < 3 && used + raw <= budget) { ++p.ds; used += raw; }
+  while (p.stages < TCW_MAX_STAGES && used + stage <= budget) { ++p.stages; used += stage; }
   p.tiles_h = sh / tpr; p.tiles_w = sw / 8; p.ntiles = n * p.tiles_h * p.tiles_w;
   p.out_ab = out_ab; p.alpha = alpha;
   const int njobs = p.mode_e ? p.n_tiles : p.m_tiles * p.n_tiles * p.tap_groups;
@@ -304,7 +311,7 @@ int launch_tcw(const float* big, const float* small, float* dw, int n, int bh, i
     attr = true;
   }
   dim3 grid((unsigned)px, (unsigned)njobs);
-  conv_tcw_kernel<<<grid, TCW_THREADS, (size_t)p.stages * stage + slack, st>>>(p);
+  conv_tcw_kernel<<<grid, TCW_THREADS, (size_t)p.stages * stage + (size_t)p.ds * raw + slack, st>>>(p);
   GS_CHECK_LAUNCH("conv_tcw");
   return GS_OK;
 }

@@ -14,7 +14,8 @@ namespace {
 
 __global__ void __launch_bounds__(160) tc_probe_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                        float* __restrict__ D, int K, int N, int rows_a, int rows_b,
-                                                       int shift, int gstride, int mode) {
+                                                       int shift, int gstride, int mode, int reps,
+                                                       long long* __restrict__ cycles) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
@@ -60,6 +61,8 @@ __global__ void __launch_bounds__(160) tc_probe_kernel(const float* __restrict__
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp == 4 && lane == 0) {
+    const long long t_start = clock64();
+    for (int rep = 0; rep < reps; ++rep) {
     const uint32_t a0 = tc::smem_u32(As), b0 = tc::smem_u32(Bs);
     const uint32_t plane_a = (uint32_t)rows_a * 16u, plane_b = (uint32_t)rows_b * 16u;
     if (mode == 0) {
@@ -78,7 +81,10 @@ __global__ void __launch_bounds__(160) tc_probe_kernel(const float* __restrict__
         tc::mma_bf16(tmem_base, da, db, idesc, s > 0);
       }
     }
+    }
     tc::mma_commit(&bar);
+    tc::mbar_wait(&bar, 0);
+    if (cycles) *cycles = clock64() - t_start;
   }
   if (warp < 4) {
     tc::mbar_wait(&bar, 0);
@@ -99,8 +105,8 @@ __global__ void __launch_bounds__(160) tc_probe_kernel(const float* __restrict__
 
 }  // namespace
 
-extern "C" int gs_tc_probe(const float* a, const float* b, float* d, int k, int n, int rows_a, int rows_b, int shift,
-                           int gstride, int mode, void* stream) {
+static int tc_probe_impl(const float* a, const float* b, float* d, int k, int n, int rows_a, int rows_b, int shift,
+                         int gstride, int mode, int reps, long long* cycles, void* stream) {
   GS_CHECK_ARG(mode == 0 || mode == 1, "tc_probe: mode must be 0 or 1");
   GS_CHECK_ARG(k > 0 && k % 16 == 0 && n >= 16 && n <= 256 && n % 16 == 0, "tc_probe: need K %% 16 == 0, 16 <= N <= 256, N %% 16 == 0");
   GS_CHECK_ARG(gstride >= 8 && shift >= 0, "tc_probe: gstride >= 8, shift >= 0");
@@ -118,7 +124,19 @@ extern "C" int gs_tc_probe(const float* a, const float* b, float* d, int k, int 
   size_t smem = a_bytes + b_bytes;
   GS_CHECK_ARG(smem <= 200 * 1024, "tc_probe: operands need %zu bytes of shared memory", smem);
   GS_CUDA(cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tc_probe_kernel<<<1, 160, smem, (cudaStream_t)stream>>>(a, b, d, k, n, rows_a, rows_b, shift, gstride, mode);
+  tc_probe_kernel<<<1, 160, smem, (cudaStream_t)stream>>>(a, b, d, k, n, rows_a, rows_b, shift, gstride, mode, reps, cycles);
   GS_CHECK_LAUNCH("tc_probe");
   return GS_OK;
+}
+
+extern "C" int gs_tc_probe(const float* a, const float* b, float* d, int k, int n, int rows_a, int rows_b, int shift,
+                           int gstride, int mode, void* stream) {
+  return tc_probe_impl(a, b, d, k, n, rows_a, rows_b, shift, gstride, mode, 1, nullptr, stream);
+}
+// timing variant: the MMA sequence is issued `reps` times back to back by the one issuing thread;
+// *cycles (device) receives the SM clock ticks from first issue to completion
+extern "C" int gs_tc_probe_time(const float* a, const float* b, float* d, int k, int n, int rows_a, int rows_b,
+                                int shift, int gstride, int mode, int reps, long long* cycles, void* stream) {
+  GS_CHECK_ARG(reps >= 1 && cycles != nullptr, "tc_probe_time: reps >= 1 and a cycles pointer are required");
+  return tc_probe_impl(a, b, d, k, n, rows_a, rows_b, shift, gstride, mode, reps, cycles, stream);
 }

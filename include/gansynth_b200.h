@@ -118,6 +118,8 @@ int gs_waveform_fwd(const float* logmel, const float* inst, const float* synth_w
  * core-matrix layout of the tensor-core convolution (see csrc/tc_probe.cu) ------------------------- */
 int gs_tc_probe(const float* a, const float* b, float* d, int k, int n, int rows_a, int rows_b, int shift, int gstride,
                 int mode, void* stream);
+int gs_tc_probe_time(const float* a, const float* b, float* d, int k, int n, int rows_a, int rows_b, int shift,
+                     int gstride, int mode, int reps, long long* cycles, void* stream);
 
 #ifdef __cplusplus
 }
