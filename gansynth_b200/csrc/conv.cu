@@ -193,12 +193,22 @@ int launch_tc_impl(const float* x, const float* w, const float* bias, float* y, 
   p.n_tiles = ndim / nt;
   // shared memory: 2 operand stages + 2 weight stages first, then staging slots for the asynchronous halo
   // prefetch (up to 3), then extra weight stages (up to 4)
-  size_t used = p.sa * a_stage + 2 * b_stage;
+  const int nblk = 9 * (kdim / KC);
+  p.b_resident = (nblk <= TC_MAX_BSTAGES) && ((size_t)p.sa * a_stage + (size_t)nblk * b_stage + 2 * stg <= budget) &&
+                 !getenv("GS_TC_NO_RESIDENT");
+  size_t used;
+  if (p.b_resident) {
+    p.sb = nblk;
+    used = p.sa * a_stage + (size_t)nblk * b_stage;
+  } else {
+    p.sb = 2;
+    used = p.sa * a_stage + 2 * b_stage;
+  }
   p.ds = 0;
   while (p.ds < 3 && used + stg <= budget) { ++p.ds; used += stg; }
   if (p.ds == 0 && used + a_stage <= budget) { ++p.sa; used += a_stage; }   // no prefetch ring: deeper operand ring
-  p.sb = 2;
-  while (p.sb < TC_MAX_STAGES && used + b_stage <= budget) { ++p.sb; used += b_stage; }
+  if (!p.b_resident)
+    while (p.sb < TC_MAX_STAGES && used + b_stage <= budget) { ++p.sb; used += b_stage; }
   if (getenv("GS_TC_NO_PREFETCH")) { p.ds = 0; }
   p.nbuf = (2 * G::NACC * nt <= 512) ? 2 : 1;
   int cols = 32;

@@ -64,12 +64,14 @@ struct TcParams {
   int tap_off[9];
   int sa, sb;                     // ring depths
   int ds;                         // fp32 staging slots of the asynchronous halo prefetch (0: direct loads)
+  int b_resident;                 // weights of this CTA's channel tile are loaded once and kept (sb = 9 * chunks)
   int nbuf;                       // accumulator buffers (1 or 2)
   int tmem_cols;                  // power of two >= nbuf * NACC * nt
 };
 
 constexpr int TC_THREADS = 320;
 constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_MAX_BSTAGES = 18;     // weight ring; 9 * chunks stages when the weights stay resident
 
 // fp32 -> NSPLIT bf16 terms whose sum reproduces x to 2^-17 (2 terms) relative
 template <int NSPLIT>
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
   using G = TcGeo<FORM>;
   constexpr int Q = KC / 8;               // 16-byte channel planes per split term
   extern __shared__ __align__(128) unsigned char tc_smem[];
-  __shared__ uint64_t a_full[TC_MAX_STAGES], a_empty[TC_MAX_STAGES], b_full[TC_MAX_STAGES], b_empty[TC_MAX_STAGES];
+  __shared__ uint64_t a_full[TC_MAX_STAGES], a_empty[TC_MAX_STAGES], b_full[TC_MAX_BSTAGES], b_empty[TC_MAX_BSTAGES];
   __shared__ uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
 
@@ -176,19 +178,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
       n = img0 + slot;
     };
     auto convert_store = [&](unsigned char* st, int ps, const float4 (&v)[CH]) {
+      static_assert(NSPLIT == 2, "the packed split handles the two-term form");
 #pragma unroll
       for (int q = 0; q < Q; ++q) {
-        const float f[8] = {v[2 * q].x, v[2 * q].y, v[2 * q].z, v[2 * q].w, v[2 * q + 1].x, v[2 * q + 1].y, v[2 * q + 1].z, v[2 * q + 1].w};
-        __nv_bfloat16 t2[8][NSPLIT];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) tc_split<NSPLIT>(f[e], t2[e]);
-#pragma unroll
-        for (int sp = 0; sp < NSPLIT; ++sp) {
-          uint4 o;
-          o.x = tc::pack_bf16(t2[0][sp], t2[1][sp]); o.y = tc::pack_bf16(t2[2][sp], t2[3][sp]);
-          o.z = tc::pack_bf16(t2[4][sp], t2[5][sp]); o.w = tc::pack_bf16(t2[6][sp], t2[7][sp]);
-          *reinterpret_cast<uint4*>(st + (size_t)(sp * Q + q) * plane_a + (size_t)ps * 16) = o;
-        }
+        uint4 h4, l4;
+        tc::split2_bf16(v[2 * q].x, v[2 * q].y, h4.x, l4.x);
+        tc::split2_bf16(v[2 * q].z, v[2 * q].w, h4.y, l4.y);
+        tc::split2_bf16(v[2 * q + 1].x, v[2 * q + 1].y, h4.z, l4.z);
+        tc::split2_bf16(v[2 * q + 1].z, v[2 * q + 1].w, h4.w, l4.w);
+        *reinterpret_cast<uint4*>(st + (size_t)q * plane_a + (size_t)ps * 16) = h4;
+        *reinterpret_cast<uint4*>(st + (size_t)(Q + q) * plane_a + (size_t)ps * 16) = l4;
       }
     };
     int stage = 0;
@@ -278,9 +277,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
       uint32_t phase = 0;
       const size_t src_plane = (size_t)p.ndim * 16;          // bytes of one [n][8] plane in wprep
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        if (p.b_resident && tile != (int)blockIdx.x) break;     // resident weights: one pass fills every stage
         for (int kc = 0; kc < nchunks; ++kc) {
           for (int tap = 0; tap < 9; ++tap) {
-            tc::mbar_wait(&b_empty[stage], phase ^ 1u);
+            if (!p.b_resident) tc::mbar_wait(&b_empty[stage], phase ^ 1u);
             tc::mbar_arrive_expect_tx(&b_full[stage], b_stage_bytes);
             const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wprep) +
                                        ((size_t)kc * 9 + tap) * (NSPLIT * Q) * src_plane + (size_t)n0 * 16;
@@ -300,8 +300,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
     // ============================== MMA issue ==========================================================
     // One thread feeds the tensor core.  With N = 32 an MMA is only ~16 cycles of tensor work, so the
     // issue loop is kept to an add or two per MMA: descriptors are a per-stage base (start address in
-    // 16-byte units in the low word) plus tap / K-slice / split offsets.
-    if (lane == 0) {
+    // 16-byte units in the low word) plus tap / K-slice / split offsets.  The WHOLE warp runs this control
+    // flow (so the compiler keeps descriptors in uniform registers); one elected lane issues.
+    {
       const uint32_t idesc = tc::idesc_bf16_f32(p.nt, 0, 0);
       const uint64_t a_desc0 = tc::smem_desc(tc::smem_u32(a_smem), plane_a, G::GSTRIDE * 16u);
       const uint64_t b_desc0 = tc::smem_desc(tc::smem_u32(b_smem), plane_b, 128u);
@@ -309,6 +310,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
       const uint32_t plane_a16 = plane_a >> 4, plane_b16 = plane_b >> 4;
       int sa = 0, sb = 0, ab = 0;
       uint32_t pa = 0, pb = 0, pacc = 0;
+      bool b_ready = false;                          // resident weights: waited for once
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         tc::mbar_wait(&acc_empty[ab], pacc ^ 1u);
         tc::tc_fence_after();
@@ -320,35 +322,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
           const uint32_t acc_rest = (kc > 0) ? 1u : 0u;
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            tc::mbar_wait(&b_full[sb], pb);
-            tc::tc_fence_after();
+            if (!b_ready) {
+              tc::mbar_wait(&b_full[sb], pb);
+              tc::tc_fence_after();
+            }
             const uint64_t b_base = b_desc0 + (uint64_t)((uint32_t)sb * b_stage16);
             const int acc = G::tap_acc(tap);
             const uint32_t d = d0 + (uint32_t)(acc * p.nt);
             const uint64_t a_tap = a_base + (uint64_t)(uint32_t)p.tap_off[tap];
             // the first tap that touches an accumulator overwrites it on the first channel chunk
             const bool opens = (G::NACC == 1) ? (tap == 0) : (tap == 0 || tap == 1 || tap == 3 || tap == 4);
+            if (tc::elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < KC / 16; ++ks) {
-              constexpr int NPROD = (NSPLIT == 2) ? 3 : 6;
-              constexpr int PA[6] = {0, 0, 1, 0, 2, 1};
-              constexpr int PB[6] = {0, 1, 0, 2, 0, 1};
+              for (int ks = 0; ks < KC / 16; ++ks) {
+                constexpr int NPROD = (NSPLIT == 2) ? 3 : 6;
+                constexpr int PA[6] = {0, 0, 1, 0, 2, 1};
+                constexpr int PB[6] = {0, 1, 0, 2, 0, 1};
 #pragma unroll
-              for (int pr = 0; pr < NPROD; ++pr) {
-                const uint64_t da = a_tap + (uint64_t)((uint32_t)(PA[pr] * Q + 2 * ks) * plane_a16);
-                const uint64_t db = b_base + (uint64_t)((uint32_t)(PB[pr] * Q + 2 * ks) * plane_b16);
-                const uint32_t accum = (opens && ks == 0 && pr == 0) ? acc_rest : 1u;
-                tc::mma_bf16(d, da, db, idesc, accum);
+                for (int pr = 0; pr < NPROD; ++pr) {
+                  const uint64_t da = a_tap + (uint64_t)((uint32_t)(PA[pr] * Q + 2 * ks) * plane_a16);
+                  const uint64_t db = b_base + (uint64_t)((uint32_t)(PB[pr] * Q + 2 * ks) * plane_b16);
+                  const uint32_t accum = (opens && ks == 0 && pr == 0) ? acc_rest : 1u;
+                  tc::mma_bf16(d, da, db, idesc, accum);
+                }
+              }
+              if (!p.b_resident) tc::mma_commit(&b_empty[sb]);
+              if (tap == 8) {
+                tc::mma_commit(&a_empty[sa]);
+                if (kc == nchunks - 1) tc::mma_commit(&acc_full[ab]);
               }
             }
-            tc::mma_commit(&b_empty[sb]);
+            __syncwarp();
             if (++sb == p.sb) { sb = 0; pb ^= 1u; }
           }
-          tc::mma_commit(&a_empty[sa]);
           if (++sa == p.sa) { sa = 0; pa ^= 1u; }
         }
-        tc::mma_commit(&acc_full[ab]);
         if (++ab == p.nbuf) { ab = 0; pacc ^= 1u; }
+        if (p.b_resident) b_ready = true;
       }
     }
   } else {

@@ -146,15 +146,11 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const TcwParam
         for (int q = 0; q < q_cnt; ++q) {
           const float4 v0 = *reinterpret_cast<const float4*>(row + (size_t)(((2 * q) ^ (ps & 7)) * 16));
           const float4 v1 = *reinterpret_cast<const float4*>(row + (size_t)(((2 * q + 1) ^ (ps & 7)) * 16));
-          const float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-          __nv_bfloat16 hi[8], lo[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) tc::split_bf16(f[e], hi[e], lo[e]);
           uint4 h4, l4;
-          h4.x = tc::pack_bf16(hi[0], hi[1]); h4.y = tc::pack_bf16(hi[2], hi[3]);
-          h4.z = tc::pack_bf16(hi[4], hi[5]); h4.w = tc::pack_bf16(hi[6], hi[7]);
-          l4.x = tc::pack_bf16(lo[0], lo[1]); l4.y = tc::pack_bf16(lo[2], lo[3]);
-          l4.z = tc::pack_bf16(lo[4], lo[5]); l4.w = tc::pack_bf16(lo[6], lo[7]);
+          tc::split2_bf16(v0.x, v0.y, h4.x, l4.x);
+          tc::split2_bf16(v0.z, v0.w, h4.y, l4.y);
+          tc::split2_bf16(v1.x, v1.y, h4.z, l4.z);
+          tc::split2_bf16(v1.z, v1.w, h4.w, l4.w);
           if (!expand) {
             *reinterpret_cast<uint4*>(st + (size_t)q * plane + (size_t)ps * 16) = h4;
             *reinterpret_cast<uint4*>(st + (size_t)(q_cnt + q) * plane + (size_t)ps * 16) = l4;
@@ -234,9 +230,10 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const TcwParam
         }
       }
     }
-  } else if (lane == 0) {
+  } else {
     // ============================== MMA issue ==========================================================
     // Descriptors = per-stage base + tap offset + k-step stride, all in 16-byte units in the low word.
+    // The whole warp runs the control flow (uniform registers); one elected lane issues.
     const uint32_t idesc = tc::idesc_bf16_f32(p.nt, 1, 1);
     const uint32_t stage16 = p.stage_bytes >> 4;
     const int ksteps = p.tpr / 2;
@@ -258,25 +255,28 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const TcwParam
         tc::tc_fence_after();
         const uint64_t m_base = m_desc0 + (uint64_t)((uint32_t)stage * stage16);
         const uint64_t n_base = n_desc0 + (uint64_t)((uint32_t)stage * stage16);
-        for (int kh = 0; kh < 3; ++kh) {
-          for (int t = 0; t < p.m_tiles; ++t) {
-            uint64_t a_hi = m_base + (uint64_t)((uint32_t)kh * 8u + (uint32_t)t * mtile16);
-            uint64_t b_hi = n_base;
-            const uint32_t d = tmem_base + (uint32_t)((kh * p.m_tiles + t) * p.nt);
-            uint32_t accum = accum_first;
+        if (tc::elect_one()) {
+          for (int kh = 0; kh < 3; ++kh) {
+            for (int t = 0; t < p.m_tiles; ++t) {
+              uint64_t a_hi = m_base + (uint64_t)((uint32_t)kh * 8u + (uint32_t)t * mtile16);
+              uint64_t b_hi = n_base;
+              const uint32_t d = tmem_base + (uint32_t)((kh * p.m_tiles + t) * p.nt);
+              uint32_t accum = accum_first;
 #pragma unroll 2
-            for (int j = 0; j < ksteps; ++j) {
-              tc::mma_bf16(d, a_hi, b_hi, idesc, accum);
-              tc::mma_bf16(d, a_hi, b_hi + n_lo16, idesc, 1u);
-              tc::mma_bf16(d, a_hi + split_lo16, b_hi, idesc, 1u);
-              accum = 1u;
-              a_hi += big_step16;
-              b_hi += 16u;
+              for (int j = 0; j < ksteps; ++j) {
+                tc::mma_bf16(d, a_hi, b_hi, idesc, accum);
+                tc::mma_bf16(d, a_hi, b_hi + n_lo16, idesc, 1u);
+                tc::mma_bf16(d, a_hi + split_lo16, b_hi, idesc, 1u);
+                accum = 1u;
+                a_hi += big_step16;
+                b_hi += 16u;
+              }
             }
           }
+          tc::mma_commit(&empty[stage]);
         }
+        __syncwarp();
         accum_first = 1u;
-        tc::mma_commit(&empty[stage]);
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     } else {
@@ -292,29 +292,33 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const TcwParam
         tc::tc_fence_after();
         const uint64_t m_base = m_desc0 + (uint64_t)((uint32_t)stage * stage16);
         const uint64_t n_base = n_desc0 + (uint64_t)((uint32_t)stage * stage16);
-        for (int tl = 0; tl < ntap; ++tl) {
-          const int tap = tap0 + tl, kh = tap / 3, kw = tap % 3;
-          const uint32_t tap16 = (p.stride == 1) ? (uint32_t)(kh * 10 + kw) : (uint32_t)(kh * 17 + (kw & 1) * 9 + (kw >> 1));
-          uint64_t a_hi = m_base + (uint64_t)(p.big_is_m ? tap16 : 0u);
-          uint64_t b_hi = n_base + (uint64_t)(p.big_is_m ? 0u : tap16);
-          const uint32_t d = tmem_base + (uint32_t)(tl * p.nt);
-          uint32_t accum = accum_first;
+        if (tc::elect_one()) {
+          for (int tl = 0; tl < ntap; ++tl) {
+            const int tap = tap0 + tl, kh = tap / 3, kw = tap % 3;
+            const uint32_t tap16 = (p.stride == 1) ? (uint32_t)(kh * 10 + kw) : (uint32_t)(kh * 17 + (kw & 1) * 9 + (kw >> 1));
+            uint64_t a_hi = m_base + (uint64_t)(p.big_is_m ? tap16 : 0u);
+            uint64_t b_hi = n_base + (uint64_t)(p.big_is_m ? 0u : tap16);
+            const uint32_t d = tmem_base + (uint32_t)(tl * p.nt);
+            uint32_t accum = accum_first;
 #pragma unroll 2
-          for (int j = 0; j < ksteps; ++j) {
-            tc::mma_bf16(d, a_hi, b_hi, idesc, accum);
-            tc::mma_bf16(d, a_hi, b_hi + n_lo16, idesc, 1u);
-            tc::mma_bf16(d, a_hi + m_lo16, b_hi, idesc, 1u);
-            accum = 1u;
-            a_hi += m_step16;
-            b_hi += n_step16;
+            for (int j = 0; j < ksteps; ++j) {
+              tc::mma_bf16(d, a_hi, b_hi, idesc, accum);
+              tc::mma_bf16(d, a_hi, b_hi + n_lo16, idesc, 1u);
+              tc::mma_bf16(d, a_hi + m_lo16, b_hi, idesc, 1u);
+              accum = 1u;
+              a_hi += m_step16;
+              b_hi += n_step16;
+            }
           }
+          tc::mma_commit(&empty[stage]);
         }
+        __syncwarp();
         accum_first = 1u;
-        tc::mma_commit(&empty[stage]);
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
-    tc::mma_commit(&done);
+    if (tc::elect_one()) tc::mma_commit(&done);
+    __syncwarp();
   }
 
   tc::tc_fence_before();
