@@ -7,6 +7,7 @@
 #include "conv_tc.cuh"
 #include "conv_tcw.cuh"
 #include "conv_tiled.cuh"
+#include "tma_host.h"
 #include "gansynth_b200.h"
 
 namespace {
@@ -147,11 +148,11 @@ bool tc_ok(int form, int ksize, int kdim, int ndim, int th_dim, int tw_dim) {
   return rows_ok && tw_dim % 8 == 0;
 }
 
-template <int FORM, int NSPLIT, int KC>
+template <int FORM, int KC>
 int launch_tc_impl(const float* x, const float* w, const float* bias, float* y, int n, int h_in, int w_in, int h_out,
                    int w_out, int kdim, int ndim, int w_is_kn, int flip, float alpha, int act, cudaStream_t st) {
   using G = TcGeo<FORM>;
-  const size_t wbytes = (size_t)9 * kdim * ndim * NSPLIT * sizeof(__nv_bfloat16);
+  const size_t wbytes = (size_t)9 * kdim * ndim * 2 * sizeof(__nv_bfloat16);
   if (g_tc_ws.bytes < wbytes) {
     GS_CUDA(cudaStreamSynchronize(st));
     if (g_tc_ws.buf) GS_CUDA(cudaFree(g_tc_ws.buf));
@@ -159,15 +160,8 @@ int launch_tc_impl(const float* x, const float* w, const float* bias, float* y, 
     GS_CUDA(cudaMalloc(&g_tc_ws.buf, want));
     g_tc_ws.bytes = want;
   }
-  {
-    size_t total = (size_t)9 * kdim * ndim;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > gs_num_sms() * 8) blocks = gs_num_sms() * 8;
-    conv_tc_prep_kernel<NSPLIT, KC><<<blocks, 256, 0, st>>>(w, g_tc_ws.buf, kdim, ndim, w_is_kn, flip);
-    GS_CHECK_LAUNCH("conv_tc_prep");
-  }
   TcParams p;
-  p.x = x; p.wprep = g_tc_ws.buf; p.bias = bias; p.y = y;
+  p.wprep = g_tc_ws.buf; p.bias = bias; p.y = y;
   p.n_img = n; p.h_in = h_in; p.w_in = w_in; p.h_out = h_out; p.w_out = w_out; p.kdim = kdim; p.ndim = ndim;
   p.alpha = alpha; p.act = act;
   const int th_dim = (FORM == TC_T2) ? h_in : h_out, tw_dim = (FORM == TC_T2) ? w_in : w_out;
@@ -176,56 +170,77 @@ int launch_tc_impl(const float* x, const float* w, const float* bias, float* y, 
   p.tiles_w = tw_dim / 8;
   p.ntiles = ((n + p.img - 1) / p.img) * p.tiles_h * p.tiles_w;
   p.pix = G::pixels(p.rows, p.img);
+  const int box_h = G::box_h(p.rows), box_w = G::box_w();
+  p.rpix = box_h * p.img * box_w;
   for (int t = 0; t < 9; ++t) p.tap_off[t] = G::tap_off(t, p.img);
   // output-channel tile: all channels when there are enough pixel tiles to fill the GPU, else split so
   // that more SMs share the layer (each CTA re-reads the same halo, the weights are partitioned)
   int nt = ndim;
   if (G::NACC * nt > 512) nt = 512 / G::NACC;
-  while (nt > 64 && nt % 64 == 0 && (long long)p.ntiles * (ndim / nt) < gs_num_sms()) nt /= 2;
-  const size_t budget = 222 * 1024;
-  const size_t a_stage = (size_t)NSPLIT * (KC / 8) * p.pix * 16;
-  const size_t stg = (size_t)p.pix * KC * 4;
+  while (nt > 32 && nt % 64 == 0 && (long long)p.ntiles * (ndim / nt) < gs_num_sms()) nt /= 2;
+  const size_t budget = 222 * 1024 - 1024 - (FORM == TC_C2 ? 2048 : 0);   // alignment slack, parity table
+  const size_t a_stage = (size_t)p.pix * KC * 4;
+  const size_t raw = (((size_t)p.rpix * KC * 4) + 1023) & ~(size_t)1023;
+  p.raw_slot_bytes = (uint32_t)raw;
   p.sa = 2;
-  while (nt > 32 && (size_t)p.sa * a_stage + 2 * (size_t)NSPLIT * (KC / 8) * nt * 16 > budget) nt /= 2;
-  const size_t b_stage = (size_t)NSPLIT * (KC / 8) * nt * 16;
-  GS_CHECK_ARG((size_t)p.sa * a_stage + 2 * b_stage <= budget, "conv_tc: shared memory budget exceeded (ndim %d)", ndim);
+  // weights: resident when every (chunk, tap) block fits beside two raw slots; else streamed in the
+  // largest tap group (9, 3, 1) that leaves room for two stages
+  const int nchunks = kdim / KC;
+  size_t b_tap = 0;
+  for (;; nt /= 2) {
+    b_tap = (size_t)4 * KC * nt;
+    if (p.sa * a_stage + 2 * raw + 2 * b_tap <= budget || nt <= 32) break;
+  }
+  GS_CHECK_ARG(p.sa * a_stage + 2 * raw + 2 * b_tap <= budget, "conv_tc: shared memory budget exceeded (ndim %d)", ndim);
   p.nt = nt;
   p.n_tiles = ndim / nt;
-  // shared memory: 2 operand stages + 2 weight stages first, then staging slots for the asynchronous halo
-  // prefetch (up to 3), then extra weight stages (up to 4)
-  const int nblk = 9 * (kdim / KC);
-  p.b_resident = (nblk <= TC_MAX_BSTAGES) && ((size_t)p.sa * a_stage + (size_t)nblk * b_stage + 2 * stg <= budget) &&
-                 !getenv("GS_TC_NO_RESIDENT");
-  size_t used;
+  size_t used = p.sa * a_stage + 2 * raw;
+  p.ds = 2;
+  p.b_resident = (nchunks <= TC_MAX_BSTAGES) && (used + (size_t)nchunks * 9 * b_tap <= budget) && !getenv("GS_TC_NO_RESIDENT");
   if (p.b_resident) {
-    p.sb = nblk;
-    used = p.sa * a_stage + (size_t)nblk * b_stage;
+    p.tps = 9;
+    p.sb = nchunks;
+    used += (size_t)nchunks * 9 * b_tap;
   } else {
+    p.tps = 1;
+    if (used + 2 * 9 * b_tap <= budget) p.tps = 9;
+    else if (used + 2 * 3 * b_tap <= budget) p.tps = 3;
     p.sb = 2;
-    used = p.sa * a_stage + 2 * b_stage;
+    used += 2 * (size_t)p.tps * b_tap;
   }
-  p.ds = 0;
-  while (p.ds < 3 && used + stg <= budget) { ++p.ds; used += stg; }
-  if (p.ds == 0 && used + a_stage <= budget) { ++p.sa; used += a_stage; }   // no prefetch ring: deeper operand ring
+  // spare room: a third raw slot (HBM latency) first, then deeper weight ring, then a fourth raw slot
+  if (used + raw <= budget) { ++p.ds; used += raw; }
   if (!p.b_resident)
-    while (p.sb < TC_MAX_STAGES && used + b_stage <= budget) { ++p.sb; used += b_stage; }
-  if (getenv("GS_TC_NO_PREFETCH")) { p.ds = 0; }
+    while (p.sb < 4 && used + (size_t)p.tps * b_tap <= budget) { ++p.sb; used += (size_t)p.tps * b_tap; }
+  if (used + raw <= budget) { ++p.ds; used += raw; }
   p.nbuf = (2 * G::NACC * nt <= 512) ? 2 : 1;
   int cols = 32;
   while (cols < p.nbuf * G::NACC * nt) cols <<= 1;
   p.tmem_cols = cols;
-  const size_t smem = p.sa * a_stage + p.sb * b_stage + p.ds * stg;
-  auto kern = conv_tc_kernel<FORM, NSPLIT, KC>;
+  {
+    size_t total = (size_t)9 * kdim * ndim;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > gs_num_sms() * 8) blocks = gs_num_sms() * 8;
+    conv_tc_prep_kernel<KC><<<blocks, 256, 0, st>>>(w, g_tc_ws.buf, kdim, ndim, nt, w_is_kn, flip);
+    GS_CHECK_LAUNCH("conv_tc_prep");
+  }
+  CUtensorMap tmx;
+  {
+    int rc = gs_make_act_tmap(&tmx, x, n, h_in, w_in, kdim, KC, box_w, p.img, box_h, KC * 4);
+    if (rc) return rc;
+  }
+  const size_t smem = used + 1024 + (FORM == TC_C2 ? 2048 : 0);
+  auto kern = conv_tc_kernel<FORM, KC>;
   static bool attr = false;
   if (!attr) {
-    GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
     attr = true;
   }
   int gx = gs_num_sms() / p.n_tiles;
   if (gx < 1) gx = 1;
   if (gx > p.ntiles) gx = p.ntiles;
   dim3 grid((unsigned)gx, (unsigned)p.n_tiles);
-  kern<<<grid, TC_THREADS, smem, st>>>(p);
+  kern<<<grid, TC_THREADS, smem, st>>>(tmx, p);
   GS_CHECK_LAUNCH("conv_tc");
   return GS_OK;
 }
@@ -236,10 +251,10 @@ int launch_tc_impl(const float* x, const float* w, const float* bias, float* y, 
 template <int FORM>
 int launch_tc(const float* x, const float* w, const float* bias, float* y, int n, int h_in, int w_in, int h_out,
               int w_out, int kdim, int ndim, int w_is_kn, int flip, float alpha, int act, cudaStream_t st) {
-  // the stride-2 gather form stages ~4x the pixels of the others: 16-channel chunks keep a prefetch ring in budget
+  // the stride-2 gather form stages ~4x the pixels of the others: 16-channel chunks keep the rings in budget
   if (FORM == TC_C2)
-    return launch_tc_impl<FORM, 2, 16>(x, w, bias, y, n, h_in, w_in, h_out, w_out, kdim, ndim, w_is_kn, flip, alpha, act, st);
-  return launch_tc_impl<FORM, 2, 32>(x, w, bias, y, n, h_in, w_in, h_out, w_out, kdim, ndim, w_is_kn, flip, alpha, act, st);
+    return launch_tc_impl<FORM, 16>(x, w, bias, y, n, h_in, w_in, h_out, w_out, kdim, ndim, w_is_kn, flip, alpha, act, st);
+  return launch_tc_impl<FORM, 32>(x, w, bias, y, n, h_in, w_in, h_out, w_out, kdim, ndim, w_is_kn, flip, alpha, act, st);
 }
 
 // filter-gradient form on the tensor cores
