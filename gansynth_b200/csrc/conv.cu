@@ -178,44 +178,56 @@ int launch_tc_impl(const float* x, const float* w, const float* bias, float* y, 
   int nt = ndim;
   if (G::NACC * nt > 512) nt = 512 / G::NACC;
   while (nt > 32 && nt % 64 == 0 && (long long)p.ntiles * (ndim / nt) < gs_num_sms()) nt /= 2;
-  const size_t budget = 222 * 1024 - 1024 - (FORM == TC_C2 ? 2048 : 0);   // alignment slack, parity table
+  const size_t budget = 222 * 1024 - 1024 - 2 * 16384 - (FORM == TC_C2 ? 2048 : 0);   // alignment slack, output staging, parity table
   const size_t a_stage = (size_t)p.pix * KC * 4;
   const size_t raw = (((size_t)p.rpix * KC * 4) + 1023) & ~(size_t)1023;
   p.raw_slot_bytes = (uint32_t)raw;
   p.sa = 2;
+  p.ds = 2;
   // weights: resident when every (chunk, tap) block fits beside two raw slots; else streamed in the
   // largest tap group (9, 3, 1) that leaves room for two stages
   const int nchunks = kdim / KC;
   size_t b_tap = 0;
   for (;; nt /= 2) {
     b_tap = (size_t)4 * KC * nt;
-    if (p.sa * a_stage + 2 * raw + 2 * b_tap <= budget || nt <= 32) break;
+    if (p.sa * a_stage + p.ds * raw + 2 * b_tap <= budget || nt <= 32) break;
   }
-  GS_CHECK_ARG(p.sa * a_stage + 2 * raw + 2 * b_tap <= budget, "conv_tc: shared memory budget exceeded (ndim %d)", ndim);
+  // the widest staged tiles (stride-2 form on interleaved low-resolution images): single-buffered rings
+  if (p.sa * a_stage + p.ds * raw + 2 * b_tap > budget) p.sa = 1;
+  if (p.sa * a_stage + p.ds * raw + 2 * b_tap > budget) p.ds = 1;
+  GS_CHECK_ARG(p.sa * a_stage + p.ds * raw + 2 * b_tap <= budget, "conv_tc: shared memory budget exceeded (ndim %d)", ndim);
   p.nt = nt;
   p.n_tiles = ndim / nt;
-  size_t used = p.sa * a_stage + 2 * raw;
-  p.ds = 2;
+  size_t used = p.sa * a_stage + p.ds * raw;
   p.b_resident = (nchunks <= TC_MAX_BSTAGES) && (used + (size_t)nchunks * 9 * b_tap <= budget) && !getenv("GS_TC_NO_RESIDENT");
+  int tps = 1;
   if (p.b_resident) {
-    p.tps = 9;
+    tps = 9;
     p.sb = nchunks;
     used += (size_t)nchunks * 9 * b_tap;
   } else {
-    p.tps = 1;
-    if (used + 2 * 9 * b_tap <= budget) p.tps = 9;
-    else if (used + 2 * 3 * b_tap <= budget) p.tps = 3;
+    if (used + 2 * 9 * b_tap <= budget) tps = 9;
+    else if (used + 2 * 3 * b_tap <= budget) tps = 3;
     p.sb = 2;
-    used += 2 * (size_t)p.tps * b_tap;
+    used += 2 * (size_t)tps * b_tap;
   }
-  // spare room: a third raw slot (HBM latency) first, then deeper weight ring, then a fourth raw slot
+  // spare room: a third raw slot (HBM latency) and a third operand stage (two issuing warps) first, then
+  // a deeper weight ring, then a fourth raw slot / operand stage
   if (used + raw <= budget) { ++p.ds; used += raw; }
+  if (used + a_stage <= budget) { ++p.sa; used += a_stage; }
   if (!p.b_resident)
-    while (p.sb < 4 && used + (size_t)p.tps * b_tap <= budget) { ++p.sb; used += (size_t)p.tps * b_tap; }
+    while (p.sb < 4 && used + (size_t)tps * b_tap <= budget) { ++p.sb; used += (size_t)tps * b_tap; }
   if (used + raw <= budget) { ++p.ds; used += raw; }
+  if (used + a_stage <= budget) { ++p.sa; used += a_stage; }
   p.nbuf = (2 * G::NACC * nt <= 512) ? 2 : 1;
+  p.cat = (4 * G::NACC * nt <= 512) && !getenv("GS_TC_NO_CAT");
+  p.nw = (p.nbuf == 2 && getenv("GS_TC_TWO_MMA_WARPS")) ? 2 : 1;   // measured: a second issuing warp buys nothing
+  if (p.nw == 2) {   // each issuing warp owns every other stage
+    p.sa &= ~1;
+    if (!p.b_resident) p.sb &= ~1;
+  }
   int cols = 32;
-  while (cols < p.nbuf * G::NACC * nt) cols <<= 1;
+  while (cols < p.nbuf * G::NACC * nt * (1 + p.cat)) cols <<= 1;
   p.tmem_cols = cols;
   {
     size_t total = (size_t)9 * kdim * ndim;
@@ -225,22 +237,38 @@ int launch_tc_impl(const float* x, const float* w, const float* bias, float* y, 
     GS_CHECK_LAUNCH("conv_tc_prep");
   }
   CUtensorMap tmx;
+  TcOutMaps tmy;
   {
     int rc = gs_make_act_tmap(&tmx, x, n, h_in, w_in, kdim, KC, box_w, p.img, box_h, KC * 4);
     if (rc) return rc;
+    if (FORM == TC_T2) {
+      // four sub-pixel phases: strided views of y, one accumulator each
+      for (int a = 0; a < 4; ++a) {
+        rc = gs_make_act_tmap(&tmy.m[a], y + ((size_t)(a >> 1) * w_out + (a & 1)) * ndim, n, h_out / 2, w_out / 2, ndim, 32, 8,
+                              p.img, p.rows, 128, 2, 2);
+        if (rc) return rc;
+      }
+    } else {
+      rc = gs_make_act_tmap(&tmy.m[0], y, n, h_out, w_out, ndim, 32, 8, p.img, p.rows, 128);
+      if (rc) return rc;
+      for (int a = 1; a < 4; ++a) tmy.m[a] = tmy.m[0];
+    }
   }
-  const size_t smem = used + 1024 + (FORM == TC_C2 ? 2048 : 0);
-  auto kern = conv_tc_kernel<FORM, KC>;
-  static bool attr = false;
-  if (!attr) {
+  const size_t smem = used + 1024 + 2 * 16384 + (FORM == TC_C2 ? 2048 : 0);
+  auto kern = conv_tc_kernel<FORM, KC, 9, 0>;
+  if (p.cat) kern = tps == 9 ? conv_tc_kernel<FORM, KC, 9, 1> : tps == 3 ? conv_tc_kernel<FORM, KC, 3, 1> : conv_tc_kernel<FORM, KC, 1, 1>;
+  else kern = tps == 9 ? conv_tc_kernel<FORM, KC, 9, 0> : tps == 3 ? conv_tc_kernel<FORM, KC, 3, 0> : conv_tc_kernel<FORM, KC, 1, 0>;
+  static bool attr[6] = {false, false, false, false, false, false};
+  const int ai = (tps == 9 ? 0 : tps == 3 ? 1 : 2) + 3 * p.cat;
+  if (!attr[ai]) {
     GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
-    attr = true;
+    attr[ai] = true;
   }
   int gx = gs_num_sms() / p.n_tiles;
   if (gx < 1) gx = 1;
   if (gx > p.ntiles) gx = p.ntiles;
   dim3 grid((unsigned)gx, (unsigned)p.n_tiles);
-  kern<<<grid, TC_THREADS, smem, st>>>(tmx, p);
+  kern<<<grid, TC_THREADS, smem, st>>>(tmx, tmy, p);
   GS_CHECK_LAUNCH("conv_tc");
   return GS_OK;
 }

@@ -7,7 +7,8 @@
 //   HBM --TMA tiled load, fp32 halo box, hardware zero fill outside the image--> raw ring (128B / 64B swizzle)
 //       --8 converter warps: fp32 -> (bf16 hi, bf16 lo)--> operand ring: 16-byte channel vectors, pixel-major
 //         ("SWIZZLE_NONE core matrices": plane q = channels 8q..8q+7, 16 bytes per pixel)
-//       --tcgen05.mma, one elected thread--> TMEM accumulators --4 epilogue warps--> alpha, bias, leaky-relu --> HBM
+//       --tcgen05.mma, one elected thread--> TMEM accumulators --4 epilogue warps--> alpha, bias, leaky-relu
+//       --> swizzled staging tile --TMA tiled store (clipped at the tensor edge)--> HBM
 //
 // In the operand layout every filter tap is just a different START ADDRESS of the same staged tile (group
 // stride fixed), so the nine taps cost nine descriptor pairs, not nine loads.  Each 16-channel K slice
@@ -15,8 +16,18 @@
 // ~1e-5 relative at K = 2304, tools/tc_precision.py).  Weights are pre-split into the same layout by
 // conv_tc_prep_kernel, contiguous per (output-channel tile, chunk), and streamed with 1-D bulk copies in
 // groups of `tps` taps (or loaded once and kept when they fit).
-// Warp roles: 0-3 epilogue, 4-11 converters, 12 TMA halo loads, 13 weight copies, 14 MMA issue + TMEM
-// allocation.  Rings: raw (TMA -> converters), A (converters -> MMA), B (weights), accumulators (per tile).
+// Warp roles: 0-3 epilogue, 4-11 converters, 12 TMA halo loads, 13 weight copies, 14-15 MMA issue (14 also
+// owns the TMEM allocation).  Rings: raw (TMA -> converters), A (converters -> MMA), B (weights),
+// accumulators (per tile).
+//
+// MMA issue rate.  With 32 output channels one MMA is ~16 cycles of tensor work, less than a single warp
+// needs to ISSUE it (measured: ~7 cycles per instruction of the issuing warp, profiles/).  Two remedies:
+//  * "cat" mode: the weight planes are stored [q][hi | lo], so hi*[hi | lo] is ONE MMA of width 2*NT into
+//    a double-width accumulator (the epilogue adds the halves) followed by lo*hi of width NT: two
+//    instructions per K slice instead of three, same tensor work;
+//  * two issuing warps that alternate TILES (each with its own accumulator buffer and its own half of the
+//    operand / weight rings: stages w, w + 2, ... belong to issuing warp w, so every ring stays
+//    single-producer single-consumer and the mbarrier parities never skip a phase).
 //
 // Tiles.  Images with >= 16 rows: 16 rows x 8 columns of one image.  Smaller images (8, 4, 2 rows: the
 // 256-channel low-resolution blocks) interleave IMG = 16 / rows images row by row -- group g = row * IMG
@@ -61,7 +72,7 @@ struct TcGeo {
 };
 
 struct TcParams {
-  const __nv_bfloat16* wprep;     // [ndim/nt][kdim/KC][9][2][KC/8][nt][8]
+  const __nv_bfloat16* wprep;     // [ndim/nt][kdim/KC][9][KC/8][2][nt][8]
   const float* bias;              // [ndim] or null
   float* y;                       // [n, h_out, w_out, ndim]
   int n_img, h_in, w_in, h_out, w_out, kdim, ndim;
@@ -74,20 +85,27 @@ struct TcParams {
   int nt, n_tiles;                // output-channel tile (grid.y)
   int tap_off[9];
   int sa, sb, ds;                 // ring depths: operand stages, weight stages, raw slots
-  int tps;                        // taps per weight stage (9, 3 or 1)
+  int cat;                        // hi x [hi | lo] as one double-width MMA (accumulator = 2 * nt columns)
+  int nw;                         // MMA-issuing warps (1 or 2)
   int b_resident;                 // the weights of this CTA's channel tile are loaded once and kept
   int nbuf;                       // accumulator buffers (1 or 2)
-  int tmem_cols;                  // power of two >= nbuf * NACC * nt
+  int tmem_cols;                  // power of two >= nbuf * NACC * nt * (1 + cat)
   uint32_t raw_slot_bytes;        // 1024-byte aligned
 };
 
-constexpr int TC_THREADS = 480;
+// Output tensor maps: one per accumulator (sub-pixel phase of the transposed form; a strided view of y)
+struct TcOutMaps {
+  CUtensorMap m[4];
+};
+
+constexpr int TC_THREADS = 512;
+constexpr int TC_MMA_WARP0 = 14, TC_MMA_WARPS = 2;
 constexpr int TC_CONV_WARPS = 8;
 constexpr int TC_MAX_STAGES = 4;       // raw and operand rings
 constexpr int TC_MAX_BSTAGES = 24;     // weight ring (all (chunk, tap group) blocks when resident)
 
 // Weight pre-pass: W_eff[tap][k][n] (k = contraction channel, n = output channel) -> bf16 split blocks
-// [n / nt][k / KC][tap][split][q][n % nt][e], value index k = KC*kc + 8*q + e.  w_is_kn: weight memory is
+// [n / nt][k / KC][tap][q][split][n % nt][e], value index k = KC*kc + 8*q + e.  w_is_kn: weight memory is
 // [tap][k][n] (else [tap][n][k]); flip: use tap 8 - t (180-degree rotation).
 template <int KC>
 __global__ void conv_tc_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int kdim, int ndim,
@@ -114,13 +132,13 @@ __global__ void conv_tc_prep_kernel(const float* __restrict__ w, __nv_bfloat16* 
     const size_t plane = (size_t)nt * 8;                                   // elements of one [nt][8] plane
     const size_t blk = (((size_t)ntile * nchunks + kc) * 9 + tap) * (2 * Q);   // first plane of this (tile, chunk, tap)
     const size_t inner = (size_t)nl * 8 + e;
-    out[(blk + q) * plane + inner] = hi;
-    out[(blk + Q + q) * plane + inner] = lo;
+    out[(blk + 2 * q) * plane + inner] = hi;
+    out[(blk + 2 * q + 1) * plane + inner] = lo;
   }
 }
 
-template <int FORM, int KC>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const TcParams p) {
+template <int FORM, int KC, int TPS, int CAT>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcOutMaps tmy, const TcParams p) {
   using G = TcGeo<FORM>;
   constexpr int Q = KC / 8;               // 16-byte channel planes per split term
   extern __shared__ unsigned char tc_smem_raw[];
@@ -128,16 +146,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   __shared__ uint64_t b_full[TC_MAX_BSTAGES], b_empty[TC_MAX_BSTAGES];
   __shared__ uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float bias_s[256];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t plane_a = (uint32_t)p.pix * 16u;
   const uint32_t plane_b = (uint32_t)p.nt * 16u;
   const uint32_t a_stage_bytes = (uint32_t)(2 * Q) * plane_a;   // [split][q] planes
   const uint32_t b_tap_bytes = (uint32_t)(2 * Q) * plane_b;
-  const uint32_t b_stage_bytes = (uint32_t)p.tps * b_tap_bytes;
+  const uint32_t b_stage_bytes = (uint32_t)TPS * b_tap_bytes;
   // the swizzled TMA destination needs 1024-byte alignment
   unsigned char* tc_smem = tc_smem_raw + ((1024u - (tc::smem_u32(tc_smem_raw) & 1023u)) & 1023u);
-  unsigned char* raw_smem = tc_smem;
+  unsigned char* out_smem = tc_smem;                        // 2 x [128 pixels][32 channels] fp32, 128B-swizzled
+  unsigned char* raw_smem = tc_smem + 2 * 16384;
   unsigned char* a_smem = raw_smem + (size_t)p.ds * p.raw_slot_bytes;
   unsigned char* b_smem = a_smem + (size_t)p.sa * a_stage_bytes;
   uint16_t* dst_tab = reinterpret_cast<uint16_t*>(b_smem + (size_t)p.sb * b_stage_bytes);   // TC_C2 only
@@ -151,6 +171,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     for (int s = 0; s < 2; ++s) { tc::mbar_init(&acc_full[s], 1); tc::mbar_init(&acc_empty[s], 128); }
     tc::mbar_fence_init();
   }
+  for (int c = tid; c < p.nt; c += TC_THREADS) bias_s[c] = p.bias ? p.bias[blockIdx.y * p.nt + c] : 0.0f;
   if (FORM == TC_C2) {
     // raw pixel (row hr, image slot, column hc) -> staged position: rows in pairs, columns split by parity
     for (int ps = tid; ps < p.rpix; ps += TC_THREADS) {
@@ -159,13 +180,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       dst_tab[ps] = (uint16_t)(((hr >> 1) * p.img + slot) * 34 + (hr & 1) * 17 + (hc & 1) * 9 + (hc >> 1));
     }
   }
-  if (warp == 14) tc::tmem_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
-  if (warp == 12 && lane == 0) tc::prefetch_tmap(&tmx);
+  if (warp == TC_MMA_WARP0) tc::tmem_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
+  if (warp == 12 && lane == 0) {
+    tc::prefetch_tmap(&tmx);
+    for (int a = 0; a < G::NACC; ++a) tc::prefetch_tmap(&tmy.m[a]);
+  }
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  const int acc_cols = G::NACC * p.nt;   // columns per accumulator buffer
+  const int acc_w = CAT ? 2 * p.nt : p.nt;      // columns of one accumulator
+  const int acc_cols = G::NACC * acc_w;           // columns per accumulator buffer
 
   if (warp >= 4 && warp < 12) {
     // ============================== fp32 -> bf16 hi/lo split ===========================================
@@ -175,35 +200,59 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int q = cw % Q;
     constexpr int PSTEP = 32 * (TC_CONV_WARPS / Q);
     const int p_first = (cw / Q) * 32 + lane;
-    int stage = 0, rs = 0;
-    uint32_t aph = 0, rph = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    // operand ring: issuing warp w owns stages w, w + nw, ... (a private single-producer single-consumer ring)
+    const int a_depth = p.sa / p.nw;
+    int apos0 = 0, apos1 = 0, rs = 0, seq = 0;
+    uint32_t aph0 = 0, aph1 = 0, rph = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++seq) {
+      const bool w1 = (p.nw == 2) && (seq & 1);
       for (int kc = 0; kc < nchunks; ++kc) {
+        const int stage = w1 ? 1 + 2 * apos1 : p.nw * apos0;
+        const uint32_t aph = w1 ? aph1 : aph0;
         tc::mbar_wait(&raw_full[rs], rph);
         tc::mbar_wait(&a_empty[stage], aph ^ 1u);
         const unsigned char* raw = raw_smem + (size_t)rs * p.raw_slot_bytes;
         unsigned char* st = a_smem + (size_t)stage * a_stage_bytes;
         unsigned char* st_hi = st + (size_t)q * plane_a;
         unsigned char* st_lo = st + (size_t)(Q + q) * plane_a;
-#pragma unroll 2
-        for (int ps = p_first; ps < p.rpix; ps += PSTEP) {
-          const int sw = (KC == 32) ? (ps & 7) : ((ps >> 1) & 3);
-          const unsigned char* row = raw + (size_t)ps * (KC * 4);
-          const float4 v0 = *reinterpret_cast<const float4*>(row + (((2 * q) ^ sw) << 4));
-          const float4 v1 = *reinterpret_cast<const float4*>(row + (((2 * q + 1) ^ sw) << 4));
-          uint4 h4, l4;
+        // two items per pass: both loads are issued before either conversion
+        for (int ps = p_first; ps < p.rpix; ps += 2 * PSTEP) {
+          const int ps1 = ps + PSTEP;
+          const bool two = ps1 < p.rpix;
+          const int sw0 = (KC == 32) ? (ps & 7) : ((ps >> 1) & 3);
+          const int sw1 = (KC == 32) ? (ps1 & 7) : ((ps1 >> 1) & 3);
+          const unsigned char* row0 = raw + (size_t)ps * (KC * 4);
+          const unsigned char* row1 = raw + (size_t)ps1 * (KC * 4);
+          const float4 v0 = *reinterpret_cast<const float4*>(row0 + (((2 * q) ^ sw0) << 4));
+          const float4 v1 = *reinterpret_cast<const float4*>(row0 + (((2 * q + 1) ^ sw0) << 4));
+          float4 u0 = make_float4(0.f, 0.f, 0.f, 0.f), u1 = u0;
+          if (two) {
+            u0 = *reinterpret_cast<const float4*>(row1 + (((2 * q) ^ sw1) << 4));
+            u1 = *reinterpret_cast<const float4*>(row1 + (((2 * q + 1) ^ sw1) << 4));
+          }
+          uint4 h4, l4, g4, k4;
           tc::split2_bf16(v0.x, v0.y, h4.x, l4.x);
           tc::split2_bf16(v0.z, v0.w, h4.y, l4.y);
           tc::split2_bf16(v1.x, v1.y, h4.z, l4.z);
           tc::split2_bf16(v1.z, v1.w, h4.w, l4.w);
-          const int d = (FORM == TC_C2) ? (int)dst_tab[ps] : ps;
-          *reinterpret_cast<uint4*>(st_hi + (size_t)d * 16) = h4;
-          *reinterpret_cast<uint4*>(st_lo + (size_t)d * 16) = l4;
+          tc::split2_bf16(u0.x, u0.y, g4.x, k4.x);
+          tc::split2_bf16(u0.z, u0.w, g4.y, k4.y);
+          tc::split2_bf16(u1.x, u1.y, g4.z, k4.z);
+          tc::split2_bf16(u1.z, u1.w, g4.w, k4.w);
+          const int d0 = (FORM == TC_C2) ? (int)dst_tab[ps] : ps;
+          *reinterpret_cast<uint4*>(st_hi + (size_t)d0 * 16) = h4;
+          *reinterpret_cast<uint4*>(st_lo + (size_t)d0 * 16) = l4;
+          if (two) {
+            const int d1 = (FORM == TC_C2) ? (int)dst_tab[ps1] : ps1;
+            *reinterpret_cast<uint4*>(st_hi + (size_t)d1 * 16) = g4;
+            *reinterpret_cast<uint4*>(st_lo + (size_t)d1 * 16) = k4;
+          }
         }
         tc::fence_proxy_async();
         tc::mbar_arrive(&a_full[stage]);
         tc::mbar_arrive(&raw_empty[rs]);
-        if (++stage == p.sa) { stage = 0; aph ^= 1u; }
+        if (w1) { if (++apos1 == a_depth) { apos1 = 0; aph1 ^= 1u; } }
+        else { if (++apos0 == a_depth) { apos0 = 0; aph0 ^= 1u; } }
         if (++rs == p.ds) { rs = 0; rph ^= 1u; }
       }
     }
@@ -232,139 +281,175 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   } else if (warp == 13) {
     // ============================== weight blocks: one bulk copy per (chunk, tap group) =================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const int groups = 9 / p.tps;
+      constexpr int groups = 9 / TPS;
       const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.wprep) + (size_t)blockIdx.y * nchunks * 9 * b_tap_bytes;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        if (p.b_resident && tile != (int)blockIdx.x) break;     // resident weights: one pass fills every stage
-        for (int kc = 0; kc < nchunks; ++kc) {
-          for (int gi = 0; gi < groups; ++gi) {
-            if (!p.b_resident) tc::mbar_wait(&b_empty[stage], phase ^ 1u);
+      if (p.b_resident) {
+        // one pass fills every stage; both issuing warps read the same copy
+        for (int i = 0; i < nchunks * groups; ++i) {
+          tc::mbar_arrive_expect_tx(&b_full[i], b_stage_bytes);
+          tc::bulk_g2s(b_smem + (size_t)i * b_stage_bytes, wsrc + (size_t)i * b_stage_bytes, b_stage_bytes, &b_full[i]);
+        }
+      } else {
+        // issuing warp w owns stages w, w + nw, ...
+        const int b_depth = p.sb / p.nw;
+        int bpos0 = 0, bpos1 = 0, seq = 0;
+        uint32_t bph0 = 0, bph1 = 0;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++seq) {
+          const bool w1 = (p.nw == 2) && (seq & 1);
+          for (int i = 0; i < nchunks * groups; ++i) {
+            const int stage = w1 ? 1 + 2 * bpos1 : p.nw * bpos0;
+            tc::mbar_wait(&b_empty[stage], (w1 ? bph1 : bph0) ^ 1u);
             tc::mbar_arrive_expect_tx(&b_full[stage], b_stage_bytes);
-            tc::bulk_g2s(b_smem + (size_t)stage * b_stage_bytes, wsrc + (size_t)(kc * groups + gi) * b_stage_bytes, b_stage_bytes,
-                         &b_full[stage]);
-            if (++stage == p.sb) { stage = 0; phase ^= 1u; }
+            tc::bulk_g2s(b_smem + (size_t)stage * b_stage_bytes, wsrc + (size_t)i * b_stage_bytes, b_stage_bytes, &b_full[stage]);
+            if (w1) { if (++bpos1 == b_depth) { bpos1 = 0; bph1 ^= 1u; } }
+            else { if (++bpos0 == b_depth) { bpos0 = 0; bph0 ^= 1u; } }
           }
         }
       }
     }
-  } else if (warp == 14) {
+  } else if (warp >= TC_MMA_WARP0) {
     // ============================== MMA issue ==========================================================
-    // One thread feeds the tensor core.  With N = 32 an MMA is only ~16 cycles of tensor work, so the
-    // issue loop is kept to an add or two per MMA: descriptors are a per-stage base (start address in
-    // 16-byte units in the low word) plus tap / K-slice / split offsets.  The WHOLE warp runs this control
-    // flow (so the compiler keeps descriptors in uniform registers); one elected lane issues.
-    const uint32_t idesc = tc::idesc_bf16_f32(p.nt, 0, 0);
-    const uint64_t a_desc0 = tc::smem_desc(tc::smem_u32(a_smem), plane_a, G::GSTRIDE * 16u);
-    const uint64_t b_desc0 = tc::smem_desc(tc::smem_u32(b_smem), plane_b, 128u);
-    const uint32_t a_stage16 = a_stage_bytes >> 4, b_stage16 = b_stage_bytes >> 4, b_tap16 = b_tap_bytes >> 4;
-    const uint32_t plane_a16 = plane_a >> 4, plane_b16 = plane_b >> 4;
-    int sa = 0, sb = 0, ab = 0, tin = 0;             // tin: tap index inside the current weight stage
-    uint32_t pa = 0, pb = 0, pacc = 0;
-    bool b_ready = false;                            // resident weights: waited for once
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-      tc::mbar_wait(&acc_empty[ab], pacc ^ 1u);
-      tc::tc_fence_after();
-      const uint32_t d0 = tmem_base + (uint32_t)(ab * acc_cols);
-      for (int kc = 0; kc < nchunks; ++kc) {
-        tc::mbar_wait(&a_full[sa], pa);
+    // Descriptors are a per-stage base (start address in 16-byte units in the low word) plus tap / K-slice
+    // / split offsets.  The WHOLE warp runs this control flow (so the compiler keeps descriptors in uniform
+    // registers); one elected lane issues, once per weight stage.  Warp `mw` owns tiles mw, mw + nw, ...
+    const int mw = warp - TC_MMA_WARP0;
+    if (mw < p.nw) {
+      constexpr int GROUPS = 9 / TPS;
+      const uint32_t idesc_w = tc::idesc_bf16_f32(acc_w, 0, 0);      // hi x [hi | lo] in cat mode, else = idesc_n
+      const uint32_t idesc_n = tc::idesc_bf16_f32(p.nt, 0, 0);
+      const uint64_t a_desc0 = tc::smem_desc(tc::smem_u32(a_smem), plane_a, G::GSTRIDE * 16u);
+      const uint64_t b_desc0 = tc::smem_desc(tc::smem_u32(b_smem), 2u * plane_b, 128u);
+      const uint32_t a_stage16 = a_stage_bytes >> 4, b_stage16 = b_stage_bytes >> 4, b_tap16 = b_tap_bytes >> 4;
+      const uint32_t plane_a16 = plane_a >> 4, plane_b16 = plane_b >> 4;
+      const uint32_t a_lo16 = (uint32_t)Q * plane_a16;
+      // private sub-rings: stages mw, mw + nw, ... of the operand ring (and of the weight ring when streamed)
+      const int a_step = p.nw, b_step = p.b_resident ? 1 : p.nw;
+      const int a_first = mw, b_first = p.b_resident ? 0 : mw;
+      int sa = a_first, sb = b_first;
+      uint32_t pa = 0, pb = 0;
+      bool b_ready = false;                            // resident weights: waited for once
+      int seq = mw;
+      for (int tile = blockIdx.x + mw * gridDim.x; tile < p.ntiles; tile += p.nw * gridDim.x, seq += p.nw) {
+        const int ab = seq % p.nbuf;
+        const uint32_t pacc = (uint32_t)(seq / p.nbuf) & 1u;
+        tc::mbar_wait(&acc_empty[ab], pacc ^ 1u);
         tc::tc_fence_after();
-        const uint64_t a_base = a_desc0 + (uint64_t)((uint32_t)sa * a_stage16);
-        const uint32_t acc_rest = (kc > 0) ? 1u : 0u;
+        const uint32_t d0 = tmem_base + (uint32_t)(ab * acc_cols);
+        for (int kc = 0; kc < nchunks; ++kc) {
+          tc::mbar_wait(&a_full[sa], pa);
+          tc::tc_fence_after();
+          const uint64_t a_base = a_desc0 + (uint64_t)((uint32_t)sa * a_stage16);
+          const uint32_t acc_rest = (kc > 0) ? 1u : 0u;
+          const bool last_chunk = (kc == nchunks - 1);
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          if (tin == 0 && !b_ready) {
-            tc::mbar_wait(&b_full[sb], pb);
-            tc::tc_fence_after();
-          }
-          const uint64_t b_base = b_desc0 + (uint64_t)((uint32_t)sb * b_stage16 + (uint32_t)tin * b_tap16);
-          const int acc = G::tap_acc(tap);
-          const uint32_t d = d0 + (uint32_t)(acc * p.nt);
-          const uint64_t a_tap = a_base + (uint64_t)(uint32_t)p.tap_off[tap];
-          // the first tap that touches an accumulator overwrites it on the first channel chunk
-          const bool opens = (G::NACC == 1) ? (tap == 0) : (tap == 0 || tap == 1 || tap == 3 || tap == 4);
-          const bool last_in_stage = (tin == p.tps - 1);
-          if (tc::elect_one()) {
+          for (int g = 0; g < GROUPS; ++g) {
+            if (!b_ready) {
+              tc::mbar_wait(&b_full[sb], pb);
+              tc::tc_fence_after();
+            }
+            const uint64_t b_base = b_desc0 + (uint64_t)((uint32_t)sb * b_stage16);
+            if (tc::elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < KC / 16; ++ks) {
-              constexpr int PA[3] = {0, 0, 1};
-              constexpr int PB[3] = {0, 1, 0};
+              for (int tt = 0; tt < TPS; ++tt) {
+                const int tap = g * TPS + tt;
+                const uint32_t d = d0 + (uint32_t)(G::tap_acc(tap) * acc_w);
+                const uint64_t a_tap = a_base + (uint64_t)(uint32_t)p.tap_off[tap];
+                const uint64_t b_tap = b_base + (uint64_t)((uint32_t)tt * b_tap16);
+                // the first tap that touches an accumulator overwrites it on the first channel chunk
+                const bool opens = (G::NACC == 1) ? (tap == 0) : (tap == 0 || tap == 1 || tap == 3 || tap == 4);
 #pragma unroll
-              for (int pr = 0; pr < 3; ++pr) {
-                const uint64_t da = a_tap + (uint64_t)((uint32_t)(PA[pr] * Q + 2 * ks) * plane_a16);
-                const uint64_t db = b_base + (uint64_t)((uint32_t)(PB[pr] * Q + 2 * ks) * plane_b16);
-                const uint32_t accum = (opens && ks == 0 && pr == 0) ? acc_rest : 1u;
-                tc::mma_bf16(d, da, db, idesc, accum);
+                for (int ks = 0; ks < KC / 16; ++ks) {
+                  const uint64_t a_hi = a_tap + (uint64_t)((uint32_t)(2 * ks) * plane_a16);
+                  const uint64_t b_hi = b_tap + (uint64_t)((uint32_t)(4 * ks) * plane_b16);
+                  const uint32_t accum = (opens && ks == 0) ? acc_rest : 1u;
+                  if (CAT) {
+                    tc::mma_bf16(d, a_hi, b_hi, idesc_w, accum);
+                    tc::mma_bf16(d, a_hi + a_lo16, b_hi, idesc_n, 1u);
+                  } else {
+                    tc::mma_bf16(d, a_hi, b_hi, idesc_n, accum);
+                    tc::mma_bf16(d, a_hi, b_hi + plane_b16, idesc_n, 1u);
+                    tc::mma_bf16(d, a_hi + a_lo16, b_hi, idesc_n, 1u);
+                  }
+                }
+              }
+              if (!p.b_resident) tc::mma_commit(&b_empty[sb]);
+              if (g == GROUPS - 1) {
+                tc::mma_commit(&a_empty[sa]);
+                if (last_chunk) tc::mma_commit(&acc_full[ab]);
               }
             }
-            if (last_in_stage && !p.b_resident) tc::mma_commit(&b_empty[sb]);
-            if (tap == 8) {
-              tc::mma_commit(&a_empty[sa]);
-              if (kc == nchunks - 1) tc::mma_commit(&acc_full[ab]);
-            }
+            __syncwarp();
+            sb += b_step;
+            if (sb >= p.sb) { sb = b_first; pb ^= 1u; }
           }
-          __syncwarp();
-          if (last_in_stage) {
-            tin = 0;
-            if (++sb == p.sb) { sb = 0; pb ^= 1u; }
-          } else {
-            ++tin;
-          }
+          sa += a_step;
+          if (sa >= p.sa) { sa = a_first; pa ^= 1u; }
         }
-        if (++sa == p.sa) { sa = 0; pa ^= 1u; }
+        if (p.b_resident) b_ready = true;
       }
-      if (++ab == p.nbuf) { ab = 0; pacc ^= 1u; }
-      if (p.b_resident) b_ready = true;
     }
   } else if (warp < 4) {
-    // ============================== epilogue: TMEM -> alpha, bias, leaky-relu -> HBM =====================
+    // ============================== epilogue: TMEM -> alpha, bias, leaky-relu -> staging -> TMA store =====
+    // Thread m owns accumulator row (pixel) m.  32 channels at a time go through a 128B-swizzled staging
+    // tile [128 pixels][32 channels]; one thread hands it to the TMA engine (a box (32, 8, img, rows) of the
+    // (c, w, n, h) view of y: elements outside the tensor are clipped), double-buffered.
     int ab = 0;
     uint32_t pacc = 0;
     const int m = warp * 32 + lane;
-    const int g = m >> 3, i = m & 7;
-    const int row = g / p.img, slot = g % p.img;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    unsigned char* my_row0 = out_smem + (size_t)m * 128;
+    const int sw = m & 7;
+    int buf = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       int t = tile;
       const int tw_ = t % p.tiles_w;
       t /= p.tiles_w;
       const int th_ = t % p.tiles_h;
-      const int n = (t / p.tiles_h) * p.img + slot;
+      const int img0 = (t / p.tiles_h) * p.img;
       tc::mbar_wait(&acc_full[ab], pacc);
       tc::tc_fence_after();
 #pragma unroll 1
       for (int a = 0; a < G::NACC; ++a) {
-        int oy, ox;
-        if (FORM == TC_T2) { oy = 2 * (th_ * 16 + row) + (a >> 1); ox = 2 * (tw_ * 8 + i) + (a & 1); }
-        else { oy = th_ * 16 + row; ox = tw_ * 8 + i; }
-        const bool in_range = (n < p.n_img) && (oy < p.h_out) && (ox < p.w_out);
-        float* dst = p.y + (((size_t)n * p.h_out + oy) * p.w_out + ox) * p.ndim + n0;
 #pragma unroll 1
         for (int c0 = 0; c0 < p.nt; c0 += 32) {
           float v[32];
-          tc::tmem_ld32(tmem_base + lane_base + (uint32_t)(ab * acc_cols + a * p.nt + c0), v);
-          if (in_range) {
+          tc::tmem_ld32(tmem_base + lane_base + (uint32_t)(ab * acc_cols + a * acc_w + c0), v);
+          if (CAT) {
+            float v2[32];
+            tc::tmem_ld32(tmem_base + lane_base + (uint32_t)(ab * acc_cols + a * acc_w + p.nt + c0), v2);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 o;
-              float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
-              o.x = fmaf(v[j + 0], p.alpha, bv.x); o.y = fmaf(v[j + 1], p.alpha, bv.y);
-              o.z = fmaf(v[j + 2], p.alpha, bv.z); o.w = fmaf(v[j + 3], p.alpha, bv.w);
-              if (p.act == 1) { o.x = gs_lrelu(o.x); o.y = gs_lrelu(o.y); o.z = gs_lrelu(o.z); o.w = gs_lrelu(o.w); }
-              *reinterpret_cast<float4*>(dst + c0 + j) = o;
-            }
+            for (int j = 0; j < 32; ++j) v[j] += v2[j];
           }
+          unsigned char* row = my_row0 + (size_t)buf * 16384;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bv = *reinterpret_cast<const float4*>(&bias_s[c0 + j]);
+            float4 o;
+            o.x = fmaf(v[j + 0], p.alpha, bv.x); o.y = fmaf(v[j + 1], p.alpha, bv.y);
+            o.z = fmaf(v[j + 2], p.alpha, bv.z); o.w = fmaf(v[j + 3], p.alpha, bv.w);
+            if (p.act == 1) { o.x = gs_lrelu(o.x); o.y = gs_lrelu(o.y); o.z = gs_lrelu(o.z); o.w = gs_lrelu(o.w); }
+            *reinterpret_cast<float4*>(row + ((((j >> 2) ^ sw)) << 4)) = o;
+          }
+          tc::fence_proxy_async();
+          // the store that used the OTHER staging buffer must have finished reading it before anyone gets
+          // past this barrier and starts the next chunk
+          if (tid == 0) tc::bulk_wait_read<0>();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (tid == 0) {
+            tc::tma_store_4d(&tmy.m[a], out_smem + (size_t)buf * 16384, n0 + c0, tw_ * 8, img0, th_ * p.rows);
+            tc::bulk_commit();
+          }
+          buf ^= 1;
         }
       }
       tc::tc_fence_before();
       tc::mbar_arrive(&acc_empty[ab]);
       if (++ab == p.nbuf) { ab = 0; pacc ^= 1u; }
     }
+    if (tid == 0) tc::bulk_wait<0>();
   }
 
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 14) tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (warp == TC_MMA_WARP0) tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }

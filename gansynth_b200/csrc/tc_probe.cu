@@ -60,31 +60,37 @@ __global__ void __launch_bounds__(160) tc_probe_kernel(const float* __restrict__
   tc::tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp == 4 && lane == 0) {
-    const long long t_start = clock64();
-    for (int rep = 0; rep < reps; ++rep) {
+  if (warp == 4) {
+    // descriptors of the (at most 8) K slices are built once: the timed loop is UTCHMMA instructions only
     const uint32_t a0 = tc::smem_u32(As), b0 = tc::smem_u32(Bs);
     const uint32_t plane_a = (uint32_t)rows_a * 16u, plane_b = (uint32_t)rows_b * 16u;
-    if (mode == 0) {
-      const uint32_t idesc = tc::idesc_bf16_f32(N, 0, 0);
-      for (int s = 0; s < K / 16; ++s) {
-        uint64_t da = tc::smem_desc(a0 + 2u * s * plane_a + (uint32_t)shift * 16u, plane_a, (uint32_t)gstride * 16u);
-        uint64_t db = tc::smem_desc(b0 + 2u * s * plane_b, plane_b, 128u);
-        tc::mma_bf16(tmem_base, da, db, idesc, s > 0);
-      }
-    } else {
-      const uint32_t idesc = tc::idesc_bf16_f32(N, 1, 1);
-      for (int s = 0; s < K / 16; ++s) {
-        uint32_t poff = (uint32_t)(s * 2 * gstride + shift) * 16u;
-        uint64_t da = tc::smem_desc(a0 + poff, (uint32_t)gstride * 16u, plane_a);
-        uint64_t db = tc::smem_desc(b0 + poff, (uint32_t)gstride * 16u, plane_b);
-        tc::mma_bf16(tmem_base, da, db, idesc, s > 0);
+    const uint32_t idesc = tc::idesc_bf16_f32(N, mode, mode);
+    uint64_t da[8], db[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      const int ss = (s < K / 16) ? s : 0;
+      if (mode == 0) {
+        da[s] = tc::smem_desc(a0 + 2u * ss * plane_a + (uint32_t)shift * 16u, plane_a, (uint32_t)gstride * 16u);
+        db[s] = tc::smem_desc(b0 + 2u * ss * plane_b, plane_b, 128u);
+      } else {
+        const uint32_t poff = (uint32_t)(ss * 2 * gstride + shift) * 16u;
+        da[s] = tc::smem_desc(a0 + poff, (uint32_t)gstride * 16u, plane_a);
+        db[s] = tc::smem_desc(b0 + poff, (uint32_t)gstride * 16u, plane_b);
       }
     }
+    const int nsl = K / 16;
+    const long long t_start = clock64();
+    if (tc::elect_one()) {
+      for (int rep = 0; rep < reps; ++rep) {
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+          if (s < nsl) tc::mma_bf16(tmem_base, da[s], db[s], idesc, (s > 0 || rep > 0) ? 1u : 0u);
+      }
+      tc::mma_commit(&bar);
     }
-    tc::mma_commit(&bar);
+    __syncwarp();
     tc::mbar_wait(&bar, 0);
-    if (cycles) *cycles = clock64() - t_start;
+    if (cycles && lane == 0) *cycles = clock64() - t_start;
   }
   if (warp < 4) {
     tc::mbar_wait(&bar, 0);

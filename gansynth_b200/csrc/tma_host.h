@@ -25,15 +25,17 @@ static inline gs_encode_tiled_fn gs_encode_tiled() {
 // fp32 NHWC activation [n, h, w, c] seen as the 4-D tensor (c, w, n, h) -- innermost first -- so that a box
 // (kc, bw, img, bh) lands in shared memory as [bh][img][bw][kc]: image rows of `img` images interleaved.
 // `swizzle_bytes` = 128 / 64 / 0 must equal kc * 4 when non-zero.
+// `sh`, `sw_` > 1 describe a strided (sub-pixel phase) view: pixel (y, x) of the view is pixel (y*sh, x*sw_) of
+// the underlying [n, h*sh, w*sw_, c] tensor starting at `base`.
 static inline int gs_make_act_tmap(CUtensorMap* tm, const float* base, int n, int h, int w, int c, int kc, int bw,
-                                   int img, int bh, int swizzle_bytes) {
+                                   int img, int bh, int swizzle_bytes, int sh = 1, int sw_ = 1) {
   gs_encode_tiled_fn enc = gs_encode_tiled();
   if (!enc) {
     gs_set_error("cuTensorMapEncodeTiled is not available from this driver");
     return GS_ERR_CUDA;
   }
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)n, (cuuint64_t)h};
-  cuuint64_t strides[3] = {(cuuint64_t)c * 4, (cuuint64_t)h * w * c * 4, (cuuint64_t)w * c * 4};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 4 * sw_, (cuuint64_t)h * sh * w * sw_ * c * 4, (cuuint64_t)w * sw_ * c * 4 * sh};
   cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)bw, (cuuint32_t)img, (cuuint32_t)bh};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
