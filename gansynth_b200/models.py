@@ -83,6 +83,9 @@ class GANSynth(object):
         self.global_step = get_or_create_global_step()
         self.store = ops.default_store()
         self._opt = None
+        self._graphs = {}
+        self._graph_pool = None
+        self.use_cuda_graphs = os.environ.get("GS_CUDA_GRAPHS", "1") != "0"
         self.generator_loss = None
         self.discriminator_loss = None
         # last evaluated tensors, named like the reference attributes (models.py:91-108)
@@ -176,19 +179,23 @@ class GANSynth(object):
         for n, v in self.store.vars.items():
             v.requires_grad_(n.startswith(scope + "/"))
 
-    def _apply(self, scope, loss):
-        """minimize(loss, var_list=scope variables) (models.py:81-89) with TF-Adam semantics."""
-        hp = self.hyper_params
+    def _backward(self, scope, loss):
+        """Gradients of `loss` w.r.t. the variables of `scope`, written into the flat gradient buffer."""
         st = self._opt[scope]
         names = list(self.store.trainable_variables(scope).keys())
         grads = torch.autograd.grad(loss, [self.store.vars[n] for n in names], allow_unused=True)
-        gflat = st["grad"]
-        views = self.store.unflatten(scope, gflat)
+        views = self.store.unflatten(scope, st["grad"])
         for n, g in zip(names, grads):
             if g is None:
                 views[n].zero_()
             else:
                 views[n].copy_(g)
+
+    def _update(self, scope):
+        """[all-reduce] + fused TF-Adam on the flat buffers (models.py:67-89)."""
+        hp = self.hyper_params
+        st = self._opt[scope]
+        gflat = st["grad"]
         scale = 1.0
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             world = torch.distributed.get_world_size(self.process_group)
@@ -199,19 +206,86 @@ class GANSynth(object):
         F.K.adam_step(st["flat"], gflat, st["m"], st["v"], hp[scope + "_learning_rate"], hp[scope + "_beta1"],
                       hp[scope + "_beta2"], 1.0e-8, st["t"], scale)
 
+    def _apply(self, scope, loss):
+        """minimize(loss, var_list=scope variables) (models.py:81-89) with TF-Adam semantics."""
+        self._backward(scope, loss)
+        self._update(scope)
+
     # ------------------------------------------------------------------ sub-steps (one session.run each)
+    def _discriminator_body(self, real_waveforms, labels, latents):
+        """Everything of the D sub-step up to the flat gradient: spectral front-end, G forward, D(real),
+        D(fake), R1 double backward, gradients of the D variables."""
+        self._set_trainable("discriminator")
+        real_images = self.real_images_from_waveforms(real_waveforms)
+        loss = self.discriminator_loss_fn(real_images, labels, latents)
+        self._backward("discriminator", loss)
+        return loss.detach()
+
+    def _generator_body(self, labels, latents):
+        self._set_trainable("generator")
+        loss = self.generator_loss_fn(labels, latents)
+        self._backward("generator", loss)
+        return loss.detach()
+
+    def _static_structure(self):
+        """True when the kernel sequence of a sub-step does not depend on global_step: both networks fully
+        grown (no lerp weights that change every step), so the sub-step can be replayed as a CUDA graph."""
+        for fn in (self.generator, self.discriminator):
+            pg = getattr(fn, "__self__", None)
+            if pg is None or not hasattr(pg, "growing_depth") or not pg.growing_depth > pg.max_depth:
+                return False
+        return True
+
+    def _run_body(self, scope, body, inputs):
+        """Runs `body(*inputs)` eagerly the first two times (lazy variable creation, workspace growth, function
+        attributes), then captures it into a CUDA graph and replays the graph on static input buffers.  The
+        all-reduce and the Adam launch stay outside the graph (the Adam step count is a kernel argument)."""
+        use = (self.use_cuda_graphs and all(t.is_cuda for t in inputs) and self._static_structure()
+               and not torch.cuda.is_current_stream_capturing())
+        if not use:
+            return body(*inputs)
+        key = (scope,) + tuple(tuple(t.shape) for t in inputs)
+        entry = self._graphs.setdefault(key, dict(calls=0))
+        entry["calls"] += 1
+        if entry["calls"] <= 2:
+            return body(*inputs)
+        if "graph" not in entry:
+            from . import _lib
+            static_in = [t.clone() for t in inputs]
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                body(*static_in)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            # the variables' AccumulateGrad nodes were created on the eager stream; autograd.grad never uses them
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+            before = _lib.launch_count
+            # the two sub-step graphs never overlap in time: they share one memory pool
+            pool = self._graph_pool
+            with torch.cuda.graph(graph, pool=pool):
+                loss = body(*static_in)
+            if pool is None:
+                self._graph_pool = graph.pool()
+            entry.update(graph=graph, static_in=static_in, loss=loss, launches=_lib.launch_count - before)
+            _lib.launch_count = before
+        for dst, src in zip(entry["static_in"], inputs):
+            dst.copy_(src, non_blocking=True)
+        entry["graph"].replay()
+        from . import _lib
+        _lib.launch_count += entry["launches"]     # the captured kernels did launch
+        return entry["loss"]
+
     def discriminator_step(self, real_waveforms=None, labels=None, latents=None):
         if real_waveforms is None:
             real_waveforms, labels = self._next_real()
         if latents is None:
             latents = self._next_latents()
         self._ensure_optimizers(labels, latents)
-        self._set_trainable("discriminator")
         self.real_waveforms, self.real_labels, self.fake_labels = real_waveforms, labels, labels
-        real_images = self.real_images_from_waveforms(real_waveforms)
-        loss = self.discriminator_loss_fn(real_images, labels, latents)
-        self._apply("discriminator", loss)
-        self.discriminator_loss = loss.detach()
+        loss = self._run_body("discriminator", self._discriminator_body, (real_waveforms, labels, latents))
+        self._update("discriminator")
+        self.discriminator_loss = loss
         return self.discriminator_loss
 
     def generator_step(self, labels=None, latents=None):
@@ -220,11 +294,10 @@ class GANSynth(object):
         if latents is None:
             latents = self._next_latents()
         self._ensure_optimizers(labels, latents)
-        self._set_trainable("generator")
         self.real_labels = self.fake_labels = labels
-        loss = self.generator_loss_fn(labels, latents)
-        self._apply("generator", loss)
-        self.generator_loss = loss.detach()
+        loss = self._run_body("generator", self._generator_body, (labels, latents))
+        self._update("generator")
+        self.generator_loss = loss
         self.global_step.value += 1
         return self.generator_loss
 

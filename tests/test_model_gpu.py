@@ -163,3 +163,46 @@ def test_train_and_generate_entry_points(cuda_store, tmp_path):
     outs = list(model.generate(str(tmp_path)))
     assert len(outs) == 2 and outs[0].shape == (4, 64000) and outs[0].dtype == np.float32
     assert np.isfinite(outs[0]).all()
+
+
+def test_cuda_graph_substeps_match_eager(cuda_store):
+    """Five iterations with the sub-steps replayed as CUDA graphs (from the third call on) against the same
+    five iterations run eagerly from the same weights: same losses, same weights.  The fp32 exact kernels
+    are used so that the only run-to-run noise is the order of the filter-gradient atomics."""
+    import gansynth_b200.functional as F
+    import gansynth_b200.models as pmodels
+    import gansynth_b200.networks as pnet
+    import gansynth_b200.ops as ops
+    # the spectral kernels are built for 1024 bins: here the "waveforms" are the 2x16x16 images themselves
+    spectral = {}
+    g = torch.Generator().manual_seed(5)
+    batches = [(0.5 * torch.randn(4, 512, generator=g),
+                torch.nn.functional.one_hot(torch.randint(0, 61, (4,), generator=g), 61).float(),
+                torch.randn(4, 256, generator=g), torch.randn(4, 256, generator=g)) for _ in range(5)]
+    results = []
+    prev = F.K.impl
+    F.K.impl = 4
+    try:
+        for use_graphs in (False, True):
+            store = ops.set_default_store(ops.VariableStore(device="cuda", seed=0))
+            pmodels.reset_global_step()
+            _, params, ppg = _pair(SMALL, 1.0, store)
+            model = pmodels.GANSynth(ppg.generator, ppg.discriminator, None, None, spectral, HYPER)
+            model.use_cuda_graphs = use_graphs
+            model.real_images_from_waveforms = lambda w: w.reshape(4, 2, 16, 16)
+            losses = []
+            for w, lab, z1, z2 in batches:
+                d = model.discriminator_step(w.cuda(), lab.cuda(), z1.cuda())
+                gl = model.generator_step(lab.cuda(), z2.cuda())
+                losses.append((float(d), float(gl)))
+            if use_graphs:
+                assert len(model._graphs) == 2 and all("graph" in e for e in model._graphs.values())
+            results.append((losses, {n: v.detach().clone() for n, v in store.vars.items()}))
+    finally:
+        F.K.impl = prev
+        ops.set_default_store(None)
+    (l0, w0), (l1, w1) = results
+    for (d0, g0), (d1, g1) in zip(l0, l1):
+        assert abs(d0 - d1) < 1e-4 * max(1.0, abs(d0)) and abs(g0 - g1) < 1e-4 * max(1.0, abs(g0)), (l0, l1)
+    for n in w0:
+        assert rel_err(w1[n], w0[n]) < 1e-3, n
