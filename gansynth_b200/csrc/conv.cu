@@ -287,84 +287,91 @@ int launch_tc(const float* x, const float* w, const float* bias, float* y, int n
 
 // filter-gradient form on the tensor cores
 bool tcw_ok(int ksize, int adim, int bdim, int sh, int sw) {
-  return ksize == 3 && adim % 32 == 0 && bdim % 32 == 0 && adim <= 256 && bdim <= 256 && sw % 8 == 0 && sh % 2 == 0;
+  return ksize == 3 && adim % 32 == 0 && bdim % 32 == 0 && sw % 8 == 0 && sh % 2 == 0;
+}
+
+// largest channel block (<= 128, multiple of 32) that divides c
+int tcw_block(int c) {
+  for (int blk = 128; blk > 32; blk -= 32)
+    if (c % blk == 0) return blk;
+  return 32;
 }
 
 int launch_tcw(const float* big, const float* small, float* dw, int n, int bh, int bw, int adim, int bdim, int sh,
                int sw, int stride, int out_ab, float alpha, cudaStream_t st) {
   TcwParams p;
-  p.big = big; p.small = small; p.dw = dw;
+  p.dw = dw;
   p.n_img = n; p.bh = bh; p.bw = bw; p.sh = sh; p.sw = sw; p.adim = adim; p.bdim = bdim; p.stride = stride;
-  p.mode_e = (adim <= 64) && !getenv("GS_TCW_NO_EXPAND");
-  if (p.mode_e) {
-    // kw-expanded: M = (kw, big channel) in tiles of 128 rows, N = small channels, one accumulator per (kh, M tile)
-    p.big_is_m = 1;
-    p.mch = 3 * adim; p.nch = bdim;
-    p.m_tiles = (3 * adim + 127) / 128;
-    p.mt = 128;
-    int nt = bdim < 128 ? bdim : 128;
-    while (3 * p.m_tiles * nt > 512) nt /= 2;
-    p.nt = nt;
-    p.n_tiles = bdim / nt;
-    p.tap_groups = 1; p.tg = 9;
-    int cols = 32;
-    while (cols < 3 * p.m_tiles * nt) cols <<= 1;
-    p.tmem_cols = cols;
-  } else {
-    p.big_is_m = adim >= bdim;
-    p.mch = p.big_is_m ? adim : bdim;
-    p.nch = p.big_is_m ? bdim : adim;
-    p.mt = p.mch < 128 ? p.mch : 128;
-    p.nt = p.nch < 128 ? p.nch : 128;
-    p.m_tiles = p.mch / p.mt;
-    p.n_tiles = p.nch / p.nt;
-    p.tap_groups = (9 * p.nt + 511) / 512;
-    p.tg = (9 + p.tap_groups - 1) / p.tap_groups;
-    int cols = 32;
-    while (cols < p.tg * p.nt) cols <<= 1;
-    p.tmem_cols = cols;
-  }
-  const size_t budget = 222 * 1024;
+  p.out_ab = out_ab; p.alpha = alpha;
+  p.nch = tcw_block(adim);
+  p.nb = tcw_block(bdim);
+  p.cat = (3 * p.nb * 2 <= 512) && !getenv("GS_TC_NO_CAT");
+  p.njobs_n = bdim / p.nb;
+  // M jobs: as many kh taps per 128-row accumulator as fit (16 chunks of 8 channels)
+  const int qj = p.nch / 8, qb = p.nb / 8;
+  const int nkh_job = qj <= 4 ? 3 : qj <= 8 ? 2 : 1;
+  p.mjobs = 0;
+  for (int c0 = 0; c0 < adim; c0 += p.nch)
+    for (int k0 = 0; k0 < 3; k0 += nkh_job) {
+      GS_CHECK_ARG(p.mjobs < 8, "conv_tcw: too many jobs (adim %d)", adim);
+      p.kh0[p.mjobs] = k0;
+      p.nkh[p.mjobs] = (3 - k0 < nkh_job) ? 3 - k0 : nkh_job;
+      p.ch0[p.mjobs] = c0;
+      p.map_id[p.mjobs] = (p.nkh[p.mjobs] == nkh_job) ? 0 : 1;
+      ++p.mjobs;
+    }
+  p.pw = stride == 1 ? 10 : 18;
+  p.bwraw = stride == 1 ? 10 : 17;
+  const size_t budget = 222 * 1024 - 1024 - 8192;       // alignment slack; over-read slack of the 128-row M operand
   int tpr = 16;
-  size_t stage = 0, raw = 0, slack = 0;
-  const int m_ch = p.mode_e ? adim : p.mt, n_ch = p.nt;       // channels staged per pixel on each side
+  size_t stage = 0, raw = 0;
   for (;; tpr >>= 1) {
     GS_CHECK_ARG(tpr >= 2, "conv_tcw: no tile fits shared memory (adim %d bdim %d)", adim, bdim);
     if (sh % tpr) continue;
-    const size_t pbig = (size_t)tcw_big_plane_pixels(tpr, stride, p.mode_e) * 16, psmall = (size_t)tpr * 8 * 16;
-    const size_t rbig = (size_t)tcw_big_raw_pixels(tpr, stride), rsmall = (size_t)tpr * 8;
-    p.m_plane = (uint32_t)(p.big_is_m ? pbig : psmall);
-    p.n_plane = (uint32_t)(p.big_is_m ? psmall : pbig);
-    const size_t m_planes = p.mode_e ? (size_t)2 * 3 * (adim / 8) : (size_t)2 * (p.mt / 8);
-    p.m_bytes = (uint32_t)(m_planes * p.m_plane);
-    stage = p.m_bytes + (size_t)2 * (p.nt / 8) * p.n_plane;
-    p.m_raw = (uint32_t)((p.big_is_m ? rbig : rsmall) * m_ch * 4);
-    raw = p.m_raw + (p.big_is_m ? rsmall : rbig) * n_ch * 4;
-    // the M = 128 instruction reads 16 channel planes of the M operand even when fewer are staged: keep that
-    // over-read inside the allocation (those accumulator rows are never drained)
-    slack = (size_t)16 * p.m_plane;
-    if (2 * stage + raw + slack <= budget && (tpr <= 2 || 2 * stage + 2 * raw + slack <= budget)) break;
+    p.hr_max = stride * (tpr - 1) + nkh_job;
+    const size_t big_stage = (size_t)p.hr_max * qj * p.pw * 16;          // one split term
+    const size_t small_stage = (size_t)tpr * 2 * qb * 128;
+    p.big_lo_off = (uint32_t)big_stage;
+    p.small_off = (uint32_t)(2 * big_stage);
+    stage = 2 * big_stage + small_stage;
+    p.raw_big_chunk = (uint32_t)((((size_t)p.hr_max * p.bwraw * 128) + 1023) & ~(size_t)1023);
+    p.raw_small_chunk = (uint32_t)((((size_t)tpr * 8 * 128) + 1023) & ~(size_t)1023);
+    raw = (size_t)(p.nch / 32) * p.raw_big_chunk + (size_t)(p.nb / 32) * p.raw_small_chunk;
+    if (2 * stage + 2 * raw <= budget) break;
   }
   p.tpr = tpr;
   p.stage_bytes = (uint32_t)stage;
-  p.raw_bytes = (uint32_t)raw;
-  p.stages = 2; p.ds = 1;
-  size_t used = 2 * stage + raw + slack;
-  while (p.ds < 3 && used + raw <= budget) { ++p.ds; used += raw; }
-  while (p.stages < TCW_MAX_STAGES && used + stage <= budget) { ++p.stages; used += stage; }
+  p.raw_slot_bytes = (uint32_t)raw;
+  p.stages = 2; p.ds = 2;
+  size_t used = 2 * stage + 2 * raw;
+  if (used + raw <= budget) { ++p.ds; used += raw; }
+  if (used + stage <= budget) { ++p.stages; used += stage; }
+  if (used + raw <= budget) { ++p.ds; used += raw; }
   p.tiles_h = sh / tpr; p.tiles_w = sw / 8; p.ntiles = n * p.tiles_h * p.tiles_w;
-  p.out_ab = out_ab; p.alpha = alpha;
-  const int njobs = p.mode_e ? p.n_tiles : p.m_tiles * p.n_tiles * p.tap_groups;
+  int cols = 32;
+  while (cols < 3 * p.nb * (1 + p.cat)) cols <<= 1;
+  p.tmem_cols = cols;
+  TcwMaps maps;
+  {
+    int rc = gs_make_act_tmap(&maps.big[0], big, n, bh, bw, adim, 32, p.bwraw, 1, stride * (tpr - 1) + nkh_job, 128);
+    if (rc) return rc;
+    const int nkh_last = 3 % nkh_job ? 3 % nkh_job : nkh_job;
+    rc = gs_make_act_tmap(&maps.big[1], big, n, bh, bw, adim, 32, p.bwraw, 1, stride * (tpr - 1) + nkh_last, 128);
+    if (rc) return rc;
+    rc = gs_make_act_tmap(&maps.small, small, n, sh, sw, bdim, 32, 8, 1, tpr, 128);
+    if (rc) return rc;
+  }
+  const int njobs = p.mjobs * p.njobs_n;
   int px = gs_num_sms() / njobs;
   if (px < 1) px = 1;
   if (px > p.ntiles) px = p.ntiles;
   static bool attr = false;
   if (!attr) {
-    GS_CUDA(cudaFuncSetAttribute(conv_tcw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    GS_CUDA(cudaFuncSetAttribute(conv_tcw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
     attr = true;
   }
   dim3 grid((unsigned)px, (unsigned)njobs);
-  conv_tcw_kernel<<<grid, TCW_THREADS, (size_t)p.stages * stage + (size_t)p.ds * raw + slack, st>>>(p);
+  conv_tcw_kernel<<<grid, TCW_THREADS, used + 1024 + 8192, st>>>(maps, p);
   GS_CHECK_LAUNCH("conv_tcw");
   return GS_OK;
 }

@@ -1,321 +1,280 @@
 // tcgen05 / TMEM filter-gradient ("W form") of the 3x3 convolutions, bf16x3, for sm_100a.
 //
-//   dw(tap, a, b) = alpha * sum_{n,oy,ox} big[n, oy*S+kh-pb, ox*S+kw-pb, a] * small[n, oy, ox, b]
+//   dw(kh, kw, a, b) = alpha * sum_{n,oy,ox} big[n, oy*S + kh - pb, ox*S + kw - pb, a] * small[n, oy, ox, b]
 //
 // Per tap this is a GEMM whose contraction index is the PIXEL.  Both operands sit in shared memory as
-// 16-byte channel vectors in pixel-major planes, which for this GEMM is the MN-major SWIZZLE_NONE
-// core-matrix layout: channel chunks along M / N (stride = plane), pixels along K (8 consecutive pixels =
-// one image-row segment, next segment = next tile row).
+// 16-byte channel vectors (8 channels of one pixel), 8 consecutive pixels of an image row contiguous: for a
+// GEMM contracted over pixels that is the MN-major SWIZZLE_NONE core-matrix layout (channel chunks along
+// M / N, 8-pixel groups along K).
 //
-// Two job layouts:
-//  * kw-EXPANDED (`big` has <= 64 channels: the high-resolution layers).  `big` is staged as three
-//    column-shifted copies (kw = 0, 1, 2), 8 pixels per row each, as extra channel planes.  M runs over
-//    (kw, channel) = 96 / 192 rows, so the 128-row MMA is filled, the nine taps cost three MMAs (one per
-//    kh, each with its own accumulator) and nothing is staged twice.  grid.y = N tiles of `small`.
-//  * TAP-GROUP (`big` has >= 128 channels).  A filter tap is a start address into the staged halo of
-//    `big`; the side with fewer channels is on N; TG taps x N columns of TMEM (<= 512) per CTA.
-//    grid.y = (M tile, N tile, tap group).
-// Each CTA accumulates over its whole pixel range (grid.x splits the pixels) and adds its partial filter
-// gradient to dw with fp32 atomics at the end.
-// Warps 0-3 stage the M-side operand, 4-7 the N-side operand: global loads are issued `ds` tiles ahead as
-// 16-byte cp.async copies into an fp32 staging ring, then split fp32 -> bf16 hi/lo into the operand ring.
-// Warp 8 issues the MMAs; warps 0-7 drain TMEM at the end.
+//   big   staged as [row][q][PW pixels]   (q = 8-channel chunk).  Consecutive (row, q) blocks are equally
+//         spaced, so the M index of ONE instruction can run over (kh, channel): the three kh taps are three
+//         runs of Q chunks one staged row apart -- "kh-stacked", no copies, M = 3 * channels (<= 128 rows
+//         per job).  kw is a start-address shift (stride 2: even / odd column planes).
+//   small staged as [row][hi q.. | lo q..][8 pixels]: hi and lo chunks adjacent, so hi x [hi | lo] is one
+//         MMA of width 2 * NB ("cat", as in conv_tc.cuh) when the accumulators fit TMEM.
+//
+// A job (blockIdx.y) = (kh range, big-channel block of <= 128, small-channel block NB <= 128): one 128-row
+// accumulator per kw (3 * NB * (1 + cat) <= 512 TMEM columns).  grid.x splits the pixel tiles; every CTA
+// accumulates over its whole pixel range and adds its partial filter gradient to dw with (vector) fp32
+// atomics at the end.
+//
+// Data path (as in conv_tc.cuh): TMA tiled loads of fp32 boxes (128B swizzle, zero fill outside the image)
+// into a raw ring -> 8 converter warps split fp32 -> bf16 hi/lo into the operand ring -> one elected thread
+// issues the MMAs -> warps 0-3 drain TMEM at the end.
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
-struct TcwParams {
-  const float* big;     // [n, bh, bw, adim]
-  const float* small;   // [n, sh, sw, bdim]
-  float* dw;
-  int n_img, bh, bw, sh, sw, adim, bdim, stride;
-  int big_is_m;         // 1: big on M, small on N; 0: small on M, big on N
-  int mode_e;           // kw-expanded layout (big on M)
-  int mch, nch;         // total channels on the M / N side
-  int mt, nt;           // channels (rows / columns) per CTA tile on each side
-  int m_tiles, n_tiles, tap_groups, tg;
-  int tpr;              // tile rows (small side), tile is tpr x 8 pixels
-  int tiles_h, tiles_w, ntiles;
-  int stages, ds, out_ab, tmem_cols;
-  float alpha;
-  uint32_t m_plane, n_plane, m_bytes, stage_bytes;   // bf16 operand ring (bytes)
-  uint32_t m_raw, raw_bytes;                          // fp32 staging ring: M-side bytes, slot bytes
+struct TcwMaps {
+  CUtensorMap big[2];     // box rows differ with the number of kh taps of the job
+  CUtensorMap small;
 };
 
-constexpr int TCW_THREADS = 288;
+struct TcwParams {
+  float* dw;
+  int n_img, bh, bw, sh, sw, adim, bdim, stride;
+  int tpr;                        // tile rows (small side); a tile is tpr x 8 pixels of one image
+  int tiles_h, tiles_w, ntiles;
+  int mjobs, njobs_n;             // grid.y = mjobs * njobs_n
+  int kh0[8], nkh[8], ch0[8], map_id[8];
+  int nch, nb;                    // big / small channels per job (multiples of 32, <= 128)
+  int cat;
+  int pw, bwraw;                  // staged / raw pixels per big row: 10 / 10 (stride 1), 18 / 17 (stride 2)
+  int hr_max;                     // staged big rows of the job with the most kh taps
+  int stages, ds, out_ab, tmem_cols;
+  float alpha;
+  uint32_t raw_big_chunk, raw_small_chunk, raw_slot_bytes;   // raw ring: 32-channel chunks, 1024-aligned
+  uint32_t big_lo_off, small_off, stage_bytes;                // operand stage layout (bytes)
+};
+
+constexpr int TCW_THREADS = 320;
+constexpr int TCW_CONV_THREADS = 256;
 constexpr int TCW_MAX_STAGES = 4;
 
-// raw (fp32) halo pixels of `big` per tile, and staged pixels per plane
-__host__ __device__ inline int tcw_big_raw_pixels(int tpr, int stride) { return stride == 1 ? (tpr + 2) * 10 : (2 * tpr + 1) * 17; }
-__host__ __device__ inline int tcw_big_plane_pixels(int tpr, int stride, int mode_e) {
-  if (mode_e) return (stride == 1 ? tpr + 2 : 2 * tpr + 1) * 8;
-  return tcw_big_raw_pixels(tpr, stride);
-}
-
-__global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const TcwParams p) {
-  extern __shared__ __align__(128) unsigned char tcw_smem[];
-  __shared__ uint64_t full_m[TCW_MAX_STAGES], full_n[TCW_MAX_STAGES], empty[TCW_MAX_STAGES], done;
+__global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const __grid_constant__ TcwMaps maps, const TcwParams p) {
+  extern __shared__ unsigned char tcw_smem_raw[];
+  __shared__ uint64_t raw_full[TCW_MAX_STAGES], raw_empty[TCW_MAX_STAGES], full[TCW_MAX_STAGES], empty[TCW_MAX_STAGES], done;
   __shared__ uint32_t tmem_base_s;
+  __shared__ uint16_t big_tab[640];       // raw big pixel -> staged position (16-byte units, q = 0)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   // job decode
-  int job = blockIdx.y;
-  const int tgi = job % p.tap_groups;
-  job /= p.tap_groups;
-  const int nti = job % p.n_tiles;
-  const int mti = job / p.n_tiles;
-  const int tap0 = tgi * p.tg;
-  const int ntap = (9 - tap0 < p.tg) ? 9 - tap0 : p.tg;
-  const int m_ch0 = p.mode_e ? 0 : mti * p.mt, n_ch0 = nti * p.nt;
-  const int mt_valid = (p.mch - m_ch0 < p.mt) ? p.mch - m_ch0 : p.mt;
-  const int nt_valid = (p.nch - n_ch0 < p.nt) ? p.nch - n_ch0 : p.nt;
-  const int qm = p.mt / 8, qn = p.nt / 8;
-  unsigned char* raw_smem = tcw_smem + (size_t)p.stages * p.stage_bytes;
+  const int mj = blockIdx.y / p.njobs_n, nj = blockIdx.y % p.njobs_n;
+  const int kh0 = p.kh0[mj], nkh = p.nkh[mj], ch0 = p.ch0[mj];
+  const int nb0 = nj * p.nb;
+  const int S = p.stride;
+  const int qj = p.nch >> 3, qb = p.nb >> 3;
+  const int hr_rows = S * (p.tpr - 1) + nkh;
+  const int nbig_px = hr_rows * p.bwraw, nsmall_px = p.tpr * 8;
+  const int big_chunks = p.nch >> 5, small_chunks = p.nb >> 5;
+  unsigned char* smem = tcw_smem_raw + ((1024u - (tc::smem_u32(tcw_smem_raw) & 1023u)) & 1023u);
+  unsigned char* raw_smem = smem;
+  unsigned char* st_smem = smem + (size_t)p.ds * p.raw_slot_bytes;
 
   if (tid == 0) {
-    for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&full_m[s], 128); tc::mbar_init(&full_n[s], 128); tc::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < p.ds; ++s) { tc::mbar_init(&raw_full[s], 1); tc::mbar_init(&raw_empty[s], TCW_CONV_THREADS); }
+    for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&full[s], TCW_CONV_THREADS); tc::mbar_init(&empty[s], 1); }
     tc::mbar_init(&done, 1);
     tc::mbar_fence_init();
   }
-  if (warp == 8) tc::tmem_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
+  for (int px = tid; px < nbig_px; px += TCW_THREADS) {
+    const int hr = px / p.bwraw, hc = px % p.bwraw;
+    big_tab[px] = (uint16_t)(hr * qj * p.pw + (S == 1 ? hc : (hc & 1) * 9 + (hc >> 1)));
+  }
+  if (warp == 9) tc::tmem_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
+  if (warp == 8 && lane == 0) {
+    tc::prefetch_tmap(&maps.big[p.map_id[mj]]);
+    tc::prefetch_tmap(&maps.small);
+  }
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  const int acc_w = p.cat ? 2 * p.nb : p.nb;
 
   if (warp < 8) {
-    // ============================== operand staging ====================================================
-    const bool m_side = warp < 4;
-    const bool is_big = m_side ? (p.big_is_m != 0) : (p.big_is_m == 0);
-    const bool expand = p.mode_e && is_big;
-    const int ct = tid & 127;
-    const int ch_cnt = expand ? p.adim : (m_side ? p.mt : p.nt);     // channels this group stages per pixel
-    const int q_cnt = ch_cnt / 8, cpp = ch_cnt / 4;                   // 16-byte bf16 vectors / fp32 chunks per pixel
-    const int ch0 = expand ? 0 : (m_side ? m_ch0 : n_ch0);
-    const uint32_t plane = m_side ? p.m_plane : p.n_plane;
-    const float* src_base = is_big ? p.big : p.small;
-    const int cdim = is_big ? p.adim : p.bdim;
-    const int ih_max = is_big ? p.bh : p.sh, iw_max = is_big ? p.bw : p.sw;
-    const int npx = is_big ? tcw_big_raw_pixels(p.tpr, p.stride) : p.tpr * 8;
-    const uint32_t raw_off = m_side ? 0u : p.m_raw;
-    const uint32_t raw_row = (uint32_t)cpp * 16u;                     // bytes of one raw pixel
-    uint64_t* full = m_side ? full_m : full_n;
-
-    // pixel ps of the raw tile -> image coordinates
-    auto coords = [&](int tile, int ps, int& n, int& iy, int& ix) {
-      int t = tile;
-      const int tw_ = t % p.tiles_w;
-      t /= p.tiles_w;
-      const int th_ = t % p.tiles_h;
-      n = t / p.tiles_h;
-      const int oy0 = th_ * p.tpr, ox0 = tw_ * 8;
-      if (!is_big) { iy = oy0 + ps / 8; ix = ox0 + ps % 8; }
-      else if (p.stride == 1) { iy = oy0 - 1 + ps / 10; ix = ox0 - 1 + ps % 10; }
-      else if (expand) { iy = 2 * oy0 + ps / 17; ix = 2 * ox0 + ps % 17; }
-      else { int hr = ps / 17, rem = ps % 17, par = rem >= 9; iy = 2 * oy0 + hr; ix = 2 * ox0 + 2 * (rem - 9 * par) + par; }
-    };
-    auto issue = [&](int tile, int slot) {
-      unsigned char* rg = raw_smem + (size_t)slot * p.raw_bytes + raw_off;
-      for (int ps = ct; ps < npx; ps += 128) {
-        int n, iy, ix;
-        coords(tile, ps, n, iy, ix);
-        const bool ok = iy >= 0 && iy < ih_max && ix >= 0 && ix < iw_max;
-        const float* src = ok ? src_base + (((size_t)n * ih_max + iy) * iw_max + ix) * cdim + ch0 : src_base;
-        unsigned char* row = rg + (size_t)ps * raw_row;
-        for (int j = 0; j < cpp; ++j) tc::cp_async16(row + (size_t)((j ^ (ps & 7)) * 16), src + j * 4, ok ? 16u : 0u);
-      }
-    };
-    auto convert = [&](int slot, unsigned char* st) {
-      const unsigned char* rg = raw_smem + (size_t)slot * p.raw_bytes + raw_off;
-      for (int ps = ct; ps < npx; ps += 128) {
-        const unsigned char* row = rg + (size_t)ps * raw_row;
-        // destination pixel positions (up to three shifted copies in the kw-expanded layout)
-        int pos[3] = {ps, -1, -1};
-        if (expand) {
-          if (p.stride == 1) {
-            const int hr = ps / 10, hc = ps % 10;
-#pragma unroll
-            for (int kw = 0; kw < 3; ++kw) { const int c = hc - kw; pos[kw] = (c >= 0 && c < 8) ? hr * 8 + c : -1; }
-          } else {
-            const int hr = ps / 17, ic = ps % 17;
-            pos[0] = (!(ic & 1) && ic <= 14) ? hr * 8 + (ic >> 1) : -1;
-            pos[1] = (ic & 1) ? hr * 8 + (ic >> 1) : -1;
-            pos[2] = (!(ic & 1) && ic >= 2) ? hr * 8 + (ic >> 1) - 1 : -1;
-          }
-        }
-        for (int q = 0; q < q_cnt; ++q) {
-          const float4 v0 = *reinterpret_cast<const float4*>(row + (size_t)(((2 * q) ^ (ps & 7)) * 16));
-          const float4 v1 = *reinterpret_cast<const float4*>(row + (size_t)(((2 * q + 1) ^ (ps & 7)) * 16));
+    // ============================== fp32 -> bf16 hi/lo split ===========================================
+    // item = (pixel, 8-channel chunk q).  A warp works on one q at a time with consecutive pixels on
+    // consecutive lanes: conflict-free reads of the swizzled raw rows, contiguous 16-byte stores.
+    const int wq_b = qj >= 8 ? 1 : 8 / qj, wq_s = qb >= 8 ? 1 : 8 / qb;     // warps per chunk
+    int stage = 0, rs = 0;
+    uint32_t ph = 0, rph = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      tc::mbar_wait(&raw_full[rs], rph);
+      tc::mbar_wait(&empty[stage], ph ^ 1u);
+      const unsigned char* raw = raw_smem + (size_t)rs * p.raw_slot_bytes;
+      unsigned char* st = st_smem + (size_t)stage * p.stage_bytes;
+      // ---- big: staged [row][q][pw] (hi block, then lo block)
+      for (int q = (qj >= 8 ? warp : warp / wq_b); q < qj; q += (qj >= 8 ? 8 : qj)) {
+        const unsigned char* chunk = raw + (size_t)(q >> 2) * p.raw_big_chunk;
+        const int j0 = 2 * (q & 3);
+        for (int px = (qj >= 8 ? 0 : (warp % wq_b) * 32) + lane; px < nbig_px; px += 32 * wq_b) {
+          const unsigned char* row = chunk + (size_t)px * 128;
+          const int sw = px & 7;
+          const float4 v0 = *reinterpret_cast<const float4*>(row + ((j0 ^ sw) << 4));
+          const float4 v1 = *reinterpret_cast<const float4*>(row + (((j0 + 1) ^ sw) << 4));
           uint4 h4, l4;
           tc::split2_bf16(v0.x, v0.y, h4.x, l4.x);
           tc::split2_bf16(v0.z, v0.w, h4.y, l4.y);
           tc::split2_bf16(v1.x, v1.y, h4.z, l4.z);
           tc::split2_bf16(v1.z, v1.w, h4.w, l4.w);
-          if (!expand) {
-            *reinterpret_cast<uint4*>(st + (size_t)q * plane + (size_t)ps * 16) = h4;
-            *reinterpret_cast<uint4*>(st + (size_t)(q_cnt + q) * plane + (size_t)ps * 16) = l4;
-          } else {
-            // planes [split][kw][q]
-#pragma unroll
-            for (int kw = 0; kw < 3; ++kw)
-              if (pos[kw] >= 0) {
-                *reinterpret_cast<uint4*>(st + (size_t)(kw * q_cnt + q) * plane + (size_t)pos[kw] * 16) = h4;
-                *reinterpret_cast<uint4*>(st + (size_t)((3 + kw) * q_cnt + q) * plane + (size_t)pos[kw] * 16) = l4;
-              }
-          }
+          const uint32_t d = ((uint32_t)big_tab[px] + (uint32_t)(q * p.pw)) << 4;
+          *reinterpret_cast<uint4*>(st + d) = h4;
+          *reinterpret_cast<uint4*>(st + p.big_lo_off + d) = l4;
         }
       }
-    };
-
-    int stage = 0;
-    uint32_t phase = 0;
-    int pt = blockIdx.x, slot_pf = 0;
-    for (int i = 0; i < p.ds; ++i) {
-      if (pt < p.ntiles) { issue(pt, slot_pf); pt += gridDim.x; }
-      tc::cp_async_commit();
-      if (++slot_pf == p.ds) slot_pf = 0;
-    }
-    int slot_cv = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-      if (p.ds == 1) tc::cp_async_wait<0>();
-      else if (p.ds == 2) tc::cp_async_wait<1>();
-      else tc::cp_async_wait<2>();
-      tc::mbar_wait(&empty[stage], phase ^ 1u);
-      convert(slot_cv, tcw_smem + (size_t)stage * p.stage_bytes + (m_side ? 0u : p.m_bytes));
+      // ---- small: staged [row][hi q.. | lo q..][8 pixels]
+      unsigned char* ss = st + p.small_off;
+      for (int q = (qb >= 8 ? warp : warp / wq_s); q < qb; q += (qb >= 8 ? 8 : qb)) {
+        const unsigned char* chunk = raw + (size_t)big_chunks * p.raw_big_chunk + (size_t)(q >> 2) * p.raw_small_chunk;
+        const int j0 = 2 * (q & 3);
+        for (int px = (qb >= 8 ? 0 : (warp % wq_s) * 32) + lane; px < nsmall_px; px += 32 * wq_s) {
+          const unsigned char* row = chunk + (size_t)px * 128;
+          const int sw = px & 7;
+          const float4 v0 = *reinterpret_cast<const float4*>(row + ((j0 ^ sw) << 4));
+          const float4 v1 = *reinterpret_cast<const float4*>(row + (((j0 + 1) ^ sw) << 4));
+          uint4 h4, l4;
+          tc::split2_bf16(v0.x, v0.y, h4.x, l4.x);
+          tc::split2_bf16(v0.z, v0.w, h4.y, l4.y);
+          tc::split2_bf16(v1.x, v1.y, h4.z, l4.z);
+          tc::split2_bf16(v1.z, v1.w, h4.w, l4.w);
+          const uint32_t r = (uint32_t)px >> 3, c = (uint32_t)px & 7u;
+          const uint32_t d = ((r * 2u * (uint32_t)qb + (uint32_t)q) * 8u + c) << 4;
+          *reinterpret_cast<uint4*>(ss + d) = h4;
+          *reinterpret_cast<uint4*>(ss + d + ((uint32_t)qb << 7)) = l4;
+        }
+      }
       tc::fence_proxy_async();
       tc::mbar_arrive(&full[stage]);
-      if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-      if (pt < p.ntiles) { issue(pt, slot_cv); pt += gridDim.x; }
-      tc::cp_async_commit();
-      if (++slot_cv == p.ds) slot_cv = 0;
+      tc::mbar_arrive(&raw_empty[rs]);
+      if (++stage == p.stages) { stage = 0; ph ^= 1u; }
+      if (++rs == p.ds) { rs = 0; rph ^= 1u; }
     }
-    tc::cp_async_wait<0>();
 
     // ============================== drain: TMEM -> atomics into dw =====================================
-    tc::mbar_wait(&done, 0);
-    tc::tc_fence_after();
-    const int quarter = warp & 3, half = warp >> 2;
-    const int m = quarter * 32 + lane;
-    const int ncols = p.mode_e ? 3 * p.m_tiles * p.nt : ntap * p.nt;
-    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    const int qa = p.adim / 8;
-    for (int c0 = half * 32; c0 < ncols; c0 += 64) {
-      float v[32];
-      tc::tmem_ld32(tmem_base + lane_base + (uint32_t)c0, v);
-      const int accn = c0 / p.nt, nn0 = c0 % p.nt;
-      int tap, a_or_m;
-      bool row_ok;
-      if (p.mode_e) {
-        // accumulator (kh, t) at ((kh * m_tiles + t) * nt); row m of M tile t = group 16 t + m/8 of (kw, channel)
-        const int kh = accn / p.m_tiles, t = accn % p.m_tiles;
-        const int gi = 16 * t + (m >> 3);
-        row_ok = gi < 3 * qa;
-        tap = kh * 3 + gi / qa;
-        a_or_m = (gi % qa) * 8 + (m & 7);
-      } else {
-        row_ok = m < mt_valid;
-        tap = tap0 + accn;
-        a_or_m = m_ch0 + m;
-      }
-      if (row_ok) {
+    if (warp < 4) {
+      tc::mbar_wait(&done, 0);
+      tc::tc_fence_after();
+      const int m = warp * 32 + lane;
+      const int g = m >> 3;
+      const bool row_ok = g < nkh * qj;
+      const int kh = kh0 + g / qj;
+      const int a = ch0 + (g % qj) * 8 + (m & 7);
+      const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+#pragma unroll 1
+      for (int kw = 0; kw < 3; ++kw) {
+        const int tap = kh * 3 + kw;
+#pragma unroll 1
+        for (int c0 = 0; c0 < p.nb; c0 += 32) {
+          float v[32];
+          tc::tmem_ld32(tmem_base + lane_base + (uint32_t)(kw * acc_w + c0), v);
+          if (p.cat) {
+            float v2[32];
+            tc::tmem_ld32(tmem_base + lane_base + (uint32_t)(kw * acc_w + p.nb + c0), v2);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int nn = nn0 + j;
-          if (nn < nt_valid) {
-            const int a = p.big_is_m ? a_or_m : (n_ch0 + nn);
-            const int b = p.big_is_m ? (n_ch0 + nn) : a_or_m;
-            const size_t o = p.out_ab ? ((size_t)tap * p.adim + a) * p.bdim + b : ((size_t)tap * p.bdim + b) * p.adim + a;
-            atomicAdd(p.dw + o, v[j] * p.alpha);
+            for (int j = 0; j < 32; ++j) v[j] += v2[j];
+          }
+          if (row_ok) {
+            if (p.out_ab) {
+              float* dst = p.dw + ((size_t)tap * p.adim + a) * p.bdim + nb0 + c0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                atomicAdd(reinterpret_cast<float4*>(dst + j),
+                          make_float4(v[j] * p.alpha, v[j + 1] * p.alpha, v[j + 2] * p.alpha, v[j + 3] * p.alpha));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                atomicAdd(p.dw + ((size_t)tap * p.bdim + nb0 + c0 + j) * p.adim + a, v[j] * p.alpha);
+            }
           }
         }
+      }
+    }
+  } else if (warp == 8) {
+    // ============================== TMA: one box per 32-channel chunk of each operand ====================
+    if (lane == 0) {
+      int rs = 0;
+      uint32_t rph = 0;
+      const uint32_t bytes = (uint32_t)(big_chunks * nbig_px + small_chunks * nsmall_px) * 128u;
+      const CUtensorMap* mb = &maps.big[p.map_id[mj]];
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        int t = tile;
+        const int tw_ = t % p.tiles_w;
+        t /= p.tiles_w;
+        const int th_ = t % p.tiles_h;
+        const int n = t / p.tiles_h;
+        const int ox0 = tw_ * 8, oy0 = th_ * p.tpr;
+        const int bx0 = (S == 1) ? ox0 - 1 : 2 * ox0;
+        const int by0 = (S == 1) ? oy0 - 1 + kh0 : 2 * oy0 + kh0;
+        tc::mbar_wait(&raw_empty[rs], rph ^ 1u);
+        tc::mbar_arrive_expect_tx(&raw_full[rs], bytes);
+        unsigned char* slot = raw_smem + (size_t)rs * p.raw_slot_bytes;
+        for (int c = 0; c < big_chunks; ++c)
+          tc::tma_load_4d(slot + (size_t)c * p.raw_big_chunk, mb, ch0 + 32 * c, bx0, n, by0, &raw_full[rs]);
+        for (int c = 0; c < small_chunks; ++c)
+          tc::tma_load_4d(slot + (size_t)big_chunks * p.raw_big_chunk + (size_t)c * p.raw_small_chunk, &maps.small, nb0 + 32 * c,
+                          ox0, n, oy0, &raw_full[rs]);
+        if (++rs == p.ds) { rs = 0; rph ^= 1u; }
       }
     }
   } else {
     // ============================== MMA issue ==========================================================
-    // Descriptors = per-stage base + tap offset + k-step stride, all in 16-byte units in the low word.
-    // The whole warp runs the control flow (uniform registers); one elected lane issues.
-    const uint32_t idesc = tc::idesc_bf16_f32(p.nt, 1, 1);
+    // A (big, M side): chunk stride = pw pixels, 8-pixel K group stride = S staged rows; B (small, N side):
+    // chunk stride = 8 pixels, K group stride = one staged row.  One K step = two tile rows.
+    const uint32_t idesc_w = tc::idesc_bf16_f32(acc_w, 1, 1);
+    const uint32_t idesc_n = tc::idesc_bf16_f32(p.nb, 1, 1);
+    const uint32_t lbo_m = (uint32_t)(S * qj * p.pw) * 16u, sbo_m = (uint32_t)p.pw * 16u;
+    const uint32_t lbo_n = (uint32_t)(2 * qb) * 128u, sbo_n = 128u;
+    const uint64_t m_desc0 = tc::smem_desc(tc::smem_u32(st_smem), lbo_m, sbo_m);
+    const uint64_t n_desc0 = tc::smem_desc(tc::smem_u32(st_smem) + p.small_off, lbo_n, sbo_n);
     const uint32_t stage16 = p.stage_bytes >> 4;
+    const uint32_t m_lo16 = p.big_lo_off >> 4, n_lo16 = ((uint32_t)qb << 7) >> 4;
+    const uint32_t m_step16 = (2u * lbo_m) >> 4, n_step16 = (2u * lbo_n) >> 4;
     const int ksteps = p.tpr / 2;
     int stage = 0;
-    uint32_t phase = 0;
-    uint32_t accum_first = 0;
-    if (p.mode_e) {
-      // big on M: tile row r, tap kh -> staged row (r*S + kh) of 8 pixels
-      const uint32_t big_lbo = (p.stride == 1) ? 128u : 256u;
-      const uint32_t big_step16 = (p.stride == 1) ? 16u : 32u;        // two tile rows
-      const uint64_t m_desc0 = tc::smem_desc(tc::smem_u32(tcw_smem), big_lbo, p.m_plane);
-      const uint64_t n_desc0 = tc::smem_desc(tc::smem_u32(tcw_smem) + p.m_bytes, 128u, p.n_plane);
-      const uint32_t split_lo16 = ((uint32_t)(3 * (p.adim / 8)) * p.m_plane) >> 4;
-      const uint32_t n_lo16 = ((uint32_t)qn * p.n_plane) >> 4;
-      const uint32_t mtile16 = (16u * p.m_plane) >> 4;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        tc::mbar_wait(&full_m[stage], phase);
-        tc::mbar_wait(&full_n[stage], phase);
-        tc::tc_fence_after();
-        const uint64_t m_base = m_desc0 + (uint64_t)((uint32_t)stage * stage16);
-        const uint64_t n_base = n_desc0 + (uint64_t)((uint32_t)stage * stage16);
-        if (tc::elect_one()) {
-          for (int kh = 0; kh < 3; ++kh) {
-            for (int t = 0; t < p.m_tiles; ++t) {
-              uint64_t a_hi = m_base + (uint64_t)((uint32_t)kh * 8u + (uint32_t)t * mtile16);
-              uint64_t b_hi = n_base;
-              const uint32_t d = tmem_base + (uint32_t)((kh * p.m_tiles + t) * p.nt);
-              uint32_t accum = accum_first;
-#pragma unroll 2
-              for (int j = 0; j < ksteps; ++j) {
-                tc::mma_bf16(d, a_hi, b_hi, idesc, accum);
-                tc::mma_bf16(d, a_hi, b_hi + n_lo16, idesc, 1u);
-                tc::mma_bf16(d, a_hi + split_lo16, b_hi, idesc, 1u);
-                accum = 1u;
-                a_hi += big_step16;
-                b_hi += 16u;
-              }
-            }
-          }
-          tc::mma_commit(&empty[stage]);
-        }
-        __syncwarp();
-        accum_first = 1u;
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-      }
-    } else {
-      const uint32_t big_lbo = (p.stride == 1) ? 160u : 544u;            // next tile row of `big`
-      const uint32_t big_step16 = (p.stride == 1) ? 20u : 68u;            // two tile rows of `big`
-      const uint32_t m_step16 = p.big_is_m ? big_step16 : 16u, n_step16 = p.big_is_m ? 16u : big_step16;
-      const uint64_t m_desc0 = tc::smem_desc(tc::smem_u32(tcw_smem), p.big_is_m ? big_lbo : 128u, p.m_plane);
-      const uint64_t n_desc0 = tc::smem_desc(tc::smem_u32(tcw_smem) + p.m_bytes, p.big_is_m ? 128u : big_lbo, p.n_plane);
-      const uint32_t m_lo16 = ((uint32_t)qm * p.m_plane) >> 4, n_lo16 = ((uint32_t)qn * p.n_plane) >> 4;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        tc::mbar_wait(&full_m[stage], phase);
-        tc::mbar_wait(&full_n[stage], phase);
-        tc::tc_fence_after();
-        const uint64_t m_base = m_desc0 + (uint64_t)((uint32_t)stage * stage16);
-        const uint64_t n_base = n_desc0 + (uint64_t)((uint32_t)stage * stage16);
-        if (tc::elect_one()) {
-          for (int tl = 0; tl < ntap; ++tl) {
-            const int tap = tap0 + tl, kh = tap / 3, kw = tap % 3;
-            const uint32_t tap16 = (p.stride == 1) ? (uint32_t)(kh * 10 + kw) : (uint32_t)(kh * 17 + (kw & 1) * 9 + (kw >> 1));
-            uint64_t a_hi = m_base + (uint64_t)(p.big_is_m ? tap16 : 0u);
-            uint64_t b_hi = n_base + (uint64_t)(p.big_is_m ? 0u : tap16);
-            const uint32_t d = tmem_base + (uint32_t)(tl * p.nt);
-            uint32_t accum = accum_first;
+    uint32_t ph = 0, accum_first = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      tc::mbar_wait(&full[stage], ph);
+      tc::tc_fence_after();
+      const uint64_t m_base = m_desc0 + (uint64_t)((uint32_t)stage * stage16);
+      const uint64_t n_base = n_desc0 + (uint64_t)((uint32_t)stage * stage16);
+      if (tc::elect_one()) {
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const uint32_t kw16 = (S == 1) ? (uint32_t)kw : (uint32_t)((kw & 1) * 9 + (kw >> 1));
+          uint64_t a_hi = m_base + (uint64_t)kw16;
+          uint64_t b_hi = n_base;
+          const uint32_t d = tmem_base + (uint32_t)(kw * acc_w);
+          uint32_t accum = accum_first;
+          if (p.cat) {
 #pragma unroll 2
             for (int j = 0; j < ksteps; ++j) {
-              tc::mma_bf16(d, a_hi, b_hi, idesc, accum);
-              tc::mma_bf16(d, a_hi, b_hi + n_lo16, idesc, 1u);
-              tc::mma_bf16(d, a_hi + m_lo16, b_hi, idesc, 1u);
+              tc::mma_bf16(d, a_hi, b_hi, idesc_w, accum);
+              tc::mma_bf16(d, a_hi + m_lo16, b_hi, idesc_n, 1u);
+              accum = 1u;
+              a_hi += m_step16;
+              b_hi += n_step16;
+            }
+          } else {
+#pragma unroll 2
+            for (int j = 0; j < ksteps; ++j) {
+              tc::mma_bf16(d, a_hi, b_hi, idesc_n, accum);
+              tc::mma_bf16(d, a_hi, b_hi + n_lo16, idesc_n, 1u);
+              tc::mma_bf16(d, a_hi + m_lo16, b_hi, idesc_n, 1u);
               accum = 1u;
               a_hi += m_step16;
               b_hi += n_step16;
             }
           }
-          tc::mma_commit(&empty[stage]);
         }
-        __syncwarp();
-        accum_first = 1u;
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        tc::mma_commit(&empty[stage]);
       }
+      __syncwarp();
+      accum_first = 1u;
+      if (++stage == p.stages) { stage = 0; ph ^= 1u; }
     }
     if (tc::elect_one()) tc::mma_commit(&done);
     __syncwarp();
@@ -323,5 +282,5 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const TcwParam
 
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 8) tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (warp == 9) tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
