@@ -35,11 +35,13 @@ SIGNATURES = {
     "gs_bias_act": [_P, _P, _P, _L, _I, _I, _P],
     "gs_row_broadcast": [_P, _P, _L, _I, _P],
     "gs_col_sum": [_P, _P, _L, _I, _P],
+    "gs_lrelu_mask_mul_colsum": [_P, _P, _P, _P, _L, _I, _P],
     "gs_axpby": [_P, _P, _P, _F, _F, _L, _P],
     "gs_mul": [_P, _P, _P, _F, _L, _P],
     "gs_pixel_norm_fwd": [_P, _P, _P, _L, _I, _F, _P],
     "gs_pixel_norm_bwd": [_P, _P, _P, _P, _L, _I, _P],
     "gs_pixel_norm_bwd2": [_P, _P, _P, _P, _P, _L, _I, _P],
+    "gs_pixel_norm_bwd_mask": [_P, _P, _P, _P, _P, _L, _I, _P],
     "gs_batch_stddev_fwd": [_P, _P, _I, _L, _I, _F, _P],
     "gs_batch_stddev_bwd": [_P, _P, _P, _I, _L, _I, _F, _P],
     "gs_batch_stddev_bwd2": [_P, _P, _P, _P, _P, _I, _L, _I, _F, _P],

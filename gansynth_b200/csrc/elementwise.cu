@@ -31,6 +31,27 @@ __global__ void mask_mul4_kernel(const float4* __restrict__ v, const float4* __r
     o[i] = r;
   }
 }
+// o = v * lrelu'(y) and colsum[c] += sum_rows o  (bias gradient of the layer in the same pass).  The grid stride is
+// a multiple of c / 4, so every thread stays on one group of four channels.
+__global__ void mask_mul_colsum_kernel(const float4* __restrict__ v, const float4* __restrict__ y, float4* __restrict__ o,
+                                       float* __restrict__ colsum, size_t n4, int c4) {
+  __shared__ float cs[256];
+  for (int i = threadIdx.x; i < 4 * c4; i += blockDim.x) cs[i] = 0.0f;
+  __syncthreads();
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  GS_GRID_STRIDE(i, n4) {
+    float4 a = v[i], b = y[i], r;
+    r.x = a.x * gs_lrelu_slope(b.x); r.y = a.y * gs_lrelu_slope(b.y);
+    r.z = a.z * gs_lrelu_slope(b.z); r.w = a.w * gs_lrelu_slope(b.w);
+    o[i] = r;
+    acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
+  }
+  const int g = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) % (size_t)c4);
+  atomicAdd(&cs[4 * g + 0], acc.x); atomicAdd(&cs[4 * g + 1], acc.y);
+  atomicAdd(&cs[4 * g + 2], acc.z); atomicAdd(&cs[4 * g + 3], acc.w);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * c4; i += blockDim.x) atomicAdd(colsum + i, cs[i]);
+}
 __global__ void lrelu_kernel(const float* __restrict__ x, float* __restrict__ o, size_t n) {
   GS_GRID_STRIDE(i, n) o[i] = gs_lrelu(x[i]);
 }
@@ -108,6 +129,8 @@ __global__ void pixel_norm_kernel(const float* __restrict__ a, const float* __re
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const float inv_c = 1.0f / (float)c;
   const bool vec = (c % 4) == 0;
+  float4 cacc0 = make_float4(0.f, 0.f, 0.f, 0.f), cacc1 = cacc0;   // MODE 3: bias-gradient partial sums of this lane
+  (void)cacc0; (void)cacc1;
   for (long long row = warp; row < rows; row += nwarps) {
     const float* ap = a + (size_t)row * c;
     float* op = out + (size_t)row * c;
@@ -134,6 +157,24 @@ __global__ void pixel_norm_kernel(const float* __restrict__ a, const float* __re
         o.x = r * d.x - k * t.x; o.y = r * d.y - k * t.y; o.z = r * d.z - k * t.z; o.w = r * d.w - k * t.w;
         *reinterpret_cast<float4*>(op + i) = o; }
       else for (int i = lane; i < c; i += 32) op[i] = r * dp[i] - k * ap[i];
+    } else if (MODE == 3) {
+      // dz = lrelu'(a) * [ r*dy - (r^3/C) (a.dy) a ]: pixel-norm backward and the leaky-relu mask of the layer
+      // that produced a, in one pass; optionally the bias gradient colsum[c] += sum_rows dz (c % 4 == 0, c <= 256)
+      const float* dp = dy + (size_t)row * c;
+      float dot = 0.0f;
+      for (int i = lane * 4; i < c; i += 128) { float4 t = *reinterpret_cast<const float4*>(ap + i); float4 d = *reinterpret_cast<const float4*>(dp + i); dot += t.x * d.x + t.y * d.y + t.z * d.z + t.w * d.w; }
+      dot = gs_warp_sum(dot);
+      float r = rin[row];
+      float k = r * r * r * inv_c * dot;
+      int slot = 0;
+      for (int i = lane * 4; i < c; i += 128, ++slot) {
+        float4 t = *reinterpret_cast<const float4*>(ap + i); float4 d = *reinterpret_cast<const float4*>(dp + i); float4 o;
+        o.x = (r * d.x - k * t.x) * gs_lrelu_slope(t.x); o.y = (r * d.y - k * t.y) * gs_lrelu_slope(t.y);
+        o.z = (r * d.z - k * t.z) * gs_lrelu_slope(t.z); o.w = (r * d.w - k * t.w) * gs_lrelu_slope(t.w);
+        *reinterpret_cast<float4*>(op + i) = o;
+        if (slot == 0) { cacc0.x += o.x; cacc0.y += o.y; cacc0.z += o.z; cacc0.w += o.w; }
+        else { cacc1.x += o.x; cacc1.y += o.y; cacc1.z += o.z; cacc1.w += o.w; }
+      }
     } else {
       // ga = -(r^3/C) [ (u.dy) a + (a.dy) u + (u.a) dy ] + 3 (r^5/C^2) (u.a)(a.dy) a
       const float* dp = dy + (size_t)row * c;
@@ -147,6 +188,16 @@ __global__ void pixel_norm_kernel(const float* __restrict__ a, const float* __re
       float ku = -r3c * ad, kd = -r3c * ua;
       for (int i = lane; i < c; i += 32) op[i] = ka * ap[i] + ku * up[i] + kd * dp[i];
     }
+  }
+  if (MODE == 3 && rout != nullptr) {
+    // rout doubles as the bias-gradient output [c] in this mode
+    __shared__ float cs[256];
+    for (int i = threadIdx.x; i < c; i += blockDim.x) cs[i] = 0.0f;
+    __syncthreads();
+    if (lane * 4 < c) { atomicAdd(&cs[lane * 4], cacc0.x); atomicAdd(&cs[lane * 4 + 1], cacc0.y); atomicAdd(&cs[lane * 4 + 2], cacc0.z); atomicAdd(&cs[lane * 4 + 3], cacc0.w); }
+    if (lane * 4 + 128 < c) { atomicAdd(&cs[lane * 4 + 128], cacc1.x); atomicAdd(&cs[lane * 4 + 129], cacc1.y); atomicAdd(&cs[lane * 4 + 130], cacc1.z); atomicAdd(&cs[lane * 4 + 131], cacc1.w); }
+    __syncthreads();
+    for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(rout + i, cs[i]);
   }
 }
 
@@ -399,6 +450,28 @@ extern "C" int gs_pixel_norm_bwd2(const float* a, const float* r, const float* d
   if (rows == 0) return GS_OK;
   pixel_norm_kernel<2><<<pn_grid(rows), EW_BLOCK, 0, ST>>>(a, r, dy, u, ga, nullptr, rows, c, 0.f);
   GS_CHECK_LAUNCH("pixel_norm_bwd2");
+  return GS_OK;
+}
+
+extern "C" int gs_pixel_norm_bwd_mask(const float* a, const float* r, const float* dy, float* dz, float* colsum, long long rows,
+                                      int c, void* stream) {
+  GS_CHECK_ARG(rows >= 0 && c > 0 && c % 4 == 0 && c <= 256, "pixel_norm_bwd_mask: needs c %% 4 == 0, c <= 256 (got %d)", c);
+  if (colsum) GS_CUDA(cudaMemsetAsync(colsum, 0, (size_t)c * sizeof(float), ST));
+  if (rows == 0) return GS_OK;
+  pixel_norm_kernel<3><<<pn_grid(rows), EW_BLOCK, 0, ST>>>(a, r, dy, nullptr, dz, colsum, rows, c, 0.f);
+  GS_CHECK_LAUNCH("pixel_norm_bwd_mask");
+  return GS_OK;
+}
+extern "C" int gs_lrelu_mask_mul_colsum(const float* v, const float* y, float* out, float* colsum, long long rows, int c,
+                                        void* stream) {
+  GS_CHECK_ARG(rows >= 0 && c > 0 && c % 4 == 0 && c <= 256 && 256 % (c / 4) == 0,
+               "lrelu_mask_mul_colsum: needs c %% 4 == 0, c <= 256, c / 4 a divisor of 256 (got %d)", c);
+  GS_CUDA(cudaMemsetAsync(colsum, 0, (size_t)c * sizeof(float), ST));
+  if (rows == 0) return GS_OK;
+  const size_t n4 = (size_t)rows * c / 4;
+  mask_mul_colsum_kernel<<<ew_grid(n4 * 4), EW_BLOCK, 0, ST>>>(reinterpret_cast<const float4*>(v), reinterpret_cast<const float4*>(y),
+                                                               reinterpret_cast<float4*>(out), colsum, n4, c / 4);
+  GS_CHECK_LAUNCH("lrelu_mask_mul_colsum");
   return GS_OK;
 }
 

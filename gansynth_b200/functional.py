@@ -15,6 +15,7 @@ it is a CudaBackend in the product.  (tests/ swap in a torch-CPU emulation of th
 check this module's graph logic against the oracle without a GPU.)
 """
 import contextlib
+import os
 
 import torch
 from torch.autograd import Function
@@ -33,6 +34,9 @@ def set_backend(backend):
 
 
 _SKIP_WGRAD = False
+# GS_NO_FUSED_EW=1 keeps the un-fused elementwise chain (MaskMul, ColSum, PixelNorm) for A/B runs
+FUSED_EW = os.environ.get("GS_NO_FUSED_EW", "0") != "1"
+FUSED_MC = FUSED_EW and os.environ.get("GS_NO_FUSED_MC", "0") != "1"
 
 
 @contextlib.contextmanager
@@ -105,14 +109,16 @@ class ConvW(Function):
 
 class ConvLayer(Function):
     """Fused layer forward: act(alpha * conv(x, w) + bias), conv in gather (`form`='c') or transposed
-    ('t') form.  The backward un-fuses into MaskMul / ColSum / the trio so it stays differentiable."""
+    ('t') form.  The backward un-fuses into MaskMul(+ColSum) / the trio so it stays differentiable.
+    `premasked`: the consumer of y (PixelNormOfLayer) hands back a gradient that already carries the
+    leaky-relu mask of this layer, so the backward must not apply it again."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, form, ksize, stride, wswap, alpha, act):
+    def forward(ctx, x, w, bias, form, ksize, stride, wswap, alpha, act, premasked=False):
         fn = K.conv_c if form == "c" else K.conv_t
         y = fn(x, w, bias, ksize, stride, wswap, alpha, act, precise=True)
         ctx.cfg = (ksize, stride, wswap, alpha)
-        ctx.form, ctx.act, ctx.has_bias = form, act, bias is not None
+        ctx.form, ctx.act, ctx.has_bias, ctx.premasked = form, act, bias is not None, premasked
         ctx.save_for_backward(x, w, y)
         return y
 
@@ -120,15 +126,23 @@ class ConvLayer(Function):
     def backward(ctx, dy):
         x, w, y = ctx.saved_tensors
         cfg = ctx.cfg
-        dz = MaskMul.apply(dy, y) if ctx.act == ACT_LRELU else dy
-        dx = dw = db = None
+        want_db = ctx.has_bias and ctx.needs_input_grad[2] and not _SKIP_WGRAD
+        db = None
+        if ctx.act == ACT_LRELU and not ctx.premasked:
+            if want_db and FUSED_MC:
+                dz, db = MaskMulColSum.apply(dy, y)      # mask and bias gradient in one pass
+            else:
+                dz = MaskMul.apply(dy, y)
+        else:
+            dz = dy
+        dx = dw = None
         if ctx.needs_input_grad[0]:
             dx = (ConvT if ctx.form == "c" else ConvC).apply(dz, w, *cfg)
         if ctx.needs_input_grad[1] and not _SKIP_WGRAD:
             dw = ConvW.apply(x, dz, *cfg) if ctx.form == "c" else ConvW.apply(dz, x, *cfg)
-        if ctx.has_bias and ctx.needs_input_grad[2] and not _SKIP_WGRAD:
+        if want_db and db is None:
             db = ColSum.apply(dz)
-        return dx, dw, db, None, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None, None
 
 
 # ----------------------------------------------------------------------------- activations / bias
@@ -144,6 +158,43 @@ class MaskMul(Function):
     def backward(ctx, g):
         (y,) = ctx.saved_tensors
         return MaskMul.apply(g, y), None
+
+
+class MaskMulColSum(Function):
+    """(v * lrelu'(y), bias gradient = column sums of that product) in one pass.  The bias gradient only
+    feeds the optimiser: it is never differentiated."""
+
+    @staticmethod
+    def forward(ctx, v, y):
+        ctx.save_for_backward(y)
+        out, cs = K.mask_mul_colsum(v, y)
+        ctx.mark_non_differentiable(cs)
+        return out, cs
+
+    @staticmethod
+    def backward(ctx, g, _gcs):
+        (y,) = ctx.saved_tensors
+        return MaskMul.apply(g, y), None
+
+
+class PnBwdMask(Function):
+    """dz = lrelu'(a) * pixel_norm_backward(a, r, dy) in one pass.  With M = lrelu'(a) (piecewise constant)
+    and J(a) the symmetric pixel-norm Jacobian: dz = M J dy, so for an incoming u
+    d/d(dy) = J (M u) and d/da = pn_bwd2(a, r, dy, M u) -- returned as M * (d/da), the gradient w.r.t. the
+    pre-activation, because `a` only ever comes from a premasked ConvLayer."""
+
+    @staticmethod
+    def forward(ctx, a, r, dy):
+        ctx.save_for_backward(a, r, dy)
+        return K.pn_bwd_mask(a, r, dy, False)[0]
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, u):
+        a, r, dy = ctx.saved_tensors
+        mu = K.mask_mul(u, a)
+        # `a` is the output of a premasked ConvLayer: every gradient handed to it must already carry the mask
+        return K.mask_mul(K.pn_bwd2(a, r, dy, mu), a), None, K.pn_bwd(a, r, mu)
 
 
 class LeakyRelu(Function):
@@ -267,6 +318,24 @@ class PixelNorm(Function):
     def backward(ctx, dy):
         a, r = ctx.saved_tensors
         return PixelNormBwd.apply(a, r, dy), None
+
+
+class PixelNormOfLayer(Function):
+    """Pixel normalisation of the output `a` of a leaky-relu ConvLayer built with premasked=True (the
+    generator's conv -> leaky_relu -> pixel_normalization triple, networks.py:57-68, 82-93).  Its backward
+    returns the gradient w.r.t. the layer's PRE-activation: pixel-norm backward and the leaky-relu mask
+    (taken from the sign of a) share one pass."""
+
+    @staticmethod
+    def forward(ctx, a, eps):
+        y, r = K.pn_fwd(a, eps)
+        ctx.save_for_backward(a, r)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, r = ctx.saved_tensors
+        return PnBwdMask.apply(a, r, dy), None
 
 
 class PixelNormBwd(Function):

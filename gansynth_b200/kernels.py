@@ -138,6 +138,18 @@ class CudaBackend(object):
     def mask_mul(self, v, y):
         return self._ew("gs_lrelu_mask_mul", v, y)
 
+    def mask_mul_colsum(self, v, y):
+        """(v * lrelu'(y), column sums of that product over the last axis) in one pass."""
+        v, y = _chk(v, y)
+        c = v.shape[-1]
+        if c % 4 or c > 256 or 256 % (c // 4):
+            out = self.mask_mul(v, y)
+            return out, self.col_sum(out)
+        out = torch.empty_like(v)
+        cs = torch.empty((c,), device=v.device, dtype=torch.float32)
+        _lib.call("gs_lrelu_mask_mul_colsum", _ptr(v), _ptr(y), _ptr(out), _ptr(cs), v.numel() // c, c, _stream())
+        return out, cs
+
     def tanh_fwd(self, x):
         return self._ew("gs_tanh_fwd", x)
 
@@ -189,6 +201,18 @@ class CudaBackend(object):
         da = torch.empty_like(a)
         _lib.call("gs_pixel_norm_bwd", _ptr(a), _ptr(r), _ptr(dy), _ptr(da), a.numel() // c, c, _stream())
         return da
+
+    def pn_bwd_mask(self, a, r, dy, want_colsum):
+        """lrelu'(a) * pixel-norm backward (a, r, dy); with want_colsum also the column sums (bias gradient)."""
+        a, r, dy = _chk(a, r, dy)
+        c = a.shape[-1]
+        if c % 4 or c > 256:
+            dz = self.mask_mul(self.pn_bwd(a, r, dy), a)
+            return dz, (self.col_sum(dz) if want_colsum else None)
+        dz = torch.empty_like(a)
+        cs = torch.empty((c,), device=a.device, dtype=torch.float32) if want_colsum else None
+        _lib.call("gs_pixel_norm_bwd_mask", _ptr(a), _ptr(r), _ptr(dy), _ptr(dz), _ptr(cs), a.numel() // c, c, _stream())
+        return dz, cs
 
     def pn_bwd2(self, a, r, dy, u):
         a, r, dy, u = _chk(a, r, dy, u)

@@ -14,6 +14,7 @@ latents.  Here each run is an eager sub-step:
 Data parallel (new design): one process per GPU, identical replicas, rank-local batch (and
 rank-local batch_stddev groups), one NCCL all-reduce of the flat gradient buffer per sub-step.
 """
+import gc
 import glob
 import os
 import time
@@ -85,6 +86,7 @@ class GANSynth(object):
         self._opt = None
         self._graphs = {}
         self._graph_pool = None
+        self._stream = None
         self.use_cuda_graphs = os.environ.get("GS_CUDA_GRAPHS", "1") != "0"
         self.generator_loss = None
         self.discriminator_loss = None
@@ -237,12 +239,27 @@ class GANSynth(object):
         return True
 
     def _run_body(self, scope, body, inputs):
-        """Runs `body(*inputs)` eagerly the first two times (lazy variable creation, workspace growth, function
-        attributes), then captures it into a CUDA graph and replays the graph on static input buffers.  The
-        all-reduce and the Adam launch stay outside the graph (the Adam step count is a kernel argument)."""
-        use = (self.use_cuda_graphs and all(t.is_cuda for t in inputs) and self._static_structure()
-               and not torch.cuda.is_current_stream_capturing())
-        if not use:
+        """Runs `body(*inputs)` on the model's own stream: eagerly the first two times (lazy variable creation,
+        workspace growth, function attributes), then captured into a CUDA graph (on the same stream, so that
+        every autograd node -- the variables' AccumulateGrad nodes included -- lives on the capturing stream)
+        and replayed on static input buffers.  The all-reduce and the Adam launch stay outside the graph (the
+        Adam step count is a kernel argument)."""
+        if not all(t.is_cuda for t in inputs):
+            return body(*inputs)
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(inputs[0].device)
+        outer = torch.cuda.current_stream()
+        if outer == self._stream or torch.cuda.is_current_stream_capturing():
+            return body(*inputs)
+        self._stream.wait_stream(outer)
+        with torch.cuda.stream(self._stream):
+            loss = self._run_body_on_stream(scope, body, inputs)
+        outer.wait_stream(self._stream)
+        return loss
+
+    def _run_body_on_stream(self, scope, body, inputs):
+        from . import _lib
+        if not (self.use_cuda_graphs and self._static_structure()):
             return body(*inputs)
         key = (scope,) + tuple(tuple(t.shape) for t in inputs)
         entry = self._graphs.setdefault(key, dict(calls=0))
@@ -250,20 +267,14 @@ class GANSynth(object):
         if entry["calls"] <= 2:
             return body(*inputs)
         if "graph" not in entry:
-            from . import _lib
             static_in = [t.clone() for t in inputs]
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                body(*static_in)
-            torch.cuda.current_stream().wait_stream(side)
+            gc.collect()            # drop autograd graphs of earlier iterations that only cycles keep alive
             graph = torch.cuda.CUDAGraph()
-            # the variables' AccumulateGrad nodes were created on the eager stream; autograd.grad never uses them
-            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
             before = _lib.launch_count
-            # the two sub-step graphs never overlap in time: they share one memory pool
-            pool = self._graph_pool
-            with torch.cuda.graph(graph, pool=pool):
+            # the two sub-step graphs never overlap in time: they share one memory pool.
+            # thread_local: the NCCL watchdog thread may query events while this thread captures
+            pool = None if os.environ.get("GS_GRAPH_NO_SHARED_POOL") else self._graph_pool
+            with torch.cuda.graph(graph, pool=pool, stream=self._stream, capture_error_mode="thread_local"):
                 loss = body(*static_in)
             if pool is None:
                 self._graph_pool = graph.pool()
@@ -272,7 +283,6 @@ class GANSynth(object):
         for dst, src in zip(entry["static_in"], inputs):
             dst.copy_(src, non_blocking=True)
         entry["graph"].replay()
-        from . import _lib
         _lib.launch_count += entry["launches"]     # the captured kernels did launch
         return entry["loss"]
 
@@ -284,7 +294,7 @@ class GANSynth(object):
         self._ensure_optimizers(labels, latents)
         self.real_waveforms, self.real_labels, self.fake_labels = real_waveforms, labels, labels
         loss = self._run_body("discriminator", self._discriminator_body, (real_waveforms, labels, latents))
-        self._update("discriminator")
+        self._update("discriminator")            # on the caller's stream, after the join with the model stream
         self.discriminator_loss = loss
         return self.discriminator_loss
 

@@ -128,19 +128,19 @@ class PGGAN(object):
                         inputs = inputs.reshape(b, h, w, channels(depth))
                         inputs = pixel_normalization(inputs)
                     with variable_scope("conv"):
+                        # conv -> leaky_relu -> pixel_normalization (networks.py:57-68) as one fused layer
                         inputs = conv2d(inputs, filters=channels(depth), kernel_size=[3, 3], use_bias=True,
-                                        variance_scale=2.0, scale_weight=True, activation="leaky_relu")
-                        inputs = pixel_normalization(inputs)
+                                        variance_scale=2.0, scale_weight=True, activation="leaky_relu",
+                                        pixel_norm_epsilon=1.0e-12)
                     return inputs
                 with variable_scope("upscale_conv"):
                     inputs = conv2d_transpose(inputs, filters=channels(depth), kernel_size=[3, 3], strides=[2, 2],
                                               use_bias=True, variance_scale=2.0, scale_weight=True,
-                                              activation="leaky_relu")
-                    inputs = pixel_normalization(inputs)
+                                              activation="leaky_relu", pixel_norm_epsilon=1.0e-12)
                 with variable_scope("conv"):
                     inputs = conv2d(inputs, filters=channels(depth), kernel_size=[3, 3], use_bias=True,
-                                    variance_scale=2.0, scale_weight=True, activation="leaky_relu")
-                    inputs = pixel_normalization(inputs)
+                                    variance_scale=2.0, scale_weight=True, activation="leaky_relu",
+                                    pixel_norm_epsilon=1.0e-12)
                 return inputs
 
         def color_block(inputs, depth):

@@ -186,25 +186,38 @@ def embedding(inputs, units, variance_scale=2.0, scale_weight=False, apply_weigh
 
 
 def conv2d(inputs, filters, kernel_size, strides=[1, 1], use_bias=True, variance_scale=2.0, scale_weight=False,
-           apply_weight_standardization=False, apply_spectral_normalization=False, activation=None):
-    """ops.py:221-247.  NHWC, TF SAME padding, square kernel 1 or 3, stride 1 or 2."""
+           apply_weight_standardization=False, apply_spectral_normalization=False, activation=None,
+           pixel_norm_epsilon=None):
+    """ops.py:221-247.  NHWC, TF SAME padding, square kernel 1 or 3, stride 1 or 2.  `pixel_norm_epsilon`
+    (extension) appends pixel_normalization (ops.py:330-333) to the fused layer."""
     ksize, stride = _square(kernel_size), _square(strides)
     weight, alpha = get_weight([ksize, ksize, inputs.shape[-1], filters], variance_scale, scale_weight,
                                apply_weight_standardization, apply_spectral_normalization)
     bias = get_bias([filters]) if use_bias else None
-    return F.ConvLayer.apply(inputs, weight, bias, "c", ksize, stride, False, alpha, _act_code(activation))
+    return _layer(inputs, weight, bias, "c", ksize, stride, False, alpha, activation, pixel_norm_epsilon)
 
 
 def conv2d_transpose(inputs, filters, kernel_size, strides=[1, 1], use_bias=True, variance_scale=2.0,
                      scale_weight=False, apply_weight_standardization=False, apply_spectral_normalization=False,
-                     activation=None):
+                     activation=None, pixel_norm_epsilon=None):
     """ops.py:250-280.  The variable is [k, k, Cin, filters] (fan-in from that shape); output is
     [B, H*s, W*s, filters]."""
     ksize, stride = _square(kernel_size), _square(strides)
     weight, alpha = get_weight([ksize, ksize, inputs.shape[-1], filters], variance_scale, scale_weight,
                                apply_weight_standardization, apply_spectral_normalization)
     bias = get_bias([filters]) if use_bias else None
-    return F.ConvLayer.apply(inputs, weight, bias, "t", ksize, stride, True, alpha, _act_code(activation))
+    return _layer(inputs, weight, bias, "t", ksize, stride, True, alpha, activation, pixel_norm_epsilon)
+
+
+def _layer(inputs, weight, bias, form, ksize, stride, wswap, alpha, activation, pixel_norm_epsilon):
+    act = _act_code(activation)
+    if pixel_norm_epsilon is None:
+        return F.ConvLayer.apply(inputs, weight, bias, form, ksize, stride, wswap, alpha, act)
+    if act != F.ACT_LRELU or not F.FUSED_EW:
+        return pixel_normalization(F.ConvLayer.apply(inputs, weight, bias, form, ksize, stride, wswap, alpha, act),
+                                   pixel_norm_epsilon)
+    y = F.ConvLayer.apply(inputs, weight, bias, form, ksize, stride, wswap, alpha, act, True)
+    return F.PixelNormOfLayer.apply(y, pixel_norm_epsilon)
 
 
 def _square(v):

@@ -70,6 +70,9 @@ int gs_tanh_bwd2(const float* y, const float* dy, const float* u, float* out, lo
 int gs_bias_act(const float* x, const float* bias, float* out, long long rows, int c, int act, void* stream);
 int gs_row_broadcast(const float* s, float* out, long long rows, int c, void* stream);
 int gs_col_sum(const float* v, float* out, long long rows, int c, void* stream);                /* bias gradient */
+/* mask-multiply and the bias gradient of the same layer in one pass (the un-fused pair above is the TF graph's
+   LeakyReluGrad + BiasAddGrad of ops.py:237-247 / networks.py); c % 4 == 0, c <= 256, c/4 divides 256 */
+int gs_lrelu_mask_mul_colsum(const float* v, const float* y, float* out, float* colsum, long long rows, int c, void* stream);
 
 /* ---- lerp networks.py:10-11 and generic linear combinations ------------------------------------- */
 int gs_axpby(const float* a, const float* b, float* out, float alpha, float beta, long long n, void* stream);
@@ -78,6 +81,10 @@ int gs_mul(const float* a, const float* b, float* out, float alpha, long long n,
 /* ---- pixel_normalization ops.py:330-333 over the channel axis of [rows, c] ----------------------- */
 int gs_pixel_norm_fwd(const float* a, float* y, float* r, long long rows, int c, float eps, void* stream);
 int gs_pixel_norm_bwd(const float* a, const float* r, const float* dy, float* da, long long rows, int c, void* stream);
+/* pixel-norm backward fused with the leaky-relu mask of the layer that produced a (networks.py:57-68,82-93: conv ->
+   leaky_relu -> pixel_normalization); colsum (may be null) receives the bias gradient; c % 4 == 0, c <= 256 */
+int gs_pixel_norm_bwd_mask(const float* a, const float* r, const float* dy, float* dz, float* colsum, long long rows, int c,
+                           void* stream);
 int gs_pixel_norm_bwd2(const float* a, const float* r, const float* dy, const float* u, float* ga, long long rows,
                        int c, void* stream);
 

@@ -99,6 +99,14 @@ class EmuBackend(object):
     def row_broadcast(self, s, lead_shape):
         return s.expand(*lead_shape, s.numel()).contiguous()
 
+    def mask_mul_colsum(self, v, y):
+        out = self.mask_mul(v, y)
+        return out, self.col_sum(out)
+
+    def pn_bwd_mask(self, a, r, dy, want_colsum):
+        dz = self.mask_mul(self.pn_bwd(a, r, dy), a)
+        return dz, (self.col_sum(dz) if want_colsum else None)
+
     def col_sum(self, v):
         return v.reshape(-1, v.shape[-1]).sum(0)
 

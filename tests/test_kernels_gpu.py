@@ -140,6 +140,31 @@ def test_elementwise_and_pixel_norm(shape):
     assert rel_err(yk, ye) < 1e-6 and rel_err(rk, re_) < 1e-6
     assert rel_err(k.pn_bwd(ac, rk, dc), EMU.pn_bwd(a, re_, dy)) < 1e-5
     assert rel_err(k.pn_bwd2(ac, rk, dc, uc), EMU.pn_bwd2(a, re_, dy, u)) < 1e-5
+    # fused forms (fall back to the un-fused pair for channel counts the fused kernels do not cover)
+    om, cm = k.mask_mul_colsum(dc, ac)
+    oe, ce = EMU.mask_mul_colsum(dy, a)
+    assert torch.equal(om.cpu(), oe) and rel_err(cm, ce.double()) < 1e-5
+    for want in (False, True):
+        zk, ck = k.pn_bwd_mask(ac, rk, dc, want)
+        ze, ce = EMU.pn_bwd_mask(a, re_, dy, want)
+        assert rel_err(zk, ze) < 1e-5
+        assert (ck is None) == (not want)
+        if want:
+            assert rel_err(ck, ce.double()) < 1e-5
+
+
+def test_fused_mask_colsum_full_size():
+    """The top-resolution activation (8 x 128 x 1024 x 32): fused mask-multiply + bias gradient and fused
+    pixel-norm backward + mask against the un-fused kernels."""
+    k = _k()
+    a, dy = _rand(8, 128, 1024, 32, seed=1).cuda(), _rand(8, 128, 1024, 32, seed=2).cuda()
+    om, cm = k.mask_mul_colsum(dy, a)
+    ref = k.mask_mul(dy, a)
+    assert torch.equal(om, ref) and rel_err(cm, ref.double().sum((0, 1, 2))) < 1e-5
+    _, r = k.pn_fwd(a, 1e-12)
+    zk, ck = k.pn_bwd_mask(a, r, dy, True)
+    zr = k.mask_mul(k.pn_bwd(a, r, dy), a)
+    assert rel_err(zk, zr) < 1e-6 and rel_err(ck, zr.double().sum((0, 1, 2))) < 1e-5
 
 
 def test_col_sum_large():
