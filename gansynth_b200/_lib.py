@@ -16,6 +16,7 @@ _F = ctypes.c_float
 
 # name -> argument types (all functions return int); mirrors include/gansynth_b200.h
 SIGNATURES = {
+    "gs_conv_weight_cache_reset": [],
     "gs_conv2d_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P],
     "gs_conv2d_dgrad": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P],
     "gs_conv2d_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
@@ -84,6 +85,10 @@ def load():
         fn.restype = _I
     _lib = lib
     return lib
+
+
+def is_loaded():
+    return _lib is not None
 
 
 launch_count = 0

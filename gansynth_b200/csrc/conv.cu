@@ -124,11 +124,23 @@ int try_conv1x1(const float* x, const float* w, const float* bias, float* y, lon
 
 // ------------------------------------------------------------------------------------------------
 // tcgen05 path
+// Workspace of pre-split (bf16 hi/lo) weights: an 8 MB scratch slot (weights used once: gradient-of-gradient
+// operands) followed by a cache region for PARAMETER weights.  Within one optimiser sub-step a parameter is
+// used by several convolutions in the same orientation (D(real), D(fake), the penalty passes): it is split
+// once.  The host invalidates the cache whenever the parameters change (gs_conv_weight_cache_reset) and at the
+// start of every sub-step, so a captured CUDA graph always contains the split kernel of the first use.
 struct TcWorkspace {
-  __nv_bfloat16* buf = nullptr;
-  size_t bytes = 0;
+  unsigned char* buf = nullptr;
+  size_t scratch = (size_t)8 << 20, cache = (size_t)256 << 20, used = 0;
 };
-TcWorkspace g_tc_ws;   // grow-only; calls are stream-ordered on one stream per process (see gansynth_b200.h)
+TcWorkspace g_tc_ws;   // calls are stream-ordered on one stream per process (see gansynth_b200.h)
+struct PrepKey {
+  const float* w;
+  int kdim, ndim, nt, kc, kn, flip;
+  size_t off;
+};
+PrepKey g_prep[512];
+int g_nprep = 0;
 
 int tc_auto_enabled() {
   static int v = -1;
@@ -150,18 +162,14 @@ bool tc_ok(int form, int ksize, int kdim, int ndim, int th_dim, int tw_dim) {
 
 template <int FORM, int KC>
 int launch_tc_impl(const float* x, const float* w, const float* bias, float* y, int n, int h_in, int w_in, int h_out,
-                   int w_out, int kdim, int ndim, int w_is_kn, int flip, float alpha, int act, cudaStream_t st) {
+                   int w_out, int kdim, int ndim, int w_is_kn, int flip, float alpha, int act, bool cacheable,
+                   cudaStream_t st) {
   using G = TcGeo<FORM>;
   const size_t wbytes = (size_t)9 * kdim * ndim * 2 * sizeof(__nv_bfloat16);
-  if (g_tc_ws.bytes < wbytes) {
-    GS_CUDA(cudaStreamSynchronize(st));
-    if (g_tc_ws.buf) GS_CUDA(cudaFree(g_tc_ws.buf));
-    size_t want = wbytes < ((size_t)8 << 20) ? ((size_t)8 << 20) : wbytes;
-    GS_CUDA(cudaMalloc(&g_tc_ws.buf, want));
-    g_tc_ws.bytes = want;
-  }
+  GS_CHECK_ARG(wbytes <= g_tc_ws.scratch, "conv_tc: weight of %zu bytes exceeds the scratch slot", wbytes);
+  if (!g_tc_ws.buf) GS_CUDA(cudaMalloc(&g_tc_ws.buf, g_tc_ws.scratch + g_tc_ws.cache));
   TcParams p;
-  p.wprep = g_tc_ws.buf; p.bias = bias; p.y = y;
+  p.bias = bias; p.y = y;
   p.n_img = n; p.h_in = h_in; p.w_in = w_in; p.h_out = h_out; p.w_out = w_out; p.kdim = kdim; p.ndim = ndim;
   p.alpha = alpha; p.act = act;
   const int th_dim = (FORM == TC_T2) ? h_in : h_out, tw_dim = (FORM == TC_T2) ? w_in : w_out;
@@ -230,11 +238,32 @@ int launch_tc_impl(const float* x, const float* w, const float* bias, float* y, 
   while (cols < p.nbuf * G::NACC * nt * (1 + p.cat)) cols <<= 1;
   p.tmem_cols = cols;
   {
-    size_t total = (size_t)9 * kdim * ndim;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > gs_num_sms() * 8) blocks = gs_num_sms() * 8;
-    conv_tc_prep_kernel<KC><<<blocks, 256, 0, st>>>(w, g_tc_ws.buf, kdim, ndim, nt, w_is_kn, flip);
-    GS_CHECK_LAUNCH("conv_tc_prep");
+    // pre-split weights: cached copy of a parameter, else split now (into the cache or the scratch slot)
+    unsigned char* dst = g_tc_ws.buf;
+    bool need_prep = true;
+    if (cacheable) {
+      for (int i = 0; i < g_nprep; ++i) {
+        const PrepKey& k = g_prep[i];
+        if (k.w == w && k.kdim == kdim && k.ndim == ndim && k.nt == nt && k.kc == KC && k.kn == w_is_kn && k.flip == flip) {
+          dst = g_tc_ws.buf + g_tc_ws.scratch + k.off;
+          need_prep = false;
+          break;
+        }
+      }
+      if (need_prep && g_nprep < 512 && g_tc_ws.used + wbytes <= g_tc_ws.cache) {
+        g_prep[g_nprep++] = PrepKey{w, kdim, ndim, nt, KC, w_is_kn, flip, g_tc_ws.used};
+        dst = g_tc_ws.buf + g_tc_ws.scratch + g_tc_ws.used;
+        g_tc_ws.used += (wbytes + 255) & ~(size_t)255;
+      }
+    }
+    if (need_prep) {
+      size_t total = (size_t)9 * kdim * ndim;
+      int blocks = (int)((total + 255) / 256);
+      if (blocks > gs_num_sms() * 8) blocks = gs_num_sms() * 8;
+      conv_tc_prep_kernel<KC><<<blocks, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(dst), kdim, ndim, nt, w_is_kn, flip);
+      GS_CHECK_LAUNCH("conv_tc_prep");
+    }
+    p.wprep = reinterpret_cast<const __nv_bfloat16*>(dst);
   }
   CUtensorMap tmx;
   TcOutMaps tmy;
@@ -278,11 +307,12 @@ int launch_tc_impl(const float* x, const float* w, const float* bias, float* y, 
 // accumulation, not the operand split, bounds the accuracy at ~1e-5.
 template <int FORM>
 int launch_tc(const float* x, const float* w, const float* bias, float* y, int n, int h_in, int w_in, int h_out,
-              int w_out, int kdim, int ndim, int w_is_kn, int flip, float alpha, int act, cudaStream_t st) {
+              int w_out, int kdim, int ndim, int w_is_kn, int flip, float alpha, int act, bool cacheable,
+              cudaStream_t st) {
   // the stride-2 gather form stages ~4x the pixels of the others: 16-channel chunks keep the rings in budget
   if (FORM == TC_C2)
-    return launch_tc_impl<FORM, 16>(x, w, bias, y, n, h_in, w_in, h_out, w_out, kdim, ndim, w_is_kn, flip, alpha, act, st);
-  return launch_tc_impl<FORM, 32>(x, w, bias, y, n, h_in, w_in, h_out, w_out, kdim, ndim, w_is_kn, flip, alpha, act, st);
+    return launch_tc_impl<FORM, 16>(x, w, bias, y, n, h_in, w_in, h_out, w_out, kdim, ndim, w_is_kn, flip, alpha, act, cacheable, st);
+  return launch_tc_impl<FORM, 32>(x, w, bias, y, n, h_in, w_in, h_out, w_out, kdim, ndim, w_is_kn, flip, alpha, act, cacheable, st);
 }
 
 // filter-gradient form on the tensor cores
@@ -378,6 +408,12 @@ int launch_tcw(const float* big, const float* small, float* dw, int n, int bh, i
 
 }  // namespace
 
+extern "C" int gs_conv_weight_cache_reset(void) {
+  g_nprep = 0;
+  g_tc_ws.used = 0;
+  return GS_OK;
+}
+
 extern "C" int gs_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, int n, int h, int wd,
                              int ci, int co, int ksize, int stride, int wswap, float alpha, int act, int impl,
                              void* stream) {
@@ -385,6 +421,8 @@ extern "C" int gs_conv2d_fwd(const float* x, const float* w, const float* bias, 
   int rc = make_geom(g, n, h, wd, ci, co, ksize, stride, wswap, alpha, act);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  const bool cacheable = (impl & GS_IMPL_PARAM_WEIGHT) != 0;   // w is a parameter: its bf16 split may be cached
+  impl &= 0xff;
   bool tiled = tiled_ok(g);
   if (impl == 4) impl = tiled ? 2 : 1;   // "fp32 auto": never the tensor-core kernel
   GS_CHECK_ARG(!(impl == 2 && !tiled), "conv2d_fwd: tiled kernel needs ksize 3 and channels %% 4 == 0");
@@ -393,8 +431,8 @@ extern "C" int gs_conv2d_fwd(const float* x, const float* w, const float* bias, 
     const bool tcok = tc_ok(form, ksize, ci, co, g.oh, g.ow);
     GS_CHECK_ARG(!(impl == 3 && !tcok), "conv2d_fwd: tensor-core kernel does not cover this shape");
     if (impl == 3 || (impl == 0 && tcok && tc_auto_enabled())) {
-      if (stride == 1) return launch_tc<TC_C1>(x, w, bias, y, n, h, wd, g.oh, g.ow, ci, co, !g.wswap, 0, alpha, act, st);
-      return launch_tc<TC_C2>(x, w, bias, y, n, h, wd, g.oh, g.ow, ci, co, !g.wswap, 0, alpha, act, st);
+      if (stride == 1) return launch_tc<TC_C1>(x, w, bias, y, n, h, wd, g.oh, g.ow, ci, co, !g.wswap, 0, alpha, act, cacheable, st);
+      return launch_tc<TC_C2>(x, w, bias, y, n, h, wd, g.oh, g.ow, ci, co, !g.wswap, 0, alpha, act, cacheable, st);
     }
   }
   if (impl != 1 && ksize == 1 && stride == 1) {
@@ -424,6 +462,8 @@ extern "C" int gs_conv2d_dgrad(const float* dy, const float* w, const float* bia
   int rc = make_geom(g, n, h, wd, ci, co, ksize, stride, wswap, alpha, act);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  const bool cacheable = (impl & GS_IMPL_PARAM_WEIGHT) != 0;
+  impl &= 0xff;
   bool tiled = tiled_ok(g);
   if (impl == 4) impl = tiled ? 2 : 1;
   GS_CHECK_ARG(!(impl == 2 && !tiled), "conv2d_dgrad: tiled kernel needs ksize 3 and channels %% 4 == 0");
@@ -433,8 +473,8 @@ extern "C" int gs_conv2d_dgrad(const float* dy, const float* w, const float* bia
     const bool tcok = stride == 1 ? tc_ok(form, ksize, co, ci, h, wd) : tc_ok(form, ksize, co, ci, g.oh, g.ow);
     GS_CHECK_ARG(!(impl == 3 && !tcok), "conv2d_dgrad: tensor-core kernel does not cover this shape");
     if (impl == 3 || (impl == 0 && tcok && tc_auto_enabled())) {
-      if (stride == 1) return launch_tc<TC_C1>(dy, w, bias, dx, n, h, wd, h, wd, co, ci, g.wswap, 1, alpha, act, st);
-      return launch_tc<TC_T2>(dy, w, bias, dx, n, g.oh, g.ow, h, wd, co, ci, g.wswap, 0, alpha, act, st);
+      if (stride == 1) return launch_tc<TC_C1>(dy, w, bias, dx, n, h, wd, h, wd, co, ci, g.wswap, 1, alpha, act, cacheable, st);
+      return launch_tc<TC_T2>(dy, w, bias, dx, n, g.oh, g.ow, h, wd, co, ci, g.wswap, 0, alpha, act, cacheable, st);
     }
   }
   if (impl != 1 && ksize == 1 && stride == 1) {

@@ -124,7 +124,7 @@ int ensure_tables(cudaStream_t st) {
 // Forward: waveform -> (log-mel magnitude, mel instantaneous frequency).
 // One warp per (clip, chunk of L consecutive frames); a chunk that does not start the clip first
 // recomputes frame t0-1 to get the previous mel phase.
-constexpr int FWD_WARPS = 8;
+constexpr int FWD_WARPS = 16;   // 16 x 12.25 KB of per-warp tiles + 16 KB of tables = 212 KB: one CTA of 16 warps per SM
 constexpr int FWD_WARP_FLOATS = WARP_BUF + NBINS;  // FFT tile (reused for mag/phase) + previous mel phase
 constexpr int FWD_SMEM = (2 * 1024 * 2 + FWD_WARPS * FWD_WARP_FLOATS) * 4;
 

@@ -48,8 +48,24 @@ class CudaBackend(object):
     # forms stay on the tensor cores (default -1: same as every other convolution)
     fwd_impl = int(os.environ.get("GS_CONV_FWD_IMPL", "-1"))
 
-    def _impl(self, precise):
-        return self.fwd_impl if (precise and self.fwd_impl >= 0) else self.impl
+    # address ranges of the packed parameter buffers: convolution weights inside them are flagged as cacheable
+    param_ranges = ()
+
+    def register_parameters(self, flats):
+        self.param_ranges = tuple((t.data_ptr(), t.data_ptr() + t.numel() * t.element_size()) for t in flats)
+        self.weight_cache_reset()
+
+    def weight_cache_reset(self):
+        if _lib.is_loaded():
+            _lib.load().gs_conv_weight_cache_reset()
+
+    def _impl(self, precise, w=None):
+        impl = self.fwd_impl if (precise and self.fwd_impl >= 0) else self.impl
+        if w is not None and self.param_ranges:
+            p = w.data_ptr()
+            if any(lo <= p < hi for lo, hi in self.param_ranges):
+                impl |= 0x100      # GS_IMPL_PARAM_WEIGHT
+        return impl
 
     # ------------------------------------------------------------------ convolution family
     def conv_c(self, x, w, bias, ksize, stride, wswap, alpha, act, precise=False):
@@ -59,7 +75,7 @@ class CudaBackend(object):
         assert (w.shape[3] if wswap else w.shape[2]) == ci, "conv_c: weight/input channel mismatch"
         y = torch.empty((n, h // stride, wd // stride, co), device=x.device, dtype=torch.float32)
         _lib.call("gs_conv2d_fwd", _ptr(x), _ptr(w), _ptr(bias), _ptr(y), n, h, wd, ci, co, ksize, stride,
-                  int(wswap), float(alpha), int(act), self._impl(precise), _stream())
+                  int(wswap), float(alpha), int(act), self._impl(precise, w), _stream())
         return y
 
     def conv_t(self, dy, w, bias, ksize, stride, wswap, alpha, act, precise=False):
@@ -70,7 +86,7 @@ class CudaBackend(object):
         h, wd = oh * stride, ow * stride
         dx = torch.empty((n, h, wd, ci), device=dy.device, dtype=torch.float32)
         _lib.call("gs_conv2d_dgrad", _ptr(dy), _ptr(w), _ptr(bias), _ptr(dx), n, h, wd, ci, co, ksize, stride,
-                  int(wswap), float(alpha), int(act), self._impl(precise), _stream())
+                  int(wswap), float(alpha), int(act), self._impl(precise, w), _stream())
         return dx
 
     def conv_w(self, x, dy, ksize, stride, wswap, alpha):

@@ -176,6 +176,7 @@ class GANSynth(object):
             flat = self.store.pack(scope)
             self._opt[scope] = dict(flat=flat, grad=torch.zeros_like(flat), m=torch.zeros_like(flat),
                                     v=torch.zeros_like(flat), t=0)
+        F.K.register_parameters([o["flat"] for o in self._opt.values()])
 
     def _set_trainable(self, scope):
         for n, v in self.store.vars.items():
@@ -207,6 +208,7 @@ class GANSynth(object):
         st["t"] += 1
         F.K.adam_step(st["flat"], gflat, st["m"], st["v"], hp[scope + "_learning_rate"], hp[scope + "_beta1"],
                       hp[scope + "_beta2"], 1.0e-8, st["t"], scale)
+        F.K.weight_cache_reset()       # the pre-split copies of the parameters are stale now
 
     def _apply(self, scope, loss):
         """minimize(loss, var_list=scope variables) (models.py:81-89) with TF-Adam semantics."""
@@ -218,6 +220,7 @@ class GANSynth(object):
         """Everything of the D sub-step up to the flat gradient: spectral front-end, G forward, D(real),
         D(fake), R1 double backward, gradients of the D variables."""
         self._set_trainable("discriminator")
+        F.K.weight_cache_reset()       # a (captured) sub-step always splits each parameter at its first use
         real_images = self.real_images_from_waveforms(real_waveforms)
         loss = self.discriminator_loss_fn(real_images, labels, latents)
         self._backward("discriminator", loss)
@@ -225,6 +228,7 @@ class GANSynth(object):
 
     def _generator_body(self, labels, latents):
         self._set_trainable("generator")
+        F.K.weight_cache_reset()
         loss = self.generator_loss_fn(labels, latents)
         self._backward("generator", loss)
         return loss.detach()

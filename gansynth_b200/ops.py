@@ -95,6 +95,7 @@ class VariableStore(object):
             for n, val in values.items():
                 t = torch.as_tensor(np.asarray(val) if not torch.is_tensor(val) else val)
                 self.vars[n].copy_(t.to(self.device, torch.float32))
+        F.K.weight_cache_reset()    # pre-split copies of the old values are stale
 
     def state(self):
         return OrderedDict((n, v.detach().cpu()) for n, v in self.vars.items())
@@ -113,6 +114,7 @@ def default_store():
 def set_default_store(store):
     global _default_store
     _default_store = store
+    F.K.register_parameters([])     # no parameter buffers are known for the new store yet (drops cached splits)
     return store
 
 

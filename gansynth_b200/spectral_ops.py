@@ -129,10 +129,12 @@ def _check_config(spectrogram_shape, overlap):
 def frames_per_chunk(batch, time_steps):
     """Frames one warp handles back to back; shorter chunks for small batches so the grid fills."""
     for cand in (16, 8, 4, 2, 1):
-        if time_steps % cand == 0 and batch * (time_steps // cand) >= 148 * 8 * 2:
+        if time_steps % cand == 0 and batch * (time_steps // cand) >= 148 * 16:
             return cand
-    for cand in (4, 2, 1):
-        if time_steps % cand == 0:
+    # small batches never fill the GPU: the chunk length only sets the latency of the longest warp
+    # (chunk + 1 recomputed frame), so take the shortest chunk that still fills every SM's 16 warps once
+    for cand in (2, 1):
+        if time_steps % cand == 0 and batch * (time_steps // cand) >= 148 * 4:
             return cand
     return 1
 

@@ -15,7 +15,9 @@
  *  - `act`: 0 none, 1 leaky-relu(0.2) applied after the bias;
  *  - `impl`: 0 auto (tensor-core kernel where the shape allows, else fp32), 1 naive anchor kernel,
  *    2 tiled fp32 FFMA kernel, 3 tcgen05 tensor-core kernel (2/3: error if the shape is unsupported),
- *    4 fp32 auto (tiled else naive; never the tensor-core kernel);
+ *    4 fp32 auto (tiled else naive; never the tensor-core kernel); OR-ed with GS_IMPL_PARAM_WEIGHT when `w` is a
+ *    network parameter (a pointer that stays valid and unchanged until gs_conv_weight_cache_reset): the
+ *    tensor-core kernels may then reuse its pre-split bf16 copy across calls;
  *  - `stream` is a cudaStream_t; every call is asynchronous on it, no hidden synchronisation (the
  *    spectral entry points synchronise once, on first use, to upload twiddle tables);
  *  - return 0 on success, negative on error; gs_last_error() gives the message (thread-local).
@@ -29,6 +31,11 @@ extern "C" {
 
 const char* gs_last_error(void);
 int gs_version(void);
+
+#define GS_IMPL_PARAM_WEIGHT 0x100
+/* Invalidates the cache of pre-split parameter weights.  Call after every optimiser update and at the start of
+   every sub-step (TF evaluates get_weight's scaling at run time, ops.py:154-160: nothing may survive an update). */
+int gs_conv_weight_cache_reset(void);
 
 /* ---- convolution family: tf.nn.conv2d ops.py:237-243 (+ bias_add :245-246) and its gradients ------
  * SAME padding as TF computes it for even sizes: 3x3 stride 1 pads (1,1); stride 2 pads (0,1).

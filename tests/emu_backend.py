@@ -25,6 +25,12 @@ def _act(y, act):
 
 class EmuBackend(object):
 
+    def register_parameters(self, flats):
+        pass
+
+    def weight_cache_reset(self):
+        pass
+
     def _w(self, w, wswap):
         return w.permute(0, 1, 3, 2) if wswap else w   # -> [k, k, ci, co]
 
