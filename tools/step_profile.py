@@ -27,7 +27,7 @@ tot = 0.0
 for ev in prof.events():
     if ev.device_type != torch.autograd.DeviceType.CUDA:
         continue
-    name = re.sub(r"\(.*", "", ev.name)[:70]
+    name = re.sub(r"\(.*", "", ev.name.replace("(anonymous namespace)::", "").replace("<unnamed>::", ""))[:70]
     us = ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
     agg[name][0] += 1
     agg[name][1] += us
