@@ -29,6 +29,14 @@ F_G = 14898199040.0   # conv+dense FLOP per sample, generator forward (SURVEY Ap
 F_D = 14894152192.0
 ITER_FLOP_PER_SAMPLE = 7 * F_G + 11 * F_D   # SURVEY 3.1 nominal model: D-run F_G + 9 F_D, G-run 6 F_G + 2 F_D
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+# (key = ConvProfiler key: form, n, h, w, ci, co, ksize, stride)
+NCU_TRAFFIC = {
+    ("conv_c", 8, 128, 1024, 32, 32, 3, 1): (134295552 + 85211392, "profiles/ncu_c1_32_v2_summary.txt"),
+    ("conv_t", 8, 128, 1024, 32, 32, 3, 1): (134295552 + 85211392, "profiles/ncu_c1_32_v2_summary.txt (same kernel and shape)"),
+    ("conv_w", 8, 128, 1024, 32, 32, 3, 1): (268535552 + 4204032, "profiles/ncu_w_32_v2_summary.txt"),
+}
+
 HYPER = dict(generator_learning_rate=8e-4, generator_beta1=0.0, generator_beta2=0.99,
              discriminator_learning_rate=8e-4, discriminator_beta1=0.0, discriminator_beta2=0.99,
              mode_seeking_loss_weight=0.1, real_gradient_penalty_weight=5.0, fake_gradient_penalty_weight=0.0)
@@ -317,7 +325,8 @@ def bench_ours(args):
         if world > 1:
             torch.distributed.destroy_process_group()
         return
-    value = args.steps / (ms / 1e3)
+    iterations_s = args.steps / (ms / 1e3)
+    value = iterations_s * world      # batch-8 steps of ALL ranks per second (every rank runs one per iteration)
     if args.conv_table:
         with open(args.conv_table, "w") as f:
             f.write("%-8s %3s %5s %5s %4s %4s %2s %2s %5s %10s %9s %9s %8s\n" % (
@@ -339,13 +348,16 @@ def bench_ours(args):
                     global_batch=BATCH * world, parallelism="dp%d" % world,
                     l2="per-step activation working set is several GB >> 126 MB L2; no flush needed",
                     cuda_graphs=bool(graphs_were), eager_ms_per_step=ms_eager / args.steps,
-                    samples_per_s=value * BATCH * world),
+                    iterations_per_s=iterations_s,
+                    value_counts="batch-8 steps over all ranks (N per lock-step data-parallel iteration)",
+                    samples_per_s=value * BATCH),
         clocks=clocks,
-        e2e=dict(value=args.steps / (ms_e2e / 1e3), unit="steps/s", h2d_bytes_per_step=h2d // args.steps,
+        e2e=dict(value=args.steps * world / (ms_e2e / 1e3), unit="steps/s", h2d_bytes_per_step=h2d // args.steps,
                  d2h_bytes_per_step=d2h // args.steps),
         gpu_launches=launches,
         roofline=dict(bound="tensor", achieved=achieved_tf, peak=pk["tf_sustained"], unit="TFLOP/s",
-                      frac=achieved_tf / pk["tf_sustained"], traffic=None,
+                      frac=achieved_tf / pk["tf_sustained"], traffic=NCU_TRAFFIC.get(top_key, (None, None))[0],
+                      traffic_source=NCU_TRAFFIC.get(top_key, (None, "no ncu --set full capture of this kernel/shape"))[1],
                       kernel="%s n=%d %dx%d ci=%d co=%d k=%d s=%d (tcgen05 bf16x3 implicit GEMM, TMA-fed)" % top_key,
                       timing="CUDA-event pair around every launch of this kernel in an eager pass of the same steps "
                              "(the timed region replays CUDA graphs)",
@@ -353,8 +365,8 @@ def bench_ours(args):
                       io_bytes_per_launch=top["bytes"], hbm_gbs_at_io_bytes=top["bytes"] / (avg_ms * 1e-3) / 1e9,
                       share_of_step=top["ms"] / ms_eager, conv_family_share_of_step=conv_ms / ms_eager,
                       peak_source="%s bf16_tflops_sustained (kernel timed inside a long step)" % pk["source"],
-                      step_tflops=ITER_FLOP_PER_SAMPLE * BATCH * world * value / 1e12,
-                      step_frac=ITER_FLOP_PER_SAMPLE * BATCH * world * value / 1e12 / (pk["tf_sustained"] * world)),
+                      step_tflops=ITER_FLOP_PER_SAMPLE * BATCH * value / 1e12,
+                      step_frac=ITER_FLOP_PER_SAMPLE * BATCH * value / 1e12 / (pk["tf_sustained"] * world)),
     )
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count()
