@@ -43,6 +43,8 @@ SIGNATURES = {
     "gs_pixel_norm_bwd": [_P, _P, _P, _P, _L, _I, _P],
     "gs_pixel_norm_bwd2": [_P, _P, _P, _P, _P, _L, _I, _P],
     "gs_pixel_norm_bwd_mask": [_P, _P, _P, _P, _P, _L, _I, _P],
+    "gs_pixel_norm_bwd_premask": [_P, _P, _P, _P, _L, _I, _P],
+    "gs_pixel_norm_bwd2_masked": [_P, _P, _P, _P, _P, _L, _I, _P],
     "gs_batch_stddev_fwd": [_P, _P, _I, _L, _I, _F, _P],
     "gs_batch_stddev_bwd": [_P, _P, _P, _I, _L, _I, _F, _P],
     "gs_batch_stddev_bwd2": [_P, _P, _P, _P, _P, _I, _L, _I, _F, _P],

@@ -430,7 +430,9 @@ extern "C" int gs_col_sum(const float* v, float* out, long long rows, int c, voi
 template <int MODE>
 __global__ void pixel_norm_vec_kernel(const float* __restrict__ a, const float* __restrict__ rin, const float* __restrict__ dy,
                                       const float* __restrict__ u, float* __restrict__ out, float* __restrict__ rout,
-                                      long long rows, int c, float eps, int lpp) {
+                                      long long rows, int c, float eps, int lpp, int flags) {
+  // flags (second-order forms of the fused pixel-norm/leaky-relu backward): 1 = multiply the incoming vector
+  // (dy in MODE 1, u in MODE 2) by lrelu'(a) first; 2 = multiply the result by lrelu'(a)
   constexpr int MAXS = 4;
   const int lane = threadIdx.x & 31;
   const int li = lane % lpp, sub = lane / lpp, ppw = 32 / lpp;
@@ -457,6 +459,10 @@ __global__ void pixel_norm_vec_kernel(const float* __restrict__ a, const float* 
         t[s] = ok ? *reinterpret_cast<const float4*>(a + off + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (MODE != 0) d[s] = ok ? *reinterpret_cast<const float4*>(dy + off + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (MODE == 2) w[s] = ok ? *reinterpret_cast<const float4*>(u + off + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (flags & 1) {
+          float4& v = (MODE == 2) ? w[s] : d[s];
+          v.x *= gs_lrelu_slope(t[s].x); v.y *= gs_lrelu_slope(t[s].y); v.z *= gs_lrelu_slope(t[s].z); v.w *= gs_lrelu_slope(t[s].w);
+        }
       }
     if (MODE == 0) {
       float ss = 0.0f;
@@ -514,9 +520,12 @@ __global__ void pixel_norm_vec_kernel(const float* __restrict__ a, const float* 
         for (int s = 0; s < MAXS; ++s)
           if (s < slots) {
             const int ch = (s * lpp + li) * 4;
-            *reinterpret_cast<float4*>(out + off + ch) =
-                make_float4(ka * t[s].x + ku * w[s].x + kd * d[s].x, ka * t[s].y + ku * w[s].y + kd * d[s].y,
-                            ka * t[s].z + ku * w[s].z + kd * d[s].z, ka * t[s].w + ku * w[s].w + kd * d[s].w);
+            float4 o = make_float4(ka * t[s].x + ku * w[s].x + kd * d[s].x, ka * t[s].y + ku * w[s].y + kd * d[s].y,
+                                   ka * t[s].z + ku * w[s].z + kd * d[s].z, ka * t[s].w + ku * w[s].w + kd * d[s].w);
+            if (flags & 2) {
+              o.x *= gs_lrelu_slope(t[s].x); o.y *= gs_lrelu_slope(t[s].y); o.z *= gs_lrelu_slope(t[s].z); o.w *= gs_lrelu_slope(t[s].w);
+            }
+            *reinterpret_cast<float4*>(out + off + ch) = o;
           }
       }
     }
@@ -563,7 +572,7 @@ static int pn_grid(long long rows) {
 extern "C" int gs_pixel_norm_fwd(const float* a, float* y, float* r, long long rows, int c, float eps, void* stream) {
   GS_CHECK_ARG(rows >= 0 && c > 0, "pixel_norm_fwd: bad shape");
   if (rows == 0) return GS_OK;
-  if (const int lpp = pn_lpp(c)) pixel_norm_vec_kernel<0><<<pn_vec_grid(rows, lpp), EW_BLOCK, 0, ST>>>(a, nullptr, nullptr, nullptr, y, r, rows, c, eps, lpp);
+  if (const int lpp = pn_lpp(c)) pixel_norm_vec_kernel<0><<<pn_vec_grid(rows, lpp), EW_BLOCK, 0, ST>>>(a, nullptr, nullptr, nullptr, y, r, rows, c, eps, lpp, 0);
   else pixel_norm_kernel<0><<<pn_grid(rows), EW_BLOCK, 0, ST>>>(a, nullptr, nullptr, nullptr, y, r, rows, c, eps);
   GS_CHECK_LAUNCH("pixel_norm_fwd");
   return GS_OK;
@@ -571,7 +580,7 @@ extern "C" int gs_pixel_norm_fwd(const float* a, float* y, float* r, long long r
 extern "C" int gs_pixel_norm_bwd(const float* a, const float* r, const float* dy, float* da, long long rows, int c, void* stream) {
   GS_CHECK_ARG(rows >= 0 && c > 0, "pixel_norm_bwd: bad shape");
   if (rows == 0) return GS_OK;
-  if (const int lpp = pn_lpp(c)) pixel_norm_vec_kernel<1><<<pn_vec_grid(rows, lpp), EW_BLOCK, 0, ST>>>(a, r, dy, nullptr, da, nullptr, rows, c, 0.f, lpp);
+  if (const int lpp = pn_lpp(c)) pixel_norm_vec_kernel<1><<<pn_vec_grid(rows, lpp), EW_BLOCK, 0, ST>>>(a, r, dy, nullptr, da, nullptr, rows, c, 0.f, lpp, 0);
   else pixel_norm_kernel<1><<<pn_grid(rows), EW_BLOCK, 0, ST>>>(a, r, dy, nullptr, da, nullptr, rows, c, 0.f);
   GS_CHECK_LAUNCH("pixel_norm_bwd");
   return GS_OK;
@@ -580,7 +589,7 @@ extern "C" int gs_pixel_norm_bwd2(const float* a, const float* r, const float* d
                                   int c, void* stream) {
   GS_CHECK_ARG(rows >= 0 && c > 0, "pixel_norm_bwd2: bad shape");
   if (rows == 0) return GS_OK;
-  if (const int lpp = pn_lpp(c)) pixel_norm_vec_kernel<2><<<pn_vec_grid(rows, lpp), EW_BLOCK, 0, ST>>>(a, r, dy, u, ga, nullptr, rows, c, 0.f, lpp);
+  if (const int lpp = pn_lpp(c)) pixel_norm_vec_kernel<2><<<pn_vec_grid(rows, lpp), EW_BLOCK, 0, ST>>>(a, r, dy, u, ga, nullptr, rows, c, 0.f, lpp, 0);
   else pixel_norm_kernel<2><<<pn_grid(rows), EW_BLOCK, 0, ST>>>(a, r, dy, u, ga, nullptr, rows, c, 0.f);
   GS_CHECK_LAUNCH("pixel_norm_bwd2");
   return GS_OK;
@@ -591,7 +600,7 @@ extern "C" int gs_pixel_norm_bwd_mask(const float* a, const float* r, const floa
   GS_CHECK_ARG(rows >= 0 && c > 0 && c % 4 == 0 && c <= 256, "pixel_norm_bwd_mask: needs c %% 4 == 0, c <= 256 (got %d)", c);
   if (colsum) GS_CUDA(cudaMemsetAsync(colsum, 0, (size_t)c * sizeof(float), ST));
   if (rows == 0) return GS_OK;
-  if (const int lpp = pn_lpp(c)) pixel_norm_vec_kernel<3><<<pn_vec_grid(rows, lpp), EW_BLOCK, 0, ST>>>(a, r, dy, nullptr, dz, colsum, rows, c, 0.f, lpp);
+  if (const int lpp = pn_lpp(c)) pixel_norm_vec_kernel<3><<<pn_vec_grid(rows, lpp), EW_BLOCK, 0, ST>>>(a, r, dy, nullptr, dz, colsum, rows, c, 0.f, lpp, 0);
   else pixel_norm_kernel<3><<<pn_grid(rows), EW_BLOCK, 0, ST>>>(a, r, dy, nullptr, dz, colsum, rows, c, 0.f);
   GS_CHECK_LAUNCH("pixel_norm_bwd_mask");
   return GS_OK;
@@ -606,6 +615,25 @@ extern "C" int gs_lrelu_mask_mul_colsum(const float* v, const float* y, float* o
   mask_mul_colsum_kernel<<<ew_grid(n4 * 4), EW_BLOCK, 0, ST>>>(reinterpret_cast<const float4*>(v), reinterpret_cast<const float4*>(y),
                                                                reinterpret_cast<float4*>(out), colsum, n4, c / 4);
   GS_CHECK_LAUNCH("lrelu_mask_mul_colsum");
+  return GS_OK;
+}
+
+extern "C" int gs_pixel_norm_bwd_premask(const float* a, const float* r, const float* u, float* out, long long rows, int c,
+                                         void* stream) {
+  const int lpp = pn_lpp(c);
+  GS_CHECK_ARG(rows >= 0 && c > 0 && lpp > 0, "pixel_norm_bwd_premask: unsupported channel count %d", c);
+  if (rows == 0) return GS_OK;
+  pixel_norm_vec_kernel<1><<<pn_vec_grid(rows, lpp), EW_BLOCK, 0, ST>>>(a, r, u, nullptr, out, nullptr, rows, c, 0.f, lpp, 1);
+  GS_CHECK_LAUNCH("pixel_norm_bwd_premask");
+  return GS_OK;
+}
+extern "C" int gs_pixel_norm_bwd2_masked(const float* a, const float* r, const float* dy, const float* u, float* ga,
+                                         long long rows, int c, void* stream) {
+  const int lpp = pn_lpp(c);
+  GS_CHECK_ARG(rows >= 0 && c > 0 && lpp > 0, "pixel_norm_bwd2_masked: unsupported channel count %d", c);
+  if (rows == 0) return GS_OK;
+  pixel_norm_vec_kernel<2><<<pn_vec_grid(rows, lpp), EW_BLOCK, 0, ST>>>(a, r, dy, u, ga, nullptr, rows, c, 0.f, lpp, 3);
+  GS_CHECK_LAUNCH("pixel_norm_bwd2_masked");
   return GS_OK;
 }
 

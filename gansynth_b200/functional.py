@@ -192,9 +192,9 @@ class PnBwdMask(Function):
     @once_differentiable
     def backward(ctx, u):
         a, r, dy = ctx.saved_tensors
-        mu = K.mask_mul(u, a)
         # `a` is the output of a premasked ConvLayer: every gradient handed to it must already carry the mask
-        return K.mask_mul(K.pn_bwd2(a, r, dy, mu), a), None, K.pn_bwd(a, r, mu)
+        ga, gdy = K.pn_bwd_mask_second(a, r, dy, u)
+        return ga, None, gdy
 
 
 class LeakyRelu(Function):

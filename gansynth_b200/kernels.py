@@ -230,6 +230,25 @@ class CudaBackend(object):
         _lib.call("gs_pixel_norm_bwd_mask", _ptr(a), _ptr(r), _ptr(dy), _ptr(dz), _ptr(cs), a.numel() // c, c, _stream())
         return dz, cs
 
+    @staticmethod
+    def _pn_vec_ok(c):
+        v = c // 4
+        return c % 4 == 0 and ((v <= 32 and v & (v - 1) == 0) or (v % 32 == 0 and v // 32 <= 4))
+
+    def pn_bwd_mask_second(self, a, r, dy, u):
+        """Second-order pieces of pn_bwd_mask for an incoming u (M = lrelu'(a)):
+        (M * pn_bwd2(a, r, dy, M u), pn_bwd(a, r, M u)) without materialising M u."""
+        a, r, dy, u = _chk(a, r, dy, u)
+        c = a.shape[-1]
+        if not self._pn_vec_ok(c):
+            mu = self.mask_mul(u, a)
+            return self.mask_mul(self.pn_bwd2(a, r, dy, mu), a), self.pn_bwd(a, r, mu)
+        ga, gdy = torch.empty_like(a), torch.empty_like(a)
+        rows = a.numel() // c
+        _lib.call("gs_pixel_norm_bwd2_masked", _ptr(a), _ptr(r), _ptr(dy), _ptr(u), _ptr(ga), rows, c, _stream())
+        _lib.call("gs_pixel_norm_bwd_premask", _ptr(a), _ptr(r), _ptr(u), _ptr(gdy), rows, c, _stream())
+        return ga, gdy
+
     def pn_bwd2(self, a, r, dy, u):
         a, r, dy, u = _chk(a, r, dy, u)
         c = a.shape[-1]

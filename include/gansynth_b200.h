@@ -92,6 +92,10 @@ int gs_pixel_norm_bwd(const float* a, const float* r, const float* dy, float* da
    leaky_relu -> pixel_normalization); colsum (may be null) receives the bias gradient; c % 4 == 0, c <= 256 */
 int gs_pixel_norm_bwd_mask(const float* a, const float* r, const float* dy, float* dz, float* colsum, long long rows, int c,
                            void* stream);
+/* second-order forms of gs_pixel_norm_bwd_mask (M = lrelu'(a)): J(a)(M u) and M * bwd2(a, r, dy, M u) */
+int gs_pixel_norm_bwd_premask(const float* a, const float* r, const float* u, float* out, long long rows, int c, void* stream);
+int gs_pixel_norm_bwd2_masked(const float* a, const float* r, const float* dy, const float* u, float* ga, long long rows, int c,
+                              void* stream);
 int gs_pixel_norm_bwd2(const float* a, const float* r, const float* dy, const float* u, float* ga, long long rows,
                        int c, void* stream);
 

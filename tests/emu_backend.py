@@ -113,6 +113,10 @@ class EmuBackend(object):
         dz = self.mask_mul(self.pn_bwd(a, r, dy), a)
         return dz, (self.col_sum(dz) if want_colsum else None)
 
+    def pn_bwd_mask_second(self, a, r, dy, u):
+        mu = self.mask_mul(u, a)
+        return self.mask_mul(self.pn_bwd2(a, r, dy, mu), a), self.pn_bwd(a, r, mu)
+
     def col_sum(self, v):
         return v.reshape(-1, v.shape[-1]).sum(0)
 

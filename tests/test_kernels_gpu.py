@@ -151,6 +151,9 @@ def test_elementwise_and_pixel_norm(shape):
         assert (ck is None) == (not want)
         if want:
             assert rel_err(ck, ce.double()) < 1e-5
+    gk, hk = k.pn_bwd_mask_second(ac, rk, dc, uc)
+    ge, he = EMU.pn_bwd_mask_second(a, re_, dy, u)
+    assert rel_err(gk, ge) < 1e-5 and rel_err(hk, he) < 1e-5
 
 
 def test_fused_mask_colsum_full_size():
