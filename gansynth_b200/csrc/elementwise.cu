@@ -427,106 +427,114 @@ extern "C" int gs_col_sum(const float* v, float* out, long long rows, int c, voi
 // top-resolution activations use all 32 lanes on 4 pixels instead of 8 lanes on one), float4 accesses, reductions
 // by xor-shuffles inside the LPP-lane group.  Same MODE meaning as pixel_norm_kernel; c % 4 == 0, c/4 a power of two
 // <= 32 or a multiple of 32 up to 128 (c <= 512).
-template <int MODE>
+template <int MODE, int SLOTS, int R>
 __global__ void pixel_norm_vec_kernel(const float* __restrict__ a, const float* __restrict__ rin, const float* __restrict__ dy,
                                       const float* __restrict__ u, float* __restrict__ out, float* __restrict__ rout,
                                       long long rows, int c, float eps, int lpp, int flags) {
+  // SLOTS = float4 per lane per pixel ((c/4) / lpp); R = pixels per lane group in flight per iteration (memory-level
+  // parallelism: every load of the R pixels is issued before the first reduction).
   // flags (second-order forms of the fused pixel-norm/leaky-relu backward): 1 = multiply the incoming vector
   // (dy in MODE 1, u in MODE 2) by lrelu'(a) first; 2 = multiply the result by lrelu'(a)
-  constexpr int MAXS = 4;
   const int lane = threadIdx.x & 31;
   const int li = lane % lpp, sub = lane / lpp, ppw = 32 / lpp;
-  const int slots = (c / 4) / lpp;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const float inv_c = 1.0f / (float)c;
-  float4 cacc[MAXS];
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 cacc[SLOTS];
 #pragma unroll
-  for (int s = 0; s < MAXS; ++s) cacc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < SLOTS; ++s) cacc[s] = zero4;
   auto group_sum = [&](float v) {
     for (int o = lpp >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
   };
-  for (long long base = warp * ppw; base < rows; base += nwarps * ppw) {
-    const long long row = base + sub;
-    const bool ok = row < rows;
-    const size_t off = (size_t)(ok ? row : 0) * c;
-    float4 t[MAXS], d[MAXS], w[MAXS];
+  auto dot4 = [](const float4& x, const float4& y) { return x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w; };
+  auto mask4 = [](float4& v, const float4& t) {
+    v.x *= gs_lrelu_slope(t.x); v.y *= gs_lrelu_slope(t.y); v.z *= gs_lrelu_slope(t.z); v.w *= gs_lrelu_slope(t.w);
+  };
+  for (long long base = warp * ppw * R; base < rows; base += nwarps * ppw * R) {
+    float4 t[R][SLOTS], d[R][SLOTS], w[R][SLOTS];
+    bool ok[R];
+    size_t off[R];
+    float rr[R];
 #pragma unroll
-    for (int s = 0; s < MAXS; ++s)
-      if (s < slots) {
+    for (int k = 0; k < R; ++k) {
+      const long long row = base + (long long)k * ppw + sub;
+      ok[k] = row < rows;
+      off[k] = (size_t)(ok[k] ? row : 0) * c;
+#pragma unroll
+      for (int s = 0; s < SLOTS; ++s) {
         const int ch = (s * lpp + li) * 4;
-        t[s] = ok ? *reinterpret_cast<const float4*>(a + off + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (MODE != 0) d[s] = ok ? *reinterpret_cast<const float4*>(dy + off + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (MODE == 2) w[s] = ok ? *reinterpret_cast<const float4*>(u + off + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (flags & 1) {
-          float4& v = (MODE == 2) ? w[s] : d[s];
-          v.x *= gs_lrelu_slope(t[s].x); v.y *= gs_lrelu_slope(t[s].y); v.z *= gs_lrelu_slope(t[s].z); v.w *= gs_lrelu_slope(t[s].w);
-        }
+        t[k][s] = ok[k] ? *reinterpret_cast<const float4*>(a + off[k] + ch) : zero4;
+        if (MODE != 0) d[k][s] = ok[k] ? *reinterpret_cast<const float4*>(dy + off[k] + ch) : zero4;
+        if (MODE == 2) w[k][s] = ok[k] ? *reinterpret_cast<const float4*>(u + off[k] + ch) : zero4;
       }
-    if (MODE == 0) {
-      float ss = 0.0f;
+      if (MODE != 0) rr[k] = ok[k] ? rin[off[k] / c] : 0.0f;
+    }
 #pragma unroll
-      for (int s = 0; s < MAXS; ++s)
-        if (s < slots) ss += t[s].x * t[s].x + t[s].y * t[s].y + t[s].z * t[s].z + t[s].w * t[s].w;
-      ss = group_sum(ss);
-      const float r = 1.0f / sqrtf(ss * inv_c + eps);
-      if (ok) {
+    for (int k = 0; k < R; ++k) {
+      if (flags & 1) {
 #pragma unroll
-        for (int s = 0; s < MAXS; ++s)
-          if (s < slots) {
+        for (int s = 0; s < SLOTS; ++s) mask4((MODE == 2) ? w[k][s] : d[k][s], t[k][s]);
+      }
+      if (MODE == 0) {
+        float ss = 0.0f;
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) ss += dot4(t[k][s], t[k][s]);
+        ss = group_sum(ss);
+        const float r = 1.0f / sqrtf(ss * inv_c + eps);
+        if (ok[k]) {
+#pragma unroll
+          for (int s = 0; s < SLOTS; ++s) {
             const int ch = (s * lpp + li) * 4;
-            *reinterpret_cast<float4*>(out + off + ch) = make_float4(t[s].x * r, t[s].y * r, t[s].z * r, t[s].w * r);
+            *reinterpret_cast<float4*>(out + off[k] + ch) = make_float4(t[k][s].x * r, t[k][s].y * r, t[k][s].z * r, t[k][s].w * r);
           }
-        if (li == 0) rout[row] = r;
-      }
-    } else if (MODE == 1 || MODE == 3) {
-      float dot = 0.0f;
+          if (li == 0) rout[off[k] / c] = r;
+        }
+      } else if (MODE == 1 || MODE == 3) {
+        float dot = 0.0f;
 #pragma unroll
-      for (int s = 0; s < MAXS; ++s)
-        if (s < slots) dot += t[s].x * d[s].x + t[s].y * d[s].y + t[s].z * d[s].z + t[s].w * d[s].w;
-      dot = group_sum(dot);
-      const float r = ok ? rin[row] : 0.0f;
-      const float k = r * r * r * inv_c * dot;
-      if (ok) {
+        for (int s = 0; s < SLOTS; ++s) dot += dot4(t[k][s], d[k][s]);
+        dot = group_sum(dot);
+        const float r = rr[k];
+        const float kk = r * r * r * inv_c * dot;
+        if (ok[k]) {
 #pragma unroll
-        for (int s = 0; s < MAXS; ++s)
-          if (s < slots) {
+          for (int s = 0; s < SLOTS; ++s) {
             const int ch = (s * lpp + li) * 4;
-            float4 o = make_float4(r * d[s].x - k * t[s].x, r * d[s].y - k * t[s].y, r * d[s].z - k * t[s].z, r * d[s].w - k * t[s].w);
+            const float4 tt = t[k][s], dd = d[k][s];
+            float4 o = make_float4(r * dd.x - kk * tt.x, r * dd.y - kk * tt.y, r * dd.z - kk * tt.z, r * dd.w - kk * tt.w);
             if (MODE == 3) {
-              o.x *= gs_lrelu_slope(t[s].x); o.y *= gs_lrelu_slope(t[s].y); o.z *= gs_lrelu_slope(t[s].z); o.w *= gs_lrelu_slope(t[s].w);
+              mask4(o, tt);
               cacc[s].x += o.x; cacc[s].y += o.y; cacc[s].z += o.z; cacc[s].w += o.w;
             }
-            *reinterpret_cast<float4*>(out + off + ch) = o;
+            *reinterpret_cast<float4*>(out + off[k] + ch) = o;
           }
-      }
-    } else {
-      float ud = 0.0f, ad = 0.0f, ua = 0.0f;
-#pragma unroll
-      for (int s = 0; s < MAXS; ++s)
-        if (s < slots) {
-          ud += w[s].x * d[s].x + w[s].y * d[s].y + w[s].z * d[s].z + w[s].w * d[s].w;
-          ad += t[s].x * d[s].x + t[s].y * d[s].y + t[s].z * d[s].z + t[s].w * d[s].w;
-          ua += w[s].x * t[s].x + w[s].y * t[s].y + w[s].z * t[s].z + w[s].w * t[s].w;
         }
-      ud = group_sum(ud); ad = group_sum(ad); ua = group_sum(ua);
-      const float r = ok ? rin[row] : 0.0f;
-      const float r3c = r * r * r * inv_c;
-      const float ka = -r3c * ud + 3.0f * r3c * r * r * inv_c * ua * ad;
-      const float ku = -r3c * ad, kd = -r3c * ua;
-      if (ok) {
+      } else {
+        float ud = 0.0f, ad = 0.0f, ua = 0.0f;
 #pragma unroll
-        for (int s = 0; s < MAXS; ++s)
-          if (s < slots) {
+        for (int s = 0; s < SLOTS; ++s) {
+          ud += dot4(w[k][s], d[k][s]);
+          ad += dot4(t[k][s], d[k][s]);
+          ua += dot4(w[k][s], t[k][s]);
+        }
+        ud = group_sum(ud); ad = group_sum(ad); ua = group_sum(ua);
+        const float r = rr[k];
+        const float r3c = r * r * r * inv_c;
+        const float ka = -r3c * ud + 3.0f * r3c * r * r * inv_c * ua * ad;
+        const float ku = -r3c * ad, kd = -r3c * ua;
+        if (ok[k]) {
+#pragma unroll
+          for (int s = 0; s < SLOTS; ++s) {
             const int ch = (s * lpp + li) * 4;
-            float4 o = make_float4(ka * t[s].x + ku * w[s].x + kd * d[s].x, ka * t[s].y + ku * w[s].y + kd * d[s].y,
-                                   ka * t[s].z + ku * w[s].z + kd * d[s].z, ka * t[s].w + ku * w[s].w + kd * d[s].w);
-            if (flags & 2) {
-              o.x *= gs_lrelu_slope(t[s].x); o.y *= gs_lrelu_slope(t[s].y); o.z *= gs_lrelu_slope(t[s].z); o.w *= gs_lrelu_slope(t[s].w);
-            }
-            *reinterpret_cast<float4*>(out + off + ch) = o;
+            const float4 tt = t[k][s], dd = d[k][s], ww = w[k][s];
+            float4 o = make_float4(ka * tt.x + ku * ww.x + kd * dd.x, ka * tt.y + ku * ww.y + kd * dd.y,
+                                   ka * tt.z + ku * ww.z + kd * dd.z, ka * tt.w + ku * ww.w + kd * dd.w);
+            if (flags & 2) mask4(o, tt);
+            *reinterpret_cast<float4*>(out + off[k] + ch) = o;
           }
+        }
       }
     }
   }
@@ -536,15 +544,29 @@ __global__ void pixel_norm_vec_kernel(const float* __restrict__ a, const float* 
     for (int i = threadIdx.x; i < c; i += blockDim.x) cs[i] = 0.0f;
     __syncthreads();
 #pragma unroll
-    for (int s = 0; s < MAXS; ++s)
-      if (s < slots) {
-        const int ch = (s * lpp + li) * 4;
-        atomicAdd(&cs[ch], cacc[s].x); atomicAdd(&cs[ch + 1], cacc[s].y);
-        atomicAdd(&cs[ch + 2], cacc[s].z); atomicAdd(&cs[ch + 3], cacc[s].w);
-      }
+    for (int s = 0; s < SLOTS; ++s) {
+      const int ch = (s * lpp + li) * 4;
+      atomicAdd(&cs[ch], cacc[s].x); atomicAdd(&cs[ch + 1], cacc[s].y);
+      atomicAdd(&cs[ch + 2], cacc[s].z); atomicAdd(&cs[ch + 3], cacc[s].w);
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(rout + i, cs[i]);
   }
+}
+
+template <int MODE>
+static void pn_vec_launch(const float* a, const float* r, const float* dy, const float* u, float* out, float* rout, long long rows,
+                          int c, float eps, int lpp, int flags, cudaStream_t st) {
+  const int slots = (c / 4) / lpp;
+  const int R = slots == 1 ? 4 : slots == 2 ? 2 : 1;
+  const long long ppw = 32 / lpp, warps_per_block = EW_BLOCK / 32;
+  long long b = (rows + warps_per_block * ppw * R - 1) / (warps_per_block * ppw * R);
+  const long long cap = (long long)gs_num_sms() * 16;
+  if (b < 1) b = 1;
+  const int blocks = (int)(b < cap ? b : cap);
+  if (slots == 1) pixel_norm_vec_kernel<MODE, 1, 4><<<blocks, EW_BLOCK, 0, st>>>(a, r, dy, u, out, rout, rows, c, eps, lpp, flags);
+  else if (slots == 2) pixel_norm_vec_kernel<MODE, 2, 2><<<blocks, EW_BLOCK, 0, st>>>(a, r, dy, u, out, rout, rows, c, eps, lpp, flags);
+  else pixel_norm_vec_kernel<MODE, 4, 1><<<blocks, EW_BLOCK, 0, st>>>(a, r, dy, u, out, rout, rows, c, eps, lpp, flags);
 }
 
 // lanes per pixel of the vectorised kernel, or 0 when c is not covered
@@ -552,16 +574,8 @@ static int pn_lpp(int c) {
   if (c % 4) return 0;
   const int v = c / 4;
   if (v <= 32) return (v & (v - 1)) == 0 ? v : 0;
-  return (v % 32 == 0 && v / 32 <= 4) ? 32 : 0;
+  return (v == 64 || v == 128) ? 32 : 0;     // 2 or 4 float4 per lane
 }
-static int pn_vec_grid(long long rows, int lpp) {
-  const long long ppw = 32 / lpp, warps_per_block = EW_BLOCK / 32;
-  long long b = (rows + warps_per_block * ppw * 4 - 1) / (warps_per_block * ppw * 4);
-  const long long cap = (long long)gs_num_sms() * 16;
-  if (b < 1) b = 1;
-  return (int)(b < cap ? b : cap);
-}
-
 static int pn_grid(long long rows) {
   long long warps_per_block = EW_BLOCK / 32;
   long long b = (rows + warps_per_block * 4 - 1) / (warps_per_block * 4);
@@ -572,7 +586,7 @@ static int pn_grid(long long rows) {
 extern "C" int gs_pixel_norm_fwd(const float* a, float* y, float* r, long long rows, int c, float eps, void* stream) {
   GS_CHECK_ARG(rows >= 0 && c > 0, "pixel_norm_fwd: bad shape");
   if (rows == 0) return GS_OK;
-  if (const int lpp = pn_lpp(c)) pixel_norm_vec_kernel<0><<<pn_vec_grid(rows, lpp), EW_BLOCK, 0, ST>>>(a, nullptr, nullptr, nullptr, y, r, rows, c, eps, lpp, 0);
+  if (const int lpp = pn_lpp(c)) pn_vec_launch<0>(a, nullptr, nullptr, nullptr, y, r, rows, c, eps, lpp, 0, ST);
   else pixel_norm_kernel<0><<<pn_grid(rows), EW_BLOCK, 0, ST>>>(a, nullptr, nullptr, nullptr, y, r, rows, c, eps);
   GS_CHECK_LAUNCH("pixel_norm_fwd");
   return GS_OK;
@@ -580,7 +594,7 @@ extern "C" int gs_pixel_norm_fwd(const float* a, float* y, float* r, long long r
 extern "C" int gs_pixel_norm_bwd(const float* a, const float* r, const float* dy, float* da, long long rows, int c, void* stream) {
   GS_CHECK_ARG(rows >= 0 && c > 0, "pixel_norm_bwd: bad shape");
   if (rows == 0) return GS_OK;
-  if (const int lpp = pn_lpp(c)) pixel_norm_vec_kernel<1><<<pn_vec_grid(rows, lpp), EW_BLOCK, 0, ST>>>(a, r, dy, nullptr, da, nullptr, rows, c, 0.f, lpp, 0);
+  if (const int lpp = pn_lpp(c)) pn_vec_launch<1>(a, r, dy, nullptr, da, nullptr, rows, c, 0.f, lpp, 0, ST);
   else pixel_norm_kernel<1><<<pn_grid(rows), EW_BLOCK, 0, ST>>>(a, r, dy, nullptr, da, nullptr, rows, c, 0.f);
   GS_CHECK_LAUNCH("pixel_norm_bwd");
   return GS_OK;
@@ -589,7 +603,7 @@ extern "C" int gs_pixel_norm_bwd2(const float* a, const float* r, const float* d
                                   int c, void* stream) {
   GS_CHECK_ARG(rows >= 0 && c > 0, "pixel_norm_bwd2: bad shape");
   if (rows == 0) return GS_OK;
-  if (const int lpp = pn_lpp(c)) pixel_norm_vec_kernel<2><<<pn_vec_grid(rows, lpp), EW_BLOCK, 0, ST>>>(a, r, dy, u, ga, nullptr, rows, c, 0.f, lpp, 0);
+  if (const int lpp = pn_lpp(c)) pn_vec_launch<2>(a, r, dy, u, ga, nullptr, rows, c, 0.f, lpp, 0, ST);
   else pixel_norm_kernel<2><<<pn_grid(rows), EW_BLOCK, 0, ST>>>(a, r, dy, u, ga, nullptr, rows, c, 0.f);
   GS_CHECK_LAUNCH("pixel_norm_bwd2");
   return GS_OK;
@@ -600,7 +614,7 @@ extern "C" int gs_pixel_norm_bwd_mask(const float* a, const float* r, const floa
   GS_CHECK_ARG(rows >= 0 && c > 0 && c % 4 == 0 && c <= 256, "pixel_norm_bwd_mask: needs c %% 4 == 0, c <= 256 (got %d)", c);
   if (colsum) GS_CUDA(cudaMemsetAsync(colsum, 0, (size_t)c * sizeof(float), ST));
   if (rows == 0) return GS_OK;
-  if (const int lpp = pn_lpp(c)) pixel_norm_vec_kernel<3><<<pn_vec_grid(rows, lpp), EW_BLOCK, 0, ST>>>(a, r, dy, nullptr, dz, colsum, rows, c, 0.f, lpp, 0);
+  if (const int lpp = pn_lpp(c)) pn_vec_launch<3>(a, r, dy, nullptr, dz, colsum, rows, c, 0.f, lpp, 0, ST);
   else pixel_norm_kernel<3><<<pn_grid(rows), EW_BLOCK, 0, ST>>>(a, r, dy, nullptr, dz, colsum, rows, c, 0.f);
   GS_CHECK_LAUNCH("pixel_norm_bwd_mask");
   return GS_OK;
@@ -623,7 +637,7 @@ extern "C" int gs_pixel_norm_bwd_premask(const float* a, const float* r, const f
   const int lpp = pn_lpp(c);
   GS_CHECK_ARG(rows >= 0 && c > 0 && lpp > 0, "pixel_norm_bwd_premask: unsupported channel count %d", c);
   if (rows == 0) return GS_OK;
-  pixel_norm_vec_kernel<1><<<pn_vec_grid(rows, lpp), EW_BLOCK, 0, ST>>>(a, r, u, nullptr, out, nullptr, rows, c, 0.f, lpp, 1);
+  pn_vec_launch<1>(a, r, u, nullptr, out, nullptr, rows, c, 0.f, lpp, 1, ST);
   GS_CHECK_LAUNCH("pixel_norm_bwd_premask");
   return GS_OK;
 }
@@ -632,7 +646,7 @@ extern "C" int gs_pixel_norm_bwd2_masked(const float* a, const float* r, const f
   const int lpp = pn_lpp(c);
   GS_CHECK_ARG(rows >= 0 && c > 0 && lpp > 0, "pixel_norm_bwd2_masked: unsupported channel count %d", c);
   if (rows == 0) return GS_OK;
-  pixel_norm_vec_kernel<2><<<pn_vec_grid(rows, lpp), EW_BLOCK, 0, ST>>>(a, r, dy, u, ga, nullptr, rows, c, 0.f, lpp, 3);
+  pn_vec_launch<2>(a, r, dy, u, ga, nullptr, rows, c, 0.f, lpp, 3, ST);
   GS_CHECK_LAUNCH("pixel_norm_bwd2_masked");
   return GS_OK;
 }

@@ -233,7 +233,7 @@ class CudaBackend(object):
     @staticmethod
     def _pn_vec_ok(c):
         v = c // 4
-        return c % 4 == 0 and ((v <= 32 and v & (v - 1) == 0) or (v % 32 == 0 and v // 32 <= 4))
+        return c % 4 == 0 and ((v <= 32 and v & (v - 1) == 0) or v in (64, 128))
 
     def pn_bwd_mask_second(self, a, r, dy, u):
         """Second-order pieces of pn_bwd_mask for an incoming u (M = lrelu'(a)):
