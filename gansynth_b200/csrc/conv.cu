@@ -5,6 +5,7 @@
 
 #include "conv1x1.cuh"
 #include "conv_tc.cuh"
+#include "conv_tck.cuh"
 #include "conv_tcw.cuh"
 #include "conv_tiled.cuh"
 #include "tma_host.h"
@@ -302,6 +303,89 @@ int launch_tc_impl(const float* x, const float* w, const float* bias, float* y, 
   return GS_OK;
 }
 
+// kw-stacked stride-1 kernel for thin layers (conv_tck.cuh): 32 or 64 output channels, all of them in one CTA,
+// rows in multiples of 8, wide enough images that the 14-column tiles fill the GPU
+bool tck_ok(int h, int w, int kdim, int ndim) {
+  return (ndim == 32 || ndim == 64) && kdim % 32 == 0 && h % 8 == 0 && w >= 128 && !getenv("GS_TC_NO_KSTACK");
+}
+
+int launch_tck(const float* x, const float* w, const float* bias, float* y, int n, int h, int wd, int kdim, int ndim,
+               int w_is_kn, int flip, float alpha, int act, bool cacheable, cudaStream_t st) {
+  const size_t wbytes = (size_t)9 * kdim * ndim * 2 * sizeof(__nv_bfloat16);
+  GS_CHECK_ARG(wbytes <= g_tc_ws.scratch, "conv_tck: weight of %zu bytes exceeds the scratch slot", wbytes);
+  if (!g_tc_ws.buf) GS_CUDA(cudaMalloc(&g_tc_ws.buf, g_tc_ws.scratch + g_tc_ws.cache));
+  TckParams p;
+  p.bias = bias; p.n_img = n; p.h = h; p.w = wd; p.kdim = kdim; p.nt = ndim; p.alpha = alpha; p.act = act;
+  p.tiles_h = h / 8; p.tiles_w = (wd + 13) / 14; p.ntiles = n * p.tiles_h * p.tiles_w;
+  p.cat = (6 * ndim <= 256) && !getenv("GS_TC_NO_CAT");
+  const int nchunks = kdim / 32;
+  const size_t budget = 222 * 1024 - 1024 - 2 * TCK_OUT;
+  const size_t a_stage = 2 * 4 * TCK_PIX * 16, raw = TCK_RAW;
+  const size_t b_row = (size_t)4 * 6 * ndim * 16;
+  p.sa = 2; p.ds = 2;
+  size_t used = p.sa * a_stage + p.ds * raw;
+  int tps = 1;
+  p.b_resident = (used + (size_t)nchunks * 3 * b_row <= budget) && nchunks <= TC_MAX_BSTAGES;
+  if (p.b_resident) { tps = 3; p.sb = nchunks; used += (size_t)nchunks * 3 * b_row; }
+  else if (used + 2 * 3 * b_row <= budget) { tps = 3; p.sb = 2; used += 2 * 3 * b_row; }
+  else { tps = 1; p.sb = 3; used += 3 * b_row; }
+  GS_CHECK_ARG(used <= budget, "conv_tck: shared memory budget exceeded (kdim %d ndim %d)", kdim, ndim);
+  if (used + raw <= budget) { ++p.ds; used += raw; }
+  if (used + a_stage <= budget) { ++p.sa; used += a_stage; }
+  if (!p.b_resident)
+    while (p.sb < 4 && used + (size_t)tps * b_row <= budget) { ++p.sb; used += (size_t)tps * b_row; }
+  if (used + raw <= budget) { ++p.ds; used += raw; }
+  if (used + a_stage <= budget) { ++p.sa; used += a_stage; }
+  p.tmem_cols = 512;
+  {
+    unsigned char* dst = g_tc_ws.buf;
+    bool need_prep = true;
+    const int layout_tag = 1032;      // distinguishes the kw-stacked layout from conv_tc's in the cache
+    if (cacheable) {
+      for (int i = 0; i < g_nprep; ++i) {
+        const PrepKey& k = g_prep[i];
+        if (k.w == w && k.kdim == kdim && k.ndim == ndim && k.nt == ndim && k.kc == layout_tag && k.kn == w_is_kn && k.flip == flip) {
+          dst = g_tc_ws.buf + g_tc_ws.scratch + k.off;
+          need_prep = false;
+          break;
+        }
+      }
+      if (need_prep && g_nprep < 512 && g_tc_ws.used + wbytes <= g_tc_ws.cache) {
+        g_prep[g_nprep++] = PrepKey{w, kdim, ndim, ndim, layout_tag, w_is_kn, flip, g_tc_ws.used};
+        dst = g_tc_ws.buf + g_tc_ws.scratch + g_tc_ws.used;
+        g_tc_ws.used += (wbytes + 255) & ~(size_t)255;
+      }
+    }
+    if (need_prep) {
+      size_t total = (size_t)9 * kdim * ndim;
+      int blocks = (int)((total + 255) / 256);
+      if (blocks > gs_num_sms() * 8) blocks = gs_num_sms() * 8;
+      conv_tck_prep_kernel<<<blocks, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(dst), kdim, ndim, w_is_kn, flip);
+      GS_CHECK_LAUNCH("conv_tck_prep");
+    }
+    p.wprep = reinterpret_cast<const __nv_bfloat16*>(dst);
+  }
+  CUtensorMap tmx, tmy;
+  int rc = gs_make_act_tmap(&tmx, x, n, h, wd, kdim, 32, 16, 1, 10, 128);
+  if (rc) return rc;
+  rc = gs_make_act_tmap(&tmy, y, n, h, wd, ndim, 32, 14, 1, 8, 128);
+  if (rc) return rc;
+  auto kern = conv_tck_kernel<3, 1>;
+  if (p.cat) kern = tps == 3 ? conv_tck_kernel<3, 1> : conv_tck_kernel<1, 1>;
+  else kern = tps == 3 ? conv_tck_kernel<3, 0> : conv_tck_kernel<1, 0>;
+  static bool attr[4] = {false, false, false, false};
+  const int ai = (tps == 3 ? 0 : 1) + 2 * p.cat;
+  if (!attr[ai]) {
+    GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+    attr[ai] = true;
+  }
+  int gx = gs_num_sms();
+  if (gx > p.ntiles) gx = p.ntiles;
+  kern<<<gx, TCK_THREADS, used + 1024 + 2 * TCK_OUT, st>>>(tmx, tmy, p);
+  GS_CHECK_LAUNCH("conv_tck");
+  return GS_OK;
+}
+
 // bf16x3 (two-term split).  A three-term split was measured and buys nothing: the tcgen05 fp32 accumulator
 // truncates (tools/tc_precision.py: mean relative error -9.5e-6 at K = 2304 whatever the split), so the
 // accumulation, not the operand split, bounds the accuracy at ~1e-5.
@@ -309,6 +393,8 @@ template <int FORM>
 int launch_tc(const float* x, const float* w, const float* bias, float* y, int n, int h_in, int w_in, int h_out,
               int w_out, int kdim, int ndim, int w_is_kn, int flip, float alpha, int act, bool cacheable,
               cudaStream_t st) {
+  if (FORM == TC_C1 && tck_ok(h_out, w_out, kdim, ndim))
+    return launch_tck(x, w, bias, y, n, h_out, w_out, kdim, ndim, w_is_kn, flip, alpha, act, cacheable, st);
   // the stride-2 gather form stages ~4x the pixels of the others: 16-channel chunks keep the rings in budget
   if (FORM == TC_C2)
     return launch_tc_impl<FORM, 16>(x, w, bias, y, n, h_in, w_in, h_out, w_out, kdim, ndim, w_is_kn, flip, alpha, act, cacheable, st);

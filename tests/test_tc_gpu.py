@@ -88,6 +88,13 @@ TC_FWD_CASES = [
     (8, 4, 32, 256, 256, 2),
     (8, 16, 128, 256, 256, 2),
     (5, 8, 16, 64, 32, 2),
+    # thin wide layers: kw-stacked kernel (8 x 14 tiles; 128 = 9 * 14 + 2 and 136 = 9 * 14 + 10 end in partial tiles)
+    (1, 8, 128, 32, 32, 1),
+    (2, 16, 136, 32, 32, 1),
+    (1, 8, 128, 64, 64, 1),
+    (2, 32, 144, 64, 64, 1),
+    (1, 16, 256, 64, 32, 1),
+    (1, 8, 128, 32, 64, 1),
 ]
 
 
@@ -122,6 +129,9 @@ TC_DGRAD_CASES = [
     (8, 4, 32, 256, 256, 2),
     (8, 16, 128, 256, 256, 2),
     (3, 8, 64, 64, 256, 2),
+    (1, 8, 128, 32, 32, 1),
+    (2, 16, 136, 64, 64, 1),
+    (1, 32, 144, 32, 64, 1),
 ]
 
 
