@@ -32,8 +32,8 @@ ITER_FLOP_PER_SAMPLE = 7 * F_G + 11 * F_D   # SURVEY 3.1 nominal model: D-run F_
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
 # (key = ConvProfiler key: form, n, h, w, ci, co, ksize, stride)
 NCU_TRAFFIC = {
-    ("conv_c", 8, 128, 1024, 32, 32, 3, 1): (134295552 + 85211392, "profiles/ncu_c1_32_v2_summary.txt"),
-    ("conv_t", 8, 128, 1024, 32, 32, 3, 1): (134295552 + 85211392, "profiles/ncu_c1_32_v2_summary.txt (same kernel and shape)"),
+    ("conv_c", 8, 128, 1024, 32, 32, 3, 1): (134295552 + 86461184, "profiles/ncu_ck_32_summary.txt"),
+    ("conv_t", 8, 128, 1024, 32, 32, 3, 1): (134295552 + 86461184, "profiles/ncu_ck_32_summary.txt (same kernel and shape)"),
     ("conv_w", 8, 128, 1024, 32, 32, 3, 1): (268535552 + 4204032, "profiles/ncu_w_32_v2_summary.txt"),
 }
 
@@ -363,6 +363,7 @@ def bench_ours(args):
                              "(the timed region replays CUDA graphs)",
                       launches_timed=top["n"], avg_launch_ms=avg_ms, algorithmic_flop_per_launch=top["flops"],
                       io_bytes_per_launch=top["bytes"], hbm_gbs_at_io_bytes=top["bytes"] / (avg_ms * 1e-3) / 1e9,
+                      hbm_frac_at_io_bytes=top["bytes"] / (avg_ms * 1e-3) / 1e9 / pk["hbm"],
                       share_of_step=top["ms"] / ms_eager, conv_family_share_of_step=conv_ms / ms_eager,
                       peak_source="%s bf16_tflops_sustained (kernel timed inside a long step)" % pk["source"],
                       step_tflops=ITER_FLOP_PER_SAMPLE * BATCH * value / 1e12,
