@@ -416,6 +416,7 @@ class GANSynth(object):
     @torch.no_grad()
     def generate_batch(self, labels, latents):
         """z + pitch -> images -> waveforms (models.py:25, 30-31)."""
+        F.K.weight_cache_reset()       # the caller may have changed the parameters since the last call
         fake_images = self.generator(latents, labels)
         self.fake_images = fake_images
         mag, inst = fake_images[:, 0].contiguous(), fake_images[:, 1].contiguous()
