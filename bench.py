@@ -226,6 +226,26 @@ def spectral_secondary(device, pk):
                 algorithmic_bytes_per_clip=1304576)
 
 
+def inference_secondary(model, device):
+    """BASELINE config 5 at B = 8: labels + latents -> generator -> inverse spectral -> waveforms (models.py:232-250)."""
+    g = torch.Generator().manual_seed(2)
+    lab = torch.nn.functional.one_hot(torch.arange(BATCH) % 61, 61).float().to(device)
+    z = torch.randn(BATCH, 256, generator=g).to(device)
+    for _ in range(3):
+        out = model.generate_batch(lab, z)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    torch.cuda.synchronize()
+    s.record()
+    for _ in range(reps):
+        out = model.generate_batch(lab, z)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / reps
+    return dict(workload="generate_batch at B=8 (eager): G forward + convert_to_waveform -> [8, 64000]",
+                ms_per_batch=ms, clips_per_s=BATCH / ms * 1e3, output_shape=list(out.shape))
+
+
 def oracle_iteration_time(batch, iters, threads=None):
     """Times the CPU oracle's full iteration (D update + G update) at `batch` on the host cores."""
     from oracle import models as omodels
@@ -377,6 +397,7 @@ def bench_ours(args):
                                            "(%.1f s), scaled x0.5 to batch 8" % times[0])
     if world == 1 and not args.no_spectral:
         line["secondary"] = spectral_secondary(device, pk)
+        line["secondary"]["inference"] = inference_secondary(model, device)
     print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()

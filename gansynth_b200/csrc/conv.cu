@@ -421,7 +421,8 @@ int launch_tcw(const float* big, const float* small, float* dw, int n, int bh, i
   p.out_ab = out_ab; p.alpha = alpha;
   p.nch = tcw_block(adim);
   p.nb = tcw_block(bdim);
-  p.cat = (3 * p.nb * 2 <= 512) && !getenv("GS_TC_NO_CAT");
+  p.nstack = (stride == 1 && p.nb <= 32 && !getenv("GS_TCW_NO_NSTACK")) ? 1 : 0;   // measured: no gain at NB = 64
+  p.cat = (p.nstack ? (6 * p.nb <= 256) : (3 * p.nb * 2 <= 512)) && !getenv("GS_TC_NO_CAT");
   p.njobs_n = bdim / p.nb;
   // M jobs: as many kh taps per 128-row accumulator as fit (16 chunks of 8 channels)
   const int qj = p.nch / 8, qb = p.nb / 8;
@@ -436,22 +437,23 @@ int launch_tcw(const float* big, const float* small, float* dw, int n, int bh, i
       p.map_id[p.mjobs] = (p.nkh[p.mjobs] == nkh_job) ? 0 : 1;
       ++p.mjobs;
     }
-  p.pw = stride == 1 ? 10 : 18;
-  p.bwraw = stride == 1 ? 10 : 17;
+  p.pw = stride == 1 ? (p.nstack ? 8 : 10) : 18;
+  p.bwraw = stride == 1 ? (p.nstack ? 8 : 10) : 17;
   const size_t budget = 222 * 1024 - 1024 - 8192;       // alignment slack; over-read slack of the 128-row M operand
   int tpr = 16;
+  if (const char* e = getenv("GS_TCW_TPR")) tpr = atoi(e);      // experiment knob: largest tile height tried
   size_t stage = 0, raw = 0;
   for (;; tpr >>= 1) {
     GS_CHECK_ARG(tpr >= 2, "conv_tcw: no tile fits shared memory (adim %d bdim %d)", adim, bdim);
     if (sh % tpr) continue;
     p.hr_max = stride * (tpr - 1) + nkh_job;
     const size_t big_stage = (size_t)p.hr_max * qj * p.pw * 16;          // one split term
-    const size_t small_stage = (size_t)tpr * 2 * qb * 128;
+    const size_t small_stage = (size_t)tpr * (p.nstack ? 6 : 2) * qb * 128;
     p.big_lo_off = (uint32_t)big_stage;
     p.small_off = (uint32_t)(2 * big_stage);
     stage = 2 * big_stage + small_stage;
     p.raw_big_chunk = (uint32_t)((((size_t)p.hr_max * p.bwraw * 128) + 1023) & ~(size_t)1023);
-    p.raw_small_chunk = (uint32_t)((((size_t)tpr * 8 * 128) + 1023) & ~(size_t)1023);
+    p.raw_small_chunk = (uint32_t)((((size_t)tpr * (p.nstack ? 10 : 8) * 128) + 1023) & ~(size_t)1023);
     raw = (size_t)(p.nch / 32) * p.raw_big_chunk + (size_t)(p.nb / 32) * p.raw_small_chunk;
     if (2 * stage + 2 * raw <= budget) break;
   }
@@ -465,7 +467,7 @@ int launch_tcw(const float* big, const float* small, float* dw, int n, int bh, i
   if (used + raw <= budget) { ++p.ds; used += raw; }
   p.tiles_h = sh / tpr; p.tiles_w = sw / 8; p.ntiles = n * p.tiles_h * p.tiles_w;
   int cols = 32;
-  while (cols < 3 * p.nb * (1 + p.cat)) cols <<= 1;
+  while (cols < 3 * p.nb * (1 + p.cat)) cols <<= 1;       // same count stacked or not: 3 kw blocks x NB x (1 + cat)
   p.tmem_cols = cols;
   TcwMaps maps;
   {
@@ -474,7 +476,7 @@ int launch_tcw(const float* big, const float* small, float* dw, int n, int bh, i
     const int nkh_last = 3 % nkh_job ? 3 % nkh_job : nkh_job;
     rc = gs_make_act_tmap(&maps.big[1], big, n, bh, bw, adim, 32, p.bwraw, 1, stride * (tpr - 1) + nkh_last, 128);
     if (rc) return rc;
-    rc = gs_make_act_tmap(&maps.small, small, n, sh, sw, bdim, 32, 8, 1, tpr, 128);
+    rc = gs_make_act_tmap(&maps.small, small, n, sh, sw, bdim, 32, p.nstack ? 10 : 8, 1, tpr, 128);
     if (rc) return rc;
   }
   const int njobs = p.mjobs * p.njobs_n;

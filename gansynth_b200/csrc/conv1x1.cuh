@@ -52,29 +52,38 @@ __global__ void __launch_bounds__(256) conv1x1_reduce_kernel(const float* __rest
   const int lane = threadIdx.x & 31, sub = lane % lpp, slot = lane / lpp;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long p0 = warp * ppw; p0 < npix; p0 += nwarps * ppw) {
-    const long long p = p0 + slot;
-    float acc[ND];
+  // U pixel groups per iteration: all their loads are issued before the first reduction (memory-level parallelism)
+  constexpr int U = 4;
+  for (long long p0 = warp * ppw * U; p0 < npix; p0 += nwarps * ppw * U) {
+    float acc[U][ND];
 #pragma unroll
-    for (int n = 0; n < ND; ++n) acc[n] = 0.0f;
-    if (p < npix) {
-      for (int k = sub * 4; k < kdim; k += lpp * 4) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(x + p * kdim + k));
+    for (int u = 0; u < U; ++u) {
+      const long long p = p0 + (long long)u * ppw + slot;
 #pragma unroll
-        for (int n = 0; n < ND; ++n) {
-          const float4 b = *reinterpret_cast<const float4*>(sB + n * kdim + k);
-          acc[n] += v.x * b.x + v.y * b.y + v.z * b.z + v.w * b.w;
+      for (int n = 0; n < ND; ++n) acc[u][n] = 0.0f;
+      if (p < npix) {
+        for (int k = sub * 4; k < kdim; k += lpp * 4) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(x + p * kdim + k));
+#pragma unroll
+          for (int n = 0; n < ND; ++n) {
+            const float4 b = *reinterpret_cast<const float4*>(sB + n * kdim + k);
+            acc[u][n] += v.x * b.x + v.y * b.y + v.z * b.z + v.w * b.w;
+          }
         }
       }
     }
 #pragma unroll
-    for (int n = 0; n < ND; ++n)
-      for (int o = lpp >> 1; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
-    if (sub == 0 && p < npix) {
+    for (int u = 0; u < U; ++u) {
+      const long long p = p0 + (long long)u * ppw + slot;
 #pragma unroll
-      for (int n = 0; n < ND; ++n) {
-        float v = acc[n] + (bias ? bias[n] : 0.0f);
-        y[p * ND + n] = act == 1 ? gs_lrelu(v) : v;
+      for (int n = 0; n < ND; ++n)
+        for (int o = lpp >> 1; o > 0; o >>= 1) acc[u][n] += __shfl_xor_sync(0xffffffffu, acc[u][n], o);
+      if (sub == 0 && p < npix) {
+#pragma unroll
+        for (int n = 0; n < ND; ++n) {
+          float v = acc[u][n] + (bias ? bias[n] : 0.0f);
+          y[p * ND + n] = act == 1 ? gs_lrelu(v) : v;
+        }
       }
     }
   }

@@ -14,6 +14,11 @@
 //   small staged as [row][hi q.. | lo q..][8 pixels]: hi and lo chunks adjacent, so hi x [hi | lo] is one
 //         MMA of width 2 * NB ("cat", as in conv_tc.cuh) when the accumulators fit TMEM.
 //
+// "N-stacked" variant (stride 1, NB = 32): the three kw taps move to the N side.  `small` is staged as three
+// column-shifted copies [row][hi: kw0 kw1 kw2 | lo: kw0 kw1 kw2][q][8 pixels] (raw box 10 pixels wide), `big` needs no
+// column halo, and ONE MMA of width 6 NB (cat) + one of width 3 NB per K step replace the three kw groups (measured:
+// 112 -> 104 us on the top layer; no gain at NB = 64, and 12 converter warps instead of 8 buy nothing either).
+//
 // A job (blockIdx.y) = (kh range, big-channel block of <= 128, small-channel block NB <= 128): one 128-row
 // accumulator per kw (3 * NB * (1 + cat) <= 512 TMEM columns).  grid.x splits the pixel tiles; every CTA
 // accumulates over its whole pixel range and adds its partial filter gradient to dw with (vector) fp32
@@ -42,6 +47,7 @@ struct TcwParams {
   int kh0[8], nkh[8], ch0[8], map_id[8];
   int nch, nb;                    // big / small channels per job (multiples of 32, <= 128)
   int cat;
+  int nstack;                     // kw taps stacked along N (three shifted copies of `small`)
   int pw, bwraw;                  // staged / raw pixels per big row: 10 / 10 (stride 1), 18 / 17 (stride 2)
   int hr_max;                     // staged big rows of the job with the most kh taps
   int stages, ds, out_ab, tmem_cols;
@@ -68,7 +74,8 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const __grid_c
   const int S = p.stride;
   const int qj = p.nch >> 3, qb = p.nb >> 3;
   const int hr_rows = S * (p.tpr - 1) + nkh;
-  const int nbig_px = hr_rows * p.bwraw, nsmall_px = p.tpr * 8;
+  const int swraw = p.nstack ? 10 : 8;                       // raw small box width
+  const int nbig_px = hr_rows * p.bwraw, nsmall_px = p.tpr * swraw;
   const int big_chunks = p.nch >> 5, small_chunks = p.nb >> 5;
   unsigned char* smem = tcw_smem_raw + ((1024u - (tc::smem_u32(tcw_smem_raw) & 1023u)) & 1023u);
   unsigned char* raw_smem = smem;
@@ -94,6 +101,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const __grid_c
   tc::tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   const int acc_w = p.cat ? 2 * p.nb : p.nb;
+  const int nchunk_row = p.nstack ? 6 * qb : 2 * qb;         // 16-byte x 8-pixel chunks per staged row of small
 
   if (warp < 8) {
     // ============================== fp32 -> bf16 hi/lo split ===========================================
@@ -141,10 +149,24 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const __grid_c
           tc::split2_bf16(v0.z, v0.w, h4.y, l4.y);
           tc::split2_bf16(v1.x, v1.y, h4.z, l4.z);
           tc::split2_bf16(v1.z, v1.w, h4.w, l4.w);
-          const uint32_t r = (uint32_t)px >> 3, c = (uint32_t)px & 7u;
-          const uint32_t d = ((r * 2u * (uint32_t)qb + (uint32_t)q) * 8u + c) << 4;
-          *reinterpret_cast<uint4*>(ss + d) = h4;
-          *reinterpret_cast<uint4*>(ss + d + ((uint32_t)qb << 7)) = l4;
+          if (!p.nstack) {
+            const uint32_t r = (uint32_t)px >> 3, c = (uint32_t)px & 7u;
+            const uint32_t d = ((r * 2u * (uint32_t)qb + (uint32_t)q) * 8u + c) << 4;
+            *reinterpret_cast<uint4*>(ss + d) = h4;
+            *reinterpret_cast<uint4*>(ss + d + ((uint32_t)qb << 7)) = l4;
+          } else {
+            // raw column hc (image column ox0 - 1 + hc) is pixel c = hc - 2 + kw of the copy for tap kw
+            const int r = px / 10, hc = px - r * 10;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              const int c = hc - 2 + kw;
+              if (c >= 0 && c < 8) {
+                const uint32_t d = (((uint32_t)(r * nchunk_row + kw * qb + q)) * 8u + (uint32_t)c) << 4;
+                *reinterpret_cast<uint4*>(ss + d) = h4;
+                *reinterpret_cast<uint4*>(ss + d + ((uint32_t)(3 * qb) << 7)) = l4;
+              }
+            }
+          }
         }
       }
       tc::fence_proxy_async();
@@ -170,10 +192,12 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const __grid_c
 #pragma unroll 1
         for (int c0 = 0; c0 < p.nb; c0 += 32) {
           float v[32];
-          tc::tmem_ld32(tmem_base + lane_base + (uint32_t)(kw * acc_w + c0), v);
+          const int col_hh = p.nstack ? kw * p.nb : kw * acc_w;
+          const int col_hl = p.nstack ? (3 + kw) * p.nb : kw * acc_w + p.nb;
+          tc::tmem_ld32(tmem_base + lane_base + (uint32_t)(col_hh + c0), v);
           if (p.cat) {
             float v2[32];
-            tc::tmem_ld32(tmem_base + lane_base + (uint32_t)(kw * acc_w + p.nb + c0), v2);
+            tc::tmem_ld32(tmem_base + lane_base + (uint32_t)(col_hl + c0), v2);
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] += v2[j];
           }
@@ -207,7 +231,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const __grid_c
         const int th_ = t % p.tiles_h;
         const int n = t / p.tiles_h;
         const int ox0 = tw_ * 8, oy0 = th_ * p.tpr;
-        const int bx0 = (S == 1) ? ox0 - 1 : 2 * ox0;
+        const int bx0 = (S == 1) ? (p.nstack ? ox0 : ox0 - 1) : 2 * ox0;
         const int by0 = (S == 1) ? oy0 - 1 + kh0 : 2 * oy0 + kh0;
         tc::mbar_wait(&raw_empty[rs], rph ^ 1u);
         tc::mbar_arrive_expect_tx(&raw_full[rs], bytes);
@@ -216,7 +240,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const __grid_c
           tc::tma_load_4d(slot + (size_t)c * p.raw_big_chunk, mb, ch0 + 32 * c, bx0, n, by0, &raw_full[rs]);
         for (int c = 0; c < small_chunks; ++c)
           tc::tma_load_4d(slot + (size_t)big_chunks * p.raw_big_chunk + (size_t)c * p.raw_small_chunk, &maps.small, nb0 + 32 * c,
-                          ox0, n, oy0, &raw_full[rs]);
+                          p.nstack ? ox0 - 1 : ox0, n, oy0, &raw_full[rs]);
         if (++rs == p.ds) { rs = 0; rph ^= 1u; }
       }
     }
@@ -224,16 +248,19 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const __grid_c
     // ============================== MMA issue ==========================================================
     // A (big, M side): chunk stride = pw pixels, 8-pixel K group stride = S staged rows; B (small, N side):
     // chunk stride = 8 pixels, K group stride = one staged row.  One K step = two tile rows.
-    const uint32_t idesc_w = tc::idesc_bf16_f32(acc_w, 1, 1);
-    const uint32_t idesc_n = tc::idesc_bf16_f32(p.nb, 1, 1);
+    const uint32_t n_wide = p.nstack ? (uint32_t)((p.cat ? 6 : 3) * p.nb) : (uint32_t)acc_w;
+    const uint32_t n_narrow = p.nstack ? (uint32_t)(3 * p.nb) : (uint32_t)p.nb;
+    const uint32_t idesc_w = tc::idesc_bf16_f32((int)n_wide, 1, 1);
+    const uint32_t idesc_n = tc::idesc_bf16_f32((int)n_narrow, 1, 1);
     const uint32_t lbo_m = (uint32_t)(S * qj * p.pw) * 16u, sbo_m = (uint32_t)p.pw * 16u;
-    const uint32_t lbo_n = (uint32_t)(2 * qb) * 128u, sbo_n = 128u;
+    const uint32_t lbo_n = (uint32_t)nchunk_row * 128u, sbo_n = 128u;
     const uint64_t m_desc0 = tc::smem_desc(tc::smem_u32(st_smem), lbo_m, sbo_m);
     const uint64_t n_desc0 = tc::smem_desc(tc::smem_u32(st_smem) + p.small_off, lbo_n, sbo_n);
     const uint32_t stage16 = p.stage_bytes >> 4;
-    const uint32_t m_lo16 = p.big_lo_off >> 4, n_lo16 = ((uint32_t)qb << 7) >> 4;
+    const uint32_t m_lo16 = p.big_lo_off >> 4, n_lo16 = ((uint32_t)(p.nstack ? 3 * qb : qb) << 7) >> 4;
     const uint32_t m_step16 = (2u * lbo_m) >> 4, n_step16 = (2u * lbo_n) >> 4;
     const int ksteps = p.tpr / 2;
+    const int ngroups = p.nstack ? 1 : 3;             // kw groups per K step (stacked: all three in one instruction)
     int stage = 0;
     uint32_t ph = 0, accum_first = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
@@ -242,9 +269,8 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const __grid_c
       const uint64_t m_base = m_desc0 + (uint64_t)((uint32_t)stage * stage16);
       const uint64_t n_base = n_desc0 + (uint64_t)((uint32_t)stage * stage16);
       if (tc::elect_one()) {
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const uint32_t kw16 = (S == 1) ? (uint32_t)kw : (uint32_t)((kw & 1) * 9 + (kw >> 1));
+        for (int kw = 0; kw < ngroups; ++kw) {
+          const uint32_t kw16 = p.nstack ? 0u : (S == 1) ? (uint32_t)kw : (uint32_t)((kw & 1) * 9 + (kw >> 1));
           uint64_t a_hi = m_base + (uint64_t)kw16;
           uint64_t b_hi = n_base;
           const uint32_t d = tmem_base + (uint32_t)(kw * acc_w);
