@@ -56,7 +56,7 @@ SIGNATURES = {
     "gs_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _L, _F, _P],
     "gs_tc_probe": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "gs_tc_probe_time": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
-    "gs_spectrogram_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "gs_spectrogram_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "gs_waveform_fwd": [_P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _P],
 }
 

@@ -143,131 +143,257 @@ int ensure_tables(cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------------
 // Forward: waveform -> (log-mel magnitude, mel instantaneous frequency).
-// One warp per (clip, chunk of L consecutive frames); a chunk that does not start the clip first
-// recomputes frame t0-1 to get the previous mel phase.
-constexpr int FWD_WARPS = 16;   // 16 x 12.25 KB of per-warp tiles + 16 KB of tables = 212 KB: one CTA of 16 warps per SM
-constexpr int FWD_WARP_FLOATS = WARP_BUF + NBINS;  // FFT tile (reused for mag/phase) + previous mel phase
-constexpr int FWD_SMEM = (2 * 1024 * 2 + FWD_WARPS * FWD_WARP_FLOATS) * 4;
+//
+// One CTA owns a RUN of consecutive frames of one clip and walks it in lock-step rounds of FWD_WARPS frames,
+// one frame per warp: neighbouring warps read overlapping samples at the same time (L1 reuse of the 75 %
+// overlap), and the mel phase of frame t-1 that the instantaneous frequency of frame t needs is the
+// neighbouring warp's result of the same round (shared memory), never a recomputed transform.  Only the first
+// frame of a run (t0 > 0) has no neighbour: it is written as raw phase, the last frame of the run before it
+// leaves its phase in `scratch`, and spectrogram_if_fixup_kernel finishes those rows.
+//
+// Per warp: an 8 KB tile = XOR-swizzled FFT exchange planes, then the 1024 (magnitude, phase) pairs of the
+// frame (slot d = FFT bin d + 1: the DC bin is dropped, the Nyquist bin is slot 1023), then the frame's 1024
+// mel phases for the neighbour.  All constant tables (mel taps, twiddles, Hann) sit in shared memory.
+constexpr int FWD_WARPS = 16;
+constexpr int TILE = 2048;                       // floats per warp
+constexpr int FWD_TABLE_FLOATS = NBINS /*mel k0*/ + MEL_TAPS * NBINS /*mel w*/ + 2048 /*tw1024*/ + 1040 /*tw2048, k<=512*/ +
+                                 FRAME /*hann*/ + 2 * NBINS /*carry*/;
+constexpr int FWD_SMEM = (FWD_TABLE_FLOATS + FWD_WARPS * TILE) * 4;
 
-__global__ void __launch_bounds__(FWD_WARPS * 32)
-spectrogram_fwd_kernel(const float* __restrict__ wave, int wave_len, int T, int L, const float* __restrict__ hann,
-                       const float2* __restrict__ tw1024g, const float2* __restrict__ tw2048g,
-                       const int* __restrict__ mel_k0, const float* __restrict__ mel_w, float* __restrict__ logmel,
-                       float* __restrict__ inst, int n_items) {
-  extern __shared__ __align__(16) float sm[];
-  float2* tw1024 = reinterpret_cast<float2*>(sm);
-  float2* tw2048 = tw1024 + 1024;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* buf = sm + 4096 + warp * FWD_WARP_FLOATS;
-  float* prev = buf + WARP_BUF;
-  for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
-    tw1024[i] = tw1024g[i];
-    tw2048[i] = tw2048g[i];
-  }
-  __syncthreads();
-  const int item = blockIdx.x * FWD_WARPS + warp;
-  if (item >= n_items) return;
-  const int chunks = T / L;
-  const int b = item / chunks;
-  const int t0 = (item % chunks) * L;
-  const int padf = HOP * (T - 1) + FRAME - wave_len;
-  const float* wv = wave + (size_t)b * wave_len;
+__device__ __forceinline__ float gs_sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// wrapped phase difference in units of pi: ((d + pi) floor-mod 2 pi) - pi, with numpy.unwrap's +pi convention
+// (spectral_ops.py:20-31 followed by diff, :34-42).  |d| < 2 pi * 6: one correction step each way covers the rounding
+// of the quotient.
+__device__ __forceinline__ float gs_wrap_diff(float d) {
   const float PI_F = 3.14159274101257324f;
   const float TWO_PI_F = 6.28318548202514648f;
-  float* zr = buf;
-  float* zi = buf + PLANE;
+  const float tt = d + PI_F;
+  float md = fmaf(-floorf(tt * 0.159154943091895336f), TWO_PI_F, tt);
+  if (md < 0.0f) md += TWO_PI_F;
+  if (md >= TWO_PI_F) md -= TWO_PI_F;
+  md -= PI_F;
+  if (md == -PI_F && d > 0.0f) md = PI_F;
+  return md * 0.318309886183790672f;
+}
 
-  for (int t = (t0 > 0 ? t0 - 1 : 0); t < t0 + L; ++t) {
-    float re[32], im[32];
+// 1024-point forward DFT over one warp, exchange through two XOR-swizzled 32x32 planes (conflict-free both ways).
+// In: lane holds z[32*n1 + lane] in slot n1.  Out: lane holds Z[lane + 32*k2] in slot brev5(k2).
+__device__ __forceinline__ void warp_fft1024_sw(float (&re)[32], float (&im)[32], float* buf, const float2* tw, int lane) {
+  fft32(re, im);
+  float* br = buf;
+  float* bi = buf + 1024;
 #pragma unroll
-    for (int n1 = 0; n1 < 32; ++n1) {
-      const int nn = 64 * n1 + 2 * lane;
-      const int s = HOP * t + nn - padf;
-      const float2 hw = __ldg(reinterpret_cast<const float2*>(hann + nn));
-      float v0 = (s >= 0 && s < wave_len) ? __ldg(wv + s) : 0.0f;
-      float v1 = (s + 1 >= 0 && s + 1 < wave_len) ? __ldg(wv + s + 1) : 0.0f;
-      re[n1] = v0 * hw.x;
-      im[n1] = v1 * hw.y;
-    }
-    warp_fft1024(re, im, buf, tw1024, lane);
+  for (int k1 = 0; k1 < 32; ++k1) {
+    const int r = brev5(k1);
+    const float2 w = tw[k1 * 32 + lane];
+    const float yr = re[r], yi = im[r];
+    const int a = k1 * 32 + (lane ^ k1);
+    br[a] = yr * w.x - yi * w.y;
+    bi[a] = yr * w.y + yi * w.x;
+  }
+  __syncwarp();
 #pragma unroll
-    for (int k2 = 0; k2 < 32; ++k2) {
-      zr[lane + 32 * k2] = re[brev5(k2)];
-      zi[lane + 32 * k2] = im[brev5(k2)];
+  for (int n2 = 0; n2 < 32; ++n2) {
+    const int a = lane * 32 + (n2 ^ lane);
+    re[n2] = br[a];
+    im[n2] = bi[a];
+  }
+  __syncwarp();
+  fft32(re, im);
+}
+
+__global__ void __launch_bounds__(FWD_WARPS * 32, 1)
+spectrogram_fwd_kernel(const float* __restrict__ wave, int wave_len, int T, int RL, int runs_per_clip,
+                       const float* __restrict__ hann_g, const float2* __restrict__ tw1024g,
+                       const float2* __restrict__ tw2048g, const int* __restrict__ mel_k0,
+                       const float* __restrict__ mel_w, float* __restrict__ logmel, float* __restrict__ inst,
+                       float* __restrict__ scratch) {
+  extern __shared__ __align__(16) float sm[];
+  int* melk = reinterpret_cast<int*>(sm);                           // [1024]
+  float* melw = sm + NBINS;                                         // [6][1024]
+  float2* tw1024 = reinterpret_cast<float2*>(melw + MEL_TAPS * NBINS);  // [1024]
+  float2* tw2048 = tw1024 + 1024;                                   // [513] (+pad)
+  float2* hann2 = reinterpret_cast<float2*>(sm + NBINS + MEL_TAPS * NBINS + 2048 + 1040);  // [1024]
+  float* carry = reinterpret_cast<float*>(hann2 + 1024);            // [2][1024]
+  float* tiles = carry + 2 * NBINS;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* buf = tiles + warp * TILE;
+  for (int i = tid; i < 1024; i += FWD_WARPS * 32) {
+    // taps of mel bin i start at data row k0; keep all MEL_TAPS reads inside [0, 1024) by sliding the window down
+    const int k0 = __ldg(mel_k0 + i);
+    const int k0c = min(max(k0, 0), NBINS - MEL_TAPS);
+    const int sh = k0 - k0c;
+    melk[i] = k0c;
+#pragma unroll
+    for (int u = 0; u < MEL_TAPS; ++u) {
+      const int src = u - sh;
+      melw[u * NBINS + i] = (src >= 0 && src < MEL_TAPS) ? __ldg(mel_w + src * NBINS + i) : 0.0f;
     }
-    __syncwarp();
-    // split step: X[k] = E + W^k O, X[1024-k] = conj(E - W^k O); magnitude -> zr, phase -> zi, stored at slot (k & 1023)
-    for (int m = 0; m <= 16; ++m) {
-      const int k = lane + 32 * m;
-      if (k <= 512) {
-        const int kc = (1024 - k) & 1023;
-        const float ar = zr[k], ai = zi[k], cr = zr[kc], ci = zi[kc];
+    tw1024[i] = tw1024g[i];
+    if (i <= 512) tw2048[i] = tw2048g[i];
+    hann2[i] = __ldg(reinterpret_cast<const float2*>(hann_g) + i);
+  }
+  __syncthreads();
+
+  const int b = blockIdx.x / runs_per_clip;
+  const int run = blockIdx.x % runs_per_clip;
+  const int t0 = run * RL;
+  const int t1 = min(T, t0 + RL);
+  const int padf = HOP * (T - 1) + FRAME - wave_len;
+  const float* wv = wave + (size_t)b * wave_len;
+  const bool vec_ok = (((wave_len | padf) & 1) == 0) && ((reinterpret_cast<uintptr_t>(wave) & 7) == 0);
+  float2* zc = reinterpret_cast<float2*>(buf);
+
+  int round = 0;
+  for (int tb = t0; tb < t1; tb += FWD_WARPS, ++round) {
+    const int t = tb + warp;
+    const bool active = t < t1;
+    float pp[32];
+    if (active) {
+      float re[32], im[32];
+      const int base = HOP * t - padf;  // sample index of frame element 0
+      if (vec_ok && base >= 0 && base + FRAME <= wave_len) {
+        const float2* p = reinterpret_cast<const float2*>(wv + base) + lane;
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+          const float2 v = __ldg(p + 32 * n1);
+          const float2 hw = hann2[32 * n1 + lane];
+          re[n1] = v.x * hw.x;
+          im[n1] = v.y * hw.y;
+        }
+      } else {
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+          const int s = base + 64 * n1 + 2 * lane;
+          const float2 hw = hann2[32 * n1 + lane];
+          const float v0 = (s >= 0 && s < wave_len) ? __ldg(wv + s) : 0.0f;
+          const float v1 = (s + 1 >= 0 && s + 1 < wave_len) ? __ldg(wv + s + 1) : 0.0f;
+          re[n1] = v0 * hw.x;
+          im[n1] = v1 * hw.y;
+        }
+      }
+      warp_fft1024_sw(re, im, buf, tw1024, lane);
+#pragma unroll
+      for (int k2 = 0; k2 < 32; ++k2) zc[lane + 32 * k2] = make_float2(re[brev5(k2)], im[brev5(k2)]);
+      __syncwarp();
+      // split step: X[k] = E + W^k O, X[1024-k] = conj(E - W^k O) from Z[k], Z[1024-k]; all operands are read
+      // before any (magnitude, phase) pair is written because X[k] lands in slot k-1
+      float2 za[17], zb[17];
+#pragma unroll
+      for (int m = 0; m < 16; ++m) {
+        const int k = lane + 32 * m;
+        za[m] = zc[k];
+        zb[m] = zc[(1024 - k) & 1023];
+      }
+      za[16] = zc[512];
+      zb[16] = za[16];
+      __syncwarp();
+#pragma unroll
+      for (int m = 0; m < 17; ++m) {
+        const int k = (m < 16) ? lane + 32 * m : 512;
+        const float ar = za[m].x, ai = za[m].y, cr = zb[m].x, ci = zb[m].y;
         const float er = 0.5f * (ar + cr), ei = 0.5f * (ai - ci);
         const float orr = 0.5f * (ai + ci), oi = -0.5f * (ar - cr);
         const float2 w = tw2048[k];
         const float tr = orr * w.x - oi * w.y, ti = orr * w.y + oi * w.x;
         const float xr = er + tr, xi = ei + ti;        // X[k]
-        const float yr = er - tr, yi = -(ei - ti);     // X[1024-k]
-        if (k >= 1) {
-          zr[k] = sqrtf(fmaf(xr, xr, xi * xi));
-          zi[k] = gs_atan2f(xi + 0.0f, xr + 0.0f);
-        }
-        if (k != 512) {
-          zr[kc] = sqrtf(fmaf(yr, yr, yi * yi));
-          zi[kc] = gs_atan2f(yi + 0.0f, yr + 0.0f);
+        const float yr = er - tr, yi = ti - ei;        // X[1024-k]
+        if (m < 16) {
+          if (k >= 1) zc[k - 1] = make_float2(gs_sqrt_approx(fmaf(xr, xr, xi * xi)), gs_atan2f(xi + 0.0f, xr + 0.0f));
+          zc[1023 - k] = make_float2(gs_sqrt_approx(fmaf(yr, yr, yi * yi)), gs_atan2f(yi + 0.0f, yr + 0.0f));
+        } else if (lane == 0) {
+          zc[511] = make_float2(gs_sqrt_approx(fmaf(xr, xr, xi * xi)), gs_atan2f(xi + 0.0f, xr + 0.0f));
         }
       }
-    }
-    __syncwarp();
-    const bool emit = (t >= t0);
-    float* lm_out = logmel + ((size_t)b * T + t) * NBINS;
-    float* if_out = inst + ((size_t)b * T + t) * NBINS;
-#pragma unroll 4
-    for (int m = 0; m < 32; ++m) {
-      const int j = lane + 32 * m;
-      const int k0 = __ldg(mel_k0 + j);
-      float mm = 0.0f, pp = 0.0f;
+      __syncwarp();
+      // sparse mel projection of magnitude and phase (spectral_ops.py:76-85), log-magnitude out
+      float* lm_out = logmel + ((size_t)b * T + t) * NBINS;
 #pragma unroll
-      for (int i = 0; i < MEL_TAPS; ++i) {
-        const float wgt = __ldg(mel_w + i * NBINS + j);
-        const int slot = (k0 + i + 1) & 1023;
-        mm = fmaf(zr[slot], wgt, mm);
-        pp = fmaf(zi[slot], wgt, pp);
-      }
-      if (emit) {
-        lm_out[j] = (__logf(mm + 1.0e-6f) + 3.76f) * (1.0f / 10.05f);
-        float v;
-        if (t == 0) {
-          v = pp * 0.318309886183790672f;
-        } else {
-          const float d = pp - prev[j];
-          // floor-mod of d + pi by 2 pi (|d| < 2 pi: one correction step each way covers the rounding of the quotient)
-          const float tt = d + PI_F;
-          float md = fmaf(-floorf(tt * 0.159154943091895336f), TWO_PI_F, tt);
-          if (md < 0.0f) md += TWO_PI_F;
-          if (md >= TWO_PI_F) md -= TWO_PI_F;
-          md -= PI_F;
-          if (md == -PI_F && d > 0.0f) md = PI_F;
-          v = md * 0.318309886183790672f;
+      for (int m = 0; m < 32; ++m) {
+        const int j = lane + 32 * m;
+        const float2* z = zc + melk[j];
+        float mm = 0.0f, ph = 0.0f;
+#pragma unroll
+        for (int i = 0; i < MEL_TAPS; ++i) {
+          const float wgt = melw[i * NBINS + j];
+          const float2 v = z[i];
+          mm = fmaf(v.x, wgt, mm);
+          ph = fmaf(v.y, wgt, ph);
         }
-        if_out[j] = v;
+        pp[m] = ph;
+        lm_out[j] = (__logf(mm + 1.0e-6f) + 3.76f) * (1.0f / 10.05f);
       }
-      prev[j] = pp;
+      __syncwarp();
+      // publish this frame's mel phase for the next frame's warp (the last warp feeds warp 0 of the next round)
+      float* pub = (warp == FWD_WARPS - 1) ? carry + (round & 1) * NBINS : buf;
+#pragma unroll
+      for (int m = 0; m < 32; ++m) pub[lane + 32 * m] = pp[m];
     }
-    __syncwarp();
+    __syncthreads();
+    if (active) {
+      float* if_out = inst + ((size_t)b * T + t) * NBINS;
+      if (t == 0) {
+#pragma unroll
+        for (int m = 0; m < 32; ++m) if_out[lane + 32 * m] = pp[m] * 0.318309886183790672f;
+      } else if (t == t0) {
+        // first frame of a later run: raw phase, finished by spectrogram_if_fixup_kernel
+#pragma unroll
+        for (int m = 0; m < 32; ++m) if_out[lane + 32 * m] = pp[m];
+      } else {
+        const float* prev = (warp == 0) ? carry + ((round + 1) & 1) * NBINS : buf - TILE;
+#pragma unroll
+        for (int m = 0; m < 32; ++m) if_out[lane + 32 * m] = gs_wrap_diff(pp[m] - prev[lane + 32 * m]);
+      }
+      if (t == t1 - 1 && t1 < T) {
+        float* sc = scratch + ((size_t)b * runs_per_clip + run) * NBINS;
+#pragma unroll
+        for (int m = 0; m < 32; ++m) sc[lane + 32 * m] = pp[m];
+      }
+    }
+    __syncthreads();
   }
 }
 
+// Rows t0 = run * RL (run >= 1) hold raw mel phase; scratch[b][run-1] holds the mel phase of frame t0 - 1.
+__global__ void __launch_bounds__(256)
+spectrogram_if_fixup_kernel(float* __restrict__ inst, const float* __restrict__ scratch, int T, int RL,
+                            int runs_per_clip, int rows) {
+  const int row = blockIdx.x;
+  if (row >= rows) return;
+  const int b = row / (runs_per_clip - 1);
+  const int run = row % (runs_per_clip - 1) + 1;
+  float4* cur = reinterpret_cast<float4*>(inst + ((size_t)b * T + (size_t)run * RL) * NBINS) + threadIdx.x;
+  const float4 p = __ldg(reinterpret_cast<const float4*>(scratch + ((size_t)b * runs_per_clip + run - 1) * NBINS) + threadIdx.x);
+  float4 c = *cur;
+  c.x = gs_wrap_diff(c.x - p.x);
+  c.y = gs_wrap_diff(c.y - p.y);
+  c.z = gs_wrap_diff(c.z - p.z);
+  c.w = gs_wrap_diff(c.w - p.w);
+  *cur = c;
+}
+
 // ------------------------------------------------------------------------------------------------
-// Inverse: (log-mel magnitude, mel IF) -> waveform.  One CTA per clip, 8 warps, frames in groups of 8:
-// running phase cumsum in registers, banded mel->linear product, one inverse FFT per warp, overlap-add
-// through a carry buffer so every output sample is written exactly once.
+// Inverse: (log-mel magnitude, mel IF) -> waveform.  One CTA of 16 warps per clip, frames in groups of 8, three
+// stages per group separated by CTA barriers:
+//   (b) all warps: banded mel->linear product for magnitude and phase + polar->rectangular.  The 8 frames of a
+//       mel bin sit in ONE padded shared-memory row (8 magnitudes, 8 phases), so a band tap costs 4 LDS.128 for
+//       16 FMAs; the 32 column blocks are handed out heaviest-first through a shared counter because the band is
+//       2 rows wide at low frequencies and 46 around bin 330;
+//   (c) warps 0-7: one inverse real FFT each (spectrum and frame share the warp's tile), synthesis window;
+//       warps 8-15 meanwhile do stage (a) of the NEXT group: un-normalise, exp, running phase cumsum in registers;
+//   (d) all warps: overlap-add through a ping-pong carry so every output sample is written exactly once.
 constexpr int INV_F = 8;
-constexpr int INV_THREADS = INV_F * 32;
+constexpr int INV_WARPS = 16;
+constexpr int INV_THREADS = INV_WARPS * 32;
 constexpr int CARRY = FRAME - HOP;  // 1536
 constexpr int XLEN = 1028;          // X planes hold k = 0..1024
-constexpr int INV_SMEM_FLOATS = 4096 /*tables*/ + 2 * INV_F * NBINS /*mel mag/phase*/ + 2 * INV_F * XLEN /*X*/ +
-                                INV_F * WARP_BUF /*fft tiles + frames*/ + CARRY;
+constexpr int MROW = 20;            // floats per mel row: 8 mag + 8 phase + 4 pad (8 consecutive rows hit 8 distinct bank quads)
+constexpr int INV_SMEM_FLOATS = 4096 /*tables*/ + NBINS * MROW + INV_F * WARP_BUF /*X, fft tiles, frames*/ + 2 * CARRY + 64;
 constexpr int INV_SMEM = INV_SMEM_FLOATS * 4;
 
 __global__ void __launch_bounds__(INV_THREADS, 1)
@@ -278,53 +404,75 @@ waveform_fwd_kernel(const float* __restrict__ logmel, const float* __restrict__ 
   extern __shared__ __align__(16) float sm[];
   float2* tw1024 = reinterpret_cast<float2*>(sm);
   float2* tw2048 = tw1024 + 1024;
-  float* mmag = sm + 4096;                    // [F][1024]
-  float* mph = mmag + INV_F * NBINS;          // [F][1024]
-  float* xr = mph + INV_F * NBINS;            // [F][XLEN]
-  float* xi = xr + INV_F * XLEN;              // [F][XLEN]
-  float* tiles = xi + INV_F * XLEN;           // [F][WARP_BUF]
-  float* carry = tiles + INV_F * WARP_BUF;    // [1536]
+  float* melmp = sm + 4096;                    // [1024][MROW]
+  float* tiles = melmp + NBINS * MROW;         // [F][WARP_BUF]
+  float* carry = tiles + INV_F * WARP_BUF;     // [2][1536]
+  int* order = reinterpret_cast<int*>(carry + 2 * CARRY);  // [32] column blocks, heaviest first
+  int* ctr = order + 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x;
   for (int i = tid; i < 1024; i += INV_THREADS) {
     tw1024[i] = tw1024g[i];
     tw2048[i] = tw2048g[i];
   }
-  for (int i = tid; i < CARRY; i += INV_THREADS) carry[i] = 0.0f;
+  for (int i = tid; i < 2 * CARRY; i += INV_THREADS) carry[i] = 0.0f;
+  if (warp == 0) {
+    int wmax = 0;
+    for (int i = 0; i < 32; ++i) wmax = max(wmax, __ldg(pb_cnt + lane * 32 + i));
+    int rank = 0;
+    for (int m = 0; m < 32; ++m) {
+      const int o = __shfl_sync(0xffffffffu, wmax, m);
+      rank += (o > wmax || (o == wmax && m < lane)) ? 1 : 0;
+    }
+    order[rank] = lane;
+    if (lane == 0) *ctr = 0;
+  }
   const float PI_F = 3.14159274101257324f;
   const int padf = HOP * (T - 1) + FRAME - wave_len;
   float run[4] = {0.f, 0.f, 0.f, 0.f};
   float* out = wave + (size_t)b * wave_len;
+
+  // (a) un-normalise, exp, running phase (threads 256..511; column j = u + 256 q)
+  auto stage_a = [&](int g0) {
+    const int u = tid - 256;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = u + 256 * q;
+      float lmv[INV_F], ifv[INV_F];
+#pragma unroll
+      for (int f = 0; f < INV_F; ++f) {
+        const size_t o = ((size_t)b * T + g0 + f) * NBINS + j;
+        const bool ok = (g0 + f) < T;
+        lmv[f] = ok ? __ldg(logmel + o) : 0.0f;
+        ifv[f] = ok ? __ldg(inst + o) : 0.0f;
+      }
+      float mg[INV_F], ph[INV_F];
+#pragma unroll
+      for (int f = 0; f < INV_F; ++f) {
+        run[q] = __fadd_rn(run[q], __fmul_rn(ifv[f], PI_F));
+        ph[f] = run[q];
+        mg[f] = expf(__fadd_rn(__fmul_rn(lmv[f], 10.05f), -3.76f));
+      }
+      float4* row = reinterpret_cast<float4*>(melmp + j * MROW);
+      row[0] = make_float4(mg[0], mg[1], mg[2], mg[3]);
+      row[1] = make_float4(mg[4], mg[5], mg[6], mg[7]);
+      row[2] = make_float4(ph[0], ph[1], ph[2], ph[3]);
+      row[3] = make_float4(ph[4], ph[5], ph[6], ph[7]);
+    }
+  };
+
+  if (warp >= 8) stage_a(0);
   __syncthreads();
 
+  int par = 0;
   for (int g0 = 0; g0 < T; g0 += INV_F) {
-    // (a) un-normalise, exp, running phase
-    {
-      float lmv[INV_F][4], ifv[INV_F][4];
-#pragma unroll
-      for (int f = 0; f < INV_F; ++f)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const size_t o = ((size_t)b * T + g0 + f) * NBINS + tid + INV_THREADS * q;
-          const bool ok = (g0 + f) < T;
-          lmv[f][q] = ok ? __ldg(logmel + o) : 0.0f;
-          ifv[f][q] = ok ? __ldg(inst + o) : 0.0f;
-        }
-#pragma unroll
-      for (int f = 0; f < INV_F; ++f)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int j = tid + INV_THREADS * q;
-          run[q] = __fadd_rn(run[q], __fmul_rn(ifv[f][q], PI_F));
-          mph[f * NBINS + j] = run[q];
-          mmag[f * NBINS + j] = expf(__fadd_rn(__fmul_rn(lmv[f][q], 10.05f), -3.76f));
-        }
-    }
-    __syncthreads();
-    // (b) banded mel -> linear for magnitude and phase, then polar -> rectangular
-#pragma unroll 1
-    for (int q = 0; q < 4; ++q) {
-      const int d = tid + INV_THREADS * q;
+    // (b) banded mel -> linear for magnitude and phase, then polar -> rectangular into the frame's tile
+    for (;;) {
+      int idx = 0;
+      if (lane == 0) idx = atomicAdd(ctr, 1);
+      idx = __shfl_sync(0xffffffffu, idx, 0);
+      if (idx >= 32) break;
+      const int d = order[idx] * 32 + lane;
       const int j0 = __ldg(pb_j0 + d);
       int cnt = __ldg(pb_cnt + d);
 #pragma unroll
@@ -341,30 +489,30 @@ waveform_fwd_kernel(const float* __restrict__ logmel, const float* __restrict__ 
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int j = min(j0 + i0 + u, NBINS - 1);
+          const float4* row = reinterpret_cast<const float4*>(melmp + j * MROW);
+          const float4 m0 = row[0], m1 = row[1], p0 = row[2], p1 = row[3];
           const float c = c8[u];
-#pragma unroll
-          for (int f = 0; f < INV_F; ++f) {
-            am[f] = fmaf(mmag[f * NBINS + j], c, am[f]);
-            ap[f] = fmaf(mph[f * NBINS + j], c, ap[f]);
-          }
+          am[0] = fmaf(m0.x, c, am[0]); am[1] = fmaf(m0.y, c, am[1]); am[2] = fmaf(m0.z, c, am[2]); am[3] = fmaf(m0.w, c, am[3]);
+          am[4] = fmaf(m1.x, c, am[4]); am[5] = fmaf(m1.y, c, am[5]); am[6] = fmaf(m1.z, c, am[6]); am[7] = fmaf(m1.w, c, am[7]);
+          ap[0] = fmaf(p0.x, c, ap[0]); ap[1] = fmaf(p0.y, c, ap[1]); ap[2] = fmaf(p0.z, c, ap[2]); ap[3] = fmaf(p0.w, c, ap[3]);
+          ap[4] = fmaf(p1.x, c, ap[4]); ap[5] = fmaf(p1.y, c, ap[5]); ap[6] = fmaf(p1.z, c, ap[6]); ap[7] = fmaf(p1.w, c, ap[7]);
         }
       }
 #pragma unroll
       for (int f = 0; f < INV_F; ++f) {
         float sn, cs;
         sincosf(ap[f], &sn, &cs);
-        xr[f * XLEN + d + 1] = am[f] * cs;
-        xi[f * XLEN + d + 1] = am[f] * sn;
+        tiles[f * WARP_BUF + d + 1] = am[f] * cs;
+        tiles[f * WARP_BUF + XLEN + d + 1] = am[f] * sn;
       }
     }
-    if (tid < INV_F) { xr[tid * XLEN] = 0.0f; xi[tid * XLEN] = 0.0f; }
+    if (tid < INV_F) { tiles[tid * WARP_BUF] = 0.0f; tiles[tid * WARP_BUF + XLEN] = 0.0f; }
     __syncthreads();
-    // (c) one inverse real FFT per warp
-    {
-      const int f = warp;
-      const float* fxr = xr + f * XLEN;
-      const float* fxi = xi + f * XLEN;
-      float* tile = tiles + f * WARP_BUF;
+    if (warp < INV_F) {
+      // (c) one inverse real FFT per warp; the spectrum X (k = 0..1024, two planes) and the output frame share the tile
+      float* tile = tiles + warp * WARP_BUF;
+      const float* fxr = tile;
+      const float* fxi = tile + XLEN;
       float re[32], im[32];
 #pragma unroll
       for (int n1 = 0; n1 < 32; ++n1) {
@@ -383,6 +531,7 @@ waveform_fwd_kernel(const float* __restrict__ logmel, const float* __restrict__ 
         re[n1] = er - oi;
         im[n1] = ei + orr;
       }
+      __syncwarp();  // every lane has read its part of X before the tile is reused for the exchange
       warp_fft1024(im, re, tile, tw1024, lane);  // swapped arguments = inverse transform
       // lane holds z[m], m = lane + 32*k2 : x[2m] = Re/1024, x[2m+1] = Im/1024
       const float sc = 1.0f / 1024.0f;
@@ -395,14 +544,19 @@ waveform_fwd_kernel(const float* __restrict__ logmel, const float* __restrict__ 
         v.y = (im[brev5(k2)] * sc) * sw.y;
         *reinterpret_cast<float2*>(tile + 2 * m) = v;
       }
+      if (tid == 0) *ctr = 0;
+    } else if (g0 + INV_F < T) {
+      stage_a(g0 + INV_F);
     }
     __syncthreads();
     // (d) overlap-add: finished samples [HOP*g0, HOP*(g0+F)), ascending frame order like the reference
     {
+      const float* cin = carry + par * CARRY;
+      float* cout = carry + (par ^ 1) * CARRY;
       const int nf = (T - g0 < INV_F) ? T - g0 : INV_F;
       const int span = HOP * nf;
       for (int s = tid; s < span + CARRY; s += INV_THREADS) {
-        float acc = (s < CARRY) ? carry[s] : 0.0f;
+        float acc = (s < CARRY) ? cin[s] : 0.0f;
         const int fhi = s / HOP;
         int flo = fhi - 3;
         if (flo < 0) flo = 0;
@@ -411,19 +565,18 @@ waveform_fwd_kernel(const float* __restrict__ logmel, const float* __restrict__ 
           const int ng = HOP * g0 + s - padf;
           if (ng >= 0 && ng < wave_len) out[ng] = acc;
         } else {
-          // becomes the next carry; stash in registers-free way: write after the barrier below
-          xr[s - span] = acc;
+          cout[s - span] = acc;
         }
       }
-      __syncthreads();
-      for (int s = tid; s < CARRY; s += INV_THREADS) carry[s] = xr[s];
-      __syncthreads();
-      if (g0 + INV_F >= T) {
-        for (int s = tid; s < CARRY; s += INV_THREADS) {
-          const int ng = HOP * T + s - padf;
-          if (ng >= 0 && ng < wave_len) out[ng] = carry[s];
-        }
-      }
+      par ^= 1;
+    }
+    __syncthreads();
+  }
+  {
+    const float* cin = carry + par * CARRY;
+    for (int s = tid; s < CARRY; s += INV_THREADS) {
+      const int ng = HOP * T + s - padf;
+      if (ng >= 0 && ng < wave_len) out[ng] = cin[s];
     }
   }
 }
@@ -431,15 +584,17 @@ waveform_fwd_kernel(const float* __restrict__ logmel, const float* __restrict__ 
 }  // namespace
 
 extern "C" int gs_spectrogram_fwd(const float* wave, const float* hann, const int* mel_k0, const float* mel_w,
-                                  float* logmel, float* inst, int batch, int wave_len, int time_steps,
-                                  int frames_per_chunk, void* stream) {
+                                  float* logmel, float* inst, float* scratch, int batch, int wave_len, int time_steps,
+                                  int frames_per_run, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   GS_CHECK_ARG(batch >= 0 && wave_len > 0 && time_steps > 0, "spectrogram_fwd: bad shape");
   GS_CHECK_ARG(HOP * (time_steps - 1) + FRAME >= wave_len,
                "spectrogram_fwd: waveform_length %d exceeds the %d samples %d frames cover", wave_len,
                HOP * (time_steps - 1) + FRAME, time_steps);
-  GS_CHECK_ARG(frames_per_chunk > 0 && time_steps % frames_per_chunk == 0,
-               "spectrogram_fwd: frames_per_chunk %d must divide time_steps %d", frames_per_chunk, time_steps);
+  GS_CHECK_ARG(frames_per_run > 0, "spectrogram_fwd: frames_per_run %d must be positive", frames_per_run);
+  const int runs = gs_cdiv(time_steps, frames_per_run);
+  GS_CHECK_ARG(runs == 1 || scratch != nullptr,
+               "spectrogram_fwd: %d runs per clip need a scratch buffer of batch * runs * 1024 floats", runs);
   if (batch == 0) return GS_OK;
   int rc = ensure_tables(st);
   if (rc) return rc;
@@ -448,12 +603,15 @@ extern "C" int gs_spectrogram_fwd(const float* wave, const float* hann, const in
     GS_CUDA(cudaFuncSetAttribute(spectrogram_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
     attr = true;
   }
-  int n_items = batch * (time_steps / frames_per_chunk);
-  int blocks = gs_cdiv(n_items, FWD_WARPS);
-  spectrogram_fwd_kernel<<<blocks, FWD_WARPS * 32, FWD_SMEM, st>>>(wave, wave_len, time_steps, frames_per_chunk, hann,
-                                                                  g_tables.tw1024, g_tables.tw2048, mel_k0, mel_w,
-                                                                  logmel, inst, n_items);
+  spectrogram_fwd_kernel<<<batch * runs, FWD_WARPS * 32, FWD_SMEM, st>>>(wave, wave_len, time_steps, frames_per_run, runs,
+                                                                       hann, g_tables.tw1024, g_tables.tw2048, mel_k0,
+                                                                       mel_w, logmel, inst, scratch);
   GS_CHECK_LAUNCH("spectrogram_fwd");
+  if (runs > 1) {
+    const int rows = batch * (runs - 1);
+    spectrogram_if_fixup_kernel<<<rows, 256, 0, st>>>(inst, scratch, time_steps, frames_per_run, runs, rows);
+    GS_CHECK_LAUNCH("spectrogram_if_fixup");
+  }
   return GS_OK;
 }
 

@@ -327,13 +327,16 @@ class CudaBackend(object):
                   float(beta2), float(eps), int(t), float(grad_scale), _stream())
 
     # ------------------------------------------------------------------ spectral
-    def spectrogram_fwd(self, wave, consts, time_steps, frames_per_chunk):
+    def spectrogram_fwd(self, wave, consts, time_steps, frames_per_run):
         (wave,) = _chk(wave)
         b, wave_len = wave.shape
         logmel = torch.empty((b, time_steps, 1024), device=wave.device, dtype=torch.float32)
         inst = torch.empty_like(logmel)
+        runs = -(-time_steps // frames_per_run)
+        scratch = torch.empty((b, runs, 1024), device=wave.device, dtype=torch.float32) if runs > 1 else None
         _lib.call("gs_spectrogram_fwd", _ptr(wave), _ptr(consts["hann"]), _ptr(consts["mel_k0"]), _ptr(consts["mel_w"]),
-                  _ptr(logmel), _ptr(inst), b, wave_len, time_steps, frames_per_chunk, _stream())
+                  _ptr(logmel), _ptr(inst), _ptr(scratch), b, wave_len, time_steps,
+                  frames_per_run, _stream())
         return logmel, inst
 
     def waveform_fwd(self, logmel, inst, consts, wave_len):

@@ -126,17 +126,13 @@ def _check_config(spectrogram_shape, overlap):
     return time_steps
 
 
-def frames_per_chunk(batch, time_steps):
-    """Frames one warp handles back to back; shorter chunks for small batches so the grid fills."""
-    for cand in (16, 8, 4, 2, 1):
-        if time_steps % cand == 0 and batch * (time_steps // cand) >= 148 * 16:
-            return cand
-    # small batches never fill the GPU: the chunk length only sets the latency of the longest warp
-    # (chunk + 1 recomputed frame), so take the shortest chunk that still fills every SM's 16 warps once
-    for cand in (2, 1):
-        if time_steps % cand == 0 and batch * (time_steps // cand) >= 148 * 4:
-            return cand
-    return 1
+def frames_per_run(batch, time_steps):
+    """Consecutive frames one CTA (16 warps, one frame per warp per round) walks.  Longer runs mean fewer
+    run-boundary rows for the fix-up pass; shorter runs give the 148 SMs more CTAs to balance: 32 when that
+    still leaves >= 4 CTAs per SM (batch 256: 1024 CTAs = 6.9 waves), else one round of 16."""
+    if batch * -(-time_steps // 32) >= 4 * 148:
+        return 32
+    return 16
 
 
 def convert_to_spectrogram(waveforms, waveform_length, sample_rate, spectrogram_shape, overlap):
@@ -146,7 +142,7 @@ def convert_to_spectrogram(waveforms, waveform_length, sample_rate, spectrogram_
         raise ValueError("waveforms have %d samples, waveform_length is %d" % (waveforms.shape[1], waveform_length))
     consts = device_constants(sample_rate, waveforms.device)
     return F.K.spectrogram_fwd(waveforms.detach(), consts, time_steps,
-                               frames_per_chunk(waveforms.shape[0], time_steps))
+                               frames_per_run(waveforms.shape[0], time_steps))
 
 
 def convert_to_waveform(log_mel_magnitude_spectrograms, mel_instantaneous_frequencies, waveform_length, sample_rate,

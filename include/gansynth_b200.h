@@ -122,12 +122,15 @@ int gs_adam_step(float* p, const float* g, float* m, float* v, long long n, floa
 /* ---- spectral front-end, reference configuration frame 2048 / hop 512 / 1024 bins ---------------
  * gs_spectrogram_fwd: spectral_ops.py:45-94.  wave [batch, wave_len] -> logmel, inst [batch, T, 1024].
  *   hann [2048]; mel_k0 int32 [1024] and mel_w [6][1024]: column-sparse linear->mel matrix (first
- *   non-zero row and up to 6 weights per mel bin).  frames_per_chunk divides T.
+ *   non-zero row and up to 6 weights per mel bin).  One CTA walks a run of frames_per_run consecutive
+ *   frames of a clip; scratch: caller-owned [batch, ceil(T / frames_per_run), 1024] floats (run-boundary
+ *   phases; may be NULL when frames_per_run >= T).
  * gs_waveform_fwd: spectral_ops.py:97-149.  logmel, inst -> wave [batch, wave_len].
  *   synth_window [2048] (hann / overlap-added hann^2); pb_j0/pb_cnt int32 [1024], pb_w [band][1024]:
  *   banded pseudo-inverse (first mel row, row count and zero-padded weights per linear bin). */
 int gs_spectrogram_fwd(const float* wave, const float* hann, const int* mel_k0, const float* mel_w, float* logmel,
-                       float* inst, int batch, int wave_len, int time_steps, int frames_per_chunk, void* stream);
+                       float* inst, float* scratch, int batch, int wave_len, int time_steps, int frames_per_run,
+                       void* stream);
 int gs_waveform_fwd(const float* logmel, const float* inst, const float* synth_window, const int* pb_j0,
                     const int* pb_cnt, const float* pb_w, int band, float* wave, int batch, int wave_len,
                     int time_steps, void* stream);

@@ -190,7 +190,7 @@ class EmuBackend(object):
             p.sub_(lr_t * m / (torch.sqrt(v) + eps))
 
     # spectral: same sparse constants as the kernels, dense torch arithmetic
-    def spectrogram_fwd(self, wave, consts, time_steps, frames_per_chunk):
+    def spectrogram_fwd(self, wave, consts, time_steps, frames_per_run):
         b, wave_len = wave.shape
         nsamp = 512 * (time_steps - 1) + 2048
         x = TF.pad(wave, (nsamp - wave_len, 0))
