@@ -58,6 +58,10 @@ SIGNATURES = {
     "gs_tc_probe_time": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "gs_spectrogram_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "gs_waveform_fwd": [_P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _P],
+    "gs_crc32c": [_P, _L, _P],
+    "gs_wav_decode_pcm16": [_P, _L, _P, _I, _P, _P],
+    "gs_wav_read_batch": [_P, _I, _P, _I, _I, _P],
+    "gs_pcm16_to_float": [_P, _P, _L, _P],
 }
 
 _lib = None
@@ -94,6 +98,15 @@ def is_loaded():
 
 
 launch_count = 0
+
+
+def host_call(name, *args):
+    """Calls a HOST-side entry point (input-pipeline natives: no kernel launch is counted)."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise GansynthLibraryError("%s failed (%d): %s" % (name, rc, lib.gs_last_error().decode()))
+    return rc
 
 
 def call(name, *args):

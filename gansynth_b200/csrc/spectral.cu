@@ -157,7 +157,7 @@ int ensure_tables(cudaStream_t st) {
 constexpr int FWD_WARPS = 16;
 constexpr int TILE = 2048;                       // floats per warp
 constexpr int FWD_TABLE_FLOATS = NBINS /*mel k0*/ + MEL_TAPS * NBINS /*mel w*/ + 2048 /*tw1024*/ + 1040 /*tw2048, k<=512*/ +
-                                 FRAME /*hann*/ + 2 * NBINS /*carry*/;
+                                 FRAME /*hann*/ + 2 * NBINS /*carry*/ + 32 /*taps per 32-bin block*/;
 constexpr int FWD_SMEM = (FWD_TABLE_FLOATS + FWD_WARPS * TILE) * 4;
 
 __device__ __forceinline__ float gs_sqrt_approx(float x) {
@@ -181,27 +181,24 @@ __device__ __forceinline__ float gs_wrap_diff(float d) {
   return md * 0.318309886183790672f;
 }
 
-// 1024-point forward DFT over one warp, exchange through two XOR-swizzled 32x32 planes (conflict-free both ways).
-// In: lane holds z[32*n1 + lane] in slot n1.  Out: lane holds Z[lane + 32*k2] in slot brev5(k2).
-__device__ __forceinline__ void warp_fft1024_sw(float (&re)[32], float (&im)[32], float* buf, const float2* tw, int lane) {
+// 1024-point forward DFT over one warp, exchange through one XOR-swizzled 32x32 tile of complex values (64-bit
+// accesses, conflict-free both ways).  In: lane holds z[32*n1 + lane] in slot n1.  Out: lane holds Z[lane + 32*k2] in
+// slot brev5(k2).
+__device__ __forceinline__ void warp_fft1024_sw(float (&re)[32], float (&im)[32], float2* buf, const float2* tw, int lane) {
   fft32(re, im);
-  float* br = buf;
-  float* bi = buf + 1024;
 #pragma unroll
   for (int k1 = 0; k1 < 32; ++k1) {
     const int r = brev5(k1);
     const float2 w = tw[k1 * 32 + lane];
     const float yr = re[r], yi = im[r];
-    const int a = k1 * 32 + (lane ^ k1);
-    br[a] = yr * w.x - yi * w.y;
-    bi[a] = yr * w.y + yi * w.x;
+    buf[k1 * 32 + (lane ^ k1)] = make_float2(yr * w.x - yi * w.y, yr * w.y + yi * w.x);
   }
   __syncwarp();
 #pragma unroll
   for (int n2 = 0; n2 < 32; ++n2) {
-    const int a = lane * 32 + (n2 ^ lane);
-    re[n2] = br[a];
-    im[n2] = bi[a];
+    const float2 v = buf[lane * 32 + (n2 ^ lane)];
+    re[n2] = v.x;
+    im[n2] = v.y;
   }
   __syncwarp();
   fft32(re, im);
@@ -220,7 +217,8 @@ spectrogram_fwd_kernel(const float* __restrict__ wave, int wave_len, int T, int 
   float2* tw2048 = tw1024 + 1024;                                   // [513] (+pad)
   float2* hann2 = reinterpret_cast<float2*>(sm + NBINS + MEL_TAPS * NBINS + 2048 + 1040);  // [1024]
   float* carry = reinterpret_cast<float*>(hann2 + 1024);            // [2][1024]
-  float* tiles = carry + 2 * NBINS;
+  int* ntaps = reinterpret_cast<int*>(carry + 2 * NBINS);           // [32]
+  float* tiles = carry + 2 * NBINS + 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   float* buf = tiles + warp * TILE;
   for (int i = tid; i < 1024; i += FWD_WARPS * 32) {
@@ -229,11 +227,19 @@ spectrogram_fwd_kernel(const float* __restrict__ wave, int wave_len, int T, int 
     const int k0c = min(max(k0, 0), NBINS - MEL_TAPS);
     const int sh = k0 - k0c;
     melk[i] = k0c;
+    int used = 0;
 #pragma unroll
     for (int u = 0; u < MEL_TAPS; ++u) {
       const int src = u - sh;
-      melw[u * NBINS + i] = (src >= 0 && src < MEL_TAPS) ? __ldg(mel_w + src * NBINS + i) : 0.0f;
+      const float wv_ = (src >= 0 && src < MEL_TAPS) ? __ldg(mel_w + src * NBINS + i) : 0.0f;
+      melw[u * NBINS + i] = wv_;
+      if (wv_ != 0.0f) used = u + 1;
     }
+    // the filters are 1 row wide at the bottom of the mel axis and 6 at the top: taps beyond the widest filter of a
+    // 32-bin block (one warp-wide step of the projection) are skipped
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) used = max(used, __shfl_xor_sync(0xffffffffu, used, o));
+    if (lane == 0) ntaps[i >> 5] = used;
     tw1024[i] = tw1024g[i];
     if (i <= 512) tw2048[i] = tw2048g[i];
     hann2[i] = __ldg(reinterpret_cast<const float2*>(hann_g) + i);
@@ -277,7 +283,7 @@ spectrogram_fwd_kernel(const float* __restrict__ wave, int wave_len, int T, int 
           im[n1] = v1 * hw.y;
         }
       }
-      warp_fft1024_sw(re, im, buf, tw1024, lane);
+      warp_fft1024_sw(re, im, zc, tw1024, lane);
 #pragma unroll
       for (int k2 = 0; k2 < 32; ++k2) zc[lane + 32 * k2] = make_float2(re[brev5(k2)], im[brev5(k2)]);
       __syncwarp();
@@ -317,9 +323,11 @@ spectrogram_fwd_kernel(const float* __restrict__ wave, int wave_len, int T, int 
       for (int m = 0; m < 32; ++m) {
         const int j = lane + 32 * m;
         const float2* z = zc + melk[j];
+        const int nt = ntaps[m];
         float mm = 0.0f, ph = 0.0f;
 #pragma unroll
         for (int i = 0; i < MEL_TAPS; ++i) {
+          if (i >= nt) break;
           const float wgt = melw[i * NBINS + j];
           const float2 v = z[i];
           mm = fmaf(v.x, wgt, mm);

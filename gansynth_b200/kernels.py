@@ -339,6 +339,14 @@ class CudaBackend(object):
                   frames_per_run, _stream())
         return logmel, inst
 
+    def pcm16_to_float(self, pcm):
+        """Device half of audio_ops.decode_wav (dataset.py:32-36): int16 -> float32 / 32768."""
+        if not (torch.is_tensor(pcm) and pcm.is_cuda and pcm.dtype == torch.int16 and pcm.is_contiguous()):
+            raise _lib.GansynthLibraryError("pcm16_to_float needs a contiguous CUDA int16 tensor (no CPU path)")
+        out = torch.empty(pcm.shape, device=pcm.device, dtype=torch.float32)
+        _lib.call("gs_pcm16_to_float", _ptr(pcm), _ptr(out), pcm.numel(), _stream())
+        return out
+
     def waveform_fwd(self, logmel, inst, consts, wave_len):
         logmel, inst = _chk(logmel, inst)
         b, time_steps, _ = logmel.shape

@@ -135,6 +135,20 @@ int gs_waveform_fwd(const float* logmel, const float* inst, const float* synth_w
                     const int* pb_cnt, const float* pb_w, int band, float* wave, int batch, int wave_len,
                     int time_steps, void* stream);
 
+/* ---- input pipeline natives, reference dataset.py:12-91 (tf.data.TFRecordDataset, tf.read_file,
+ * audio_ops.decode_wav).  gs_crc32c / gs_wav_decode_pcm16 / gs_wav_read_batch are HOST functions on HOST
+ * pointers; gs_pcm16_to_float is the device half of decode_wav (int16 -> float32 / 32768).
+ * gs_crc32c: CRC-32C (Castagnoli) of n bytes -- the TFRecord framing checksum (before TF's mask rotation).
+ * gs_wav_decode_pcm16: RIFF/WAVE 16-bit PCM bytes -> channel 0, cropped / zero-padded at the end to
+ *   desired_samples int16 (dataset.py:32-36: desired_channels=1, desired_samples=64000).
+ * gs_wav_read_batch: reads and decodes n files on `threads` host threads into dst [n, desired_samples]
+ *   (caller-owned, normally pinned); status [n] (may be NULL) receives 0 or a negative code per file. */
+int gs_crc32c(const void* data, long long n, unsigned int* out);
+int gs_wav_decode_pcm16(const void* file_bytes, long long n, short* dst, int desired_samples, int* sample_rate,
+                        int* samples_in_file);
+int gs_wav_read_batch(const char* const* paths, int n, short* dst, int desired_samples, int threads, int* status);
+int gs_pcm16_to_float(const short* src, float* dst, long long n, void* stream);
+
 /* ---- tcgen05 self-test: one 128 x n bf16 UMMA accumulation from operands staged in the SWIZZLE_NONE
  * core-matrix layout of the tensor-core convolution (see csrc/tc_probe.cu) ------------------------- */
 int gs_tc_probe(const float* a, const float* b, float* d, int k, int n, int rows_a, int rows_b, int shift, int gstride,
