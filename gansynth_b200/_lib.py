@@ -57,7 +57,7 @@ SIGNATURES = {
     "gs_tc_probe": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "gs_tc_probe_time": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "gs_spectrogram_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
-    "gs_waveform_fwd": [_P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _P],
+    "gs_waveform_fwd": [_P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P],
     "gs_crc32c": [_P, _L, _P],
     "gs_wav_decode_pcm16": [_P, _L, _P, _I, _P, _P],
     "gs_wav_read_batch": [_P, _I, _P, _I, _I, _P],

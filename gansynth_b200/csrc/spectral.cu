@@ -404,11 +404,36 @@ constexpr int MROW = 20;            // floats per mel row: 8 mag + 8 phase + 4 p
 constexpr int INV_SMEM_FLOATS = 4096 /*tables*/ + NBINS * MROW + INV_F * WARP_BUF /*X, fft tiles, frames*/ + 2 * CARRY + 64;
 constexpr int INV_SMEM = INV_SMEM_FLOATS * 4;
 
+// Phase prefix of every later segment: prefix[b][seg][j] = sum_{t < seg * seg_frames} inst[b][t][j] * pi, accumulated
+// in frame order with the same two roundings per step as the in-kernel cumsum (tf.cumsum, spectral_ops.py:112).
+__global__ void __launch_bounds__(256)
+waveform_phase_prefix_kernel(const float* __restrict__ inst, int T, int seg_frames, int segs, float* __restrict__ prefix) {
+  const int b = blockIdx.x >> 2;
+  const int j = (blockIdx.x & 3) * 256 + threadIdx.x;
+  const float PI_F = 3.14159274101257324f;
+  const float* col = inst + (size_t)b * T * NBINS + j;
+  float run = 0.0f;
+  const int t_last = min(T, (segs - 1) * seg_frames);
+  for (int t0 = 0; t0 < t_last; t0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = (t0 + u < t_last) ? __ldg(col + (size_t)(t0 + u) * NBINS) : 0.0f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (t0 + u < t_last) {
+        run = __fadd_rn(run, __fmul_rn(v[u], PI_F));
+        if ((t0 + u + 1) % seg_frames == 0) prefix[((size_t)b * segs + (t0 + u + 1) / seg_frames) * NBINS + j] = run;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(INV_THREADS, 1)
 waveform_fwd_kernel(const float* __restrict__ logmel, const float* __restrict__ inst, int T, int wave_len,
                     const float* __restrict__ synwin, const float2* __restrict__ tw1024g,
                     const float2* __restrict__ tw2048g, const int* __restrict__ pb_j0, const int* __restrict__ pb_cnt,
-                    const float* __restrict__ pb_w, int band, float* __restrict__ wave) {
+                    const float* __restrict__ pb_w, int band, float* __restrict__ wave, int seg_frames, int segs,
+                    const float* __restrict__ prefix) {
   extern __shared__ __align__(16) float sm[];
   float2* tw1024 = reinterpret_cast<float2*>(sm);
   float2* tw2048 = tw1024 + 1024;
@@ -418,7 +443,13 @@ waveform_fwd_kernel(const float* __restrict__ logmel, const float* __restrict__ 
   int* order = reinterpret_cast<int*>(carry + 2 * CARRY);  // [32] column blocks, heaviest first
   int* ctr = order + 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.x;
+  // segs > 1 (small batches): the clip is cut into segments of seg_frames frames, one CTA each.  A segment starts
+  // from the phase prefix of the frames before it (waveform_phase_prefix_kernel) and exchanges the 1536-sample
+  // overlap with its neighbours through atomicAdd on the pre-zeroed output (two addends per sample: order-free).
+  const int b = blockIdx.x / segs;
+  const int seg = blockIdx.x % segs;
+  const int t_begin = seg * seg_frames;
+  const int t_end = min(T, t_begin + seg_frames);
   for (int i = tid; i < 1024; i += INV_THREADS) {
     tw1024[i] = tw1024g[i];
     tw2048[i] = tw2048g[i];
@@ -438,6 +469,10 @@ waveform_fwd_kernel(const float* __restrict__ logmel, const float* __restrict__ 
   const float PI_F = 3.14159274101257324f;
   const int padf = HOP * (T - 1) + FRAME - wave_len;
   float run[4] = {0.f, 0.f, 0.f, 0.f};
+  if (seg > 0 && tid >= 256) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) run[q] = __ldg(prefix + ((size_t)b * segs + seg) * NBINS + (tid - 256) + 256 * q);
+  }
   float* out = wave + (size_t)b * wave_len;
 
   // (a) un-normalise, exp, running phase (threads 256..511; column j = u + 256 q)
@@ -450,7 +485,7 @@ waveform_fwd_kernel(const float* __restrict__ logmel, const float* __restrict__ 
 #pragma unroll
       for (int f = 0; f < INV_F; ++f) {
         const size_t o = ((size_t)b * T + g0 + f) * NBINS + j;
-        const bool ok = (g0 + f) < T;
+        const bool ok = (g0 + f) < t_end;
         lmv[f] = ok ? __ldg(logmel + o) : 0.0f;
         ifv[f] = ok ? __ldg(inst + o) : 0.0f;
       }
@@ -469,11 +504,11 @@ waveform_fwd_kernel(const float* __restrict__ logmel, const float* __restrict__ 
     }
   };
 
-  if (warp >= 8) stage_a(0);
+  if (warp >= 8) stage_a(t_begin);
   __syncthreads();
 
   int par = 0;
-  for (int g0 = 0; g0 < T; g0 += INV_F) {
+  for (int g0 = t_begin; g0 < t_end; g0 += INV_F) {
     // (b) banded mel -> linear for magnitude and phase, then polar -> rectangular into the frame's tile
     for (;;) {
       int idx = 0;
@@ -488,18 +523,25 @@ waveform_fwd_kernel(const float* __restrict__ logmel, const float* __restrict__ 
       float am[INV_F], ap[INV_F];
 #pragma unroll
       for (int f = 0; f < INV_F; ++f) { am[f] = 0.0f; ap[f] = 0.0f; }
-      // the band weights come from L2: fetch eight at a time so their latencies overlap (rows >= this lane's own
-      // count hold zeros, the warp-wide maximum `cnt` only bounds the loop)
-      for (int i0 = 0; i0 < cnt; i0 += 8) {
-        float c8[8];
+      // the band weights come from L2: four per step, the next four in flight while these are used (rows >= this
+      // lane's own count hold zeros, the warp-wide maximum `cnt` only bounds the loop)
+      float cn[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) c8[u] = (i0 + u < band) ? __ldg(pb_w + (size_t)(i0 + u) * NBINS + d) : 0.0f;
+      for (int u = 0; u < 4; ++u) cn[u] = (u < band) ? __ldg(pb_w + (size_t)u * NBINS + d) : 0.0f;
+      for (int i0 = 0; i0 < cnt; i0 += 4) {
+        float c4[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 4; ++u) c4[u] = cn[u];
+        if (i0 + 4 < cnt) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) cn[u] = (i0 + 4 + u < band) ? __ldg(pb_w + (size_t)(i0 + 4 + u) * NBINS + d) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
           const int j = min(j0 + i0 + u, NBINS - 1);
           const float4* row = reinterpret_cast<const float4*>(melmp + j * MROW);
           const float4 m0 = row[0], m1 = row[1], p0 = row[2], p1 = row[3];
-          const float c = c8[u];
+          const float c = c4[u];
           am[0] = fmaf(m0.x, c, am[0]); am[1] = fmaf(m0.y, c, am[1]); am[2] = fmaf(m0.z, c, am[2]); am[3] = fmaf(m0.w, c, am[3]);
           am[4] = fmaf(m1.x, c, am[4]); am[5] = fmaf(m1.y, c, am[5]); am[6] = fmaf(m1.z, c, am[6]); am[7] = fmaf(m1.w, c, am[7]);
           ap[0] = fmaf(p0.x, c, ap[0]); ap[1] = fmaf(p0.y, c, ap[1]); ap[2] = fmaf(p0.z, c, ap[2]); ap[3] = fmaf(p0.w, c, ap[3]);
@@ -553,7 +595,7 @@ waveform_fwd_kernel(const float* __restrict__ logmel, const float* __restrict__ 
         *reinterpret_cast<float2*>(tile + 2 * m) = v;
       }
       if (tid == 0) *ctr = 0;
-    } else if (g0 + INV_F < T) {
+    } else if (g0 + INV_F < t_end) {
       stage_a(g0 + INV_F);
     }
     __syncthreads();
@@ -561,19 +603,37 @@ waveform_fwd_kernel(const float* __restrict__ logmel, const float* __restrict__ 
     {
       const float* cin = carry + par * CARRY;
       float* cout = carry + (par ^ 1) * CARRY;
-      const int nf = (T - g0 < INV_F) ? T - g0 : INV_F;
+      const int nf = (t_end - g0 < INV_F) ? t_end - g0 : INV_F;
+      const bool head = (seg > 0) && (g0 == t_begin);   // the first 1536 samples also receive the previous segment's tail
       const int span = HOP * nf;
-      for (int s = tid; s < span + CARRY; s += INV_THREADS) {
-        float acc = (s < CARRY) ? cin[s] : 0.0f;
+      // four consecutive samples per thread: they share the same (up to four) contributing frames
+      const bool vec_out = ((padf & 3) == 0) && ((wave_len & 3) == 0) && ((reinterpret_cast<uintptr_t>(wave) & 15) == 0);
+      for (int s = 4 * tid; s < span + CARRY; s += 4 * INV_THREADS) {
+        float4 acc = (s < CARRY) ? *reinterpret_cast<const float4*>(cin + s) : make_float4(0.f, 0.f, 0.f, 0.f);
         const int fhi = s / HOP;
         int flo = fhi - 3;
         if (flo < 0) flo = 0;
-        for (int f = flo; f <= fhi && f < nf; ++f) acc += tiles[f * WARP_BUF + (s - HOP * f)];
+        for (int f = flo; f <= fhi && f < nf; ++f) {
+          const float4 v = *reinterpret_cast<const float4*>(tiles + f * WARP_BUF + (s - HOP * f));
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
         if (s < span) {
           const int ng = HOP * g0 + s - padf;
-          if (ng >= 0 && ng < wave_len) out[ng] = acc;
+          if (head && s < CARRY) {
+            if (ng >= 0 && ng < wave_len) atomicAdd(out + ng, acc.x);
+            if (ng + 1 >= 0 && ng + 1 < wave_len) atomicAdd(out + ng + 1, acc.y);
+            if (ng + 2 >= 0 && ng + 2 < wave_len) atomicAdd(out + ng + 2, acc.z);
+            if (ng + 3 >= 0 && ng + 3 < wave_len) atomicAdd(out + ng + 3, acc.w);
+          } else if (vec_out && ng >= 0 && ng + 3 < wave_len) {
+            *reinterpret_cast<float4*>(out + ng) = acc;
+          } else {
+            if (ng >= 0 && ng < wave_len) out[ng] = acc.x;
+            if (ng + 1 >= 0 && ng + 1 < wave_len) out[ng + 1] = acc.y;
+            if (ng + 2 >= 0 && ng + 2 < wave_len) out[ng + 2] = acc.z;
+            if (ng + 3 >= 0 && ng + 3 < wave_len) out[ng + 3] = acc.w;
+          }
         } else {
-          cout[s - span] = acc;
+          *reinterpret_cast<float4*>(cout + (s - span)) = acc;
         }
       }
       par ^= 1;
@@ -583,8 +643,11 @@ waveform_fwd_kernel(const float* __restrict__ logmel, const float* __restrict__ 
   {
     const float* cin = carry + par * CARRY;
     for (int s = tid; s < CARRY; s += INV_THREADS) {
-      const int ng = HOP * T + s - padf;
-      if (ng >= 0 && ng < wave_len) out[ng] = cin[s];
+      const int ng = HOP * t_end + s - padf;
+      if (ng >= 0 && ng < wave_len) {
+        if (segs > 1) atomicAdd(out + ng, cin[s]);   // may overlap the next segment's head (or, for a last segment
+        else out[ng] = cin[s];                       // shorter than 3 frames, the previous segment's tail)
+      }
     }
   }
 }
@@ -624,13 +687,19 @@ extern "C" int gs_spectrogram_fwd(const float* wave, const float* hann, const in
 }
 
 extern "C" int gs_waveform_fwd(const float* logmel, const float* inst, const float* synth_window, const int* pb_j0,
-                               const int* pb_cnt, const float* pb_w, int band, float* wave, int batch, int wave_len,
-                               int time_steps, void* stream) {
+                               const int* pb_cnt, const float* pb_w, int band, float* wave, float* scratch, int batch,
+                               int wave_len, int time_steps, int frames_per_segment, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   GS_CHECK_ARG(batch >= 0 && wave_len > 0 && time_steps > 0 && band > 0, "waveform_fwd: bad shape");
   GS_CHECK_ARG(HOP * (time_steps - 1) + FRAME >= wave_len,
                "waveform_fwd: waveform_length %d exceeds the %d samples %d frames cover", wave_len,
                HOP * (time_steps - 1) + FRAME, time_steps);
+  GS_CHECK_ARG(frames_per_segment > 0 && (frames_per_segment >= time_steps || frames_per_segment % INV_F == 0),
+               "waveform_fwd: frames_per_segment %d must be a multiple of %d (or cover all %d frames)", frames_per_segment,
+               INV_F, time_steps);
+  const int segs = gs_cdiv(time_steps, frames_per_segment);
+  GS_CHECK_ARG(segs == 1 || scratch != nullptr,
+               "waveform_fwd: %d segments per clip need a scratch buffer of batch * segments * 1024 floats", segs);
   if (batch == 0) return GS_OK;
   int rc = ensure_tables(st);
   if (rc) return rc;
@@ -639,9 +708,14 @@ extern "C" int gs_waveform_fwd(const float* logmel, const float* inst, const flo
     GS_CUDA(cudaFuncSetAttribute(waveform_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, INV_SMEM));
     attr = true;
   }
-  waveform_fwd_kernel<<<batch, INV_THREADS, INV_SMEM, st>>>(logmel, inst, time_steps, wave_len, synth_window,
-                                                           g_tables.tw1024, g_tables.tw2048, pb_j0, pb_cnt, pb_w, band,
-                                                           wave);
+  if (segs > 1) {
+    GS_CUDA(cudaMemsetAsync(wave, 0, (size_t)batch * wave_len * sizeof(float), st));
+    waveform_phase_prefix_kernel<<<batch * 4, 256, 0, st>>>(inst, time_steps, frames_per_segment, segs, scratch);
+    GS_CHECK_LAUNCH("waveform_phase_prefix");
+  }
+  waveform_fwd_kernel<<<batch * segs, INV_THREADS, INV_SMEM, st>>>(logmel, inst, time_steps, wave_len, synth_window,
+                                                                  g_tables.tw1024, g_tables.tw2048, pb_j0, pb_cnt, pb_w,
+                                                                  band, wave, frames_per_segment, segs, scratch);
   GS_CHECK_LAUNCH("waveform_fwd");
   return GS_OK;
 }

@@ -347,11 +347,15 @@ class CudaBackend(object):
         _lib.call("gs_pcm16_to_float", _ptr(pcm), _ptr(out), pcm.numel(), _stream())
         return out
 
-    def waveform_fwd(self, logmel, inst, consts, wave_len):
+    def waveform_fwd(self, logmel, inst, consts, wave_len, frames_per_segment=None):
         logmel, inst = _chk(logmel, inst)
         b, time_steps, _ = logmel.shape
+        if frames_per_segment is None or frames_per_segment >= time_steps:
+            frames_per_segment = time_steps
+        segs = -(-time_steps // frames_per_segment)
         wave = torch.empty((b, wave_len), device=logmel.device, dtype=torch.float32)
+        scratch = torch.empty((b, segs, 1024), device=logmel.device, dtype=torch.float32) if segs > 1 else None
         _lib.call("gs_waveform_fwd", _ptr(logmel), _ptr(inst), _ptr(consts["synth_window"]), _ptr(consts["pb_j0"]),
-                  _ptr(consts["pb_cnt"]), _ptr(consts["pb_w"]), int(consts["band"]), _ptr(wave), b, wave_len,
-                  time_steps, _stream())
+                  _ptr(consts["pb_cnt"]), _ptr(consts["pb_w"]), int(consts["band"]), _ptr(wave), _ptr(scratch), b,
+                  wave_len, time_steps, frames_per_segment, _stream())
         return wave

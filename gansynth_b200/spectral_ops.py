@@ -135,6 +135,15 @@ def frames_per_run(batch, time_steps):
     return 16
 
 
+def frames_per_segment(batch, time_steps):
+    """Inverse kernel: one CTA per clip when the batch fills the 148 SMs; smaller batches cut every clip into
+    segments of a multiple of 8 frames so that about one CTA per SM exists (batch 8: 16 segments of 8 frames)."""
+    segs = min(max(1, 148 // max(1, batch)), max(1, time_steps // 8))
+    if segs <= 1:
+        return time_steps
+    return 8 * -(-time_steps // (8 * segs))
+
+
 def convert_to_spectrogram(waveforms, waveform_length, sample_rate, spectrogram_shape, overlap):
     """spectral_ops.py:45-94."""
     time_steps = _check_config(spectrogram_shape, overlap)
@@ -153,4 +162,4 @@ def convert_to_waveform(log_mel_magnitude_spectrograms, mel_instantaneous_freque
         raise ValueError("spectrograms must be [B, %d, %d]" % (time_steps, NUM_BINS))
     consts = device_constants(sample_rate, log_mel_magnitude_spectrograms.device)
     return F.K.waveform_fwd(log_mel_magnitude_spectrograms.detach(), mel_instantaneous_frequencies.detach(), consts,
-                            waveform_length)
+                            waveform_length, frames_per_segment(log_mel_magnitude_spectrograms.shape[0], time_steps))

@@ -127,13 +127,16 @@ int gs_adam_step(float* p, const float* g, float* m, float* v, long long n, floa
  *   phases; may be NULL when frames_per_run >= T).
  * gs_waveform_fwd: spectral_ops.py:97-149.  logmel, inst -> wave [batch, wave_len].
  *   synth_window [2048] (hann / overlap-added hann^2); pb_j0/pb_cnt int32 [1024], pb_w [band][1024]:
- *   banded pseudo-inverse (first mel row, row count and zero-padded weights per linear bin). */
+ *   banded pseudo-inverse (first mel row, row count and zero-padded weights per linear bin).
+ *   frames_per_segment >= T: one CTA per clip.  Smaller (a multiple of 8; for batches that do not fill the
+ *   GPU): one CTA per segment, scratch = caller-owned [batch, ceil(T / frames_per_segment), 1024] floats
+ *   (phase prefix per segment). */
 int gs_spectrogram_fwd(const float* wave, const float* hann, const int* mel_k0, const float* mel_w, float* logmel,
                        float* inst, float* scratch, int batch, int wave_len, int time_steps, int frames_per_run,
                        void* stream);
 int gs_waveform_fwd(const float* logmel, const float* inst, const float* synth_window, const int* pb_j0,
-                    const int* pb_cnt, const float* pb_w, int band, float* wave, int batch, int wave_len,
-                    int time_steps, void* stream);
+                    const int* pb_cnt, const float* pb_w, int band, float* wave, float* scratch, int batch,
+                    int wave_len, int time_steps, int frames_per_segment, void* stream);
 
 /* ---- input pipeline natives, reference dataset.py:12-91 (tf.data.TFRecordDataset, tf.read_file,
  * audio_ops.decode_wav).  gs_crc32c / gs_wav_decode_pcm16 / gs_wav_read_batch are HOST functions on HOST

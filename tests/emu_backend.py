@@ -212,7 +212,7 @@ class EmuBackend(object):
         inst = torch.cat([pp[:, :1], md], 1) / pi
         return logmel, inst
 
-    def waveform_fwd(self, logmel, inst, consts, wave_len):
+    def waveform_fwd(self, logmel, inst, consts, wave_len, frames_per_segment=None):
         b, t, _ = logmel.shape
         mm = torch.exp(logmel * 10.05 - 3.76)
         pp = torch.cumsum(inst * torch.tensor(math.pi, dtype=torch.float32), 1)
