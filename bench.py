@@ -202,19 +202,18 @@ def spectral_secondary(device, pk):
     for _ in range(3):
         lm, inst = sp.convert_to_spectrogram(w, **SPECTRAL)
         back = sp.convert_to_waveform(lm, inst, **SPECTRAL)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     reps = 10
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(reps)]
     torch.cuda.synchronize()
-    tf = ti = 0.0
-    for _ in range(reps):
-        ev[0].record()
+    for r in range(reps):          # queued back to back: the host runs ahead, the events bracket device time only
+        ev[r][0].record()
         lm, inst = sp.convert_to_spectrogram(w, **SPECTRAL)
-        ev[1].record()
+        ev[r][1].record()
         back = sp.convert_to_waveform(lm, inst, **SPECTRAL)
-        ev[2].record()
-        torch.cuda.synchronize()
-        tf += ev[0].elapsed_time(ev[1])
-        ti += ev[1].elapsed_time(ev[2])
+        ev[r][2].record()
+    torch.cuda.synchronize()
+    tf = sum(e[0].elapsed_time(e[1]) for e in ev)
+    ti = sum(e[1].elapsed_time(e[2]) for e in ev)
     tf, ti = tf / reps, ti / reps
     nbytes = 256 * 1304576.0
     samp = 256 * 64000.0

@@ -67,6 +67,8 @@ class NSynthPipeline(object):
         if device is None:
             device = "cuda"
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())   # the producer thread pins this device
         self.batch_size = int(batch_size)
         self.num_epochs = num_epochs
         self.shuffle = bool(shuffle)

@@ -390,10 +390,40 @@ class GANSynth(object):
         if rank0:
             self.save_checkpoint(model_dir)
 
-    def evaluate(self, model_dir, config, classifier, input_name, output_names):
-        """models.py:196-230 needs the frozen pitch-classifier graph the reference never ships; the
-        classifier network is outside this hot path."""
-        raise NotImplementedError("evaluate() needs the ResNet pitch classifier, which is outside the hot path")
+    def evaluate(self, model_dir, config, classifier, input_name="images:0", output_names=("features:0", "logits:0")):
+        """models.py:196-230: Frechet distance between classifier features of real and generated images over
+        the whole input.  The reference splices a frozen TF GraphDef (`classifier`) onto `real_images` /
+        `fake_images`; a GraphDef cannot be executed without TensorFlow, so `classifier` is a CALLABLE here:
+        images [B, 2, H, W] (CUDA) -> (features [B, F], logits [B, C]) -- the two `output_names`, in order."""
+        if not callable(classifier):
+            raise NotImplementedError("evaluate() takes the pitch classifier as a callable images -> (features, logits); "
+                                      "a frozen TensorFlow GraphDef cannot be run without TensorFlow")
+        from . import metrics
+        real_feats, fake_feats = [], []
+        restored = False
+        with torch.no_grad():
+            while True:
+                try:
+                    waveforms, labels = self._next_real()
+                except (StopIteration, IndexError):
+                    break
+                latents = self._next_latents()
+                if not restored:
+                    pg = getattr(self.generator, "__self__", None)
+                    if pg is not None and hasattr(pg, "_ensure_variables"):
+                        pg._ensure_variables("generator", latents.shape[1], labels.shape[1])
+                        pg._ensure_variables("discriminator", 0, labels.shape[1])
+                    self.restore_latest(model_dir)
+                    F.K.weight_cache_reset()
+                    restored = True
+                self.real_images = self.real_images_from_waveforms(waveforms)
+                self.fake_images = self.generator(latents, labels)
+                real_feats.append(classifier(self.real_images)[0].detach().float().cpu().numpy())
+                fake_feats.append(classifier(self.fake_images)[0].detach().float().cpu().numpy())
+        if not real_feats:
+            raise ValueError("evaluate(): the input function produced no batch")
+        return dict(frechet_inception_distance=metrics.frechet_inception_distance(np.concatenate(real_feats),
+                                                                                   np.concatenate(fake_feats)))
 
     def generate(self, model_dir, config=None):
         """models.py:232-250: yields float32 numpy [B, waveform_length] until the input function ends."""

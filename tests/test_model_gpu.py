@@ -163,6 +163,24 @@ def test_train_and_generate_entry_points(cuda_store, tmp_path):
     outs = list(model.generate(str(tmp_path)))
     assert len(outs) == 2 and outs[0].shape == (4, 64000) and outs[0].dtype == np.float32
     assert np.isfinite(outs[0]).all()
+    # evaluate (models.py:196-230) with a callable standing in for the frozen pitch-classifier graph
+    from gansynth_b200 import metrics
+    proj = torch.randn(2 * 128, 6, generator=torch.Generator().manual_seed(4)).cuda()
+    seen = {"real": [], "fake": []}
+
+    def classifier(images):
+        feats = images.mean(dim=3).reshape(images.shape[0], -1) @ proj
+        seen["real" if images is model.real_images else "fake"].append(feats.cpu().numpy())
+        return feats, feats[:, :3]
+
+    it3 = iter(batches[:6])
+    model.real_input_fn = lambda: next(it3)
+    out = model.evaluate(str(tmp_path), None, classifier, "images:0", ["features:0", "logits:0"])
+    assert set(out) == {"frechet_inception_distance"} and np.isfinite(out["frechet_inception_distance"])
+    want = metrics.frechet_inception_distance(np.concatenate(seen["real"]), np.concatenate(seen["fake"]))
+    assert len(seen["real"]) == 6 and abs(out["frechet_inception_distance"] - want) <= 1e-9 * max(1.0, abs(want))
+    with pytest.raises(NotImplementedError):
+        model.evaluate(str(tmp_path), None, b"frozen-graph-bytes", "images:0", ["features:0", "logits:0"])
 
 
 def test_cuda_graph_substeps_match_eager(cuda_store):

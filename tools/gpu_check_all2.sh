@@ -1,6 +1,6 @@
 # full GPU validation: tests, smoke, bench, spectral timing + ncu captures, inference sweep, step profile
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -12 > gpurun_out/pytest_gpu.log
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -25 > gpurun_out/pytest_gpu.log
 cat gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2
 timeout 200 python tools/profile_spectral.py 256 2>&1 | tail -1 | tee gpurun_out/spectral_times.log
