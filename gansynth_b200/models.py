@@ -343,6 +343,9 @@ class GANSynth(object):
         paths = sorted(glob.glob(os.path.join(model_dir, "model.ckpt-*.pt")),
                        key=lambda p: int(p.rsplit("-", 1)[1][:-3]))
         if not paths:
+            # a model_dir written by the reference itself: TensorFlow Saver files + `checkpoint` state file
+            if os.path.exists(os.path.join(model_dir, "checkpoint")):
+                return self.import_tf_checkpoint(model_dir, labels, latents)
             return None
         state = torch.load(paths[-1], map_location="cpu")
         if labels is not None:
@@ -355,6 +358,56 @@ class GANSynth(object):
                 self._opt[s]["v"].copy_(o["v"])
                 self._opt[s]["t"] = o["t"]
         return paths[-1]
+
+    def import_tf_checkpoint(self, prefix_or_dir, labels=None, latents=None):
+        """Loads a TensorFlow-1 Saver checkpoint of the reference graph (variables by their TF names, global step,
+        Adam slots when present): `prefix_or_dir` is a checkpoint prefix (`.../model.ckpt-1000`) or a model_dir
+        holding a `checkpoint` state file (tf.train.latest_checkpoint)."""
+        from . import tf_checkpoint as tfc
+        prefix = tfc.latest_checkpoint(prefix_or_dir) if os.path.isdir(prefix_or_dir) else prefix_or_dir
+        if prefix is None:
+            return None
+        hp = self.hyper_params
+        state = tfc.split_training_state(tfc.load_bundle(prefix),
+                                         (hp["generator_beta2"], hp["discriminator_beta2"]))
+        if labels is not None:
+            self._ensure_optimizers(labels, latents)
+        missing = [n for n in self.store.vars if n not in state["variables"]]
+        if missing:
+            raise KeyError("checkpoint %s lacks %d variables, e.g. %s" % (prefix, len(missing), missing[0]))
+        self.store.load({n: state["variables"][n] for n in self.store.vars})
+        if state["global_step"] is not None:
+            self.global_step.value = state["global_step"]
+        if self._opt is not None:
+            for scope, st in state["optimizers"].items():
+                for slot in ("m", "v"):
+                    flat = self._opt[scope][slot]
+                    for n, (o, k) in self.store.offsets[scope].items():
+                        if n in st[slot]:
+                            flat[o:o + k].copy_(torch.as_tensor(st[slot][n]).reshape(-1))
+                if st["t"] is not None:
+                    self._opt[scope]["t"] = st["t"]
+        return prefix
+
+    def export_tf_checkpoint(self, prefix):
+        """Writes the current state as a TensorFlow-1 Saver checkpoint (`<prefix>.index`, `.data-00000-of-00001`,
+        `checkpoint`) under the names the reference graph uses."""
+        from . import tf_checkpoint as tfc
+        hp = self.hyper_params
+        opts = {}
+        if self._opt is not None:
+            for scope, o in self._opt.items():
+                m, v = o["m"].detach().cpu(), o["v"].detach().cpu()
+                shapes = {n: tuple(self.store.vars[n].shape) for n in self.store.offsets[scope]}
+                opts[scope] = dict(m={n: m[a:a + k].reshape(shapes[n]).numpy() for n, (a, k) in self.store.offsets[scope].items()},
+                                   v={n: v[a:a + k].reshape(shapes[n]).numpy() for n, (a, k) in self.store.offsets[scope].items()},
+                                   t=int(o["t"]))
+        tensors = tfc.join_training_state({n: t.numpy() for n, t in self.store.state().items()},
+                                          int(self.global_step.value), opts,
+                                          (hp["generator_beta1"], hp["discriminator_beta1"]),
+                                          (hp["generator_beta2"], hp["discriminator_beta2"]))
+        tfc.save_bundle(prefix, tensors)
+        return prefix
 
     # ------------------------------------------------------------------ reference entry points
     def train(self, model_dir, config=None, total_steps=1000000, save_checkpoint_steps=1000, save_summary_steps=100,

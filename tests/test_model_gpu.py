@@ -181,6 +181,22 @@ def test_train_and_generate_entry_points(cuda_store, tmp_path):
     assert len(seen["real"]) == 6 and abs(out["frechet_inception_distance"] - want) <= 1e-9 * max(1.0, abs(want))
     with pytest.raises(NotImplementedError):
         model.evaluate(str(tmp_path), None, b"frozen-graph-bytes", "images:0", ["features:0", "logits:0"])
+    # TensorFlow-1 Saver files out and back in: variables, global step, Adam slots and step counts
+    prefix = model.export_tf_checkpoint(str(tmp_path / "tf" / ("model.ckpt-%d" % int(gs.value))))
+    before = {n: v.clone() for n, v in model.store.state().items()}
+    slots = {s: (o["m"].clone(), o["v"].clone(), o["t"]) for s, o in model._opt.items()}
+    model.store.load({n: torch.zeros_like(v) for n, v in before.items()})
+    for o in model._opt.values():
+        o["m"].zero_()
+        o["v"].zero_()
+        o["t"] = 0
+    gs.value = 0
+    assert model.import_tf_checkpoint(str(tmp_path / "tf")) == prefix
+    assert int(gs.value) == 2
+    for n, v in model.store.state().items():
+        assert torch.equal(v, before[n]), n
+    for s_, o in model._opt.items():
+        assert torch.equal(o["m"], slots[s_][0]) and torch.equal(o["v"], slots[s_][1]) and o["t"] == slots[s_][2]
 
 
 def test_cuda_graph_substeps_match_eager(cuda_store):
