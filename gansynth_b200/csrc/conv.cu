@@ -2,6 +2,7 @@
 // Replaces the tf.nn.conv2d / tf.nn.conv2d_transpose call sites of the reference
 // (ops.py:237, ops.py:269) and their TF-generated gradients (models.py:47,60,81-89).
 #include <stdlib.h>
+#include <algorithm>
 
 #include "conv1x1.cuh"
 #include "conv_tc.cuh"
@@ -187,6 +188,21 @@ int launch_tc_impl(const float* x, const float* w, const float* bias, float* y, 
   int nt = ndim;
   if (G::NACC * nt > 512) nt = 512 / G::NACC;
   while (nt > 32 && nt % 64 == 0 && (long long)p.ntiles * (ndim / nt) < gs_num_sms()) nt /= 2;
+  if (G::NACC == 1 && !getenv("GS_TC_OLD_NT")) {
+    // Issue-time model (profiles/mma_timing_r1.txt, cycles per 16-channel K slice in cat mode: N=2nt MMA + N=nt MMA;
+    // three N=256 MMAs at nt = 256): time ~ tiles per CTA x cycles per slice.  Halving the channel tile doubles the
+    // CTAs but the thin MMAs are operand-fetch bound, so "split until every SM has a CTA" can overshoot (8x64 images:
+    // 2 tiles x 107 cycles at nt = 32 against 1 x 135 at nt = 64).  Override only for a clear (>= 20 %) gain.
+    auto cost = [](int t) { return t <= 32 ? 107.0 : t <= 64 ? 135.0 : t <= 128 ? 218.0 : 422.0; };
+    auto model = [&](int t) {
+      const int per_tile_ctas = std::max(1, gs_num_sms() / (ndim / t));
+      return cost(t) * (double)((p.ntiles + per_tile_ctas - 1) / per_tile_ctas);
+    };
+    int best = nt;
+    for (int t = 32; t <= ndim && t <= 256; t *= 2)
+      if (ndim % t == 0 && model(t) < 0.8 * model(best)) best = t;
+    nt = best;
+  }
   const size_t budget = 222 * 1024 - 1024 - 2 * 16384 - (FORM == TC_C2 ? 2048 : 0);   // alignment slack, output staging, parity table
   const size_t a_stage = (size_t)p.pix * KC * 4;
   const size_t raw = (((size_t)p.rpix * KC * 4) + 1023) & ~(size_t)1023;
@@ -208,12 +224,25 @@ int launch_tc_impl(const float* x, const float* w, const float* bias, float* y, 
   p.nt = nt;
   p.n_tiles = ndim / nt;
   size_t used = p.sa * a_stage + p.ds * raw;
-  p.b_resident = (nchunks <= TC_MAX_BSTAGES) && (used + (size_t)nchunks * 9 * b_tap <= budget) && !getenv("GS_TC_NO_RESIDENT");
+  // split-K for layers that cannot give every SM a CTA (2- and 4-row 256-channel blocks: 16-64 CTAs, each walking
+  // all 2304 contraction rows): grid.z CTAs take `cps` channel chunks each and add their partial tiles into the
+  // pre-zeroed y with TMA reduce-add; bias rides on z = 0, the activation is a separate in-place pass afterwards
+  p.ksplit = 1;
+  {
+    const long long ctas = (long long)std::min(p.ntiles, std::max(1, gs_num_sms() / p.n_tiles)) * p.n_tiles;
+    if (2 * ctas <= gs_num_sms() && nchunks >= 2 && !getenv("GS_TC_NO_KSPLIT")) {
+      const int want = (int)std::min<long long>(nchunks, gs_num_sms() / ctas);
+      for (int ks = want; ks >= 2; --ks)
+        if (nchunks % ks == 0) { p.ksplit = ks; break; }
+    }
+  }
+  p.cps = nchunks / p.ksplit;
+  p.b_resident = (p.cps <= TC_MAX_BSTAGES) && (used + (size_t)p.cps * 9 * b_tap <= budget) && !getenv("GS_TC_NO_RESIDENT");
   int tps = 1;
   if (p.b_resident) {
     tps = 9;
-    p.sb = nchunks;
-    used += (size_t)nchunks * 9 * b_tap;
+    p.sb = p.cps;
+    used += (size_t)p.cps * 9 * b_tap;
   } else {
     if (used + 2 * 9 * b_tap <= budget) tps = 9;
     else if (used + 2 * 3 * b_tap <= budget) tps = 3;
@@ -297,9 +326,12 @@ int launch_tc_impl(const float* x, const float* w, const float* bias, float* y, 
   int gx = gs_num_sms() / p.n_tiles;
   if (gx < 1) gx = 1;
   if (gx > p.ntiles) gx = p.ntiles;
-  dim3 grid((unsigned)gx, (unsigned)p.n_tiles);
+  dim3 grid((unsigned)gx, (unsigned)p.n_tiles, (unsigned)p.ksplit);
+  const size_t y_count = (size_t)n * h_out * w_out * ndim;
+  if (p.ksplit > 1) GS_CUDA(cudaMemsetAsync(y, 0, y_count * sizeof(float), st));
   kern<<<grid, TC_THREADS, smem, st>>>(tmx, tmy, p);
   GS_CHECK_LAUNCH("conv_tc");
+  if (p.ksplit > 1 && act == 1) return gs_lrelu(y, y, (long long)y_count, st);
   return GS_OK;
 }
 

@@ -91,6 +91,8 @@ struct TcParams {
   int nbuf;                       // accumulator buffers (1 or 2)
   int tmem_cols;                  // power of two >= nbuf * NACC * nt * (1 + cat)
   uint32_t raw_slot_bytes;        // 1024-byte aligned
+  int ksplit, cps;                // split-K: grid.z CTAs per (tile, channel tile), each `cps` channel chunks; partial
+                                  // sums meet in y through TMA reduce-add (y pre-zeroed, activation applied afterwards)
 };
 
 // Output tensor maps: one per accumulator (sub-pixel phase of the transposed form; a strided view of y)
@@ -161,7 +163,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   unsigned char* a_smem = raw_smem + (size_t)p.ds * p.raw_slot_bytes;
   unsigned char* b_smem = a_smem + (size_t)p.sa * a_stage_bytes;
   uint16_t* dst_tab = reinterpret_cast<uint16_t*>(b_smem + (size_t)p.sb * b_stage_bytes);   // TC_C2 only
-  const int nchunks = p.kdim / KC;
+  const int nchunks_all = p.kdim / KC;
+  const int kc_begin = blockIdx.z * p.cps;                     // this CTA's share of the contraction (split-K)
+  const int kc_end = min(nchunks_all, kc_begin + p.cps);
+  const int nchunks = kc_end - kc_begin;
   const int n0 = blockIdx.y * p.nt;       // first output channel of this CTA
 
   if (tid == 0) {
@@ -171,7 +176,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     for (int s = 0; s < 2; ++s) { tc::mbar_init(&acc_full[s], 1); tc::mbar_init(&acc_empty[s], 128); }
     tc::mbar_fence_init();
   }
-  for (int c = tid; c < p.nt; c += TC_THREADS) bias_s[c] = p.bias ? p.bias[blockIdx.y * p.nt + c] : 0.0f;
+  for (int c = tid; c < p.nt; c += TC_THREADS) bias_s[c] = (p.bias && blockIdx.z == 0) ? p.bias[blockIdx.y * p.nt + c] : 0.0f;
   if (FORM == TC_C2) {
     // raw pixel (row hr, image slot, column hc) -> staged position: rows in pairs, columns split by parity
     for (int ps = tid; ps < p.rpix; ps += TC_THREADS) {
@@ -273,7 +278,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         for (int kc = 0; kc < nchunks; ++kc) {
           tc::mbar_wait(&raw_empty[rs], rph ^ 1u);
           tc::mbar_arrive_expect_tx(&raw_full[rs], box_bytes);
-          tc::tma_load_4d(raw_smem + (size_t)rs * p.raw_slot_bytes, &tmx, kc * KC, w0, img0, h0, &raw_full[rs]);
+          tc::tma_load_4d(raw_smem + (size_t)rs * p.raw_slot_bytes, &tmx, (kc_begin + kc) * KC, w0, img0, h0, &raw_full[rs]);
           if (++rs == p.ds) { rs = 0; rph ^= 1u; }
         }
       }
@@ -282,7 +287,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     // ============================== weight blocks: one bulk copy per (chunk, tap group) =================
     if (lane == 0) {
       constexpr int groups = 9 / TPS;
-      const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.wprep) + (size_t)blockIdx.y * nchunks * 9 * b_tap_bytes;
+      const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.wprep) +
+                                  ((size_t)blockIdx.y * nchunks_all + kc_begin) * 9 * b_tap_bytes;
       if (p.b_resident) {
         // one pass fills every stage; both issuing warps read the same copy
         for (int i = 0; i < nchunks * groups; ++i) {
@@ -427,7 +433,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             float4 o;
             o.x = fmaf(v[j + 0], p.alpha, bv.x); o.y = fmaf(v[j + 1], p.alpha, bv.y);
             o.z = fmaf(v[j + 2], p.alpha, bv.z); o.w = fmaf(v[j + 3], p.alpha, bv.w);
-            if (p.act == 1) { o.x = gs_lrelu(o.x); o.y = gs_lrelu(o.y); o.z = gs_lrelu(o.z); o.w = gs_lrelu(o.w); }
+            if (p.act == 1 && p.ksplit == 1) { o.x = gs_lrelu(o.x); o.y = gs_lrelu(o.y); o.z = gs_lrelu(o.z); o.w = gs_lrelu(o.w); }
             *reinterpret_cast<float4*>(row + ((((j >> 2) ^ sw)) << 4)) = o;
           }
           tc::fence_proxy_async();
@@ -436,7 +442,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           if (tid == 0) tc::bulk_wait_read<0>();
           asm volatile("bar.sync 1, 128;" ::: "memory");
           if (tid == 0) {
-            tc::tma_store_4d(&tmy.m[a], out_smem + (size_t)buf * 16384, n0 + c0, tw_ * 8, img0, th_ * p.rows);
+            if (p.ksplit > 1) tc::tma_reduce_add_4d(&tmy.m[a], out_smem + (size_t)buf * 16384, n0 + c0, tw_ * 8, img0, th_ * p.rows);
+            else tc::tma_store_4d(&tmy.m[a], out_smem + (size_t)buf * 16384, n0 + c0, tw_ * 8, img0, th_ * p.rows);
             tc::bulk_commit();
           }
           buf ^= 1;

@@ -65,6 +65,13 @@ __device__ __forceinline__ void tma_store_4d(const void* tmap, const void* src_s
                ::"l"(tmap), "r"(smem_u32(src_smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+// Tiled TMA reduction shared -> global: global[box] += shared tile (fp32 add performed at L2, element type from the
+// tensor map); used by the split-K epilogue.
+__device__ __forceinline__ void tma_reduce_add_4d(const void* tmap, const void* src_smem, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(tmap), "r"(smem_u32(src_smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
