@@ -86,6 +86,7 @@ class NSynthPipeline(object):
         self._queue = queue.Queue(maxsize=max(1, int(prefetch)))
         self._error = None
         self._done = False
+        self._closed = False
         self._thread = threading.Thread(target=self._producer, daemon=True)
         self._thread.start()
 
@@ -155,6 +156,16 @@ class NSynthPipeline(object):
             ready.record(self._stream)
         return wave, lab, (ready, pcm, dev)
 
+    def close(self):
+        """Stops the prefetch thread (it may be parked on a full queue) and ends the iteration."""
+        self._done = True
+        self._closed = True
+        try:
+            while True:
+                self._queue.get_nowait()
+        except queue.Empty:
+            pass
+
     def _producer(self):
         try:
             if self.device.type == "cuda":
@@ -163,7 +174,15 @@ class NSynthPipeline(object):
             for i in self._records:
                 batch.append(i)
                 if len(batch) == self.batch_size:
-                    self._queue.put(self._make_batch(batch))
+                    item = self._make_batch(batch)
+                    while not self._closed:
+                        try:
+                            self._queue.put(item, timeout=0.2)
+                            break
+                        except queue.Full:
+                            continue
+                    if self._closed:
+                        return
                     batch = []
         except BaseException as e:           # surfaced by the consumer
             self._error = e
@@ -206,4 +225,6 @@ def nsynth_input_fn(filenames, batch_size, num_epochs, shuffle, buffer_size=None
 
 def reset_pipelines():
     """Forgets the cached pipelines (a fresh `tf.Graph()` in reference terms)."""
+    for pipe in _PIPELINES.values():
+        pipe.close()
     _PIPELINES.clear()

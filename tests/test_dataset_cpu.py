@@ -152,3 +152,14 @@ def test_main_parser_matches_reference_flags():
     assert (a.model_dir, a.filenames, a.batch_size, a.num_epochs, a.total_steps, a.growing_steps, a.classifier) == \
         ("gan_synth_model", "nsynth*.tfrecord", 8, None, 1000000, 1000000, "pitch_classifier.pb")
     assert not (a.train or a.evaluate or a.generate)
+
+
+def test_pipeline_close_releases_the_prefetch_thread(tmp_path):
+    rec, _ = _make_dataset(tmp_path)
+    pipe = dataset.NSynthPipeline([rec], batch_size=2, num_epochs=None, shuffle=True, device="cpu", waveform_length=64)
+    next(pipe)
+    pipe.close()
+    pipe._thread.join(timeout=5.0)
+    assert not pipe._thread.is_alive()
+    with pytest.raises(StopIteration):
+        next(pipe)

@@ -145,3 +145,20 @@ def test_round_trip_property_full_batch():
     assert int(zero_cols.sum()) == 107
     assert float((lm[..., zero_cols] - (math.log(1e-6) + 3.76) / 10.05).abs().max()) < 1e-6
     assert float(inst[..., zero_cols].abs().max()) == 0.0
+
+
+def test_empty_batch_and_argument_errors():
+    """Edge cases of the C ABI: batch 0 is a no-op, inconsistent framing is refused with a message."""
+    from gansynth_b200 import _lib
+    from gansynth_b200 import functional as F
+    from gansynth_b200 import spectral_ops as sp
+    consts = sp.device_constants(16000, torch.device("cuda"))
+    lm, inst = F.K.spectrogram_fwd(torch.zeros(0, 64000, device="cuda"), consts, 128, 32)
+    assert lm.shape == (0, 128, 1024) and inst.shape == (0, 128, 1024)
+    assert F.K.waveform_fwd(lm, inst, consts, 64000).shape == (0, 64000)
+    with pytest.raises(_lib.GansynthLibraryError):
+        F.K.spectrogram_fwd(torch.zeros(1, 70000, device="cuda"), consts, 128, 32)      # 128 frames cover 67072 samples
+    with pytest.raises(_lib.GansynthLibraryError):
+        F.K.waveform_fwd(torch.zeros(1, 128, 1024, device="cuda"), torch.zeros(1, 128, 1024, device="cuda"), consts, 64000, 12)
+    with pytest.raises(NotImplementedError):
+        sp.convert_to_spectrogram(torch.zeros(1, 64000, device="cuda"), 64000, 16000, [128, 512], 0.75)
