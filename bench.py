@@ -270,6 +270,41 @@ def oracle_iteration_time(batch, iters, threads=None):
     return times
 
 
+def oracle_secondary_times(threads=None):
+    """CPU restatement timed on the host cores for the two secondary workloads: the spectral
+    round trip on a bounded sample of config 3 (two chunks of 8 clips) and pitch-conditional inference at B = 1."""
+    from oracle import networks as onet
+    from oracle import spectral_ops as osp
+    if threads:
+        torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(0)
+    w = 0.1 * torch.randn(8, 64000, generator=g)
+    osp.convert_to_waveform(*osp.convert_to_spectrogram(w, **SPECTRAL), **SPECTRAL)       # warm-up (constants)
+    tf = ti = 0.0
+    for _ in range(2):
+        w = 0.1 * torch.randn(8, 64000, generator=g)
+        t0 = time.perf_counter()
+        mag, inst = osp.convert_to_spectrogram(w, **SPECTRAL)
+        t1 = time.perf_counter()
+        osp.convert_to_waveform(mag, inst, **SPECTRAL)
+        t2 = time.perf_counter()
+        tf, ti = tf + (t1 - t0), ti + (t2 - t1)
+    samp = 16 * 64000.0
+    pg = onet.PGGAN(growing_level=1.0, **FULL)
+    params = pg.init_variables(seed=3)
+    lab = torch.nn.functional.one_hot(torch.arange(1) % 61, 61).float()
+    z = torch.randn(1, 256, generator=g)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        img = pg.generator(params, z, lab)
+        osp.convert_to_waveform(img[:, 0], img[:, 1], **SPECTRAL)
+        t_inf = time.perf_counter() - t0
+    return dict(kind="port", cores=threads or torch.get_num_threads(),
+                sample="spectral: 2 chunks of 8 clips of the batch-256 workload; inference: one clip (B = 1)",
+                fwd_gsamp_s=samp / tf / 1e9, inv_gsamp_s=samp / ti / 1e9, roundtrip_gsamp_s=samp / (tf + ti) / 1e9,
+                inference_clips_per_s=1.0 / t_inf)
+
+
 def bench_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -397,6 +432,8 @@ def bench_ours(args):
     if world == 1 and not args.no_spectral:
         line["secondary"] = spectral_secondary(device, pk)
         line["secondary"]["inference"] = inference_secondary(model, device)
+        if rank == 0 and not args.no_cpu_baseline:
+            line["secondary"]["cpu_baseline"] = oracle_secondary_times(os.cpu_count())
     print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
