@@ -42,7 +42,7 @@ import tempfile  # noqa: E402
 
 path = os.path.join(tempfile.gettempdir(), "gs_step_trace.json")
 prof.export_chrome_trace(path)
-detail = collections.defaultdict(lambda: [0, 0.0])
+detail = collections.defaultdict(lambda: [0, 0.0, []])
 for ev in json.load(open(path)).get("traceEvents", []):
     args = ev.get("args") or {}
     if ev.get("cat") != "kernel" or "grid" not in args or "conv_" not in ev.get("name", ""):
@@ -51,6 +51,8 @@ for ev in json.load(open(path)).get("traceEvents", []):
     key = (name, tuple(args["grid"]))
     detail[key][0] += 1
     detail[key][1] += ev.get("dur", 0.0)
-print("\nconvolution kernels by grid (us per launch, launches per step, us per step):")
+    detail[key][2].append(ev.get("dur", 0.0))
+print("\nconvolution kernels by grid (us per launch: mean [min .. max], launches per step, us per step):")
 for (name, grid), v in sorted(detail.items(), key=lambda kv: -kv[1][1])[:60]:
-    print("%8.1f  n=%3d  %8.1f  %-40s grid %s" % (v[1] / v[0], v[0] // steps, v[1] / steps, name, "x".join(str(g) for g in grid)))
+    print("%8.1f [%6.1f .. %6.1f]  n=%3d  %8.1f  %-40s grid %s" % (v[1] / v[0], min(v[2]), max(v[2]), v[0] // steps, v[1] / steps,
+                                                            name, "x".join(str(g) for g in grid)))
