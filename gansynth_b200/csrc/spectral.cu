@@ -664,9 +664,9 @@ extern "C" int gs_spectrogram_fwd(const float* wave, const float* hann, const in
                HOP * (time_steps - 1) + FRAME, time_steps);
   GS_CHECK_ARG(frames_per_run > 0, "spectrogram_fwd: frames_per_run %d must be positive", frames_per_run);
   const int runs = gs_cdiv(time_steps, frames_per_run);
+  if (batch == 0) return GS_OK;
   GS_CHECK_ARG(runs == 1 || scratch != nullptr,
                "spectrogram_fwd: %d runs per clip need a scratch buffer of batch * runs * 1024 floats", runs);
-  if (batch == 0) return GS_OK;
   int rc = ensure_tables(st);
   if (rc) return rc;
   static bool attr = false;
@@ -698,9 +698,9 @@ extern "C" int gs_waveform_fwd(const float* logmel, const float* inst, const flo
                "waveform_fwd: frames_per_segment %d must be a multiple of %d (or cover all %d frames)", frames_per_segment,
                INV_F, time_steps);
   const int segs = gs_cdiv(time_steps, frames_per_segment);
+  if (batch == 0) return GS_OK;
   GS_CHECK_ARG(segs == 1 || scratch != nullptr,
                "waveform_fwd: %d segments per clip need a scratch buffer of batch * segments * 1024 floats", segs);
-  if (batch == 0) return GS_OK;
   int rc = ensure_tables(st);
   if (rc) return rc;
   static bool attr = false;
