@@ -258,3 +258,34 @@ def test_cuda_graph_substeps_match_eager(cuda_store):
         for got, want in ((gd, gd_e), (gg, gg_e)):
             cos = float(torch.dot(got.double(), want.double()) / (got.double().norm() * want.double().norm()))
             assert cos > 0.999 and abs(float(got.norm() / want.norm()) - 1.0) < 2e-2, cos
+
+
+def test_generate_batch_graph_replay_matches_eager(cuda_store):
+    """Inference replayed as a CUDA graph (third call on) against the eager chain, including after the weights
+    changed in place (the weight split is part of the graph)."""
+    import gansynth_b200.models as pmodels
+    import gansynth_b200.networks as pnet
+    ppg = pnet.PGGAN(growing_level=1.0, **FULL)
+    model = pmodels.GANSynth(ppg.generator, ppg.discriminator, None, None, SPECTRAL, HYPER)
+    g = torch.Generator().manual_seed(9)
+    lab = torch.nn.functional.one_hot(torch.arange(2) % 61, 61).float().cuda()
+    z = torch.randn(2, 256, generator=g).cuda()
+    model.use_cuda_graphs = False
+    want = model.generate_batch(lab, z)
+    model.use_cuda_graphs = True
+    outs = [model.generate_batch(lab, z) for _ in range(4)]
+    assert any("graph" in e for k, e in model._graphs.items() if k[0] == "generate")
+    peak = float(want.abs().max())
+    for o in outs:
+        assert o.shape == (2, 64000) and float((o - want).abs().max()) <= 1e-4 * peak
+    assert outs[2].data_ptr() != outs[3].data_ptr()                       # copies, not the graph's buffer
+    z2 = torch.randn(2, 256, generator=g).cuda()
+    with torch.no_grad():
+        for n, v in cuda_store.vars.items():
+            if n.endswith("dense/weight") and n.startswith("generator/"):
+                v.mul_(0.5)
+    got = model.generate_batch(lab, z2)                                   # replay with new inputs and new weights
+    model.use_cuda_graphs = False
+    want2 = model.generate_batch(lab, z2)
+    assert float((got - want2).abs().max()) <= 1e-4 * float(want2.abs().max())
+    assert float((want2 - want).abs().max()) > 1e-3 * peak
