@@ -262,30 +262,39 @@ def test_cuda_graph_substeps_match_eager(cuda_store):
 
 def test_generate_batch_graph_replay_matches_eager(cuda_store):
     """Inference replayed as a CUDA graph (third call on) against the eager chain, including after the weights
-    changed in place (the weight split is part of the graph)."""
+    changed in place (the weight split is part of the graph).  The generated IMAGES are compared with the eager
+    run (1e-4 on the tanh range: the split-K reduction order differs run to run); the waveform is compared with
+    the eager inverse transform OF THE SAME IMAGES, because the phase cumsum + sin/cos of the inverse amplify
+    1e-7 image differences far beyond any fixed waveform tolerance."""
     import gansynth_b200.models as pmodels
     import gansynth_b200.networks as pnet
+    from gansynth_b200 import spectral_ops as sp
     ppg = pnet.PGGAN(growing_level=1.0, **FULL)
     model = pmodels.GANSynth(ppg.generator, ppg.discriminator, None, None, SPECTRAL, HYPER)
     g = torch.Generator().manual_seed(9)
     lab = torch.nn.functional.one_hot(torch.arange(2) % 61, 61).float().cuda()
+
+    def check(z):
+        model.use_cuda_graphs = False
+        model.generate_batch(lab, z)
+        want_img = model.fake_images.clone()
+        model.use_cuda_graphs = True
+        got = model.generate_batch(lab, z)
+        img = model.fake_images.clone()
+        assert got.shape == (2, 64000) and bool(torch.isfinite(got).all())
+        assert float((img - want_img).abs().max()) <= 1e-4
+        wave = sp.convert_to_waveform(img[:, 0].contiguous(), img[:, 1].contiguous(), **SPECTRAL)
+        assert float((got - wave).abs().max()) <= 1e-6 * float(wave.abs().max())
+        return got, img
+
     z = torch.randn(2, 256, generator=g).cuda()
-    model.use_cuda_graphs = False
-    want = model.generate_batch(lab, z)
-    model.use_cuda_graphs = True
-    outs = [model.generate_batch(lab, z) for _ in range(4)]
+    outs = [check(z) for _ in range(4)]
     assert any("graph" in e for k, e in model._graphs.items() if k[0] == "generate")
-    peak = float(want.abs().max())
-    for o in outs:
-        assert o.shape == (2, 64000) and float((o - want).abs().max()) <= 1e-4 * peak
-    assert outs[2].data_ptr() != outs[3].data_ptr()                       # copies, not the graph's buffer
-    z2 = torch.randn(2, 256, generator=g).cuda()
+    assert outs[2][0].data_ptr() != outs[3][0].data_ptr()                 # copies, not the graph's buffer
     with torch.no_grad():
         for n, v in cuda_store.vars.items():
             if n.endswith("dense/weight") and n.startswith("generator/"):
                 v.mul_(0.5)
-    got = model.generate_batch(lab, z2)                                   # replay with new inputs and new weights
-    model.use_cuda_graphs = False
-    want2 = model.generate_batch(lab, z2)
-    assert float((got - want2).abs().max()) <= 1e-4 * float(want2.abs().max())
-    assert float((want2 - want).abs().max()) > 1e-3 * peak
+    z2 = torch.randn(2, 256, generator=g).cuda()
+    _, img2 = check(z2)                                                   # replay with new inputs and new weights
+    assert float((img2 - outs[3][1]).abs().max()) > 1e-3
