@@ -499,18 +499,18 @@ class GANSynth(object):
     def _generate_body(self, labels, latents):
         F.K.weight_cache_reset()       # the caller may have changed the parameters since the last call
         fake_images = self.generator(latents, labels)
-        self.fake_images = fake_images
         mag, inst = fake_images[:, 0].contiguous(), fake_images[:, 1].contiguous()
-        return spectral_ops.convert_to_waveform(mag, inst, **self.spectral_params)
+        return spectral_ops.convert_to_waveform(mag, inst, **self.spectral_params), fake_images
 
     @torch.no_grad()
     def generate_batch(self, labels, latents):
         """z + pitch -> images -> waveforms (models.py:25, 30-31).  Once the generator is fully grown the whole
         chain (weight split, ~60 kernels, inverse spectral transform) is replayed as one CUDA graph per batch size
         from the third call on: at small batches the host needs longer to enqueue it than the device to run it."""
-        out = self._run_body("generate", self._generate_body, (labels, latents))
+        waveforms, images = self._run_body("generate", self._generate_body, (labels, latents))
         # a replayed graph re-splits the weights into cache slots the host-side table no longer describes, and its
-        # output buffer belongs to the graph: invalidate the table, hand out a copy
+        # output buffers belong to the graph: invalidate the table, hand out copies
         F.K.weight_cache_reset()
-        self.fake_waveforms = out.clone()
+        self.fake_images = images.clone()
+        self.fake_waveforms = waveforms.clone()
         return self.fake_waveforms
