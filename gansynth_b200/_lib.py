@@ -38,6 +38,7 @@ SIGNATURES = {
     "gs_col_sum": [_P, _P, _L, _I, _P],
     "gs_lrelu_mask_mul_colsum": [_P, _P, _P, _P, _L, _I, _P],
     "gs_axpby": [_P, _P, _P, _F, _F, _L, _P],
+    "gs_axpby_dev": [_P, _P, _P, _P, _I, _I, _L, _P],
     "gs_mul": [_P, _P, _P, _F, _L, _P],
     "gs_pixel_norm_fwd": [_P, _P, _P, _L, _I, _F, _P],
     "gs_pixel_norm_bwd": [_P, _P, _P, _P, _L, _I, _P],

@@ -72,6 +72,13 @@ __global__ void axpby_kernel(const float* __restrict__ a, const float* __restric
                              float beta, size_t n) {
   GS_GRID_STRIDE(i, n) o[i] = b ? fmaf(alpha, a[i], beta * b[i]) : alpha * a[i];
 }
+// o = coef[ia] * a + coef[ib] * b with the coefficients in DEVICE memory (b may be null: o = coef[ia] * a).  The
+// progressive-growing blend weight changes every step; read from memory it can live outside a replayed CUDA graph.
+__global__ void axpby_dev_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o,
+                                 const float* __restrict__ coef, int ia, int ib, size_t n) {
+  const float alpha = __ldg(coef + ia), beta = __ldg(coef + ib);
+  GS_GRID_STRIDE(i, n) o[i] = b ? fmaf(alpha, a[i], beta * b[i]) : alpha * a[i];
+}
 __global__ void mul_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, float alpha, size_t n) {
   GS_GRID_STRIDE(i, n) o[i] = alpha * a[i] * b[i];
 }
@@ -384,6 +391,14 @@ extern "C" int gs_axpby(const float* a, const float* b, float* out, float alpha,
   if (n <= 0) return GS_OK;
   axpby_kernel<<<ew_grid(n), EW_BLOCK, 0, ST>>>(a, b, out, alpha, beta, n);
   GS_CHECK_LAUNCH("axpby");
+  return GS_OK;
+}
+extern "C" int gs_axpby_dev(const float* a, const float* b, float* out, const float* coef, int ia, int ib, long long n,
+                            void* stream) {
+  GS_CHECK_ARG(coef != nullptr && ia >= 0 && ib >= 0, "axpby_dev: bad coefficients");
+  if (n <= 0) return GS_OK;
+  axpby_dev_kernel<<<ew_grid(n), EW_BLOCK, 0, ST>>>(a, b, out, coef, ia, ib, n);
+  GS_CHECK_LAUNCH("axpby_dev");
   return GS_OK;
 }
 extern "C" int gs_mul(const float* a, const float* b, float* out, float alpha, long long n, void* stream) {

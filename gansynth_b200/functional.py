@@ -293,6 +293,31 @@ class Axpby(Function):
         return Scale.apply(g, alpha), Scale.apply(g, beta), None, None
 
 
+class AxpbyDev(Function):
+    """coef[0] * a + coef[1] * b with `coef` a DEVICE tensor [2]: the progressive-growing blend (networks.py:10-11,
+    126-152) inside a replayed CUDA graph, where the weight depends on global_step and cannot be a launch argument."""
+
+    @staticmethod
+    def forward(ctx, a, b, coef):
+        ctx.coef = coef
+        return K.axpby_dev(a, b, coef, 0, 1)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ScaleDev.apply(g, ctx.coef, 0), ScaleDev.apply(g, ctx.coef, 1), None
+
+
+class ScaleDev(Function):
+    @staticmethod
+    def forward(ctx, a, coef, idx):
+        ctx.coef, ctx.idx = coef, idx
+        return K.axpby_dev(a, None, coef, idx, idx)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ScaleDev.apply(g, ctx.coef, ctx.idx), None, None
+
+
 class Scale(Function):
     @staticmethod
     def forward(ctx, a, s):

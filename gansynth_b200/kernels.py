@@ -181,6 +181,12 @@ class CudaBackend(object):
         _lib.call("gs_axpby", _ptr(a), _ptr(b), _ptr(out), float(alpha), float(beta), a.numel(), _stream())
         return out
 
+    def axpby_dev(self, a, b, coef, ia, ib):
+        a, b, coef = _chk(a, b, coef)
+        out = torch.empty_like(a)
+        _lib.call("gs_axpby_dev", _ptr(a), _ptr(b), _ptr(out), _ptr(coef), int(ia), int(ib), a.numel(), _stream())
+        return out
+
     def bias_act(self, x, bias, act):
         x, bias = _chk(x, bias)
         c = x.shape[-1]

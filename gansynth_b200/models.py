@@ -233,14 +233,24 @@ class GANSynth(object):
         self._backward("generator", loss)
         return loss.detach()
 
-    def _static_structure(self):
-        """True when the kernel sequence of a sub-step does not depend on global_step: both networks fully
-        grown (no lerp weights that change every step), so the sub-step can be replayed as a CUDA graph."""
+    def _pggans(self):
+        """The PGGAN object(s) the two network callables are bound to ([] for foreign callables)."""
+        owners = []
         for fn in (self.generator, self.discriminator):
             pg = getattr(fn, "__self__", None)
-            if pg is None or not hasattr(pg, "growing_depth") or not pg.growing_depth > pg.max_depth:
-                return False
-        return True
+            if pg is None or not hasattr(pg, "structure_key"):
+                return []
+            if not any(pg is o for o in owners):
+                owners.append(pg)
+        return owners
+
+    def _structure_key(self):
+        """Key of the kernel sequence of a sub-step, or None when it cannot be known (foreign networks): fully
+        grown, or the integer depth at which the progressive-growing blend happens.  Within one key only the blend
+        weight changes with global_step, and that lives in device memory (PGGAN.lerp_coef), so the sub-step can be
+        replayed as a CUDA graph."""
+        owners = self._pggans()
+        return tuple(pg.structure_key() for pg in owners) if owners else None
 
     def _run_body(self, scope, body, inputs):
         """Runs `body(*inputs)` on the model's own stream: eagerly the first two times (lazy variable creation,
@@ -256,16 +266,25 @@ class GANSynth(object):
         if outer == self._stream or torch.cuda.is_current_stream_capturing():
             return body(*inputs)
         self._stream.wait_stream(outer)
+        owners = self._pggans()
         with torch.cuda.stream(self._stream):
-            loss = self._run_body_on_stream(scope, body, inputs)
+            for pg in owners:
+                pg.update_lerp_coef(inputs[0].device)       # this step's blend weight, outside any graph
+                pg.device_lerp_active = True
+            try:
+                loss = self._run_body_on_stream(scope, body, inputs)
+            finally:
+                for pg in owners:
+                    pg.device_lerp_active = False
         outer.wait_stream(self._stream)
         return loss
 
     def _run_body_on_stream(self, scope, body, inputs):
         from . import _lib
-        if not (self.use_cuda_graphs and self._static_structure()):
+        structure = self._structure_key()
+        if not self.use_cuda_graphs or structure is None:
             return body(*inputs)
-        key = (scope,) + tuple(tuple(t.shape) for t in inputs)
+        key = (scope, structure) + tuple(tuple(t.shape) for t in inputs)
         entry = self._graphs.setdefault(key, dict(calls=0))
         entry["calls"] += 1
         if entry["calls"] <= 2:

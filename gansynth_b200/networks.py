@@ -45,6 +45,30 @@ class PGGAN(object):
         self.min_depth = log2(self.min_resolution // self.min_resolution)
         self.max_depth = log2(self.max_resolution // self.min_resolution)
         self._built = set()
+        # progressive-growing blend weights (t, 1 - t) in device memory, maintained by GANSynth while it runs a
+        # sub-step (so that the sub-step can be a replayed CUDA graph); None / inactive: lerp takes host floats
+        self.lerp_coef = None
+        self.device_lerp_active = False
+
+    def structure_key(self):
+        """What the kernel sequence of a forward pass depends on: the depth at which the blend happens
+        (networks.py:126-152, 261-287: `growing_depth > depth` picks the branch, the fraction only scales)."""
+        gd = self.growing_depth
+        return ("grown",) if gd > self.max_depth else ("grow", int(math.ceil(gd)))
+
+    def update_lerp_coef(self, device):
+        """Writes lerp's (t, 1 - t) = (depth - growing_depth, 1 - t) for the current global step to `lerp_coef`."""
+        gd = self.growing_depth
+        t = float(math.ceil(gd) - gd) if 0.0 < gd <= self.max_depth else 0.0
+        if self.lerp_coef is None or self.lerp_coef.device != torch.device(device):
+            self.lerp_coef = torch.zeros(2, device=device, dtype=torch.float32)
+        # pageable source: the driver stages it before returning, so the host value cannot be overwritten in flight
+        self.lerp_coef.copy_(torch.tensor([t, 1.0 - t], dtype=torch.float32), non_blocking=True)
+
+    def _lerp(self, a, b, t):
+        if self.device_lerp_active and self.lerp_coef is not None:
+            return F.AxpbyDev.apply(a, b, self.lerp_coef)
+        return lerp(a, b, t)
 
     @property
     def growing_depth(self):
@@ -169,10 +193,10 @@ class PGGAN(object):
             if depth == self.max_depth:
                 if grown:
                     return middle_resolution_images()
-                return lerp(low_resolution_images(), middle_resolution_images(), depth - growing_depth)
+                return self._lerp(low_resolution_images(), middle_resolution_images(), depth - growing_depth)
             if grown:
                 return high_resolution_images()
-            return lerp(low_resolution_images(), middle_resolution_images(), depth - growing_depth)
+            return self._lerp(low_resolution_images(), middle_resolution_images(), depth - growing_depth)
 
         with variable_scope(name):
             embedded = embedding(labels, units=latents.shape[1], variance_scale=1.0, scale_weight=True)
@@ -247,10 +271,10 @@ class PGGAN(object):
             if depth == self.max_depth:
                 if grown:
                     return middle_resolution_feature_maps()
-                return lerp(low_resolution_feature_maps(), middle_resolution_feature_maps(), depth - growing_depth)
+                return self._lerp(low_resolution_feature_maps(), middle_resolution_feature_maps(), depth - growing_depth)
             if grown:
                 return high_resolution_feature_maps()
-            return lerp(low_resolution_feature_maps(), middle_resolution_feature_maps(), depth - growing_depth)
+            return self._lerp(low_resolution_feature_maps(), middle_resolution_feature_maps(), depth - growing_depth)
 
         with variable_scope(name):
             return grow(self.min_depth)

@@ -83,6 +83,10 @@ int gs_lrelu_mask_mul_colsum(const float* v, const float* y, float* out, float* 
 
 /* ---- lerp networks.py:10-11 and generic linear combinations ------------------------------------- */
 int gs_axpby(const float* a, const float* b, float* out, float alpha, float beta, long long n, void* stream);
+/* lerp (networks.py:10-11) with the blend weights in DEVICE memory: out = coef[ia] * a + coef[ib] * b (b may be NULL).
+   Lets the progressive-growing sub-steps be replayed as CUDA graphs while the weight follows global_step. */
+int gs_axpby_dev(const float* a, const float* b, float* out, const float* coef, int ia, int ib, long long n,
+                 void* stream);
 int gs_mul(const float* a, const float* b, float* out, float alpha, long long n, void* stream);
 
 /* ---- pixel_normalization ops.py:330-333 over the channel axis of [rows, c] ----------------------- */

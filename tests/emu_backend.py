@@ -99,6 +99,9 @@ class EmuBackend(object):
     def axpby(self, a, b, alpha, beta):
         return alpha * a if b is None else alpha * a + beta * b
 
+    def axpby_dev(self, a, b, coef, ia, ib):
+        return coef[ia] * a if b is None else coef[ia] * a + coef[ib] * b
+
     def bias_act(self, x, bias, act):
         return _act(x if bias is None else x + bias, act)
 

@@ -298,3 +298,80 @@ def test_generate_batch_graph_replay_matches_eager(cuda_store):
     z2 = torch.randn(2, 256, generator=g).cuda()
     _, img2 = check(z2)                                                   # replay with new inputs and new weights
     assert float((img2 - outs[3][1]).abs().max()) > 1e-3
+
+
+def test_growth_phase_substeps_replay_as_graphs(cuda_store):
+    """Progressive growing (growing_depth <= max_depth): one graph per blend depth, the blend weight in device memory.
+    Three consecutive iterations with a different weight each, every one against the same iteration run eagerly from
+    the same state; the step crosses no depth boundary (global steps 4..6 of 64: growing_depth 0.52 .. 0.73)."""
+    import gansynth_b200.functional as F
+    import gansynth_b200.models as pmodels
+    g = torch.Generator().manual_seed(6)
+    batches = [(0.5 * torch.randn(4, 512, generator=g),
+                torch.nn.functional.one_hot(torch.randint(0, 61, (4,), generator=g), 61).float(),
+                torch.randn(4, 256, generator=g), torch.randn(4, 256, generator=g)) for _ in range(6)]
+    # the device-coefficient blend is the host-coefficient blend, forward and both gradients, bit for bit
+    a = torch.randn(3, 5, 7, generator=g).cuda().requires_grad_()
+    b = torch.randn(3, 5, 7, generator=g).cuda().requires_grad_()
+    coef = torch.tensor([0.3, 0.7], device="cuda")
+    y_dev, y_host = F.AxpbyDev.apply(a, b, coef), F.Axpby.apply(a, b, float(coef[0]), float(coef[1]))
+    assert torch.equal(y_dev, y_host)
+    up = torch.randn(3, 5, 7, generator=g).cuda()
+    for yy in (y_dev, y_host):
+        ga, gb = torch.autograd.grad(yy, (a, b), up, retain_graph=True)
+        assert torch.equal(ga, float(coef[0]) * up) and torch.equal(gb, float(coef[1]) * up)
+    prev = F.K.impl
+    F.K.impl = 4
+    try:
+        store = cuda_store
+        gs = pmodels.get_or_create_global_step()
+        _, params, ppg = _pair(SMALL, gs / 64, store)
+        model = pmodels.GANSynth(ppg.generator, ppg.discriminator, None, None, {}, HYPER)
+        model.real_images_from_waveforms = lambda w: w.reshape(4, 2, 16, 16)
+
+        def iteration(batch):
+            w, lab, z1, z2 = (t.cuda() for t in batch)
+            d = float(model.discriminator_step(w, lab, z1))
+            gl = float(model.generator_step(lab, z2))
+            return d, gl, model._opt["generator"]["grad"].clone()
+
+        def snapshot():
+            return dict(vars={n: v.detach().clone() for n, v in store.vars.items()},
+                        opt={s: (o["m"].clone(), o["v"].clone(), o["t"]) for s, o in model._opt.items()},
+                        step=model.global_step.value)
+
+        def restore(snap):
+            with torch.no_grad():
+                for n, v in store.vars.items():
+                    v.copy_(snap["vars"][n])
+            for s, o in model._opt.items():
+                o["m"].copy_(snap["opt"][s][0]); o["v"].copy_(snap["opt"][s][1]); o["t"] = snap["opt"][s][2]
+            model.global_step.value = snap["step"]
+
+        gs.value = 2
+        model.use_cuda_graphs = True
+        for b in batches[:2]:
+            iteration(b)                     # global steps 2 and 3: eager calls 1 and 2 of the depth-1 structure
+        assert ppg.structure_key() == ("grow", 1) and int(gs.value) == 4
+        results = []
+        for b in batches[2:5]:
+            snap = snapshot()
+            model.use_cuda_graphs = False
+            want = iteration(b)
+            restore(snap)
+            model.use_cuda_graphs = True
+            got = iteration(b)               # capture on the first pass through here, pure replays afterwards
+            results.append((got, want))
+        keys = [k for k in model._graphs if "graph" in model._graphs[k]]
+        assert len(keys) == 2 and all(k[1] == (("grow", 1),) for k in keys), keys
+        coefs = ppg.lerp_coef.cpu()
+        assert abs(float(coefs.sum()) - 1.0) < 1e-6 and 0.0 < float(coefs[0]) < 1.0
+    finally:
+        F.K.impl = prev
+    for (d, gl, gg), (d_e, g_e, gg_e) in results:
+        assert abs(d - d_e) < 1e-5 * max(1.0, abs(d_e)), (d, d_e)
+        assert abs(gl - g_e) < 2e-3 * max(1.0, abs(g_e)), (gl, g_e)
+        cos = float(torch.dot(gg.double(), gg_e.double()) / (gg.double().norm() * gg_e.double().norm()))
+        assert cos > 0.999 and abs(float(gg.norm() / gg_e.norm()) - 1.0) < 2e-2, cos
+    # the three iterations really used different blend weights
+    assert len({round(w[0], 6) for _, w in results}) == 3
