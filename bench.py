@@ -101,13 +101,13 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------------------------ ours
-def build_model(device, seed=3):
+def build_model(device, seed=3, growing_level=1.0):
     import gansynth_b200.models as M
     import gansynth_b200.networks as N
     import gansynth_b200.ops as ops
     store = ops.set_default_store(ops.VariableStore(device=device, seed=seed))
     M.reset_global_step()
-    pggan = N.PGGAN(growing_level=1.0, **FULL)
+    pggan = N.PGGAN(growing_level=growing_level, **FULL)
     model = M.GANSynth(pggan.generator, pggan.discriminator, None, None, SPECTRAL, HYPER, device=device)
     return model, store
 
@@ -331,7 +331,7 @@ def bench_ours(args):
 
     import gansynth_b200._lib as lib
     import gansynth_b200.functional as Fn
-    model, store = build_model(device)
+    model, store = build_model(device, growing_level=args.growing_level)
     host = host_batches(args.steps + args.warmup, rank, pinned=True)
     dev = [[t.to(device) for t in b] for b in host]
     torch.cuda.synchronize()
@@ -408,7 +408,8 @@ def bench_ours(args):
         steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
         vs_baseline=None, dtype="f32", data="synthetic",
         config=dict(workload="BASELINE configs[1]: full 2x16->128x1024 PGGAN G+D step (D update + G update, R1 + "
-                             "mode-seeking double backward, TF-Adam), batch 8 per GPU, fully grown",
+                             "mode-seeking double backward, TF-Adam), batch 8 per GPU, %s" %
+                             ("fully grown" if args.growing_level >= 1.0 else "growing_level %.4f" % args.growing_level),
                     global_batch=BATCH * world, parallelism="dp%d" % world,
                     l2="per-step activation working set is several GB >> 126 MB L2; no flush needed",
                     cuda_graphs=bool(graphs_were), eager_ms_per_step=ms_eager / args.steps,
@@ -490,6 +491,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-spectral", action="store_true")
+    ap.add_argument("--growing-level", type=float, default=1.0,
+                    help="PGGAN growing_level held fixed for the run (default 1.0 = fully grown = BASELINE configs[1]; "
+                         "< 63/127 exercises the progressive-growing blend path)")
     ap.add_argument("--conv-table", default=None, help="write per-shape convolution timings of the timed region here")
     args = ap.parse_args()
     if args.impl == "reference":
