@@ -314,6 +314,8 @@ def bench_ours(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        # NCCL writes its version banner (NCCL_DEBUG=VERSION and above) to stdout: keep stdout for the ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         torch.distributed.init_process_group("nccl", device_id=device)
     pk = peaks()
 
