@@ -11,6 +11,8 @@ one generator update at batch 8 per GPU on the full 2x16 -> 128x1024 PGGAN (full
 TF-Adam.  Rank 0 prints ONE JSON line.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -314,8 +316,6 @@ def bench_ours(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
-        # NCCL writes its version banner (NCCL_DEBUG=VERSION and above) to stdout: keep stdout for the ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         torch.distributed.init_process_group("nccl", device_id=device)
     pk = peaks()
 
@@ -498,6 +498,24 @@ def main():
                          "< 63/127 exercises the progressive-growing blend path)")
     ap.add_argument("--conv-table", default=None, help="write per-shape convolution timings of the timed region here")
     args = ap.parse_args()
+    # stdout carries ONE JSON line: everything libraries print there meanwhile (NCCL's version banner is a plain
+    # printf to stdout at NCCL_DEBUG >= VERSION) is routed to stderr at the file-descriptor level
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line_out = io.StringIO()
+        with contextlib.redirect_stdout(line_out):
+            _dispatch(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    sys.stdout.write(line_out.getvalue())
+    sys.stdout.flush()
+
+
+def _dispatch(args):
     if args.impl == "reference":
         bench_reference(args)
     else:
