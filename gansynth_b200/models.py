@@ -391,6 +391,16 @@ class GANSynth(object):
                                          (hp["generator_beta2"], hp["discriminator_beta2"]))
         if labels is not None:
             self._ensure_optimizers(labels, latents)
+        if not self.store.vars and "generator/weight" in state["variables"]:
+            # fresh model: create the variables first; the label embedding [num_labels, latent_dim] (networks.py:154-160)
+            # carries the two sizes the constructors need
+            num_labels, latent_dim = (int(d) for d in state["variables"]["generator/weight"].shape)
+            for pg in self._pggans():
+                pg._ensure_variables("generator", latent_dim, num_labels)
+                pg._ensure_variables("discriminator", 0, num_labels)
+        if not self.store.vars:
+            raise RuntimeError("import_tf_checkpoint: the model has no variables yet (call it after the first step, or "
+                               "bind PGGAN methods so they can be created from the checkpoint)")
         missing = [n for n in self.store.vars if n not in state["variables"]]
         if missing:
             raise KeyError("checkpoint %s lacks %d variables, e.g. %s" % (prefix, len(missing), missing[0]))
