@@ -209,7 +209,7 @@ spectrogram_fwd_kernel(const float* __restrict__ wave, int wave_len, int T, int 
                        const float* __restrict__ hann_g, const float2* __restrict__ tw1024g,
                        const float2* __restrict__ tw2048g, const int* __restrict__ mel_k0,
                        const float* __restrict__ mel_w, float* __restrict__ logmel, float* __restrict__ inst,
-                       float* __restrict__ scratch) {
+                       float* __restrict__ scratch, int total_runs) {
   extern __shared__ __align__(16) float sm[];
   int* melk = reinterpret_cast<int*>(sm);                           // [1024]
   float* melw = sm + NBINS;                                         // [6][1024]
@@ -246,15 +246,17 @@ spectrogram_fwd_kernel(const float* __restrict__ wave, int wave_len, int T, int 
   }
   __syncthreads();
 
-  const int b = blockIdx.x / runs_per_clip;
-  const int run = blockIdx.x % runs_per_clip;
-  const int t0 = run * RL;
-  const int t1 = min(T, t0 + RL);
   const int padf = HOP * (T - 1) + FRAME - wave_len;
-  const float* wv = wave + (size_t)b * wave_len;
   const bool vec_ok = (((wave_len | padf) & 1) == 0) && ((reinterpret_cast<uintptr_t>(wave) & 7) == 0);
   float2* zc = reinterpret_cast<float2*>(buf);
 
+  // persistent CTAs: the 48 KB of tables are loaded once per SM, not once per run
+  for (int run_id = blockIdx.x; run_id < total_runs; run_id += gridDim.x) {
+  const int b = run_id / runs_per_clip;
+  const int run = run_id % runs_per_clip;
+  const int t0 = run * RL;
+  const int t1 = min(T, t0 + RL);
+  const float* wv = wave + (size_t)b * wave_len;
   int round = 0;
   for (int tb = t0; tb < t1; tb += FWD_WARPS, ++round) {
     const int t = tb + warp;
@@ -364,6 +366,7 @@ spectrogram_fwd_kernel(const float* __restrict__ wave, int wave_len, int T, int 
       }
     }
     __syncthreads();
+  }
   }
 }
 
@@ -674,9 +677,11 @@ extern "C" int gs_spectrogram_fwd(const float* wave, const float* hann, const in
     GS_CUDA(cudaFuncSetAttribute(spectrogram_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
     attr = true;
   }
-  spectrogram_fwd_kernel<<<batch * runs, FWD_WARPS * 32, FWD_SMEM, st>>>(wave, wave_len, time_steps, frames_per_run, runs,
-                                                                       hann, g_tables.tw1024, g_tables.tw2048, mel_k0,
-                                                                       mel_w, logmel, inst, scratch);
+  const int total_runs = batch * runs;
+  const int grid = total_runs < gs_num_sms() ? total_runs : gs_num_sms();      // one 16-warp CTA per SM (188 KB smem)
+  spectrogram_fwd_kernel<<<grid, FWD_WARPS * 32, FWD_SMEM, st>>>(wave, wave_len, time_steps, frames_per_run, runs, hann,
+                                                                g_tables.tw1024, g_tables.tw2048, mel_k0, mel_w, logmel,
+                                                                inst, scratch, total_runs);
   GS_CHECK_LAUNCH("spectrogram_fwd");
   if (runs > 1) {
     const int rows = batch * (runs - 1);
