@@ -13,6 +13,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _library_built():
+    """The data-format tests (TFRecord CRC, WAV decode, TF checkpoints) call HOST entry points of the shared library:
+    build it when a fresh checkout has none (an existing one is never rebuilt here)."""
+    from gansynth_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+
+
 @pytest.fixture
 def emu():
     """Product host code on the torch-CPU emulation of the kernel API (tests/emu_backend.py)."""
