@@ -93,3 +93,31 @@ def test_training_state_naming_round_trip():
     assert back["global_step"] == 42 and back["optimizers"]["generator"]["t"] == 7
     assert back["optimizers"]["discriminator"]["t"] == 9 and set(back["variables"]) == set(v)
     assert np.array_equal(back["optimizers"]["generator"]["v"]["generator/a/weight"], opt["generator"]["v"]["generator/a/weight"])
+
+
+def test_model_export_then_import_into_a_fresh_model(emu, tmp_path):
+    """GANSynth.export_tf_checkpoint / import_tf_checkpoint on the CPU emulation backend: a fresh model (no variables
+    yet) is populated from the checkpoint alone -- the embedding's shape gives num_labels and latent_dim."""
+    import torch
+    import gansynth_b200.models as M
+    import gansynth_b200.networks as N
+    import gansynth_b200.ops as ops
+    from common import HYPER, SMALL
+    pg = N.PGGAN(growing_level=0.3, **SMALL)
+    pg._ensure_variables("generator", 256, 61)
+    pg._ensure_variables("discriminator", 0, 61)
+    model = M.GANSynth(pg.generator, pg.discriminator, None, None, {}, HYPER, device="cpu")
+    model.global_step.value = 17
+    want = {n: v.clone() for n, v in emu.state().items()}
+    prefix = model.export_tf_checkpoint(str(tmp_path / "ckpt" / "model.ckpt-17"))
+    assert os.path.exists(prefix + ".index") and os.path.exists(prefix + ".data-00000-of-00001")
+    # a new store, a new model, nothing created yet
+    store2 = ops.set_default_store(ops.VariableStore(device="cpu", seed=123))
+    M.reset_global_step()
+    pg2 = N.PGGAN(growing_level=0.3, **SMALL)
+    model2 = M.GANSynth(pg2.generator, pg2.discriminator, None, None, {}, HYPER, device="cpu")
+    assert not store2.vars
+    assert model2.import_tf_checkpoint(str(tmp_path / "ckpt")) == prefix
+    assert int(model2.global_step.value) == 17 and set(store2.vars) == set(want)
+    for n, v in store2.state().items():
+        assert torch.equal(v, want[n]), n
