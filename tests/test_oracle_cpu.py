@@ -115,6 +115,62 @@ def test_mel_matrix_structure():
     assert np.abs(m[1:] - ref).max() < 5e-4
 
 
+def test_mel_matrix_against_torchaudio_htk():
+    """Third-party corroboration of the HTK filterbank: torchaudio's melscale_fbanks(mel_scale="htk", norm=None)
+    builds its triangles in Hz instead of mel (a different but equally standard reading of the same centres), so the
+    two agree to ~4e-4 with IDENTICAL supports -- which pins the edge frequencies, the bin-to-frequency mapping
+    (linspace(0, nyquist, 1024), the reference's off-by-one quirk included) and the zero first row."""
+    torchaudio = pytest.importorskip("torchaudio")
+    m, _ = osp.mel_constants(1024, 16000)
+    fb = torchaudio.functional.melscale_fbanks(n_freqs=1024, f_min=0.0, f_max=8000.0, n_mels=1024, sample_rate=16000,
+                                               norm=None, mel_scale="htk").numpy()
+    assert fb.shape == m.shape
+    assert np.array_equal(m != 0, fb != 0)
+    assert np.abs(m - fb).max() < 1e-3
+    from gansynth_b200 import spectral_ops as sp                     # the product's host constants are the same matrix
+    assert np.array_equal(sp.host_constants(16000)["mel"], m)
+
+
+def test_pinv_against_numpy_with_tfp_rcond():
+    """tfp.math.pinv(a) = SVD pseudo-inverse with singular values below rcond * s_max dropped, rcond = 10 * max(shape)
+    * eps(float32) (App. B.12): numpy's pinv with that rcond is the same definition from an independent code path.
+    The cut matters here: the mel matrix has rank 726 of 1024, and 726 is what survives."""
+    m, p = osp.mel_constants(1024, 16000)
+    rcond = 10.0 * 1024 * np.finfo(np.float32).eps
+    ref = np.linalg.pinv(m.astype(np.float64), rcond=rcond)
+    assert p.shape == ref.shape == (1024, 1024)
+    assert np.abs(p - ref).max() < 2e-3 * np.abs(ref).max()
+    s = np.linalg.svd(m.astype(np.float64), compute_uv=False)
+    assert int((s > rcond * s.max()).sum()) == 726
+
+
+def test_inverse_stft_against_torch_istft():
+    """Third-party corroboration of tf.signal.inverse_stft as restated (irfft -> window / 1.5 -> overlap-add -> crop of
+    the front padding): torch.istft divides by the true overlap-added window envelope, which equals 1.5 wherever four
+    frames overlap, so the two agree on every sample except the first and last 1536 of the padded signal."""
+    g = torch.Generator().manual_seed(3)
+    log_mel = (torch.rand(2, 128, 1024, generator=g, dtype=torch.float64) * 1.6 - 1.0)
+    mel_if = torch.randn(2, 128, 1024, generator=g, dtype=torch.float64) * 0.3
+    got = osp.convert_to_waveform(log_mel, mel_if, **SPECTRAL)
+    p = torch.from_numpy(osp.mel_constants(1024, 16000)[1]).double()
+    mag = torch.exp(log_mel * 10.05 - 3.76) @ p
+    phase = torch.cumsum(mel_if * math.pi, dim=-2) @ p
+    spec = torch.nn.functional.pad(torch.polar(mag, phase), (1, 0))              # [B, T, 1025], DC = 0
+    spec[..., -1] = spec[..., -1].real + 0j                                      # irfft ignores Im of the Nyquist bin
+    n = 512 * 127 + 2048
+    # center=True only trims 1024 samples at each end (the untrimmed form trips torch's check that the window
+    # envelope is non-zero: hann[0] = 0): want[i] is padded sample i + 1024
+    want = torch.istft(spec.transpose(1, 2), n_fft=2048, hop_length=512, win_length=2048,
+                       window=osp.hann_window(2048, torch.float64), center=True)
+    pad = n - 64000
+    assert got.shape == (2, 64000) and want.shape == (2, n - 2048)
+    lo, hi = 1536, n - 1536                                                      # padded samples with four frames
+    a = got[:, lo - pad:hi - pad] if lo >= pad else got[:, :hi - pad]            # got[i] is padded sample i + pad
+    b = want[:, max(lo, pad) - 1024:hi - 1024]
+    assert a.shape == b.shape
+    assert float((a - b).abs().max()) < 1e-9 * float(want.abs().max())
+
+
 def test_stft_against_scipy():
     import scipy.signal
     x = torch.randn(1, 4096 + 2048, dtype=torch.float64)
