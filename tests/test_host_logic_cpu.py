@@ -69,3 +69,41 @@ def test_step_gradients_and_adam_parity(emu, level):
         # weights after the TF-Adam update
         for n, v in emu.vars.items():
             assert rel_err(v, ostep.params[n]) < 5e-4, n
+
+
+@pytest.mark.parametrize("level", [0.05, 0.1, 0.3])
+def test_device_resident_blend_weight_matches_host_floats(emu, level):
+    """Growth-phase graphs keep lerp's (t, 1 - t) in device memory (PGGAN.lerp_coef, AxpbyDev): forward values and the
+    gradients w.r.t. latents and images must equal the host-float path, and both must match the oracle."""
+    opg, params, ppg, latents, labels, images = _pair(level, emu)
+    latents = latents.clone().requires_grad_()
+    images = images.clone().requires_grad_()
+    host_g = ppg.generator(latents, labels)
+    host_f, host_l = ppg.discriminator(images, labels)
+    g_host = torch.autograd.grad(host_g.sum() + host_l.sum(), (latents, images))
+    ppg.update_lerp_coef("cpu")
+    ppg.device_lerp_active = True
+    try:
+        dev_g = ppg.generator(latents, labels)
+        dev_f, dev_l = ppg.discriminator(images, labels)
+        g_dev = torch.autograd.grad(dev_g.sum() + dev_l.sum(), (latents, images))
+    finally:
+        ppg.device_lerp_active = False
+    assert rel_err(dev_g, host_g) < 1e-6 and rel_err(dev_l, host_l) < 1e-6 and rel_err(dev_f, host_f) < 1e-6
+    for a, b in zip(g_dev, g_host):
+        assert rel_err(a, b) < 1e-6
+    assert rel_err(dev_g, opg.generator(params, latents.detach(), labels)) < TOL
+    gd = ppg.growing_depth
+    import math
+    assert ppg.structure_key() == ("grow", math.ceil(gd))
+    t = float(ppg.lerp_coef[0])
+    assert abs(t - (math.ceil(gd) - gd)) < 1e-6 and abs(float(ppg.lerp_coef.sum()) - 1.0) < 1e-6
+
+
+def test_structure_key_follows_the_blend_depth(emu):
+    import gansynth_b200.networks as pnet
+    keys = []
+    for level in (0.0, 0.1, 1.0 / 7.0, 0.3, 3.0 / 7.0, 0.5, 1.0):
+        keys.append(pnet.PGGAN(growing_level=level, **SMALL).structure_key())
+    # SMALL has max_depth 2: growing_depth = log2(1 + 7 level) -> 0, 0.77, 1, 1.63, 2, 2.17, 3
+    assert keys == [("grow", 0), ("grow", 1), ("grow", 1), ("grow", 2), ("grow", 2), ("grown",), ("grown",)]
