@@ -467,10 +467,26 @@ class GANSynth(object):
                 print("INFO:gansynth_b200:global_step = %d, generator_loss = %.6f, discriminator_loss = %.6f (%.3f sec)"
                       % (step, float(self.generator_loss), float(self.discriminator_loss), time.time() - t0), flush=True)
                 t0 = time.time()
+            if rank0 and save_summary_steps and iteration % save_summary_steps == 0:
+                self._write_summary(model_dir, step)
             if rank0 and save_checkpoint_steps and step % save_checkpoint_steps == 0:
                 self.save_checkpoint(model_dir)
         if rank0:
             self.save_checkpoint(model_dir)
+
+    def _write_summary(self, model_dir, step):
+        """SummarySaverHook stand-in (models.py:131-170): the scalar summaries (generator_loss, discriminator_loss) plus
+        the growing depth, one JSON object per line in `<model_dir>/summaries.jsonl` (the audio / image summaries of
+        the reference are TensorBoard artefacts and are not reproduced)."""
+        import json
+        os.makedirs(model_dir, exist_ok=True)
+        depth = [float(pg.growing_depth) for pg in self._pggans()]
+        rec = dict(global_step=int(step), generator_loss=float(self.generator_loss),
+                   discriminator_loss=float(self.discriminator_loss), time=time.time())
+        if depth:
+            rec["growing_depth"] = depth[0]
+        with open(os.path.join(model_dir, "summaries.jsonl"), "a") as f:
+            f.write(json.dumps(rec) + "\n")
 
     def evaluate(self, model_dir, config, classifier, input_name="images:0", output_names=("features:0", "logits:0")):
         """models.py:196-230: Frechet distance between classifier features of real and generated images over

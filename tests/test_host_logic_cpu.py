@@ -107,3 +107,41 @@ def test_structure_key_follows_the_blend_depth(emu):
         keys.append(pnet.PGGAN(growing_level=level, **SMALL).structure_key())
     # SMALL has max_depth 2: growing_depth = log2(1 + 7 level) -> 0, 0.77, 1, 1.63, 2, 2.17, 3
     assert keys == [("grow", 0), ("grow", 1), ("grow", 1), ("grow", 2), ("grow", 2), ("grown",), ("grown",)]
+
+
+def test_train_loop_checkpoints_and_scalar_summaries(emu, tmp_path):
+    """GANSynth.train (models.py:110-194) on the CPU emulation backend: stops at total_steps, restores from its own
+    checkpoint on the next call, writes one scalar-summary line per save_summary_steps iterations."""
+    import json
+    import gansynth_b200.models as pmodels
+    import gansynth_b200.networks as pnet
+    gs = pmodels.get_or_create_global_step()
+    ppg = pnet.PGGAN(growing_level=gs / 8, **SMALL)
+    g = torch.Generator().manual_seed(0)
+
+    def real():
+        return (torch.randn(4, 512, generator=g) * 0.5,
+                torch.nn.functional.one_hot(torch.randint(0, 61, (4,), generator=g), 61).float())
+
+    def build():
+        m = pmodels.GANSynth(ppg.generator, ppg.discriminator, real, lambda: torch.randn(4, 256, generator=g), {}, HYPER,
+                             device="cpu")
+        m.real_images_from_waveforms = lambda w: w.reshape(4, 2, 16, 16)
+        return m
+
+    model = build()
+    model.train(str(tmp_path), None, total_steps=3, save_checkpoint_steps=2, save_summary_steps=1, log_tensor_steps=0)
+    assert int(gs.value) == 3
+    lines = [json.loads(l) for l in open(tmp_path / "summaries.jsonl")]
+    assert [l["global_step"] for l in lines] == [1, 2, 3]
+    assert all(set(l) >= {"generator_loss", "discriminator_loss", "growing_depth"} for l in lines)
+    assert lines[0]["growing_depth"] < lines[2]["growing_depth"]
+    assert sorted(p.name for p in tmp_path.glob("model.ckpt-*.pt")) == ["model.ckpt-2.pt", "model.ckpt-3.pt"]
+    weights = {n: v.clone() for n, v in emu.state().items()}
+    # a second run: nothing to do (restored at step 3), the weights are the checkpoint's
+    gs.value = 0
+    model2 = build()
+    model2.train(str(tmp_path), None, total_steps=3, save_checkpoint_steps=2, save_summary_steps=1, log_tensor_steps=0)
+    assert int(gs.value) == 3
+    for n, v in emu.state().items():
+        assert torch.equal(v, weights[n]), n
