@@ -1,7 +1,6 @@
 """GPU: the user path end to end with the reference's command line (gan_synth_main.py:25-36, 91-130): TFRecord-of-paths
 + WAV files -> nsynth_input_fn -> GANSynth.train (checkpoint) -> --generate (samples/*.wav)."""
 import glob
-import os
 
 import numpy as np
 import pytest
