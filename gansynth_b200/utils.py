@@ -1,16 +1,17 @@
-"""reference utils.py: attribute-access dict used for spectral_params / hyper_params."""
+"""Attribute-access dictionary (reference utils.py): `gan_synth_main.py` builds `spectral_params` and `hyper_params`
+with it and the model code reads them as `hyper_params.generator_learning_rate`."""
 
 
 class Dict(dict):
+    """dict whose keys can also be read, written and deleted as attributes.  A missing key raises AttributeError on
+    attribute reads (so `getattr(d, k, default)` and `hasattr` behave), KeyError on item reads as usual."""
 
-    def __getattr__(self, name):
-        try:
-            return self[name]
-        except KeyError:
-            raise AttributeError(name)
+    __slots__ = ()
 
-    def __setattr__(self, name, value):
-        self[name] = value
+    def __getattr__(self, key):
+        if key in self:
+            return dict.__getitem__(self, key)
+        raise AttributeError("%s has no attribute or key %r" % (type(self).__name__, key))
 
-    def __delattr__(self, name):
-        del self[name]
+    __setattr__ = dict.__setitem__
+    __delattr__ = dict.__delitem__
