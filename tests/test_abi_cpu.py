@@ -51,3 +51,40 @@ def test_product_does_not_import_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+
+
+def test_argument_errors_are_reported_before_any_device_work():
+    """The entry points validate shapes first: a refused call returns a negative code and a message without touching
+    CUDA (so this runs on the CPU box)."""
+    import __graft_entry__ as ge
+    from gansynth_b200 import _lib
+    ge.build()
+    lib = _lib.load()
+    # 128 frames of hop 512 / length 2048 cover 67072 samples: 70000 is refused
+    assert lib.gs_spectrogram_fwd(None, None, None, None, None, None, None, 1, 70000, 128, 32, None) < 0
+    assert b"exceeds" in lib.gs_last_error()
+    # segments must be a multiple of 8 frames
+    assert lib.gs_waveform_fwd(None, None, None, None, None, None, 46, None, None, 1, 64000, 128, 12, None) < 0
+    assert b"multiple of 8" in lib.gs_last_error()
+    # several runs per clip need the caller's scratch buffer
+    assert lib.gs_spectrogram_fwd(None, None, None, None, None, None, None, 1, 64000, 128, 32, None) < 0
+    assert b"scratch" in lib.gs_last_error()
+    # an empty batch is a no-op
+    assert lib.gs_spectrogram_fwd(None, None, None, None, None, None, None, 0, 64000, 128, 32, None) == 0
+    assert lib.gs_pcm16_to_float(None, None, 0, None) == 0 and lib.gs_pcm16_to_float(None, None, -1, None) < 0
+    with __import__("pytest").raises(_lib.GansynthLibraryError):
+        _lib.host_call("gs_wav_read_batch", None, 1, None, 0, 1, None)
+
+
+def test_spectral_launch_policies():
+    from gansynth_b200 import spectral_ops as sp
+    # forward: runs of 32 frames once that still gives >= 4 CTAs per SM, else one 16-frame round per CTA
+    assert sp.frames_per_run(256, 128) == 32 and sp.frames_per_run(8, 128) == 16 and sp.frames_per_run(148, 128) == 32
+    # inverse: whole clips when the batch fills the SMs, 8-frame multiples otherwise
+    assert sp.frames_per_segment(256, 128) == 128 and sp.frames_per_segment(148, 128) == 128
+    assert sp.frames_per_segment(8, 128) == 8 and sp.frames_per_segment(64, 128) == 64 and sp.frames_per_segment(1, 128) == 8
+    assert sp.frames_per_segment(3, 20) == 16 and sp.frames_per_segment(3, 4) == 4
+    for b in (1, 2, 5, 8, 33, 100, 300):
+        for t in (4, 8, 20, 128):
+            f = sp.frames_per_segment(b, t)
+            assert f >= t or f % 8 == 0
