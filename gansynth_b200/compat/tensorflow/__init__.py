@@ -95,5 +95,14 @@ class GraphDef(object):
 
 
 def __getattr__(name):
+    # TensorBoard's compat layer imports `tensorflow` when it can and expects tf.io.gfile & co.; it ships a stub of
+    # exactly those pieces for TensorFlow-less installs -- hand it its own stub so that SummaryWriter keeps working
+    # while this stand-in is on sys.path
+    try:
+        from tensorboard.compat import tensorflow_stub as _stub
+        if hasattr(_stub, name):
+            return getattr(_stub, name)
+    except Exception:
+        pass
     raise AttributeError("gansynth_b200.compat.tensorflow is a stand-in for the names gan_synth_main.py uses; "
                          "`tf.%s` is not one of them" % name)

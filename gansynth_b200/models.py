@@ -476,8 +476,8 @@ class GANSynth(object):
 
     def _write_summary(self, model_dir, step):
         """SummarySaverHook stand-in (models.py:131-170): the scalar summaries (generator_loss, discriminator_loss) plus
-        the growing depth, one JSON object per line in `<model_dir>/summaries.jsonl` (the audio / image summaries of
-        the reference are TensorBoard artefacts and are not reproduced)."""
+        the growing depth, one JSON object per line in `<model_dir>/summaries.jsonl` and as TensorBoard scalar events
+        (the audio / image summaries of the reference are not reproduced)."""
         import json
         os.makedirs(model_dir, exist_ok=True)
         depth = [float(pg.growing_depth) for pg in self._pggans()]
@@ -487,6 +487,21 @@ class GANSynth(object):
             rec["growing_depth"] = depth[0]
         with open(os.path.join(model_dir, "summaries.jsonl"), "a") as f:
             f.write(json.dumps(rec) + "\n")
+        # the same scalars as TensorBoard event files in model_dir (tags as in models.py:163-172), when the
+        # tensorboard package is there
+        if getattr(self, "_tb", None) is None or getattr(self, "_tb_dir", None) != model_dir:
+            try:
+                from torch.utils.tensorboard import SummaryWriter
+                self._tb, self._tb_dir = SummaryWriter(log_dir=model_dir), model_dir
+            except Exception:
+                self._tb, self._tb_dir = False, model_dir
+        if self._tb:
+            try:
+                for tag in ("generator_loss", "discriminator_loss"):
+                    self._tb.add_scalar(tag, rec[tag], global_step=int(step))
+                self._tb.flush()
+            except Exception:                      # never let an optional event file stop a training run
+                self._tb = False
 
     def evaluate(self, model_dir, config, classifier, input_name="images:0", output_names=("features:0", "logits:0")):
         """models.py:196-230: Frechet distance between classifier features of real and generated images over

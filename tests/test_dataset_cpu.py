@@ -163,3 +163,34 @@ def test_pipeline_close_releases_the_prefetch_thread(tmp_path):
     assert not pipe._thread.is_alive()
     with pytest.raises(StopIteration):
         next(pipe)
+
+
+def test_tfrecord_framing_against_tensorboard_stub(tmp_path):
+    """Third-party pin of the TFRecord container: TensorBoard ships its own pure-Python TFRecord reader / writer and
+    masked CRC-32C (tensorboard.compat.tensorflow_stub, written against TensorFlow's record_writer.cc)."""
+    pywrap = pytest.importorskip("tensorboard.compat.tensorflow_stub.pywrap_tensorflow")
+    from tensorboard.summary.writer.record_writer import RecordWriter
+    recs = [b"", b"a", os.urandom(300), tfrecord.serialize_example(dict(path=b"x.wav", pitch=60, source=0))]
+    for r in recs:
+        assert tfrecord.masked_crc32c(r) == pywrap.masked_crc32c(r) and tfrecord.crc32c(r) == pywrap.crc32c(r)
+    mine = str(tmp_path / "mine.tfrecord")
+    with tfrecord.TFRecordWriter(mine) as w:
+        for r in recs:
+            w.write(r)
+    reader = pywrap.PyRecordReader_New(mine)          # TensorBoard reads (and CRC-checks) this package's file
+    got = []
+    while True:
+        try:
+            reader.GetNext()
+        except Exception:
+            break
+        got.append(reader.record())
+    assert got == recs
+    theirs = str(tmp_path / "theirs.tfrecord")
+    with open(theirs, "wb") as f:                     # ... and this package reads TensorBoard's
+        w = RecordWriter(f)
+        for r in recs:
+            w.write(r)
+        w.flush()
+    assert list(tfrecord.read_records(theirs)) == recs
+    assert open(theirs, "rb").read() == open(mine, "rb").read()

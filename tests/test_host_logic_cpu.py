@@ -137,6 +137,18 @@ def test_train_loop_checkpoints_and_scalar_summaries(emu, tmp_path):
     assert all(set(l) >= {"generator_loss", "discriminator_loss", "growing_depth"} for l in lines)
     assert lines[0]["growing_depth"] < lines[2]["growing_depth"]
     assert sorted(p.name for p in tmp_path.glob("model.ckpt-*.pt")) == ["model.ckpt-2.pt", "model.ckpt-3.pt"]
+    # the scalars are also TensorBoard events under the reference's tags
+    try:
+        from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+    except ImportError:
+        EventAccumulator = None
+    if EventAccumulator is not None:
+        acc = EventAccumulator(str(tmp_path))
+        acc.Reload()
+        assert set(acc.Tags()["scalars"]) >= {"generator_loss", "discriminator_loss"}
+        ev = acc.Scalars("generator_loss")
+        assert [e.step for e in ev] == [1, 2, 3]
+        assert abs(ev[2].value - lines[2]["generator_loss"]) < 1e-6 * max(1.0, abs(lines[2]["generator_loss"]))
     weights = {n: v.clone() for n, v in emu.state().items()}
     # a second run: nothing to do (restored at step 3), the weights are the checkpoint's
     gs.value = 0
