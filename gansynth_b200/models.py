@@ -88,6 +88,9 @@ class GANSynth(object):
         self._graph_pool = None
         self._stream = None
         self.use_cuda_graphs = os.environ.get("GS_CUDA_GRAPHS", "1") != "0"
+        # audio / image summaries next to the scalar ones (needs tensorboard).  Validated on the CPU emulation backend
+        # only so far (the round's GPU budget was spent): opt in with GS_MEDIA_SUMMARIES=1 or model.media_summaries = True
+        self.media_summaries = os.environ.get("GS_MEDIA_SUMMARIES", "0") == "1"
         self.generator_loss = None
         self.discriminator_loss = None
         # last evaluated tensors, named like the reference attributes (models.py:91-108)
@@ -476,8 +479,8 @@ class GANSynth(object):
 
     def _write_summary(self, model_dir, step):
         """SummarySaverHook stand-in (models.py:131-170): the scalar summaries (generator_loss, discriminator_loss) plus
-        the growing depth, one JSON object per line in `<model_dir>/summaries.jsonl` and as TensorBoard scalar events
-        (the audio / image summaries of the reference are not reproduced)."""
+        the growing depth, one JSON object per line in `<model_dir>/summaries.jsonl` and as TensorBoard scalar events,
+        followed by the audio / image summaries (`_write_media_summaries`)."""
         import json
         os.makedirs(model_dir, exist_ok=True)
         depth = [float(pg.growing_depth) for pg in self._pggans()]
@@ -499,9 +502,37 @@ class GANSynth(object):
             try:
                 for tag in ("generator_loss", "discriminator_loss"):
                     self._tb.add_scalar(tag, rec[tag], global_step=int(step))
+                if self.media_summaries:
+                    self._write_media_summaries(int(step))
                 self._tb.flush()
-            except Exception:                      # never let an optional event file stop a training run
+            except Exception as e:                 # never let an optional event file stop a training run
+                print("WARNING:gansynth_b200:summaries disabled after %s: %s" % (type(e).__name__, e), flush=True)
                 self._tb = False
+
+    @torch.no_grad()
+    def _write_media_summaries(self, step, max_outputs=4):
+        """The audio and image summaries of models.py:131-161: up to four real and generated clips (16 kHz audio) and
+        their log-mel magnitude / instantaneous-frequency images.  Generated clips come from a fresh draw of
+        `fake_input_fn` through `generate_batch` (in the reference every `session.run` draws new latents too)."""
+        if self.real_waveforms is None or self.real_labels is None:
+            return
+        real = self.real_waveforms
+        fake = self.generate_batch(self.real_labels, self._next_latents())
+        n = min(max_outputs, int(real.shape[0]))
+        rate = int(self.spectral_params.get("sample_rate", 16000))
+        for name, wave in (("real_waveforms", real), ("fake_waveforms", fake)):
+            for i in range(n):
+                self._tb.add_audio("%s/%d" % (name, i), wave[i:i + 1].detach().float().cpu().clamp(-1.0, 1.0), step,
+                                   sample_rate=rate)
+        real_images = self.real_images_from_waveforms(real)
+        for name, img in (("real_magnitude_spectrograms", real_images[:, 0]),
+                          ("fake_magnitude_spectrograms", self.fake_images[:, 0]),
+                          ("real_instantaneous_frequencies", real_images[:, 1]),
+                          ("fake_instantaneous_frequencies", self.fake_images[:, 1])):
+            for i in range(n):
+                x = img[i].detach().float()
+                lo, hi = x.min(), x.max()
+                self._tb.add_image("%s/%d" % (name, i), ((x - lo) / (hi - lo + 1.0e-12)).cpu(), step, dataformats="HW")
 
     def evaluate(self, model_dir, config, classifier, input_name="images:0", output_names=("features:0", "logits:0")):
         """models.py:196-230: Frechet distance between classifier features of real and generated images over

@@ -157,3 +157,36 @@ def test_train_loop_checkpoints_and_scalar_summaries(emu, tmp_path):
     assert int(gs.value) == 3
     for n, v in emu.state().items():
         assert torch.equal(v, weights[n]), n
+
+
+def test_media_summaries_on_the_real_spectral_shapes(emu, tmp_path):
+    """models.py:131-161 on the CPU emulation backend with a small 1024-bin model (1x128 -> 8x1024 images, 5000-sample
+    clips): the event file carries the loss scalars, 4 + 4 audio clips and the four image groups."""
+    pytest.importorskip("tensorboard")
+    from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+    import gansynth_b200.models as pmodels
+    import gansynth_b200.networks as pnet
+    cfg = dict(min_resolution=[1, 128], max_resolution=[8, 1024], min_channels=32, max_channels=64)
+    spectral = dict(waveform_length=5000, sample_rate=16000, spectrogram_shape=[8, 1024], overlap=0.75)
+    ppg = pnet.PGGAN(growing_level=1.0, **cfg)
+    g = torch.Generator().manual_seed(0)
+
+    def real():
+        return (0.1 * torch.randn(4, 5000, generator=g),
+                torch.nn.functional.one_hot(torch.randint(0, 61, (4,), generator=g), 61).float())
+
+    model = pmodels.GANSynth(ppg.generator, ppg.discriminator, real, lambda: torch.randn(4, 256, generator=g), spectral,
+                             HYPER, device="cpu")
+    model.media_summaries = True
+    model.train(str(tmp_path), None, total_steps=1, save_checkpoint_steps=0, save_summary_steps=1, log_tensor_steps=0)
+    assert model._tb, "summaries were disabled"
+    acc = EventAccumulator(str(tmp_path), size_guidance={"audio": 0, "images": 0, "scalars": 0})
+    acc.Reload()
+    tags = acc.Tags()
+    assert set(tags["scalars"]) >= {"generator_loss", "discriminator_loss"}
+    assert sorted(tags["audio"]) == sorted("%s/%d" % (n, i) for n in ("real_waveforms", "fake_waveforms") for i in range(4))
+    assert len(tags["images"]) == 16 and "fake_instantaneous_frequencies/3" in tags["images"]
+    a = acc.Audio("fake_waveforms/0")[0]
+    assert a.sample_rate == 16000 and a.length_frames == 5000
+    im = acc.Images("real_magnitude_spectrograms/0")[0]
+    assert (im.height, im.width) == (8, 1024)
