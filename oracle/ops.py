@@ -104,6 +104,50 @@ def batch_stddev(x, groups=4, epsilon=1.0e-12):
     return g.repeat(groups, 1, h, w)
 
 
+class MaskTape(object):
+    """Parity instrument, not reference behaviour: the leaky-relu masks (x > 0) of a run, in call order.
+
+    `record`: every leaky_relu call appends its mask.  `replay`: every call takes the next mask of the tape
+    instead of the sign of its own input -- the run then follows the SAME piecewise-linear branch as the run the
+    tape came from (e.g. the CUDA path), which is what separates "a mask flipped because a pre-activation sits
+    within rounding of zero" from "the arithmetic differs".  `flips` counts replayed elements whose mask differs
+    from this run's own sign, `total` all elements seen."""
+
+    def __init__(self, masks=None):
+        self.masks = [] if masks is None else list(masks)
+        self.replay = masks is not None
+        self.pos = self.flips = self.total = 0
+
+    def __enter__(self):
+        global _TAPE
+        assert _TAPE is None, "mask tapes do not nest"
+        _TAPE = self
+        return self
+
+    def __exit__(self, *exc):
+        global _TAPE
+        _TAPE = None
+        if exc[0] is None and self.replay:
+            assert self.pos == len(self.masks), "mask tape: %d of %d masks consumed" % (self.pos, len(self.masks))
+        return False
+
+
+_TAPE = None
+
+
 def leaky_relu(x):
     """tf.nn.leaky_relu default alpha = 0.2."""
-    return F.leaky_relu(x, 0.2)
+    if _TAPE is None:
+        return F.leaky_relu(x, 0.2)
+    own = x.detach() > 0
+    if not _TAPE.replay:
+        _TAPE.masks.append(own)
+        return F.leaky_relu(x, 0.2)
+    assert _TAPE.pos < len(_TAPE.masks), "mask tape exhausted at leaky_relu call %d" % _TAPE.pos
+    m = _TAPE.masks[_TAPE.pos]
+    _TAPE.pos += 1
+    assert m.numel() == x.numel(), "mask tape: call %d has %s, tape has %s" % (_TAPE.pos - 1, tuple(x.shape), tuple(m.shape))
+    m = m.reshape(x.shape)
+    _TAPE.flips += int((m != own).sum())
+    _TAPE.total += x.numel()
+    return torch.where(m, x, 0.2 * x)

@@ -190,3 +190,30 @@ def test_media_summaries_on_the_real_spectral_shapes(emu, tmp_path):
     assert a.sample_rate == 16000 and a.length_frames == 5000
     im = acc.Images("real_magnitude_spectrograms/0")[0]
     assert (im.height, im.width) == (8, 1024)
+
+
+@pytest.mark.parametrize("level", [0.3, 1.0])
+def test_mask_pinned_gradient_criterion(emu, level):
+    """The GPU step tests' criterion (common.check_substep) on the emulated kernels: the product's leaky-relu masks
+    are taped in the oracle's call order, the fp64 oracle replays them and every gradient element agrees to 1e-3;
+    a tape from a DIFFERENT input makes the flip count explode (the instrument really pins the branch)."""
+    import gansynth_b200.functional as F
+    import gansynth_b200.models as pmodels
+    from common import check_substep, record_masks
+    from oracle import ops as oops
+    opg, params, ppg, latents, labels, images = _pair(level, emu)
+    o64 = omodels.GANSynthStep(opg, {n: p.double() for n, p in params.items()}, HYPER)
+    model = pmodels.GANSynth(ppg.generator, ppg.discriminator, None, None, {}, HYPER, device="cpu")
+    model._ensure_optimizers(labels, latents)
+
+    def coarse(mode, got, want):
+        return grad_close(got, want, 5e-3), "max-norm"
+
+    for scope in ("discriminator", "generator"):
+        check_substep(model, emu, o64, scope, images, labels, latents, torch.float64, "emu", True, coarse)
+    # a tape recorded on other latents does not describe this run: most masks of the generator disagree
+    with record_masks(F.K) as masks:
+        model.generator_loss_fn(labels, torch.randn(4, 256, generator=torch.Generator().manual_seed(99)))
+    with oops.MaskTape(masks) as tape:
+        o64.generator_update(labels.double(), latents.double(), apply=False)
+    assert tape.flips > 0.05 * tape.total

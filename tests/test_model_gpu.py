@@ -3,7 +3,7 @@
 import pytest
 import torch
 
-from common import FULL, HYPER, SMALL, SPECTRAL, grad_close, rel_err, seeded_inputs
+from common import FULL, HYPER, SMALL, SPECTRAL, check_substep as _check_substep, rel_err, seeded_inputs
 from oracle import models as omodels
 from oracle import networks as onet
 
@@ -23,14 +23,8 @@ def conv_mode(request):
 
 
 def grad_ok(mode, got, want64, want32=None):
-    """Gradient criterion -> (ok, description).  The step's gradients pass through ~30 leaky-relu masks;
-    an element whose pre-activation is within rounding of zero flips its mask and moves the gradient
-    discontinuously, so even the fp32 ORACLE sits 1e-3..8e-3 (max-norm, per variable) from the fp64
-    oracle on the second-order terms, and the fp32 CUDA path varies run to run with the order of its
-    atomic accumulations (profiles/grad_diag_r1.txt).  The bound is therefore on direction and size:
-      fp32 mode: cosine >= 0.9995, relative L2 error <= 2e-2
-      tc mode  : cosine >= 0.995,  relative L2 error <= 1e-1   (1e-5 convolution noise: ~100x more flips)
-    The exact-math check of the same autograd composition is tests/test_host_logic_cpu.py (5e-4)."""
+    """Direction / size criterion against the UNPINNED fp64 oracle (kept as a coarse sanity bound only; the
+    gradient parity claim itself is `check_substep` below): cosine >= 0.9995 / 0.995, relative L2 <= 2e-2 / 1e-1."""
     g, w = got.detach().double().cpu().reshape(-1), want64.detach().double().reshape(-1)
     if float(w.abs().max()) == 0.0:
         return float(g.abs().max()) == 0.0, "zero reference"
@@ -38,6 +32,10 @@ def grad_ok(mode, got, want64, want32=None):
     rel = float((g - w).norm() / w.norm())
     lim = (0.9995, 2e-2) if mode == "fp32" else (0.995, 1e-1)
     return (cos >= lim[0] and rel <= lim[1]), "cos %.6f relL2 %.3e" % (cos, rel)
+
+
+def check_substep(model, store, ostep, scope, images, labels, latents, dtype, mode, plain=True):
+    return _check_substep(model, store, ostep, scope, images, labels, latents, dtype, mode, plain, grad_ok)
 
 
 def _pair(cfg, level, store, bias_std=0.1):
@@ -65,40 +63,40 @@ def test_small_forward_parity(cuda_store, conv_mode, level):
 
 @pytest.mark.parametrize("level", [0.3, 1.0])
 def test_small_step_parity(cuda_store, conv_mode, level):
-    """Two full iterations (D update + G update): losses, flat gradients and updated weights."""
+    """Two full iterations (D update + G update): losses and flat gradients by `check_substep` (masks pinned, 1e-3
+    on every element), then the fused TF-Adam update.  With beta1 = 0 the first Adam steps move every element by
+    about lr * sign(g), so the updated weights are compared where the gradient is RESOLVED (|g| above 1e-2 of the
+    variable's largest): there they must meet 1e-3 outright; elements with a gradient inside the 1e-3 noise floor
+    may legitimately step the other way (2 * lr apart).  Each iteration starts from the oracle's weights."""
     import gansynth_b200.models as pmodels
     opg, params, ppg = _pair(SMALL, level, cuda_store)
     latents, labels, images = seeded_inputs(4, [16, 16])
     ostep = omodels.GANSynthStep(opg, {n: p.double() for n, p in params.items()}, HYPER)
     model = pmodels.GANSynth(ppg.generator, ppg.discriminator, None, None, {}, HYPER)
-    lc, zc, ic = labels.cuda(), latents.cuda(), images.cuda()
-    model._ensure_optimizers(lc, zc)
+    model._ensure_optimizers(labels.cuda(), latents.cuda())
+    lr = HYPER["generator_learning_rate"]
     for it in range(2):
         lat2 = torch.randn(4, 256, generator=torch.Generator().manual_seed(10 + it))
-        want_loss, want_grads = ostep.discriminator_update(images.double(), labels.double(), latents.double())
-        model._set_trainable("discriminator")
-        loss = model.discriminator_loss_fn(ic, lc, zc)
-        assert abs(float(loss.detach()) - float(want_loss)) < TOL * max(1.0, abs(float(want_loss)))
-        model._apply("discriminator", loss)
-        for n, g in cuda_store.unflatten("discriminator", model._opt["discriminator"]["grad"]).items():
-            ok, why = grad_ok(conv_mode, g, want_grads[n])
-            assert ok, (n, why)
-        want_loss, want_grads = ostep.generator_update(labels.double(), lat2.double())
-        model._set_trainable("generator")
-        loss = model.generator_loss_fn(lc, lat2.cuda())
-        assert abs(float(loss.detach()) - float(want_loss)) < TOL * max(1.0, abs(float(want_loss)))
-        model._apply("generator", loss)
-        for n, g in cuda_store.unflatten("generator", model._opt["generator"]["grad"]).items():
-            ok, why = grad_ok(conv_mode, g, want_grads[n])
-            assert ok, (n, why)
-        # updated weights.  With beta1 = 0 the first TF-Adam steps move every element by +-lr whatever the
-        # gradient's size, so an element whose (tiny) gradient changes sign under the tc-mode noise ends
-        # 2*lr away per update: tc mode allows that, fp32 mode must meet 1e-3 outright.
-        slack = 0.0 if conv_mode == "fp32" else 2.0 * HYPER["generator_learning_rate"] * (it + 1)
-        for n, v in cuda_store.vars.items():
-            ref = ostep.params[n].detach()
-            diff = float((v.detach().double().cpu() - ref).abs().max())
-            assert diff <= TOL * float(ref.abs().max()) + slack, (n, diff)
+        for scope, z in (("discriminator", latents), ("generator", lat2)):
+            loss, got, want = check_substep(model, cuda_store, ostep, scope, images, labels, z, torch.float64, conv_mode)
+            before = {n: ostep.params[n].detach().clone() for n in got}
+            model._apply(scope, loss)
+            if scope == "discriminator":
+                ostep.discriminator_update(images.double(), labels.double(), z.double())
+            else:
+                ostep.generator_update(labels.double(), z.double())
+            for n in got:
+                ref = ostep.params[n].detach()
+                diff = (cuda_store.vars[n].detach().double().cpu() - ref).abs()
+                g = want[n].detach().abs()
+                resolved = g > 1e-2 * float(g.max())
+                bound = TOL * float(ref.abs().max())
+                if bool(resolved.any()):
+                    assert float(diff[resolved].max()) <= bound, (n, float(diff[resolved].max()))
+                assert float(diff.max()) <= bound + 2.5 * lr, (n, float(diff.max()))
+                assert float((ref - before[n]).abs().max()) > 0.0 or float(g.max()) == 0.0
+            # next sub-step from the oracle's state (the un-resolved elements would otherwise drift apart)
+            cuda_store.load({n: ostep.params[n].detach() for n in got})
 
 
 def test_full_forward_parity(cuda_store, conv_mode):
@@ -114,32 +112,45 @@ def test_full_forward_parity(cuda_store, conv_mode):
     assert rel_err(got, want) < TOL and rel_err(gf, wf) < TOL and rel_err(gl, wl) < TOL
 
 
+@pytest.mark.parametrize("level", [0.1, 0.3])
+def test_full_forward_parity_growing(cuda_store, level):
+    """Full-size networks in the growth phase (blend at 32x256 for level 0.1, at 128x1024 for 0.3), batch 4,
+    default (tensor-core) mode: the lerp / upscale2d / downscale2d branches of networks.py:109-152, 244-287."""
+    opg, params, ppg = _pair(FULL, level, cuda_store)
+    latents, labels, images = seeded_inputs(4, [128, 1024])
+    with torch.no_grad():
+        got = ppg.generator(latents.cuda(), labels.cuda())
+        gf, gl = ppg.discriminator(images.cuda(), labels.cuda())
+        want = opg.generator(params, latents, labels)
+        wf, wl = opg.discriminator(params, images, labels)
+    assert got.shape == (4, 2, 128, 1024)
+    assert rel_err(got, want) < TOL and rel_err(gf, wf) < TOL and rel_err(gl, wl) < TOL
+
+
 def test_full_step_gradient_parity(cuda_store, conv_mode):
-    """Full-size D and G sub-step gradients (R1 and mode-seeking double backward) at batch 4, against the
-    fp64 oracle (criterion: grad_ok).  Losses (first-order quantities) must meet 1e-3 outright."""
+    """Full-size D and G sub-step gradients (R1 and mode-seeking double backward) at batch 4 against the fp64
+    oracle: `check_substep` (masks pinned: 1e-3 on every gradient element; mask flips counted; losses 1e-3)."""
     import gansynth_b200.models as pmodels
     opg, params, ppg = _pair(FULL, 1.0, cuda_store)
     latents, labels, images = seeded_inputs(4, [128, 1024])
     o64 = omodels.GANSynthStep(opg, {n: p.double() for n, p in params.items()}, HYPER)
     model = pmodels.GANSynth(ppg.generator, ppg.discriminator, None, None, {}, HYPER)
-    lc, zc, ic = labels.cuda(), latents.cuda(), images.cuda()
-    model._ensure_optimizers(lc, zc)
+    model._ensure_optimizers(labels.cuda(), latents.cuda())
     for scope in ("discriminator", "generator"):
-        if scope == "discriminator":
-            l64, g64 = o64.discriminator_update(images.double(), labels.double(), latents.double(), apply=False)
-            model._set_trainable(scope)
-            loss = model.discriminator_loss_fn(ic, lc, zc)
-        else:
-            l64, g64 = o64.generator_update(labels.double(), latents.double(), apply=False)
-            model._set_trainable(scope)
-            loss = model.generator_loss_fn(lc, zc)
-        assert abs(float(loss.detach()) - float(l64)) < TOL * max(1.0, abs(float(l64)))
-        names = list(cuda_store.trainable_variables(scope))
-        grads = torch.autograd.grad(loss, [cuda_store.vars[n] for n in names], allow_unused=True)
-        for n, g in zip(names, grads):
-            if g is not None:
-                ok, why = grad_ok(conv_mode, g, g64[n])
-                assert ok, (n, why)
+        check_substep(model, cuda_store, o64, scope, images, labels, latents, torch.float64, conv_mode)
+
+
+def test_full_step_parity_batch8(cuda_store):
+    """The metric's own configuration (BASELINE configs[1]: full size, batch 8 -- batch_stddev groups {0,2,4,6} /
+    {1,3,5,7}), default tensor-core mode, against the fp32 oracle: losses 1e-3, gradients by `check_substep`."""
+    import gansynth_b200.models as pmodels
+    opg, params, ppg = _pair(FULL, 1.0, cuda_store)
+    latents, labels, images = seeded_inputs(8, [128, 1024])
+    o32 = omodels.GANSynthStep(opg, params, HYPER)
+    model = pmodels.GANSynth(ppg.generator, ppg.discriminator, None, None, {}, HYPER)
+    model._ensure_optimizers(labels.cuda(), latents.cuda())
+    for scope in ("discriminator", "generator"):
+        check_substep(model, cuda_store, o32, scope, images, labels, latents, torch.float32, "tc")
 
 
 def test_train_and_generate_entry_points(cuda_store, tmp_path):
