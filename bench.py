@@ -144,46 +144,107 @@ def run_steps(model, batches, device, from_host):
     return h2d, d2h
 
 
-class ConvProfiler(object):
-    """CUDA-event pairs around every convolution-family ABI call inside the timed region (no syncs)."""
+def conv_kernel_label(key):
+    """Which kernel function serves a convolution-family call (the gates of csrc/conv.cu restated), for joining the
+    event-timed algorithmic work with the CUPTI kernel names: (label, CUPTI name prefix)."""
+    form, n, h, w, ci, co, ksize, stride = key
+    if form == "conv_w":
+        if ksize == 3 and ci % 32 == 0 and co % 32 == 0:
+            return "conv_tcw_kernel (filter gradients)", "conv_tcw_kernel"
+        return "filter gradient, 1x1 / 257-channel (SIMT)", None
+    out_ch = co if form == "conv_c" else ci
+    in_ch = ci if form == "conv_c" else co
+    if ksize == 3 and in_ch % 32 == 0 and out_ch % 32 == 0 and out_ch <= 256:
+        if stride == 1:
+            if out_ch in (32, 64) and w >= 128 and h % 8 == 0:
+                return "conv_tck_kernel (3x3 s1, thin layers, kw-stacked)", "conv_tck_kernel"
+            return "conv_tc_kernel<C1> (3x3 s1)", "conv_tc_kernel<0"
+        if form == "conv_c":
+            return "conv_tc_kernel<C2> (3x3 s2 gather)", "conv_tc_kernel<1"
+        return "conv_tc_kernel<T2> (3x3 s2 transposed)", "conv_tc_kernel<2"
+    return "1x1 / 257-channel convolutions (SIMT)", None
+
+
+# backend method -> CUPTI kernel-name prefix, for the HBM-bound elementwise passes whose algorithmic bytes are the
+# tensors they read and write
+ELEMENTWISE_KERNELS = {
+    "mask_mul": "mask_mul4_kernel", "mask_mul_colsum": "mask_mul_colsum_kernel", "col_sum": "col_sum_kernel",
+    "pn_fwd": "pixel_norm_vec_kernel<0", "pn_bwd": "pixel_norm_vec_kernel<1", "pn_bwd_mask_y": "pixel_norm_vec_kernel<3",
+    "pn_bwd_mask": "pixel_norm_vec_kernel<3", "dense_fwd": "dense_fwd_kernel", "dense_dgrad": "dense_dgrad_kernel",
+    "dense_wgrad": "dense_wgrad_kernel", "transpose_inner": "transpose_inner_kernel",
+}
+
+
+class KernelProfiler(object):
+    """CUDA-event pairs around every convolution-family ABI call of an eager pass (no syncs), and the algorithmic
+    bytes (tensors read + written) of the elementwise backend calls."""
 
     def __init__(self, backend):
-        self.backend, self.records, self.orig = backend, [], {}
+        self.backend, self.records, self.ew = backend, [], {}
+        self.patched = []
 
     def __enter__(self):
-        for name in ("conv_c", "conv_t", "conv_w"):
-            fn = getattr(self.backend, name)
-            self.orig[name] = fn
-            setattr(self.backend, name, self._wrap(name, fn))
+        self._patch("_conv", self._wrap_conv(self.backend._conv))
+        self._patch("conv_w", self._wrap_w(self.backend.conv_w))
+        for name in ELEMENTWISE_KERNELS:
+            if hasattr(self.backend, name):
+                self._patch(name, self._wrap_ew(name, getattr(self.backend, name)))
+        if hasattr(self.backend, "pn_bwd_mask_second_y"):
+            self._patch("pn_bwd_mask_second_y", self._wrap_ew("pn_bwd_mask_second_y", self.backend.pn_bwd_mask_second_y))
         return self
 
-    def _wrap(self, name, fn):
-        def wrapped(a, b, *rest, **kw):
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            out = fn(a, b, *rest, **kw)
-            e.record()
-            if name == "conv_w":
-                ksize, stride = rest[0], rest[1]
-                n, h, w, ci = a.shape
-                co = b.shape[3]
-                big_pixels = n * h * w
-            else:
-                ksize, stride = rest[1], rest[2]
-                big = a if name == "conv_c" else out
-                n, h, w = big.shape[:3]
-                ci = a.shape[3] if name == "conv_c" else out.shape[3]
-                co = out.shape[3] if name == "conv_c" else a.shape[3]
-                big_pixels = n * h * w
-            flops = 2.0 * (big_pixels // (stride * stride)) * ksize * ksize * ci * co
-            io_bytes = 4.0 * (a.numel() + out.numel() + b.numel())
-            self.records.append(((name, n, h, w, ci, co, ksize, stride), s, e, flops, io_bytes))
+    def _patch(self, name, fn):
+        setattr(self.backend, name, fn)          # instance attribute shadows the class method
+        self.patched.append(name)
+
+    def _timed(self, key, flops, call):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        out = call()
+        e.record()
+        outs = out if isinstance(out, tuple) else (out,)
+        return out, s, e, outs
+
+    def _wrap_conv(self, fn):
+        def wrapped(name, x, w, bias, ksize, stride, wswap, alpha, act, precise, epi, aux, want_r, eps):
+            out, s, e, outs = self._timed(None, None, lambda: fn(name, x, w, bias, ksize, stride, wswap, alpha, act, precise,
+                                                                 epi, aux, want_r, eps))
+            y = outs[0]
+            form = "conv_c" if name == "gs_conv2d_fwd_ex" else "conv_t"
+            big = x if form == "conv_c" else y
+            n, h, wd = big.shape[:3]
+            ci = x.shape[3] if form == "conv_c" else y.shape[3]
+            co = y.shape[3] if form == "conv_c" else x.shape[3]
+            flops = 2.0 * (n * h * wd // (stride * stride)) * ksize * ksize * ci * co
+            io = 4.0 * (x.numel() + y.numel() + w.numel() + (aux.numel() if aux is not None else 0))
+            self.records.append(((form, n, h, wd, ci, co, ksize, stride), s, e, flops, io))
+            return out
+        return wrapped
+
+    def _wrap_w(self, fn):
+        def wrapped(x, dy, ksize, stride, wswap, alpha):
+            out, s, e, _ = self._timed(None, None, lambda: fn(x, dy, ksize, stride, wswap, alpha))
+            n, h, wd, ci = x.shape
+            co = dy.shape[3]
+            flops = 2.0 * (n * h * wd // (stride * stride)) * ksize * ksize * ci * co
+            self.records.append((("conv_w", n, h, wd, ci, co, ksize, stride), s, e, flops, 4.0 * (x.numel() + dy.numel() + out.numel())))
+            return out
+        return wrapped
+
+    def _wrap_ew(self, name, fn):
+        def wrapped(*a, **k):
+            out = fn(*a, **k)
+            outs = out if isinstance(out, tuple) else (out,)
+            nbytes = 4.0 * sum(t.numel() for t in list(a) + list(outs) if torch.is_tensor(t))
+            rec = self.ew.setdefault(name, dict(bytes=0.0, n=0))
+            rec["bytes"] += nbytes
+            rec["n"] += 1
             return out
         return wrapped
 
     def __exit__(self, *exc):
-        for name, fn in self.orig.items():
-            setattr(self.backend, name, fn)
+        for name in self.patched:
+            delattr(self.backend, name)
 
     def summary(self):
         agg = {}
@@ -193,6 +254,69 @@ class ConvProfiler(object):
             a["ms"] += ms
             a["n"] += 1
         return agg
+
+
+def cupti_kernel_times(model, batches, device):
+    """Kernel time per function name over graph-replayed iterations (CUPTI activity records through torch.profiler;
+    outside the timed region) -> ({name: [launches, microseconds]}, total microseconds)."""
+    import collections
+    import re
+    from torch.profiler import ProfilerActivity, profile
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        run_steps(model, batches, device, False)
+        torch.cuda.synchronize()
+    tot = 0.0
+    for ev in prof.events():
+        if ev.device_type != torch.autograd.DeviceType.CUDA:
+            continue
+        name = re.sub(r"\(.*", "", ev.name.replace("(anonymous namespace)::", "").replace("<unnamed>::", "").replace("void ", ""))
+        us = ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
+        agg[name][0] += 1
+        agg[name][1] += us
+        tot += us
+    return agg, tot
+
+
+def kernel_table(conv, ew, cupti, cupti_total_us, steps_profiled, steps_eager, pk):
+    """One row per kernel FUNCTION: CUPTI time per replayed step joined with the algorithmic FLOP / bytes of the calls
+    it serves (from the eager pass), each against the roofline that bounds it (arithmetic intensity vs the ridge)."""
+    ridge = pk["tf_sustained"] * 1e12 / (pk["hbm"] * 1e9)
+    groups = {}
+    for key, v in conv.items():
+        label, prefix = conv_kernel_label(key)
+        g = groups.setdefault(label, dict(prefix=prefix, flops=0.0, bytes=0.0, calls=0, event_ms=0.0))
+        g["flops"] += v["flops"] * v["n"] / steps_eager
+        g["bytes"] += v["bytes"] * v["n"] / steps_eager
+        g["calls"] += v["n"] / steps_eager
+        g["event_ms"] += v["ms"] / steps_eager
+    for name, v in ew.items():
+        prefix = ELEMENTWISE_KERNELS.get(name, "pixel_norm_vec_kernel<2" if name == "pn_bwd_mask_second_y" else None)
+        g = groups.setdefault(prefix or name, dict(prefix=prefix, flops=0.0, bytes=0.0, calls=0, event_ms=None))
+        g["bytes"] += v["bytes"] / steps_eager
+        g["calls"] += v["n"] / steps_eager
+    rows = []
+    for label, g in groups.items():
+        us = n = None
+        if g["prefix"]:
+            hits = [(k, v) for k, v in cupti.items() if k.startswith(g["prefix"])]
+            if hits:
+                us = sum(v[1] for _, v in hits) / steps_profiled
+                n = sum(v[0] for _, v in hits) / steps_profiled
+        if us is None and g["event_ms"] is not None:
+            us = g["event_ms"] * 1e3          # SIMT convolutions: several kernel names, event time of the eager pass
+        if not us:
+            continue
+        ai = g["flops"] / g["bytes"] if g["bytes"] else 0.0
+        bound = "tensor" if ai >= ridge else "hbm"
+        tf, gbs = g["flops"] / us / 1e6, g["bytes"] / us / 1e3
+        rows.append(dict(kernel=label, launches_per_step=n if n is not None else g["calls"], us_per_step=us,
+                         share_of_kernel_time=us * steps_profiled / cupti_total_us,
+                         gflop_per_step=g["flops"] / 1e9, mbytes_per_step=g["bytes"] / 1e6, flop_per_byte=ai, bound=bound,
+                         tflops=tf, gbs=gbs, frac=(tf / pk["tf_sustained"]) if bound == "tensor" else (gbs / pk["hbm"]),
+                         tensor_frac=tf / pk["tf_sustained"], hbm_frac=gbs / pk["hbm"]))
+    rows.sort(key=lambda r: -r["us_per_step"])
+    return rows
 
 
 def spectral_secondary(device, pk):
@@ -362,13 +486,18 @@ def bench_ours(args):
     barrier()
     ms_e2e = max_over_ranks(start.elapsed_time(end))
 
-    # ---- per-kernel timing: the graph replay cannot be bracketed kernel by kernel, so the same steps run once
-    # more EAGERLY with a CUDA-event pair around every convolution-family ABI call (same inputs, same process)
+    # ---- per-kernel timing: the graph replay cannot be bracketed kernel by kernel, so (1) the same steps run once
+    # more EAGERLY with a CUDA-event pair around every convolution-family ABI call (same inputs, same process), and
+    # (2) two replayed iterations run under CUPTI (torch.profiler) for the time per kernel FUNCTION.  Both are outside
+    # the timed regions above.
+    cupti, cupti_total, cupti_steps = {}, 0.0, min(2, args.steps)
+    if rank == 0:
+        cupti, cupti_total = cupti_kernel_times(model, dev[args.warmup:args.warmup + cupti_steps], device)
     graphs_were = model.use_cuda_graphs
     model.use_cuda_graphs = False
     run_steps(model, dev[:1], device, False)
     barrier()
-    with ConvProfiler(Fn.K) as prof:
+    with KernelProfiler(Fn.K) as prof:
         start.record()
         run_steps(model, dev[args.warmup:], device, False)
         end.record()
@@ -391,20 +520,26 @@ def bench_ours(args):
                 avg = v["ms"] / v["n"]
                 f.write("%-8s %3d %5d %5d %4d %4d %2d %2d %5d %10.3f %9.1f %9.1f %8.0f\n" % (
                     key + (v["n"], v["ms"], avg * 1e3, v["flops"] / (avg * 1e-3) / 1e12, v["bytes"] / (avg * 1e-3) / 1e9)))
-    # one KERNEL per entry: the stride-1 3x3 input-gradient (conv_t) is the forward kernel on flipped weights, so the
-    # two forms of a shape are the same launches as far as an ncu / CUPTI list can tell
-    kernels = {}
+    # per kernel FUNCTION: CUPTI time of the replayed step joined with the algorithmic work of the eager pass
+    table = kernel_table(conv, prof.ew, cupti, cupti_total, cupti_steps, args.steps, pk)
+    conv_rows = [r for r in table if r["gflop_per_step"] > 0]
+    dominant = max(conv_rows, key=lambda r: r["us_per_step"]) if conv_rows else None
+    # the dominant function's heaviest (kernel, shape): per-launch numbers from the event pairs
+    shapes = {}
     for key, v in conv.items():
-        form = key[0]
-        if form in ("conv_c", "conv_t") and key[6] == 3 and key[7] == 1 and key[4] == key[5]:
-            key = ("conv_c",) + key[1:]
-        a = kernels.setdefault(key, dict(ms=0.0, n=0, flops=v["flops"], bytes=v["bytes"]))
+        if dominant is None or conv_kernel_label(key)[0] != dominant["kernel"]:
+            continue
+        a = shapes.setdefault(key[1:] if key[0] != "conv_w" else key, dict(ms=0.0, n=0, flops=v["flops"], bytes=v["bytes"], key=key))
         a["ms"] += v["ms"]
         a["n"] += v["n"]
-    top_key, top = max(kernels.items(), key=lambda kv: kv[1]["ms"])
+    top = max(shapes.values(), key=lambda v: v["ms"])
+    top_key = top["key"]
     conv_ms = sum(v["ms"] for v in conv.values())
     avg_ms = top["ms"] / top["n"]
     achieved_tf = top["flops"] / (avg_ms * 1e-3) / 1e12
+    achieved_gbs = top["bytes"] / (avg_ms * 1e-3) / 1e9
+    ridge = pk["tf_sustained"] * 1e12 / (pk["hbm"] * 1e9)
+    top_bound = "tensor" if top["flops"] / top["bytes"] >= ridge else "hbm"
     line = dict(
         metric="GAN train steps/sec (batch 8/GPU, 128x1024 mel+IF)", value=value, unit="steps/s", n_gpus=world,
         steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
@@ -422,32 +557,49 @@ def bench_ours(args):
         e2e=dict(value=args.steps * world / (ms_e2e / 1e3), unit="steps/s", h2d_bytes_per_step=h2d // args.steps,
                  d2h_bytes_per_step=d2h // args.steps),
         gpu_launches=launches,
-        roofline=dict(bound="tensor", achieved=achieved_tf, peak=pk["tf_sustained"], unit="TFLOP/s",
-                      frac=achieved_tf / pk["tf_sustained"], traffic=NCU_TRAFFIC.get(top_key, (None, None))[0],
+        roofline=dict(bound=top_bound,
+                      achieved=achieved_tf if top_bound == "tensor" else achieved_gbs,
+                      peak=pk["tf_sustained"] if top_bound == "tensor" else pk["hbm"],
+                      unit="TFLOP/s" if top_bound == "tensor" else "GB/s",
+                      frac=(achieved_tf / pk["tf_sustained"]) if top_bound == "tensor" else (achieved_gbs / pk["hbm"]),
+                      traffic=NCU_TRAFFIC.get(top_key, (None, None))[0],
                       traffic_source=NCU_TRAFFIC.get(top_key, (None, "no ncu --set full capture of this kernel/shape"))[1],
-                      kernel="%s n=%d %dx%d ci=%d co=%d k=%d s=%d (tcgen05 bf16x3 implicit GEMM, TMA-fed; forward and "
-                             "stride-1 input-gradient launches of this shape)" % top_key,
+                      kernel="%s; heaviest shape: %s n=%d %dx%d ci=%d co=%d k=%d s=%d" % ((dominant["kernel"],) + top_key),
+                      chosen_by="largest CUPTI time per replayed step among the kernel FUNCTIONS (see `kernels`); the "
+                                "per-launch figures are the heaviest shape of that function",
+                      bound_rule="arithmetic intensity %.0f FLOP/B %s ridge %.0f (sustained bf16 peak / copy bandwidth)" %
+                                 (top["flops"] / top["bytes"], ">=" if top_bound == "tensor" else "<", ridge),
                       timing="CUDA-event pair around every launch of this kernel in an eager pass of the same steps "
                              "(the timed region replays CUDA graphs)",
                       launches_timed=top["n"], avg_launch_ms=avg_ms, algorithmic_flop_per_launch=top["flops"],
-                      io_bytes_per_launch=top["bytes"], hbm_gbs_at_io_bytes=top["bytes"] / (avg_ms * 1e-3) / 1e9,
-                      hbm_frac_at_io_bytes=top["bytes"] / (avg_ms * 1e-3) / 1e9 / pk["hbm"],
-                      # launches per step x event-timed launch duration over the graph-replayed step time: comparable
-                      # with the kernel's share in profiles/launches_*.csv / step_kernels_*.txt
-                      share_of_step=top["ms"] / ms, share_of_eager_step=top["ms"] / ms_eager,
-                      # the family total is dominated by launch-bound small layers whose event pairs include eager
-                      # launch gaps: only meaningful against the eager pass it was measured in
+                      algorithmic_bytes_per_launch=top["bytes"],
+                      tensor_tflops=achieved_tf, tensor_frac=achieved_tf / pk["tf_sustained"],
+                      hbm_gbs=achieved_gbs, hbm_frac=achieved_gbs / pk["hbm"],
+                      function_us_per_step=dominant["us_per_step"], function_share_of_step=dominant["us_per_step"] / (ms / args.steps * 1e3),
+                      share_of_eager_step=top["ms"] / ms_eager,
                       conv_family_share_of_eager_step=conv_ms / ms_eager,
-                      peak_source="%s bf16_tflops_sustained (kernel timed inside a long step)" % pk["source"],
+                      peak_source="%s: bf16_tflops_sustained / hbm_gbs (kernel timed inside a long step)" % pk["source"],
                       step_tflops=ITER_FLOP_PER_SAMPLE * BATCH * value / 1e12,
                       step_frac=ITER_FLOP_PER_SAMPLE * BATCH * value / 1e12 / (pk["tf_sustained"] * world)),
+        kernels=dict(note="per kernel function, per graph-replayed step: CUPTI time (outside the timed region) joined with "
+                          "the algorithmic FLOP and bytes (tensors read + written) of the calls it serves; bf16x3 issues "
+                          "3 MMA passes per algorithmic FLOP, so tensor_frac 0.33 is a saturated pipe",
+                     kernel_time_us_per_step=cupti_total / max(1, cupti_steps), rows=table[:14]),
     )
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count()
-        times = oracle_iteration_time(4, 1, cores)
-        line["cpu_baseline"] = dict(value=0.5 / times[0], unit="steps/s", cores=cores, kind="port",
-                                    sample="one full iteration (D update + G update) of the oracle at batch 4 "
-                                           "(%.1f s), scaled x0.5 to batch 8" % times[0])
+        times = oracle_iteration_time(BATCH, 3, cores)[1:]          # first iteration = warm-up (constants, allocator)
+        line["cpu_baseline"] = dict(value=1.0 / float(np.mean(times)), unit="steps/s", cores=cores, kind="port",
+                                    sample="two full iterations (D update + G update) of the oracle port at batch 8 after "
+                                           "one warm-up iteration (%.1f s each)" % float(np.mean(times)))
+    if args.kernel_table:
+        with open(args.kernel_table, "w") as f:
+            f.write("%-52s %6s %9s %6s %9s %9s %7s %6s %8s %8s %6s\n" % ("kernel function", "n/step", "us/step", "share", "GFLOP", "MB", "FLOP/B", "bound",
+                                                                          "TFLOP/s", "GB/s", "frac"))
+            for r in table:
+                f.write("%-52s %6.0f %9.1f %6.3f %9.1f %9.1f %7.1f %6s %8.1f %8.0f %6.3f\n" % (
+                    r["kernel"][:52], r["launches_per_step"], r["us_per_step"], r["share_of_kernel_time"], r["gflop_per_step"],
+                    r["mbytes_per_step"], r["flop_per_byte"], r["bound"], r["tflops"], r["gbs"], r["frac"]))
     if world == 1 and not args.no_spectral:
         line["secondary"] = spectral_secondary(device, pk)
         line["secondary"]["inference"] = inference_secondary(model, device)
@@ -467,14 +619,17 @@ def bench_reference(args):
         return
     cores = os.cpu_count()
     budget = float(os.environ.get("GS_REF_BUDGET_S", "240"))
-    probe = oracle_iteration_time(4, 1, cores)[0]          # also serves as warm-up
-    total = args.steps + max(0, args.warmup - 1)
-    steps = args.steps if probe * total <= budget else max(1, int(budget / probe) - max(0, args.warmup - 1))
-    times = oracle_iteration_time(4, max(0, args.warmup - 1) + steps, cores)[max(0, args.warmup - 1):]
+    # the configuration itself: batch 8, every step a full iteration.  One warm-up iteration always runs (constants,
+    # allocator); the rest of the requested warm-up and as many of the requested steps as the budget allows follow.
+    probe = oracle_iteration_time(BATCH, 1, cores)[0]
+    extra_warm = max(0, min(args.warmup - 1, 1))
+    steps = max(1, min(args.steps, int(budget / probe) - extra_warm))
+    times = oracle_iteration_time(BATCH, extra_warm + steps, cores)[extra_warm:]
     per = float(np.mean(times))
-    value = 0.5 / per
-    sample = ("each step = one full iteration (D update + G update) of the CPU oracle at batch 4, scaled x0.5 to "
-              "batch 8; %d of the requested %d steps run to stay within %.0f s" % (steps, args.steps, budget))
+    value = 1.0 / per
+    sample = ("each step = one full iteration (D update + G update) of the CPU oracle port at batch 8 on %d threads; "
+              "%d of the requested %d steps timed (%.0f s budget), %d warm-up iteration(s)" %
+              (cores, steps, args.steps, budget, 1 + extra_warm))
     print(json.dumps(dict(
         impl="reference", metric="GAN train steps/sec (batch 8/GPU, 128x1024 mel+IF)", value=value, unit="steps/s",
         n_gpus=world, steps=steps, warmup=args.warmup, ms_per_step=1e3 / value, higher_is_better=True, scaling="weak",
@@ -497,6 +652,7 @@ def main():
                     help="PGGAN growing_level held fixed for the run (default 1.0 = fully grown = BASELINE configs[1]; "
                          "< 63/127 exercises the progressive-growing blend path)")
     ap.add_argument("--conv-table", default=None, help="write per-shape convolution timings of the timed region here")
+    ap.add_argument("--kernel-table", default=None, help="write the per-kernel-function table (also in the JSON line) here")
     args = ap.parse_args()
     # stdout carries ONE JSON line: everything libraries print there meanwhile (NCCL's version banner is a plain
     # printf to stdout at NCCL_DEBUG >= VERSION) is routed to stderr at the file-descriptor level

@@ -20,6 +20,8 @@ SIGNATURES = {
     "gs_conv2d_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P],
     "gs_conv2d_dgrad": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P],
     "gs_conv2d_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
+    "gs_conv2d_fwd_ex": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P, _P, _F, _I, _P],
+    "gs_conv2d_dgrad_ex": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P, _P, _F, _I, _P],
     "gs_conv2d_transpose_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P],
     "gs_conv2d_transpose_dgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
     "gs_conv2d_transpose_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
@@ -46,6 +48,9 @@ SIGNATURES = {
     "gs_pixel_norm_bwd_mask": [_P, _P, _P, _P, _P, _L, _I, _P],
     "gs_pixel_norm_bwd_premask": [_P, _P, _P, _P, _L, _I, _P],
     "gs_pixel_norm_bwd2_masked": [_P, _P, _P, _P, _P, _L, _I, _P],
+    "gs_pixel_norm_bwd_mask_y": [_P, _P, _P, _P, _P, _L, _I, _P],
+    "gs_pixel_norm_bwd_premask_y": [_P, _P, _P, _P, _L, _I, _P],
+    "gs_pixel_norm_bwd2_masked_y": [_P, _P, _P, _P, _P, _L, _I, _P],
     "gs_batch_stddev_fwd": [_P, _P, _I, _L, _I, _F, _P],
     "gs_batch_stddev_bwd": [_P, _P, _P, _I, _L, _I, _F, _P],
     "gs_batch_stddev_bwd2": [_P, _P, _P, _P, _P, _I, _L, _I, _F, _P],

@@ -12,7 +12,19 @@
 #include "tma_host.h"
 #include "gansynth_b200.h"
 
+// elementwise fallbacks of the fused epilogues (elementwise.cu)
+extern "C" int gs_lrelu_mask_mul(const float* v, const float* y, float* out, long long n, void* stream);
+extern "C" int gs_pixel_norm_fwd(const float* a, float* y, float* r, long long rows, int c, float eps, void* stream);
+
 namespace {
+
+// Fused epilogue request of the *_ex entry points (TcEpi of conv_tc.cuh)
+struct Epi {
+  int mode = 0;
+  const float* aux = nullptr;     // MASK: mask source, shaped like the output
+  float* rvec = nullptr;          // PNF: per-pixel 1 / sqrt(mean_c(a^2) + eps)
+  float eps = 0.0f;
+};
 
 int make_geom(ConvGeom& g, int n, int h, int w, int ci, int co, int ksize, int stride, int wswap, float alpha,
               int act) {
@@ -165,7 +177,7 @@ bool tc_ok(int form, int ksize, int kdim, int ndim, int th_dim, int tw_dim) {
 template <int FORM, int KC>
 int launch_tc_impl(const float* x, const float* w, const float* bias, float* y, int n, int h_in, int w_in, int h_out,
                    int w_out, int kdim, int ndim, int w_is_kn, int flip, float alpha, int act, bool cacheable,
-                   cudaStream_t st) {
+                   cudaStream_t st, const Epi& epi, bool* fused) {
   using G = TcGeo<FORM>;
   const size_t wbytes = (size_t)9 * kdim * ndim * 2 * sizeof(__nv_bfloat16);
   GS_CHECK_ARG(wbytes <= g_tc_ws.scratch, "conv_tc: weight of %zu bytes exceeds the scratch slot", wbytes);
@@ -203,9 +215,18 @@ int launch_tc_impl(const float* x, const float* w, const float* bias, float* y, 
       if (ndim % t == 0 && model(t) < 0.8 * model(best)) best = t;
     nt = best;
   }
-  const size_t budget = 222 * 1024 - 1024 - 2 * 16384 - (FORM == TC_C2 ? 2048 : 0);   // alignment slack, output staging, parity table
+  size_t budget = 222 * 1024 - 1024 - 2 * 16384 - (FORM == TC_C2 ? 2048 : 0);   // alignment slack, output staging, parity table
   const size_t a_stage = (size_t)p.pix * KC * 4;
   const size_t raw = (((size_t)p.rpix * KC * 4) + 1023) & ~(size_t)1023;
+  // MASK epilogue: a ring of 16 KB aux tiles comes out of the same budget (3 slots, 2 when the smallest ring
+  // configuration would not fit beside them; else the mask runs as a separate pass)
+  p.aux_k = 0;
+  if (epi.mode == TC_EPI_MASK && !getenv("GS_TC_NO_EPI")) {
+    const size_t minimal = a_stage + raw + 2 * (size_t)4 * KC * 32;
+    for (int k = 3; k >= 2 && !p.aux_k; --k)
+      if (minimal + (size_t)k * 16384 <= budget) p.aux_k = k;
+    budget -= (size_t)p.aux_k * 16384;
+  }
   p.raw_slot_bytes = (uint32_t)raw;
   p.sa = 2;
   p.ds = 2;
@@ -237,6 +258,12 @@ int launch_tc_impl(const float* x, const float* w, const float* bias, float* y, 
     }
   }
   p.cps = nchunks / p.ksplit;
+  // fused epilogue: MASK needs the whole contraction in one CTA, PNF also every output channel of a pixel
+  p.epi = TC_EPI_PLAIN; p.eps = epi.eps; p.rvec = epi.rvec;
+  if (epi.mode == TC_EPI_MASK && p.ksplit == 1 && p.aux_k > 0) p.epi = TC_EPI_MASK;
+  if (epi.mode == TC_EPI_PNF && p.ksplit == 1 && nt == ndim) p.epi = TC_EPI_PNF;
+  if (getenv("GS_TC_NO_EPI")) p.epi = TC_EPI_PLAIN;
+  if (fused) *fused = (p.epi == epi.mode);
   p.b_resident = (p.cps <= TC_MAX_BSTAGES) && (used + (size_t)p.cps * 9 * b_tap <= budget) && !getenv("GS_TC_NO_RESIDENT");
   int tps = 1;
   if (p.b_resident) {
@@ -259,7 +286,7 @@ int launch_tc_impl(const float* x, const float* w, const float* bias, float* y, 
   if (used + a_stage <= budget) { ++p.sa; used += a_stage; }
   p.nbuf = (2 * G::NACC * nt <= 512) ? 2 : 1;
   p.cat = (4 * G::NACC * nt <= 512) && !getenv("GS_TC_NO_CAT");
-  p.nw = (p.nbuf == 2 && getenv("GS_TC_TWO_MMA_WARPS")) ? 2 : 1;   // measured: a second issuing warp buys nothing
+  p.nw = (p.nbuf == 2 && getenv("GS_TC_TWO_MMA_WARPS") && p.epi != TC_EPI_MASK) ? 2 : 1;   // measured: a second issuing warp buys nothing
   if (p.nw == 2) {   // each issuing warp owns every other stage
     p.sa &= ~1;
     if (!p.b_resident) p.sb &= ~1;
@@ -296,24 +323,29 @@ int launch_tc_impl(const float* x, const float* w, const float* bias, float* y, 
     p.wprep = reinterpret_cast<const __nv_bfloat16*>(dst);
   }
   CUtensorMap tmx;
-  TcOutMaps tmy;
+  TcOutMaps tmy, tmaux;
   {
     int rc = gs_make_act_tmap(&tmx, x, n, h_in, w_in, kdim, KC, box_w, p.img, box_h, KC * 4);
     if (rc) return rc;
-    if (FORM == TC_T2) {
-      // four sub-pixel phases: strided views of y, one accumulator each
-      for (int a = 0; a < 4; ++a) {
-        rc = gs_make_act_tmap(&tmy.m[a], y + ((size_t)(a >> 1) * w_out + (a & 1)) * ndim, n, h_out / 2, w_out / 2, ndim, 32, 8,
-                              p.img, p.rows, 128, 2, 2);
+    // output maps and, for the MASK epilogue, identical maps over the mask source
+    for (int which = 0; which < 2; ++which) {
+      TcOutMaps& tm = which ? tmaux : tmy;
+      const float* base = which ? (p.epi == TC_EPI_MASK ? epi.aux : y) : y;
+      if (FORM == TC_T2) {
+        // four sub-pixel phases: strided views of y, one accumulator each
+        for (int a = 0; a < 4; ++a) {
+          rc = gs_make_act_tmap(&tm.m[a], base + ((size_t)(a >> 1) * w_out + (a & 1)) * ndim, n, h_out / 2, w_out / 2, ndim, 32, 8,
+                                p.img, p.rows, 128, 2, 2);
+          if (rc) return rc;
+        }
+      } else {
+        rc = gs_make_act_tmap(&tm.m[0], base, n, h_out, w_out, ndim, 32, 8, p.img, p.rows, 128);
         if (rc) return rc;
+        for (int a = 1; a < 4; ++a) tm.m[a] = tm.m[0];
       }
-    } else {
-      rc = gs_make_act_tmap(&tmy.m[0], y, n, h_out, w_out, ndim, 32, 8, p.img, p.rows, 128);
-      if (rc) return rc;
-      for (int a = 1; a < 4; ++a) tmy.m[a] = tmy.m[0];
     }
   }
-  const size_t smem = used + 1024 + 2 * 16384 + (FORM == TC_C2 ? 2048 : 0);
+  const size_t smem = used + 1024 + 2 * 16384 + (size_t)p.aux_k * 16384 + (FORM == TC_C2 ? 2048 : 0);
   auto kern = conv_tc_kernel<FORM, KC, 9, 0>;
   if (p.cat) kern = tps == 9 ? conv_tc_kernel<FORM, KC, 9, 1> : tps == 3 ? conv_tc_kernel<FORM, KC, 3, 1> : conv_tc_kernel<FORM, KC, 1, 1>;
   else kern = tps == 9 ? conv_tc_kernel<FORM, KC, 9, 0> : tps == 3 ? conv_tc_kernel<FORM, KC, 3, 0> : conv_tc_kernel<FORM, KC, 1, 0>;
@@ -329,7 +361,7 @@ int launch_tc_impl(const float* x, const float* w, const float* bias, float* y, 
   dim3 grid((unsigned)gx, (unsigned)p.n_tiles, (unsigned)p.ksplit);
   const size_t y_count = (size_t)n * h_out * w_out * ndim;
   if (p.ksplit > 1) GS_CUDA(cudaMemsetAsync(y, 0, y_count * sizeof(float), st));
-  kern<<<grid, TC_THREADS, smem, st>>>(tmx, tmy, p);
+  kern<<<grid, TC_THREADS, smem, st>>>(tmx, tmy, tmaux, p);
   GS_CHECK_LAUNCH("conv_tc");
   if (p.ksplit > 1 && act == 1) return gs_lrelu(y, y, (long long)y_count, st);
   return GS_OK;
@@ -342,7 +374,7 @@ bool tck_ok(int h, int w, int kdim, int ndim) {
 }
 
 int launch_tck(const float* x, const float* w, const float* bias, float* y, int n, int h, int wd, int kdim, int ndim,
-               int w_is_kn, int flip, float alpha, int act, bool cacheable, cudaStream_t st) {
+               int w_is_kn, int flip, float alpha, int act, bool cacheable, cudaStream_t st, const Epi& epi, bool* fused) {
   const size_t wbytes = (size_t)9 * kdim * ndim * 2 * sizeof(__nv_bfloat16);
   GS_CHECK_ARG(wbytes <= g_tc_ws.scratch, "conv_tck: weight of %zu bytes exceeds the scratch slot", wbytes);
   if (!g_tc_ws.buf) GS_CUDA(cudaMalloc(&g_tc_ws.buf, g_tc_ws.scratch + g_tc_ws.cache));
@@ -350,10 +382,22 @@ int launch_tck(const float* x, const float* w, const float* bias, float* y, int 
   p.bias = bias; p.n_img = n; p.h = h; p.w = wd; p.kdim = kdim; p.nt = ndim; p.alpha = alpha; p.act = act;
   p.tiles_h = h / 8; p.tiles_w = (wd + 13) / 14; p.ntiles = n * p.tiles_h * p.tiles_w;
   p.cat = (6 * ndim <= 256) && !getenv("GS_TC_NO_CAT");
+  p.epi = getenv("GS_TC_NO_EPI") ? TC_EPI_PLAIN : epi.mode;
+  p.eps = epi.eps; p.rvec = epi.rvec;
   const int nchunks = kdim / 32;
-  const size_t budget = 222 * 1024 - 1024 - 2 * TCK_OUT;
+  size_t budget = 222 * 1024 - 1024 - 2 * TCK_OUT;
   const size_t a_stage = 2 * 4 * TCK_PIX * 16, raw = TCK_RAW;
   const size_t b_row = (size_t)4 * 6 * ndim * 16;
+  // MASK epilogue: ring of aux tiles (see launch_tc_impl); at least one output tile's worth of chunks
+  p.aux_k = 0;
+  if (p.epi == TC_EPI_MASK) {
+    const size_t minimal = 2 * a_stage + 2 * raw + 3 * b_row;
+    for (int k = 3; k >= 2 && !p.aux_k; --k)
+      if (minimal + (size_t)k * TCK_OUT <= budget) p.aux_k = k;
+    if (!p.aux_k) p.epi = TC_EPI_PLAIN;
+    budget -= (size_t)p.aux_k * TCK_OUT;
+  }
+  if (fused) *fused = (p.epi == epi.mode);
   p.sa = 2; p.ds = 2;
   size_t used = p.sa * a_stage + p.ds * raw;
   int tps = 1;
@@ -397,23 +441,29 @@ int launch_tck(const float* x, const float* w, const float* bias, float* y, int 
     }
     p.wprep = reinterpret_cast<const __nv_bfloat16*>(dst);
   }
-  CUtensorMap tmx, tmy;
+  CUtensorMap tmx, tmy, tmaux;
   int rc = gs_make_act_tmap(&tmx, x, n, h, wd, kdim, 32, 16, 1, 10, 128);
   if (rc) return rc;
   rc = gs_make_act_tmap(&tmy, y, n, h, wd, ndim, 32, 14, 1, 8, 128);
   if (rc) return rc;
-  auto kern = conv_tck_kernel<3, 1>;
-  if (p.cat) kern = tps == 3 ? conv_tck_kernel<3, 1> : conv_tck_kernel<1, 1>;
-  else kern = tps == 3 ? conv_tck_kernel<3, 0> : conv_tck_kernel<1, 0>;
-  static bool attr[4] = {false, false, false, false};
-  const int ai = (tps == 3 ? 0 : 1) + 2 * p.cat;
+  rc = gs_make_act_tmap(&tmaux, p.epi == TC_EPI_MASK ? epi.aux : y, n, h, wd, ndim, 32, 14, 1, 8, 128);
+  if (rc) return rc;
+  using TckKernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TckParams);
+  // [epilogue][cat][tps == 3]
+  static const TckKernel kerns[3][2][2] = {
+      {{conv_tck_kernel<1, 0, 0>, conv_tck_kernel<3, 0, 0>}, {conv_tck_kernel<1, 1, 0>, conv_tck_kernel<3, 1, 0>}},
+      {{conv_tck_kernel<1, 0, 1>, conv_tck_kernel<3, 0, 1>}, {conv_tck_kernel<1, 1, 1>, conv_tck_kernel<3, 1, 1>}},
+      {{conv_tck_kernel<1, 0, 2>, conv_tck_kernel<3, 0, 2>}, {conv_tck_kernel<1, 1, 2>, conv_tck_kernel<3, 1, 2>}}};
+  TckKernel kern = kerns[p.epi][p.cat ? 1 : 0][tps == 3 ? 1 : 0];
+  static bool attr[12] = {false};
+  const int ai = (p.epi * 2 + (p.cat ? 1 : 0)) * 2 + (tps == 3 ? 1 : 0);
   if (!attr[ai]) {
     GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
     attr[ai] = true;
   }
   int gx = gs_num_sms();
   if (gx > p.ntiles) gx = p.ntiles;
-  kern<<<gx, TCK_THREADS, used + 1024 + 2 * TCK_OUT, st>>>(tmx, tmy, p);
+  kern<<<gx, TCK_THREADS, used + 1024 + 2 * TCK_OUT + (size_t)p.aux_k * TCK_OUT, st>>>(tmx, tmy, tmaux, p);
   GS_CHECK_LAUNCH("conv_tck");
   return GS_OK;
 }
@@ -424,13 +474,13 @@ int launch_tck(const float* x, const float* w, const float* bias, float* y, int 
 template <int FORM>
 int launch_tc(const float* x, const float* w, const float* bias, float* y, int n, int h_in, int w_in, int h_out,
               int w_out, int kdim, int ndim, int w_is_kn, int flip, float alpha, int act, bool cacheable,
-              cudaStream_t st) {
+              cudaStream_t st, const Epi& epi = Epi(), bool* fused = nullptr) {
   if (FORM == TC_C1 && tck_ok(h_out, w_out, kdim, ndim))
-    return launch_tck(x, w, bias, y, n, h_out, w_out, kdim, ndim, w_is_kn, flip, alpha, act, cacheable, st);
+    return launch_tck(x, w, bias, y, n, h_out, w_out, kdim, ndim, w_is_kn, flip, alpha, act, cacheable, st, epi, fused);
   // the stride-2 gather form stages ~4x the pixels of the others: 16-channel chunks keep the rings in budget
   if (FORM == TC_C2)
-    return launch_tc_impl<FORM, 16>(x, w, bias, y, n, h_in, w_in, h_out, w_out, kdim, ndim, w_is_kn, flip, alpha, act, cacheable, st);
-  return launch_tc_impl<FORM, 32>(x, w, bias, y, n, h_in, w_in, h_out, w_out, kdim, ndim, w_is_kn, flip, alpha, act, cacheable, st);
+    return launch_tc_impl<FORM, 16>(x, w, bias, y, n, h_in, w_in, h_out, w_out, kdim, ndim, w_is_kn, flip, alpha, act, cacheable, st, epi, fused);
+  return launch_tc_impl<FORM, 32>(x, w, bias, y, n, h_in, w_in, h_out, w_out, kdim, ndim, w_is_kn, flip, alpha, act, cacheable, st, epi, fused);
 }
 
 // filter-gradient form on the tensor cores
@@ -534,9 +584,25 @@ extern "C" int gs_conv_weight_cache_reset(void) {
   return GS_OK;
 }
 
-extern "C" int gs_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, int n, int h, int wd,
-                             int ci, int co, int ksize, int stride, int wswap, float alpha, int act, int impl,
-                             void* stream) {
+namespace {
+// the un-fused form of an epilogue request, in place on the finished convolution output
+int epi_fallback(const Epi& epi, float* y, long long pixels, int channels, cudaStream_t st) {
+  if (epi.mode == TC_EPI_MASK) return gs_lrelu_mask_mul(y, epi.aux, y, pixels * channels, st);
+  if (epi.mode == TC_EPI_PNF) return gs_pixel_norm_fwd(y, y, epi.rvec, pixels, channels, epi.eps, st);
+  return GS_OK;
+}
+
+int check_epi(const Epi& epi, const float* bias, int act) {
+  GS_CHECK_ARG(epi.mode >= 0 && epi.mode <= 2, "conv: unknown epilogue %d", epi.mode);
+  GS_CHECK_ARG(epi.mode != TC_EPI_MASK || (epi.aux && !bias && act == 0), "conv: the mask epilogue takes a mask source, no bias, no activation");
+  GS_CHECK_ARG(epi.mode != TC_EPI_PNF || (epi.rvec && act == 1), "conv: the pixel-norm epilogue needs rvec and act = 1 (leaky relu)");
+  return GS_OK;
+}
+
+int conv_fwd_impl(const float* x, const float* w, const float* bias, float* y, int n, int h, int wd,
+                  int ci, int co, int ksize, int stride, int wswap, float alpha, int act, int impl,
+                  void* stream, const Epi& epi, bool* fused) {
+  *fused = false;
   ConvGeom g;
   int rc = make_geom(g, n, h, wd, ci, co, ksize, stride, wswap, alpha, act);
   if (rc) return rc;
@@ -551,8 +617,8 @@ extern "C" int gs_conv2d_fwd(const float* x, const float* w, const float* bias, 
     const bool tcok = tc_ok(form, ksize, ci, co, g.oh, g.ow);
     GS_CHECK_ARG(!(impl == 3 && !tcok), "conv2d_fwd: tensor-core kernel does not cover this shape");
     if (impl == 3 || (impl == 0 && tcok && tc_auto_enabled())) {
-      if (stride == 1) return launch_tc<TC_C1>(x, w, bias, y, n, h, wd, g.oh, g.ow, ci, co, !g.wswap, 0, alpha, act, cacheable, st);
-      return launch_tc<TC_C2>(x, w, bias, y, n, h, wd, g.oh, g.ow, ci, co, !g.wswap, 0, alpha, act, cacheable, st);
+      if (stride == 1) return launch_tc<TC_C1>(x, w, bias, y, n, h, wd, g.oh, g.ow, ci, co, !g.wswap, 0, alpha, act, cacheable, st, epi, fused);
+      return launch_tc<TC_C2>(x, w, bias, y, n, h, wd, g.oh, g.ow, ci, co, !g.wswap, 0, alpha, act, cacheable, st, epi, fused);
     }
   }
   if (impl != 1 && ksize == 1 && stride == 1) {
@@ -575,9 +641,33 @@ extern "C" int gs_conv2d_fwd(const float* x, const float* w, const float* bias, 
   return launch_c<2, 64>(x, w, bias, y, n, h, wd, ci, co, g.oh, g.ow, g.pb, kn, 0, alpha, act, st);
 }
 
-extern "C" int gs_conv2d_dgrad(const float* dy, const float* w, const float* bias, float* dx, int n, int h, int wd,
-                               int ci, int co, int ksize, int stride, int wswap, float alpha, int act, int impl,
-                               void* stream) {
+}  // namespace
+
+extern "C" int gs_conv2d_fwd_ex(const float* x, const float* w, const float* bias, float* y, int n, int h, int wd, int ci,
+                                int co, int ksize, int stride, int wswap, float alpha, int act, int epi_mode,
+                                const float* aux, float* rvec, float eps, int impl, void* stream) {
+  Epi epi;
+  epi.mode = epi_mode; epi.aux = aux; epi.rvec = rvec; epi.eps = eps;
+  int rc = check_epi(epi, bias, act);
+  if (rc) return rc;
+  bool fused = false;
+  rc = conv_fwd_impl(x, w, bias, y, n, h, wd, ci, co, ksize, stride, wswap, alpha, act, impl, stream, epi, &fused);
+  if (rc || fused) return rc;
+  return epi_fallback(epi, y, (long long)n * (h / stride) * (wd / stride), co, (cudaStream_t)stream);
+}
+
+extern "C" int gs_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, int n, int h, int wd,
+                             int ci, int co, int ksize, int stride, int wswap, float alpha, int act, int impl,
+                             void* stream) {
+  bool fused = false;
+  return conv_fwd_impl(x, w, bias, y, n, h, wd, ci, co, ksize, stride, wswap, alpha, act, impl, stream, Epi(), &fused);
+}
+
+namespace {
+int conv_dgrad_impl(const float* dy, const float* w, const float* bias, float* dx, int n, int h, int wd,
+                    int ci, int co, int ksize, int stride, int wswap, float alpha, int act, int impl,
+                    void* stream, const Epi& epi, bool* fused) {
+  *fused = false;
   ConvGeom g;
   int rc = make_geom(g, n, h, wd, ci, co, ksize, stride, wswap, alpha, act);
   if (rc) return rc;
@@ -593,8 +683,8 @@ extern "C" int gs_conv2d_dgrad(const float* dy, const float* w, const float* bia
     const bool tcok = stride == 1 ? tc_ok(form, ksize, co, ci, h, wd) : tc_ok(form, ksize, co, ci, g.oh, g.ow);
     GS_CHECK_ARG(!(impl == 3 && !tcok), "conv2d_dgrad: tensor-core kernel does not cover this shape");
     if (impl == 3 || (impl == 0 && tcok && tc_auto_enabled())) {
-      if (stride == 1) return launch_tc<TC_C1>(dy, w, bias, dx, n, h, wd, h, wd, co, ci, g.wswap, 1, alpha, act, cacheable, st);
-      return launch_tc<TC_T2>(dy, w, bias, dx, n, g.oh, g.ow, h, wd, co, ci, g.wswap, 0, alpha, act, cacheable, st);
+      if (stride == 1) return launch_tc<TC_C1>(dy, w, bias, dx, n, h, wd, h, wd, co, ci, g.wswap, 1, alpha, act, cacheable, st, epi, fused);
+      return launch_tc<TC_T2>(dy, w, bias, dx, n, g.oh, g.ow, h, wd, co, ci, g.wswap, 0, alpha, act, cacheable, st, epi, fused);
     }
   }
   if (impl != 1 && ksize == 1 && stride == 1) {
@@ -622,6 +712,28 @@ extern "C" int gs_conv2d_dgrad(const float* dy, const float* w, const float* bia
   }
   if (ci <= 32) return launch_t2<32>(dy, w, bias, dx, n, g.oh, g.ow, co, ci, kn, alpha, act, st);
   return launch_t2<64>(dy, w, bias, dx, n, g.oh, g.ow, co, ci, kn, alpha, act, st);
+}
+
+}  // namespace
+
+extern "C" int gs_conv2d_dgrad_ex(const float* dy, const float* w, const float* bias, float* dx, int n, int h, int wd,
+                                  int ci, int co, int ksize, int stride, int wswap, float alpha, int act, int epi_mode,
+                                  const float* aux, float* rvec, float eps, int impl, void* stream) {
+  Epi epi;
+  epi.mode = epi_mode; epi.aux = aux; epi.rvec = rvec; epi.eps = eps;
+  int rc = check_epi(epi, bias, act);
+  if (rc) return rc;
+  bool fused = false;
+  rc = conv_dgrad_impl(dy, w, bias, dx, n, h, wd, ci, co, ksize, stride, wswap, alpha, act, impl, stream, epi, &fused);
+  if (rc || fused) return rc;
+  return epi_fallback(epi, dx, (long long)n * h * wd, ci, (cudaStream_t)stream);
+}
+
+extern "C" int gs_conv2d_dgrad(const float* dy, const float* w, const float* bias, float* dx, int n, int h, int wd,
+                               int ci, int co, int ksize, int stride, int wswap, float alpha, int act, int impl,
+                               void* stream) {
+  bool fused = false;
+  return conv_dgrad_impl(dy, w, bias, dx, n, h, wd, ci, co, ksize, stride, wswap, alpha, act, impl, stream, Epi(), &fused);
 }
 
 extern "C" int gs_conv2d_wgrad(const float* x, const float* dy, float* dw, int n, int h, int wd, int ci, int co,

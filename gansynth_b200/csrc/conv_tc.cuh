@@ -93,7 +93,16 @@ struct TcParams {
   uint32_t raw_slot_bytes;        // 1024-byte aligned
   int ksplit, cps;                // split-K: grid.z CTAs per (tile, channel tile), each `cps` channel chunks; partial
                                   // sums meet in y through TMA reduce-add (y pre-zeroed, activation applied afterwards)
+  // fused epilogues (TcEpi).  MASK: y = lrelu'(aux) * alpha * conv (aux: a tensor shaped like y; its tiles arrive
+  // through `tmaux` in a ring of `aux_k` 16 KB slots filled by the otherwise idle second issue warp).  PNF: y =
+  // pixel_norm(lrelu(alpha * conv + bias)) over ALL output channels (needs nt == ndim, ksplit == 1),
+  // rvec[pixel] = 1 / sqrt(mean_c(a^2) + eps).
+  int epi, aux_k;
+  float eps;
+  float* rvec;                    // [n, h_out, w_out]
 };
+
+enum TcEpi { TC_EPI_PLAIN = 0, TC_EPI_MASK = 1, TC_EPI_PNF = 2 };
 
 // Output tensor maps: one per accumulator (sub-pixel phase of the transposed form; a strided view of y)
 struct TcOutMaps {
@@ -105,6 +114,7 @@ constexpr int TC_MMA_WARP0 = 14, TC_MMA_WARPS = 2;
 constexpr int TC_CONV_WARPS = 8;
 constexpr int TC_MAX_STAGES = 4;       // raw and operand rings
 constexpr int TC_MAX_BSTAGES = 24;     // weight ring (all (chunk, tap group) blocks when resident)
+constexpr int TC_MAX_AUX = 4;          // aux ring of the MASK epilogue
 
 // Weight pre-pass: W_eff[tap][k][n] (k = contraction channel, n = output channel) -> bf16 split blocks
 // [n / nt][k / KC][tap][q][split][n % nt][e], value index k = KC*kc + 8*q + e.  w_is_kn: weight memory is
@@ -140,13 +150,14 @@ __global__ void conv_tc_prep_kernel(const float* __restrict__ w, __nv_bfloat16* 
 }
 
 template <int FORM, int KC, int TPS, int CAT>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcOutMaps tmy, const TcParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcOutMaps tmy,
+                                                                const __grid_constant__ TcOutMaps tmaux, const TcParams p) {
   using G = TcGeo<FORM>;
   constexpr int Q = KC / 8;               // 16-byte channel planes per split term
   extern __shared__ unsigned char tc_smem_raw[];
   __shared__ uint64_t raw_full[TC_MAX_STAGES], raw_empty[TC_MAX_STAGES], a_full[TC_MAX_STAGES], a_empty[TC_MAX_STAGES];
   __shared__ uint64_t b_full[TC_MAX_BSTAGES], b_empty[TC_MAX_BSTAGES];
-  __shared__ uint64_t acc_full[2], acc_empty[2];
+  __shared__ uint64_t acc_full[2], acc_empty[2], aux_full[TC_MAX_AUX], aux_empty[TC_MAX_AUX];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_s[256];
 
@@ -159,7 +170,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   // the swizzled TMA destination needs 1024-byte alignment
   unsigned char* tc_smem = tc_smem_raw + ((1024u - (tc::smem_u32(tc_smem_raw) & 1023u)) & 1023u);
   unsigned char* out_smem = tc_smem;                        // 2 x [128 pixels][32 channels] fp32, 128B-swizzled
-  unsigned char* raw_smem = tc_smem + 2 * 16384;
+  unsigned char* aux_smem = tc_smem + 2 * 16384;            // aux_k x [128 pixels][32 channels] fp32, 128B-swizzled
+  unsigned char* raw_smem = aux_smem + (size_t)p.aux_k * 16384;
   unsigned char* a_smem = raw_smem + (size_t)p.ds * p.raw_slot_bytes;
   unsigned char* b_smem = a_smem + (size_t)p.sa * a_stage_bytes;
   uint16_t* dst_tab = reinterpret_cast<uint16_t*>(b_smem + (size_t)p.sb * b_stage_bytes);   // TC_C2 only
@@ -174,6 +186,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     for (int s = 0; s < p.sa; ++s) { tc::mbar_init(&a_full[s], TC_CONV_WARPS * 32); tc::mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < p.sb; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { tc::mbar_init(&acc_full[s], 1); tc::mbar_init(&acc_empty[s], 128); }
+    for (int s = 0; s < TC_MAX_AUX; ++s) { tc::mbar_init(&aux_full[s], 1); tc::mbar_init(&aux_empty[s], 128); }
     tc::mbar_fence_init();
   }
   for (int c = tid; c < p.nt; c += TC_THREADS) bias_s[c] = (p.bias && blockIdx.z == 0) ? p.bias[blockIdx.y * p.nt + c] : 0.0f;
@@ -189,6 +202,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   if (warp == 12 && lane == 0) {
     tc::prefetch_tmap(&tmx);
     for (int a = 0; a < G::NACC; ++a) tc::prefetch_tmap(&tmy.m[a]);
+    if (p.epi == TC_EPI_MASK)
+      for (int a = 0; a < G::NACC; ++a) tc::prefetch_tmap(&tmaux.m[a]);
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -393,6 +408,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
         if (p.b_resident) b_ready = true;
       }
+    } else if (p.epi == TC_EPI_MASK && lane == 0) {
+      // ============================== aux tiles of the MASK epilogue (this warp issues no MMAs) ===========
+      // one TMA box per (tile, accumulator, 32-channel chunk), in the order the epilogue consumes them
+      int slot = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        int t = tile;
+        const int tw_ = t % p.tiles_w;
+        t /= p.tiles_w;
+        const int th_ = t % p.tiles_h;
+        const int img0 = (t / p.tiles_h) * p.img;
+        for (int a = 0; a < G::NACC; ++a)
+          for (int c0 = 0; c0 < p.nt; c0 += 32) {
+            tc::mbar_wait(&aux_empty[slot], ph ^ 1u);
+            tc::mbar_arrive_expect_tx(&aux_full[slot], 16384u);
+            tc::tma_load_4d(aux_smem + (size_t)slot * 16384, &tmaux.m[a], n0 + c0, tw_ * 8, img0, th_ * p.rows, &aux_full[slot]);
+            if (++slot == p.aux_k) { slot = 0; ph ^= 1u; }
+          }
+      }
     }
   } else if (warp < 4) {
     // ============================== epilogue: TMEM -> alpha, bias, leaky-relu -> staging -> TMA store =====
@@ -405,7 +439,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     unsigned char* my_row0 = out_smem + (size_t)m * 128;
     const int sw = m & 7;
-    int buf = 0;
+    const int epi = p.epi;
+    // pixel of this thread inside a tile: group g = m / 8 = row * img + slot, column m % 8
+    const int trow = (m >> 3) / p.img, tslot = (m >> 3) - trow * p.img, tcol = m & 7;
+    const float inv_nt = 1.0f / (float)p.nt;
+    int aslot = 0;
+    uint32_t aph = 0, seq = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       int t = tile;
       const int tw_ = t % p.tiles_w;
@@ -416,9 +455,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       tc::tc_fence_after();
 #pragma unroll 1
       for (int a = 0; a < G::NACC; ++a) {
-#pragma unroll 1
-        for (int c0 = 0; c0 < p.nt; c0 += 32) {
-          float v[32];
+        float rscale = 1.0f;
+        float v[32];
+        bool have_v = false;
+        auto load_chunk = [&](int c0) {
           tc::tmem_ld32(tmem_base + lane_base + (uint32_t)(ab * acc_cols + a * acc_w + c0), v);
           if (CAT) {
             float v2[32];
@@ -426,15 +466,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] += v2[j];
           }
-          unsigned char* row = my_row0 + (size_t)buf * 16384;
+        };
+        if (epi == TC_EPI_PNF) {
+          // mean square of the activated outputs of this pixel over all channels (one chunk: kept in registers)
+          float ss = 0.0f;
+#pragma unroll 1
+          for (int c0 = 0; c0 < p.nt; c0 += 32) {
+            load_chunk(c0);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 bv = *reinterpret_cast<const float4*>(&bias_s[c0 + j]);
-            float4 o;
-            o.x = fmaf(v[j + 0], p.alpha, bv.x); o.y = fmaf(v[j + 1], p.alpha, bv.y);
-            o.z = fmaf(v[j + 2], p.alpha, bv.z); o.w = fmaf(v[j + 3], p.alpha, bv.w);
-            if (p.act == 1 && p.ksplit == 1) { o.x = gs_lrelu(o.x); o.y = gs_lrelu(o.y); o.z = gs_lrelu(o.z); o.w = gs_lrelu(o.w); }
-            *reinterpret_cast<float4*>(row + ((((j >> 2) ^ sw)) << 4)) = o;
+            for (int j = 0; j < 32; ++j) {
+              const float o = gs_lrelu(fmaf(v[j], p.alpha, bias_s[c0 + j]));
+              ss = fmaf(o, o, ss);
+            }
+          }
+          have_v = (p.nt == 32);
+          rscale = 1.0f / sqrtf(ss * inv_nt + p.eps);
+          const int pn = img0 + tslot;
+          if (pn < p.n_img) {
+            int py = th_ * p.rows + trow, px = tw_ * 8 + tcol;
+            if (FORM == TC_T2) { py = 2 * py + (a >> 1); px = 2 * px + (a & 1); }
+            p.rvec[((size_t)pn * p.h_out + py) * p.w_out + px] = rscale;
+          }
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < p.nt; c0 += 32, ++seq) {
+          if (!have_v) load_chunk(c0);
+          have_v = false;
+          const uint32_t buf = seq & 1u;
+          unsigned char* row = my_row0 + (size_t)buf * 16384;
+          if (epi == TC_EPI_MASK) {
+            tc::mbar_wait(&aux_full[aslot], aph);
+            const unsigned char* arow = aux_smem + (size_t)aslot * 16384 + (size_t)m * 128;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 ax = *reinterpret_cast<const float4*>(arow + ((((j >> 2) ^ sw)) << 4));
+              float4 o;
+              o.x = v[j + 0] * p.alpha * gs_lrelu_slope(ax.x); o.y = v[j + 1] * p.alpha * gs_lrelu_slope(ax.y);
+              o.z = v[j + 2] * p.alpha * gs_lrelu_slope(ax.z); o.w = v[j + 3] * p.alpha * gs_lrelu_slope(ax.w);
+              *reinterpret_cast<float4*>(row + ((((j >> 2) ^ sw)) << 4)) = o;
+            }
+            tc::mbar_arrive(&aux_empty[aslot]);
+            if (++aslot == p.aux_k) { aslot = 0; aph ^= 1u; }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = *reinterpret_cast<const float4*>(&bias_s[c0 + j]);
+              float4 o;
+              o.x = fmaf(v[j + 0], p.alpha, bv.x); o.y = fmaf(v[j + 1], p.alpha, bv.y);
+              o.z = fmaf(v[j + 2], p.alpha, bv.z); o.w = fmaf(v[j + 3], p.alpha, bv.w);
+              if (p.act == 1 && p.ksplit == 1) { o.x = gs_lrelu(o.x); o.y = gs_lrelu(o.y); o.z = gs_lrelu(o.z); o.w = gs_lrelu(o.w); }
+              if (epi == TC_EPI_PNF) { o.x *= rscale; o.y *= rscale; o.z *= rscale; o.w *= rscale; }
+              *reinterpret_cast<float4*>(row + ((((j >> 2) ^ sw)) << 4)) = o;
+            }
           }
           tc::fence_proxy_async();
           // the store that used the OTHER staging buffer must have finished reading it before anyone gets
@@ -446,7 +529,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             else tc::tma_store_4d(&tmy.m[a], out_smem + (size_t)buf * 16384, n0 + c0, tw_ * 8, img0, th_ * p.rows);
             tc::bulk_commit();
           }
-          buf ^= 1;
         }
       }
       tc::tc_fence_before();

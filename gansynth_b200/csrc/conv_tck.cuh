@@ -32,6 +32,11 @@ struct TckParams {
   int tiles_h, tiles_w, ntiles;
   int sa, sb, ds;                 // ring depths: operand stages, weight stages, raw slots
   int b_resident, cat, tmem_cols;
+  // fused epilogues (TcEpi of conv_tc.cuh): MASK reads `aux` (shaped like y) through `tmaux` into a ring of `aux_k`
+  // 16 KB slots filled by warp 15; PNF writes rvec
+  int epi, aux_k;
+  float eps;
+  float* rvec;                    // [n, h, w]
 };
 
 constexpr int TCK_PIX = 160;                       // staged = raw pixels per tile (10 rows x 16 columns)
@@ -67,15 +72,16 @@ __global__ void conv_tck_prep_kernel(const float* __restrict__ w, __nv_bfloat16*
   }
 }
 
-// TPS: filter rows (kh) per weight stage: 3 (one stage per chunk) or 1
-template <int TPS, int CAT>
+// TPS: filter rows (kh) per weight stage: 3 (one stage per chunk) or 1; EPI: TcEpi (compiled in: the plain epilogue
+// keeps its instruction count)
+template <int TPS, int CAT, int EPI>
 __global__ void __launch_bounds__(TCK_THREADS, 1) conv_tck_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
-                                                                 const TckParams p) {
+                                                                 const __grid_constant__ CUtensorMap tmaux, const TckParams p) {
   constexpr int KC = 32, Q = 4;
   extern __shared__ unsigned char tck_smem_raw[];
   __shared__ uint64_t raw_full[TC_MAX_STAGES], raw_empty[TC_MAX_STAGES], a_full[TC_MAX_STAGES], a_empty[TC_MAX_STAGES];
   __shared__ uint64_t b_full[TC_MAX_BSTAGES], b_empty[TC_MAX_BSTAGES];
-  __shared__ uint64_t acc_full[2], acc_empty[2];
+  __shared__ uint64_t acc_full[2], acc_empty[2], aux_full[TC_MAX_AUX], aux_empty[TC_MAX_AUX];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_s[64];
 
@@ -87,7 +93,8 @@ __global__ void __launch_bounds__(TCK_THREADS, 1) conv_tck_kernel(const __grid_c
   const uint32_t b_stage_bytes = (uint32_t)TPS * b_row_bytes;
   unsigned char* smem = tck_smem_raw + ((1024u - (tc::smem_u32(tck_smem_raw) & 1023u)) & 1023u);
   unsigned char* out_smem = smem;                                   // 2 staging tiles
-  unsigned char* raw_smem = smem + 2 * TCK_OUT;
+  unsigned char* aux_smem = smem + 2 * TCK_OUT;                     // aux_k slots of TCK_OUT bytes (MASK epilogue)
+  unsigned char* raw_smem = aux_smem + (size_t)p.aux_k * TCK_OUT;
   unsigned char* a_smem = raw_smem + (size_t)p.ds * TCK_RAW;
   unsigned char* b_smem = a_smem + (size_t)p.sa * a_stage_bytes;
   const int nchunks = p.kdim / KC;
@@ -98,11 +105,16 @@ __global__ void __launch_bounds__(TCK_THREADS, 1) conv_tck_kernel(const __grid_c
     for (int s = 0; s < p.sa; ++s) { tc::mbar_init(&a_full[s], TC_CONV_WARPS * 32); tc::mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < p.sb; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { tc::mbar_init(&acc_full[s], 1); tc::mbar_init(&acc_empty[s], 128); }
+    for (int s = 0; s < TC_MAX_AUX; ++s) { tc::mbar_init(&aux_full[s], 1); tc::mbar_init(&aux_empty[s], 128); }
     tc::mbar_fence_init();
   }
   for (int c = tid; c < p.nt; c += TCK_THREADS) bias_s[c] = p.bias ? p.bias[c] : 0.0f;
   if (warp == TC_MMA_WARP0) tc::tmem_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
-  if (warp == 12 && lane == 0) { tc::prefetch_tmap(&tmx); tc::prefetch_tmap(&tmy); }
+  if (warp == 12 && lane == 0) {
+    tc::prefetch_tmap(&tmx);
+    tc::prefetch_tmap(&tmy);
+    if (EPI == TC_EPI_MASK) tc::prefetch_tmap(&tmaux);
+  }
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -262,6 +274,25 @@ __global__ void __launch_bounds__(TCK_THREADS, 1) conv_tck_kernel(const __grid_c
       if (++ab == 2) { ab = 0; pacc ^= 1u; }
       if (p.b_resident) b_ready = true;
     }
+  } else if (warp == 15) {
+    // ============================== aux tiles of the MASK epilogue: one TMA box per (tile, chunk) ==========
+    if (EPI == TC_EPI_MASK && lane == 0) {
+      int slot = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        int t = tile;
+        const int tw_ = t % p.tiles_w;
+        t /= p.tiles_w;
+        const int th_ = t % p.tiles_h;
+        const int n = t / p.tiles_h;
+        for (int c0 = 0; c0 < p.nt; c0 += 32) {
+          tc::mbar_wait(&aux_empty[slot], ph ^ 1u);
+          tc::mbar_arrive_expect_tx(&aux_full[slot], 14336u);
+          tc::tma_load_4d(aux_smem + (size_t)slot * TCK_OUT, &tmaux, c0, tw_ * 14, n, th_ * 8, &aux_full[slot]);
+          if (++slot == p.aux_k) { slot = 0; ph ^= 1u; }
+        }
+      }
+    }
   } else if (warp < 4 || warp >= 16) {
     // ============================== epilogue: TMEM -> shift-add over kw -> alpha, bias, leaky-relu -> TMA store =====
     // Two warpgroups (warps 0-3 and 16-19) alternate tiles: group g drains accumulator buffer g through its own
@@ -279,7 +310,32 @@ __global__ void __launch_bounds__(TCK_THREADS, 1) conv_tck_kernel(const __grid_c
     unsigned char* row = stage_tile + (size_t)srow * 128;
     const uint32_t acc0 = tmem_base + lane_base + (uint32_t)(grp * acc_cols);
     uint32_t pacc = 0;
-    for (int tile = blockIdx.x + grp * gridDim.x; tile < p.ntiles; tile += 2 * gridDim.x) {
+    const float inv_nt = 1.0f / (float)p.nt;
+    const int nchunks_out = p.nt >> 5;
+    // one (kw shift-added) 32-channel chunk of this thread's output pixel
+    auto load_chunk = [&](int c0, float (&v)[32]) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          float pk[16];
+          tc::tmem_ld16(acc0 + (uint32_t)(kw * p.nt + c0 + 16 * h), pk);
+          if (CAT) {
+            float p2[16];
+            tc::tmem_ld16(acc0 + (uint32_t)((3 + kw) * p.nt + c0 + 16 * h), p2);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[j] += p2[j];
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (kw == 0) v[16 * h + j] = pk[j];
+            else v[16 * h + j] += __shfl_down_sync(0xffffffffu, pk[j], kw);
+          }
+        }
+      }
+    };
+    int li = grp;                                       // index of the tile in this CTA's sequence (both groups)
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < p.ntiles; tile += 2 * gridDim.x, li += 2) {
       int t = tile;
       const int tw_ = t % p.tiles_w;
       t /= p.tiles_w;
@@ -287,32 +343,51 @@ __global__ void __launch_bounds__(TCK_THREADS, 1) conv_tck_kernel(const __grid_c
       const int n = t / p.tiles_h;
       tc::mbar_wait(&acc_full[grp], pacc);
       tc::tc_fence_after();
+      float rscale = 1.0f;
+      float v[32];
+      bool have_v = false;
+      if (EPI == TC_EPI_PNF) {
+        // mean square of the activated outputs of this pixel over all channels (one chunk: kept in registers)
+        float ss = 0.0f;
 #pragma unroll 1
-      for (int c0 = 0; c0 < p.nt; c0 += 32) {
-        float v[32];
+        for (int c0 = 0; c0 < p.nt; c0 += 32) {
+          load_chunk(c0, v);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-#pragma unroll
-          for (int kw = 0; kw < 3; ++kw) {
-            float pk[16];
-            tc::tmem_ld16(acc0 + (uint32_t)(kw * p.nt + c0 + 16 * h), pk);
-            if (CAT) {
-              float p2[16];
-              tc::tmem_ld16(acc0 + (uint32_t)((3 + kw) * p.nt + c0 + 16 * h), p2);
-#pragma unroll
-              for (int j = 0; j < 16; ++j) pk[j] += p2[j];
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (kw == 0) v[16 * h + j] = pk[j];
-              else v[16 * h + j] += __shfl_down_sync(0xffffffffu, pk[j], kw);
-            }
+          for (int j = 0; j < 32; ++j) {
+            const float o = gs_lrelu(fmaf(v[j], p.alpha, bias_s[c0 + j]));
+            ss = fmaf(o, o, ss);
           }
         }
+        have_v = (p.nt == 32);
+        rscale = 1.0f / sqrtf(ss * inv_nt + p.eps);
+        const int px = tw_ * 14 + cp;
+        if (writer && px < p.w) p.rvec[((size_t)n * p.h + th_ * 8 + r) * p.w + px] = rscale;
+      }
+#pragma unroll 1
+      for (int c0 = 0; c0 < p.nt; c0 += 32) {
+        if (EPI != TC_EPI_PNF || !have_v) load_chunk(c0, v);
+        have_v = false;
         // the previous store of this group must have finished reading the staging tile
         if (issuer) tc::bulk_wait_read<0>();
         asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-        if (writer) {
+        if (EPI == TC_EPI_MASK) {
+          // chunk number in the CTA's sequence -> ring slot / phase (the two groups share one ring)
+          const uint32_t s = (uint32_t)(li * nchunks_out + (c0 >> 5));
+          const uint32_t aslot = s % (uint32_t)p.aux_k, aph = (s / (uint32_t)p.aux_k) & 1u;
+          tc::mbar_wait(&aux_full[aslot], aph);
+          if (writer) {
+            const unsigned char* arow = aux_smem + (size_t)aslot * TCK_OUT + (size_t)srow * 128;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 ax = *reinterpret_cast<const float4*>(arow + (((j >> 2) ^ sw) << 4));
+              float4 o;
+              o.x = v[j + 0] * p.alpha * gs_lrelu_slope(ax.x); o.y = v[j + 1] * p.alpha * gs_lrelu_slope(ax.y);
+              o.z = v[j + 2] * p.alpha * gs_lrelu_slope(ax.z); o.w = v[j + 3] * p.alpha * gs_lrelu_slope(ax.w);
+              *reinterpret_cast<float4*>(row + (((j >> 2) ^ sw) << 4)) = o;
+            }
+          }
+          tc::mbar_arrive(&aux_empty[aslot]);
+        } else if (writer) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 bv = *reinterpret_cast<const float4*>(&bias_s[c0 + j]);
@@ -320,6 +395,7 @@ __global__ void __launch_bounds__(TCK_THREADS, 1) conv_tck_kernel(const __grid_c
             o.x = fmaf(v[j + 0], p.alpha, bv.x); o.y = fmaf(v[j + 1], p.alpha, bv.y);
             o.z = fmaf(v[j + 2], p.alpha, bv.z); o.w = fmaf(v[j + 3], p.alpha, bv.w);
             if (p.act == 1) { o.x = gs_lrelu(o.x); o.y = gs_lrelu(o.y); o.z = gs_lrelu(o.z); o.w = gs_lrelu(o.w); }
+            if (EPI == TC_EPI_PNF) { o.x *= rscale; o.y *= rscale; o.z *= rscale; o.w *= rscale; }
             *reinterpret_cast<float4*>(row + (((j >> 2) ^ sw) << 4)) = o;
           }
         }

@@ -449,7 +449,7 @@ __global__ void pixel_norm_vec_kernel(const float* __restrict__ a, const float* 
   // SLOTS = float4 per lane per pixel ((c/4) / lpp); R = pixels per lane group in flight per iteration (memory-level
   // parallelism: every load of the R pixels is issued before the first reduction).
   // flags (second-order forms of the fused pixel-norm/leaky-relu backward): 1 = multiply the incoming vector
-  // (dy in MODE 1, u in MODE 2) by lrelu'(a) first; 2 = multiply the result by lrelu'(a)
+  // (dy in MODE 1, u in MODE 2) by lrelu'(a) first; 2 = multiply the result by lrelu'(a); 4 = `a` is given as y = a * r
   const int lane = threadIdx.x & 31;
   const int li = lane % lpp, sub = lane / lpp, ppw = 32 / lpp;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
@@ -485,6 +485,12 @@ __global__ void pixel_norm_vec_kernel(const float* __restrict__ a, const float* 
         if (MODE == 2) w[k][s] = ok[k] ? *reinterpret_cast<const float4*>(u + off[k] + ch) : zero4;
       }
       if (MODE != 0) rr[k] = ok[k] ? rin[off[k] / c] : 0.0f;
+      if (MODE != 0 && (flags & 4)) {
+        // "y form": `a` holds the NORMALISED output y = a * r of the fused conv + pixel-norm layer; a = y / r
+        const float inv = ok[k] ? 1.0f / rr[k] : 0.0f;
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) { t[k][s].x *= inv; t[k][s].y *= inv; t[k][s].z *= inv; t[k][s].w *= inv; }
+      }
     }
 #pragma unroll
     for (int k = 0; k < R; ++k) {
@@ -663,6 +669,37 @@ extern "C" int gs_pixel_norm_bwd2_masked(const float* a, const float* r, const f
   if (rows == 0) return GS_OK;
   pn_vec_launch<2>(a, r, dy, u, ga, nullptr, rows, c, 0.f, lpp, 3, ST);
   GS_CHECK_LAUNCH("pixel_norm_bwd2_masked");
+  return GS_OK;
+}
+
+// "y form" of the three fused pixel-norm / leaky-relu gradient kernels: the layer kept only its normalised output
+// y = a * r (conv epilogue GS_EPI_PIXEL_NORM) and r; a = y / r is rebuilt in registers.
+extern "C" int gs_pixel_norm_bwd_mask_y(const float* y, const float* r, const float* dy, float* dz, float* colsum, long long rows,
+                                        int c, void* stream) {
+  const int lpp = pn_lpp(c);
+  GS_CHECK_ARG(rows >= 0 && c > 0 && lpp > 0 && c <= 512, "pixel_norm_bwd_mask_y: unsupported channel count %d", c);
+  if (colsum) GS_CUDA(cudaMemsetAsync(colsum, 0, (size_t)c * sizeof(float), ST));
+  if (rows == 0) return GS_OK;
+  pn_vec_launch<3>(y, r, dy, nullptr, dz, colsum, rows, c, 0.f, lpp, 4, ST);
+  GS_CHECK_LAUNCH("pixel_norm_bwd_mask_y");
+  return GS_OK;
+}
+extern "C" int gs_pixel_norm_bwd_premask_y(const float* y, const float* r, const float* u, float* out, long long rows, int c,
+                                           void* stream) {
+  const int lpp = pn_lpp(c);
+  GS_CHECK_ARG(rows >= 0 && c > 0 && lpp > 0, "pixel_norm_bwd_premask_y: unsupported channel count %d", c);
+  if (rows == 0) return GS_OK;
+  pn_vec_launch<1>(y, r, u, nullptr, out, nullptr, rows, c, 0.f, lpp, 1 | 4, ST);
+  GS_CHECK_LAUNCH("pixel_norm_bwd_premask_y");
+  return GS_OK;
+}
+extern "C" int gs_pixel_norm_bwd2_masked_y(const float* y, const float* r, const float* dy, const float* u, float* ga,
+                                           long long rows, int c, void* stream) {
+  const int lpp = pn_lpp(c);
+  GS_CHECK_ARG(rows >= 0 && c > 0 && lpp > 0, "pixel_norm_bwd2_masked_y: unsupported channel count %d", c);
+  if (rows == 0) return GS_OK;
+  pn_vec_launch<2>(y, r, dy, u, ga, nullptr, rows, c, 0.f, lpp, 3 | 4, ST);
+  GS_CHECK_LAUNCH("pixel_norm_bwd2_masked_y");
   return GS_OK;
 }
 

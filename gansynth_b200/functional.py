@@ -107,18 +107,51 @@ class ConvW(Function):
         return gx, gdy, None, None, None, None
 
 
+class PreMasked(object):
+    """Wrapper protocol (D side).  `t` is the output y = leaky_relu(z) of a ConvLayer built with premasked=True: whoever
+    consumes it returns the gradient w.r.t. the layer's PRE-activation z, i.e. lrelu'(y) * (gradient w.r.t. y) -- a
+    convolution does that in its epilogue (ConvMasked), anything else goes through `plain()`."""
+    __slots__ = ("t",)
+
+    def __init__(self, t):
+        self.t = t
+
+
+class PnOut(object):
+    """Wrapper protocol (G side).  `t` is the output y = pixel_norm(leaky_relu(z)) of a ConvPnLayer, `r` its per-pixel
+    1 / sqrt(mean(a^2) + eps): whoever consumes it returns the gradient w.r.t. the layer's pre-activation z
+    (PnBwdMaskY of the gradient w.r.t. y)."""
+    __slots__ = ("t", "r")
+
+    def __init__(self, t, r):
+        self.t, self.r = t, r
+
+
+def plain(x):
+    """A protocol wrapper as an ordinary tensor for consumers that do not speak the protocol: identity forward, the
+    un-fused mask / pixel-norm backward kernel on the way back."""
+    if isinstance(x, PreMasked):
+        return ApplyMask.apply(x.t)
+    if isinstance(x, PnOut):
+        return PnAdapter.apply(x.t, x.r)
+    return x
+
+
 class ConvLayer(Function):
     """Fused layer forward: act(alpha * conv(x, w) + bias), conv in gather (`form`='c') or transposed
     ('t') form.  The backward un-fuses into MaskMul(+ColSum) / the trio so it stays differentiable.
-    `premasked`: the consumer of y (PixelNormOfLayer) hands back a gradient that already carries the
-    leaky-relu mask of this layer, so the backward must not apply it again."""
+    `premasked`: the consumer of y (PixelNormOfLayer, or a consumer of PreMasked(y)) hands back a gradient that
+    already carries the leaky-relu mask of this layer, so the backward must not apply it again.
+    `x_premasked`: x is the output of such a premasked layer: the input gradient is returned multiplied by
+    lrelu'(x), in the epilogue of the convolution that computes it (ConvMasked)."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, form, ksize, stride, wswap, alpha, act, premasked=False):
+    def forward(ctx, x, w, bias, form, ksize, stride, wswap, alpha, act, premasked=False, x_premasked=False):
         fn = K.conv_c if form == "c" else K.conv_t
         y = fn(x, w, bias, ksize, stride, wswap, alpha, act, precise=True)
         ctx.cfg = (ksize, stride, wswap, alpha)
         ctx.form, ctx.act, ctx.has_bias, ctx.premasked = form, act, bias is not None, premasked
+        ctx.x_premasked = x_premasked
         ctx.save_for_backward(x, w, y)
         return y
 
@@ -137,12 +170,119 @@ class ConvLayer(Function):
             dz = dy
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            dx = (ConvT if ctx.form == "c" else ConvC).apply(dz, w, *cfg)
+            if ctx.x_premasked:
+                dx = ConvMasked.apply(dz, w, x, "t" if ctx.form == "c" else "c", *cfg)
+            else:
+                dx = (ConvT if ctx.form == "c" else ConvC).apply(dz, w, *cfg)
         if ctx.needs_input_grad[1] and not _SKIP_WGRAD:
             dw = ConvW.apply(x, dz, *cfg) if ctx.form == "c" else ConvW.apply(dz, x, *cfg)
         if want_db and db is None:
             db = ColSum.apply(dz)
-        return dx, dw, db, None, None, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None, None, None
+
+
+class ConvMasked(Function):
+    """lrelu'(src) * alpha * conv(v, w), conv in gather ('c') or transposed ('t') form, the mask applied in the
+    convolution's epilogue (GS_EPI_MASK).  Linear in v and in w; `src` only contributes its sign."""
+
+    @staticmethod
+    def forward(ctx, v, w, src, form, ksize, stride, wswap, alpha):
+        ctx.cfg = (ksize, stride, wswap, alpha)
+        ctx.form = form
+        ctx.save_for_backward(v, w, src)
+        fn = K.conv_c if form == "c" else K.conv_t
+        return fn(v, w, None, ksize, stride, wswap, alpha, ACT_NONE, mask_src=src)
+
+    @staticmethod
+    def backward(ctx, u):
+        v, w, src = ctx.saved_tensors
+        cfg = ctx.cfg
+        mu = MaskMul.apply(u, src)
+        gv = gw = None
+        if ctx.needs_input_grad[0]:
+            gv = (ConvT if ctx.form == "c" else ConvC).apply(mu, w, *cfg)
+        if ctx.needs_input_grad[1]:
+            gw = ConvW.apply(v, mu, *cfg) if ctx.form == "c" else ConvW.apply(mu, v, *cfg)
+        return gv, gw, None, None, None, None, None, None
+
+
+class ApplyMask(Function):
+    """Identity on the output y of a premasked leaky-relu layer; the backward applies that layer's mask (the un-fused
+    route of the PreMasked protocol)."""
+
+    @staticmethod
+    def forward(ctx, y):
+        ctx.save_for_backward(y)
+        return y.view_as(y)
+
+    @staticmethod
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        return MaskMul.apply(g, y)
+
+
+class ConvPnLayer(Function):
+    """pixel_normalization(leaky_relu(alpha * conv(x, w) + bias)) as ONE kernel (networks.py:57-68, 82-93; the
+    normalisation runs in the convolution's epilogue) -> (y, r).  The layer keeps y and r only.
+    Protocol (PnOut): the incoming gradient is w.r.t. this layer's PRE-activation; `xr` is the r of the PnOut that x
+    came from (None for an ordinary tensor), in which case the returned input gradient is w.r.t. THAT layer's
+    pre-activation."""
+
+    @staticmethod
+    def forward(ctx, x, xr, w, bias, form, ksize, stride, wswap, alpha, eps):
+        y, r = K.conv_pn(x, w, bias, form, ksize, stride, wswap, alpha, eps)
+        ctx.cfg = (ksize, stride, wswap, alpha)
+        ctx.form, ctx.has_bias = form, bias is not None
+        ctx.save_for_backward(x, xr, w)
+        ctx.mark_non_differentiable(r)
+        return y, r
+
+    @staticmethod
+    def backward(ctx, dz, _gr):
+        x, xr, w = ctx.saved_tensors
+        cfg = ctx.cfg
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = (ConvT if ctx.form == "c" else ConvC).apply(dz, w, *cfg)
+            if xr is not None:
+                dx = PnBwdMaskY.apply(x, xr, dx)
+        if ctx.needs_input_grad[2] and not _SKIP_WGRAD:
+            dw = ConvW.apply(x, dz, *cfg) if ctx.form == "c" else ConvW.apply(dz, x, *cfg)
+        if ctx.has_bias and ctx.needs_input_grad[3] and not _SKIP_WGRAD:
+            db = ColSum.apply(dz)
+        return dx, None, dw, db, None, None, None, None, None, None
+
+
+class PnAdapter(Function):
+    """Identity on the y of a PnOut; the backward turns the gradient w.r.t. y into the gradient w.r.t. the producing
+    layer's pre-activation (the un-fused route of the PnOut protocol)."""
+
+    @staticmethod
+    def forward(ctx, y, r):
+        ctx.save_for_backward(y, r)
+        return y.view_as(y)
+
+    @staticmethod
+    def backward(ctx, g):
+        y, r = ctx.saved_tensors
+        return PnBwdMaskY.apply(y, r, g), None
+
+
+class PnBwdMaskY(Function):
+    """PnBwdMask for a layer that kept (y = a * r, r): dz = lrelu'(y) * pixel_norm_backward(y / r, r, dy).  Second
+    order exactly as PnBwdMask (the gradient w.r.t. y's slot is the one w.r.t. the pre-activation)."""
+
+    @staticmethod
+    def forward(ctx, y, r, dy):
+        ctx.save_for_backward(y, r, dy)
+        return K.pn_bwd_mask_y(y, r, dy, False)[0]
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, u):
+        y, r, dy = ctx.saved_tensors
+        ga, gdy = K.pn_bwd_mask_second_y(y, r, dy, u)
+        return ga, None, gdy
 
 
 # ----------------------------------------------------------------------------- activations / bias

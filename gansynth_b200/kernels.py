@@ -11,6 +11,7 @@ import torch
 from . import _lib
 
 IMPL_AUTO, IMPL_NAIVE, IMPL_TILED, IMPL_TC, IMPL_FP32 = 0, 1, 2, 3, 4
+EPI_NONE, EPI_MASK, EPI_PIXEL_NORM = 0, 1, 2
 
 
 def _ptr(t):
@@ -68,26 +69,43 @@ class CudaBackend(object):
         return impl
 
     # ------------------------------------------------------------------ convolution family
-    def conv_c(self, x, w, bias, ksize, stride, wswap, alpha, act, precise=False):
-        x, w, bias = _chk(x, w, bias)
-        n, h, wd, ci = x.shape
-        co = w.shape[2] if wswap else w.shape[3]
-        assert (w.shape[3] if wswap else w.shape[2]) == ci, "conv_c: weight/input channel mismatch"
-        y = torch.empty((n, h // stride, wd // stride, co), device=x.device, dtype=torch.float32)
-        _lib.call("gs_conv2d_fwd", _ptr(x), _ptr(w), _ptr(bias), _ptr(y), n, h, wd, ci, co, ksize, stride,
-                  int(wswap), float(alpha), int(act), self._impl(precise, w), _stream())
-        return y
+    def conv_c(self, x, w, bias, ksize, stride, wswap, alpha, act, precise=False, mask_src=None):
+        """Gather convolution; with `mask_src` (shaped like the output) the result is multiplied by lrelu'(mask_src)
+        in the kernel epilogue (GS_EPI_MASK)."""
+        return self._conv("gs_conv2d_fwd_ex", x, w, bias, ksize, stride, wswap, alpha, act, precise,
+                          EPI_MASK if mask_src is not None else EPI_NONE, mask_src, None, 0.0)
 
-    def conv_t(self, dy, w, bias, ksize, stride, wswap, alpha, act, precise=False):
-        dy, w, bias = _chk(dy, w, bias)
-        n, oh, ow, co = dy.shape
-        ci = w.shape[3] if wswap else w.shape[2]
-        assert (w.shape[2] if wswap else w.shape[3]) == co, "conv_t: weight/input channel mismatch"
-        h, wd = oh * stride, ow * stride
-        dx = torch.empty((n, h, wd, ci), device=dy.device, dtype=torch.float32)
-        _lib.call("gs_conv2d_dgrad", _ptr(dy), _ptr(w), _ptr(bias), _ptr(dx), n, h, wd, ci, co, ksize, stride,
-                  int(wswap), float(alpha), int(act), self._impl(precise, w), _stream())
-        return dx
+    def conv_t(self, dy, w, bias, ksize, stride, wswap, alpha, act, precise=False, mask_src=None):
+        """Transposed (input-gradient form) convolution; `mask_src` as in conv_c."""
+        return self._conv("gs_conv2d_dgrad_ex", dy, w, bias, ksize, stride, wswap, alpha, act, precise,
+                          EPI_MASK if mask_src is not None else EPI_NONE, mask_src, None, 0.0)
+
+    def conv_pn(self, x, w, bias, form, ksize, stride, wswap, alpha, eps):
+        """pixel_normalization(leaky_relu(alpha * conv(x, w) + bias)) in one kernel (GS_EPI_PIXEL_NORM), conv in gather
+        ('c') or transposed ('t') form -> (y, r) with r = 1 / sqrt(mean_c(a^2) + eps) per pixel."""
+        name = "gs_conv2d_fwd_ex" if form == "c" else "gs_conv2d_dgrad_ex"
+        return self._conv(name, x, w, bias, ksize, stride, wswap, alpha, 1, True, EPI_PIXEL_NORM, None, True, eps)
+
+    def _conv(self, name, x, w, bias, ksize, stride, wswap, alpha, act, precise, epi, aux, want_r, eps):
+        x, w, bias, aux = _chk(x, w, bias, aux)
+        n = x.shape[0]
+        if name == "gs_conv2d_fwd_ex":
+            h, wd, ci = x.shape[1:]
+            co = w.shape[2] if wswap else w.shape[3]
+            assert (w.shape[3] if wswap else w.shape[2]) == ci, "conv_c: weight/input channel mismatch"
+            out = torch.empty((n, h // stride, wd // stride, co), device=x.device, dtype=torch.float32)
+        else:
+            oh, ow, co = x.shape[1:]
+            ci = w.shape[3] if wswap else w.shape[2]
+            assert (w.shape[2] if wswap else w.shape[3]) == co, "conv_t: weight/input channel mismatch"
+            h, wd = oh * stride, ow * stride
+            out = torch.empty((n, h, wd, ci), device=x.device, dtype=torch.float32)
+        if aux is not None:
+            assert aux.shape == out.shape, "conv: mask source must be shaped like the output"
+        r = torch.empty(out.shape[:-1], device=x.device, dtype=torch.float32) if want_r else None
+        _lib.call(name, _ptr(x), _ptr(w), _ptr(bias), _ptr(out), n, h, wd, ci, co, ksize, stride, int(wswap),
+                  float(alpha), int(act), int(epi), _ptr(aux), _ptr(r), float(eps), self._impl(precise, w), _stream())
+        return (out, r) if want_r else out
 
     def conv_w(self, x, dy, ksize, stride, wswap, alpha):
         x, dy = _chk(x, dy)
@@ -253,6 +271,25 @@ class CudaBackend(object):
         rows = a.numel() // c
         _lib.call("gs_pixel_norm_bwd2_masked", _ptr(a), _ptr(r), _ptr(dy), _ptr(u), _ptr(ga), rows, c, _stream())
         _lib.call("gs_pixel_norm_bwd_premask", _ptr(a), _ptr(r), _ptr(u), _ptr(gdy), rows, c, _stream())
+        return ga, gdy
+
+    def pn_bwd_mask_y(self, y, r, dy, want_colsum=False):
+        """pn_bwd_mask for a fused conv + pixel-norm layer that kept (y = a * r, r): lrelu'(y) * pixel-norm backward."""
+        y, r, dy = _chk(y, r, dy)
+        c = y.shape[-1]
+        dz = torch.empty_like(y)
+        cs = torch.empty((c,), device=y.device, dtype=torch.float32) if want_colsum else None
+        _lib.call("gs_pixel_norm_bwd_mask_y", _ptr(y), _ptr(r), _ptr(dy), _ptr(dz), _ptr(cs), y.numel() // c, c, _stream())
+        return dz, cs
+
+    def pn_bwd_mask_second_y(self, y, r, dy, u):
+        """pn_bwd_mask_second in the (y, r) form."""
+        y, r, dy, u = _chk(y, r, dy, u)
+        c = y.shape[-1]
+        ga, gdy = torch.empty_like(y), torch.empty_like(y)
+        rows = y.numel() // c
+        _lib.call("gs_pixel_norm_bwd2_masked_y", _ptr(y), _ptr(r), _ptr(dy), _ptr(u), _ptr(ga), rows, c, _stream())
+        _lib.call("gs_pixel_norm_bwd_premask_y", _ptr(y), _ptr(r), _ptr(u), _ptr(gdy), rows, c, _stream())
         return ga, gdy
 
     def pn_bwd2(self, a, r, dy, u):

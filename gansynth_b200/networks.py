@@ -66,6 +66,7 @@ class PGGAN(object):
         self.lerp_coef.copy_(torch.tensor([t, 1.0 - t], dtype=torch.float32), non_blocking=True)
 
     def _lerp(self, a, b, t):
+        a, b = F.plain(a), F.plain(b)
         if self.device_lerp_active and self.lerp_coef is not None:
             return F.AxpbyDev.apply(a, b, self.lerp_coef)
         return lerp(a, b, t)
@@ -155,16 +156,16 @@ class PGGAN(object):
                         # conv -> leaky_relu -> pixel_normalization (networks.py:57-68) as one fused layer
                         inputs = conv2d(inputs, filters=channels(depth), kernel_size=[3, 3], use_bias=True,
                                         variance_scale=2.0, scale_weight=True, activation="leaky_relu",
-                                        pixel_norm_epsilon=1.0e-12)
+                                        pixel_norm_epsilon=1.0e-12, protocol=True)
                     return inputs
                 with variable_scope("upscale_conv"):
                     inputs = conv2d_transpose(inputs, filters=channels(depth), kernel_size=[3, 3], strides=[2, 2],
                                               use_bias=True, variance_scale=2.0, scale_weight=True,
-                                              activation="leaky_relu", pixel_norm_epsilon=1.0e-12)
+                                              activation="leaky_relu", pixel_norm_epsilon=1.0e-12, protocol=True)
                 with variable_scope("conv"):
                     inputs = conv2d(inputs, filters=channels(depth), kernel_size=[3, 3], use_bias=True,
                                     variance_scale=2.0, scale_weight=True, activation="leaky_relu",
-                                    pixel_norm_epsilon=1.0e-12)
+                                    pixel_norm_epsilon=1.0e-12, protocol=True)
                 return inputs
 
         def color_block(inputs, depth):
@@ -201,7 +202,7 @@ class PGGAN(object):
         with variable_scope(name):
             embedded = embedding(labels, units=latents.shape[1], variance_scale=1.0, scale_weight=True)
             images = grow(torch.cat([latents, embedded], dim=1), self.min_depth)
-        return F.nhwc_to_nchw(images)
+        return F.nhwc_to_nchw(F.plain(images))
 
     # ------------------------------------------------------------------ discriminator
     def discriminator(self, images, labels, name="discriminator", reuse=None):
@@ -220,6 +221,7 @@ class PGGAN(object):
                         # the C-channel part stays on the vectorised / tensor-core kernels instead of
                         # dragging a 257-channel tensor through the generic path.
                         ch = channels(depth)
+                        inputs = F.plain(inputs)
                         weight, alpha = ops.get_weight([3, 3, ch + 1, ch], 2.0, True)
                         bias = ops.get_bias([ch])
                         stddev = batch_stddev(inputs).contiguous()
@@ -237,19 +239,22 @@ class PGGAN(object):
                         logits = dense(inputs, units=labels.shape[1], use_bias=True, variance_scale=1.0,
                                        scale_weight=True)
                     return features, logits
+                # protocol=True: each activated output travels as functional.PreMasked, so that the next convolution's
+                # backward applies this layer's leaky-relu mask in its epilogue
                 with variable_scope("conv"):
                     inputs = conv2d(inputs, filters=channels(depth), kernel_size=[3, 3], use_bias=True,
-                                    variance_scale=2.0, scale_weight=True, activation="leaky_relu")
+                                    variance_scale=2.0, scale_weight=True, activation="leaky_relu", protocol=True)
                 with variable_scope("conv_downscale"):
                     inputs = conv2d(inputs, filters=channels(depth - 1), kernel_size=[3, 3], strides=[2, 2],
-                                    use_bias=True, variance_scale=2.0, scale_weight=True, activation="leaky_relu")
+                                    use_bias=True, variance_scale=2.0, scale_weight=True, activation="leaky_relu",
+                                    protocol=True)
                 return inputs
 
         def color_block(inputs, depth):
             with variable_scope("color_block_{}x{}".format(*resolution(depth))):
                 with variable_scope("conv"):
                     inputs = conv2d(inputs, filters=channels(depth), kernel_size=[1, 1], use_bias=True,
-                                    variance_scale=2.0, scale_weight=True, activation="leaky_relu")
+                                    variance_scale=2.0, scale_weight=True, activation="leaky_relu", protocol=True)
                 return inputs
 
         def grow(depth):

@@ -168,6 +168,7 @@ def _act_code(activation):
 def dense(inputs, units, use_bias=True, variance_scale=2.0, scale_weight=False,
           apply_weight_standardization=False, apply_spectral_normalization=False, activation=None):
     """ops.py:183-201.  inputs [B, in] -> [B, units]."""
+    inputs = F.plain(inputs)
     weight, alpha = get_weight([inputs.shape[1], units], variance_scale, scale_weight,
                                apply_weight_standardization, apply_spectral_normalization)
     out = F.DenseF.apply(inputs, weight, alpha)
@@ -189,37 +190,54 @@ def embedding(inputs, units, variance_scale=2.0, scale_weight=False, apply_weigh
 
 def conv2d(inputs, filters, kernel_size, strides=[1, 1], use_bias=True, variance_scale=2.0, scale_weight=False,
            apply_weight_standardization=False, apply_spectral_normalization=False, activation=None,
-           pixel_norm_epsilon=None):
-    """ops.py:221-247.  NHWC, TF SAME padding, square kernel 1 or 3, stride 1 or 2.  `pixel_norm_epsilon`
-    (extension) appends pixel_normalization (ops.py:330-333) to the fused layer."""
+           pixel_norm_epsilon=None, protocol=False):
+    """ops.py:221-247.  NHWC, TF SAME padding, square kernel 1 or 3, stride 1 or 2.  Extensions: `pixel_norm_epsilon`
+    appends pixel_normalization (ops.py:330-333) to the fused layer; `protocol` returns the activated output as a
+    functional.PreMasked / PnOut wrapper (and `inputs` may be one) so that the NEXT layer's backward applies this
+    layer's leaky-relu / pixel-norm gradient in its convolution epilogue -- networks.py uses it internally."""
     ksize, stride = _square(kernel_size), _square(strides)
-    weight, alpha = get_weight([ksize, ksize, inputs.shape[-1], filters], variance_scale, scale_weight,
+    weight, alpha = get_weight([ksize, ksize, _channels(inputs), filters], variance_scale, scale_weight,
                                apply_weight_standardization, apply_spectral_normalization)
     bias = get_bias([filters]) if use_bias else None
-    return _layer(inputs, weight, bias, "c", ksize, stride, False, alpha, activation, pixel_norm_epsilon)
+    return _layer(inputs, weight, bias, "c", ksize, stride, False, alpha, activation, pixel_norm_epsilon, protocol)
 
 
 def conv2d_transpose(inputs, filters, kernel_size, strides=[1, 1], use_bias=True, variance_scale=2.0,
                      scale_weight=False, apply_weight_standardization=False, apply_spectral_normalization=False,
-                     activation=None, pixel_norm_epsilon=None):
+                     activation=None, pixel_norm_epsilon=None, protocol=False):
     """ops.py:250-280.  The variable is [k, k, Cin, filters] (fan-in from that shape); output is
-    [B, H*s, W*s, filters]."""
+    [B, H*s, W*s, filters].  `pixel_norm_epsilon`, `protocol`: see conv2d."""
     ksize, stride = _square(kernel_size), _square(strides)
-    weight, alpha = get_weight([ksize, ksize, inputs.shape[-1], filters], variance_scale, scale_weight,
+    weight, alpha = get_weight([ksize, ksize, _channels(inputs), filters], variance_scale, scale_weight,
                                apply_weight_standardization, apply_spectral_normalization)
     bias = get_bias([filters]) if use_bias else None
-    return _layer(inputs, weight, bias, "t", ksize, stride, True, alpha, activation, pixel_norm_epsilon)
+    return _layer(inputs, weight, bias, "t", ksize, stride, True, alpha, activation, pixel_norm_epsilon, protocol)
 
 
-def _layer(inputs, weight, bias, form, ksize, stride, wswap, alpha, activation, pixel_norm_epsilon):
+def _channels(inputs):
+    return (inputs.t if isinstance(inputs, (F.PreMasked, F.PnOut)) else inputs).shape[-1]
+
+
+def _layer(inputs, weight, bias, form, ksize, stride, wswap, alpha, activation, pixel_norm_epsilon, protocol=False):
     act = _act_code(activation)
-    if pixel_norm_epsilon is None:
-        return F.ConvLayer.apply(inputs, weight, bias, form, ksize, stride, wswap, alpha, act)
-    if act != F.ACT_LRELU or not F.FUSED_EW:
-        return pixel_normalization(F.ConvLayer.apply(inputs, weight, bias, form, ksize, stride, wswap, alpha, act),
-                                   pixel_norm_epsilon)
-    y = F.ConvLayer.apply(inputs, weight, bias, form, ksize, stride, wswap, alpha, act, True)
-    return F.PixelNormOfLayer.apply(y, pixel_norm_epsilon)
+    if pixel_norm_epsilon is not None:
+        if act != F.ACT_LRELU or not F.FUSED_EW:
+            return pixel_normalization(F.ConvLayer.apply(F.plain(inputs), weight, bias, form, ksize, stride, wswap, alpha,
+                                                         act), pixel_norm_epsilon)
+        # conv -> leaky_relu -> pixel_normalization in one kernel; the gradient of the activation pair is applied by
+        # whoever consumes the PnOut
+        if isinstance(inputs, F.PnOut):
+            x, xr = inputs.t, inputs.r
+        else:
+            x, xr = F.plain(inputs), None
+        y, r = F.ConvPnLayer.apply(x, xr, weight, bias, form, ksize, stride, wswap, alpha, pixel_norm_epsilon)
+        out = F.PnOut(y, r)
+        return out if protocol else F.plain(out)
+    x_pm = isinstance(inputs, F.PreMasked) and F.FUSED_EW
+    x = inputs.t if x_pm else F.plain(inputs)
+    pm_out = bool(protocol) and act == F.ACT_LRELU and F.FUSED_EW
+    y = F.ConvLayer.apply(x, weight, bias, form, ksize, stride, wswap, alpha, act, pm_out, x_pm)
+    return F.PreMasked(y) if pm_out else y
 
 
 def _square(v):
@@ -233,6 +251,7 @@ def _square(v):
 
 def upscale2d(inputs, factors=[2, 2]):
     """ops.py:283-291 (NHWC)."""
+    inputs = F.plain(inputs)
     factors = np.asanyarray(factors)
     if (factors == 1).all():
         return inputs
@@ -241,6 +260,7 @@ def upscale2d(inputs, factors=[2, 2]):
 
 def downscale2d(inputs, factors=[2, 2]):
     """ops.py:294-305 (NHWC): average pool, kernel = stride = factors."""
+    inputs = F.plain(inputs)
     factors = np.asanyarray(factors)
     if (factors == 1).all():
         return inputs
@@ -250,11 +270,13 @@ def downscale2d(inputs, factors=[2, 2]):
 
 def pixel_normalization(inputs, epsilon=1.0e-12):
     """ops.py:330-333 over the channel (last) axis."""
+    inputs = F.plain(inputs)
     return F.PixelNorm.apply(inputs, epsilon)
 
 
 def batch_stddev(inputs, groups=4, epsilon=1.0e-12):
     """ops.py:336-348.  inputs [B, H, W, C] -> [B, H, W, 1]; B must be a multiple of `groups`."""
+    inputs = F.plain(inputs)
     b = inputs.shape[0]
     if b % groups:
         raise ValueError("batch_stddev: batch %d is not a multiple of groups %d" % (b, groups))
@@ -265,8 +287,10 @@ def batch_stddev(inputs, groups=4, epsilon=1.0e-12):
 
 def leaky_relu(inputs):
     """tf.nn.leaky_relu, alpha 0.2."""
+    inputs = F.plain(inputs)
     return F.LeakyRelu.apply(inputs)
 
 
 def tanh(inputs):
+    inputs = F.plain(inputs)
     return F.Tanh.apply(inputs)

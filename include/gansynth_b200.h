@@ -50,6 +50,26 @@ int gs_conv2d_dgrad(const float* dy, const float* w, const float* bias, float* d
 int gs_conv2d_wgrad(const float* x, const float* dy, float* dw, int n, int h, int wd, int ci, int co, int ksize,
                     int stride, int wswap, float alpha, int impl, void* stream);
 
+/* The same two convolutions with a FUSED EPILOGUE, `epi`:
+ *   GS_EPI_NONE  (0): as above.
+ *   GS_EPI_MASK  (1): out = lrelu'(aux) * alpha * conv(...).  `aux` is shaped like the output; only its sign is used.  This
+ *                     is tf.nn.leaky_relu's gradient (LeakyReluGrad of networks.py:184,194,216,227: the mask of the layer
+ *                     whose output the convolution's result is a gradient of) applied while the tile is still on chip.
+ *                     bias must be NULL, act 0.
+ *   GS_EPI_PIXEL_NORM (2): out = pixel_normalization(leaky_relu(alpha * conv + bias)) over the output channels (ops.py:330-333
+ *                     after networks.py:57-68, 82-93), rvec[n, oh, ow] = 1 / sqrt(mean_c(a^2) + eps).  act must be 1.
+ * The result is always the fused one; shapes the tensor-core epilogue does not cover run the plain convolution followed by
+ * the elementwise kernel, in place. */
+#define GS_EPI_NONE 0
+#define GS_EPI_MASK 1
+#define GS_EPI_PIXEL_NORM 2
+int gs_conv2d_fwd_ex(const float* x, const float* w, const float* bias, float* y, int n, int h, int wd, int ci, int co,
+                     int ksize, int stride, int wswap, float alpha, int act, int epi, const float* aux, float* rvec,
+                     float eps, int impl, void* stream);
+int gs_conv2d_dgrad_ex(const float* dy, const float* w, const float* bias, float* dx, int n, int h, int wd, int ci,
+                       int co, int ksize, int stride, int wswap, float alpha, int act, int epi, const float* aux,
+                       float* rvec, float eps, int impl, void* stream);
+
 /* ---- tf.nn.conv2d_transpose ops.py:266-276: x [n,h,w,cin], var [k,k,cin,filters] -> y [n,h*s,w*s,filters] */
 int gs_conv2d_transpose_fwd(const float* x, const float* var, const float* bias, float* y, int n, int h, int wd,
                             int cin, int filters, int ksize, int stride, float alpha, int act, int impl, void* stream);
@@ -102,6 +122,13 @@ int gs_pixel_norm_bwd2_masked(const float* a, const float* r, const float* dy, c
                               void* stream);
 int gs_pixel_norm_bwd2(const float* a, const float* r, const float* dy, const float* u, float* ga, long long rows,
                        int c, void* stream);
+/* "y form" of the fused gradients above for layers run with GS_EPI_PIXEL_NORM, which keep only the normalised output
+   y = a * r and r (a = y / r is rebuilt in registers): networks.py:57-68, 82-93 differentiated */
+int gs_pixel_norm_bwd_mask_y(const float* y, const float* r, const float* dy, float* dz, float* colsum, long long rows, int c,
+                             void* stream);
+int gs_pixel_norm_bwd_premask_y(const float* y, const float* r, const float* u, float* out, long long rows, int c, void* stream);
+int gs_pixel_norm_bwd2_masked_y(const float* y, const float* r, const float* dy, const float* u, float* ga, long long rows, int c,
+                                void* stream);
 
 /* ---- batch_stddev ops.py:336-348 on [b, e]; stat is [b/groups] ---------------------------------- */
 int gs_batch_stddev_fwd(const float* x, float* stat, int b, long long e, int groups, float eps, void* stream);

@@ -52,7 +52,7 @@ def record_masks(backend):
     (the order oracle.ops.leaky_relu is called in: both sides walk the reference's graph in the same order).
     The mask is read from the sign of the layer OUTPUT, which is what the product's backward kernels use."""
     masks = []
-    act_pos = {"conv_c": 7, "conv_t": 7, "bias_act": 2, "conv_pn": 7}
+    act_pos = {"conv_c": 7, "conv_t": 7, "bias_act": 2, "conv_pn": -1}      # conv_pn always activates
     originals = {}
 
     def wrap(name, pos):
@@ -60,7 +60,7 @@ def record_masks(backend):
 
         def f(*a, **k):
             out = orig(*a, **k)
-            act = k.get("act", a[pos] if len(a) > pos else 0)
+            act = 1 if pos < 0 else k.get("act", a[pos] if len(a) > pos else 0)
             if act == 1:
                 masks.append(_mask_of(out[0] if isinstance(out, tuple) else out))
             return out
@@ -100,7 +100,8 @@ def masked_grad_report(got, want, tol):
 MAX_FLIP_FRACTION = 1e-3
 
 
-def check_substep(model, store, ostep, scope, images, labels, latents, dtype, mode, plain=True, grad_ok=None):
+def check_substep(model, store, ostep, scope, images, labels, latents, dtype, mode, plain=True, grad_ok=None,
+                  retain_graph=False):
     """One sub-step's loss and flat gradient against the oracle, with the leaky-relu discontinuity MEASURED
     instead of tolerated:
 
@@ -124,7 +125,8 @@ def check_substep(model, store, ostep, scope, images, labels, latents, dtype, mo
             loss = model.discriminator_loss_fn(images.to(dev), labels.to(dev), latents.to(dev))
         else:
             loss = model.generator_loss_fn(labels.to(dev), latents.to(dev))
-        grads = torch.autograd.grad(loss, [store.vars[n] for n in names], allow_unused=True)
+        # retain_graph: the caller differentiates `loss` again (model._apply)
+        grads = torch.autograd.grad(loss, [store.vars[n] for n in names], allow_unused=True, retain_graph=retain_graph)
     got = dict(zip(names, grads))
     with oops.MaskTape(masks) as tape:
         if scope == "discriminator":

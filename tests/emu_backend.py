@@ -34,7 +34,9 @@ class EmuBackend(object):
     def _w(self, w, wswap):
         return w.permute(0, 1, 3, 2) if wswap else w   # -> [k, k, ci, co]
 
-    def conv_c(self, x, w, bias, ksize, stride, wswap, alpha, act, precise=False):
+    def conv_c(self, x, w, bias, ksize, stride, wswap, alpha, act, precise=False, mask_src=None):
+        if mask_src is not None:
+            return self.mask_mul(EmuBackend.conv_c(self, x, w, bias, ksize, stride, wswap, alpha, act), mask_src)
         wt = self._w(w, wswap).permute(3, 2, 0, 1)
         pb = 1 if (ksize == 3 and stride == 1) else 0
         pa = (ksize - stride) - pb if ksize == 3 else 0
@@ -44,7 +46,19 @@ class EmuBackend(object):
             y = y + bias.view(1, -1, 1, 1)
         return _nhwc(_act(y, act))
 
-    def conv_t(self, dy, w, bias, ksize, stride, wswap, alpha, act, precise=False):
+    def conv_pn(self, x, w, bias, form, ksize, stride, wswap, alpha, eps):
+        fn = EmuBackend.conv_c if form == "c" else EmuBackend.conv_t     # class functions: one kernel, one call
+        return self.pn_fwd(fn(self, x, w, bias, ksize, stride, wswap, alpha, 1), eps)
+
+    def pn_bwd_mask_y(self, y, r, dy, want_colsum=False):
+        return self.pn_bwd_mask(y / r.unsqueeze(-1), r, dy, want_colsum)
+
+    def pn_bwd_mask_second_y(self, y, r, dy, u):
+        return self.pn_bwd_mask_second(y / r.unsqueeze(-1), r, dy, u)
+
+    def conv_t(self, dy, w, bias, ksize, stride, wswap, alpha, act, precise=False, mask_src=None):
+        if mask_src is not None:
+            return self.mask_mul(EmuBackend.conv_t(self, dy, w, bias, ksize, stride, wswap, alpha, act), mask_src)
         wt = self._w(w, wswap).permute(3, 2, 0, 1)      # [co, ci, k, k]
         pb = 1 if (ksize == 3 and stride == 1) else 0
         n, oh, ow, co = dy.shape

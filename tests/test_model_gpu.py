@@ -34,8 +34,8 @@ def grad_ok(mode, got, want64, want32=None):
     return (cos >= lim[0] and rel <= lim[1]), "cos %.6f relL2 %.3e" % (cos, rel)
 
 
-def check_substep(model, store, ostep, scope, images, labels, latents, dtype, mode, plain=True):
-    return _check_substep(model, store, ostep, scope, images, labels, latents, dtype, mode, plain, grad_ok)
+def check_substep(model, store, ostep, scope, images, labels, latents, dtype, mode, plain=True, retain_graph=False):
+    return _check_substep(model, store, ostep, scope, images, labels, latents, dtype, mode, plain, grad_ok, retain_graph)
 
 
 def _pair(cfg, level, store, bias_std=0.1):
@@ -78,7 +78,8 @@ def test_small_step_parity(cuda_store, conv_mode, level):
     for it in range(2):
         lat2 = torch.randn(4, 256, generator=torch.Generator().manual_seed(10 + it))
         for scope, z in (("discriminator", latents), ("generator", lat2)):
-            loss, got, want = check_substep(model, cuda_store, ostep, scope, images, labels, z, torch.float64, conv_mode)
+            loss, got, want = check_substep(model, cuda_store, ostep, scope, images, labels, z, torch.float64, conv_mode,
+                                            retain_graph=True)
             before = {n: ostep.params[n].detach().clone() for n in got}
             model._apply(scope, loss)
             if scope == "discriminator":

@@ -194,3 +194,85 @@ def test_tc_filter_gradient(case, wswap):
     want = EMU.conv_w(x.double(), dy.double(), 3, st, wswap, 0.37)
     assert got.shape == want.shape
     assert rel_err(got, want) < 1e-4, (case, wswap, rel_err(got, want))
+
+
+# ------------------------------------------------------------------------------------------------
+# fused epilogues (GS_EPI_MASK, GS_EPI_PIXEL_NORM): tensor-core tiles (both kernels, all three forms), shapes that
+# fall back to convolution + elementwise kernel (split-K / split channel tiles / fp32 kernels), the (y, r) gradients
+@pytest.mark.parametrize("case", [c for c in TC_FWD_CASES if c[:5] != (3, 48, 40, 96, 160)] + [(2, 8, 16, 8, 12, 1), (2, 8, 16, 8, 12, 2)])
+@pytest.mark.parametrize("impl", [0, 4])
+def test_mask_epilogue_gather(case, impl):
+    n, h, w, ci, co, st = case
+    k = _k3(impl)
+    x, wt = _rand(n, h, w, ci, seed=1), _rand(3, 3, ci, co, seed=3)
+    src = _rand(n, h // st, w // st, co, seed=6)
+    got = k.conv_c(x.cuda(), wt.cuda(), None, 3, st, 0, 0.37, 0, mask_src=src.cuda())
+    want = EMU.conv_c(x.double(), wt.double(), None, 3, st, 0, 0.37, 0, mask_src=src.double())
+    assert got.shape == want.shape and rel_err(got, want) < 1e-4, (case, rel_err(got, want))
+
+
+@pytest.mark.parametrize("case", TC_DGRAD_CASES + [(2, 8, 16, 8, 12, 1), (2, 8, 16, 8, 12, 2)])
+@pytest.mark.parametrize("impl", [0, 4])
+def test_mask_epilogue_transposed(case, impl):
+    n, h, w, ci, co, st = case
+    k = _k3(impl)
+    dy, wt = _rand(n, h // st, w // st, co, seed=2), _rand(3, 3, ci, co, seed=3)
+    src = _rand(n, h, w, ci, seed=6)
+    got = k.conv_t(dy.cuda(), wt.cuda(), None, 3, st, 0, 0.37, 0, mask_src=src.cuda())
+    want = EMU.conv_t(dy.double(), wt.double(), None, 3, st, 0, 0.37, 0, mask_src=src.double())
+    assert got.shape == want.shape and rel_err(got, want) < 1e-4, (case, rel_err(got, want))
+
+
+PN_CASES = [
+    # form, n, h, w (large side), ci, co, stride
+    ("c", 1, 8, 128, 32, 32, 1), ("c", 2, 16, 136, 32, 32, 1), ("c", 1, 8, 128, 64, 64, 1), ("c", 2, 32, 144, 64, 64, 1),
+    ("c", 1, 16, 256, 64, 32, 1),                                   # kw-stacked kernel, one and two channel chunks
+    ("c", 2, 16, 16, 32, 32, 1), ("c", 1, 32, 24, 64, 64, 1), ("c", 2, 32, 64, 128, 128, 1), ("c", 1, 16, 8, 256, 256, 1),
+    ("c", 8, 2, 16, 256, 256, 1), ("c", 8, 4, 32, 256, 256, 1),    # split-K / split channel tiles: un-fused route
+    ("t", 1, 32, 16, 32, 32, 2), ("t", 2, 64, 32, 32, 64, 2), ("t", 1, 32, 48, 128, 256, 2), ("t", 1, 64, 16, 64, 128, 2),
+    ("t", 8, 4, 32, 256, 256, 2), ("t", 2, 128, 256, 32, 64, 2),
+    ("c", 2, 8, 16, 8, 12, 1),                                      # fp32 kernels + elementwise pixel norm
+]
+
+
+@pytest.mark.parametrize("case", PN_CASES)
+def test_pixel_norm_epilogue(case):
+    form, n, h, w, ci, co, st = case
+    k = _k3(0)
+    bias = _rand(co if form == "c" else ci, seed=4)
+    if form == "c":
+        x, wt = _rand(n, h, w, ci, seed=1), _rand(3, 3, ci, co, seed=3)
+    else:
+        x, wt = _rand(n, h // st, w // st, co, seed=2), _rand(3, 3, ci, co, seed=3)
+    y, r = k.conv_pn(x.cuda(), wt.cuda(), bias.cuda(), form, 3, st, 0, 0.37, 1e-8)
+    ye, re_ = EMU.conv_pn(x.double(), wt.double(), bias.double(), form, 3, st, 0, 0.37, 1e-8)
+    assert y.shape == ye.shape and r.shape == re_.shape
+    assert rel_err(y, ye) < 1e-4 and rel_err(r, re_) < 1e-4, (case, rel_err(y, ye), rel_err(r, re_))
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 16, 32), (1, 4, 8, 64), (1, 2, 16, 256), (3, 4, 4, 128)])
+def test_pixel_norm_y_form_gradients(shape):
+    k = _k3(0)
+    a, dy, u = _rand(*shape, seed=1), _rand(*shape, seed=2), _rand(*shape, seed=3)
+    y, r = EMU.pn_fwd(a.double(), 1e-8)
+    yc, rc = y.float().cuda(), r.float().cuda()
+    for want_cs in (False, True):
+        dz, cs = k.pn_bwd_mask_y(yc, rc, dy.cuda(), want_cs)
+        ze, ce = EMU.pn_bwd_mask(a.double(), r, dy.double(), want_cs)
+        assert rel_err(dz, ze) < 1e-5
+        if want_cs:
+            assert rel_err(cs, ce) < 1e-5
+    ga, gdy = k.pn_bwd_mask_second_y(yc, rc, dy.cuda(), u.cuda())
+    ge, he = EMU.pn_bwd_mask_second(a.double(), r, dy.double(), u.double())
+    assert rel_err(ga, ge) < 1e-5 and rel_err(gdy, he) < 1e-5
+
+
+def test_mask_epilogue_full_size_layer():
+    """The discriminator's top layer gradient (8 x 128 x 1024, 32 -> 32) with the mask applied in the epilogue
+    against the un-fused pair, bit for bit (same accumulators, same multiplication order)."""
+    k = _k3(0)
+    dy, wt = _rand(8, 128, 1024, 32, seed=1).cuda(), _rand(3, 3, 32, 32, seed=2).cuda()
+    src = _rand(8, 128, 1024, 32, seed=3).cuda()
+    fused = k.conv_t(dy, wt, None, 3, 1, 0, 0.0589, 0, mask_src=src)
+    plain = k.conv_t(dy, wt, None, 3, 1, 0, 0.0589, 0)
+    assert rel_err(fused, k.mask_mul(plain, src)) < 1e-6

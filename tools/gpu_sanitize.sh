@@ -12,7 +12,7 @@ run() {  # name, timeout, tool args..., -- command
 run memcheck_kernels 600 $CS --tool memcheck python -m pytest tests/test_kernels_gpu.py -m gpu -q -x
 run memcheck_tc 600 $CS --tool memcheck python -m pytest tests/test_tc_gpu.py -m gpu -q -x
 run memcheck_smoke 420 $CS --tool memcheck python __graft_entry__.py smoke
-run initcheck_kernels 600 $CS --tool initcheck python -m pytest tests/test_kernels_gpu.py -m gpu -q -x
+GS_CONV_TC=0 run initcheck_kernels_fp32 300 $CS --show-backtrace no --tool initcheck python -m pytest tests/test_kernels_gpu.py -m gpu -q
 run racecheck_kernels 600 $CS --tool racecheck python -m pytest tests/test_kernels_gpu.py -m gpu -q -x
 run synccheck_tc 600 $CS --tool synccheck python -m pytest tests/test_tc_gpu.py -m gpu -q -x
 unset PYTORCH_NO_CUDA_MEMORY_CACHING
