@@ -222,13 +222,15 @@ class KernelProfiler(object):
         return wrapped
 
     def _wrap_w(self, fn):
-        def wrapped(x, dy, ksize, stride, wswap, alpha):
-            out, s, e, _ = self._timed(None, None, lambda: fn(x, dy, ksize, stride, wswap, alpha))
+        def wrapped(x, dy, ksize, stride, wswap, alpha, bias_of=None, out=None):
+            res, s, e, outs = self._timed(None, None, lambda: fn(x, dy, ksize, stride, wswap, alpha, bias_of=bias_of, out=out))
             n, h, wd, ci = x.shape
             co = dy.shape[3]
             flops = 2.0 * (n * h * wd // (stride * stride)) * ksize * ksize * ci * co
-            self.records.append((("conv_w", n, h, wd, ci, co, ksize, stride), s, e, flops, 4.0 * (x.numel() + dy.numel() + out.numel())))
-            return out
+            written = [o for o in (out if out is not None else outs) if torch.is_tensor(o)]
+            self.records.append((("conv_w", n, h, wd, ci, co, ksize, stride), s, e, flops,
+                                 4.0 * (x.numel() + dy.numel() + sum(o.numel() for o in written))))
+            return res
         return wrapped
 
     def _wrap_ew(self, name, fn):

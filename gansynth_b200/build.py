@@ -8,7 +8,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgansynth_b200.so")
-SOURCES = ["abi.cu", "conv.cu", "elementwise.cu", "dense.cu", "spectral.cu", "io.cu", "tc_probe.cu"]
+SOURCES = ["abi.cu", "conv.cu", "elementwise.cu", "dense.cu", "spectral.cu", "io.cu"]
+PROBE_LIB = os.path.join(HERE, "libgansynth_b200_probe.so")     # development self-test, not the product ABI
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
 
@@ -18,6 +19,20 @@ def _stale(target, deps):
         return True
     t = os.path.getmtime(target)
     return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_prof(verbose=False):
+    """The stage-profiling variant (conv.cu with -DGS_TC_PROF) -> libgansynth_b200_prof.so; a development tool
+    (tools/tc_stage_profile.py, GS_LIB=prof), never loaded by default."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    build()
+    o = os.path.join(CSRC, "conv_prof.o")
+    cmd = [nvcc] + NVCC_FLAGS + ["-DGS_TC_PROF", "-c", os.path.join(CSRC, "conv.cu"), "-o", o]
+    subprocess.check_call(cmd)
+    objs = [os.path.join(CSRC, s.replace(".cu", ".o")) for s in SOURCES if s != "conv.cu"] + [o]
+    lib = os.path.join(HERE, "libgansynth_b200_prof.so")
+    subprocess.check_call([nvcc, "-shared", "-o", lib] + objs + ["-lcudart"])
+    return lib
 
 
 def build(force=False, verbose=False):
@@ -44,8 +59,14 @@ def build(force=False, verbose=False):
     if force or procs or _stale(LIB, objs):
         cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
         subprocess.check_call(cmd)
+    probe_src = os.path.join(CSRC, "tc_probe.cu")
+    if force or _stale(PROBE_LIB, [probe_src, os.path.join(CSRC, "abi.o")] + headers):
+        subprocess.check_call([nvcc] + NVCC_FLAGS + ["-shared", "-o", PROBE_LIB, probe_src, os.path.join(CSRC, "abi.o"), "-lcudart"])
     return LIB
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--prof" in sys.argv:
+        print(build_prof())
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -37,6 +37,32 @@ void gs_set_error(const char* fmt, ...);
     }                                                                              \
   } while (0)
 
+// ---- library context (include/gansynth_b200.h: gs_context_create / gs_context_bind) ---------------------------
+// All state the library keeps between calls lives here, in caller-owned memory: the device workspace the caller passed
+// (spectral twiddle tables | scratch slot for split weights used once | cache of split PARAMETER weights) and the host
+// table describing what the cache holds.  One context is bound per host thread; a context serves one stream at a time.
+struct GsPrepKey {
+  const float* w;
+  int kdim, ndim, nt, kc, kn, flip;
+  size_t off;
+};
+struct gs_context {
+  unsigned char* ws;
+  size_t bytes;
+  size_t tables_off, scratch_off, scratch, cache_off, cache, used;
+  GsPrepKey prep[512];
+  int nprep;
+  int cache_full_warned;
+  bool tables_ready;
+};
+constexpr size_t GS_WS_TABLES = 64 << 10;            // twiddle tables (16 KB used)
+constexpr size_t GS_WS_SCRATCH = (size_t)8 << 20;    // largest split weight: 9 * 256 * 256 * 2 * 2 bytes = 2.4 MB
+constexpr size_t GS_WS_CACHE = (size_t)256 << 20;
+gs_context* gs_bound_context();                      // context of the calling thread, or nullptr
+#define GS_NEED_CONTEXT(ctx, what)                                                                         \
+  gs_context* ctx = gs_bound_context();                                                                    \
+  GS_CHECK_ARG(ctx != nullptr, what ": no context bound to this thread (gs_context_create + gs_context_bind)")
+
 static inline int gs_num_sms() {
   static int sms = 0;
   if (sms == 0) {

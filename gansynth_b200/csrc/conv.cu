@@ -143,18 +143,49 @@ int try_conv1x1(const float* x, const float* w, const float* bias, float* y, lon
 // used by several convolutions in the same orientation (D(real), D(fake), the penalty passes): it is split
 // once.  The host invalidates the cache whenever the parameters change (gs_conv_weight_cache_reset) and at the
 // start of every sub-step, so a captured CUDA graph always contains the split kernel of the first use.
-struct TcWorkspace {
-  unsigned char* buf = nullptr;
-  size_t scratch = (size_t)8 << 20, cache = (size_t)256 << 20, used = 0;
-};
-TcWorkspace g_tc_ws;   // calls are stream-ordered on one stream per process (see gansynth_b200.h)
-struct PrepKey {
-  const float* w;
-  int kdim, ndim, nt, kc, kn, flip;
-  size_t off;
-};
-PrepKey g_prep[512];
-int g_nprep = 0;
+// (the workspace and the cache table live in the caller's gs_context, common.cuh)
+// Where the split copy of `w` in the layout (nt, kc tag, kn, flip) goes: the cached copy of a parameter (need_prep =
+// false), a new cache entry, or the scratch slot.
+unsigned char* prep_slot(gs_context* ctx, bool cacheable, const float* w, int kdim, int ndim, int nt, int kc, int kn, int flip,
+                         size_t wbytes, bool* need_prep) {
+  *need_prep = true;
+  if (cacheable) {
+    for (int i = 0; i < ctx->nprep; ++i) {
+      const GsPrepKey& k = ctx->prep[i];
+      if (k.w == w && k.kdim == kdim && k.ndim == ndim && k.nt == nt && k.kc == kc && k.kn == kn && k.flip == flip) {
+        *need_prep = false;
+        return ctx->ws + ctx->cache_off + k.off;
+      }
+    }
+    if (ctx->nprep < 512 && ctx->used + wbytes <= ctx->cache) {
+      ctx->prep[ctx->nprep++] = GsPrepKey{w, kdim, ndim, nt, kc, kn, flip, ctx->used};
+      unsigned char* dst = ctx->ws + ctx->cache_off + ctx->used;
+      ctx->used += (wbytes + 255) & ~(size_t)255;
+      return dst;
+    }
+    if (!ctx->cache_full_warned) {
+      ctx->cache_full_warned = 1;
+      fprintf(stderr, "gansynth_b200: the split-weight cache of this context is full (%d entries, %zu of %zu bytes): "
+                      "parameters are re-split at every use; pass a larger workspace\n", ctx->nprep, ctx->used, ctx->cache);
+    }
+  }
+  return ctx->ws + ctx->scratch_off;
+}
+
+#ifdef GS_TC_PROF
+// stage-profiling build only (tc_common.cuh): [role][wait0, wait1, wait2, total] cycle sums, filled by the kernels
+unsigned long long* g_prof = nullptr;
+unsigned long long* prof_table() {
+  if (!g_prof) {
+    cudaMalloc(&g_prof, 64 * 4 * sizeof(unsigned long long));
+    cudaMemset(g_prof, 0, 64 * 4 * sizeof(unsigned long long));
+  }
+  return g_prof;
+}
+#define TC_SET_PROF(p) (p).prof = prof_table()
+#else
+#define TC_SET_PROF(p)
+#endif
 
 int tc_auto_enabled() {
   static int v = -1;
@@ -180,9 +211,10 @@ int launch_tc_impl(const float* x, const float* w, const float* bias, float* y, 
                    cudaStream_t st, const Epi& epi, bool* fused) {
   using G = TcGeo<FORM>;
   const size_t wbytes = (size_t)9 * kdim * ndim * 2 * sizeof(__nv_bfloat16);
-  GS_CHECK_ARG(wbytes <= g_tc_ws.scratch, "conv_tc: weight of %zu bytes exceeds the scratch slot", wbytes);
-  if (!g_tc_ws.buf) GS_CUDA(cudaMalloc(&g_tc_ws.buf, g_tc_ws.scratch + g_tc_ws.cache));
+  GS_NEED_CONTEXT(ctx, "conv_tc");
+  GS_CHECK_ARG(wbytes <= ctx->scratch, "conv_tc: weight of %zu bytes exceeds the scratch slot", wbytes);
   TcParams p;
+  TC_SET_PROF(p);
   p.bias = bias; p.y = y;
   p.n_img = n; p.h_in = h_in; p.w_in = w_in; p.h_out = h_out; p.w_out = w_out; p.kdim = kdim; p.ndim = ndim;
   p.alpha = alpha; p.act = act;
@@ -296,23 +328,8 @@ int launch_tc_impl(const float* x, const float* w, const float* bias, float* y, 
   p.tmem_cols = cols;
   {
     // pre-split weights: cached copy of a parameter, else split now (into the cache or the scratch slot)
-    unsigned char* dst = g_tc_ws.buf;
     bool need_prep = true;
-    if (cacheable) {
-      for (int i = 0; i < g_nprep; ++i) {
-        const PrepKey& k = g_prep[i];
-        if (k.w == w && k.kdim == kdim && k.ndim == ndim && k.nt == nt && k.kc == KC && k.kn == w_is_kn && k.flip == flip) {
-          dst = g_tc_ws.buf + g_tc_ws.scratch + k.off;
-          need_prep = false;
-          break;
-        }
-      }
-      if (need_prep && g_nprep < 512 && g_tc_ws.used + wbytes <= g_tc_ws.cache) {
-        g_prep[g_nprep++] = PrepKey{w, kdim, ndim, nt, KC, w_is_kn, flip, g_tc_ws.used};
-        dst = g_tc_ws.buf + g_tc_ws.scratch + g_tc_ws.used;
-        g_tc_ws.used += (wbytes + 255) & ~(size_t)255;
-      }
-    }
+    unsigned char* dst = prep_slot(ctx, cacheable, w, kdim, ndim, nt, KC, w_is_kn, flip, wbytes, &need_prep);
     if (need_prep) {
       size_t total = (size_t)9 * kdim * ndim;
       int blocks = (int)((total + 255) / 256);
@@ -376,12 +393,19 @@ bool tck_ok(int h, int w, int kdim, int ndim) {
 int launch_tck(const float* x, const float* w, const float* bias, float* y, int n, int h, int wd, int kdim, int ndim,
                int w_is_kn, int flip, float alpha, int act, bool cacheable, cudaStream_t st, const Epi& epi, bool* fused) {
   const size_t wbytes = (size_t)9 * kdim * ndim * 2 * sizeof(__nv_bfloat16);
-  GS_CHECK_ARG(wbytes <= g_tc_ws.scratch, "conv_tck: weight of %zu bytes exceeds the scratch slot", wbytes);
-  if (!g_tc_ws.buf) GS_CUDA(cudaMalloc(&g_tc_ws.buf, g_tc_ws.scratch + g_tc_ws.cache));
+  GS_NEED_CONTEXT(ctx, "conv_tck");
+  GS_CHECK_ARG(wbytes <= ctx->scratch, "conv_tck: weight of %zu bytes exceeds the scratch slot", wbytes);
   TckParams p;
+  TC_SET_PROF(p);
   p.bias = bias; p.n_img = n; p.h = h; p.w = wd; p.kdim = kdim; p.nt = ndim; p.alpha = alpha; p.act = act;
   p.tiles_h = h / 8; p.tiles_w = (wd + 13) / 14; p.ntiles = n * p.tiles_h * p.tiles_w;
-  p.cat = (6 * ndim <= 256) && !getenv("GS_TC_NO_CAT");
+  // "cat" (hi x [hi | lo] as one double-width MMA) halves the MMA count of a K slice but doubles the accumulator columns
+  // the epilogue has to read back, and TMEM reads run at 64 B/clk per SM: 128 lanes x 6 nt columns = 1536 cycles per
+  // tile at nt = 32, more than the MMAs of a 32-channel contraction take.  Cat only when the contraction is long
+  // enough to hide that (GS_TCK_CAT=0/1 forces it for A/B runs).
+  p.cat = (6 * ndim <= 256) && kdim > 32 && !getenv("GS_TC_NO_CAT");
+  if (const char* e = getenv("GS_TCK_CAT")) p.cat = (e[0] == '1') && (6 * ndim <= 256);
+  p.nbuf = std::min(4, 512 / ((p.cat ? 6 : 3) * ndim));
   p.epi = getenv("GS_TC_NO_EPI") ? TC_EPI_PLAIN : epi.mode;
   p.eps = epi.eps; p.rvec = epi.rvec;
   const int nchunks = kdim / 32;
@@ -414,24 +438,9 @@ int launch_tck(const float* x, const float* w, const float* bias, float* y, int 
   if (used + a_stage <= budget) { ++p.sa; used += a_stage; }
   p.tmem_cols = 512;
   {
-    unsigned char* dst = g_tc_ws.buf;
-    bool need_prep = true;
     const int layout_tag = 1032;      // distinguishes the kw-stacked layout from conv_tc's in the cache
-    if (cacheable) {
-      for (int i = 0; i < g_nprep; ++i) {
-        const PrepKey& k = g_prep[i];
-        if (k.w == w && k.kdim == kdim && k.ndim == ndim && k.nt == ndim && k.kc == layout_tag && k.kn == w_is_kn && k.flip == flip) {
-          dst = g_tc_ws.buf + g_tc_ws.scratch + k.off;
-          need_prep = false;
-          break;
-        }
-      }
-      if (need_prep && g_nprep < 512 && g_tc_ws.used + wbytes <= g_tc_ws.cache) {
-        g_prep[g_nprep++] = PrepKey{w, kdim, ndim, ndim, layout_tag, w_is_kn, flip, g_tc_ws.used};
-        dst = g_tc_ws.buf + g_tc_ws.scratch + g_tc_ws.used;
-        g_tc_ws.used += (wbytes + 255) & ~(size_t)255;
-      }
-    }
+    bool need_prep = true;
+    unsigned char* dst = prep_slot(ctx, cacheable, w, kdim, ndim, ndim, layout_tag, w_is_kn, flip, wbytes, &need_prep);
     if (need_prep) {
       size_t total = (size_t)9 * kdim * ndim;
       int blocks = (int)((total + 255) / 256);
@@ -496,9 +505,11 @@ int tcw_block(int c) {
 }
 
 int launch_tcw(const float* big, const float* small, float* dw, int n, int bh, int bw, int adim, int bdim, int sh,
-               int sw, int stride, int out_ab, float alpha, cudaStream_t st) {
+               int sw, int stride, int out_ab, float alpha, cudaStream_t st, float* dbias = nullptr, int bias_side = 0) {
   TcwParams p;
+  TC_SET_PROF(p);
   p.dw = dw;
+  p.dbias = dbias; p.bias_side = dbias ? bias_side : 0;
   p.n_img = n; p.bh = bh; p.bw = bw; p.sh = sh; p.sw = sw; p.adim = adim; p.bdim = bdim; p.stride = stride;
   p.out_ab = out_ab; p.alpha = alpha;
   p.nch = tcw_block(adim);
@@ -548,6 +559,23 @@ int launch_tcw(const float* big, const float* small, float* dw, int n, int bh, i
   if (used + stage <= budget) { ++p.stages; used += stage; }
   if (used + raw <= budget) { ++p.ds; used += raw; }
   p.tiles_h = sh / tpr; p.tiles_w = sw / 8; p.ntiles = n * p.tiles_h * p.tiles_w;
+  {
+    // fused bias gradient over the big operand: the kh jobs of a channel block load overlapping row ranges; hand
+    // every tile row [0, stride * tpr) (relative to the tile's first image row) to exactly one of them
+    const int pb = stride == 1 ? 1 : 0;
+    p.bias_c0 = (stride == 1 && !p.nstack) ? 1 : 0;
+    p.bias_c1 = stride == 1 ? p.bias_c0 + 8 : 16;
+    int covered = 0, block = -1;
+    for (int j = 0; j < p.mjobs; ++j) {
+      if (p.ch0[j] != block) { block = p.ch0[j]; covered = 0; }
+      const int first = p.kh0[j] - pb;                                   // tile-relative image row of raw row 0
+      const int lo = std::max(first, covered), hi = std::min(first + stride * (tpr - 1) + p.nkh[j], stride * tpr);
+      p.bias_r0[j] = lo - first;
+      p.bias_r1[j] = hi > lo ? hi - first : lo - first;
+      if (hi > lo) covered = hi;
+    }
+    for (int j = p.mjobs; j < 8; ++j) p.bias_r0[j] = p.bias_r1[j] = 0;
+  }
   int cols = 32;
   while (cols < 3 * p.nb * (1 + p.cat)) cols <<= 1;       // same count stacked or not: 3 kw blocks x NB x (1 + cat)
   p.tmem_cols = cols;
@@ -578,9 +606,53 @@ int launch_tcw(const float* big, const float* small, float* dw, int n, int bh, i
 
 }  // namespace
 
+#ifdef GS_TC_PROF
+// copies the table to `out` (64 x 4 values) and clears it; synchronises the device
+extern "C" int gs_tc_prof_read(unsigned long long* out) {
+  GS_CUDA(cudaDeviceSynchronize());
+  GS_CUDA(cudaMemcpy(out, prof_table(), 64 * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  GS_CUDA(cudaMemset(prof_table(), 0, 64 * 4 * sizeof(unsigned long long)));
+  return GS_OK;
+}
+#endif
+
+// Re-splits, in place, every cached parameter weight that lies in [lo, hi) (both NULL: all of them): the caller has
+// just changed those parameters (optimiser update, checkpoint load).  The cache slots keep their addresses, so kernels
+// already recorded in CUDA graphs keep reading the right copies.  One launch per 48 entries.
+extern "C" int gs_conv_weight_cache_refresh(const float* lo, const float* hi, void* stream) {
+  gs_context* ctx = gs_bound_context();
+  if (!ctx) return GS_OK;
+  PrepBatch b;
+  b.njobs = 0; b.nblocks = 0;
+  auto flush = [&]() -> int {
+    if (b.njobs == 0) return GS_OK;
+    conv_prep_batch_kernel<<<b.nblocks, 256, 0, (cudaStream_t)stream>>>(b);
+    GS_CHECK_LAUNCH("conv_prep_batch");
+    b.njobs = 0; b.nblocks = 0;
+    return GS_OK;
+  };
+  for (int i = 0; i < ctx->nprep; ++i) {
+    const GsPrepKey& k = ctx->prep[i];
+    if (lo != nullptr && (k.w < lo || k.w >= hi)) continue;
+    PrepJob& j = b.jobs[b.njobs++];
+    j.w = k.w;
+    j.out = reinterpret_cast<__nv_bfloat16*>(ctx->ws + ctx->cache_off + k.off);
+    j.kdim = k.kdim; j.ndim = k.ndim; j.nt = k.nt; j.kc = k.kc; j.kn = k.kn; j.flip = k.flip;
+    j.block0 = b.nblocks;
+    b.nblocks += (int)(((size_t)9 * k.kdim * k.ndim + PREP_ELEMS_PER_BLOCK - 1) / PREP_ELEMS_PER_BLOCK);
+    if (b.njobs == 48) {
+      int rc = flush();
+      if (rc) return rc;
+    }
+  }
+  return flush();
+}
+
 extern "C" int gs_conv_weight_cache_reset(void) {
-  g_nprep = 0;
-  g_tc_ws.used = 0;
+  if (gs_context* ctx = gs_bound_context()) {
+    ctx->nprep = 0;
+    ctx->used = 0;
+  }
   return GS_OK;
 }
 
@@ -736,8 +808,43 @@ extern "C" int gs_conv2d_dgrad(const float* dy, const float* w, const float* bia
   return conv_dgrad_impl(dy, w, bias, dx, n, h, wd, ci, co, ksize, stride, wswap, alpha, act, impl, stream, Epi(), &fused);
 }
 
+namespace {
+int conv_wgrad_impl(const float* x, const float* dy, float* dw, int n, int h, int wd, int ci, int co, int ksize, int stride,
+                    int wswap, float alpha, int impl, void* stream, float* dbias, int bias_of_x, bool* bias_done,
+                    bool accumulate = false);
+}
+int gs_col_sum_acc(const float* v, float* out, long long rows, int c, void* stream);   // elementwise.cu: out += column sums
+
 extern "C" int gs_conv2d_wgrad(const float* x, const float* dy, float* dw, int n, int h, int wd, int ci, int co,
                                int ksize, int stride, int wswap, float alpha, int impl, void* stream) {
+  bool done = false;
+  return conv_wgrad_impl(x, dy, dw, n, h, wd, ci, co, ksize, stride, wswap, alpha, impl, stream, nullptr, 0, &done);
+}
+
+// Filter gradient and, from the same pass over the operands, the bias gradient dbias[c] = sum over pixels of dy
+// (bias_of_x = 0: conv2d layers, ops.py:240-244) or of x (bias_of_x = 1: the conv2d_transpose layers, whose
+// pre-activation gradient is the HIGH-resolution operand, ops.py:272-277); dbias may be NULL.  accumulate = 0: dw and
+// dbias are overwritten; 1: the results are ADDED to what they hold (several uses of one parameter summing into the
+// caller's gradient buffer: tf.gradients' AddN without the extra passes).
+extern "C" int gs_conv2d_wgrad_ex(const float* x, const float* dy, float* dw, float* dbias, int bias_of_x, int accumulate,
+                                  int n, int h, int wd, int ci, int co, int ksize, int stride, int wswap, float alpha,
+                                  int impl, void* stream) {
+  const int cb = bias_of_x ? ci : co;
+  if (dbias && !accumulate) GS_CUDA(cudaMemsetAsync(dbias, 0, (size_t)cb * sizeof(float), (cudaStream_t)stream));
+  bool done = false;
+  int rc = conv_wgrad_impl(x, dy, dw, n, h, wd, ci, co, ksize, stride, wswap, alpha, impl, stream, dbias, bias_of_x, &done,
+                           accumulate != 0);
+  if (rc || done || !dbias) return rc;
+  const long long rows = bias_of_x ? (long long)n * h * wd : (long long)n * (h / stride) * (wd / stride);
+  return gs_col_sum_acc(bias_of_x ? x : dy, dbias, rows, cb, stream);      // adds to the (zeroed or live) dbias
+}
+
+namespace {
+int conv_wgrad_impl(const float* x, const float* dy, float* dw, int n, int h, int wd, int ci, int co, int ksize, int stride,
+                    int wswap, float alpha, int impl, void* stream, float* dbias, int bias_of_x, bool* bias_done,
+                    bool accumulate) {
+  // every kernel below ADDS into dw with atomics: overwrite = zero first, accumulate = don't
+  *bias_done = false;
   ConvGeom g;
   int rc = make_geom(g, n, h, wd, ci, co, ksize, stride, wswap, alpha, 0);
   if (rc) return rc;
@@ -749,12 +856,14 @@ extern "C" int gs_conv2d_wgrad(const float* x, const float* dy, float* dw, int n
     const bool tcok = tcw_ok(ksize, ci, co, g.oh, g.ow);
     GS_CHECK_ARG(!(impl == 3 && !tcok), "conv2d_wgrad: tensor-core kernel does not cover this shape");
     if (impl == 3 || (impl == 0 && tcok && tc_auto_enabled())) {
-      GS_CUDA(cudaMemsetAsync(dw, 0, (size_t)ksize * ksize * ci * co * sizeof(float), (cudaStream_t)stream));
-      return launch_tcw(x, dy, dw, n, h, wd, ci, co, g.oh, g.ow, stride, !g.wswap, alpha, (cudaStream_t)stream);
+      if (!accumulate) GS_CUDA(cudaMemsetAsync(dw, 0, (size_t)ksize * ksize * ci * co * sizeof(float), (cudaStream_t)stream));
+      *bias_done = dbias != nullptr;
+      return launch_tcw(x, dy, dw, n, h, wd, ci, co, g.oh, g.ow, stride, !g.wswap, alpha, (cudaStream_t)stream, dbias,
+                        bias_of_x ? 2 : 1);
     }
   }
   size_t nel = (size_t)ksize * ksize * ci * co;
-  GS_CUDA(cudaMemsetAsync(dw, 0, nel * sizeof(float), st));
+  if (!accumulate) GS_CUDA(cudaMemsetAsync(dw, 0, nel * sizeof(float), st));
   if (impl != 1 && ksize == 1 && stride == 1 && (ci == 2 || co == 2)) {
     const int W = (ci == 2) ? co : ci;
     if (W != 2 && W <= 256 && 256 % W == 0) {
@@ -796,6 +905,7 @@ extern "C" int gs_conv2d_wgrad(const float* x, const float* dy, float* dw, int n
   if (small) return launch_w<2, 32>(x, dy, dw, n, h, wd, ci, co, g.oh, g.ow, g.pb, out_ab, alpha, st);
   return launch_w<2, 64>(x, dy, dw, n, h, wd, ci, co, g.oh, g.ow, g.pb, out_ab, alpha, st);
 }
+}  // namespace
 
 // conv2d_transpose (ops.py:250-280): value [n,h,w,cin], variable [k,k,cin,filters], output
 // [n,h*s,w*s,filters].  It is the dgrad form with the channel roles swapped.

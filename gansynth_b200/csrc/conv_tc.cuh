@@ -100,6 +100,9 @@ struct TcParams {
   int epi, aux_k;
   float eps;
   float* rvec;                    // [n, h_out, w_out]
+#ifdef GS_TC_PROF
+  unsigned long long* prof;       // [role][wait0, wait1, wait2, total] cycles
+#endif
 };
 
 enum TcEpi { TC_EPI_PLAIN = 0, TC_EPI_MASK = 1, TC_EPI_PNF = 2 };
@@ -120,33 +123,38 @@ constexpr int TC_MAX_AUX = 4;          // aux ring of the MASK epilogue
 // [n / nt][k / KC][tap][q][split][n % nt][e], value index k = KC*kc + 8*q + e.  w_is_kn: weight memory is
 // [tap][k][n] (else [tap][n][k]); flip: use tap 8 - t (180-degree rotation).
 template <int KC>
+__device__ __forceinline__ void conv_tc_prep_elem(size_t i, const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int kdim,
+                                                  int ndim, int nt, int w_is_kn, int flip) {
+  constexpr int Q = KC / 8;
+  const int nchunks = kdim / KC;
+  int e = (int)(i % 8);
+  size_t r = i / 8;
+  int nl = (int)(r % nt);
+  r /= nt;
+  int q = (int)(r % Q);
+  r /= Q;
+  int tap = (int)(r % 9);
+  r /= 9;
+  int kc = (int)(r % nchunks);
+  int ntile = (int)(r / nchunks);
+  int k = kc * KC + q * 8 + e, n = ntile * nt + nl;
+  int st = flip ? 8 - tap : tap;
+  float v = w_is_kn ? w[((size_t)st * kdim + k) * ndim + n] : w[((size_t)st * ndim + n) * kdim + k];
+  __nv_bfloat16 hi, lo;
+  tc::split_bf16(v, hi, lo);
+  const size_t plane = (size_t)nt * 8;                                   // elements of one [nt][8] plane
+  const size_t blk = (((size_t)ntile * nchunks + kc) * 9 + tap) * (2 * Q);   // first plane of this (tile, chunk, tap)
+  const size_t inner = (size_t)nl * 8 + e;
+  out[(blk + 2 * q) * plane + inner] = hi;
+  out[(blk + 2 * q + 1) * plane + inner] = lo;
+}
+
+template <int KC>
 __global__ void conv_tc_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int kdim, int ndim,
                                     int nt, int w_is_kn, int flip) {
-  constexpr int Q = KC / 8;
   const size_t total = (size_t)9 * kdim * ndim;
-  const int nchunks = kdim / KC;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int e = (int)(i % 8);
-    size_t r = i / 8;
-    int nl = (int)(r % nt);
-    r /= nt;
-    int q = (int)(r % Q);
-    r /= Q;
-    int tap = (int)(r % 9);
-    r /= 9;
-    int kc = (int)(r % nchunks);
-    int ntile = (int)(r / nchunks);
-    int k = kc * KC + q * 8 + e, n = ntile * nt + nl;
-    int st = flip ? 8 - tap : tap;
-    float v = w_is_kn ? w[((size_t)st * kdim + k) * ndim + n] : w[((size_t)st * ndim + n) * kdim + k];
-    __nv_bfloat16 hi, lo;
-    tc::split_bf16(v, hi, lo);
-    const size_t plane = (size_t)nt * 8;                                   // elements of one [nt][8] plane
-    const size_t blk = (((size_t)ntile * nchunks + kc) * 9 + tap) * (2 * Q);   // first plane of this (tile, chunk, tap)
-    const size_t inner = (size_t)nl * 8 + e;
-    out[(blk + 2 * q) * plane + inner] = hi;
-    out[(blk + 2 * q + 1) * plane + inner] = lo;
-  }
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    conv_tc_prep_elem<KC>(i, w, out, kdim, ndim, nt, w_is_kn, flip);
 }
 
 template <int FORM, int KC, int TPS, int CAT>
@@ -224,13 +232,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int a_depth = p.sa / p.nw;
     int apos0 = 0, apos1 = 0, rs = 0, seq = 0;
     uint32_t aph0 = 0, aph1 = 0, rph = 0;
+    TC_PROF_DECL
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++seq) {
       const bool w1 = (p.nw == 2) && (seq & 1);
       for (int kc = 0; kc < nchunks; ++kc) {
         const int stage = w1 ? 1 + 2 * apos1 : p.nw * apos0;
         const uint32_t aph = w1 ? aph1 : aph0;
-        tc::mbar_wait(&raw_full[rs], rph);
-        tc::mbar_wait(&a_empty[stage], aph ^ 1u);
+        TC_WAIT(&raw_full[rs], rph, 0);
+        TC_WAIT(&a_empty[stage], aph ^ 1u, 1);
         const unsigned char* raw = raw_smem + (size_t)rs * p.raw_slot_bytes;
         unsigned char* st = a_smem + (size_t)stage * a_stage_bytes;
         unsigned char* st_hi = st + (size_t)q * plane_a;
@@ -276,12 +285,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         if (++rs == p.ds) { rs = 0; rph ^= 1u; }
       }
     }
+    TC_PROF_FLUSH(p.prof, 16, warp == 4 && lane == 0);
   } else if (warp == 12) {
     // ============================== halo tiles: one TMA box per (tile, chunk) ===========================
     if (lane == 0) {
       int rs = 0;
       uint32_t rph = 0;
       const uint32_t box_bytes = (uint32_t)p.rpix * (KC * 4u);
+      TC_PROF_DECL
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         int t = tile;
         const int tw_ = t % p.tiles_w;
@@ -291,12 +302,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int w0 = (FORM == TC_C2) ? tw_ * 16 : tw_ * 8 - 1;
         const int h0 = (FORM == TC_C2) ? th_ * 32 : th_ * 16 - 1;
         for (int kc = 0; kc < nchunks; ++kc) {
-          tc::mbar_wait(&raw_empty[rs], rph ^ 1u);
+          TC_WAIT(&raw_empty[rs], rph ^ 1u, 0);
           tc::mbar_arrive_expect_tx(&raw_full[rs], box_bytes);
           tc::tma_load_4d(raw_smem + (size_t)rs * p.raw_slot_bytes, &tmx, (kc_begin + kc) * KC, w0, img0, h0, &raw_full[rs]);
           if (++rs == p.ds) { rs = 0; rph ^= 1u; }
         }
       }
+      TC_PROF_FLUSH(p.prof, 17, true);
     }
   } else if (warp == 13) {
     // ============================== weight blocks: one bulk copy per (chunk, tap group) =================
@@ -350,14 +362,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       uint32_t pa = 0, pb = 0;
       bool b_ready = false;                            // resident weights: waited for once
       int seq = mw;
+      TC_PROF_DECL
       for (int tile = blockIdx.x + mw * gridDim.x; tile < p.ntiles; tile += p.nw * gridDim.x, seq += p.nw) {
         const int ab = seq % p.nbuf;
         const uint32_t pacc = (uint32_t)(seq / p.nbuf) & 1u;
-        tc::mbar_wait(&acc_empty[ab], pacc ^ 1u);
+        TC_WAIT(&acc_empty[ab], pacc ^ 1u, 0);
         tc::tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(ab * acc_cols);
         for (int kc = 0; kc < nchunks; ++kc) {
-          tc::mbar_wait(&a_full[sa], pa);
+          TC_WAIT(&a_full[sa], pa, 1);
           tc::tc_fence_after();
           const uint64_t a_base = a_desc0 + (uint64_t)((uint32_t)sa * a_stage16);
           const uint32_t acc_rest = (kc > 0) ? 1u : 0u;
@@ -365,7 +378,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
           for (int g = 0; g < GROUPS; ++g) {
             if (!b_ready) {
-              tc::mbar_wait(&b_full[sb], pb);
+              TC_WAIT(&b_full[sb], pb, 2);
               tc::tc_fence_after();
             }
             const uint64_t b_base = b_desc0 + (uint64_t)((uint32_t)sb * b_stage16);
@@ -408,6 +421,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
         if (p.b_resident) b_ready = true;
       }
+      TC_PROF_FLUSH(p.prof, 18, mw == 0 && lane == 0);
     } else if (p.epi == TC_EPI_MASK && lane == 0) {
       // ============================== aux tiles of the MASK epilogue (this warp issues no MMAs) ===========
       // one TMA box per (tile, accumulator, 32-channel chunk), in the order the epilogue consumes them
@@ -445,13 +459,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const float inv_nt = 1.0f / (float)p.nt;
     int aslot = 0;
     uint32_t aph = 0, seq = 0;
+    TC_PROF_DECL
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       int t = tile;
       const int tw_ = t % p.tiles_w;
       t /= p.tiles_w;
       const int th_ = t % p.tiles_h;
       const int img0 = (t / p.tiles_h) * p.img;
-      tc::mbar_wait(&acc_full[ab], pacc);
+      TC_WAIT(&acc_full[ab], pacc, 0);
       tc::tc_fence_after();
 #pragma unroll 1
       for (int a = 0; a < G::NACC; ++a) {
@@ -495,7 +510,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           const uint32_t buf = seq & 1u;
           unsigned char* row = my_row0 + (size_t)buf * 16384;
           if (epi == TC_EPI_MASK) {
-            tc::mbar_wait(&aux_full[aslot], aph);
+            TC_WAIT(&aux_full[aslot], aph, 2);
             const unsigned char* arow = aux_smem + (size_t)aslot * 16384 + (size_t)m * 128;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -522,8 +537,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           tc::fence_proxy_async();
           // the store that used the OTHER staging buffer must have finished reading it before anyone gets
           // past this barrier and starts the next chunk
+          TC_PROF_BEGIN(1)
           if (tid == 0) tc::bulk_wait_read<0>();
           asm volatile("bar.sync 1, 128;" ::: "memory");
+          TC_PROF_END(1)
           if (tid == 0) {
             if (p.ksplit > 1) tc::tma_reduce_add_4d(&tmy.m[a], out_smem + (size_t)buf * 16384, n0 + c0, tw_ * 8, img0, th_ * p.rows);
             else tc::tma_store_4d(&tmy.m[a], out_smem + (size_t)buf * 16384, n0 + c0, tw_ * 8, img0, th_ * p.rows);
@@ -535,6 +552,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       tc::mbar_arrive(&acc_empty[ab]);
       if (++ab == p.nbuf) { ab = 0; pacc ^= 1u; }
     }
+    TC_PROF_FLUSH(p.prof, 19, tid == 0);
     if (tid == 0) tc::bulk_wait<0>();
   }
 

@@ -12,7 +12,8 @@
 //            (Cout = 64: three MMAs of width 192);
 //   acc    P_kw[r][c'] = sum_{kh, cin} x[r + kh - 1, x0 - 1 + c'] W[kh][kw]   (column block kw of the accumulator);
 //   out    y[r][x0 + j] = P_0[r][j] + P_1[r][j + 1] + P_2[r][j + 2], j < 14: the epilogue thread of lane (r, j)
-//            takes P_1 / P_2 from its neighbours with shfl_down 1 / 2 (a 16-lane row never crosses a warp).
+//            takes P_1 / P_2 from its neighbours with shfl_down 1 / 2 (a 16-lane row never crosses a warp); two
+//            epilogue warpgroups split the channels of every tile (640 threads).
 //
 // 12 (Cout = 32) or 18 (Cout = 64) MMAs per 32-channel chunk and tile instead of 36 / 54, and 102 KB instead of
 // 198 KB of operand fetches per tile.  Data path, rings and warp roles are those of conv_tc.cuh.
@@ -32,11 +33,15 @@ struct TckParams {
   int tiles_h, tiles_w, ntiles;
   int sa, sb, ds;                 // ring depths: operand stages, weight stages, raw slots
   int b_resident, cat, tmem_cols;
+  int nbuf;                       // accumulator buffers (2 .. 4): nbuf * (cat ? 6 : 3) * nt <= 512 TMEM columns
   // fused epilogues (TcEpi of conv_tc.cuh): MASK reads `aux` (shaped like y) through `tmaux` into a ring of `aux_k`
   // 16 KB slots filled by warp 15; PNF writes rvec
   int epi, aux_k;
   float eps;
   float* rvec;                    // [n, h, w]
+#ifdef GS_TC_PROF
+  unsigned long long* prof;       // [role][wait0, wait1, wait2, total] cycles
+#endif
 };
 
 constexpr int TCK_PIX = 160;                       // staged = raw pixels per tile (10 rows x 16 columns)
@@ -45,30 +50,63 @@ constexpr int TCK_OUT = 16384;                     // staging tile (8 x 14 pixel
 constexpr int TCK_THREADS = 640;                   // conv_tc's 16 warps + a second epilogue warpgroup (warps 16-19)
 
 // Weight pre-pass for the kw-stacked layout: plane index ((kc * 3 + kh) * 4 + q), plane = [split][kw][nt][8].
+__device__ __forceinline__ void conv_tck_prep_elem(size_t i, const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int kdim,
+                                                   int nt, int w_is_kn, int flip) {
+  int e = (int)(i % 8);
+  size_t r = i / 8;
+  int n = (int)(r % nt);
+  r /= nt;
+  int kw = (int)(r % 3);
+  r /= 3;
+  int q = (int)(r % 4);
+  r /= 4;
+  int kh = (int)(r % 3);
+  int kc = (int)(r / 3);
+  int k = kc * 32 + q * 8 + e;
+  int tap = kh * 3 + kw;
+  int st = flip ? 8 - tap : tap;
+  float v = w_is_kn ? w[((size_t)st * kdim + k) * nt + n] : w[((size_t)st * nt + n) * kdim + k];
+  __nv_bfloat16 hi, lo;
+  tc::split_bf16(v, hi, lo);
+  const size_t plane = (size_t)6 * nt * 8;
+  const size_t base = (((size_t)kc * 3 + kh) * 4 + q) * plane;
+  out[base + ((size_t)kw * nt + n) * 8 + e] = hi;
+  out[base + ((size_t)(3 + kw) * nt + n) * 8 + e] = lo;
+}
+
 __global__ void conv_tck_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int kdim, int nt,
                                      int w_is_kn, int flip) {
   const size_t total = (size_t)9 * kdim * nt;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int e = (int)(i % 8);
-    size_t r = i / 8;
-    int n = (int)(r % nt);
-    r /= nt;
-    int kw = (int)(r % 3);
-    r /= 3;
-    int q = (int)(r % 4);
-    r /= 4;
-    int kh = (int)(r % 3);
-    int kc = (int)(r / 3);
-    int k = kc * 32 + q * 8 + e;
-    int tap = kh * 3 + kw;
-    int st = flip ? 8 - tap : tap;
-    float v = w_is_kn ? w[((size_t)st * kdim + k) * nt + n] : w[((size_t)st * nt + n) * kdim + k];
-    __nv_bfloat16 hi, lo;
-    tc::split_bf16(v, hi, lo);
-    const size_t plane = (size_t)6 * nt * 8;
-    const size_t base = (((size_t)kc * 3 + kh) * 4 + q) * plane;
-    out[base + ((size_t)kw * nt + n) * 8 + e] = hi;
-    out[base + ((size_t)(3 + kw) * nt + n) * 8 + e] = lo;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    conv_tck_prep_elem(i, w, out, kdim, nt, w_is_kn, flip);
+}
+
+// Re-split of up to 48 cached parameter weights in ONE launch (gs_conv_weight_cache_refresh): block b works on the job
+// whose block range holds it, 2048 elements per block.
+struct PrepJob {
+  const float* w;
+  __nv_bfloat16* out;
+  int kdim, ndim, nt, kc, kn, flip;     // kc: 16 / 32 = conv_tc layout with that chunk, 1032 = the kw-stacked layout
+  int block0;                           // first block of this job
+};
+struct PrepBatch {
+  int njobs, nblocks;
+  PrepJob jobs[48];
+};
+constexpr int PREP_ELEMS_PER_BLOCK = 2048;
+__global__ void __launch_bounds__(256) conv_prep_batch_kernel(const __grid_constant__ PrepBatch b) {
+  int j = 0;
+  while (j + 1 < b.njobs && (int)blockIdx.x >= b.jobs[j + 1].block0) ++j;
+  const PrepJob& job = b.jobs[j];
+  const size_t total = (size_t)9 * job.kdim * job.ndim;
+  const size_t i0 = (size_t)((int)blockIdx.x - job.block0) * PREP_ELEMS_PER_BLOCK;
+#pragma unroll 1
+  for (int t = threadIdx.x; t < PREP_ELEMS_PER_BLOCK; t += 256) {
+    const size_t i = i0 + t;
+    if (i >= total) break;
+    if (job.kc == 1032) conv_tck_prep_elem(i, job.w, job.out, job.kdim, job.nt, job.kn, job.flip);
+    else if (job.kc == 32) conv_tc_prep_elem<32>(i, job.w, job.out, job.kdim, job.ndim, job.nt, job.kn, job.flip);
+    else conv_tc_prep_elem<16>(i, job.w, job.out, job.kdim, job.ndim, job.nt, job.kn, job.flip);
   }
 }
 
@@ -81,9 +119,10 @@ __global__ void __launch_bounds__(TCK_THREADS, 1) conv_tck_kernel(const __grid_c
   extern __shared__ unsigned char tck_smem_raw[];
   __shared__ uint64_t raw_full[TC_MAX_STAGES], raw_empty[TC_MAX_STAGES], a_full[TC_MAX_STAGES], a_empty[TC_MAX_STAGES];
   __shared__ uint64_t b_full[TC_MAX_BSTAGES], b_empty[TC_MAX_BSTAGES];
-  __shared__ uint64_t acc_full[2], acc_empty[2], aux_full[TC_MAX_AUX], aux_empty[TC_MAX_AUX];
+  __shared__ uint64_t acc_full[4], acc_empty[4], aux_full[TC_MAX_AUX], aux_empty[TC_MAX_AUX];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_s[64];
+  __shared__ float ss_x[2][128];          // PNF epilogue: per-pixel partial sums of squares of the two channel halves
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr uint32_t plane_a = TCK_PIX * 16u;
@@ -104,8 +143,8 @@ __global__ void __launch_bounds__(TCK_THREADS, 1) conv_tck_kernel(const __grid_c
     for (int s = 0; s < p.ds; ++s) { tc::mbar_init(&raw_full[s], 1); tc::mbar_init(&raw_empty[s], TC_CONV_WARPS * 32); }
     for (int s = 0; s < p.sa; ++s) { tc::mbar_init(&a_full[s], TC_CONV_WARPS * 32); tc::mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < p.sb; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { tc::mbar_init(&acc_full[s], 1); tc::mbar_init(&acc_empty[s], 128); }
-    for (int s = 0; s < TC_MAX_AUX; ++s) { tc::mbar_init(&aux_full[s], 1); tc::mbar_init(&aux_empty[s], 128); }
+    for (int s = 0; s < 4; ++s) { tc::mbar_init(&acc_full[s], 1); tc::mbar_init(&acc_empty[s], 256); }
+    for (int s = 0; s < TC_MAX_AUX; ++s) { tc::mbar_init(&aux_full[s], 1); tc::mbar_init(&aux_empty[s], 256); }
     tc::mbar_fence_init();
   }
   for (int c = tid; c < p.nt; c += TCK_THREADS) bias_s[c] = p.bias ? p.bias[c] : 0.0f;
@@ -128,10 +167,11 @@ __global__ void __launch_bounds__(TCK_THREADS, 1) conv_tck_kernel(const __grid_c
     const int p_first = (cw >> 2) * 32 + lane;
     int stage = 0, rs = 0;
     uint32_t aph = 0, rph = 0;
+    TC_PROF_DECL
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       for (int kc = 0; kc < nchunks; ++kc) {
-        tc::mbar_wait(&raw_full[rs], rph);
-        tc::mbar_wait(&a_empty[stage], aph ^ 1u);
+        TC_WAIT(&raw_full[rs], rph, 0);
+        TC_WAIT(&a_empty[stage], aph ^ 1u, 1);
         const unsigned char* raw = raw_smem + (size_t)rs * TCK_RAW;
         unsigned char* st = a_smem + (size_t)stage * a_stage_bytes;
         unsigned char* st_hi = st + (size_t)q * plane_a;
@@ -168,11 +208,13 @@ __global__ void __launch_bounds__(TCK_THREADS, 1) conv_tck_kernel(const __grid_c
         if (++rs == p.ds) { rs = 0; rph ^= 1u; }
       }
     }
+    TC_PROF_FLUSH(p.prof, 0, warp == 4 && lane == 0);
   } else if (warp == 12) {
     // ============================== halo tiles: one TMA box (32 ch, 16, 1, 10) per (tile, chunk) =========
     if (lane == 0) {
       int rs = 0;
       uint32_t rph = 0;
+      TC_PROF_DECL
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         int t = tile;
         const int tw_ = t % p.tiles_w;
@@ -180,12 +222,13 @@ __global__ void __launch_bounds__(TCK_THREADS, 1) conv_tck_kernel(const __grid_c
         const int th_ = t % p.tiles_h;
         const int n = t / p.tiles_h;
         for (int kc = 0; kc < nchunks; ++kc) {
-          tc::mbar_wait(&raw_empty[rs], rph ^ 1u);
+          TC_WAIT(&raw_empty[rs], rph ^ 1u, 0);
           tc::mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)TCK_RAW);
           tc::tma_load_4d(raw_smem + (size_t)rs * TCK_RAW, &tmx, kc * KC, tw_ * 14 - 1, n, th_ * 8 - 1, &raw_full[rs]);
           if (++rs == p.ds) { rs = 0; rph ^= 1u; }
         }
       }
+      TC_PROF_FLUSH(p.prof, 1, true);
     }
   } else if (warp == 13) {
     // ============================== weight blocks ======================================================
@@ -222,12 +265,13 @@ __global__ void __launch_bounds__(TCK_THREADS, 1) conv_tck_kernel(const __grid_c
     int sa = 0, sb = 0, ab = 0;
     uint32_t pa = 0, pb = 0, pacc = 0;
     bool b_ready = false;
+    TC_PROF_DECL
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-      tc::mbar_wait(&acc_empty[ab], pacc ^ 1u);
+      TC_WAIT(&acc_empty[ab], pacc ^ 1u, 0);
       tc::tc_fence_after();
       const uint32_t d = tmem_base + (uint32_t)(ab * acc_cols);
       for (int kc = 0; kc < nchunks; ++kc) {
-        tc::mbar_wait(&a_full[sa], pa);
+        TC_WAIT(&a_full[sa], pa, 1);
         tc::tc_fence_after();
         const uint64_t a_base = a_desc0 + (uint64_t)((uint32_t)sa * a_stage16);
         const uint32_t acc_rest = (kc > 0) ? 1u : 0u;
@@ -235,7 +279,7 @@ __global__ void __launch_bounds__(TCK_THREADS, 1) conv_tck_kernel(const __grid_c
 #pragma unroll
         for (int g = 0; g < GROUPS; ++g) {
           if (!b_ready) {
-            tc::mbar_wait(&b_full[sb], pb);
+            TC_WAIT(&b_full[sb], pb, 2);
             tc::tc_fence_after();
           }
           const uint64_t b_base = b_desc0 + (uint64_t)((uint32_t)sb * b_stage16);
@@ -271,9 +315,10 @@ __global__ void __launch_bounds__(TCK_THREADS, 1) conv_tck_kernel(const __grid_c
         }
         if (++sa == p.sa) { sa = 0; pa ^= 1u; }
       }
-      if (++ab == 2) { ab = 0; pacc ^= 1u; }
+      if (++ab == p.nbuf) { ab = 0; pacc ^= 1u; }
       if (p.b_resident) b_ready = true;
     }
+    TC_PROF_FLUSH(p.prof, 2, lane == 0);
   } else if (warp == 15) {
     // ============================== aux tiles of the MASK epilogue: one TMA box per (tile, chunk) ==========
     if (EPI == TC_EPI_MASK && lane == 0) {
@@ -295,121 +340,162 @@ __global__ void __launch_bounds__(TCK_THREADS, 1) conv_tck_kernel(const __grid_c
     }
   } else if (warp < 4 || warp >= 16) {
     // ============================== epilogue: TMEM -> shift-add over kw -> alpha, bias, leaky-relu -> TMA store =====
-    // Two warpgroups (warps 0-3 and 16-19) alternate tiles: group g drains accumulator buffer g through its own
-    // staging tile and named barrier, so a single warp's dependent LDTM -> SHFL -> FADD chain is never the pace.
+    // Both warpgroups (warps 0-3 and 16-19) work on EVERY tile: a warp reads the TMEM lane quarter warp % 4, so the two
+    // warps of a quarter split the COLUMNS -- group g owns channels [16 g, 16 g + 16) of each 32-channel chunk.  Per
+    // (tile, kw) the hi / lo column blocks are fetched with one TMEM round trip, and the accumulator buffer goes back
+    // to the MMA warp as soon as it is in registers, before the arithmetic and the store (measured with the stage
+    // profile, tools/tc_stage_profile.py: the buffer cycle MMA -> drain was the pace of this kernel, not the MMAs).
     const int grp = warp >= 16 ? 1 : 0;
     const int wq = warp & 3;                                         // TMEM lane quarter of this warp
     const int m = wq * 32 + lane;
     const int r = m >> 4, cp = m & 15;
     const bool writer = cp < 14;
-    const bool issuer = (wq == 0 && lane == 0);
+    const bool issuer = (grp == 0 && wq == 0 && lane == 0);
     const int srow = r * 14 + cp;                                    // row of the dense [8][14] staging tile
     const int sw = srow & 7;
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
-    unsigned char* stage_tile = out_smem + (size_t)grp * TCK_OUT;
-    unsigned char* row = stage_tile + (size_t)srow * 128;
-    const uint32_t acc0 = tmem_base + lane_base + (uint32_t)(grp * acc_cols);
-    uint32_t pacc = 0;
+    const int nchunks_out = p.nt >> 5;                               // 1 or 2
     const float inv_nt = 1.0f / (float)p.nt;
-    const int nchunks_out = p.nt >> 5;
-    // one (kw shift-added) 32-channel chunk of this thread's output pixel
-    auto load_chunk = [&](int c0, float (&v)[32]) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          float pk[16];
-          tc::tmem_ld16(acc0 + (uint32_t)(kw * p.nt + c0 + 16 * h), pk);
-          if (CAT) {
-            float p2[16];
-            tc::tmem_ld16(acc0 + (uint32_t)((3 + kw) * p.nt + c0 + 16 * h), p2);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) pk[j] += p2[j];
-          }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (kw == 0) v[16 * h + j] = pk[j];
-            else v[16 * h + j] += __shfl_down_sync(0xffffffffu, pk[j], kw);
-          }
-        }
-      }
-    };
-    int li = grp;                                       // index of the tile in this CTA's sequence (both groups)
-    for (int tile = blockIdx.x + grp * gridDim.x; tile < p.ntiles; tile += 2 * gridDim.x, li += 2) {
+    int ab = 0;
+    uint32_t pacc = 0, seq = 0;                                      // seq: 32-channel chunk number in this CTA's sequence
+    TC_PROF_DECL
+#ifdef GS_TC_PROF
+    long long pe0_ = 0, pe1_ = 0, pe2_ = 0;
+#endif
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       int t = tile;
       const int tw_ = t % p.tiles_w;
       t /= p.tiles_w;
       const int th_ = t % p.tiles_h;
       const int n = t / p.tiles_h;
-      tc::mbar_wait(&acc_full[grp], pacc);
+      TC_WAIT(&acc_full[ab], pacc, 0);
       tc::tc_fence_after();
-      float rscale = 1.0f;
-      float v[32];
-      bool have_v = false;
-      if (EPI == TC_EPI_PNF) {
-        // mean square of the activated outputs of this pixel over all channels (one chunk: kept in registers)
-        float ss = 0.0f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < p.nt; c0 += 32) {
-          load_chunk(c0, v);
+      const uint32_t acc0 = tmem_base + lane_base + (uint32_t)(ab * acc_cols + 16 * grp);
+      float v[2][16];
+#ifdef GS_TC_PROF
+      const long long te0_ = clock64();
+#endif
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float o = gs_lrelu(fmaf(v[j], p.alpha, bias_s[c0 + j]));
-            ss = fmaf(o, o, ss);
-          }
-        }
-        have_v = (p.nt == 32);
-        rscale = 1.0f / sqrtf(ss * inv_nt + p.eps);
-        const int px = tw_ * 14 + cp;
-        if (writer && px < p.w) p.rvec[((size_t)n * p.h + th_ * 8 + r) * p.w + px] = rscale;
-      }
-#pragma unroll 1
-      for (int c0 = 0; c0 < p.nt; c0 += 32) {
-        if (EPI != TC_EPI_PNF || !have_v) load_chunk(c0, v);
-        have_v = false;
-        // the previous store of this group must have finished reading the staging tile
-        if (issuer) tc::bulk_wait_read<0>();
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-        if (EPI == TC_EPI_MASK) {
-          // chunk number in the CTA's sequence -> ring slot / phase (the two groups share one ring)
-          const uint32_t s = (uint32_t)(li * nchunks_out + (c0 >> 5));
-          const uint32_t aslot = s % (uint32_t)p.aux_k, aph = (s / (uint32_t)p.aux_k) & 1u;
-          tc::mbar_wait(&aux_full[aslot], aph);
-          if (writer) {
-            const unsigned char* arow = aux_smem + (size_t)aslot * TCK_OUT + (size_t)srow * 128;
+      for (int c = 0; c < 2; ++c) {
+        if (c < nchunks_out) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 ax = *reinterpret_cast<const float4*>(arow + (((j >> 2) ^ sw) << 4));
-              float4 o;
-              o.x = v[j + 0] * p.alpha * gs_lrelu_slope(ax.x); o.y = v[j + 1] * p.alpha * gs_lrelu_slope(ax.y);
-              o.z = v[j + 2] * p.alpha * gs_lrelu_slope(ax.z); o.w = v[j + 3] * p.alpha * gs_lrelu_slope(ax.w);
-              *reinterpret_cast<float4*>(row + (((j >> 2) ^ sw) << 4)) = o;
+          for (int kw = 0; kw < 3; ++kw) {
+            uint32_t pk[16], p2[16];
+            tc::tmem_ld16_issue(acc0 + (uint32_t)(kw * p.nt + 32 * c), pk);
+            if (CAT) {
+              tc::tmem_ld16_issue(acc0 + (uint32_t)((3 + kw) * p.nt + 32 * c), p2);
+              tc::tmem_ld_wait(pk, p2);
+            } else {
+              tc::tmem_ld_wait(pk);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float x = __uint_as_float(pk[j]);
+              if (CAT) x += __uint_as_float(p2[j]);
+              if (kw == 0) v[c][j] = x;
+              else v[c][j] += __shfl_down_sync(0xffffffffu, x, kw);
             }
           }
-          tc::mbar_arrive(&aux_empty[aslot]);
-        } else if (writer) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 bv = *reinterpret_cast<const float4*>(&bias_s[c0 + j]);
-            float4 o;
-            o.x = fmaf(v[j + 0], p.alpha, bv.x); o.y = fmaf(v[j + 1], p.alpha, bv.y);
-            o.z = fmaf(v[j + 2], p.alpha, bv.z); o.w = fmaf(v[j + 3], p.alpha, bv.w);
-            if (p.act == 1) { o.x = gs_lrelu(o.x); o.y = gs_lrelu(o.y); o.z = gs_lrelu(o.z); o.w = gs_lrelu(o.w); }
-            if (EPI == TC_EPI_PNF) { o.x *= rscale; o.y *= rscale; o.z *= rscale; o.w *= rscale; }
-            *reinterpret_cast<float4*>(row + (((j >> 2) ^ sw) << 4)) = o;
-          }
-        }
-        tc::fence_proxy_async();
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-        if (issuer) {
-          tc::tma_store_4d(&tmy, stage_tile, c0, tw_ * 14, n, th_ * 8);
-          tc::bulk_commit();
         }
       }
+#ifdef GS_TC_PROF
+      const long long te1_ = clock64();
+      pe0_ += te1_ - te0_;
+#endif
+      // the accumulator is in registers: the MMA warp may start the tile after next
       tc::tc_fence_before();
-      tc::mbar_arrive(&acc_empty[grp]);
-      pacc ^= 1u;
+      tc::mbar_arrive(&acc_empty[ab]);
+      if (++ab == p.nbuf) { ab = 0; pacc ^= 1u; }
+#ifdef GS_TC_PROF
+      pe1_ += clock64() - te1_;
+#endif
+
+      float rscale = 1.0f;
+      if (EPI == TC_EPI_PNF) {
+        // mean square of the activated outputs of this pixel over ALL channels: the two groups exchange partial sums
+        float ss = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (c < nchunks_out) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float o = gs_lrelu(fmaf(v[c][j], p.alpha, bias_s[32 * c + 16 * grp + j]));
+              ss = fmaf(o, o, ss);
+            }
+          }
+        }
+        ss_x[grp][m] = ss;
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        ss += ss_x[grp ^ 1][m];                   // rewritten only after this tile's staging barrier
+        rscale = 1.0f / sqrtf(ss * inv_nt + p.eps);
+        const int px = tw_ * 14 + cp;
+        if (grp == 0 && writer && px < p.w) p.rvec[((size_t)n * p.h + th_ * 8 + r) * p.w + px] = rscale;
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        if (c < nchunks_out) {
+          const uint32_t buf = seq & 1u;
+          unsigned char* row = out_smem + (size_t)buf * TCK_OUT + (size_t)srow * 128;
+          if (EPI == TC_EPI_MASK) {
+            const uint32_t aslot = seq % (uint32_t)p.aux_k, aph = (seq / (uint32_t)p.aux_k) & 1u;
+            TC_WAIT(&aux_full[aslot], aph, 2);
+            if (writer) {
+              const unsigned char* arow = aux_smem + (size_t)aslot * TCK_OUT + (size_t)srow * 128;
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const int ch16 = 4 * grp + (j >> 2);
+                const float4 ax = *reinterpret_cast<const float4*>(arow + ((ch16 ^ sw) << 4));
+                float4 o;
+                o.x = v[c][j + 0] * p.alpha * gs_lrelu_slope(ax.x); o.y = v[c][j + 1] * p.alpha * gs_lrelu_slope(ax.y);
+                o.z = v[c][j + 2] * p.alpha * gs_lrelu_slope(ax.z); o.w = v[c][j + 3] * p.alpha * gs_lrelu_slope(ax.w);
+                *reinterpret_cast<float4*>(row + ((ch16 ^ sw) << 4)) = o;
+              }
+            }
+            tc::mbar_arrive(&aux_empty[aslot]);
+          } else if (writer) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const int ch16 = 4 * grp + (j >> 2);
+              const float4 bv = *reinterpret_cast<const float4*>(&bias_s[32 * c + 16 * grp + j]);
+              float4 o;
+              o.x = fmaf(v[c][j + 0], p.alpha, bv.x); o.y = fmaf(v[c][j + 1], p.alpha, bv.y);
+              o.z = fmaf(v[c][j + 2], p.alpha, bv.z); o.w = fmaf(v[c][j + 3], p.alpha, bv.w);
+              if (p.act == 1) { o.x = gs_lrelu(o.x); o.y = gs_lrelu(o.y); o.z = gs_lrelu(o.z); o.w = gs_lrelu(o.w); }
+              if (EPI == TC_EPI_PNF) { o.x *= rscale; o.y *= rscale; o.z *= rscale; o.w *= rscale; }
+              *reinterpret_cast<float4*>(row + ((ch16 ^ sw) << 4)) = o;
+            }
+          }
+#ifdef GS_TC_PROF
+          const long long te2_ = clock64();
+#endif
+          tc::fence_proxy_async();
+#ifdef GS_TC_PROF
+          pe2_ += clock64() - te2_;
+#endif
+          // Staging tile seq & 1 was last read by the store of chunk seq - 2; the issuer has waited for that store
+          // before the barrier of chunk seq - 1.  Here it waits for the store of chunk seq - 1, whose tile chunk
+          // seq + 1 rewrites after this barrier.
+          TC_PROF_BEGIN(1)
+          if (issuer) tc::bulk_wait_read<0>();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          TC_PROF_END(1)
+          if (issuer) {
+            tc::tma_store_4d(&tmy, out_smem + (size_t)buf * TCK_OUT, 32 * c, tw_ * 14, n, th_ * 8);
+            tc::bulk_commit();
+          }
+          ++seq;
+        }
+      }
     }
+    TC_PROF_FLUSH(p.prof, 3 + grp, wq == 0 && lane == 0);
+#ifdef GS_TC_PROF
+    if (p.prof != nullptr && grp == 0 && wq == 0 && lane == 0) {
+      atomicAdd(p.prof + 5 * 4 + 0, (unsigned long long)pe0_);                   // TMEM loads + shift-add
+      atomicAdd(p.prof + 5 * 4 + 1, (unsigned long long)pe1_);                   // fence + arrive on acc_empty
+      atomicAdd(p.prof + 5 * 4 + 2, (unsigned long long)pe2_);                   // fence.proxy.async
+      atomicAdd(p.prof + 5 * 4 + 3, (unsigned long long)(clock64() - pt0_));
+    }
+#endif
     if (issuer) tc::bulk_wait<0>();
   }
 

@@ -54,6 +54,17 @@ struct TcwParams {
   float alpha;
   uint32_t raw_big_chunk, raw_small_chunk, raw_slot_bytes;   // raw ring: 32-channel chunks, 1024-aligned
   uint32_t big_lo_off, small_off, stage_bytes;                // operand stage layout (bytes)
+  // fused bias gradient: dbias[c] += sum over all pixels of one operand (the layer's pre-activation gradient), taken
+  // from the converter warps' registers.  bias_side 1 = `small`, 2 = `big`.  Every pixel must be counted once: the
+  // small side by the jobs with mj == 0 (raw columns 1..8 in the N-stacked form, whose boxes overlap), the big side
+  // by the jobs with nj == 0 on the raw rows [bias_r0, bias_r1) of job mj (the kh jobs of a channel block overlap)
+  // and the raw columns [bias_c0, bias_c1).
+  float* dbias;
+  int bias_side, bias_c0, bias_c1;
+  int bias_r0[8], bias_r1[8];
+#ifdef GS_TC_PROF
+  unsigned long long* prof;       // [role][wait0, wait1, wait2, total] cycles
+#endif
 };
 
 constexpr int TCW_THREADS = 320;
@@ -64,7 +75,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const __grid_c
   extern __shared__ unsigned char tcw_smem_raw[];
   __shared__ uint64_t raw_full[TCW_MAX_STAGES], raw_empty[TCW_MAX_STAGES], full[TCW_MAX_STAGES], empty[TCW_MAX_STAGES], done;
   __shared__ uint32_t tmem_base_s;
-  __shared__ uint16_t big_tab[640];       // raw big pixel -> staged position (16-byte units, q = 0)
+  __shared__ uint16_t big_tab[640];       // raw big pixel -> staged position (16-byte units, q = 0); bit 15: counts for dbias
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   // job decode
@@ -89,7 +100,8 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const __grid_c
   }
   for (int px = tid; px < nbig_px; px += TCW_THREADS) {
     const int hr = px / p.bwraw, hc = px % p.bwraw;
-    big_tab[px] = (uint16_t)(hr * qj * p.pw + (S == 1 ? hc : (hc & 1) * 9 + (hc >> 1)));
+    const bool counts = p.bias_side == 2 && nj == 0 && hr >= p.bias_r0[mj] && hr < p.bias_r1[mj] && hc >= p.bias_c0 && hc < p.bias_c1;
+    big_tab[px] = (uint16_t)((hr * qj * p.pw + (S == 1 ? hc : (hc & 1) * 9 + (hc >> 1))) | (counts ? 0x8000 : 0));
   }
   if (warp == 9) tc::tmem_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
   if (warp == 8 && lane == 0) {
@@ -110,9 +122,22 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const __grid_c
     const int wq_b = qj >= 8 ? 1 : 8 / qj, wq_s = qb >= 8 ? 1 : 8 / qb;     // warps per chunk
     int stage = 0, rs = 0;
     uint32_t ph = 0, rph = 0;
+    // fused bias gradient: a warp visits at most two 8-channel chunks of the operand (q, q + 8)
+    const bool bias_big = p.bias_side == 2 && nj == 0 && p.bias_r1[mj] > p.bias_r0[mj];
+    const bool bias_small = p.bias_side == 1 && mj == 0;
+    float bsum[2][8];
+    auto bias_add = [](float (&b)[8], const float4& a0, const float4& a1) {
+      b[0] += a0.x; b[1] += a0.y; b[2] += a0.z; b[3] += a0.w;
+      b[4] += a1.x; b[5] += a1.y; b[6] += a1.z; b[7] += a1.w;
+    };
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bsum[i][j] = 0.0f;
+    TC_PROF_DECL
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-      tc::mbar_wait(&raw_full[rs], rph);
-      tc::mbar_wait(&empty[stage], ph ^ 1u);
+      TC_WAIT(&raw_full[rs], rph, 0);
+      TC_WAIT(&empty[stage], ph ^ 1u, 1);
       const unsigned char* raw = raw_smem + (size_t)rs * p.raw_slot_bytes;
       unsigned char* st = st_smem + (size_t)stage * p.stage_bytes;
       // ---- big: staged [row][q][pw] (hi block, then lo block)
@@ -129,9 +154,14 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const __grid_c
           tc::split2_bf16(v0.z, v0.w, h4.y, l4.y);
           tc::split2_bf16(v1.x, v1.y, h4.z, l4.z);
           tc::split2_bf16(v1.z, v1.w, h4.w, l4.w);
-          const uint32_t d = ((uint32_t)big_tab[px] + (uint32_t)(q * p.pw)) << 4;
+          const uint32_t tab = big_tab[px];
+          const uint32_t d = ((tab & 0x7fffu) + (uint32_t)(q * p.pw)) << 4;
           *reinterpret_cast<uint4*>(st + d) = h4;
           *reinterpret_cast<uint4*>(st + p.big_lo_off + d) = l4;
+          if (bias_big && (tab & 0x8000u)) {
+            if (q >= 8) bias_add(bsum[1], v0, v1);     // constant indices: the sums stay in registers
+            else bias_add(bsum[0], v0, v1);
+          }
         }
       }
       // ---- small: staged [row][hi q.. | lo q..][8 pixels]
@@ -149,6 +179,14 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const __grid_c
           tc::split2_bf16(v0.z, v0.w, h4.y, l4.y);
           tc::split2_bf16(v1.x, v1.y, h4.z, l4.z);
           tc::split2_bf16(v1.z, v1.w, h4.w, l4.w);
+          if (bias_small) {
+            bool counts = true;
+            if (p.nstack) { const int hc = px % 10; counts = hc >= 1 && hc <= 8; }
+            if (counts) {
+              if (q >= 8) bias_add(bsum[1], v0, v1);
+              else bias_add(bsum[0], v0, v1);
+            }
+          }
           if (!p.nstack) {
             const uint32_t r = (uint32_t)px >> 3, c = (uint32_t)px & 7u;
             const uint32_t d = ((r * 2u * (uint32_t)qb + (uint32_t)q) * 8u + c) << 4;
@@ -176,10 +214,35 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const __grid_c
       if (++rs == p.ds) { rs = 0; rph ^= 1u; }
     }
 
+    TC_PROF_FLUSH(p.prof, 8, warp == 0 && lane == 0);
+    // ============================== fused bias gradient: lanes -> one atomic per (warp, channel) =========
+    if (bias_big || bias_small) {
+      const int qn = bias_big ? qj : qb;
+      const int cbase = bias_big ? ch0 : nb0;
+      const int q0 = qn >= 8 ? warp : warp / (8 / qn);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int q = q0 + 8 * i;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v = bsum[i][j];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == 0 && q < qn && (i == 0 || qn > 8)) atomicAdd(p.dbias + cbase + q * 8 + j, v);
+        }
+      }
+    }
+
     // ============================== drain: TMEM -> atomics into dw =====================================
     if (warp < 4) {
+#ifdef GS_TC_PROF
+      const long long td0_ = clock64();
+#endif
       tc::mbar_wait(&done, 0);
       tc::tc_fence_after();
+#ifdef GS_TC_PROF
+      const long long td1_ = clock64();
+#endif
       const int m = warp * 32 + lane;
       const int g = m >> 3;
       const bool row_ok = g < nkh * qj;
@@ -216,6 +279,12 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const __grid_c
           }
         }
       }
+#ifdef GS_TC_PROF
+      if (p.prof != nullptr && tid == 0) {
+        atomicAdd(p.prof + 11 * 4 + 0, (unsigned long long)(td1_ - td0_));        // wait for the last MMA
+        atomicAdd(p.prof + 11 * 4 + 3, (unsigned long long)(clock64() - td1_));   // TMEM -> atomics
+      }
+#endif
     }
   } else if (warp == 8) {
     // ============================== TMA: one box per 32-channel chunk of each operand ====================
@@ -224,6 +293,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const __grid_c
       uint32_t rph = 0;
       const uint32_t bytes = (uint32_t)(big_chunks * nbig_px + small_chunks * nsmall_px) * 128u;
       const CUtensorMap* mb = &maps.big[p.map_id[mj]];
+      TC_PROF_DECL
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         int t = tile;
         const int tw_ = t % p.tiles_w;
@@ -233,7 +303,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const __grid_c
         const int ox0 = tw_ * 8, oy0 = th_ * p.tpr;
         const int bx0 = (S == 1) ? (p.nstack ? ox0 : ox0 - 1) : 2 * ox0;
         const int by0 = (S == 1) ? oy0 - 1 + kh0 : 2 * oy0 + kh0;
-        tc::mbar_wait(&raw_empty[rs], rph ^ 1u);
+        TC_WAIT(&raw_empty[rs], rph ^ 1u, 0);
         tc::mbar_arrive_expect_tx(&raw_full[rs], bytes);
         unsigned char* slot = raw_smem + (size_t)rs * p.raw_slot_bytes;
         for (int c = 0; c < big_chunks; ++c)
@@ -243,6 +313,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const __grid_c
                           p.nstack ? ox0 - 1 : ox0, n, oy0, &raw_full[rs]);
         if (++rs == p.ds) { rs = 0; rph ^= 1u; }
       }
+      TC_PROF_FLUSH(p.prof, 9, true);
     }
   } else {
     // ============================== MMA issue ==========================================================
@@ -263,8 +334,9 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const __grid_c
     const int ngroups = p.nstack ? 1 : 3;             // kw groups per K step (stacked: all three in one instruction)
     int stage = 0;
     uint32_t ph = 0, accum_first = 0;
+    TC_PROF_DECL
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-      tc::mbar_wait(&full[stage], ph);
+      TC_WAIT(&full[stage], ph, 0);
       tc::tc_fence_after();
       const uint64_t m_base = m_desc0 + (uint64_t)((uint32_t)stage * stage16);
       const uint64_t n_base = n_desc0 + (uint64_t)((uint32_t)stage * stage16);
@@ -304,6 +376,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const __grid_c
     }
     if (tc::elect_one()) tc::mma_commit(&done);
     __syncwarp();
+    TC_PROF_FLUSH(p.prof, 10, lane == 0);
   }
 
   tc::tc_fence_before();

@@ -422,9 +422,15 @@ extern "C" int gs_row_broadcast(const float* s, float* out, long long rows, int 
   GS_CHECK_LAUNCH("row_broadcast");
   return GS_OK;
 }
+int gs_col_sum_acc(const float* v, float* out, long long rows, int c, void* stream);
 extern "C" int gs_col_sum(const float* v, float* out, long long rows, int c, void* stream) {
   GS_CHECK_ARG(rows >= 0 && c > 0, "col_sum: bad shape");
   GS_CUDA(cudaMemsetAsync(out, 0, (size_t)c * sizeof(float), ST));
+  return gs_col_sum_acc(v, out, rows, c, stream);
+}
+// out[c] += column sums (library-internal: the accumulate form of gs_conv2d_wgrad_ex's fallback)
+int gs_col_sum_acc(const float* v, float* out, long long rows, int c, void* stream) {
+  GS_CHECK_ARG(rows >= 0 && c > 0, "col_sum: bad shape");
   if (rows == 0) return GS_OK;
   int lanes = EW_BLOCK / c;
   if (lanes < 1) lanes = 1;
@@ -449,7 +455,8 @@ __global__ void pixel_norm_vec_kernel(const float* __restrict__ a, const float* 
   // SLOTS = float4 per lane per pixel ((c/4) / lpp); R = pixels per lane group in flight per iteration (memory-level
   // parallelism: every load of the R pixels is issued before the first reduction).
   // flags (second-order forms of the fused pixel-norm/leaky-relu backward): 1 = multiply the incoming vector
-  // (dy in MODE 1, u in MODE 2) by lrelu'(a) first; 2 = multiply the result by lrelu'(a); 4 = `a` is given as y = a * r
+  // (dy in MODE 1, u in MODE 2) by lrelu'(a) first; 2 = multiply the result by lrelu'(a); 4 = `a` is given as y = a * r;
+  // 8 (MODE 2) = also write the MODE 1 result for the same incoming u to `rout` (shaped like `out`)
   const int lane = threadIdx.x & 31;
   const int li = lane % lpp, sub = lane / lpp, ppw = 32 / lpp;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
@@ -554,6 +561,12 @@ __global__ void pixel_norm_vec_kernel(const float* __restrict__ a, const float* 
                                    ka * tt.z + ku * ww.z + kd * dd.z, ka * tt.w + ku * ww.w + kd * dd.w);
             if (flags & 2) mask4(o, tt);
             *reinterpret_cast<float4*>(out + off[k] + ch) = o;
+            if (flags & 8) {
+              // second output: the MODE 1 result for the same (masked) u, r * u - r^3 / c * <a, u> * a; <a, u> = ua
+              const float k1 = r3c * ua;
+              *reinterpret_cast<float4*>(rout + off[k] + ch) =
+                  make_float4(r * ww.x - k1 * tt.x, r * ww.y - k1 * tt.y, r * ww.z - k1 * tt.z, r * ww.w - k1 * tt.w);
+            }
           }
         }
       }
@@ -700,6 +713,18 @@ extern "C" int gs_pixel_norm_bwd2_masked_y(const float* y, const float* r, const
   if (rows == 0) return GS_OK;
   pn_vec_launch<2>(y, r, dy, u, ga, nullptr, rows, c, 0.f, lpp, 3 | 4, ST);
   GS_CHECK_LAUNCH("pixel_norm_bwd2_masked_y");
+  return GS_OK;
+}
+
+// Both second-order pieces of the fused pixel-norm / leaky-relu backward from ONE pass over (y, r, dy, u):
+// ga = gs_pixel_norm_bwd2_masked_y(...), gdy = gs_pixel_norm_bwd_premask_y(y, r, u) -- 20 instead of 32 bytes per element.
+extern "C" int gs_pixel_norm_bwd2_pair_y(const float* y, const float* r, const float* dy, const float* u, float* ga, float* gdy,
+                                         long long rows, int c, void* stream) {
+  const int lpp = pn_lpp(c);
+  GS_CHECK_ARG(rows >= 0 && c > 0 && lpp > 0, "pixel_norm_bwd2_pair_y: unsupported channel count %d", c);
+  if (rows == 0) return GS_OK;
+  pn_vec_launch<2>(y, r, dy, u, ga, gdy, rows, c, 0.f, lpp, 3 | 4 | 8, ST);
+  GS_CHECK_LAUNCH("pixel_norm_bwd2_pair_y");
   return GS_OK;
 }
 

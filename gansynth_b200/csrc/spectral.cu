@@ -113,31 +113,33 @@ __device__ __forceinline__ void warp_fft1024(float (&re)[32], float (&im)[32], f
   fft32(re, im);
 }
 
+// Twiddle tables tw1024[32 * 32] and tw2048[1024] (float2 each) live at the head of the caller's workspace
+// (gs_context, common.cuh).  They are computed ON THE DEVICE by a kernel enqueued on the stream of the context's first
+// spectral call -- in double precision, rounded to float -- so no entry point allocates, copies from the host or
+// synchronises.
+__global__ void twiddle_init_kernel(float2* __restrict__ tw1024, float2* __restrict__ tw2048) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 1024) {
+    double sn, cs;
+    sincospi(-2.0 * (double)((i >> 5) * (i & 31)) / 1024.0, &sn, &cs);
+    tw1024[i] = make_float2((float)cs, (float)sn);
+    sincospi(-2.0 * (double)i / 2048.0, &sn, &cs);
+    tw2048[i] = make_float2((float)cs, (float)sn);
+  }
+}
+
 struct Tables {
   float2* tw1024;  // [32*32]
   float2* tw2048;  // [1024]
-  bool ready;
 };
-Tables g_tables = {nullptr, nullptr, false};
 
-int ensure_tables(cudaStream_t st) {
-  if (g_tables.ready) return GS_OK;
-  static float2 h1[1024], h2[1024];
-  for (int k1 = 0; k1 < 32; ++k1)
-    for (int l = 0; l < 32; ++l) {
-      double a = -2.0 * M_PI * (double)(k1 * l) / 1024.0;
-      h1[k1 * 32 + l] = make_float2((float)cos(a), (float)sin(a));
-    }
-  for (int k = 0; k < 1024; ++k) {
-    double a = -2.0 * M_PI * (double)k / 2048.0;
-    h2[k] = make_float2((float)cos(a), (float)sin(a));
-  }
-  GS_CUDA(cudaMalloc(&g_tables.tw1024, sizeof(h1)));
-  GS_CUDA(cudaMalloc(&g_tables.tw2048, sizeof(h2)));
-  GS_CUDA(cudaMemcpyAsync(g_tables.tw1024, h1, sizeof(h1), cudaMemcpyHostToDevice, st));
-  GS_CUDA(cudaMemcpyAsync(g_tables.tw2048, h2, sizeof(h2), cudaMemcpyHostToDevice, st));
-  GS_CUDA(cudaStreamSynchronize(st));
-  g_tables.ready = true;
+int ensure_tables(gs_context* ctx, cudaStream_t st, Tables* t) {
+  t->tw1024 = reinterpret_cast<float2*>(ctx->ws + ctx->tables_off);
+  t->tw2048 = t->tw1024 + 1024;
+  if (ctx->tables_ready) return GS_OK;
+  twiddle_init_kernel<<<4, 256, 0, st>>>(t->tw1024, t->tw2048);
+  GS_CHECK_LAUNCH("twiddle_init");
+  ctx->tables_ready = true;
   return GS_OK;
 }
 
@@ -670,7 +672,9 @@ extern "C" int gs_spectrogram_fwd(const float* wave, const float* hann, const in
   if (batch == 0) return GS_OK;
   GS_CHECK_ARG(runs == 1 || scratch != nullptr,
                "spectrogram_fwd: %d runs per clip need a scratch buffer of batch * runs * 1024 floats", runs);
-  int rc = ensure_tables(st);
+  GS_NEED_CONTEXT(ctx, "spectral");
+  Tables g_tables;
+  int rc = ensure_tables(ctx, st, &g_tables);
   if (rc) return rc;
   static bool attr = false;
   if (!attr) {
@@ -706,7 +710,9 @@ extern "C" int gs_waveform_fwd(const float* logmel, const float* inst, const flo
   if (batch == 0) return GS_OK;
   GS_CHECK_ARG(segs == 1 || scratch != nullptr,
                "waveform_fwd: %d segments per clip need a scratch buffer of batch * segments * 1024 floats", segs);
-  int rc = ensure_tables(st);
+  GS_NEED_CONTEXT(ctx, "spectral");
+  Tables g_tables;
+  int rc = ensure_tables(ctx, st, &g_tables);
   if (rc) return rc;
   static bool attr = false;
   if (!attr) {

@@ -5,6 +5,31 @@
 #include <stdint.h>
 #include <stdio.h>
 
+// Stage profiling build (-DGS_TC_PROF, libgansynth_b200_prof.so; tools/tc_stage_profile.py): every role of the
+// warp-specialised convolution kernels accumulates the cycles it spends waiting on each of its mbarriers and its total
+// run time; one lane per role adds them to a global table at the end.  The product build compiles none of this.
+#ifdef GS_TC_PROF
+#define TC_PROF_DECL long long pw0_ = 0, pw1_ = 0, pw2_ = 0; const long long pt0_ = clock64();
+#define TC_WAIT(bar, par, slot) do { const long long t_ = clock64(); tc::mbar_wait(bar, par); pw##slot##_ += clock64() - t_; } while (0)
+#define TC_PROF_BEGIN(slot) const long long tb##slot##_ = clock64();
+#define TC_PROF_END(slot) pw##slot##_ += clock64() - tb##slot##_;
+#define TC_PROF_FLUSH(prof, role, cond)                                                                  \
+  do {                                                                                                   \
+    if ((prof) != nullptr && (cond)) {                                                                   \
+      atomicAdd((prof) + (role) * 4 + 0, (unsigned long long)pw0_);                                      \
+      atomicAdd((prof) + (role) * 4 + 1, (unsigned long long)pw1_);                                      \
+      atomicAdd((prof) + (role) * 4 + 2, (unsigned long long)pw2_);                                      \
+      atomicAdd((prof) + (role) * 4 + 3, (unsigned long long)(clock64() - pt0_));                        \
+    }                                                                                                    \
+  } while (0)
+#else
+#define TC_PROF_DECL
+#define TC_WAIT(bar, par, slot) tc::mbar_wait(bar, par)
+#define TC_PROF_BEGIN(slot)
+#define TC_PROF_END(slot)
+#define TC_PROF_FLUSH(prof, role, cond)
+#endif
+
 namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -178,6 +203,34 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Split form of tmem_ld16: issue several loads, then ONE wait for all of them (a TMEM round trip is ~100 cycles).  The
+// wait takes the destination registers as in/out operands so that no use of them can be scheduled above it.
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&a)[16], uint32_t (&b)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]),
+                 "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]), "+r"(b[0]),
+                 "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]), "+r"(b[8]), "+r"(b[9]),
+                 "+r"(b[10]), "+r"(b[11]), "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&a)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]),
+                 "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15])
+               :
+               : "memory");
 }
 
 // ---- fp32 -> bf16 (hi, lo) split: x ~= hi + lo with |x - hi - lo| <= 2^-17 |x| ------------------------

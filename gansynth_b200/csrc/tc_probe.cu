@@ -7,7 +7,7 @@
 // `shift` / `gstride` exercise exactly the "shifted window into a halo tile" addressing (descriptor start
 // address and stride fields) that gives the 3x3 taps without re-staging the tile.
 #include "common.cuh"
-#include "gansynth_b200.h"
+#include "tc_probe.h"
 #include "tc_common.cuh"
 
 namespace {

@@ -37,6 +37,7 @@ _SKIP_WGRAD = False
 # GS_NO_FUSED_EW=1 keeps the un-fused elementwise chain (MaskMul, ColSum, PixelNorm) for A/B runs
 FUSED_EW = os.environ.get("GS_NO_FUSED_EW", "0") != "1"
 FUSED_MC = FUSED_EW and os.environ.get("GS_NO_FUSED_MC", "0") != "1"
+FUSED_WB = FUSED_EW and os.environ.get("GS_NO_FUSED_WB", "0") != "1"      # bias gradient inside the filter-gradient kernel
 
 
 @contextlib.contextmanager
@@ -107,6 +108,81 @@ class ConvW(Function):
         return gx, gdy, None, None, None, None
 
 
+class ConvWB(Function):
+    """(dw, db) = (ConvW(x, dy), column sum of the layer's pre-activation gradient) from ONE pass over the operands
+    (gs_conv2d_wgrad_ex).  `bias_of`: 'dy' for conv2d layers, 'x' for conv2d_transpose layers (there the pre-activation
+    gradient is the high-resolution operand `x` of the filter-gradient form)."""
+
+    @staticmethod
+    def forward(ctx, x, dy, ksize, stride, wswap, alpha, bias_of):
+        ctx.cfg = (ksize, stride, wswap, alpha)
+        ctx.bias_of = bias_of
+        ctx.lead = tuple((x if bias_of == "x" else dy).shape[:-1])
+        ctx.save_for_backward(x, dy)
+        return K.conv_w(x, dy, ksize, stride, wswap, alpha, bias_of=bias_of)
+
+    @staticmethod
+    def backward(ctx, gw, gb):
+        x, dy = ctx.saved_tensors
+        cfg = ctx.cfg
+        gx = ConvT.apply(dy, gw, *cfg) if ctx.needs_input_grad[0] else None
+        gdy = ConvC.apply(x, gw, *cfg) if ctx.needs_input_grad[1] else None
+        if ctx.bias_of == "x" and ctx.needs_input_grad[0]:
+            gx = gx + RowBroadcast.apply(gb, ctx.lead)
+        if ctx.bias_of == "dy" and ctx.needs_input_grad[1]:
+            gdy = gdy + RowBroadcast.apply(gb, ctx.lead)
+        return gx, gdy, None, None, None, None, None
+
+
+# Gradient sinks: data_ptr of a parameter (a view of the packed parameter buffer) -> the view of the packed GRADIENT
+# buffer laid out like it.  While a sink map is active (models.GANSynth._backward) and the backward pass is a plain
+# first-order one, the convolution layers ADD their filter / bias gradients straight into the sinks
+# (gs_conv2d_wgrad_ex, accumulate = 1) and hand autograd None: the three uses of a discriminator weight then cost no
+# zero-fill, no AddN pass and no copy into the flat buffer.
+_GRAD_SINKS = None
+
+
+@contextlib.contextmanager
+def grad_sinks(mapping):
+    global _GRAD_SINKS
+    prev, _GRAD_SINKS = _GRAD_SINKS, (mapping if FUSED_WB else None)
+    try:
+        yield
+    finally:
+        _GRAD_SINKS = prev
+
+
+def _sink(key):
+    """The gradient sink of the parameter whose data_ptr is `key`, if sinks are active in a first-order backward."""
+    if _GRAD_SINKS is None or key is None or torch.is_grad_enabled():
+        return None
+    return _GRAD_SINKS.get(key)
+
+
+def _wgrad_and_bias(form, x, dz, cfg, want_dw, want_db, w_key=None, b_key=None):
+    """Parameter gradients of a conv layer in gather ('c') or transposed ('t') form from its input x and its
+    pre-activation gradient dz -> (dw, db); one kernel when both are wanted.  With active gradient sinks for the
+    parameters (`w_key` / `b_key`: their data_ptr) the results are accumulated there and (None, None) is returned."""
+    dw = db = None
+    w_sink = _sink(w_key) if want_dw else None
+    if w_sink is not None:
+        b_sink = _sink(b_key) if want_db else None
+        if not want_db or b_sink is not None:
+            if form == "c":
+                K.conv_w(x, dz, *cfg, bias_of="dy" if want_db else None, out=(w_sink, b_sink))
+            else:
+                K.conv_w(dz, x, *cfg, bias_of="x" if want_db else None, out=(w_sink, b_sink))
+            return None, None
+    if want_dw and want_db and FUSED_WB:
+        dw, db = ConvWB.apply(x, dz, *cfg, "dy") if form == "c" else ConvWB.apply(dz, x, *cfg, "x")
+        return dw, db
+    if want_dw:
+        dw = ConvW.apply(x, dz, *cfg) if form == "c" else ConvW.apply(dz, x, *cfg)
+    if want_db:
+        db = ColSum.apply(dz)
+    return dw, db
+
+
 class PreMasked(object):
     """Wrapper protocol (D side).  `t` is the output y = leaky_relu(z) of a ConvLayer built with premasked=True: whoever
     consumes it returns the gradient w.r.t. the layer's PRE-activation z, i.e. lrelu'(y) * (gradient w.r.t. y) -- a
@@ -152,6 +228,7 @@ class ConvLayer(Function):
         ctx.cfg = (ksize, stride, wswap, alpha)
         ctx.form, ctx.act, ctx.has_bias, ctx.premasked = form, act, bias is not None, premasked
         ctx.x_premasked = x_premasked
+        ctx.w_key, ctx.b_key = w.data_ptr(), (bias.data_ptr() if bias is not None else None)
         ctx.save_for_backward(x, w, y)
         return y
 
@@ -174,10 +251,10 @@ class ConvLayer(Function):
                 dx = ConvMasked.apply(dz, w, x, "t" if ctx.form == "c" else "c", *cfg)
             else:
                 dx = (ConvT if ctx.form == "c" else ConvC).apply(dz, w, *cfg)
-        if ctx.needs_input_grad[1] and not _SKIP_WGRAD:
-            dw = ConvW.apply(x, dz, *cfg) if ctx.form == "c" else ConvW.apply(dz, x, *cfg)
-        if want_db and db is None:
-            db = ColSum.apply(dz)
+        want_dw = ctx.needs_input_grad[1] and not _SKIP_WGRAD
+        if want_dw or (want_db and db is None):
+            dw, db2 = _wgrad_and_bias(ctx.form, x, dz, cfg, want_dw, want_db and db is None, ctx.w_key, ctx.b_key)
+            db = db if db is not None else db2
         return dx, dw, db, None, None, None, None, None, None, None, None
 
 
@@ -233,6 +310,7 @@ class ConvPnLayer(Function):
         y, r = K.conv_pn(x, w, bias, form, ksize, stride, wswap, alpha, eps)
         ctx.cfg = (ksize, stride, wswap, alpha)
         ctx.form, ctx.has_bias = form, bias is not None
+        ctx.w_key, ctx.b_key = w.data_ptr(), (bias.data_ptr() if bias is not None else None)
         ctx.save_for_backward(x, xr, w)
         ctx.mark_non_differentiable(r)
         return y, r
@@ -246,10 +324,8 @@ class ConvPnLayer(Function):
             dx = (ConvT if ctx.form == "c" else ConvC).apply(dz, w, *cfg)
             if xr is not None:
                 dx = PnBwdMaskY.apply(x, xr, dx)
-        if ctx.needs_input_grad[2] and not _SKIP_WGRAD:
-            dw = ConvW.apply(x, dz, *cfg) if ctx.form == "c" else ConvW.apply(dz, x, *cfg)
-        if ctx.has_bias and ctx.needs_input_grad[3] and not _SKIP_WGRAD:
-            db = ColSum.apply(dz)
+        dw, db = _wgrad_and_bias(ctx.form, x, dz, cfg, ctx.needs_input_grad[2] and not _SKIP_WGRAD,
+                                 ctx.has_bias and ctx.needs_input_grad[3] and not _SKIP_WGRAD, ctx.w_key, ctx.b_key)
         return dx, None, dw, db, None, None, None, None, None, None
 
 

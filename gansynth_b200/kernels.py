@@ -57,8 +57,20 @@ class CudaBackend(object):
         self.weight_cache_reset()
 
     def weight_cache_reset(self):
-        if _lib.is_loaded():
-            _lib.load().gs_conv_weight_cache_reset()
+        """Drops every cached split weight (new parameter buffers: the cached addresses mean nothing any more)."""
+        _lib.reset_weight_cache()
+
+    def weight_cache_refresh(self, flat=None):
+        """Re-splits in place the cached copies of the parameters inside `flat` (None: all) -- to be called after every
+        change of parameter VALUES (optimiser update, load): the cache then never holds a stale copy, its slots keep
+        their addresses (CUDA graphs stay valid), and the sub-steps contain no split kernels."""
+        if not _lib.is_loaded() or not _lib._contexts:
+            return
+        if flat is None:
+            _lib.call("gs_conv_weight_cache_refresh", None, None, _stream())
+        else:
+            _lib.call("gs_conv_weight_cache_refresh", flat.data_ptr(), flat.data_ptr() + flat.numel() * flat.element_size(),
+                      _stream())
 
     def _impl(self, precise, w=None):
         impl = self.fwd_impl if (precise and self.fwd_impl >= 0) else self.impl
@@ -107,15 +119,30 @@ class CudaBackend(object):
                   float(alpha), int(act), int(epi), _ptr(aux), _ptr(r), float(eps), self._impl(precise, w), _stream())
         return (out, r) if want_r else out
 
-    def conv_w(self, x, dy, ksize, stride, wswap, alpha):
+    def conv_w(self, x, dy, ksize, stride, wswap, alpha, bias_of=None, out=None):
+        """Filter gradient; with `bias_of` ('dy' or 'x') also the column sum of that operand (the bias gradient of the
+        layer, taken from the same pass) -> (dw, db).  `out` = (dw buffer, db buffer or None): the results are ADDED to
+        those tensors (gradient accumulation in the caller's buffer) and nothing is returned."""
         x, dy = _chk(x, dy)
         n, h, wd, ci = x.shape
         co = dy.shape[3]
         shape = (ksize, ksize, co, ci) if wswap else (ksize, ksize, ci, co)
+        if out is not None:
+            dw, db = out
+            assert tuple(dw.shape) == shape and dw.is_contiguous() and (db is None or bias_of in ("dy", "x"))
+            _lib.call("gs_conv2d_wgrad_ex", _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), int(bias_of == "x"), 1, n, h, wd, ci, co,
+                      ksize, stride, int(wswap), float(alpha), self.impl, _stream())
+            return None
         dw = torch.empty(shape, device=x.device, dtype=torch.float32)
-        _lib.call("gs_conv2d_wgrad", _ptr(x), _ptr(dy), _ptr(dw), n, h, wd, ci, co, ksize, stride, int(wswap),
-                  float(alpha), self.impl, _stream())
-        return dw
+        if bias_of is None:
+            _lib.call("gs_conv2d_wgrad", _ptr(x), _ptr(dy), _ptr(dw), n, h, wd, ci, co, ksize, stride, int(wswap),
+                      float(alpha), self.impl, _stream())
+            return dw
+        assert bias_of in ("dy", "x")
+        db = torch.empty((ci if bias_of == "x" else co,), device=x.device, dtype=torch.float32)
+        _lib.call("gs_conv2d_wgrad_ex", _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), int(bias_of == "x"), 0, n, h, wd, ci, co, ksize,
+                  stride, int(wswap), float(alpha), self.impl, _stream())
+        return dw, db
 
     # ------------------------------------------------------------------ dense / embedding
     def dense_fwd(self, x, w, alpha):
@@ -288,8 +315,7 @@ class CudaBackend(object):
         c = y.shape[-1]
         ga, gdy = torch.empty_like(y), torch.empty_like(y)
         rows = y.numel() // c
-        _lib.call("gs_pixel_norm_bwd2_masked_y", _ptr(y), _ptr(r), _ptr(dy), _ptr(u), _ptr(ga), rows, c, _stream())
-        _lib.call("gs_pixel_norm_bwd_premask_y", _ptr(y), _ptr(r), _ptr(u), _ptr(gdy), rows, c, _stream())
+        _lib.call("gs_pixel_norm_bwd2_pair_y", _ptr(y), _ptr(r), _ptr(dy), _ptr(u), _ptr(ga), _ptr(gdy), rows, c, _stream())
         return ga, gdy
 
     def pn_bwd2(self, a, r, dy, u):

@@ -16,6 +16,7 @@ rank-local batch_stddev groups), one NCCL all-reduce of the flat gradient buffer
 """
 import gc
 import glob
+import logging
 import os
 import time
 
@@ -25,6 +26,8 @@ import torch
 from . import functional as F
 from . import ops
 from . import spectral_ops
+
+logger = logging.getLogger("gansynth_b200")
 
 
 class GlobalStep(object):
@@ -119,6 +122,8 @@ class GANSynth(object):
         hp = self.hyper_params
         with torch.no_grad():
             fake_images = self.generator(latents, labels)
+        if hp.get("fake_gradient_penalty_weight"):
+            fake_images = fake_images.detach().requires_grad_(True)
         real_images = real_images.detach().requires_grad_(True)
         real_features, real_logits = self.discriminator(real_images, labels)
         fake_features, fake_logits = self.discriminator(fake_images, labels)
@@ -132,9 +137,14 @@ class GANSynth(object):
             flat = grads.reshape(grads.shape[0], -1)
             losses = losses + F.RowDot.apply(flat, flat) * hp["real_gradient_penalty_weight"]
         if hp.get("fake_gradient_penalty_weight"):
-            raise NotImplementedError("fake_gradient_penalty_weight != 0 is not on the reference path "
-                                      "(gan_synth_main.py:87)")
-        self.real_images, self.fake_images = real_images.detach(), fake_images
+            # models.py:50-54: the same penalty on the generator distribution (0.0 on the reference's command line,
+            # gan_synth_main.py:87, so off the benchmarked path)
+            with F.skip_weight_grads():
+                (grads,) = torch.autograd.grad(fake_logits, fake_images, grad_outputs=torch.ones_like(fake_logits),
+                                               create_graph=True)
+            flat = grads.reshape(grads.shape[0], -1)
+            losses = losses + F.RowDot.apply(flat, flat) * hp["fake_gradient_penalty_weight"]
+        self.real_images, self.fake_images = real_images.detach(), fake_images.detach()
         self.real_features, self.fake_features = real_features.detach(), fake_features.detach()
         self.real_logits, self.fake_logits = real_logits.detach(), fake_logits.detach()
         return losses.mean()
@@ -189,13 +199,17 @@ class GANSynth(object):
         """Gradients of `loss` w.r.t. the variables of `scope`, written into the flat gradient buffer."""
         st = self._opt[scope]
         names = list(self.store.trainable_variables(scope).keys())
-        grads = torch.autograd.grad(loss, [self.store.vars[n] for n in names], allow_unused=True)
         views = self.store.unflatten(scope, st["grad"])
-        for n, g in zip(names, grads):
-            if g is None:
-                views[n].zero_()
-            else:
-                views[n].copy_(g)
+        if "sinks" not in st:
+            st["sinks"] = {self.store.vars[n].data_ptr(): views[n] for n in names}
+        # the convolution layers add their filter / bias gradients straight into the flat buffer (functional.grad_sinks);
+        # what autograd still returns (dense, embedding, 1x1 / to-RGB layers) is added on top
+        st["grad"].zero_()
+        with F.grad_sinks(st["sinks"]):
+            grads = torch.autograd.grad(loss, [self.store.vars[n] for n in names], allow_unused=True)
+        rest = [(views[n], g) for n, g in zip(names, grads) if g is not None]
+        if rest:
+            torch._foreach_add_([v for v, _ in rest], [g for _, g in rest])      # one launch for the lot
 
     def _update(self, scope):
         """[all-reduce] + fused TF-Adam on the flat buffers (models.py:67-89)."""
@@ -211,7 +225,7 @@ class GANSynth(object):
         st["t"] += 1
         F.K.adam_step(st["flat"], gflat, st["m"], st["v"], hp[scope + "_learning_rate"], hp[scope + "_beta1"],
                       hp[scope + "_beta2"], 1.0e-8, st["t"], scale)
-        F.K.weight_cache_reset()       # the pre-split copies of the parameters are stale now
+        F.K.weight_cache_refresh(st["flat"])   # re-split the cached bf16 copies of these parameters, in place
 
     def _apply(self, scope, loss):
         """minimize(loss, var_list=scope variables) (models.py:81-89) with TF-Adam semantics."""
@@ -223,7 +237,6 @@ class GANSynth(object):
         """Everything of the D sub-step up to the flat gradient: spectral front-end, G forward, D(real),
         D(fake), R1 double backward, gradients of the D variables."""
         self._set_trainable("discriminator")
-        F.K.weight_cache_reset()       # a (captured) sub-step always splits each parameter at its first use
         real_images = self.real_images_from_waveforms(real_waveforms)
         loss = self.discriminator_loss_fn(real_images, labels, latents)
         self._backward("discriminator", loss)
@@ -231,7 +244,6 @@ class GANSynth(object):
 
     def _generator_body(self, labels, latents):
         self._set_trainable("generator")
-        F.K.weight_cache_reset()
         loss = self.generator_loss_fn(labels, latents)
         self._backward("generator", loss)
         return loss.detach()
@@ -353,7 +365,11 @@ class GANSynth(object):
     def save_checkpoint(self, model_dir, max_to_keep=10):
         os.makedirs(model_dir, exist_ok=True)
         path = os.path.join(model_dir, "model.ckpt-%d.pt" % int(self.global_step.value))
-        torch.save(self._checkpoint_state(), path)
+        # written under a temporary name and renamed (as tf.train.Saver does): a crash mid-write never leaves a
+        # truncated file that sorts as the newest checkpoint
+        tmp = path + ".tmp"
+        torch.save(self._checkpoint_state(), tmp)
+        os.replace(tmp, path)
         kept = sorted(glob.glob(os.path.join(model_dir, "model.ckpt-*.pt")),
                       key=lambda p: int(p.rsplit("-", 1)[1][:-3]))
         for old in kept[:-max_to_keep]:
@@ -369,7 +385,16 @@ class GANSynth(object):
             if os.path.exists(os.path.join(model_dir, "checkpoint")):
                 return self.import_tf_checkpoint(model_dir, labels, latents)
             return None
-        state = torch.load(paths[-1], map_location="cpu")
+        state = None
+        while paths:
+            try:
+                state = torch.load(paths[-1], map_location="cpu")
+                break
+            except Exception as exc:          # unreadable (e.g. written by an interrupted older version): try the one before
+                logger.warning("checkpoint %s is unreadable (%s); falling back", paths[-1], exc)
+                paths.pop()
+        if state is None:
+            return None
         if labels is not None:
             self._ensure_optimizers(labels, latents)
         self.store.load(state["variables"])
@@ -476,6 +501,8 @@ class GANSynth(object):
                 self.save_checkpoint(model_dir)
         if rank0:
             self.save_checkpoint(model_dir)
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.barrier(group=self.process_group)     # nobody reads model_dir before rank 0 has written it
 
     def _write_summary(self, model_dir, step):
         """SummarySaverHook stand-in (models.py:131-170): the scalar summaries (generator_loss, discriminator_loss) plus
@@ -558,7 +585,6 @@ class GANSynth(object):
                         pg._ensure_variables("generator", latents.shape[1], labels.shape[1])
                         pg._ensure_variables("discriminator", 0, labels.shape[1])
                     self.restore_latest(model_dir)
-                    F.K.weight_cache_reset()
                     restored = True
                 self.real_images = self.real_images_from_waveforms(waveforms)
                 self.fake_images = self.generator(latents, labels)
@@ -588,7 +614,6 @@ class GANSynth(object):
             yield self.generate_batch(labels, latents).cpu().numpy()
 
     def _generate_body(self, labels, latents):
-        F.K.weight_cache_reset()       # the caller may have changed the parameters since the last call
         fake_images = self.generator(latents, labels)
         mag, inst = fake_images[:, 0].contiguous(), fake_images[:, 1].contiguous()
         return spectral_ops.convert_to_waveform(mag, inst, **self.spectral_params), fake_images
@@ -599,9 +624,7 @@ class GANSynth(object):
         chain (weight split, ~60 kernels, inverse spectral transform) is replayed as one CUDA graph per batch size
         from the third call on: at small batches the host needs longer to enqueue it than the device to run it."""
         waveforms, images = self._run_body("generate", self._generate_body, (labels, latents))
-        # a replayed graph re-splits the weights into cache slots the host-side table no longer describes, and its
-        # output buffers belong to the graph: invalidate the table, hand out copies
-        F.K.weight_cache_reset()
+        # the output buffers belong to the graph: hand out copies
         self.fake_images = images.clone()
         self.fake_waveforms = waveforms.clone()
         return self.fake_waveforms

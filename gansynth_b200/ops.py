@@ -95,7 +95,7 @@ class VariableStore(object):
             for n, val in values.items():
                 t = torch.as_tensor(np.asarray(val) if not torch.is_tensor(val) else val)
                 self.vars[n].copy_(t.to(self.device, torch.float32))
-        F.K.weight_cache_reset()    # pre-split copies of the old values are stale
+        F.K.weight_cache_refresh()  # pre-split copies of the old values are stale: re-split them in place
 
     def state(self):
         return OrderedDict((n, v.detach().cpu()) for n, v in self.vars.items())

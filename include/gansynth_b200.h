@@ -18,12 +18,17 @@
  *    4 fp32 auto (tiled else naive; never the tensor-core kernel); OR-ed with GS_IMPL_PARAM_WEIGHT when `w` is a
  *    network parameter (a pointer that stays valid and unchanged until gs_conv_weight_cache_reset): the
  *    tensor-core kernels may then reuse its pre-split bf16 copy across calls;
- *  - `stream` is a cudaStream_t; every call is asynchronous on it, no hidden synchronisation (the
- *    spectral entry points synchronise once, on first use, to upload twiddle tables);
+ *  - `stream` is a cudaStream_t; every call is asynchronous on it: no entry point synchronises, allocates or frees
+ *    device memory, or copies from the host;
+ *  - the library keeps NO global mutable state.  What survives a call -- the bf16-split copies of parameter weights the
+ *    tensor-core convolutions reuse within a sub-step, and the spectral twiddle tables -- lives in a caller-owned
+ *    device workspace behind an opaque gs_context (below), bound per host thread;
  *  - return 0 on success, negative on error; gs_last_error() gives the message (thread-local).
  */
 #ifndef GANSYNTH_B200_H_
 #define GANSYNTH_B200_H_
+
+#include <stddef.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -32,10 +37,30 @@ extern "C" {
 const char* gs_last_error(void);
 int gs_version(void);
 
+/* ---- context: caller-owned workspace ------------------------------------------------------------------------------
+ * gs_workspace_bytes(): the recommended size of the device workspace (twiddle tables + an 8 MB slot for split weights that
+ * are used once + a 256 MB cache for split parameter weights); gs_workspace_min_bytes(): the smallest accepted (no
+ * cache: every parameter is re-split at each use).  gs_context_create() only records the pointer (256-byte aligned;
+ * it stays the caller's: the library never frees it) -- no device work.  gs_context_bind() makes `ctx` the context of the
+ * CALLING HOST THREAD (NULL unbinds); the convolution, spectral and cache-reset entry points use the bound context and
+ * fail with GS_ERR_ARG when there is none.  A context serves one stream at a time: the caller orders hand-overs
+ * between streams as for any other buffer (the twiddle tables are filled by a kernel enqueued on the stream of the
+ * context's first spectral call).  A full cache degrades to re-splitting, with one warning on stderr. */
+typedef struct gs_context gs_context;
+size_t gs_workspace_bytes(void);
+size_t gs_workspace_min_bytes(void);
+int gs_context_create(void* workspace, size_t bytes, gs_context** out);
+int gs_context_destroy(gs_context* ctx);
+int gs_context_bind(gs_context* ctx);
+
 #define GS_IMPL_PARAM_WEIGHT 0x100
-/* Invalidates the cache of pre-split parameter weights.  Call after every optimiser update and at the start of
+/* Invalidates the bound context's cache of pre-split parameter weights.  Call after every optimiser update and at the start of
    every sub-step (TF evaluates get_weight's scaling at run time, ops.py:154-160: nothing may survive an update). */
 int gs_conv_weight_cache_reset(void);
+/* Re-splits in place every cached parameter weight inside [lo, hi) (NULL, NULL: all) after the caller changed those
+   parameters: the cache slots keep their addresses (kernels recorded in CUDA graphs stay valid), one launch per 48
+   entries.  With a refresh after every change the cache never holds a stale copy and a sub-step contains no split kernels. */
+int gs_conv_weight_cache_refresh(const float* lo, const float* hi, void* stream);
 
 /* ---- convolution family: tf.nn.conv2d ops.py:237-243 (+ bias_add :245-246) and its gradients ------
  * SAME padding as TF computes it for even sizes: 3x3 stride 1 pads (1,1); stride 2 pads (0,1).
@@ -49,6 +74,14 @@ int gs_conv2d_dgrad(const float* dy, const float* w, const float* bias, float* d
                     int co, int ksize, int stride, int wswap, float alpha, int act, int impl, void* stream);
 int gs_conv2d_wgrad(const float* x, const float* dy, float* dw, int n, int h, int wd, int ci, int co, int ksize,
                     int stride, int wswap, float alpha, int impl, void* stream);
+/* gs_conv2d_wgrad plus, from the same pass over the operands, the bias gradient (BiasAddGrad of ops.py:244 / 277):
+ * dbias[c] = sum over pixels of dy (bias_of_x = 0, conv2d layers) or of x (bias_of_x = 1: conv2d_transpose layers,
+ * whose pre-activation gradient is the high-resolution operand `x` of this call); dbias ([co] / [ci]) may be NULL.
+ * accumulate = 0 overwrites dw / dbias; 1 ADDS to them: the uses of one parameter (D(real), D(fake), the penalty pass)
+ * then sum straight into the caller's gradient buffer -- tf.gradients' AddN (models.py:81-89) without extra passes. */
+int gs_conv2d_wgrad_ex(const float* x, const float* dy, float* dw, float* dbias, int bias_of_x, int accumulate, int n,
+                       int h, int wd, int ci, int co, int ksize, int stride, int wswap, float alpha, int impl,
+                       void* stream);
 
 /* The same two convolutions with a FUSED EPILOGUE, `epi`:
  *   GS_EPI_NONE  (0): as above.
@@ -129,6 +162,10 @@ int gs_pixel_norm_bwd_mask_y(const float* y, const float* r, const float* dy, fl
 int gs_pixel_norm_bwd_premask_y(const float* y, const float* r, const float* u, float* out, long long rows, int c, void* stream);
 int gs_pixel_norm_bwd2_masked_y(const float* y, const float* r, const float* dy, const float* u, float* ga, long long rows, int c,
                                 void* stream);
+/* both second-order pieces for one incoming u in a single pass: ga as gs_pixel_norm_bwd2_masked_y, gdy as
+   gs_pixel_norm_bwd_premask_y(y, r, u) */
+int gs_pixel_norm_bwd2_pair_y(const float* y, const float* r, const float* dy, const float* u, float* ga, float* gdy,
+                              long long rows, int c, void* stream);
 
 /* ---- batch_stddev ops.py:336-348 on [b, e]; stat is [b/groups] ---------------------------------- */
 int gs_batch_stddev_fwd(const float* x, float* stat, int b, long long e, int groups, float eps, void* stream);
@@ -182,13 +219,6 @@ int gs_wav_decode_pcm16(const void* file_bytes, long long n, short* dst, int des
                         int* samples_in_file);
 int gs_wav_read_batch(const char* const* paths, int n, short* dst, int desired_samples, int threads, int* status);
 int gs_pcm16_to_float(const short* src, float* dst, long long n, void* stream);
-
-/* ---- tcgen05 self-test: one 128 x n bf16 UMMA accumulation from operands staged in the SWIZZLE_NONE
- * core-matrix layout of the tensor-core convolution (see csrc/tc_probe.cu) ------------------------- */
-int gs_tc_probe(const float* a, const float* b, float* d, int k, int n, int rows_a, int rows_b, int shift, int gstride,
-                int mode, void* stream);
-int gs_tc_probe_time(const float* a, const float* b, float* d, int k, int n, int rows_a, int rows_b, int shift,
-                     int gstride, int mode, int reps, long long* cycles, void* stream);
 
 #ifdef __cplusplus
 }

@@ -29,6 +29,8 @@ def real_images_from_waveforms(waveforms, spectral_params):
 def discriminator_loss(pggan, params, real_images, labels, latents, hp):
     """models.py:25-54, 65 for the D update: G forward, D on real and fake, softplus terms, R1."""
     fake_images = pggan.generator(params, latents, labels).detach()
+    if hp.get("fake_gradient_penalty_weight"):
+        fake_images.requires_grad_(True)
     real_images = real_images.detach().requires_grad_(True)
     _, real_logits = pggan.discriminator(params, real_images, labels)
     _, fake_logits = pggan.discriminator(params, fake_images, labels)
@@ -39,8 +41,9 @@ def discriminator_loss(pggan, params, real_images, labels, latents, hp):
         grads = torch.autograd.grad(real_logits.sum(), real_images, create_graph=True)[0]
         losses = losses + grads.pow(2).sum(dim=(1, 2, 3)) * hp["real_gradient_penalty_weight"]
     if hp.get("fake_gradient_penalty_weight"):
-        fake_images.requires_grad_(True)
-        raise NotImplementedError("fake_gradient_penalty_weight is 0.0 on the reference path")
+        # models.py:50-54 (off on the reference's command line, gan_synth_main.py:87)
+        grads = torch.autograd.grad(fake_logits.sum(), fake_images, create_graph=True)[0]
+        losses = losses + grads.pow(2).sum(dim=(1, 2, 3)) * hp["fake_gradient_penalty_weight"]
     return losses.mean()
 
 

@@ -28,6 +28,9 @@ class EmuBackend(object):
     def register_parameters(self, flats):
         pass
 
+    def weight_cache_refresh(self, flat=None):
+        pass
+
     def weight_cache_reset(self):
         pass
 
@@ -70,7 +73,16 @@ class EmuBackend(object):
             dx = dx + bias.view(1, -1, 1, 1)
         return _nhwc(_act(dx, act))
 
-    def conv_w(self, x, dy, ksize, stride, wswap, alpha):
+    def conv_w(self, x, dy, ksize, stride, wswap, alpha, bias_of=None, out=None):
+        if out is not None:
+            out[0].add_(EmuBackend.conv_w(self, x, dy, ksize, stride, wswap, alpha))
+            if out[1] is not None:
+                src = x if bias_of == "x" else dy
+                out[1].add_(src.reshape(-1, src.shape[-1]).sum(0))
+            return None
+        if bias_of is not None:
+            src = x if bias_of == "x" else dy
+            return EmuBackend.conv_w(self, x, dy, ksize, stride, wswap, alpha), src.reshape(-1, src.shape[-1]).sum(0)
         pb = 1 if (ksize == 3 and stride == 1) else 0
         pa = (ksize - stride) - pb if ksize == 3 else 0
         xp = TF.pad(_nchw(x), (pb, pa, pb, pa))

@@ -12,7 +12,7 @@ def _header_functions():
     text = open(os.path.join(ROOT, "include", "gansynth_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     out = {}
-    for m in re.finditer(r"\b(?:int|const char\*)\s+(gs_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+    for m in re.finditer(r"\b(?:int|size_t|const char\*)\s+(gs_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
         args = m.group(2).strip()
         out[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
     return out
@@ -74,6 +74,31 @@ def test_argument_errors_are_reported_before_any_device_work():
     assert lib.gs_pcm16_to_float(None, None, 0, None) == 0 and lib.gs_pcm16_to_float(None, None, -1, None) < 0
     with __import__("pytest").raises(_lib.GansynthLibraryError):
         _lib.host_call("gs_wav_read_batch", None, 1, None, 0, 1, None)
+
+
+def test_context_api_without_a_device():
+    """gs_context_*: host-side bookkeeping only (no device work), so it runs here: sizes, argument checks, and the
+    entry points that need a workspace refuse to run without a bound context instead of allocating one."""
+    import ctypes
+    import __graft_entry__ as ge
+    from gansynth_b200 import _lib
+    ge.build()
+    lib = _lib.load()
+    assert lib.gs_workspace_bytes() > lib.gs_workspace_min_bytes() >= (8 << 20)
+    handle = ctypes.c_void_p()
+    assert lib.gs_context_create(None, lib.gs_workspace_bytes(), ctypes.byref(handle)) < 0        # null workspace
+    assert lib.gs_context_create(0x1000, 1024, ctypes.byref(handle)) < 0                           # too small
+    assert b"gs_workspace_min_bytes" in lib.gs_last_error()
+    assert lib.gs_context_create(0x1001, lib.gs_workspace_bytes(), ctypes.byref(handle)) < 0      # misaligned
+    lib.gs_context_bind(None)
+    # a tensor-core-shaped convolution without a context: refused before any device work
+    rc = lib.gs_conv2d_fwd(None, None, None, None, 1, 16, 16, 32, 32, 3, 1, 0, 1.0, 0, 3, None)
+    assert rc < 0 and b"no context bound" in lib.gs_last_error()
+    rc = lib.gs_spectrogram_fwd(None, None, None, None, None, None, 1, 1, 64000, 128, 32, None)
+    assert rc < 0 and b"no context bound" in lib.gs_last_error()
+    assert lib.gs_context_create(0x1000, lib.gs_workspace_min_bytes(), ctypes.byref(handle)) == 0  # records the pointer only
+    assert lib.gs_context_bind(handle) == 0 and lib.gs_conv_weight_cache_reset() == 0
+    assert lib.gs_context_bind(None) == 0 and lib.gs_context_destroy(handle) == 0
 
 
 def test_spectral_launch_policies():

@@ -71,6 +71,25 @@ def test_step_gradients_and_adam_parity(emu, level):
             assert rel_err(v, ostep.params[n]) < 5e-4, n
 
 
+def test_fake_gradient_penalty_branch(emu):
+    """models.py:50-54 (fake_gradient_penalty_weight != 0; 0.0 on the reference's command line): loss and D gradients."""
+    import gansynth_b200.models as pmodels
+    hp = dict(HYPER, fake_gradient_penalty_weight=2.5)
+    opg, params, ppg, latents, labels, images = _pair(1.0, emu)
+    ostep = omodels.GANSynthStep(opg, params, hp)
+    model = pmodels.GANSynth(ppg.generator, ppg.discriminator, None, None, {}, hp, device="cpu")
+    model._ensure_optimizers(labels, latents)
+    want_loss, want_grads = ostep.discriminator_update(images, labels, latents, apply=False)
+    base_loss, _ = omodels.GANSynthStep(opg, params, HYPER).discriminator_update(images, labels, latents, apply=False)
+    assert abs(float(want_loss) - float(base_loss)) > 1e-6            # the branch contributes
+    model._set_trainable("discriminator")
+    loss = model.discriminator_loss_fn(images, labels, latents)
+    assert abs(float(loss.detach()) - float(want_loss)) < 1e-4 * max(1.0, abs(float(want_loss)))
+    model._backward("discriminator", loss)
+    for n, g in emu.unflatten("discriminator", model._opt["discriminator"]["grad"]).items():
+        assert grad_close(g, want_grads[n], 5e-4), n
+
+
 @pytest.mark.parametrize("level", [0.05, 0.1, 0.3])
 def test_device_resident_blend_weight_matches_host_floats(emu, level):
     """Growth-phase graphs keep lerp's (t, 1 - t) in device memory (PGGAN.lerp_coef, AxpbyDev): forward values and the

@@ -219,3 +219,32 @@ def test_error_reporting():
         _lib.call("gs_conv2d_fwd", 0, 0, 0, 0, 1, 8, 8, 4, 4, 5, 1, 0, 1.0, 0, 0, 0)   # ksize 5
     with pytest.raises(_lib.GansynthLibraryError):
         _k().lrelu(torch.zeros(4))   # CPU tensor: no fallback
+
+
+def test_context_is_shared_by_the_host_threads_of_a_device():
+    """The library binds its context (caller-owned workspace, split-weight cache) per host thread; PyTorch runs backward
+    functions on its autograd thread, so every thread of the process binds the ONE context of the device: a second
+    thread computes the same tensor-core convolution bit for bit, allocates no second workspace, and a cache reset
+    from either thread reaches the shared cache."""
+    import threading
+    from gansynth_b200 import _lib
+    from gansynth_b200.kernels import CudaBackend
+    k = CudaBackend()
+    g = torch.Generator().manual_seed(0)
+    x, w = torch.randn(2, 16, 16, 32, generator=g).cuda(), torch.randn(3, 3, 32, 32, generator=g).cuda()
+    main = k.conv_c(x, w, None, 3, 1, 0, 0.1, 0)
+    torch.cuda.synchronize()
+    before = len(_lib._contexts)
+    out = {}
+
+    def worker():
+        torch.cuda.set_device(0)
+        out["y"] = CudaBackend().conv_c(x, w, None, 3, 1, 0, 0.1, 0)
+        CudaBackend().weight_cache_reset()
+        torch.cuda.synchronize()
+
+    t = threading.Thread(target=worker)
+    t.start()
+    t.join()
+    assert len(_lib._contexts) == before == 1
+    assert torch.equal(out["y"], main)

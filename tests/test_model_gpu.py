@@ -100,6 +100,19 @@ def test_small_step_parity(cuda_store, conv_mode, level):
             cuda_store.load({n: ostep.params[n].detach() for n in got})
 
 
+def test_fake_gradient_penalty_branch(cuda_store, conv_mode):
+    """models.py:50-54: the zero-centred penalty on the generator distribution (weight 0.0 on the reference's command
+    line, so off the benchmarked path): D sub-step loss and gradients by `check_substep`."""
+    import gansynth_b200.models as pmodels
+    hp = dict(HYPER, fake_gradient_penalty_weight=2.5)
+    opg, params, ppg = _pair(SMALL, 1.0, cuda_store)
+    latents, labels, images = seeded_inputs(4, [16, 16])
+    ostep = omodels.GANSynthStep(opg, {n: p.double() for n, p in params.items()}, hp)
+    model = pmodels.GANSynth(ppg.generator, ppg.discriminator, None, None, {}, hp)
+    model._ensure_optimizers(labels.cuda(), latents.cuda())
+    check_substep(model, cuda_store, ostep, "discriminator", images, labels, latents, torch.float64, conv_mode)
+
+
 def test_full_forward_parity(cuda_store, conv_mode):
     """BASELINE config 2 architecture (2x16 -> 128x1024, fully grown), batch 4."""
     opg, params, ppg = _pair(FULL, 1.0, cuda_store)
@@ -250,6 +263,7 @@ def test_cuda_graph_substeps_match_eager(cuda_store):
             with torch.no_grad():
                 for n, v in store.vars.items():
                     v.copy_(snap["vars"][n])
+            F.K.weight_cache_refresh()       # parameter values changed behind the store's back (VariableStore.load does this)
             for s, o in model._opt.items():
                 o["m"].copy_(snap["opt"][s][0]); o["v"].copy_(snap["opt"][s][1]); o["t"] = snap["opt"][s][2]
             model.global_step.value = snap["step"]
@@ -356,6 +370,7 @@ def test_growth_phase_substeps_replay_as_graphs(cuda_store):
             with torch.no_grad():
                 for n, v in store.vars.items():
                     v.copy_(snap["vars"][n])
+            F.K.weight_cache_refresh()       # parameter values changed behind the store's back (VariableStore.load does this)
             for s, o in model._opt.items():
                 o["m"].copy_(snap["opt"][s][0]); o["v"].copy_(snap["opt"][s][1]); o["t"] = snap["opt"][s][2]
             model.global_step.value = snap["step"]

@@ -14,7 +14,7 @@ def _probe(a, b, k, n, shift, gstride, mode):
     from gansynth_b200 import _lib
     ad, bd = a.cuda().contiguous(), b.cuda().contiguous()
     d = torch.full((128, n), float("nan"), device="cuda")
-    _lib.call("gs_tc_probe", ad.data_ptr(), bd.data_ptr(), d.data_ptr(), k, n, a.shape[0], b.shape[0], shift, gstride, mode,
+    _lib.probe_call("gs_tc_probe", ad.data_ptr(), bd.data_ptr(), d.data_ptr(), k, n, a.shape[0], b.shape[0], shift, gstride, mode,
               torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     return d.cpu().double()
@@ -194,6 +194,24 @@ def test_tc_filter_gradient(case, wswap):
     want = EMU.conv_w(x.double(), dy.double(), 3, st, wswap, 0.37)
     assert got.shape == want.shape
     assert rel_err(got, want) < 1e-4, (case, wswap, rel_err(got, want))
+
+
+@pytest.mark.parametrize("case", TC_WGRAD_CASES + [(2, 64, 40, 96, 160, 1), (1, 8, 16, 8, 12, 1), (2, 8, 16, 8, 12, 2)])
+@pytest.mark.parametrize("bias_of", ["dy", "x"])
+@pytest.mark.parametrize("impl", [0, 4])
+def test_filter_gradient_with_bias_gradient(case, bias_of, impl):
+    """gs_conv2d_wgrad_ex: the bias gradient (column sum of either operand) taken inside the filter-gradient kernel --
+    every pixel counted once although the kh jobs / N-stacked boxes of the tensor-core kernel overlap -- and the
+    col_sum fallback of the fp32 kernels; dw itself unchanged."""
+    n, h, w, ci, co, st = case
+    k = _k3(impl)
+    x = _rand(n, h, w, ci, seed=1)
+    dy = _rand(n, h // st, w // st, co, seed=2)
+    dw, db = k.conv_w(x.cuda(), dy.cuda(), 3, st, 0, 0.37, bias_of=bias_of)
+    want_w, want_b = EMU.conv_w(x.double(), dy.double(), 3, st, 0, 0.37, bias_of=bias_of)
+    assert dw.shape == want_w.shape and db.shape == want_b.shape
+    assert rel_err(dw, want_w) < 1e-4, (case, rel_err(dw, want_w))
+    assert rel_err(db, want_b) < 1e-5, (case, bias_of, rel_err(db, want_b))
 
 
 # ------------------------------------------------------------------------------------------------

@@ -22,7 +22,7 @@ for mode, name in ((0, "K-major"), (1, "MN-major")):
             b = torch.randn(rows_b, k if mode == 0 else n, device="cuda")
             d = torch.zeros(128, n, device="cuda")
             reps = 2000
-            _lib.call("gs_tc_probe_time", a.data_ptr(), b.data_ptr(), d.data_ptr(), k, n, rows_a, rows_b, 0, gstride, mode,
+            _lib.probe_call("gs_tc_probe_time", a.data_ptr(), b.data_ptr(), d.data_ptr(), k, n, rows_a, rows_b, 0, gstride, mode,
                       reps, cyc.data_ptr(), st)
             torch.cuda.synchronize()
             per = float(cyc.item()) / (reps * (k // 16))
