@@ -34,9 +34,11 @@ ITER_FLOP_PER_SAMPLE = 7 * F_G + 11 * F_D   # SURVEY 3.1 nominal model: D-run F_
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
 # (key = ConvProfiler key: form, n, h, w, ci, co, ksize, stride)
 NCU_TRAFFIC = {
-    ("conv_c", 8, 128, 1024, 32, 32, 3, 1): (134295552 + 86461184, "profiles/ncu_ck_32_summary.txt"),
-    ("conv_t", 8, 128, 1024, 32, 32, 3, 1): (134295552 + 86461184, "profiles/ncu_ck_32_summary.txt (same kernel and shape)"),
-    ("conv_w", 8, 128, 1024, 32, 32, 3, 1): (268535552 + 4204032, "profiles/ncu_w_32_v2_summary.txt"),
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch, `ncu --set full` captures of the round-2 binary
+    ("conv_c", 8, 128, 1024, 32, 32, 3, 1): (134296064 + 85676800, "profiles/ncu_r2_ck_32_summary.txt"),
+    ("conv_t", 8, 128, 1024, 32, 32, 3, 1): (134296064 + 85676800, "profiles/ncu_r2_ck_32_summary.txt (same kernel and shape)"),
+    ("conv_w", 8, 128, 1024, 32, 32, 3, 1): (268608000 + 4684800, "profiles/ncu_r2_w_32_summary.txt"),
+    ("conv_t", 8, 128, 1024, 32, 64, 3, 2): (67240448 + 74136064, "profiles/ncu_r2_t2_64_32_summary.txt"),
 }
 
 HYPER = dict(generator_learning_rate=8e-4, generator_beta1=0.0, generator_beta2=0.99,

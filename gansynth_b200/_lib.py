@@ -9,8 +9,8 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgansynth_b200.so")
-if os.environ.get("GS_LIB") == "prof":      # development: the stage-profiling build (gansynth_b200.build --prof)
-    LIB_PATH = os.path.join(_HERE, "libgansynth_b200_prof.so")
+if os.environ.get("GS_LIB", "").startswith("prof"):      # development: a stage-profiling build (gansynth_b200.build --prof)
+    LIB_PATH = os.path.join(_HERE, "libgansynth_b200_%s.so" % os.environ["GS_LIB"])
 
 _P = ctypes.c_void_p
 _I = ctypes.c_int
@@ -68,6 +68,9 @@ SIGNATURES = {
     "gs_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _L, _F, _P],
     "gs_spectrogram_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "gs_waveform_fwd": [_P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P],
+    "gs_group_norm_fwd": [_P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _I, _P],
+    "gs_max_pool2d": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "gs_spatial_mean": [_P, _P, _I, _L, _I, _P],
     "gs_crc32c": [_P, _L, _P],
     "gs_wav_decode_pcm16": [_P, _L, _P, _I, _P, _P],
     "gs_wav_read_batch": [_P, _I, _P, _I, _I, _P],

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgansynth_b200.so")
-SOURCES = ["abi.cu", "conv.cu", "elementwise.cu", "dense.cu", "spectral.cu", "io.cu"]
+SOURCES = ["abi.cu", "conv.cu", "elementwise.cu", "dense.cu", "spectral.cu", "io.cu", "classifier.cu"]
 PROBE_LIB = os.path.join(HERE, "libgansynth_b200_probe.so")     # development self-test, not the product ABI
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
@@ -21,16 +21,17 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_prof(verbose=False):
+def build_prof(verbose=False, defs=(), suffix="prof"):
     """The stage-profiling variant (conv.cu with -DGS_TC_PROF) -> libgansynth_b200_prof.so; a development tool
-    (tools/tc_stage_profile.py, GS_LIB=prof), never loaded by default."""
+    (tools/tc_stage_profile.py, GS_LIB=prof), never loaded by default.  `defs` / `suffix`: further experiment builds
+    (e.g. -DTCW_CW=16 -> libgansynth_b200_prof16.so, GS_LIB=prof16)."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     build()
-    o = os.path.join(CSRC, "conv_prof.o")
-    cmd = [nvcc] + NVCC_FLAGS + ["-DGS_TC_PROF", "-c", os.path.join(CSRC, "conv.cu"), "-o", o]
+    o = os.path.join(CSRC, "conv_%s.o" % suffix)
+    cmd = [nvcc] + NVCC_FLAGS + ["-DGS_TC_PROF"] + list(defs) + ["-c", os.path.join(CSRC, "conv.cu"), "-o", o]
     subprocess.check_call(cmd)
     objs = [os.path.join(CSRC, s.replace(".cu", ".o")) for s in SOURCES if s != "conv.cu"] + [o]
-    lib = os.path.join(HERE, "libgansynth_b200_prof.so")
+    lib = os.path.join(HERE, "libgansynth_b200_%s.so" % suffix)
     subprocess.check_call([nvcc, "-shared", "-o", lib] + objs + ["-lcudart"])
     return lib
 
@@ -68,5 +69,7 @@ def build(force=False, verbose=False):
 if __name__ == "__main__":
     if "--prof" in sys.argv:
         print(build_prof())
+    elif "--prof16" in sys.argv:
+        print(build_prof(defs=["-DTCW_CW=16"], suffix="prof16"))
     else:
         print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

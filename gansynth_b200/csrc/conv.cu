@@ -29,14 +29,16 @@ struct Epi {
 int make_geom(ConvGeom& g, int n, int h, int w, int ci, int co, int ksize, int stride, int wswap, float alpha,
               int act) {
   GS_CHECK_ARG(n > 0 && h > 0 && w > 0 && ci > 0 && co > 0, "conv: non-positive dimension");
-  GS_CHECK_ARG(ksize == 1 || ksize == 3, "conv: ksize must be 1 or 3 (got %d)", ksize);
+  GS_CHECK_ARG(ksize == 1 || ksize == 3 || ksize == 5 || ksize == 7, "conv: ksize must be 1, 3, 5 or 7 (got %d)", ksize);
   GS_CHECK_ARG(stride == 1 || stride == 2, "conv: stride must be 1 or 2 (got %d)", stride);
   GS_CHECK_ARG(h % stride == 0 && w % stride == 0, "conv: spatial size %dx%d not divisible by stride %d", h, w, stride);
   GS_CHECK_ARG(act == 0 || act == 1, "conv: act must be 0 (none) or 1 (leaky relu)");
   g.n = n; g.h = h; g.w = w; g.ci = ci; g.co = co;
   g.oh = h / stride; g.ow = w / stride;
   g.ksize = ksize; g.stride = stride;
-  g.pb = (ksize == 3 && stride == 1) ? 1 : 0;  // TF SAME, even sizes
+  // TF SAME on sizes divisible by the stride: total padding max(ksize - stride, 0), the smaller half in front
+  // (3x3: stride 1 -> 1, stride 2 -> 0; the classifier's 7x7 stride-2 stem -> 2)
+  g.pb = (ksize > stride ? ksize - stride : 0) / 2;
   g.wswap = wswap ? 1 : 0;
   g.alpha = alpha;
   g.act = act;

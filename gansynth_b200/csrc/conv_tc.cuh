@@ -149,6 +149,43 @@ __device__ __forceinline__ void conv_tc_prep_elem(size_t i, const float* __restr
   out[(blk + 2 * q + 1) * plane + inner] = lo;
 }
 
+// The same for the 8 consecutive contraction channels of group g = i / 8 (one 16-byte store per split term).
+template <int KC>
+__device__ __forceinline__ void conv_tc_prep_group(size_t g, const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int kdim,
+                                                   int ndim, int nt, int w_is_kn, int flip) {
+  constexpr int Q = KC / 8;
+  const int nchunks = kdim / KC;
+  size_t r = g;
+  int nl = (int)(r % nt);
+  r /= nt;
+  int q = (int)(r % Q);
+  r /= Q;
+  int tap = (int)(r % 9);
+  r /= 9;
+  int kc = (int)(r % nchunks);
+  int ntile = (int)(r / nchunks);
+  const int k0 = kc * KC + q * 8, n = ntile * nt + nl;
+  const int st = flip ? 8 - tap : tap;
+  float v[8];
+  if (w_is_kn) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = w[((size_t)st * kdim + k0 + e) * ndim + n];
+  } else {
+    const float4* src = reinterpret_cast<const float4*>(w + ((size_t)st * ndim + n) * kdim + k0);
+    const float4 a = src[0], b = src[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  uint4 h4, l4;
+  tc::split2_bf16(v[0], v[1], h4.x, l4.x);
+  tc::split2_bf16(v[2], v[3], h4.y, l4.y);
+  tc::split2_bf16(v[4], v[5], h4.z, l4.z);
+  tc::split2_bf16(v[6], v[7], h4.w, l4.w);
+  const size_t plane = (size_t)nt * 8;
+  const size_t blk = (((size_t)ntile * nchunks + kc) * 9 + tap) * (2 * Q);
+  *reinterpret_cast<uint4*>(out + (blk + 2 * q) * plane + (size_t)nl * 8) = h4;
+  *reinterpret_cast<uint4*>(out + (blk + 2 * q + 1) * plane + (size_t)nl * 8) = l4;
+}
+
 template <int KC>
 __global__ void conv_tc_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int kdim, int ndim,
                                     int nt, int w_is_kn, int flip) {

@@ -74,6 +74,40 @@ __device__ __forceinline__ void conv_tck_prep_elem(size_t i, const float* __rest
   out[base + ((size_t)(3 + kw) * nt + n) * 8 + e] = lo;
 }
 
+__device__ __forceinline__ void conv_tck_prep_group(size_t g, const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int kdim,
+                                                    int nt, int w_is_kn, int flip) {
+  size_t r = g;
+  int n = (int)(r % nt);
+  r /= nt;
+  int kw = (int)(r % 3);
+  r /= 3;
+  int q = (int)(r % 4);
+  r /= 4;
+  int kh = (int)(r % 3);
+  int kc = (int)(r / 3);
+  const int k0 = kc * 32 + q * 8;
+  const int tap = kh * 3 + kw;
+  const int st = flip ? 8 - tap : tap;
+  float v[8];
+  if (w_is_kn) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = w[((size_t)st * kdim + k0 + e) * nt + n];
+  } else {
+    const float4* src = reinterpret_cast<const float4*>(w + ((size_t)st * nt + n) * kdim + k0);
+    const float4 a = src[0], b = src[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  uint4 h4, l4;
+  tc::split2_bf16(v[0], v[1], h4.x, l4.x);
+  tc::split2_bf16(v[2], v[3], h4.y, l4.y);
+  tc::split2_bf16(v[4], v[5], h4.z, l4.z);
+  tc::split2_bf16(v[6], v[7], h4.w, l4.w);
+  const size_t plane = (size_t)6 * nt * 8;
+  const size_t base = (((size_t)kc * 3 + kh) * 4 + q) * plane;
+  *reinterpret_cast<uint4*>(out + base + ((size_t)kw * nt + n) * 8) = h4;
+  *reinterpret_cast<uint4*>(out + base + ((size_t)(3 + kw) * nt + n) * 8) = l4;
+}
+
 __global__ void conv_tck_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int kdim, int nt,
                                      int w_is_kn, int flip) {
   const size_t total = (size_t)9 * kdim * nt;
@@ -98,15 +132,16 @@ __global__ void __launch_bounds__(256) conv_prep_batch_kernel(const __grid_const
   int j = 0;
   while (j + 1 < b.njobs && (int)blockIdx.x >= b.jobs[j + 1].block0) ++j;
   const PrepJob& job = b.jobs[j];
-  const size_t total = (size_t)9 * job.kdim * job.ndim;
-  const size_t i0 = (size_t)((int)blockIdx.x - job.block0) * PREP_ELEMS_PER_BLOCK;
+  // a thread handles groups of 8 consecutive contraction channels: one set of index divisions, 16-byte stores
+  const size_t groups = (size_t)9 * job.kdim * job.ndim / 8;
+  const size_t g0 = (size_t)((int)blockIdx.x - job.block0) * (PREP_ELEMS_PER_BLOCK / 8);
 #pragma unroll 1
-  for (int t = threadIdx.x; t < PREP_ELEMS_PER_BLOCK; t += 256) {
-    const size_t i = i0 + t;
-    if (i >= total) break;
-    if (job.kc == 1032) conv_tck_prep_elem(i, job.w, job.out, job.kdim, job.nt, job.kn, job.flip);
-    else if (job.kc == 32) conv_tc_prep_elem<32>(i, job.w, job.out, job.kdim, job.ndim, job.nt, job.kn, job.flip);
-    else conv_tc_prep_elem<16>(i, job.w, job.out, job.kdim, job.ndim, job.nt, job.kn, job.flip);
+  for (int t = threadIdx.x; t < PREP_ELEMS_PER_BLOCK / 8; t += 256) {
+    const size_t g = g0 + t;
+    if (g >= groups) break;
+    if (job.kc == 1032) conv_tck_prep_group(g, job.w, job.out, job.kdim, job.nt, job.kn, job.flip);
+    else if (job.kc == 32) conv_tc_prep_group<32>(g, job.w, job.out, job.kdim, job.ndim, job.nt, job.kn, job.flip);
+    else conv_tc_prep_group<16>(g, job.w, job.out, job.kdim, job.ndim, job.nt, job.kn, job.flip);
   }
 }
 

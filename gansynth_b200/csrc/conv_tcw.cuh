@@ -67,8 +67,12 @@ struct TcwParams {
 #endif
 };
 
-constexpr int TCW_THREADS = 320;
-constexpr int TCW_CONV_THREADS = 256;
+#ifndef TCW_CW
+#define TCW_CW 8                     // converter warps (a build-time experiment knob: -DTCW_CW=16)
+#endif
+constexpr int TCW_CONV_WARPS = TCW_CW;
+constexpr int TCW_THREADS = 32 * (TCW_CONV_WARPS + 2);        // + the TMA warp and the MMA warp
+constexpr int TCW_CONV_THREADS = 32 * TCW_CONV_WARPS;
 constexpr int TCW_MAX_STAGES = 4;
 
 __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const __grid_constant__ TcwMaps maps, const TcwParams p) {
@@ -103,8 +107,8 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const __grid_c
     const bool counts = p.bias_side == 2 && nj == 0 && hr >= p.bias_r0[mj] && hr < p.bias_r1[mj] && hc >= p.bias_c0 && hc < p.bias_c1;
     big_tab[px] = (uint16_t)((hr * qj * p.pw + (S == 1 ? hc : (hc & 1) * 9 + (hc >> 1))) | (counts ? 0x8000 : 0));
   }
-  if (warp == 9) tc::tmem_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
-  if (warp == 8 && lane == 0) {
+  if (warp == TCW_CONV_WARPS + 1) tc::tmem_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
+  if (warp == TCW_CONV_WARPS && lane == 0) {
     tc::prefetch_tmap(&maps.big[p.map_id[mj]]);
     tc::prefetch_tmap(&maps.small);
   }
@@ -115,11 +119,12 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const __grid_c
   const int acc_w = p.cat ? 2 * p.nb : p.nb;
   const int nchunk_row = p.nstack ? 6 * qb : 2 * qb;         // 16-byte x 8-pixel chunks per staged row of small
 
-  if (warp < 8) {
+  if (warp < TCW_CONV_WARPS) {
     // ============================== fp32 -> bf16 hi/lo split ===========================================
     // item = (pixel, 8-channel chunk q).  A warp works on one q at a time with consecutive pixels on
     // consecutive lanes: conflict-free reads of the swizzled raw rows, contiguous 16-byte stores.
-    const int wq_b = qj >= 8 ? 1 : 8 / qj, wq_s = qb >= 8 ? 1 : 8 / qb;     // warps per chunk
+    constexpr int CW = TCW_CONV_WARPS;
+    const int wq_b = qj >= CW ? 1 : CW / qj, wq_s = qb >= CW ? 1 : CW / qb;     // warps per chunk (idle warps when CW % q != 0)
     int stage = 0, rs = 0;
     uint32_t ph = 0, rph = 0;
     // fused bias gradient: a warp visits at most two 8-channel chunks of the operand (q, q + 8)
@@ -141,10 +146,10 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const __grid_c
       const unsigned char* raw = raw_smem + (size_t)rs * p.raw_slot_bytes;
       unsigned char* st = st_smem + (size_t)stage * p.stage_bytes;
       // ---- big: staged [row][q][pw] (hi block, then lo block)
-      for (int q = (qj >= 8 ? warp : warp / wq_b); q < qj; q += (qj >= 8 ? 8 : qj)) {
+      for (int q = (qj >= CW ? warp : warp / wq_b); q < qj; q += (qj >= CW ? CW : qj)) {
         const unsigned char* chunk = raw + (size_t)(q >> 2) * p.raw_big_chunk;
         const int j0 = 2 * (q & 3);
-        for (int px = (qj >= 8 ? 0 : (warp % wq_b) * 32) + lane; px < nbig_px; px += 32 * wq_b) {
+        for (int px = (qj >= CW ? 0 : (warp % wq_b) * 32) + lane; px < nbig_px; px += 32 * wq_b) {
           const unsigned char* row = chunk + (size_t)px * 128;
           const int sw = px & 7;
           const float4 v0 = *reinterpret_cast<const float4*>(row + ((j0 ^ sw) << 4));
@@ -159,17 +164,17 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const __grid_c
           *reinterpret_cast<uint4*>(st + d) = h4;
           *reinterpret_cast<uint4*>(st + p.big_lo_off + d) = l4;
           if (bias_big && (tab & 0x8000u)) {
-            if (q >= 8) bias_add(bsum[1], v0, v1);     // constant indices: the sums stay in registers
+            if (q >= CW) bias_add(bsum[1], v0, v1);    // constant indices: the sums stay in registers
             else bias_add(bsum[0], v0, v1);
           }
         }
       }
       // ---- small: staged [row][hi q.. | lo q..][8 pixels]
       unsigned char* ss = st + p.small_off;
-      for (int q = (qb >= 8 ? warp : warp / wq_s); q < qb; q += (qb >= 8 ? 8 : qb)) {
+      for (int q = (qb >= CW ? warp : warp / wq_s); q < qb; q += (qb >= CW ? CW : qb)) {
         const unsigned char* chunk = raw + (size_t)big_chunks * p.raw_big_chunk + (size_t)(q >> 2) * p.raw_small_chunk;
         const int j0 = 2 * (q & 3);
-        for (int px = (qb >= 8 ? 0 : (warp % wq_s) * 32) + lane; px < nsmall_px; px += 32 * wq_s) {
+        for (int px = (qb >= CW ? 0 : (warp % wq_s) * 32) + lane; px < nsmall_px; px += 32 * wq_s) {
           const unsigned char* row = chunk + (size_t)px * 128;
           const int sw = px & 7;
           const float4 v0 = *reinterpret_cast<const float4*>(row + ((j0 ^ sw) << 4));
@@ -183,7 +188,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const __grid_c
             bool counts = true;
             if (p.nstack) { const int hc = px % 10; counts = hc >= 1 && hc <= 8; }
             if (counts) {
-              if (q >= 8) bias_add(bsum[1], v0, v1);
+              if (q >= CW) bias_add(bsum[1], v0, v1);
               else bias_add(bsum[0], v0, v1);
             }
           }
@@ -219,16 +224,16 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const __grid_c
     if (bias_big || bias_small) {
       const int qn = bias_big ? qj : qb;
       const int cbase = bias_big ? ch0 : nb0;
-      const int q0 = qn >= 8 ? warp : warp / (8 / qn);
+      const int q0 = qn >= CW ? warp : warp / (CW / qn);
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        const int q = q0 + 8 * i;
+        const int q = q0 + CW * i;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float v = bsum[i][j];
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          if (lane == 0 && q < qn && (i == 0 || qn > 8)) atomicAdd(p.dbias + cbase + q * 8 + j, v);
+          if (lane == 0 && q < qn && (i == 0 || qn > CW)) atomicAdd(p.dbias + cbase + q * 8 + j, v);
         }
       }
     }
@@ -286,7 +291,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const __grid_c
       }
 #endif
     }
-  } else if (warp == 8) {
+  } else if (warp == TCW_CONV_WARPS) {
     // ============================== TMA: one box per 32-channel chunk of each operand ====================
     if (lane == 0) {
       int rs = 0;
@@ -381,5 +386,5 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) conv_tcw_kernel(const __grid_c
 
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 9) tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (warp == TCW_CONV_WARPS + 1) tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }

@@ -780,3 +780,31 @@ class BatchStddevBwd(Function):
         x, df = ctx.saved_tensors
         gx, q = K.stddev_bwd2(x, df, u, *ctx.cfg)
         return gx, q, None, None
+
+
+# ----------------------------------------------------------------------------- pitch classifier (forward only)
+class _ForwardOnly(Function):
+    @staticmethod
+    def backward(ctx, *grads):
+        raise NotImplementedError("the pitch classifier (networks.ResNet) is an evaluation network here: its kernels have "
+                                  "no gradients (the reference trains it with pitch_classifier_main.py, outside the hot path)")
+
+
+class GroupNorm(_ForwardOnly):
+    """group_normalization (ops.py:118-146) [+ relu] on NHWC."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, groups, eps, relu):
+        return K.group_norm(x, gamma, beta, groups, eps, relu)
+
+
+class MaxPool(_ForwardOnly):
+    @staticmethod
+    def forward(ctx, x, ksize, stride):
+        return K.max_pool(x, ksize, stride)
+
+
+class SpatialMean(_ForwardOnly):
+    @staticmethod
+    def forward(ctx, x):
+        return K.spatial_mean(x)

@@ -365,6 +365,32 @@ class CudaBackend(object):
         _lib.call("gs_pool2d", _ptr(x), _ptr(out), n, h, w, c, fh, fw, float(scale), _stream())
         return out
 
+    # ------------------------------------------------------------------ pitch classifier (forward only)
+    def group_norm(self, x, gamma, beta, groups, eps, relu):
+        """ops.py:118-146 on NHWC, optionally followed by relu (networks.py:318-322)."""
+        x, gamma, beta = _chk(x, gamma, beta)
+        n, c = x.shape[0], x.shape[-1]
+        hw = x.numel() // (n * c)
+        y = torch.empty_like(x)
+        stats = torch.empty((n, groups, 2), device=x.device, dtype=torch.float32)
+        _lib.call("gs_group_norm_fwd", _ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(stats), n, hw, c, int(groups), float(eps),
+                  int(bool(relu)), _stream())
+        return y
+
+    def max_pool(self, x, ksize, stride):
+        (x,) = _chk(x)
+        n, h, w, c = x.shape
+        y = torch.empty((n, -(-h // stride), -(-w // stride), c), device=x.device, dtype=torch.float32)
+        _lib.call("gs_max_pool2d", _ptr(x), _ptr(y), n, h, w, c, int(ksize), int(stride), _stream())
+        return y
+
+    def spatial_mean(self, x):
+        (x,) = _chk(x)
+        n, c = x.shape[0], x.shape[-1]
+        y = torch.empty((n, c), device=x.device, dtype=torch.float32)
+        _lib.call("gs_spatial_mean", _ptr(x), _ptr(y), n, x.numel() // (n * c), c, _stream())
+        return y
+
     def transpose_inner(self, x):
         """[n, a, b] -> [n, b, a]"""
         (x,) = _chk(x)

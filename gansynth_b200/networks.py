@@ -15,8 +15,8 @@ import torch
 
 from . import functional as F
 from . import ops
-from .ops import (batch_stddev, conv2d, conv2d_transpose, dense, downscale2d, embedding, pixel_normalization,
-                  upscale2d, variable_scope)
+from .ops import (batch_stddev, conv2d, conv2d_transpose, dense, downscale2d, embedding, group_normalization,
+                  max_pooling2d, pixel_normalization, reduce_mean_spatial, upscale2d, variable_scope)
 
 
 def log(x, base):
@@ -283,3 +283,78 @@ class PGGAN(object):
 
         with variable_scope(name):
             return grow(self.min_depth)
+
+
+class ResNet(object):
+    """The pitch classifier `GANSynth.evaluate` takes its features from (reference networks.py:293-413: pre-activation
+    ResNet v2 blocks without bottleneck, group normalisation, weight-standardised convolutions; constructor arguments as
+    in pitch_classifier_main.py:42-53).  FORWARD ONLY: `__call__(images NCHW [B, 2, H, W]) -> (features [B, F],
+    logits [B, classes])` under torch.no_grad(); training it (models.PitchClassifier of the reference) is outside the hot
+    path.  Variables carry the reference's names (`resnet/conv/weight`, `resnet/residual_block_0_0/conv_1st/weight`,
+    `.../group_normalization_1st/gamma`, `resnet/logits/weight` ...), so a checkpoint of the reference's classifier
+    loads by name (GANSynth.import_tf_checkpoint / VariableStore.load)."""
+
+    def __init__(self, conv_param, pool_param, residual_params, groups, classes):
+        self.conv_param = conv_param
+        self.pool_param = pool_param
+        self.residual_params = residual_params
+        self.groups = groups
+        self.classes = classes
+
+    @staticmethod
+    def _get(param, key):
+        return param[key] if isinstance(param, dict) else getattr(param, key)
+
+    def __call__(self, inputs, name="resnet", reuse=None):
+        get = self._get
+
+        def residual_block(inputs, filters, strides, projection_shortcut, groups):
+            # networks.py:305-358
+            shortcut = inputs
+            with variable_scope("group_normalization_1st"):
+                inputs = group_normalization(inputs, groups=groups, relu=True)
+            if projection_shortcut:
+                with variable_scope("projection_shortcut"):
+                    shortcut = conv2d(inputs, filters=filters, kernel_size=[1, 1], strides=strides, use_bias=False,
+                                      variance_scale=2.0, apply_weight_standardization=True)
+            with variable_scope("conv_1st"):
+                inputs = conv2d(inputs, filters=filters, kernel_size=[3, 3], strides=strides, use_bias=True,
+                                variance_scale=2.0, apply_weight_standardization=True)
+            with variable_scope("group_normalization_2nd"):
+                inputs = group_normalization(inputs, groups=groups, relu=True)
+            with variable_scope("conv_2nd"):
+                inputs = conv2d(inputs, filters=filters, kernel_size=[3, 3], strides=[1, 1], use_bias=True,
+                                variance_scale=2.0, apply_weight_standardization=True)
+            return F.Axpby.apply(inputs, shortcut, 1.0, 1.0)
+
+        with torch.no_grad(), variable_scope(name):
+            inputs = F.nchw_to_nhwc(inputs)
+            if self.conv_param:
+                with variable_scope("conv"):
+                    inputs = conv2d(inputs, filters=get(self.conv_param, "filters"), kernel_size=get(self.conv_param, "kernel_size"),
+                                    strides=get(self.conv_param, "strides"), use_bias=True, variance_scale=2.0,
+                                    apply_weight_standardization=True)
+            if self.pool_param:
+                inputs = max_pooling2d(inputs, kernel_size=get(self.pool_param, "kernel_size"),
+                                       strides=get(self.pool_param, "strides"))
+            for i, rp in enumerate(self.residual_params):
+                for j in range(get(rp, "blocks")):
+                    with variable_scope("residual_block_{}_{}".format(i, j)):
+                        inputs = residual_block(inputs, filters=get(rp, "filters"),
+                                                strides=get(rp, "strides") if j == 0 else [1, 1],
+                                                projection_shortcut=(j == 0), groups=self.groups)
+            with variable_scope("group_normalization"):
+                inputs = group_normalization(inputs, groups=self.groups, relu=True)
+            features = reduce_mean_spatial(inputs)
+            with variable_scope("logits"):
+                logits = dense(features, units=self.classes, use_bias=True, variance_scale=1.0)
+            return features, logits
+
+    @classmethod
+    def pitch_classifier(cls, classes=61):
+        """The configuration of pitch_classifier_main.py:42-53 (ResNet-34 layout, 32 groups, 61 pitches)."""
+        return cls(conv_param=dict(filters=64, kernel_size=[7, 7], strides=[2, 2]),
+                   pool_param=dict(kernel_size=[3, 3], strides=[2, 2]),
+                   residual_params=[dict(filters=64, strides=[1, 1], blocks=3), dict(filters=128, strides=[2, 2], blocks=4),
+                                    dict(filters=256, strides=[2, 2], blocks=6), dict(filters=512, strides=[2, 2], blocks=3)],
+                   groups=32, classes=classes)

@@ -135,20 +135,34 @@ def _zeros(shape, rng):
 
 
 def _reject_normalisers(apply_weight_standardization, apply_spectral_normalization):
-    if apply_weight_standardization or apply_spectral_normalization:
-        raise NotImplementedError("weight standardisation / spectral normalisation are outside the GANSynth hot "
-                                  "path (reference ops.py:5-66); PGGAN never enables them")
+    if apply_spectral_normalization:
+        raise NotImplementedError("spectral normalisation (reference ops.py:8-49) is used by no network of the "
+                                  "reference (and its body calls tf.indentity, which does not exist)")
+
+
+def weight_standardization(weight, epsilon=1.0e-12):
+    """ops.py:52-66: (w - mean) / sqrt(var + eps) over every axis but the last (tf.nn.moments: biased variance).
+    Weight-sized arithmetic of the pitch classifier, done with torch ops."""
+    axes = tuple(range(weight.dim() - 1))
+    mean = weight.mean(dim=axes, keepdim=True)
+    var = weight.var(dim=axes, unbiased=False, keepdim=True)
+    return (weight - mean) / torch.sqrt(var + epsilon)
 
 
 def get_weight(shape, variance_scale=2.0, scale_weight=False, apply_weight_standardization=False,
                apply_spectral_normalization=False):
     """ops.py:149-171.  Returns (variable, alpha): the value the reference would return is
-    variable * alpha; alpha is applied inside the kernels."""
+    variable * alpha; alpha is applied inside the kernels.  With weight standardisation (the pitch classifier) the
+    returned tensor is the standardised weight."""
     _reject_normalisers(apply_weight_standardization, apply_spectral_normalization)
     stddev = math.sqrt(variance_scale / float(np.prod(shape[:-1])))
     if scale_weight:
-        return default_store().get_variable("weight", shape, _truncated_normal(1.0)), stddev
-    return default_store().get_variable("weight", shape, _truncated_normal(stddev)), 1.0
+        weight, alpha = default_store().get_variable("weight", shape, _truncated_normal(1.0)), stddev
+    else:
+        weight, alpha = default_store().get_variable("weight", shape, _truncated_normal(stddev)), 1.0
+    if apply_weight_standardization:
+        weight = weight_standardization(weight).contiguous()
+    return weight, alpha
 
 
 def get_bias(shape):
@@ -294,3 +308,24 @@ def leaky_relu(inputs):
 def tanh(inputs):
     inputs = F.plain(inputs)
     return F.Tanh.apply(inputs)
+
+
+# ----------------------------------------------------------------------------- pitch classifier ops (forward only)
+def group_normalization(inputs, groups, epsilon=1.0e-12, relu=False):
+    """ops.py:118-146 (NHWC): variables `beta` (zeros) and `gamma` (ones) of shape [C]; `relu` (extension) fuses the
+    tf.nn.relu that follows every use in networks.py:318-322, 345-349, 391-396."""
+    inputs = F.plain(inputs)
+    c = inputs.shape[-1]
+    beta = default_store().get_variable("beta", [c], _zeros)
+    gamma = default_store().get_variable("gamma", [c], lambda shape, rng: torch.ones(shape, dtype=torch.float32))
+    return F.GroupNorm.apply(inputs, gamma, beta, int(groups), float(epsilon), bool(relu))
+
+
+def max_pooling2d(inputs, kernel_size, strides):
+    """ops.py:308-316 (NHWC, TF SAME)."""
+    return F.MaxPool.apply(F.plain(inputs), _square(kernel_size), _square(strides))
+
+
+def reduce_mean_spatial(inputs):
+    """tf.reduce_mean(inputs, axis=[2, 3]) of the NCHW reference (networks.py:399): [B, H, W, C] -> [B, C]."""
+    return F.SpatialMean.apply(F.plain(inputs))

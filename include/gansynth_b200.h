@@ -220,6 +220,17 @@ int gs_wav_decode_pcm16(const void* file_bytes, long long n, short* dst, int des
 int gs_wav_read_batch(const char* const* paths, int n, short* dst, int desired_samples, int threads, int* status);
 int gs_pcm16_to_float(const short* src, float* dst, long long n, void* stream);
 
+/* ---- ResNet pitch classifier, forward (networks.py:293-413; evaluation only, models.py:196-230) ------------------
+ * group_normalization ops.py:118-146 on NHWC [n, hw, c]: per (sample, group) mean / biased variance over (hw, c/groups),
+ * y = (x - mean) / sqrt(var + eps) * gamma[c] + beta[c], optionally followed by tf.nn.relu (networks.py:318-322);
+ * `stats` is caller scratch of n * groups * 2 floats.  max_pooling2d ops.py:308-316 (TF SAME).  spatial_mean:
+ * tf.reduce_mean over the image axes (networks.py:399) -> [n, c].  The convolutions use the family above (7x7 / 5x5
+ * kernels and 1x1 stride 2 run on the generic kernels). */
+int gs_group_norm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* stats, int n, long long hw,
+                      int c, int groups, float eps, int relu, void* stream);
+int gs_max_pool2d(const float* x, float* y, int n, int h, int w, int c, int ksize, int stride, void* stream);
+int gs_spatial_mean(const float* x, float* y, int n, long long hw, int c, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

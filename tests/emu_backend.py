@@ -41,8 +41,8 @@ class EmuBackend(object):
         if mask_src is not None:
             return self.mask_mul(EmuBackend.conv_c(self, x, w, bias, ksize, stride, wswap, alpha, act), mask_src)
         wt = self._w(w, wswap).permute(3, 2, 0, 1)
-        pb = 1 if (ksize == 3 and stride == 1) else 0
-        pa = (ksize - stride) - pb if ksize == 3 else 0
+        pb = max(ksize - stride, 0) // 2                 # TF SAME on sizes divisible by the stride
+        pa = max(ksize - stride, 0) - pb
         xp = TF.pad(_nchw(x), (pb, pa, pb, pa))
         y = TF.conv2d(xp, wt, stride=stride) * alpha
         if bias is not None:
@@ -63,7 +63,7 @@ class EmuBackend(object):
         if mask_src is not None:
             return self.mask_mul(EmuBackend.conv_t(self, dy, w, bias, ksize, stride, wswap, alpha, act), mask_src)
         wt = self._w(w, wswap).permute(3, 2, 0, 1)      # [co, ci, k, k]
-        pb = 1 if (ksize == 3 and stride == 1) else 0
+        pb = max(ksize - stride, 0) // 2
         n, oh, ow, co = dy.shape
         full = TF.conv_transpose2d(_nchw(dy), wt, stride=stride)
         h, wd = oh * stride, ow * stride
@@ -83,8 +83,8 @@ class EmuBackend(object):
         if bias_of is not None:
             src = x if bias_of == "x" else dy
             return EmuBackend.conv_w(self, x, dy, ksize, stride, wswap, alpha), src.reshape(-1, src.shape[-1]).sum(0)
-        pb = 1 if (ksize == 3 and stride == 1) else 0
-        pa = (ksize - stride) - pb if ksize == 3 else 0
+        pb = max(ksize - stride, 0) // 2
+        pa = max(ksize - stride, 0) - pb
         xp = TF.pad(_nchw(x), (pb, pa, pb, pa))
         ci, co = x.shape[3], dy.shape[3]
         dw = torch.nn.grad.conv2d_weight(xp, (co, ci, ksize, ksize), _nchw(dy).contiguous(), stride=stride)
@@ -109,6 +109,24 @@ class EmuBackend(object):
 
     def lrelu(self, x):
         return TF.leaky_relu(x, 0.2)
+
+    def group_norm(self, x, gamma, beta, groups, eps, relu):
+        n, c = x.shape[0], x.shape[-1]
+        v = x.reshape(n, -1, groups, c // groups)
+        mean = v.mean(dim=(1, 3), keepdim=True)
+        var = v.var(dim=(1, 3), unbiased=False, keepdim=True)
+        y = ((v - mean) / torch.sqrt(var + eps)).reshape(x.shape) * gamma + beta
+        return torch.relu(y) if relu else y
+
+    def max_pool(self, x, ksize, stride):
+        h, w = x.shape[1], x.shape[2]
+        oh, ow = -(-h // stride), -(-w // stride)
+        ph, pw = max((oh - 1) * stride + ksize - h, 0), max((ow - 1) * stride + ksize - w, 0)
+        xp = TF.pad(_nchw(x), (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2), value=float("-inf"))
+        return _nhwc(TF.max_pool2d(xp, ksize, stride))
+
+    def spatial_mean(self, x):
+        return x.mean(dim=(1, 2))
 
     def mask_mul(self, v, y):
         return v * torch.where(y > 0, torch.ones_like(y), torch.full_like(y, 0.2))

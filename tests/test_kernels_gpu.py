@@ -216,7 +216,7 @@ def test_adam_tf_semantics():
 def test_error_reporting():
     from gansynth_b200 import _lib
     with pytest.raises(_lib.GansynthLibraryError):
-        _lib.call("gs_conv2d_fwd", 0, 0, 0, 0, 1, 8, 8, 4, 4, 5, 1, 0, 1.0, 0, 0, 0)   # ksize 5
+        _lib.call("gs_conv2d_fwd", 0, 0, 0, 0, 1, 8, 8, 4, 4, 4, 1, 0, 1.0, 0, 0, 0)   # ksize 4
     with pytest.raises(_lib.GansynthLibraryError):
         _k().lrelu(torch.zeros(4))   # CPU tensor: no fallback
 

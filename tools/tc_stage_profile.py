@@ -7,7 +7,7 @@ import ctypes
 import os
 import sys
 
-os.environ["GS_LIB"] = "prof"
+os.environ.setdefault("GS_LIB", "prof")
 import torch  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
