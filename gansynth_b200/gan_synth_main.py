@@ -65,7 +65,12 @@ def build(args, device="cuda", world_size=1, rank=0):
 
 
 def main(argv=None):
-    args = build_parser().parse_args(argv)
+    parser = build_parser()
+    args = parser.parse_args(argv)
+    if args.evaluate and str(args.classifier).endswith(".pb"):
+        parser.error("--classifier %s is a frozen TensorFlow GraphDef, which cannot be executed without TensorFlow; pass the "
+                     "CHECKPOINT of the pitch classifier instead (model_dir of the reference's pitch_classifier_main.py): "
+                     "it is run by gansynth_b200.networks.ResNet" % args.classifier)
     world_size, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     if world_size > 1 and not torch.distributed.is_initialized():

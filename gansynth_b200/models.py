@@ -72,6 +72,38 @@ def _select_logits(logits, labels):
     return logits.gather(1, torch.argmax(labels, dim=1, keepdim=True))[:, 0]
 
 
+def load_pitch_classifier(path, device="cuda"):
+    """`networks.ResNet.pitch_classifier()` (pitch_classifier_main.py:42-53) with the variables of the checkpoint at
+    `path`: a TF-1 Saver prefix or model_dir (variables `resnet/...`, Momentum slots ignored) or a `.pt` file holding
+    {name: array}.  A frozen GraphDef (`*.pb`, the reference's --classifier default) is refused: it needs TensorFlow."""
+    from . import networks
+    from . import tf_checkpoint as tfc
+    if path.endswith(".pb"):
+        raise NotImplementedError("%s is a frozen TensorFlow GraphDef; pass the classifier's CHECKPOINT instead (the "
+                                  "model_dir of pitch_classifier_main.py) -- it is run by networks.ResNet" % path)
+    if path.endswith(".pt"):
+        values = torch.load(path, map_location="cpu")
+        values = values.get("variables", values)
+    else:
+        prefix = tfc.latest_checkpoint(path) if os.path.isdir(path) else path
+        if prefix is None:
+            raise FileNotFoundError("no checkpoint under %s" % path)
+        values = tfc.load_bundle(prefix)
+    values = {n: v for n, v in values.items() if n.startswith("resnet/") and "/Momentum" not in n}
+    if not values:
+        raise KeyError("%s holds no `resnet/...` variables" % path)
+    net = networks.ResNet.pitch_classifier(classes=int(np.asarray(values["resnet/logits/bias"]).shape[0]))
+    with torch.no_grad():
+        net(torch.zeros(1, 2, 32, 64, device=device))        # creates the variables (tf.get_variable on first use)
+    store = ops.default_store()
+    missing = [n for n in store.vars if n.startswith("resnet/") and n not in values]
+    if missing:
+        raise KeyError("classifier checkpoint %s lacks %d variables, e.g. %s" % (path, len(missing), missing[0]))
+    # the reference keeps gamma / beta as [1, C, 1, 1] (ops.py:131-140): same values, flat here
+    store.load({n: np.asarray(v).reshape(tuple(store.vars[n].shape)) for n, v in values.items() if n in store.vars})
+    return net
+
+
 class GANSynth(object):
 
     def __init__(self, generator, discriminator, real_input_fn, fake_input_fn, spectral_params, hyper_params,
@@ -563,12 +595,19 @@ class GANSynth(object):
 
     def evaluate(self, model_dir, config, classifier, input_name="images:0", output_names=("features:0", "logits:0")):
         """models.py:196-230: Frechet distance between classifier features of real and generated images over
-        the whole input.  The reference splices a frozen TF GraphDef (`classifier`) onto `real_images` /
-        `fake_images`; a GraphDef cannot be executed without TensorFlow, so `classifier` is a CALLABLE here:
-        images [B, 2, H, W] (CUDA) -> (features [B, F], logits [B, C]) -- the two `output_names`, in order."""
+        the whole input.  The reference splices a frozen TF GraphDef of its pitch classifier (`classifier`) onto
+        `real_images` / `fake_images`; a GraphDef cannot be executed without TensorFlow, so `classifier` is one of
+          * a callable images [B, 2, H, W] (CUDA) -> (features [B, F], logits [B, C]) -- e.g. a `networks.ResNet`, which
+            is that classifier on this repo's kernels (forward only);
+          * the path of a CHECKPOINT of the reference's classifier (a TF-1 Saver prefix / model_dir written by
+            pitch_classifier_main.py, or a `.pt` dict of name -> array): `networks.ResNet.pitch_classifier()` is built
+            and the variables are loaded by their TF names."""
+        if isinstance(classifier, (str, os.PathLike)):
+            classifier = load_pitch_classifier(os.fspath(classifier), self.device)
         if not callable(classifier):
-            raise NotImplementedError("evaluate() takes the pitch classifier as a callable images -> (features, logits); "
-                                      "a frozen TensorFlow GraphDef cannot be run without TensorFlow")
+            raise NotImplementedError("evaluate() takes the pitch classifier as a callable images -> (features, logits) or "
+                                      "as the path of a checkpoint of networks.ResNet; a frozen TensorFlow GraphDef cannot "
+                                      "be run without TensorFlow")
         from . import metrics
         real_feats, fake_feats = [], []
         restored = False

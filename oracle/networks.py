@@ -195,3 +195,86 @@ class PGGAN(object):
             return high() if grown else lerp(low(), middle(), depth - gd)
 
         return grow(self.min_depth)
+
+
+class ResNet(object):
+    """networks.py:293-413 restated (forward): ResNet-v2 blocks, group normalisation, weight-standardised convolutions.
+    `params` maps the reference's variable names (resnet/conv/weight, resnet/residual_block_i_j/..., resnet/logits/...)."""
+
+    def __init__(self, conv_param, pool_param, residual_params, groups, classes):
+        self.conv_param, self.pool_param, self.residual_params = conv_param, pool_param, residual_params
+        self.groups, self.classes = groups, classes
+
+    def variable_shapes(self, in_channels=2):
+        d = {}
+        c = in_channels
+        if self.conv_param:
+            k = self.conv_param["kernel_size"]
+            d["resnet/conv/weight"] = (k[0], k[1], c, self.conv_param["filters"])
+            d["resnet/conv/bias"] = (self.conv_param["filters"],)
+            c = self.conv_param["filters"]
+        for i, rp in enumerate(self.residual_params):
+            for j in range(rp["blocks"]):
+                b = "resnet/residual_block_%d_%d/" % (i, j)
+                f = rp["filters"]
+                d[b + "group_normalization_1st/beta"] = (c,)
+                d[b + "group_normalization_1st/gamma"] = (c,)
+                if j == 0:
+                    d[b + "projection_shortcut/weight"] = (1, 1, c, f)
+                d[b + "conv_1st/weight"] = (3, 3, c, f)
+                d[b + "conv_1st/bias"] = (f,)
+                d[b + "group_normalization_2nd/beta"] = (f,)
+                d[b + "group_normalization_2nd/gamma"] = (f,)
+                d[b + "conv_2nd/weight"] = (3, 3, f, f)
+                d[b + "conv_2nd/bias"] = (f,)
+                c = f
+        d["resnet/group_normalization/beta"] = (c,)
+        d["resnet/group_normalization/gamma"] = (c,)
+        d["resnet/logits/weight"] = (c, self.classes)
+        d["resnet/logits/bias"] = (self.classes,)
+        return d
+
+    def init_variables(self, seed=5, dtype=torch.float32):
+        """Random values for EVERY variable (also gamma / beta / biases, which the reference starts at 1 / 0), so that
+        parity tests exercise them."""
+        gen = torch.Generator().manual_seed(seed)
+        out = {}
+        for name, shape in self.variable_shapes().items():
+            t = torch.randn(shape, generator=gen, dtype=torch.float64)
+            if name.endswith("gamma"):
+                t = 1.0 + 0.3 * t
+            elif name.endswith(("beta", "bias")):
+                t = 0.2 * t
+            else:
+                fan_in = 1
+                for s_ in shape[:-1]:
+                    fan_in *= s_
+                t = t * (2.0 / fan_in) ** 0.5
+            out[name] = t.to(dtype)
+        return out
+
+    def __call__(self, params, images):
+        P = lambda n: params["resnet/" + n]
+        x = images
+        if self.conv_param:
+            x = ops.conv2d_plain(x, P("conv/weight"), P("conv/bias"), self.conv_param["strides"])
+        if self.pool_param:
+            x = ops.max_pooling2d(x, self.pool_param["kernel_size"], self.pool_param["strides"])
+        for i, rp in enumerate(self.residual_params):
+            for j in range(rp["blocks"]):
+                b = "residual_block_%d_%d/" % (i, j)
+                strides = rp["strides"] if j == 0 else [1, 1]
+                shortcut = x
+                x = torch.relu(ops.group_normalization(x, P(b + "group_normalization_1st/gamma"),
+                                                       P(b + "group_normalization_1st/beta"), self.groups))
+                if j == 0:
+                    shortcut = ops.conv2d_plain(x, P(b + "projection_shortcut/weight"), None, strides)
+                x = ops.conv2d_plain(x, P(b + "conv_1st/weight"), P(b + "conv_1st/bias"), strides)
+                x = torch.relu(ops.group_normalization(x, P(b + "group_normalization_2nd/gamma"),
+                                                       P(b + "group_normalization_2nd/beta"), self.groups))
+                x = ops.conv2d_plain(x, P(b + "conv_2nd/weight"), P(b + "conv_2nd/bias"), [1, 1])
+                x = x + shortcut
+        x = torch.relu(ops.group_normalization(x, P("group_normalization/gamma"), P("group_normalization/beta"), self.groups))
+        features = x.mean(dim=(2, 3))
+        logits = features @ P("logits/weight") + P("logits/bias")
+        return features, logits

@@ -151,3 +151,41 @@ def leaky_relu(x):
     _TAPE.flips += int((m != own).sum())
     _TAPE.total += x.numel()
     return torch.where(m, x, 0.2 * x)
+
+
+# ----------------------------------------------------------------------------- pitch classifier ops (ops.py:52-66, 118-146, 308-316)
+def weight_standardization(weight, epsilon=1.0e-12):
+    """ops.py:52-66: tf.nn.moments over every axis but the last (biased variance)."""
+    axes = tuple(range(weight.dim() - 1))
+    mean = weight.mean(dim=axes, keepdim=True)
+    var = weight.var(dim=axes, unbiased=False, keepdim=True)
+    return (weight - mean) / torch.sqrt(var + epsilon)
+
+
+def conv2d_plain(x, weight, bias=None, strides=(1, 1), standardize=True):
+    """ops.py:221-247 with scale_weight=False (the classifier): the variable itself, weight-standardised."""
+    kh, kw = weight.shape[0], weight.shape[1]
+    w = (weight_standardization(weight) if standardize else weight).permute(3, 2, 0, 1)
+    pt, pb = same_padding(x.shape[2], kh, strides[0])
+    pl, pr = same_padding(x.shape[3], kw, strides[1])
+    y = F.conv2d(F.pad(x, (pl, pr, pt, pb)), w, stride=tuple(strides))
+    if bias is not None:
+        y = y + bias.view(1, -1, 1, 1)
+    return y
+
+
+def group_normalization(x, gamma, beta, groups, epsilon=1.0e-12):
+    """ops.py:118-146 (NCHW): moments over (C/groups, H, W) per (sample, group); gamma / beta are [C]."""
+    n, c, h, w = x.shape
+    v = x.reshape(n, groups, c // groups, h, w)
+    mean = v.mean(dim=(2, 3, 4), keepdim=True)
+    var = v.var(dim=(2, 3, 4), unbiased=False, keepdim=True)
+    v = ((v - mean) / torch.sqrt(var + epsilon)).reshape(n, c, h, w)
+    return v * gamma.view(1, -1, 1, 1) + beta.view(1, -1, 1, 1)
+
+
+def max_pooling2d(x, kernel_size, strides):
+    """ops.py:308-316: tf.nn.max_pool, SAME (padding never wins)."""
+    pt, pb = same_padding(x.shape[2], kernel_size[0], strides[0])
+    pl, pr = same_padding(x.shape[3], kernel_size[1], strides[1])
+    return F.max_pool2d(F.pad(x, (pl, pr, pt, pb), value=float("-inf")), tuple(kernel_size), tuple(strides))

@@ -236,3 +236,85 @@ def test_mask_pinned_gradient_criterion(emu, level):
     with oops.MaskTape(masks) as tape:
         o64.generator_update(labels.double(), latents.double(), apply=False)
     assert tape.flips > 0.05 * tape.total
+
+
+# ----------------------------------------------------------------------------- pitch classifier (networks.py:293-413)
+RESNET_SMALL = dict(conv_param=dict(filters=8, kernel_size=[7, 7], strides=[2, 2]), pool_param=dict(kernel_size=[3, 3], strides=[2, 2]),
+                    residual_params=[dict(filters=8, strides=[1, 1], blocks=2), dict(filters=16, strides=[2, 2], blocks=2)],
+                    groups=4, classes=11)
+
+
+def test_resnet_classifier_forward_parity(emu):
+    """networks.ResNet (forward only) on the emulated kernels against the oracle restatement: variable names / shapes of
+    the reference's scopes, features and logits."""
+    import gansynth_b200.networks as pnet
+    onet_ = onet.ResNet(**RESNET_SMALL)
+    params = onet_.init_variables(seed=5)
+    images = torch.randn(3, 2, 32, 64, generator=torch.Generator().manual_seed(1))
+    pres = pnet.ResNet(**RESNET_SMALL)
+    pres(images)                                   # creates the variables (tf.get_variable on first use)
+    assert sorted(emu.vars.keys()) == sorted(params.keys())
+    for n, v in emu.vars.items():
+        assert tuple(v.shape) == tuple(params[n].shape), n
+    emu.load(params)
+    gf, gl = pres(images)
+    wf, wl = onet_(params, images)
+    assert gf.shape == wf.shape == (3, 16) and gl.shape == wl.shape == (3, 11)
+    assert rel_err(gf, wf) < TOL and rel_err(gl, wl) < TOL
+
+
+def test_evaluate_with_a_resnet_classifier(emu):
+    """GANSynth.evaluate with a networks.ResNet as the classifier (the reference splices a frozen GraphDef of this
+    network, models.py:196-230): the Frechet distance equals metrics.frechet_inception_distance of the oracle's features."""
+    import numpy as np
+    import gansynth_b200.metrics as metrics
+    import gansynth_b200.models as pmodels
+    import gansynth_b200.networks as pnet
+    from oracle import spectral_ops as osp
+    opg, params, ppg, latents, labels, images = _pair(1.0, emu, batch=4)
+    cls_o = onet.ResNet(**RESNET_SMALL)
+    cparams = cls_o.init_variables(seed=7)
+    cls_p = pnet.ResNet(**RESNET_SMALL)
+    spectral = dict(waveform_length=152, sample_rate=16000, spectrogram_shape=[16, 16], overlap=0.75)
+    waves = [0.1 * torch.randn(4, 152, generator=torch.Generator().manual_seed(20 + i)) for i in range(3)]
+    lats = [torch.randn(4, 256, generator=torch.Generator().manual_seed(30 + i)) for i in range(3)]
+    it_w, it_z = iter(waves), iter(lats)
+    model = pmodels.GANSynth(ppg.generator, ppg.discriminator, lambda: (next(it_w), labels), lambda: next(it_z), spectral, HYPER,
+                             device="cpu")
+    model.real_images_from_waveforms = lambda w: torch.stack(osp.convert_to_spectrogram(w, **spectral), dim=1)   # no CUDA here
+    cls_p(images)
+    emu.load(cparams)
+    got = model.evaluate("/nonexistent", None, cls_p)
+    real = np.concatenate([cls_o(cparams, torch.stack(osp.convert_to_spectrogram(w, **spectral), dim=1))[0].numpy() for w in waves])
+    fake = np.concatenate([cls_o(cparams, opg.generator(params, z, labels))[0].numpy() for z in lats])
+    want = metrics.frechet_inception_distance(real, fake)
+    assert abs(got["frechet_inception_distance"] - want) < 1e-3 * max(1.0, abs(want))
+
+
+def test_pitch_classifier_checkpoint_loads_by_tf_names(emu, tmp_path):
+    """models.load_pitch_classifier: a TF-1 Saver checkpoint of the reference's classifier (variables `resnet/...`, gamma /
+    beta stored [1, C, 1, 1] as ops.py:131-140 creates them, Momentum slots beside them) -> networks.ResNet in the
+    pitch_classifier_main.py configuration; features equal the oracle's on the same values."""
+    import numpy as np
+    import gansynth_b200.models as pmodels
+    import gansynth_b200.networks as pnet
+    from gansynth_b200 import tf_checkpoint as tfc
+    cfg = pnet.ResNet.pitch_classifier()
+    o = onet.ResNet(cfg.conv_param, cfg.pool_param, cfg.residual_params, cfg.groups, cfg.classes)
+    params = o.init_variables(seed=9)
+    tensors = {}
+    for n, v in params.items():
+        a = v.numpy()
+        tensors[n] = a.reshape(1, -1, 1, 1) if n.endswith(("gamma", "beta")) else a
+        tensors[n + "/Momentum"] = np.zeros_like(tensors[n])
+    tensors["global_step"] = np.asarray(50000, dtype=np.int64)
+    prefix = str(tmp_path / "model.ckpt-50000")
+    tfc.save_bundle(prefix, tensors)
+    net = pmodels.load_pitch_classifier(str(tmp_path), device="cpu")
+    images = torch.randn(2, 2, 32, 64, generator=torch.Generator().manual_seed(2))
+    gf, gl = net(images)
+    wf, wl = o(params, images)
+    assert gf.shape == (2, 512) and gl.shape == (2, 61)
+    assert rel_err(gf, wf) < TOL and rel_err(gl, wl) < TOL
+    with pytest.raises(NotImplementedError):
+        pmodels.load_pitch_classifier("pitch_classifier.pb", device="cpu")

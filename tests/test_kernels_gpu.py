@@ -43,6 +43,9 @@ CONV_CASES = [
     (1, 4, 8, 2, 64, 1, 1),
     (1, 4, 8, 128, 2, 1, 1),
     (1, 40, 24, 36, 20, 3, 1),    # K remainder (36 % 8 = 4)
+    (2, 16, 32, 2, 16, 7, 2),     # pitch classifier: 7x7 stride-2 stem (SAME pads 2 / 3)
+    (1, 12, 20, 3, 8, 5, 1),      # 5x5
+    (2, 8, 16, 16, 32, 1, 2),     # 1x1 stride-2 projection shortcut
 ]
 
 
@@ -248,3 +251,23 @@ def test_context_is_shared_by_the_host_threads_of_a_device():
     t.join()
     assert len(_lib._contexts) == before == 1
     assert torch.equal(out["y"], main)
+
+
+@pytest.mark.parametrize("shape,groups", [((2, 8, 16, 64), 32), ((3, 5, 7, 32), 4), ((1, 16, 64, 512), 32), ((2, 4, 4, 6), 3),
+                                           ((2, 64, 128, 64), 32)])
+@pytest.mark.parametrize("relu", [False, True])
+def test_group_norm(shape, groups, relu):
+    """gs_group_norm_fwd (ops.py:118-146, + the relu that follows every use in networks.py) against the emulation."""
+    x = _rand(*shape, seed=1) * 2.0 + 0.5
+    gamma, beta = 1.0 + 0.3 * _rand(shape[-1], seed=2), 0.2 * _rand(shape[-1], seed=3)
+    got = _k().group_norm(x.cuda(), gamma.cuda(), beta.cuda(), groups, 1e-12, relu)
+    want = EMU.group_norm(x.double(), gamma.double(), beta.double(), groups, 1e-12, relu)
+    assert rel_err(got, want) < 1e-5
+
+
+@pytest.mark.parametrize("shape,k,s", [((2, 16, 32, 64), 3, 2), ((1, 7, 9, 5), 3, 2), ((2, 8, 8, 16), 2, 2), ((1, 6, 10, 4), 3, 1)])
+def test_max_pool_and_spatial_mean(shape, k, s):
+    """gs_max_pool2d (ops.py:308-316, TF SAME: padding never wins) is an index op: bit-exact; gs_spatial_mean."""
+    x = _rand(*shape, seed=4)
+    assert torch.equal(_k().max_pool(x.cuda(), k, s).cpu(), EMU.max_pool(x, k, s))
+    assert rel_err(_k().spatial_mean(x.cuda()), EMU.spatial_mean(x.double())) < 1e-6

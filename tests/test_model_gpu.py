@@ -402,3 +402,29 @@ def test_growth_phase_substeps_replay_as_graphs(cuda_store):
         assert cos > 0.999 and abs(float(gg.norm() / gg_e.norm()) - 1.0) < 2e-2, cos
     # the three iterations really used different blend weights
     assert len({round(w[0], 6) for _, w in results}) == 3
+
+
+# ----------------------------------------------------------------------------- pitch classifier (networks.py:293-413)
+@pytest.mark.parametrize("cfg,shape", [
+    (dict(conv_param=dict(filters=8, kernel_size=[7, 7], strides=[2, 2]), pool_param=dict(kernel_size=[3, 3], strides=[2, 2]),
+          residual_params=[dict(filters=8, strides=[1, 1], blocks=2), dict(filters=16, strides=[2, 2], blocks=2)],
+          groups=4, classes=11), (3, 2, 32, 64)),
+    # tensor-core sized blocks (64 / 128 / 256 channels) and a 512-channel block on the fp32 kernels
+    (dict(conv_param=dict(filters=64, kernel_size=[7, 7], strides=[2, 2]), pool_param=dict(kernel_size=[3, 3], strides=[2, 2]),
+          residual_params=[dict(filters=64, strides=[1, 1], blocks=2), dict(filters=128, strides=[2, 2], blocks=1),
+                           dict(filters=256, strides=[2, 2], blocks=1), dict(filters=512, strides=[2, 2], blocks=1)],
+          groups=32, classes=61), (2, 2, 128, 256)),
+])
+def test_resnet_classifier_forward_parity(cuda_store, cfg, shape):
+    """networks.ResNet on the CUDA kernels (7x7 stem, max pool, group norm + relu, weight-standardised 3x3 / 1x1 stride-2
+    convolutions, spatial mean, logits) against the oracle restatement, 1e-3."""
+    import gansynth_b200.networks as pnet
+    o = onet.ResNet(**cfg)
+    params = o.init_variables(seed=5)
+    images = torch.randn(*shape, generator=torch.Generator().manual_seed(1))
+    net = pnet.ResNet(**cfg)
+    net(images.cuda())
+    cuda_store.load(params)
+    gf, gl = net(images.cuda())
+    wf, wl = o({n: p.double() for n, p in params.items()}, images.double())
+    assert rel_err(gf, wf) < TOL and rel_err(gl, wl) < TOL
