@@ -68,6 +68,8 @@ SIGNATURES = {
     "gs_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _L, _F, _P],
     "gs_spectrogram_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "gs_waveform_fwd": [_P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P],
+    "gs_spectrogram_generic": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "gs_waveform_generic": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "gs_group_norm_fwd": [_P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _I, _P],
     "gs_max_pool2d": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "gs_spatial_mean": [_P, _P, _I, _L, _I, _P],

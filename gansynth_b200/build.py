@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgansynth_b200.so")
-SOURCES = ["abi.cu", "conv.cu", "elementwise.cu", "dense.cu", "spectral.cu", "io.cu", "classifier.cu"]
+SOURCES = ["abi.cu", "conv.cu", "elementwise.cu", "dense.cu", "spectral.cu", "spectral_generic.cu", "io.cu", "classifier.cu"]
 PROBE_LIB = os.path.join(HERE, "libgansynth_b200_probe.so")     # development self-test, not the product ABI
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include"), "-I", CSRC]

@@ -434,6 +434,27 @@ class CudaBackend(object):
                   frames_per_run, _stream())
         return logmel, inst
 
+    def spectrogram_generic(self, wave, consts, time_steps, bins, frame_step):
+        """convert_to_spectrogram for any (bins, overlap): csrc/spectral_generic.cu."""
+        (wave,) = _chk(wave)
+        b, wave_len = wave.shape
+        logmel = torch.empty((b, time_steps, bins), device=wave.device, dtype=torch.float32)
+        inst = torch.empty_like(logmel)
+        scratch = torch.empty_like(logmel)
+        _lib.call("gs_spectrogram_generic", _ptr(wave), _ptr(consts["hann"]), _ptr(consts["mel"]), _ptr(logmel), _ptr(inst),
+                  _ptr(scratch), b, wave_len, time_steps, int(bins), int(frame_step), _stream())
+        return logmel, inst
+
+    def waveform_generic(self, logmel, inst, consts, wave_len, bins, frame_step):
+        """convert_to_waveform for any (bins, overlap)."""
+        logmel, inst = _chk(logmel, inst)
+        b, time_steps, _ = logmel.shape
+        wave = torch.empty((b, wave_len), device=logmel.device, dtype=torch.float32)
+        scratch = torch.empty((b, time_steps, 3 * bins), device=logmel.device, dtype=torch.float32)
+        _lib.call("gs_waveform_generic", _ptr(logmel), _ptr(inst), _ptr(consts["synth_window"]), _ptr(consts["pinv"]), _ptr(wave),
+                  _ptr(scratch), b, wave_len, time_steps, int(bins), int(frame_step), _stream())
+        return wave
+
     def pcm16_to_float(self, pcm):
         """Device half of audio_ops.decode_wav (dataset.py:32-36): int16 -> float32 / 32768."""
         if not (torch.is_tensor(pcm) and pcm.is_cuda and pcm.dtype == torch.int16 and pcm.is_contiguous()):

@@ -6,8 +6,10 @@ function names and arguments).
     convert_to_waveform(log_mel, mel_if, waveform_length, sample_rate, spectrogram_shape, overlap)
         -> waveforms [B, L]
 
-The kernels are specialised to the reference's only configuration (gan_synth_main.py:70-75):
-1024 frequency bins (frame 2048) and 75 % overlap (hop 512); time_steps and waveform_length are free.
+The fast kernels are specialised to the reference's production configuration (gan_synth_main.py:70-75):
+1024 frequency bins (frame 2048) and 75 % overlap (hop 512); time_steps and waveform_length are free.  Any other
+(bins, overlap) -- e.g. BASELINE config 1's [16, 16] spectrogram -- runs on the generic kernels (direct DFT, dense mel
+products; csrc/spectral_generic.cu).
 The constant matrices the reference lets TF constant-fold (tf.signal.linear_to_mel_weight_matrix,
 tfp.math.pinv; spectral_ops.py:76-82,115-122) are built once on the host here and handed to the
 kernels in sparse form: the mel matrix has <= 6 non-zeros per column, its pseudo-inverse decays
@@ -119,11 +121,36 @@ def device_constants(sample_rate, device):
 
 
 def _check_config(spectrogram_shape, overlap):
+    """-> (time_steps, bins, fast): `fast` = the reference's production configuration (1024 bins, 75 % overlap), which
+    the specialised kernels of csrc/spectral.cu serve; every other configuration (spectral_ops.py:50-53 is generic;
+    BASELINE config 1 uses [16, 16]) runs on the generic kernels of csrc/spectral_generic.cu."""
     time_steps, num_freq_bins = (int(s) for s in spectrogram_shape)
-    if num_freq_bins != NUM_BINS or abs(float(overlap) - OVERLAP) > 1e-12:
-        raise NotImplementedError("the spectral kernels are built for 1024 bins at 75 %% overlap "
-                                  "(got %d bins, overlap %r)" % (num_freq_bins, overlap))
-    return time_steps
+    fast = num_freq_bins == NUM_BINS and abs(float(overlap) - OVERLAP) <= 1e-12
+    return time_steps, num_freq_bins, fast
+
+
+_GENERIC_CONSTS = {}
+
+
+def generic_constants(num_freq_bins, sample_rate, overlap, device):
+    """Dense constants of the generic path: analysis / synthesis windows, linear->mel matrix and its pseudo-inverse
+    (spectral_ops.py:50-53, 58-62, 76-82, 115-122, 133-139) -> (dict of device tensors, frame_step)."""
+    key = (int(num_freq_bins), sample_rate, float(overlap), str(device))
+    if key not in _GENERIC_CONSTS:
+        bins = int(num_freq_bins)
+        frame_length = 2 * bins
+        frame_step = int((1.0 - overlap) * frame_length)
+        if frame_step <= 0 or frame_length % frame_step:
+            raise NotImplementedError("overlap %r: the frame step %d must divide the frame length %d" % (overlap, frame_step, frame_length))
+        m = linear_to_mel_weight_matrix(bins, bins, sample_rate, 0.0, sample_rate / 2.0)
+        p = pseudo_inverse(m)
+        n = torch.arange(frame_length, dtype=torch.float64)
+        hann = (0.5 - 0.5 * torch.cos(2.0 * math.pi * n / frame_length)).to(torch.float32)
+        denom = (hann * hann).reshape(-1, frame_step).sum(0).repeat(frame_length // frame_step)
+        host = dict(hann=hann, synth_window=hann / denom, mel=torch.from_numpy(np.ascontiguousarray(m)),
+                    pinv=torch.from_numpy(np.ascontiguousarray(p)))
+        _GENERIC_CONSTS[key] = ({k: v.contiguous().to(device) for k, v in host.items()}, frame_step)
+    return _GENERIC_CONSTS[key]
 
 
 def frames_per_run(batch, time_steps):
@@ -146,9 +173,12 @@ def frames_per_segment(batch, time_steps):
 
 def convert_to_spectrogram(waveforms, waveform_length, sample_rate, spectrogram_shape, overlap):
     """spectral_ops.py:45-94."""
-    time_steps = _check_config(spectrogram_shape, overlap)
+    time_steps, bins, fast = _check_config(spectrogram_shape, overlap)
     if waveforms.shape[1] != waveform_length:
         raise ValueError("waveforms have %d samples, waveform_length is %d" % (waveforms.shape[1], waveform_length))
+    if not fast:
+        consts, frame_step = generic_constants(bins, sample_rate, overlap, waveforms.device)
+        return F.K.spectrogram_generic(waveforms.detach(), consts, time_steps, bins, frame_step)
     consts = device_constants(sample_rate, waveforms.device)
     return F.K.spectrogram_fwd(waveforms.detach(), consts, time_steps,
                                frames_per_run(waveforms.shape[0], time_steps))
@@ -157,9 +187,13 @@ def convert_to_spectrogram(waveforms, waveform_length, sample_rate, spectrogram_
 def convert_to_waveform(log_mel_magnitude_spectrograms, mel_instantaneous_frequencies, waveform_length, sample_rate,
                         spectrogram_shape, overlap):
     """spectral_ops.py:97-149."""
-    time_steps = _check_config(spectrogram_shape, overlap)
-    if tuple(log_mel_magnitude_spectrograms.shape[1:]) != (time_steps, NUM_BINS):
-        raise ValueError("spectrograms must be [B, %d, %d]" % (time_steps, NUM_BINS))
+    time_steps, bins, fast = _check_config(spectrogram_shape, overlap)
+    if tuple(log_mel_magnitude_spectrograms.shape[1:]) != (time_steps, bins):
+        raise ValueError("spectrograms must be [B, %d, %d]" % (time_steps, bins))
+    if not fast:
+        consts, frame_step = generic_constants(bins, sample_rate, overlap, log_mel_magnitude_spectrograms.device)
+        return F.K.waveform_generic(log_mel_magnitude_spectrograms.detach(), mel_instantaneous_frequencies.detach(), consts,
+                                    waveform_length, bins, frame_step)
     consts = device_constants(sample_rate, log_mel_magnitude_spectrograms.device)
     return F.K.waveform_fwd(log_mel_magnitude_spectrograms.detach(), mel_instantaneous_frequencies.detach(), consts,
                             waveform_length, frames_per_segment(log_mel_magnitude_spectrograms.shape[0], time_steps))

@@ -220,6 +220,16 @@ int gs_wav_decode_pcm16(const void* file_bytes, long long n, short* dst, int des
 int gs_wav_read_batch(const char* const* paths, int n, short* dst, int desired_samples, int threads, int* status);
 int gs_pcm16_to_float(const short* src, float* dst, long long n, void* stream);
 
+/* ---- spectral front-end, ANY configuration (spectral_ops.py:50-53 is generic in spectrogram_shape / overlap; BASELINE
+ * config 1 uses a [16, 16] spectrogram: frame 32, hop 8): direct DFTs and dense mel / pseudo-inverse products, one CTA per
+ * frame.  hann, synth_window [2 bins]; mel [bins][bins] (linear x mel, DC row dropped), pinv [bins mel][bins linear];
+ * frame_step = int((1 - overlap) * 2 bins).  scratch is caller-owned: batch * T * bins floats (forward), batch * T * 3 bins
+ * floats (inverse). */
+int gs_spectrogram_generic(const float* wave, const float* hann, const float* mel, float* logmel, float* inst, float* scratch,
+                           int batch, int wave_len, int time_steps, int bins, int frame_step, void* stream);
+int gs_waveform_generic(const float* logmel, const float* inst, const float* synth_window, const float* pinv, float* wave,
+                        float* scratch, int batch, int wave_len, int time_steps, int bins, int frame_step, void* stream);
+
 /* ---- ResNet pitch classifier, forward (networks.py:293-413; evaluation only, models.py:196-230) ------------------
  * group_normalization ops.py:118-146 on NHWC [n, hw, c]: per (sample, group) mean / biased variance over (hw, c/groups),
  * y = (x - mean) / sqrt(var + eps) * gamma[c] + beta[c], optionally followed by tf.nn.relu (networks.py:318-322);

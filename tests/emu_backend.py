@@ -259,6 +259,34 @@ class EmuBackend(object):
         inst = torch.cat([pp[:, :1], md], 1) / pi
         return logmel, inst
 
+    def spectrogram_generic(self, wave, consts, time_steps, bins, frame_step):
+        b, wave_len = wave.shape
+        n_fft = 2 * bins
+        nsamp = frame_step * (time_steps - 1) + n_fft
+        x = TF.pad(wave, (nsamp - wave_len, 0))
+        s = torch.fft.rfft(x.unfold(-1, n_fft, frame_step) * consts["hann"], n=n_fft)[..., 1:]
+        mag, ph = torch.abs(s), torch.atan2(s.imag + 0.0, s.real + 0.0)
+        mm, pp = mag @ consts["mel"], ph @ consts["mel"]
+        pi = torch.tensor(math.pi, dtype=torch.float32)
+        d = pp[:, 1:] - pp[:, :-1]
+        md = torch.remainder(d + pi, 2 * pi) - pi
+        md = torch.where((md == -pi) & (d > 0), pi.expand_as(md), md)
+        return (torch.log(mm + 1e-6) + 3.76) / 10.05, torch.cat([pp[:, :1], md], 1) / pi
+
+    def waveform_generic(self, logmel, inst, consts, wave_len, bins, frame_step):
+        b, t, _ = logmel.shape
+        n_fft = 2 * bins
+        mm = torch.exp(logmel * 10.05 - 3.76)
+        pp = torch.cumsum(inst * torch.tensor(math.pi, dtype=torch.float32), 1)
+        mag, ph = mm @ consts["pinv"], pp @ consts["pinv"]
+        s = TF.pad(torch.complex(mag * torch.cos(ph), mag * torch.sin(ph)), (1, 0))
+        frames = torch.fft.irfft(s, n=n_fft) * consts["synth_window"]
+        nsamp = frame_step * (t - 1) + n_fft
+        out = torch.zeros(b, nsamp)
+        for k in range(t):
+            out[:, frame_step * k:frame_step * k + n_fft] += frames[:, k]
+        return out[:, nsamp - wave_len:]
+
     def waveform_fwd(self, logmel, inst, consts, wave_len, frames_per_segment=None):
         b, t, _ = logmel.shape
         mm = torch.exp(logmel * 10.05 - 3.76)

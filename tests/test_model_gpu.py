@@ -428,3 +428,42 @@ def test_resnet_classifier_forward_parity(cuda_store, cfg, shape):
     gf, gl = net(images.cuda())
     wf, wl = o({n: p.double() for n, p in params.items()}, images.double())
     assert rel_err(gf, wf) < TOL and rel_err(gl, wl) < TOL
+
+
+def test_baseline_config1_trains_on_the_cuda_path_with_media_summaries(cuda_store, tmp_path):
+    """BASELINE configs[0]: the 2-stage PGGAN (4x4 -> 16x16), batch 4, spectrogram_shape [16, 16] (frame 32, hop 8,
+    152-sample clips) -- the spectral front-end runs on the generic kernels -- through GANSynth.train on the GPU with the
+    audio / image summaries of models.py:131-161 switched on; losses finite, the event file carries every summary, the
+    first D loss equals the oracle's."""
+    pytest.importorskip("tensorboard")
+    from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+    import gansynth_b200.models as pmodels
+    import gansynth_b200.networks as pnet
+    from oracle import spectral_ops as osp
+    spectral = dict(waveform_length=152, sample_rate=16000, spectrogram_shape=[16, 16], overlap=0.75)
+    gs = pmodels.get_or_create_global_step()
+    opg, params, ppg = _pair(SMALL, gs / 8, cuda_store)
+    g = torch.Generator().manual_seed(0)
+    batches = [(0.1 * torch.randn(4, 152, generator=g), torch.nn.functional.one_hot(torch.randint(0, 61, (4,), generator=g), 61).float())
+               for _ in range(8)]
+    lats = [torch.randn(4, 256, generator=g) for _ in range(8)]
+    it, itz = iter(batches), iter(lats)
+    model = pmodels.GANSynth(ppg.generator, ppg.discriminator, lambda: next(it), lambda: next(itz), spectral, HYPER)
+    model.media_summaries = True
+    model.train(str(tmp_path), None, total_steps=3, save_checkpoint_steps=0, save_summary_steps=1, log_tensor_steps=1)
+    assert int(gs.value) == 3 and torch.isfinite(model.generator_loss) and torch.isfinite(model.discriminator_loss)
+    acc = EventAccumulator(str(tmp_path), size_guidance={"audio": 0, "images": 0, "scalars": 0})
+    acc.Reload()
+    tags = acc.Tags()
+    assert set(tags["scalars"]) >= {"generator_loss", "discriminator_loss"}
+    assert sorted(tags["audio"]) == sorted("%s/%d" % (n, i) for n in ("real_waveforms", "fake_waveforms") for i in range(4))
+    assert len(tags["images"]) == 16
+    assert acc.Audio("fake_waveforms/0")[0].length_frames == 152
+    im = acc.Images("real_magnitude_spectrograms/0")[0]
+    assert (im.height, im.width) == (16, 16)
+    # the very first D loss against the oracle (same weights, first batch, first latents; growing_level 0)
+    ostep = omodels.GANSynthStep(onet.PGGAN(growing_level=0.0, **SMALL), params, HYPER)
+    real_images = torch.stack(osp.convert_to_spectrogram(batches[0][0], **spectral), dim=1)
+    want, _ = ostep.discriminator_update(real_images, batches[0][1], lats[0], apply=False)
+    first = [e.value for e in acc.Scalars("discriminator_loss")][0]
+    assert abs(first - float(want)) < 1e-3 * max(1.0, abs(float(want))), (first, float(want))

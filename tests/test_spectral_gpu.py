@@ -160,5 +160,36 @@ def test_empty_batch_and_argument_errors():
         F.K.spectrogram_fwd(torch.zeros(1, 70000, device="cuda"), consts, 128, 32)      # 128 frames cover 67072 samples
     with pytest.raises(_lib.GansynthLibraryError):
         F.K.waveform_fwd(torch.zeros(1, 128, 1024, device="cuda"), torch.zeros(1, 128, 1024, device="cuda"), consts, 64000, 12)
-    with pytest.raises(NotImplementedError):
-        sp.convert_to_spectrogram(torch.zeros(1, 64000, device="cuda"), 64000, 16000, [128, 512], 0.75)
+    with pytest.raises(NotImplementedError):      # frame step 2048 * (1 - 0.3) does not divide the frame
+        sp.convert_to_spectrogram(torch.zeros(1, 64000, device="cuda"), 64000, 16000, [128, 1024], 0.3)
+
+
+GENERIC_CONFIGS = [
+    # waveform_length, spectrogram_shape, overlap          (BASELINE config 1: [16, 16] at 75 %: frame 32, hop 8, 152 samples)
+    (152, [16, 16], 0.75), (140, [16, 16], 0.75), (800, [12, 64], 0.5), (1400, [20, 128], 0.75), (4500, [8, 512], 0.5),
+]
+
+
+@pytest.mark.parametrize("wave_len,shape,overlap", GENERIC_CONFIGS)
+def test_generic_configurations_match_oracle(wave_len, shape, overlap):
+    """spectral_ops.py:45-149 is generic in spectrogram_shape / overlap: every configuration other than the production
+    one (1024 bins, 75 %) runs on the generic kernels (csrc/spectral_generic.cu) -- forward and inverse against the
+    oracle, same tolerances as the fast kernels."""
+    from gansynth_b200 import spectral_ops as sp
+    from oracle import spectral_ops as osp
+    cfg = dict(waveform_length=wave_len, sample_rate=16000, spectrogram_shape=shape, overlap=overlap)
+    g = torch.Generator().manual_seed(3)
+    t = torch.arange(wave_len) / 16000.0
+    w = torch.stack([0.1 * torch.randn(wave_len, generator=g), 0.3 * torch.sin(2 * math.pi * 1500.0 * t) + 0.01 * torch.randn(wave_len, generator=g),
+                     torch.zeros(wave_len)])
+    lm, inst = sp.convert_to_spectrogram(w.cuda(), **cfg)
+    olm, oinst = osp.convert_to_spectrogram(w, **cfg)
+    assert tuple(lm.shape) == (3, shape[0], shape[1])
+    assert float((lm.cpu() - olm).abs().max()) < 1e-3
+    d = _if_diff(inst.cpu(), oinst)
+    assert float((d > 1e-3).float().mean()) < 2e-3, float((d > 1e-3).float().mean())
+    assert float(d[2].max()) == 0.0                                  # silence: phase 0 everywhere
+    back = sp.convert_to_waveform(olm.cuda(), oinst.cuda(), **cfg).cpu()
+    oback = osp.convert_to_waveform(olm, oinst, **cfg)
+    assert back.shape == (3, wave_len)
+    assert float((back - oback).abs().max()) < 1e-3 * max(1e-3, float(oback.abs().max()))
