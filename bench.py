@@ -497,6 +497,8 @@ def bench_ours(args):
     cupti, cupti_total, cupti_steps = {}, 0.0, min(2, args.steps)
     if rank == 0:
         cupti, cupti_total = cupti_kernel_times(model, dev[args.warmup:args.warmup + cupti_steps], device)
+    else:
+        run_steps(model, dev[args.warmup:args.warmup + cupti_steps], device, False)     # the steps hold collectives: every rank runs them
     graphs_were = model.use_cuda_graphs
     model.use_cuda_graphs = False
     run_steps(model, dev[:1], device, False)

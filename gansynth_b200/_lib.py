@@ -66,6 +66,8 @@ SIGNATURES = {
     "gs_row_dot": [_P, _P, _P, _I, _L, _P],
     "gs_row_scale": [_P, _P, _P, _I, _L, _F, _P],
     "gs_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _L, _F, _P],
+    "gs_adam_slice": [_L, _I, _I, _P, _P],
+    "gs_adam_step_allreduce": [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _F, _F, _F, _F, _L, _F, _P],
     "gs_spectrogram_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "gs_waveform_fwd": [_P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P],
     "gs_spectrogram_generic": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],

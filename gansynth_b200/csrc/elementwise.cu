@@ -350,6 +350,67 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// ---------------------------------------------------------------- gradient all-reduce FUSED with TF Adam over NVLink
+// Data-parallel update of models.py:81-89 as ONE kernel per network instead of ncclAllReduce + Adam: rank r owns the
+// slice [lo, hi) of the flat buffers.  It (1) reads the SUM of all ranks' gradients of its slice -- MODE 0: one
+// multimem.ld_reduce per 16 bytes on the NVSwitch multicast address (the switch adds the eight copies in flight);
+// MODE 1: plain peer loads through the NVLink-mapped pointers -- (2) applies TF-Adam to its slice (the Adam slots m, v
+// are SHARDED: only the owner's slice is ever valid), (3) writes the new parameters into EVERY rank's buffer
+// (multimem.st broadcast / peer stores).  Per rank and sub-step: n/W * 4 bytes in, n * 4 * (W-1)/W bytes out of the
+// switch, against 2 * n * 4 * (W-1)/W each way for a ring all-reduce, and Adam touches n/W elements instead of n.
+// The caller brackets the launch with cross-rank barriers (all gradients written / all parameters visible).
+__device__ __forceinline__ float4 mm_ld_reduce_f32x4(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void mm_st_f32x4(float* mc, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+template <int MODE>
+__global__ void adam_reduce_kernel(const float* __restrict__ p_local, float* __restrict__ m, float* __restrict__ v,
+                                   const float* g_mc, float* p_mc, const float* const* __restrict__ g_peers,
+                                   float* const* __restrict__ p_peers, int world, long long lo4, long long hi4, float lr_t,
+                                   float b1, float b2, float eps, float gscale) {
+  for (long long q = lo4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; q < hi4; q += (long long)gridDim.x * blockDim.x) {
+    const long long i = 4 * q;
+    float4 g;
+    if (MODE == 0) {
+      g = mm_ld_reduce_f32x4(g_mc + i);
+    } else {
+      g = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < world; ++r) {
+        const float4 t = *reinterpret_cast<const float4*>(g_peers[r] + i);
+        g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+      }
+    }
+    const float4 pm = *reinterpret_cast<const float4*>(m + i), pv = *reinterpret_cast<const float4*>(v + i);
+    const float4 pp = *reinterpret_cast<const float4*>(p_local + i);
+    float4 nm, nv, np;
+#define GS_ADAM1(c)                                   \
+    {                                                 \
+      const float gi = g.c * gscale;                  \
+      nm.c = b1 * pm.c + (1.0f - b1) * gi;            \
+      nv.c = b2 * pv.c + (1.0f - b2) * gi * gi;       \
+      np.c = pp.c - lr_t * nm.c / (sqrtf(nv.c) + eps); \
+    }
+    GS_ADAM1(x) GS_ADAM1(y) GS_ADAM1(z) GS_ADAM1(w)
+#undef GS_ADAM1
+    *reinterpret_cast<float4*>(m + i) = nm;
+    *reinterpret_cast<float4*>(v + i) = nv;
+    if (MODE == 0) {
+      mm_st_f32x4(p_mc + i, np);
+    } else {
+      for (int r = 0; r < world; ++r) *reinterpret_cast<float4*>(p_peers[r] + i) = np;
+    }
+  }
+}
+
 }  // namespace
 
 #define ST ((cudaStream_t)stream)
@@ -818,5 +879,43 @@ extern "C" int gs_adam_step(float* p, const float* g, float* m, float* v, long l
   double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)t)) / (1.0 - pow((double)beta1, (double)t));
   adam_kernel<<<ew_grid(n), EW_BLOCK, 0, ST>>>(p, g, m, v, (size_t)n, (float)lr_t, beta1, beta2, eps, grad_scale);
   GS_CHECK_LAUNCH("adam_step");
+  return GS_OK;
+}
+
+// The slice [*lo, *hi) of an n-element flat buffer that rank `rank` of `world` owns in gs_adam_step_allreduce
+// (multiples of 4 elements: 16-byte multimem accesses).
+extern "C" int gs_adam_slice(long long n, int rank, int world, long long* lo, long long* hi) {
+  GS_CHECK_ARG(n >= 0 && n % 4 == 0 && world >= 1 && rank >= 0 && rank < world && lo && hi, "adam_slice: bad arguments");
+  const long long quads = n / 4, per = (quads + world - 1) / world;
+  const long long a = per * rank < quads ? per * rank : quads, b = per * (rank + 1) < quads ? per * (rank + 1) : quads;
+  *lo = 4 * a;
+  *hi = 4 * b;
+  return GS_OK;
+}
+
+extern "C" int gs_adam_step_allreduce(const float* p_local, float* m, float* v, const float* grad_multicast,
+                                      float* param_multicast, const float* const* grad_peers, float* const* param_peers,
+                                      long long n, int rank, int world, float lr, float beta1, float beta2, float eps,
+                                      long long t, float grad_scale, void* stream) {
+  GS_CHECK_ARG(n >= 0 && n % 4 == 0 && t >= 1 && world >= 1 && rank >= 0 && rank < world, "adam_step_allreduce: bad arguments");
+  const bool mc = grad_multicast != nullptr && param_multicast != nullptr;
+  GS_CHECK_ARG(mc || (grad_peers != nullptr && param_peers != nullptr),
+               "adam_step_allreduce: needs multicast addresses or the arrays of peer pointers");
+  long long lo = 0, hi = 0;
+  int rc = gs_adam_slice(n, rank, world, &lo, &hi);
+  if (rc) return rc;
+  if (hi <= lo) return GS_OK;
+  const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)t)) / (1.0 - pow((double)beta1, (double)t));
+  const long long quads = (hi - lo) / 4;
+  long long blocks = (quads + EW_BLOCK - 1) / EW_BLOCK;
+  const long long cap = (long long)gs_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (mc)
+    adam_reduce_kernel<0><<<(unsigned)blocks, EW_BLOCK, 0, ST>>>(p_local, m, v, grad_multicast, param_multicast, nullptr, nullptr, world,
+                                                                  lo / 4, hi / 4, (float)lr_t, beta1, beta2, eps, grad_scale);
+  else
+    adam_reduce_kernel<1><<<(unsigned)blocks, EW_BLOCK, 0, ST>>>(p_local, m, v, nullptr, nullptr, grad_peers, param_peers, world, lo / 4,
+                                                                  hi / 4, (float)lr_t, beta1, beta2, eps, grad_scale);
+  GS_CHECK_LAUNCH("adam_step_allreduce");
   return GS_OK;
 }

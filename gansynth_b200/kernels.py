@@ -421,6 +421,23 @@ class CudaBackend(object):
         _lib.call("gs_adam_step", _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), float(beta1),
                   float(beta2), float(eps), int(t), float(grad_scale), _stream())
 
+    def adam_slice(self, n, rank, world):
+        import ctypes
+        lo, hi = ctypes.c_longlong(), ctypes.c_longlong()
+        _lib.host_call("gs_adam_slice", int(n), int(rank), int(world), ctypes.byref(lo), ctypes.byref(hi))
+        return int(lo.value), int(hi.value)
+
+    def adam_step_allreduce(self, p_local, m, v, grad_mc, param_mc, grad_peers, param_peers, rank, world, lr, beta1, beta2,
+                            eps, t, grad_scale):
+        """Gradient all-reduce fused with TF-Adam over NVLink (gs_adam_step_allreduce): `grad_mc` / `param_mc` are the
+        NVSwitch multicast addresses (ints, 0 = none), `grad_peers` / `param_peers` int64 CUDA tensors holding the peers'
+        pointers.  The caller brackets the call with cross-rank barriers."""
+        for tns in (p_local, m, v):
+            assert tns.is_cuda and tns.is_contiguous() and tns.dtype == torch.float32
+        _lib.call("gs_adam_step_allreduce", _ptr(p_local), _ptr(m), _ptr(v), int(grad_mc) or None, int(param_mc) or None,
+                  _ptr(grad_peers), _ptr(param_peers), p_local.numel(), int(rank), int(world), float(lr), float(beta1),
+                  float(beta2), float(eps), int(t), float(grad_scale), _stream())
+
     # ------------------------------------------------------------------ spectral
     def spectrogram_fwd(self, wave, consts, time_steps, frames_per_run):
         (wave,) = _chk(wave)

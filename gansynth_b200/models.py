@@ -217,11 +217,86 @@ class GANSynth(object):
             else:
                 self.discriminator(self.generator(latents, labels), labels)
         self._opt = {}
+        symm = self._symmetric_allocator()
         for scope in ("generator", "discriminator"):
-            flat = self.store.pack(scope)
-            self._opt[scope] = dict(flat=flat, grad=torch.zeros_like(flat), m=torch.zeros_like(flat),
-                                    v=torch.zeros_like(flat), t=0)
+            flat = self.store.pack(scope, alloc=symm)
+            grad = symm(flat.numel()) if symm is not None and getattr(flat, "_gs_symmetric", False) else torch.zeros_like(flat)
+            self._opt[scope] = dict(flat=flat, grad=grad, m=torch.zeros_like(flat), v=torch.zeros_like(flat), t=0)
+            if getattr(flat, "_gs_symmetric", False) and getattr(grad, "_gs_symmetric", False):
+                self._opt[scope]["fused"] = self._rendezvous(flat, grad)
         F.K.register_parameters([o["flat"] for o in self._opt.values()])
+
+    # ------------------------------------------------------------------ NVLink symmetric memory (data parallel)
+    def _world(self):
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            return torch.distributed.get_world_size(self.process_group), torch.distributed.get_rank(self.process_group)
+        return 1, 0
+
+    def _symmetric_allocator(self):
+        """numel -> zeroed fp32 tensor in NVLink symmetric memory, or None: single process, CPU, GS_FUSED_ALLREDUCE=0, or a
+        PyTorch build / fabric without symmetric memory (then the update is ncclAllReduce + gs_adam_step)."""
+        world, _ = self._world()
+        if world <= 1 or self.device.type != "cuda" or os.environ.get("GS_FUSED_ALLREDUCE", "1") == "0":
+            return None
+        if torch.distributed.get_backend(self.process_group) != "nccl":
+            return None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            group = self.process_group if self.process_group is not None else torch.distributed.group.WORLD
+            if hasattr(symm_mem, "enable_symm_mem_for_group"):
+                symm_mem.enable_symm_mem_for_group(group.group_name)
+        except Exception as exc:                                   # no symmetric memory in this build
+            logger.warning("symmetric memory unavailable (%s): gradient all-reduce through NCCL", exc)
+            return None
+        device = self.device if self.device.index is not None else torch.device("cuda", torch.cuda.current_device())
+
+        def alloc(numel):
+            t = symm_mem.empty(int(numel), dtype=torch.float32, device=device)
+            t.zero_()
+            t._gs_symmetric = True
+            return t
+        try:
+            alloc(32)
+        except Exception as exc:
+            logger.warning("symmetric memory allocation failed (%s): gradient all-reduce through NCCL", exc)
+            return None
+        return alloc
+
+    def _rendezvous(self, flat, grad):
+        """Maps the parameter and gradient buffers of all ranks into each other (collective) -> what
+        gs_adam_step_allreduce needs: multicast addresses when the NVSwitch offers them (GS_FUSED_ALLREDUCE=p2p forces the
+        peer-pointer form), the peers' pointers, the two handles for the barriers."""
+        import torch.distributed._symmetric_memory as symm_mem
+        group = self.process_group if self.process_group is not None else torch.distributed.group.WORLD
+        hp, hg = symm_mem.rendezvous(flat, group), symm_mem.rendezvous(grad, group)
+        world, rank = self._world()
+
+        def peers(h, t):
+            ptrs = [int(p) for p in h.buffer_ptrs]
+            off = int(t.data_ptr()) - ptrs[rank]                       # the tensor's offset inside the mapped allocation
+            return torch.tensor([p + off for p in ptrs], dtype=torch.int64, device=flat.device), off
+        pp, poff = peers(hp, flat)
+        gp, goff = peers(hg, grad)
+        use_mc = os.environ.get("GS_FUSED_ALLREDUCE", "1") != "p2p" and int(getattr(hp, "multicast_ptr", 0) or 0) != 0 \
+            and int(getattr(hg, "multicast_ptr", 0) or 0) != 0
+        return dict(hp=hp, hg=hg, param_peers=pp, grad_peers=gp, world=world, rank=rank,
+                    param_mc=int(hp.multicast_ptr) + poff if use_mc else 0, grad_mc=int(hg.multicast_ptr) + goff if use_mc else 0,
+                    mode="multimem" if use_mc else "p2p", synced=True)
+
+    def _sync_optimizer_state(self):
+        """The fused update shards the Adam slots: every rank holds only its slice of m / v.  Collective: after this call
+        every rank holds the full slots (before a checkpoint is written)."""
+        for scope, st in (self._opt or {}).items():
+            f = st.get("fused")
+            if f is None or f["synced"]:
+                continue
+            lo, hi = F.K.adam_slice(st["flat"].numel(), f["rank"], f["world"])
+            for key in ("m", "v"):
+                full = torch.zeros_like(st[key])
+                full[lo:hi] = st[key][lo:hi]
+                torch.distributed.all_reduce(full, group=self.process_group)
+                st[key].copy_(full)
+            f["synced"] = True
 
     def _set_trainable(self, scope):
         for n, v in self.store.vars.items():
@@ -248,6 +323,19 @@ class GANSynth(object):
         hp = self.hyper_params
         st = self._opt[scope]
         gflat = st["grad"]
+        f = st.get("fused")
+        if f is not None:
+            # ONE kernel reduces the gradients over NVLink (in the switch when it multicasts), applies Adam to this rank's
+            # slice and broadcasts the new parameters; barriers: all gradients written / all parameters visible
+            st["t"] += 1
+            f["hg"].barrier(channel=0)
+            F.K.adam_step_allreduce(st["flat"], st["m"], st["v"], f["grad_mc"], f["param_mc"], f["grad_peers"], f["param_peers"],
+                                    f["rank"], f["world"], hp[scope + "_learning_rate"], hp[scope + "_beta1"],
+                                    hp[scope + "_beta2"], 1.0e-8, st["t"], 1.0 / f["world"])
+            f["hp"].barrier(channel=1)
+            f["synced"] = False
+            F.K.weight_cache_refresh(st["flat"])
+            return
         scale = 1.0
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             world = torch.distributed.get_world_size(self.process_group)
@@ -529,8 +617,11 @@ class GANSynth(object):
                 t0 = time.time()
             if rank0 and save_summary_steps and iteration % save_summary_steps == 0:
                 self._write_summary(model_dir, step)
-            if rank0 and save_checkpoint_steps and step % save_checkpoint_steps == 0:
-                self.save_checkpoint(model_dir)
+            if save_checkpoint_steps and step % save_checkpoint_steps == 0:
+                self._sync_optimizer_state()         # collective (sharded Adam slots of the fused update); every rank
+                if rank0:
+                    self.save_checkpoint(model_dir)
+        self._sync_optimizer_state()
         if rank0:
             self.save_checkpoint(model_dir)
         if torch.distributed.is_available() and torch.distributed.is_initialized():

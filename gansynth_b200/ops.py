@@ -64,9 +64,10 @@ class VariableStore(object):
         """tf.get_collection(TRAINABLE_VARIABLES, scope=...) (models.py:78-79)."""
         return OrderedDict((n, v) for n, v in self.vars.items() if n.startswith(scope + "/"))
 
-    def pack(self, scope):
+    def pack(self, scope, alloc=None):
         """Moves every variable of `scope` into one flat fp32 buffer (views keep their names) so the
-        optimiser and the data-parallel all-reduce work on a single tensor."""
+        optimiser and the data-parallel all-reduce work on a single tensor.  `alloc(numel) -> zeroed fp32 tensor`
+        lets the caller place the buffer (e.g. in NVLink symmetric memory)."""
         if scope in self.flat:
             return self.flat[scope]
         items = self.trainable_variables(scope)
@@ -75,7 +76,7 @@ class VariableStore(object):
         for n, v in items.items():
             offsets[n] = (off, v.numel())
             off += -(-v.numel() // align) * align
-        flat = torch.zeros(off, device=self.device, dtype=torch.float32)
+        flat = alloc(off) if alloc is not None else torch.zeros(off, device=self.device, dtype=torch.float32)
         for n, v in items.items():
             o, k = offsets[n]
             view = flat[o:o + k].view(v.shape)

@@ -187,6 +187,21 @@ int gs_row_scale(const float* a, const float* s, float* out, int rows, long long
 int gs_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                  float eps, long long t, float grad_scale, void* stream);
 
+/* ---- data-parallel update: gradient all-reduce FUSED with Adam over NVLink / NVSwitch (models.py:81-89 on W ranks) ------
+ * One kernel per network instead of ncclAllReduce + gs_adam_step.  The flat gradient and parameter buffers live in
+ * SYMMETRIC memory (the same allocation mapped on every rank; the host obtains the mappings, e.g. through
+ * torch.distributed._symmetric_memory).  Rank r owns the slice gs_adam_slice(n, r, W): it reads the sum of all ranks'
+ * gradients of that slice -- `grad_multicast` != NULL: multimem.ld_reduce on the NVSwitch multicast address (the switch
+ * adds); else plain loads through `grad_peers[W]` (device array of the peers' pointers) -- applies TF-Adam to the slice
+ * (m, v are therefore SHARDED: only the owner's slice is valid) and writes the new parameters into every rank's buffer
+ * (multimem.st on `param_multicast`, else stores through `param_peers[W]`).  `p_local`: this rank's parameter buffer.
+ * The CALLER brackets the launch with cross-rank barriers: every rank's gradients complete before, every rank's
+ * parameters visible after.  grad_scale = 1 / W for mean-reduced losses. */
+int gs_adam_slice(long long n, int rank, int world, long long* lo, long long* hi);
+int gs_adam_step_allreduce(const float* p_local, float* m, float* v, const float* grad_multicast, float* param_multicast,
+                           const float* const* grad_peers, float* const* param_peers, long long n, int rank, int world,
+                           float lr, float beta1, float beta2, float eps, long long t, float grad_scale, void* stream);
+
 /* ---- spectral front-end, reference configuration frame 2048 / hop 512 / 1024 bins ---------------
  * gs_spectrogram_fwd: spectral_ops.py:45-94.  wave [batch, wave_len] -> logmel, inst [batch, T, 1024].
  *   hann [2048]; mel_k0 int32 [1024] and mel_w [6][1024]: column-sparse linear->mel matrix (first

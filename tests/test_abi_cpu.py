@@ -113,3 +113,27 @@ def test_spectral_launch_policies():
         for t in (4, 8, 20, 128):
             f = sp.frames_per_segment(b, t)
             assert f >= t or f % 8 == 0
+
+
+def test_adam_slices_partition_the_flat_buffer():
+    """gs_adam_slice: the per-rank slices of the fused all-reduce + Adam kernel are 16-byte aligned, disjoint and cover
+    the buffer for every world size (host arithmetic only)."""
+    import ctypes
+    import __graft_entry__ as ge
+    from gansynth_b200 import _lib
+    ge.build()
+    lib = _lib.load()
+    for n in (0, 4, 32, 6830976, 8932256, 1000):
+        for world in (1, 2, 3, 4, 8):
+            edges = []
+            for rank in range(world):
+                lo, hi = ctypes.c_longlong(), ctypes.c_longlong()
+                assert lib.gs_adam_slice(n, rank, world, ctypes.byref(lo), ctypes.byref(hi)) == 0
+                assert lo.value % 4 == 0 and hi.value % 4 == 0 and lo.value <= hi.value
+                edges.append((lo.value, hi.value))
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
+    lo, hi = ctypes.c_longlong(), ctypes.c_longlong()
+    assert lib.gs_adam_slice(10, 0, 2, ctypes.byref(lo), ctypes.byref(hi)) < 0          # not a multiple of 4
+    assert lib.gs_adam_step_allreduce(None, None, None, None, None, None, None, 8, 0, 2, 1e-3, 0.0, 0.99, 1e-8, 1, 0.5, None) < 0
+    assert b"multicast addresses or the arrays of peer pointers" in lib.gs_last_error()
