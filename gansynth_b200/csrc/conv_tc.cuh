@@ -16,8 +16,8 @@
 // ~1e-5 relative at K = 2304, tools/tc_precision.py).  Weights are pre-split into the same layout by
 // conv_tc_prep_kernel, contiguous per (output-channel tile, chunk), and streamed with 1-D bulk copies in
 // groups of `tps` taps (or loaded once and kept when they fit).
-// Warp roles: 0-3 epilogue, 4-11 converters, 12 TMA halo loads, 13 weight copies, 14-15 MMA issue (14 also
-// owns the TMEM allocation).  Rings: raw (TMA -> converters), A (converters -> MMA), B (weights),
+// Warp roles: 0-3 and 16-19 epilogue (two groups splitting the channels of every chunk), 4-11 converters, 12 TMA halo
+// loads, 13 weight copies, 14-15 MMA issue (14 also owns the TMEM allocation).  Rings: raw (TMA -> converters), A (converters -> MMA), B (weights),
 // accumulators (per tile).
 //
 // MMA issue rate.  With 32 output channels one MMA is ~16 cycles of tensor work, less than a single warp
@@ -112,7 +112,7 @@ struct TcOutMaps {
   CUtensorMap m[4];
 };
 
-constexpr int TC_THREADS = 512;
+constexpr int TC_THREADS = 640;         // 16 warps of conv_tc's roles + a second epilogue warpgroup (warps 16-19)
 constexpr int TC_MMA_WARP0 = 14, TC_MMA_WARPS = 2;
 constexpr int TC_CONV_WARPS = 8;
 constexpr int TC_MAX_STAGES = 4;       // raw and operand rings
@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   __shared__ uint64_t acc_full[2], acc_empty[2], aux_full[TC_MAX_AUX], aux_empty[TC_MAX_AUX];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_s[256];
+  __shared__ float ss_x[2][128];          // PNF epilogue: per-pixel partial sums of squares of the two channel halves
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t plane_a = (uint32_t)p.pix * 16u;
@@ -230,8 +231,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     for (int s = 0; s < p.ds; ++s) { tc::mbar_init(&raw_full[s], 1); tc::mbar_init(&raw_empty[s], TC_CONV_WARPS * 32); }
     for (int s = 0; s < p.sa; ++s) { tc::mbar_init(&a_full[s], TC_CONV_WARPS * 32); tc::mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < p.sb; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { tc::mbar_init(&acc_full[s], 1); tc::mbar_init(&acc_empty[s], 128); }
-    for (int s = 0; s < TC_MAX_AUX; ++s) { tc::mbar_init(&aux_full[s], 1); tc::mbar_init(&aux_empty[s], 128); }
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(&acc_full[s], 1); tc::mbar_init(&acc_empty[s], 256); }
+    for (int s = 0; s < TC_MAX_AUX; ++s) { tc::mbar_init(&aux_full[s], 1); tc::mbar_init(&aux_empty[s], 256); }
     tc::mbar_fence_init();
   }
   for (int c = tid; c < p.nt; c += TC_THREADS) bias_s[c] = (p.bias && blockIdx.z == 0) ? p.bias[blockIdx.y * p.nt + c] : 0.0f;
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
       }
     }
-  } else if (warp >= TC_MMA_WARP0) {
+  } else if (warp >= TC_MMA_WARP0 && warp < TC_MMA_WARP0 + TC_MMA_WARPS) {
     // ============================== MMA issue ==========================================================
     // Descriptors are a per-stage base (start address in 16-byte units in the low word) plus tap / K-slice
     // / split offsets.  The WHOLE warp runs this control flow (so the compiler keeps descriptors in uniform
@@ -479,23 +480,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           }
       }
     }
-  } else if (warp < 4) {
+  } else if (warp < 4 || warp >= 16) {
     // ============================== epilogue: TMEM -> alpha, bias, leaky-relu -> staging -> TMA store =====
-    // Thread m owns accumulator row (pixel) m.  32 channels at a time go through a 128B-swizzled staging
-    // tile [128 pixels][32 channels]; one thread hands it to the TMA engine (a box (32, 8, img, rows) of the
-    // (c, w, n, h) view of y: elements outside the tensor are clipped), double-buffered.
+    // Two warpgroups (warps 0-3 and 16-19) work on every unit (accumulator a, 32-channel chunk c0): a warp reads the TMEM
+    // lane quarter warp % 4, so the two warps of a quarter split the COLUMNS -- group g owns channels [16 g, 16 g + 16)
+    // of the chunk (the stage profile showed the single-group epilogue as the pace of the transposed stride-2 form, 83 %
+    // busy, and the busiest role of the stride-2 gather form).  Thread m owns accumulator row (pixel) m.  The chunk goes
+    // through a 128B-swizzled staging tile [128 pixels][32 channels]; one thread hands it to the TMA engine (a box
+    // (32, 8, img, rows) of the (c, w, n, h) view of y: elements outside the tensor are clipped), double-buffered.
+    const int grp = warp >= 16 ? 1 : 0;
+    const int wq = warp & 3;
     int ab = 0;
     uint32_t pacc = 0;
-    const int m = warp * 32 + lane;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const int m = wq * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
     unsigned char* my_row0 = out_smem + (size_t)m * 128;
     const int sw = m & 7;
     const int epi = p.epi;
+    const bool issuer = (tid == 0);
     // pixel of this thread inside a tile: group g = m / 8 = row * img + slot, column m % 8
     const int trow = (m >> 3) / p.img, tslot = (m >> 3) - trow * p.img, tcol = m & 7;
     const float inv_nt = 1.0f / (float)p.nt;
-    int aslot = 0;
-    uint32_t aph = 0, seq = 0;
+    uint32_t seq = 0;
     TC_PROF_DECL
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       int t = tile;
@@ -508,33 +514,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll 1
       for (int a = 0; a < G::NACC; ++a) {
         float rscale = 1.0f;
-        float v[32];
+        float v[16];
         bool have_v = false;
-        auto load_chunk = [&](int c0) {
-          tc::tmem_ld32(tmem_base + lane_base + (uint32_t)(ab * acc_cols + a * acc_w + c0), v);
+        // this thread's 16 channels of chunk c0 (hi / lo column blocks of the cat form with one TMEM round trip)
+        auto load_half = [&](int c0) {
+          uint32_t pk[16], p2[16];
+          const uint32_t col = tmem_base + lane_base + (uint32_t)(ab * acc_cols + a * acc_w + c0 + 16 * grp);
+          tc::tmem_ld16_issue(col, pk);
           if (CAT) {
-            float v2[32];
-            tc::tmem_ld32(tmem_base + lane_base + (uint32_t)(ab * acc_cols + a * acc_w + p.nt + c0), v2);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += v2[j];
+            tc::tmem_ld16_issue(col + (uint32_t)p.nt, p2);
+            tc::tmem_ld_wait(pk, p2);
+          } else {
+            tc::tmem_ld_wait(pk);
           }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(pk[j]) + (CAT ? __uint_as_float(p2[j]) : 0.0f);
         };
         if (epi == TC_EPI_PNF) {
-          // mean square of the activated outputs of this pixel over all channels (one chunk: kept in registers)
+          // mean square of the activated outputs of this pixel over ALL channels: each group sums its halves of every
+          // chunk, the two exchange partial sums through shared memory
           float ss = 0.0f;
 #pragma unroll 1
           for (int c0 = 0; c0 < p.nt; c0 += 32) {
-            load_chunk(c0);
+            load_half(c0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float o = gs_lrelu(fmaf(v[j], p.alpha, bias_s[c0 + j]));
+            for (int j = 0; j < 16; ++j) {
+              const float o = gs_lrelu(fmaf(v[j], p.alpha, bias_s[c0 + 16 * grp + j]));
               ss = fmaf(o, o, ss);
             }
           }
           have_v = (p.nt == 32);
+          ss_x[grp][m] = ss;
+          asm volatile("bar.sync 3, 256;" ::: "memory");
+          ss += ss_x[grp ^ 1][m];                 // rewritten only after the staging barrier of this accumulator's chunks
           rscale = 1.0f / sqrtf(ss * inv_nt + p.eps);
           const int pn = img0 + tslot;
-          if (pn < p.n_img) {
+          if (grp == 0 && pn < p.n_img) {
             int py = th_ * p.rows + trow, px = tw_ * 8 + tcol;
             if (FORM == TC_T2) { py = 2 * py + (a >> 1); px = 2 * px + (a & 1); }
             p.rvec[((size_t)pn * p.h_out + py) * p.w_out + px] = rscale;
@@ -542,43 +557,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
 #pragma unroll 1
         for (int c0 = 0; c0 < p.nt; c0 += 32, ++seq) {
-          if (!have_v) load_chunk(c0);
+          if (!have_v) load_half(c0);
           have_v = false;
           const uint32_t buf = seq & 1u;
           unsigned char* row = my_row0 + (size_t)buf * 16384;
           if (epi == TC_EPI_MASK) {
+            const uint32_t aslot = seq % (uint32_t)p.aux_k, aph = (seq / (uint32_t)p.aux_k) & 1u;
             TC_WAIT(&aux_full[aslot], aph, 2);
             const unsigned char* arow = aux_smem + (size_t)aslot * 16384 + (size_t)m * 128;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 ax = *reinterpret_cast<const float4*>(arow + ((((j >> 2) ^ sw)) << 4));
+            for (int j = 0; j < 16; j += 4) {
+              const int ch16 = 4 * grp + (j >> 2);
+              const float4 ax = *reinterpret_cast<const float4*>(arow + ((ch16 ^ sw) << 4));
               float4 o;
               o.x = v[j + 0] * p.alpha * gs_lrelu_slope(ax.x); o.y = v[j + 1] * p.alpha * gs_lrelu_slope(ax.y);
               o.z = v[j + 2] * p.alpha * gs_lrelu_slope(ax.z); o.w = v[j + 3] * p.alpha * gs_lrelu_slope(ax.w);
-              *reinterpret_cast<float4*>(row + ((((j >> 2) ^ sw)) << 4)) = o;
+              *reinterpret_cast<float4*>(row + ((ch16 ^ sw) << 4)) = o;
             }
             tc::mbar_arrive(&aux_empty[aslot]);
-            if (++aslot == p.aux_k) { aslot = 0; aph ^= 1u; }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 bv = *reinterpret_cast<const float4*>(&bias_s[c0 + j]);
+            for (int j = 0; j < 16; j += 4) {
+              const int ch16 = 4 * grp + (j >> 2);
+              const float4 bv = *reinterpret_cast<const float4*>(&bias_s[c0 + 16 * grp + j]);
               float4 o;
               o.x = fmaf(v[j + 0], p.alpha, bv.x); o.y = fmaf(v[j + 1], p.alpha, bv.y);
               o.z = fmaf(v[j + 2], p.alpha, bv.z); o.w = fmaf(v[j + 3], p.alpha, bv.w);
               if (p.act == 1 && p.ksplit == 1) { o.x = gs_lrelu(o.x); o.y = gs_lrelu(o.y); o.z = gs_lrelu(o.z); o.w = gs_lrelu(o.w); }
               if (epi == TC_EPI_PNF) { o.x *= rscale; o.y *= rscale; o.z *= rscale; o.w *= rscale; }
-              *reinterpret_cast<float4*>(row + ((((j >> 2) ^ sw)) << 4)) = o;
+              *reinterpret_cast<float4*>(row + ((ch16 ^ sw) << 4)) = o;
             }
           }
           tc::fence_proxy_async();
-          // the store that used the OTHER staging buffer must have finished reading it before anyone gets
-          // past this barrier and starts the next chunk
+          // staging tile seq & 1 was last read by the store of chunk seq - 2, which the issuer waited for before the
+          // barrier of chunk seq - 1; here it waits for the store of chunk seq - 1 (its tile is rewritten by chunk seq + 1)
           TC_PROF_BEGIN(1)
-          if (tid == 0) tc::bulk_wait_read<0>();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (issuer) tc::bulk_wait_read<0>();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
           TC_PROF_END(1)
-          if (tid == 0) {
+          if (issuer) {
             if (p.ksplit > 1) tc::tma_reduce_add_4d(&tmy.m[a], out_smem + (size_t)buf * 16384, n0 + c0, tw_ * 8, img0, th_ * p.rows);
             else tc::tma_store_4d(&tmy.m[a], out_smem + (size_t)buf * 16384, n0 + c0, tw_ * 8, img0, th_ * p.rows);
             tc::bulk_commit();
@@ -590,7 +607,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       if (++ab == p.nbuf) { ab = 0; pacc ^= 1u; }
     }
     TC_PROF_FLUSH(p.prof, 19, tid == 0);
-    if (tid == 0) tc::bulk_wait<0>();
+    if (issuer) tc::bulk_wait<0>();
   }
 
   tc::tc_fence_before();

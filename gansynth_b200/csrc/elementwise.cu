@@ -552,7 +552,7 @@ __global__ void pixel_norm_vec_kernel(const float* __restrict__ a, const float* 
         if (MODE != 0) d[k][s] = ok[k] ? *reinterpret_cast<const float4*>(dy + off[k] + ch) : zero4;
         if (MODE == 2) w[k][s] = ok[k] ? *reinterpret_cast<const float4*>(u + off[k] + ch) : zero4;
       }
-      if (MODE != 0) rr[k] = ok[k] ? rin[off[k] / c] : 0.0f;
+      if (MODE != 0) rr[k] = ok[k] ? __ldg(rin + row) : 0.0f;       // (row itself: off[k] / c would be a 64-bit division per pixel)
       if (MODE != 0 && (flags & 4)) {
         // "y form": `a` holds the NORMALISED output y = a * r of the fused conv + pixel-norm layer; a = y / r
         const float inv = ok[k] ? 1.0f / rr[k] : 0.0f;
@@ -578,7 +578,7 @@ __global__ void pixel_norm_vec_kernel(const float* __restrict__ a, const float* 
             const int ch = (s * lpp + li) * 4;
             *reinterpret_cast<float4*>(out + off[k] + ch) = make_float4(t[k][s].x * r, t[k][s].y * r, t[k][s].z * r, t[k][s].w * r);
           }
-          if (li == 0) rout[off[k] / c] = r;
+          if (li == 0) rout[base + (long long)k * ppw + sub] = r;
         }
       } else if (MODE == 1 || MODE == 3) {
         float dot = 0.0f;

@@ -420,6 +420,11 @@ class GANSynth(object):
         if not self.use_cuda_graphs or structure is None:
             return body(*inputs)
         key = (scope, structure) + tuple(tuple(t.shape) for t in inputs)
+        if key not in self._graphs:
+            # growing_depth only increases: a blend depth that has been left never comes back, so the graphs of other
+            # structures (and the output buffers they keep alive) are dropped when a new one appears
+            for old in [k for k in self._graphs if k[0] == scope and k[1] != structure]:
+                del self._graphs[old]
         entry = self._graphs.setdefault(key, dict(calls=0))
         entry["calls"] += 1
         if entry["calls"] <= 2:

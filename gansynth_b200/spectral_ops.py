@@ -153,19 +153,31 @@ def generic_constants(num_freq_bins, sample_rate, overlap, device):
     return _GENERIC_CONSTS[key]
 
 
+_SM_COUNT = None
+
+
+def sm_count():
+    """Streaming multiprocessors of the current device (148 on a B200); the launch policies below size their grids from it."""
+    global _SM_COUNT
+    if _SM_COUNT is None:
+        _SM_COUNT = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count \
+            if torch.cuda.is_available() else 148
+    return _SM_COUNT
+
+
 def frames_per_run(batch, time_steps):
     """Consecutive frames one CTA (16 warps, one frame per warp per round) walks.  Longer runs mean fewer
-    run-boundary rows for the fix-up pass; shorter runs give the 148 SMs more CTAs to balance: 32 when that
+    run-boundary rows for the fix-up pass; shorter runs give the SMs (148 on a B200) more CTAs to balance: 32 when that
     still leaves >= 4 CTAs per SM (batch 256: 1024 CTAs = 6.9 waves), else one round of 16."""
-    if batch * -(-time_steps // 32) >= 4 * 148:
+    if batch * -(-time_steps // 32) >= 4 * sm_count():
         return 32
     return 16
 
 
 def frames_per_segment(batch, time_steps):
-    """Inverse kernel: one CTA per clip when the batch fills the 148 SMs; smaller batches cut every clip into
+    """Inverse kernel: one CTA per clip when the batch fills the SMs; smaller batches cut every clip into
     segments of a multiple of 8 frames so that about one CTA per SM exists (batch 8: 16 segments of 8 frames)."""
-    segs = min(max(1, 148 // max(1, batch)), max(1, time_steps // 8))
+    segs = min(max(1, sm_count() // max(1, batch)), max(1, time_steps // 8))
     if segs <= 1:
         return time_steps
     return 8 * -(-time_steps // (8 * segs))
