@@ -868,7 +868,7 @@ int conv_wgrad_impl(const float* x, const float* dy, float* dw, int n, int h, in
   if (!accumulate) GS_CUDA(cudaMemsetAsync(dw, 0, nel * sizeof(float), st));
   if (impl != 1 && ksize == 1 && stride == 1 && (ci == 2 || co == 2)) {
     const int W = (ci == 2) ? co : ci;
-    if (W != 2 && W <= 256 && 256 % W == 0) {
+    if (W != 2 && W % 4 == 0 && W <= 256 && 256 % W == 0) {
       const long long npix = (long long)n * h * wd;
       // wide-channel index c, narrow index j -> element offset in dw ([ci][co], or [co][ci] when wswap)
       int sc, sj;

@@ -53,9 +53,24 @@ __global__ void __launch_bounds__(256) conv1x1_reduce_kernel(const float* __rest
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   // U pixel groups per iteration: all their loads are issued before the first reduction (memory-level parallelism)
-  constexpr int U = 4;
+  constexpr int U = 8;
+  const bool one_pass = kdim <= lpp * 4;      // every lane holds one float4 of its pixel: all U loads first, then the math
   for (long long p0 = warp * ppw * U; p0 < npix; p0 += nwarps * ppw * U) {
     float acc[U][ND];
+    if (one_pass) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long p = p0 + (long long)u * ppw + slot;
+        v[u] = p < npix ? __ldg(reinterpret_cast<const float4*>(x + p * kdim + sub * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int n = 0; n < ND; ++n) {
+        const float4 b = *reinterpret_cast<const float4*>(sB + n * kdim + sub * 4);
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc[u][n] = v[u].x * b.x + v[u].y * b.y + v[u].z * b.z + v[u].w * b.w;
+      }
+    } else
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long p = p0 + (long long)u * ppw + slot;
@@ -89,35 +104,52 @@ __global__ void __launch_bounds__(256) conv1x1_reduce_kernel(const float* __rest
   }
 }
 
-// dw[c*sc + j*sj] += alpha * sum_p wide[p][c] * narrow[p][j],  j < ND <= 4, wide channels W <= 256.
+// dw[c*sc + j*sj] += alpha * sum_p wide[p][c] * narrow[p][j],  j < ND <= 4, wide channels W <= 256, W % 4 == 0.
+// A thread owns one float4 of wide channels and walks pixels, four of them in flight (16-byte loads); the block meets in
+// shared memory, one atomic per (block, output element).
 template <int ND>
 __global__ void __launch_bounds__(256) conv1x1_w_kernel(const float* __restrict__ wide, const float* __restrict__ narrow,
                                                         float* __restrict__ dw, long long npix, int W, int sc, int sj,
                                                         float alpha, long long pix_per_block) {
-  __shared__ float red[256 * ND];
-  const int lanes = 256 / W;                  // pixel lanes per block (W in {32,64,128,256})
-  const int c = threadIdx.x % W, pl = threadIdx.x / W;
+  __shared__ float red[256 * 4 * ND];
+  const int quads = W / 4;                     // threads per pixel
+  const int lanes = 256 / quads;               // pixel lanes per block (W in {32, 64, 128, 256})
+  const int q = threadIdx.x % quads, pl = threadIdx.x / quads;
   const long long p0 = blockIdx.x * pix_per_block;
   const long long p1 = p0 + pix_per_block < npix ? p0 + pix_per_block : npix;
-  float acc[ND];
+  float4 acc[ND];
 #pragma unroll
-  for (int j = 0; j < ND; ++j) acc[j] = 0.0f;
-  if (pl < lanes) {
-    for (long long p = p0 + pl; p < p1; p += lanes) {
-      const float v = __ldg(wide + p * W + c);
+  for (int j = 0; j < ND; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  constexpr int U = 4;
+  for (long long p = p0 + pl; p < p1; p += (long long)lanes * U) {
+    float4 v[U];
+    float nv[U][ND];
 #pragma unroll
-      for (int j = 0; j < ND; ++j) acc[j] = fmaf(v, __ldg(narrow + p * ND + j), acc[j]);
+    for (int u = 0; u < U; ++u) {
+      const long long pp = p + (long long)u * lanes;
+      const bool ok = pp < p1;
+      v[u] = ok ? __ldg(reinterpret_cast<const float4*>(wide + pp * W + 4 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < ND; ++j) nv[u][j] = ok ? __ldg(narrow + pp * ND + j) : 0.0f;
     }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int j = 0; j < ND; ++j) {
+        acc[j].x = fmaf(v[u].x, nv[u][j], acc[j].x); acc[j].y = fmaf(v[u].y, nv[u][j], acc[j].y);
+        acc[j].z = fmaf(v[u].z, nv[u][j], acc[j].z); acc[j].w = fmaf(v[u].w, nv[u][j], acc[j].w);
+      }
   }
 #pragma unroll
-  for (int j = 0; j < ND; ++j) red[j * 256 + threadIdx.x] = acc[j];
+  for (int j = 0; j < ND; ++j) *reinterpret_cast<float4*>(&red[(j * 256 + threadIdx.x) * 4]) = acc[j];
   __syncthreads();
   if (threadIdx.x < W) {
+    const int c = threadIdx.x, cq = c >> 2, ce = c & 3;
 #pragma unroll
     for (int j = 0; j < ND; ++j) {
       float s = 0.0f;
-      for (int l = 0; l < lanes; ++l) s += red[j * 256 + l * W + threadIdx.x];
-      atomicAdd(dw + (size_t)threadIdx.x * sc + (size_t)j * sj, alpha * s);
+      for (int l = 0; l < lanes; ++l) s += red[(j * 256 + l * quads + cq) * 4 + ce];
+      atomicAdd(dw + (size_t)c * sc + (size_t)j * sj, alpha * s);
     }
   }
 }
