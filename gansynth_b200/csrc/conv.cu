@@ -140,12 +140,12 @@ int try_conv1x1(const float* x, const float* w, const float* bias, float* y, lon
 
 // ------------------------------------------------------------------------------------------------
 // tcgen05 path
-// Workspace of pre-split (bf16 hi/lo) weights: an 8 MB scratch slot (weights used once: gradient-of-gradient
-// operands) followed by a cache region for PARAMETER weights.  Within one optimiser sub-step a parameter is
-// used by several convolutions in the same orientation (D(real), D(fake), the penalty passes): it is split
-// once.  The host invalidates the cache whenever the parameters change (gs_conv_weight_cache_reset) and at the
-// start of every sub-step, so a captured CUDA graph always contains the split kernel of the first use.
-// (the workspace and the cache table live in the caller's gs_context, common.cuh)
+// Pre-split (bf16 hi/lo) weights live in the CALLER's workspace (gs_context, common.cuh): an 8 MB scratch slot (weights
+// used once: gradient-of-gradient operands) followed by a cache of PARAMETER weights, one slot per (parameter, layout).
+// A parameter is used by several convolutions in the same orientation (D(real), D(fake), the penalty passes, both
+// sub-steps): it is split at its first use and RE-SPLIT IN PLACE by gs_conv_weight_cache_refresh after every change of
+// its value (optimiser update, load).  Slots never move, so kernels recorded in CUDA graphs stay valid, and the sub-steps
+// contain no split kernels.  gs_conv_weight_cache_reset drops the table when the parameter buffers themselves move.
 // Where the split copy of `w` in the layout (nt, kc tag, kn, flip) goes: the cached copy of a parameter (need_prep =
 // false), a new cache entry, or the scratch slot.
 unsigned char* prep_slot(gs_context* ctx, bool cacheable, const float* w, int kdim, int ndim, int nt, int kc, int kn, int flip,

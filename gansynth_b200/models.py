@@ -123,8 +123,8 @@ class GANSynth(object):
         self._graph_pool = None
         self._stream = None
         self.use_cuda_graphs = os.environ.get("GS_CUDA_GRAPHS", "1") != "0"
-        # audio / image summaries next to the scalar ones (needs tensorboard).  Validated on the CPU emulation backend
-        # only so far (the round's GPU budget was spent): opt in with GS_MEDIA_SUMMARIES=1 or model.media_summaries = True
+        # audio / image summaries next to the scalar ones (needs tensorboard): opt in with GS_MEDIA_SUMMARIES=1 or
+        # model.media_summaries = True (exercised on the GPU by tests/test_model_gpu.py, BASELINE config 1)
         self.media_summaries = os.environ.get("GS_MEDIA_SUMMARIES", "0") == "1"
         self.generator_loss = None
         self.discriminator_loss = None
@@ -484,6 +484,9 @@ class GANSynth(object):
     def _checkpoint_state(self):
         state = dict(global_step=int(self.global_step.value), variables=self.store.state())
         if self._opt is not None:
+            if any(o.get("fused") is not None and not o["fused"]["synced"] for o in self._opt.values()):
+                raise RuntimeError("the fused data-parallel update shards the Adam slots over the ranks: call "
+                                   "_sync_optimizer_state() on EVERY rank before a checkpoint is written (train() does)")
             state["optimizers"] = {s: dict(m=o["m"].cpu(), v=o["v"].cpu(), t=o["t"]) for s, o in self._opt.items()}
         return state
 
@@ -529,6 +532,8 @@ class GANSynth(object):
                 self._opt[s]["m"].copy_(o["m"])
                 self._opt[s]["v"].copy_(o["v"])
                 self._opt[s]["t"] = o["t"]
+                if self._opt[s].get("fused") is not None:
+                    self._opt[s]["fused"]["synced"] = True       # every rank holds the full slots again
         return paths[-1]
 
     def import_tf_checkpoint(self, prefix_or_dir, labels=None, latents=None):
