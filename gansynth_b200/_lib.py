@@ -75,6 +75,10 @@ SIGNATURES = {
     "gs_group_norm_fwd": [_P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _I, _P],
     "gs_max_pool2d": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "gs_spatial_mean": [_P, _P, _I, _L, _I, _P],
+    "gs_group_norm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _I, _P],
+    "gs_max_pool2d_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "gs_spatial_mean_bwd": [_P, _P, _I, _L, _I, _P],
+    "gs_momentum_step": [_P, _P, _P, _P, _L, _F, _F, _I, _F, _P],
     "gs_crc32c": [_P, _L, _P],
     "gs_wav_decode_pcm16": [_P, _L, _P, _I, _P, _P],
     "gs_wav_read_batch": [_P, _I, _P, _I, _I, _P],

@@ -1,5 +1,6 @@
 """A `tensorflow` stand-in with exactly the names the reference `gan_synth_main.py` touches (SURVEY App. C;
-gan_synth_main.py:39-54, 69, 91-98, 113-114), so that file runs UNCHANGED on gansynth_b200:
+gan_synth_main.py:39-54, 69, 91-98, 113-114) -- and `pitch_classifier_main.py` (:33-37, 69-74, 80-87) -- so that those files
+run UNCHANGED on gansynth_b200:
 
     PYTHONPATH=<repo>/gansynth_b200/compat:<repo> python /path/to/reference/gan_synth_main.py --train ...
 
@@ -56,6 +57,11 @@ class _Train(object):
 
     get_or_create_global_step = create_global_step
     get_global_step = create_global_step
+
+    @staticmethod
+    def exponential_decay(learning_rate, global_step, decay_steps, decay_rate, staircase=False, name=None):
+        """pitch_classifier_main.py:69-74 (called inside hyper_params.learning_rate's lambda with the live global step)."""
+        return _models.exponential_decay(learning_rate, global_step, decay_steps, decay_rate, staircase)
 
 
 train = _Train()

@@ -104,6 +104,134 @@ __global__ void __launch_bounds__(256) spatial_mean_kernel(const float* __restri
   }
 }
 
+// ---- group normalisation backward (training the classifier, models.py:253-304) -----------------------------------------
+// With xh = (x - mean) / sigma, g = dy' * gamma (dy' = dy masked by the fused relu: y > 0), M = hw * c / groups:
+//   dx = (g - mean_M(g) - xh * mean_M(g * xh)) / sigma,   dgamma[c] = sum dy' * xh,   dbeta[c] = sum dy'.
+// Pass 1: per (sample, group) sums of g and g * xh into red [n, groups, 2], per-channel dgamma / dbeta (all zeroed by the
+// host).  Layout and thread mapping as group_stats_kernel (scalar path only: gradients are off the hot path).
+__global__ void __launch_bounds__(256) group_bwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                              const float* __restrict__ dy, const float* __restrict__ stats,
+                                                              const float* __restrict__ gamma, float* __restrict__ red,
+                                                              float* __restrict__ dgamma, float* __restrict__ dbeta, long long hw,
+                                                              int c, int groups, float eps, int relu, long long pix_per_block) {
+  extern __shared__ float sh[];      // [groups][2] | dgamma [c] | dbeta [c]
+  float* sg = sh + 2 * groups;
+  float* sb = sg + c;
+  const int n = blockIdx.y;
+  const int cpg = c / groups;
+  const float inv_cnt = 1.0f / ((float)hw * (float)cpg);
+  for (int i = threadIdx.x; i < 2 * groups + 2 * c; i += blockDim.x) sh[i] = 0.0f;
+  __syncthreads();
+  const long long p0 = blockIdx.x * pix_per_block;
+  const long long p1 = p0 + pix_per_block < hw ? p0 + pix_per_block : hw;
+  const size_t base = (size_t)n * hw * c;
+  // a thread keeps one channel (c <= blockDim.x) or strides over channels; pixels strided by the lanes of that channel
+  for (int ch = threadIdx.x % c; ch < c; ch += (blockDim.x >= c ? c : blockDim.x)) {
+    const int lanes = blockDim.x >= c ? blockDim.x / c : 1, pl = blockDim.x >= c ? threadIdx.x / c : 0;
+    if (pl >= lanes) continue;
+    const int g = ch / cpg;
+    const float* st = stats + ((size_t)n * groups + g) * 2;
+    const float mean = st[0] * inv_cnt;
+    const float rs = rsqrtf(fmaxf(st[1] * inv_cnt - mean * mean, 0.0f) + eps);
+    const float gm = gamma[ch];
+    float s1 = 0.0f, s2 = 0.0f, dg = 0.0f, db = 0.0f;
+    for (long long p = p0 + pl; p < p1; p += lanes) {
+      const size_t i = base + (size_t)p * c + ch;
+      float d = dy[i];
+      if (relu && !(y[i] > 0.0f)) d = 0.0f;
+      const float xh = (x[i] - mean) * rs;
+      s1 += d * gm;
+      s2 += d * gm * xh;
+      dg += d * xh;
+      db += d;
+    }
+    atomicAdd(&sh[2 * g], s1);
+    atomicAdd(&sh[2 * g + 1], s2);
+    atomicAdd(&sg[ch], dg);
+    atomicAdd(&sb[ch], db);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) atomicAdd(red + (size_t)n * 2 * groups + i, sh[i]);
+  for (int i = threadIdx.x; i < c; i += blockDim.x) {
+    atomicAdd(dgamma + i, sg[i]);
+    atomicAdd(dbeta + i, sb[i]);
+  }
+}
+
+__global__ void group_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dy,
+                                       const float* __restrict__ stats, const float* __restrict__ gamma,
+                                       const float* __restrict__ red, float* __restrict__ dx, long long hw, int c, int groups,
+                                       float eps, int relu, size_t total) {
+  const int cpg = c / groups;
+  const float inv_cnt = 1.0f / ((float)hw * (float)cpg);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c);
+    const size_t n = i / ((size_t)hw * c);
+    const size_t sg = (n * groups + ch / cpg) * 2;
+    const float mean = stats[sg] * inv_cnt;
+    const float rs = rsqrtf(fmaxf(stats[sg + 1] * inv_cnt - mean * mean, 0.0f) + eps);
+    float d = dy[i];
+    if (relu && !(y[i] > 0.0f)) d = 0.0f;
+    const float xh = (x[i] - mean) * rs;
+    dx[i] = (d * gamma[ch] - red[sg] * inv_cnt - xh * red[sg + 1] * inv_cnt) * rs;
+  }
+}
+
+// ---- max pooling backward: the gradient of a window goes to its FIRST maximum in row-major window order -------------
+// (what tf.nn.max_pool's gradient does; it matters on exact ties, e.g. the constant region the zero-padded head of a clip
+// produces).  Gather form: an input element scans the windows that contain it and takes a window's gradient when no
+// earlier element of that window holds the same maximum.
+__global__ void max_pool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dy,
+                                    float* __restrict__ dx, int n, int h, int w, int c, int k, int s, int pb, int oh, int ow) {
+  const size_t total = (size_t)n * h * w * c;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c);
+    size_t p = i / c;
+    const int ix = (int)(p % w);
+    p /= w;
+    const int iy = (int)(p % h);
+    const int b = (int)(p / h);
+    const float v = x[i];
+    float acc = 0.0f;
+    // windows (oy, ox) with oy * s - pb <= iy < oy * s - pb + k
+    for (int oy = max(0, (iy + pb - k + s) / s); oy < oh && oy * s - pb <= iy; ++oy)
+      for (int ox = max(0, (ix + pb - k + s) / s); ox < ow && ox * s - pb <= ix; ++ox) {
+        const size_t o = (((size_t)b * oh + oy) * ow + ox) * c + ch;
+        if (y[o] != v) continue;
+        bool first = true;                       // is there an earlier element of this window with the same value?
+        for (int wy = oy * s - pb; first && wy <= iy; ++wy) {
+          if (wy < 0) continue;
+          const int x_end = (wy == iy) ? ix : min(w, ox * s - pb + k);
+          for (int wx = max(0, ox * s - pb); wx < x_end; ++wx)
+            if (x[(((size_t)b * h + wy) * w + wx) * c + ch] == v) { first = false; break; }
+        }
+        if (first) acc += dy[o];
+      }
+    dx[i] = acc;
+  }
+}
+
+// ---- spatial mean backward: dx[n, p, c] = dy[n, c] / hw ---------------------------------------------------------------
+__global__ void spatial_mean_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, long long hw, int c, float inv_hw,
+                                        size_t total) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = i / ((size_t)hw * c);
+    dx[i] = dy[n * c + i % c] * inv_hw;
+  }
+}
+
+// ---- tf.train.MomentumOptimizer (models.py:283-295), weight decay of models.py:267-271 folded in as wd * p ------------
+// accum = momentum * accum + g;  p -= lr * (nesterov ? g + momentum * accum : accum)      (g includes wd * p where wd != 0)
+__global__ void momentum_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ accum,
+                                const float* __restrict__ wd, size_t n, float lr, float momentum, int nesterov, float gscale) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale + (wd ? wd[i] * p[i] : 0.0f);
+    const float a = momentum * accum[i] + gi;
+    accum[i] = a;
+    p[i] -= lr * (nesterov ? gi + momentum * a : a);
+  }
+}
+
 }  // namespace
 
 #define ST ((cudaStream_t)stream)
@@ -151,5 +279,65 @@ extern "C" int gs_spatial_mean(const float* x, float* y, int n, long long hw, in
   blocks_x = (hw + ppb - 1) / ppb;
   spatial_mean_kernel<<<dim3((unsigned)blocks_x, (unsigned)n), 256, 0, ST>>>(x, y, hw, c, ppb, 1.0f / (float)hw);
   GS_CHECK_LAUNCH("spatial_mean");
+  return GS_OK;
+}
+
+
+static unsigned cls_grid(size_t total, int per_block = 1024) {
+  size_t b = (total + per_block - 1) / per_block;
+  const size_t cap = (size_t)gs_num_sms() * 16;
+  return (unsigned)(b < cap ? (b ? b : 1) : cap);
+}
+
+// x, y (the forward output, read only for the relu mask), dy, stats (of the forward) -> dx, dgamma [c], dbeta [c];
+// red: caller scratch of n * groups * 2 floats
+extern "C" int gs_group_norm_bwd(const float* x, const float* y, const float* dy, const float* stats, const float* gamma,
+                                 float* dx, float* dgamma, float* dbeta, float* red, int n, long long hw, int c, int groups,
+                                 float eps, int relu, void* stream) {
+  GS_CHECK_ARG(n > 0 && hw > 0 && c > 0 && groups > 0 && c % groups == 0 && groups <= 1024 && c <= 4096,
+               "group_norm_bwd: bad shape (c %d, groups %d)", c, groups);
+  GS_CUDA(cudaMemsetAsync(red, 0, (size_t)n * groups * 2 * sizeof(float), ST));
+  GS_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)c * sizeof(float), ST));
+  GS_CUDA(cudaMemsetAsync(dbeta, 0, (size_t)c * sizeof(float), ST));
+  long long blocks_x = (2LL * gs_num_sms() + n - 1) / n;
+  long long ppb = (hw + blocks_x - 1) / blocks_x;
+  if (ppb < 16) ppb = 16;
+  blocks_x = (hw + ppb - 1) / ppb;
+  const size_t smem = (size_t)(2 * groups + 2 * c) * sizeof(float);
+  group_bwd_stats_kernel<<<dim3((unsigned)blocks_x, (unsigned)n), 256, smem, ST>>>(x, y, dy, stats, gamma, red, dgamma, dbeta, hw, c, groups,
+                                                                                    eps, relu, ppb);
+  GS_CHECK_LAUNCH("group_bwd_stats");
+  const size_t total = (size_t)n * hw * c;
+  group_bwd_apply_kernel<<<cls_grid(total), 256, 0, ST>>>(x, y, dy, stats, gamma, red, dx, hw, c, groups, eps, relu, total);
+  GS_CHECK_LAUNCH("group_bwd_apply");
+  return GS_OK;
+}
+
+extern "C" int gs_max_pool2d_bwd(const float* x, const float* y, const float* dy, float* dx, int n, int h, int w, int c,
+                                 int ksize, int stride, void* stream) {
+  GS_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0 && ksize >= 1 && stride >= 1, "max_pool2d_bwd: bad shape");
+  const int oh = (h + stride - 1) / stride, ow = (w + stride - 1) / stride;
+  const int pad_h = (oh - 1) * stride + ksize - h;
+  const int pb = (pad_h > 0 ? pad_h : 0) / 2;
+  max_pool_bwd_kernel<<<cls_grid((size_t)n * h * w * c, 256), 256, 0, ST>>>(x, y, dy, dx, n, h, w, c, ksize, stride, pb, oh, ow);
+  GS_CHECK_LAUNCH("max_pool2d_bwd");
+  return GS_OK;
+}
+
+extern "C" int gs_spatial_mean_bwd(const float* dy, float* dx, int n, long long hw, int c, void* stream) {
+  GS_CHECK_ARG(n > 0 && hw > 0 && c > 0, "spatial_mean_bwd: bad shape");
+  const size_t total = (size_t)n * hw * c;
+  spatial_mean_bwd_kernel<<<cls_grid(total), 256, 0, ST>>>(dy, dx, hw, c, 1.0f / (float)hw, total);
+  GS_CHECK_LAUNCH("spatial_mean_bwd");
+  return GS_OK;
+}
+
+// wd: per-element weight-decay coefficient [n] (0 for the normalisation variables) or NULL
+extern "C" int gs_momentum_step(float* p, const float* g, float* accum, const float* wd, long long n, float lr, float momentum,
+                                int nesterov, float grad_scale, void* stream) {
+  GS_CHECK_ARG(n >= 0, "momentum_step: negative size");
+  if (n == 0) return GS_OK;
+  momentum_kernel<<<cls_grid((size_t)n), 256, 0, ST>>>(p, g, accum, wd, (size_t)n, lr, momentum, nesterov, grad_scale);
+  GS_CHECK_LAUNCH("momentum_step");
   return GS_OK;
 }

@@ -782,29 +782,49 @@ class BatchStddevBwd(Function):
         return gx, q, None, None
 
 
-# ----------------------------------------------------------------------------- pitch classifier (forward only)
-class _ForwardOnly(Function):
-    @staticmethod
-    def backward(ctx, *grads):
-        raise NotImplementedError("the pitch classifier (networks.ResNet) is an evaluation network here: its kernels have "
-                                  "no gradients (the reference trains it with pitch_classifier_main.py, outside the hot path)")
-
-
-class GroupNorm(_ForwardOnly):
-    """group_normalization (ops.py:118-146) [+ relu] on NHWC."""
+# ----------------------------------------------------------------------------- pitch classifier (first-order gradients)
+class GroupNorm(Function):
+    """group_normalization (ops.py:118-146) [+ relu] on NHWC; the backward is a kernel (first order only: nothing in the
+    classifier's training differentiates twice)."""
 
     @staticmethod
     def forward(ctx, x, gamma, beta, groups, eps, relu):
-        return K.group_norm(x, gamma, beta, groups, eps, relu)
+        y, stats = K.group_norm(x, gamma, beta, groups, eps, relu)
+        ctx.cfg = (groups, eps, relu)
+        ctx.save_for_backward(x, y, stats, gamma)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, y, stats, gamma = ctx.saved_tensors
+        groups, eps, relu = ctx.cfg
+        dx, dgamma, dbeta = K.group_norm_bwd(x, y, dy.contiguous(), stats, gamma, groups, eps, relu)
+        return dx, dgamma, dbeta, None, None, None
 
 
-class MaxPool(_ForwardOnly):
+class MaxPool(Function):
     @staticmethod
     def forward(ctx, x, ksize, stride):
-        return K.max_pool(x, ksize, stride)
+        y = K.max_pool(x, ksize, stride)
+        ctx.cfg = (ksize, stride)
+        ctx.save_for_backward(x, y)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, y = ctx.saved_tensors
+        return K.max_pool_bwd(x, y, dy.contiguous(), *ctx.cfg), None, None
 
 
-class SpatialMean(_ForwardOnly):
+class SpatialMean(Function):
     @staticmethod
     def forward(ctx, x):
+        ctx.shape = tuple(x.shape)
         return K.spatial_mean(x)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        return K.spatial_mean_bwd(dy.contiguous(), ctx.shape)

@@ -365,9 +365,9 @@ class CudaBackend(object):
         _lib.call("gs_pool2d", _ptr(x), _ptr(out), n, h, w, c, fh, fw, float(scale), _stream())
         return out
 
-    # ------------------------------------------------------------------ pitch classifier (forward only)
+    # ------------------------------------------------------------------ pitch classifier
     def group_norm(self, x, gamma, beta, groups, eps, relu):
-        """ops.py:118-146 on NHWC, optionally followed by relu (networks.py:318-322)."""
+        """ops.py:118-146 on NHWC, optionally followed by relu (networks.py:318-322) -> (y, stats [n, groups, 2])."""
         x, gamma, beta = _chk(x, gamma, beta)
         n, c = x.shape[0], x.shape[-1]
         hw = x.numel() // (n * c)
@@ -375,7 +375,18 @@ class CudaBackend(object):
         stats = torch.empty((n, groups, 2), device=x.device, dtype=torch.float32)
         _lib.call("gs_group_norm_fwd", _ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(stats), n, hw, c, int(groups), float(eps),
                   int(bool(relu)), _stream())
-        return y
+        return y, stats
+
+    def group_norm_bwd(self, x, y, dy, stats, gamma, groups, eps, relu):
+        x, y, dy, stats, gamma = _chk(x, y, dy, stats, gamma)
+        n, c = x.shape[0], x.shape[-1]
+        hw = x.numel() // (n * c)
+        dx = torch.empty_like(x)
+        dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(gamma)
+        red = torch.empty((n, groups, 2), device=x.device, dtype=torch.float32)
+        _lib.call("gs_group_norm_bwd", _ptr(x), _ptr(y), _ptr(dy), _ptr(stats), _ptr(gamma), _ptr(dx), _ptr(dgamma), _ptr(dbeta),
+                  _ptr(red), n, hw, c, int(groups), float(eps), int(bool(relu)), _stream())
+        return dx, dgamma, dbeta
 
     def max_pool(self, x, ksize, stride):
         (x,) = _chk(x)
@@ -384,12 +395,33 @@ class CudaBackend(object):
         _lib.call("gs_max_pool2d", _ptr(x), _ptr(y), n, h, w, c, int(ksize), int(stride), _stream())
         return y
 
+    def max_pool_bwd(self, x, y, dy, ksize, stride):
+        x, y, dy = _chk(x, y, dy)
+        n, h, w, c = x.shape
+        dx = torch.empty_like(x)
+        _lib.call("gs_max_pool2d_bwd", _ptr(x), _ptr(y), _ptr(dy), _ptr(dx), n, h, w, c, int(ksize), int(stride), _stream())
+        return dx
+
     def spatial_mean(self, x):
         (x,) = _chk(x)
         n, c = x.shape[0], x.shape[-1]
         y = torch.empty((n, c), device=x.device, dtype=torch.float32)
         _lib.call("gs_spatial_mean", _ptr(x), _ptr(y), n, x.numel() // (n * c), c, _stream())
         return y
+
+    def spatial_mean_bwd(self, dy, shape):
+        (dy,) = _chk(dy)
+        n, c = dy.shape
+        dx = torch.empty(tuple(shape), device=dy.device, dtype=torch.float32)
+        _lib.call("gs_spatial_mean_bwd", _ptr(dy), _ptr(dx), n, dx.numel() // (n * c), c, _stream())
+        return dx
+
+    def momentum_step(self, p, g, accum, wd, lr, momentum, nesterov, grad_scale=1.0):
+        """tf.train.MomentumOptimizer on flat buffers (gs_momentum_step); wd: per-element L2 coefficient or None."""
+        for tns in (p, g, accum):
+            assert tns.is_cuda and tns.is_contiguous() and tns.dtype == torch.float32
+        _lib.call("gs_momentum_step", _ptr(p), _ptr(g), _ptr(accum), _ptr(wd), p.numel(), float(lr), float(momentum),
+                  int(bool(nesterov)), float(grad_scale), _stream())
 
     def transpose_inner(self, x):
         """[n, a, b] -> [n, b, a]"""

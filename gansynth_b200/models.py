@@ -17,6 +17,7 @@ rank-local batch_stddev groups), one NCCL all-reduce of the flat gradient buffer
 import gc
 import glob
 import logging
+import math
 import os
 import time
 
@@ -768,3 +769,171 @@ class GANSynth(object):
         self.fake_images = images.clone()
         self.fake_waveforms = waveforms.clone()
         return self.fake_waveforms
+
+
+def exponential_decay(learning_rate, global_step, decay_steps, decay_rate, staircase=False):
+    """tf.train.exponential_decay: learning_rate * decay_rate ^ (global_step / decay_steps) (pitch_classifier_main.py:69-74)."""
+    p = float(global_step) / float(decay_steps)
+    return float(learning_rate) * float(decay_rate) ** (math.floor(p) if staircase else p)
+
+
+class PitchClassifier(object):
+    """The reference's pitch classifier trainer (models.py:253-410): `network(images) -> (features, logits)` (a
+    networks.ResNet) on the log-mel / IF images of real clips, softmax cross-entropy + L2 weight decay on every variable
+    whose name does not contain "normalization" (:267-271), tf.train.MomentumOptimizer (Nesterov) with a learning rate that
+    may be a callable of the global step (:283-290).  Same constructor and method signatures; hyper_params keys
+    `weight_decay, learning_rate, momentum, use_nesterov`."""
+
+    SCOPE = "resnet"
+
+    def __init__(self, network, input_fn, spectral_params, hyper_params, device="cuda"):
+        self.network = network
+        self.input_fn = input_fn
+        self.spectral_params = dict(spectral_params)
+        self.hyper_params = hyper_params
+        self.device = torch.device(device)
+        self.global_step = get_or_create_global_step()
+        self.store = ops.default_store()
+        self._opt = None
+        self.loss = self.accuracy = None
+        self._correct = self._seen = 0
+
+    def _hp(self, key):
+        hp = self.hyper_params
+        return hp[key] if isinstance(hp, dict) else getattr(hp, key)
+
+    def _images(self, waveforms):
+        mag, inst = spectral_ops.convert_to_spectrogram(waveforms, **self.spectral_params)
+        return torch.stack([mag, inst], dim=1)
+
+    def _ensure_optimizer(self, images):
+        if self._opt is not None:
+            return
+        with torch.no_grad():
+            self.network(images[:1])                 # tf.get_variable: every variable exists after one call
+        flat = self.store.pack(self.SCOPE)
+        wd = torch.zeros_like(flat)
+        decay = float(self._hp("weight_decay"))
+        for n, (o, k) in self.store.offsets[self.SCOPE].items():
+            if "normalization" not in n:
+                wd[o:o + k] = decay
+        self._opt = dict(flat=flat, grad=torch.zeros_like(flat), accum=torch.zeros_like(flat), wd=wd)
+
+    def learning_rate(self):
+        lr = self._hp("learning_rate")
+        return float(lr(self.global_step)) if callable(lr) else float(lr)
+
+    def loss_fn(self, images, labels):
+        """Cross-entropy part of models.py:264-266 (the weight decay of :267-271 is applied inside the optimiser kernel and
+        added to the reported loss by `weight_decay_loss`)."""
+        features, logits = self.network(images)
+        ce = -(torch.log_softmax(logits, dim=1) * labels).sum(dim=1).mean()
+        return ce, logits
+
+    def weight_decay_loss(self):
+        st = self._opt
+        return 0.5 * float((st["flat"] * st["flat"] * st["wd"]).sum())
+
+    def train_step(self, waveforms=None, labels=None):
+        if waveforms is None:
+            waveforms, labels = self.input_fn()
+        waveforms, labels = _to_device(waveforms, self.device), _to_device(labels, self.device)
+        images = self._images(waveforms)
+        self._ensure_optimizer(images)
+        st = self._opt
+        names = list(self.store.trainable_variables(self.SCOPE).keys())
+        for n in names:
+            self.store.vars[n].requires_grad_(True)
+        ce, logits = self.loss_fn(images, labels)
+        grads = torch.autograd.grad(ce, [self.store.vars[n] for n in names], allow_unused=True)
+        views = self.store.unflatten(self.SCOPE, st["grad"])
+        st["grad"].zero_()
+        pairs = [(views[n], g) for n, g in zip(names, grads) if g is not None]
+        torch._foreach_add_([v for v, _ in pairs], [g for _, g in pairs])
+        scale = 1.0
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            torch.distributed.all_reduce(st["grad"])
+            scale = 1.0 / torch.distributed.get_world_size()
+        self.loss = ce.detach()
+        F.K.momentum_step(st["flat"], st["grad"], st["accum"], st["wd"], self.learning_rate(), self._hp("momentum"),
+                          self._hp("use_nesterov"), scale)
+        F.K.weight_cache_refresh(st["flat"])
+        self.global_step.value += 1
+        pred, true = torch.argmax(logits.detach(), dim=1), torch.argmax(labels, dim=1)
+        self._correct += int((pred == true).sum())
+        self._seen += int(true.numel())
+        self.accuracy = self._correct / max(1, self._seen)       # tf.metrics.accuracy: running
+        return self.loss
+
+    # ------------------------------------------------------------------ checkpoints
+    def save_checkpoint(self, model_dir):
+        os.makedirs(model_dir, exist_ok=True)
+        path = os.path.join(model_dir, "model.ckpt-%d.pt" % int(self.global_step.value))
+        state = dict(global_step=int(self.global_step.value),
+                     variables={n: v for n, v in self.store.state().items() if n.startswith(self.SCOPE + "/")})
+        if self._opt is not None:
+            state["momentum"] = self._opt["accum"].cpu()
+        torch.save(state, path + ".tmp")
+        os.replace(path + ".tmp", path)
+        return path
+
+    def restore_latest(self, model_dir, images=None):
+        paths = sorted(glob.glob(os.path.join(model_dir, "model.ckpt-*.pt")), key=lambda p: int(p.rsplit("-", 1)[1][:-3]))
+        if not paths:
+            return None
+        state = torch.load(paths[-1], map_location="cpu")
+        if images is not None:
+            self._ensure_optimizer(images)
+        self.store.load({n: v for n, v in state["variables"].items() if n in self.store.vars})
+        self.global_step.value = state["global_step"]
+        if self._opt is not None and "momentum" in state:
+            self._opt["accum"].copy_(state["momentum"])
+        return paths[-1]
+
+    def train(self, model_dir, config=None, total_steps=50000, save_checkpoint_steps=1000, save_summary_steps=100,
+              log_tensor_steps=100):
+        """models.py:306-386: train until `total_steps` or the end of the input; checkpoints, loss / accuracy log lines."""
+        restored = False
+        iteration = 0
+        t0 = time.time()
+        while int(self.global_step.value) < total_steps:
+            try:
+                waveforms, labels = self.input_fn()
+            except (StopIteration, IndexError):
+                break
+            if not restored:
+                self.restore_latest(model_dir, self._images(_to_device(waveforms, self.device)))
+                restored = True
+                if int(self.global_step.value) >= total_steps:
+                    break
+            self.train_step(waveforms, labels)
+            iteration += 1
+            step = int(self.global_step.value)
+            if log_tensor_steps and iteration % log_tensor_steps == 0:
+                print("INFO:gansynth_b200:global_step = %d, loss = %.6f, accuracy = %.4f (%.3f sec)" %
+                      (step, float(self.loss) + self.weight_decay_loss(), self.accuracy, time.time() - t0), flush=True)
+                t0 = time.time()
+            if save_checkpoint_steps and step % save_checkpoint_steps == 0:
+                self.save_checkpoint(model_dir)
+        self.save_checkpoint(model_dir)
+
+    def evaluate(self, model_dir, config=None):
+        """models.py:388-410: accuracy over the whole input."""
+        correct = seen = 0
+        restored = False
+        with torch.no_grad():
+            while True:
+                try:
+                    waveforms, labels = self.input_fn()
+                except (StopIteration, IndexError):
+                    break
+                waveforms, labels = _to_device(waveforms, self.device), _to_device(labels, self.device)
+                images = self._images(waveforms)
+                if not restored:
+                    self.network(images[:1])
+                    self.restore_latest(model_dir)
+                    restored = True
+                _, logits = self.network(images)
+                correct += int((torch.argmax(logits, dim=1) == torch.argmax(labels, dim=1)).sum())
+                seen += int(labels.shape[0])
+        return dict(accuracy=correct / max(1, seen))

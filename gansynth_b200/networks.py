@@ -327,7 +327,7 @@ class ResNet(object):
                                 variance_scale=2.0, apply_weight_standardization=True)
             return F.Axpby.apply(inputs, shortcut, 1.0, 1.0)
 
-        with torch.no_grad(), variable_scope(name):
+        with variable_scope(name):
             inputs = F.nchw_to_nhwc(inputs)
             if self.conv_param:
                 with variable_scope("conv"):

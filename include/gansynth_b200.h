@@ -245,7 +245,7 @@ int gs_spectrogram_generic(const float* wave, const float* hann, const float* me
 int gs_waveform_generic(const float* logmel, const float* inst, const float* synth_window, const float* pinv, float* wave,
                         float* scratch, int batch, int wave_len, int time_steps, int bins, int frame_step, void* stream);
 
-/* ---- ResNet pitch classifier, forward (networks.py:293-413; evaluation only, models.py:196-230) ------------------
+/* ---- ResNet pitch classifier (networks.py:293-413; features for evaluate, models.py:196-230; trained by models.py:253-410)
  * group_normalization ops.py:118-146 on NHWC [n, hw, c]: per (sample, group) mean / biased variance over (hw, c/groups),
  * y = (x - mean) / sqrt(var + eps) * gamma[c] + beta[c], optionally followed by tf.nn.relu (networks.py:318-322);
  * `stats` is caller scratch of n * groups * 2 floats.  max_pooling2d ops.py:308-316 (TF SAME).  spatial_mean:
@@ -255,6 +255,21 @@ int gs_group_norm_fwd(const float* x, const float* gamma, const float* beta, flo
                       int c, int groups, float eps, int relu, void* stream);
 int gs_max_pool2d(const float* x, float* y, int n, int h, int w, int c, int ksize, int stride, void* stream);
 int gs_spatial_mean(const float* x, float* y, int n, long long hw, int c, void* stream);
+/* Gradients for TRAINING the classifier (models.py:253-304).  gs_group_norm_bwd: x, y (forward output: the relu mask),
+ * dy, stats (as written by gs_group_norm_fwd) -> dx, dgamma [c], dbeta [c]; red = caller scratch of n * groups * 2 floats.
+ * gs_max_pool2d_bwd: a window's gradient goes to its first maximum in row-major order, as tf's MaxPoolGrad (it matters on
+ * exact ties: constant regions).  gs_momentum_step: tf.train.MomentumOptimizer
+ * (models.py:283-295) on flat buffers with the L2 weight decay of models.py:267-271 folded in as wd[i] * p[i] (wd NULL or a
+ * per-element coefficient, 0 on the normalisation variables):  accum = momentum * accum + g;
+ * p -= lr * (nesterov ? g + momentum * accum : accum). */
+int gs_group_norm_bwd(const float* x, const float* y, const float* dy, const float* stats, const float* gamma, float* dx,
+                      float* dgamma, float* dbeta, float* red, int n, long long hw, int c, int groups, float eps, int relu,
+                      void* stream);
+int gs_max_pool2d_bwd(const float* x, const float* y, const float* dy, float* dx, int n, int h, int w, int c, int ksize,
+                      int stride, void* stream);
+int gs_spatial_mean_bwd(const float* dy, float* dx, int n, long long hw, int c, void* stream);
+int gs_momentum_step(float* p, const float* g, float* accum, const float* wd, long long n, float lr, float momentum,
+                     int nesterov, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

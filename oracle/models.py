@@ -112,3 +112,32 @@ class GANSynthStep(object):
             self.g_opt.apply(self.params, grads)
             self.global_step += 1
         return loss.detach(), grads
+
+
+class PitchClassifierStep(object):
+    """models.py:253-304 restated: softmax cross-entropy (mean over the batch) + weight_decay * sum of tf.nn.l2_loss over the
+    variables whose name lacks "normalization", tf.train.MomentumOptimizer with use_nesterov (accum = momentum * accum + g;
+    var -= lr * (g + momentum * accum))."""
+
+    def __init__(self, resnet, params, weight_decay, momentum, use_nesterov):
+        self.resnet = resnet
+        self.params = {n: p.detach().clone().requires_grad_(True) for n, p in params.items()}
+        self.accum = {n: torch.zeros_like(p) for n, p in params.items()}
+        self.weight_decay, self.momentum, self.use_nesterov = weight_decay, momentum, use_nesterov
+
+    def loss(self, images, labels):
+        _, logits = self.resnet(self.params, images)
+        ce = -(torch.log_softmax(logits, dim=1) * labels).sum(dim=1).mean()
+        l2 = sum((p * p).sum() / 2 for n, p in self.params.items() if "normalization" not in n)
+        return ce + self.weight_decay * l2, ce, logits
+
+    def update(self, images, labels, lr):
+        total, ce, logits = self.loss(images, labels)
+        names = list(self.params)
+        grads = torch.autograd.grad(total, [self.params[n] for n in names])
+        with torch.no_grad():
+            for n, g in zip(names, grads):
+                self.accum[n].mul_(self.momentum).add_(g)
+                step = g + self.momentum * self.accum[n] if self.use_nesterov else self.accum[n]
+                self.params[n].sub_(lr * step)
+        return float(total), float(ce), logits.detach()

@@ -87,7 +87,13 @@ class EmuBackend(object):
         pa = max(ksize - stride, 0) - pb
         xp = TF.pad(_nchw(x), (pb, pa, pb, pa))
         ci, co = x.shape[3], dy.shape[3]
-        dw = torch.nn.grad.conv2d_weight(xp, (co, ci, ksize, ksize), _nchw(dy).contiguous(), stride=stride)
+        # (torch.nn.grad.conv2d_weight aborts on 1x1 stride-2 shapes whose last row / column is unused: differentiate instead)
+        # -- and crop the rows / columns no window reaches (1x1 stride 2), which corrupt the heap in torch's CPU kernel
+        oh, ow = dy.shape[1], dy.shape[2]
+        xp = xp[:, :, :(oh - 1) * stride + ksize, :(ow - 1) * stride + ksize].contiguous()
+        w0 = torch.zeros(co, ci, ksize, ksize, dtype=x.dtype, requires_grad=True)
+        with torch.enable_grad():
+            (dw,) = torch.autograd.grad(TF.conv2d(xp.detach(), w0, stride=stride), w0, _nchw(dy).contiguous().detach())
         dw = dw.permute(2, 3, 1, 0) * alpha             # [k, k, ci, co]
         return (dw.permute(0, 1, 3, 2) if wswap else dw).contiguous()
 
@@ -116,7 +122,35 @@ class EmuBackend(object):
         mean = v.mean(dim=(1, 3), keepdim=True)
         var = v.var(dim=(1, 3), unbiased=False, keepdim=True)
         y = ((v - mean) / torch.sqrt(var + eps)).reshape(x.shape) * gamma + beta
-        return torch.relu(y) if relu else y
+        cnt = v.shape[1] * v.shape[3]
+        stats = torch.stack([v.sum(dim=(1, 3)), (v * v).sum(dim=(1, 3))], dim=-1)          # [n, groups, 2] as the kernel keeps them
+        return (torch.relu(y) if relu else y), stats
+
+    def group_norm_bwd(self, x, y, dy, stats, gamma, groups, eps, relu):
+        xd, gd = x.detach().clone().requires_grad_(True), gamma.detach().clone().requires_grad_(True)
+        bd = torch.zeros_like(gamma).requires_grad_(True)
+        if relu:
+            dy = dy * (y > 0).to(dy.dtype)          # the mask comes from the forward OUTPUT (which includes beta)
+        with torch.enable_grad():
+            out, _ = EmuBackend.group_norm(self, xd, gd, bd, groups, eps, False)
+            dx, dg, db = torch.autograd.grad(out, (xd, gd, bd), dy)
+        return dx, dg, db
+
+    def max_pool_bwd(self, x, y, dy, ksize, stride):
+        xd = x.detach().clone().requires_grad_(True)
+        with torch.enable_grad():
+            (dx,) = torch.autograd.grad(EmuBackend.max_pool(self, xd, ksize, stride), xd, dy)
+        return dx
+
+    def spatial_mean_bwd(self, dy, shape):
+        hw = shape[1] * shape[2]
+        return (dy / hw).view(shape[0], 1, 1, shape[3]).expand(*shape).contiguous()
+
+    def momentum_step(self, p, g, accum, wd, lr, momentum, nesterov, grad_scale=1.0):
+        with torch.no_grad():
+            gi = g * grad_scale + (wd * p if wd is not None else 0.0)
+            accum.mul_(momentum).add_(gi)
+            p.sub_(lr * (gi + momentum * accum if nesterov else accum))
 
     def max_pool(self, x, ksize, stride):
         h, w = x.shape[1], x.shape[2]

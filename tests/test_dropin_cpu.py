@@ -47,3 +47,14 @@ def test_stand_in_refuses_everything_else():
             "assert ok" % (ROOT, os.path.join(ROOT, "gansynth_b200", "compat")))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_unmodified_pitch_classifier_main_builds_the_model(tmp_path):
+    """The reference's pitch_classifier_main.py, byte for byte: ResNet + PitchClassifier construction through the stand-in
+    (tf.train.exponential_decay inside the learning-rate lambda included); no action flag, so it exits after the build."""
+    ref = "/root/reference/pitch_classifier_main.py"
+    shutil.copy(ref, tmp_path / "pitch_classifier_main.py")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "gansynth_b200", "compat"), ROOT]))
+    r = subprocess.run([sys.executable, "pitch_classifier_main.py"], cwd=tmp_path, env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]

@@ -318,3 +318,42 @@ def test_pitch_classifier_checkpoint_loads_by_tf_names(emu, tmp_path):
     assert rel_err(gf, wf) < TOL and rel_err(gl, wl) < TOL
     with pytest.raises(NotImplementedError):
         pmodels.load_pitch_classifier("pitch_classifier.pb", device="cpu")
+
+
+def test_pitch_classifier_training_parity(emu):
+    """models.PitchClassifier (models.py:253-410) on the emulated kernels against the oracle restatement: three Momentum
+    (Nesterov) steps with weight decay and a decaying learning rate -- loss, running accuracy, every variable."""
+    import gansynth_b200.models as pmodels
+    import gansynth_b200.networks as pnet
+    from oracle import spectral_ops as osp
+    o = onet.ResNet(**RESNET_SMALL)
+    params = o.init_variables(seed=5)
+    net = pnet.ResNet(**RESNET_SMALL)
+    spectral = dict(waveform_length=600, sample_rate=16000, spectrogram_shape=[32, 64], overlap=0.75)
+    g = torch.Generator().manual_seed(4)
+    batches = [(0.1 * torch.randn(4, 600, generator=g), torch.nn.functional.one_hot(torch.randint(0, 11, (4,), generator=g), 11).float())
+               for _ in range(3)]
+    hp = dict(weight_decay=1e-3, momentum=0.9, use_nesterov=True,
+              learning_rate=lambda step: pmodels.exponential_decay(0.05, step, 2, 0.5))
+    it = iter(batches)
+    clf = pmodels.PitchClassifier(net, lambda: next(it), spectral, hp, device="cpu")
+    clf._images = lambda w: torch.stack(osp.convert_to_spectrogram(w, **spectral), dim=1)          # no CUDA here
+    ostep = omodels.PitchClassifierStep(o, {n: p.double() for n, p in params.items()}, 1e-3, 0.9, True)
+    correct = seen = 0
+    for i, (w, lab) in enumerate(batches):
+        images = clf._images(w)
+        if i == 0:
+            clf._ensure_optimizer(images)
+            emu.load(params)
+        lr = hp["learning_rate"](clf.global_step)
+        want_total, want_ce, want_logits = ostep.update(images.double(), lab.double(), lr)
+        got_wd = clf.weight_decay_loss()
+        ce = clf.train_step(w, lab)
+        assert abs(float(ce) - want_ce) < 1e-4 * max(1.0, abs(want_ce))
+        assert abs(float(ce) + got_wd - want_total) < 1e-4 * max(1.0, abs(want_total))
+        correct += int((want_logits.argmax(1) == lab.argmax(1)).sum())
+        seen += 4
+        assert abs(clf.accuracy - correct / seen) < 1e-9
+        for n, v in emu.vars.items():
+            assert rel_err(v, ostep.params[n]) < 5e-4, (i, n, rel_err(v, ostep.params[n]))
+    assert int(clf.global_step.value) == 3

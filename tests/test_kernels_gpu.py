@@ -260,14 +260,42 @@ def test_group_norm(shape, groups, relu):
     """gs_group_norm_fwd (ops.py:118-146, + the relu that follows every use in networks.py) against the emulation."""
     x = _rand(*shape, seed=1) * 2.0 + 0.5
     gamma, beta = 1.0 + 0.3 * _rand(shape[-1], seed=2), 0.2 * _rand(shape[-1], seed=3)
-    got = _k().group_norm(x.cuda(), gamma.cuda(), beta.cuda(), groups, 1e-12, relu)
-    want = EMU.group_norm(x.double(), gamma.double(), beta.double(), groups, 1e-12, relu)
+    got, stats = _k().group_norm(x.cuda(), gamma.cuda(), beta.cuda(), groups, 1e-12, relu)
+    want, _ = EMU.group_norm(x.double(), gamma.double(), beta.double(), groups, 1e-12, relu)
     assert rel_err(got, want) < 1e-5
+    # gradients (training the classifier): dx, dgamma, dbeta
+    dy = _rand(*shape, seed=5)
+    dx, dg, db = _k().group_norm_bwd(x.cuda(), got, dy.cuda(), stats, gamma.cuda(), groups, 1e-12, relu)
+    ex, eg, eb = EMU.group_norm_bwd(x.double(), want, dy.double(), None, gamma.double(), groups, 1e-12, relu)
+    assert rel_err(dx, ex) < 2e-4 and rel_err(dg, eg) < 2e-4 and rel_err(db, eb) < 2e-4, (rel_err(dx, ex), rel_err(dg, eg), rel_err(db, eb))
 
 
 @pytest.mark.parametrize("shape,k,s", [((2, 16, 32, 64), 3, 2), ((1, 7, 9, 5), 3, 2), ((2, 8, 8, 16), 2, 2), ((1, 6, 10, 4), 3, 1)])
 def test_max_pool_and_spatial_mean(shape, k, s):
     """gs_max_pool2d (ops.py:308-316, TF SAME: padding never wins) is an index op: bit-exact; gs_spatial_mean."""
     x = _rand(*shape, seed=4)
-    assert torch.equal(_k().max_pool(x.cuda(), k, s).cpu(), EMU.max_pool(x, k, s))
+    y = _k().max_pool(x.cuda(), k, s)
+    assert torch.equal(y.cpu(), EMU.max_pool(x, k, s))
     assert rel_err(_k().spatial_mean(x.cuda()), EMU.spatial_mean(x.double())) < 1e-6
+    dy = _rand(*y.shape, seed=6)
+    assert rel_err(_k().max_pool_bwd(x.cuda(), y, dy.cuda(), k, s), EMU.max_pool_bwd(x.double(), None, dy.double(), k, s)) < 1e-6
+    # exact ties (a constant region, as the zero-padded head of a clip produces): the gradient goes to the FIRST maximum
+    xt = x.clone()
+    xt[:, : shape[1] // 2] = 0.25
+    yt = _k().max_pool(xt.cuda(), k, s)
+    assert rel_err(_k().max_pool_bwd(xt.cuda(), yt, dy.cuda(), k, s), EMU.max_pool_bwd(xt.double(), None, dy.double(), k, s)) < 1e-6
+    dm = _rand(shape[0], shape[3], seed=7)
+    assert rel_err(_k().spatial_mean_bwd(dm.cuda(), shape), EMU.spatial_mean_bwd(dm.double(), shape)) < 1e-6
+
+
+@pytest.mark.parametrize("nesterov", [False, True])
+def test_momentum_step(nesterov):
+    """gs_momentum_step: tf.train.MomentumOptimizer with the weight decay folded in, two steps."""
+    n = 10000
+    p, g, wd = _rand(n, seed=1), _rand(n, seed=2), (torch.arange(n) % 3 == 0).float() * 1e-2
+    pc, ac = p.clone().cuda(), torch.zeros(n).cuda()
+    pe, ae = p.clone().double(), torch.zeros(n, dtype=torch.float64)
+    for step in range(2):
+        _k().momentum_step(pc, (g * (step + 1)).cuda(), ac, wd.cuda(), 0.05, 0.9, nesterov, 0.5)
+        EMU.momentum_step(pe, (g * (step + 1)).double(), ae, wd.double(), 0.05, 0.9, nesterov, 0.5)
+    assert rel_err(pc, pe) < 1e-6 and rel_err(ac, ae) < 1e-6

@@ -467,3 +467,52 @@ def test_baseline_config1_trains_on_the_cuda_path_with_media_summaries(cuda_stor
     want, _ = ostep.discriminator_update(real_images, batches[0][1], lats[0], apply=False)
     first = [e.value for e in acc.Scalars("discriminator_loss")][0]
     assert abs(first - float(want)) < 1e-3 * max(1.0, abs(float(want))), (first, float(want))
+
+
+def test_pitch_classifier_training_parity(cuda_store):
+    """models.PitchClassifier (models.py:253-410) on the GPU -- generic spectral front-end ([32, 64] spectrogram), ResNet
+    forward and backward kernels, weight-decayed Nesterov momentum -- against the oracle restatement: three steps, loss 1e-3,
+    every variable 1e-3; then evaluate() returns the accuracy over an input."""
+    import gansynth_b200.models as pmodels
+    import gansynth_b200.networks as pnet
+    from oracle import spectral_ops as osp
+    cfg = dict(conv_param=dict(filters=8, kernel_size=[7, 7], strides=[2, 2]), pool_param=dict(kernel_size=[3, 3], strides=[2, 2]),
+               residual_params=[dict(filters=8, strides=[1, 1], blocks=2), dict(filters=16, strides=[2, 2], blocks=2)],
+               groups=4, classes=11)
+    o = onet.ResNet(**cfg)
+    params = o.init_variables(seed=5)
+    net = pnet.ResNet(**cfg)
+    spectral = dict(waveform_length=600, sample_rate=16000, spectrogram_shape=[32, 64], overlap=0.75)
+    g = torch.Generator().manual_seed(4)
+    batches = [(0.1 * torch.randn(4, 600, generator=g), torch.nn.functional.one_hot(torch.randint(0, 11, (4,), generator=g), 11).float())
+               for _ in range(3)]
+    hp = dict(weight_decay=1e-3, momentum=0.9, use_nesterov=True,
+              learning_rate=lambda step: pmodels.exponential_decay(0.05, step, 2, 0.5))
+    it = iter(batches)
+    clf = pmodels.PitchClassifier(net, lambda: next(it), spectral, hp)
+    ostep = omodels.PitchClassifierStep(o, {n: p.double() for n, p in params.items()}, 1e-3, 0.9, True)
+    cuda_images = clf._images                   # the CUDA front-end (generic kernels): used once, for the shapes
+    for i, (w, lab) in enumerate(batches):
+        images = torch.stack(osp.convert_to_spectrogram(w, **spectral), dim=1)
+        if i == 0:
+            assert tuple(cuda_images(w.cuda()).shape) == tuple(images.shape)
+            clf._ensure_optimizer(cuda_images(w.cuda()))
+            cuda_store.load(params)
+        # both sides see the ORACLE's images: an instantaneous frequency next to the +-pi branch cut may legitimately come
+        # out 2 apart (test_spectral_gpu compares it modulo 2), which a classifier input cannot tolerate
+        clf._images = lambda _w, _im=images: _im.cuda()
+        lr = hp["learning_rate"](clf.global_step)
+        want_total, want_ce, _ = ostep.update(images.double(), lab.double(), lr)
+        ce = clf.train_step(w, lab)
+        assert abs(float(ce) - want_ce) < TOL * max(1.0, abs(want_ce)), (float(ce), want_ce)
+        for n, v in cuda_store.vars.items():
+            assert rel_err(v, ostep.params[n]) < TOL, (i, n, rel_err(v, ostep.params[n]))
+    it2 = iter(batches)
+    clf.input_fn = lambda: next(it2)
+    clf._images = lambda wv: torch.stack(osp.convert_to_spectrogram(wv.cpu(), **spectral), dim=1).cuda()
+    clf.save_checkpoint("/tmp/gs_clf_ckpt")
+    acc = clf.evaluate("/tmp/gs_clf_ckpt")["accuracy"]
+    with torch.no_grad():
+        want = sum(int((o(ostep.params, torch.stack(osp.convert_to_spectrogram(w, **spectral), dim=1).double())[1].argmax(1)
+                        == lab.argmax(1)).sum()) for w, lab in batches) / 12.0
+    assert abs(acc - want) <= 1.0 / 12.0 + 1e-9      # (a borderline argmax may differ between the fp32 and the fp64 weights)
