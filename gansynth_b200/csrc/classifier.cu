@@ -1,7 +1,8 @@
-// Forward kernels of the ResNet pitch classifier that `GANSynth.evaluate` runs real and generated spectrograms through
-// (reference networks.py:293-413, ops.py:118-146 group_normalization, ops.py:308-316 max_pooling2d): NHWC fp32.
-// The 3x3 convolutions of the residual blocks run on the tensor-core kernels of conv.cu; these are the HBM-bound rest.
-// Inference only: the reference TRAINS this network with pitch_classifier_main.py, which is outside the hot path.
+// Kernels of the ResNet pitch classifier that `GANSynth.evaluate` runs real and generated spectrograms through
+// (reference networks.py:293-413, ops.py:118-146 group_normalization, ops.py:308-316 max_pooling2d) and that
+// models.PitchClassifier trains (models.py:253-410): NHWC fp32, forward and first-order gradients, plus the Momentum
+// optimiser step.  The 3x3 convolutions of the residual blocks run on the tensor-core kernels of conv.cu; these are the
+// HBM-bound rest -- plain kernels: the classifier is an evaluation network, off the benchmarked path.
 #include "common.cuh"
 #include "gansynth_b200.h"
 

@@ -700,7 +700,7 @@ class GANSynth(object):
         the whole input.  The reference splices a frozen TF GraphDef of its pitch classifier (`classifier`) onto
         `real_images` / `fake_images`; a GraphDef cannot be executed without TensorFlow, so `classifier` is one of
           * a callable images [B, 2, H, W] (CUDA) -> (features [B, F], logits [B, C]) -- e.g. a `networks.ResNet`, which
-            is that classifier on this repo's kernels (forward only);
+            is that classifier on this repo's kernels;
           * the path of a CHECKPOINT of the reference's classifier (a TF-1 Saver prefix / model_dir written by
             pitch_classifier_main.py, or a `.pt` dict of name -> array): `networks.ResNet.pitch_classifier()` is built
             and the variables are loaded by their TF names."""

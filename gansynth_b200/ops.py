@@ -311,7 +311,7 @@ def tanh(inputs):
     return F.Tanh.apply(inputs)
 
 
-# ----------------------------------------------------------------------------- pitch classifier ops (forward only)
+# ----------------------------------------------------------------------------- pitch classifier ops
 def group_normalization(inputs, groups, epsilon=1.0e-12, relu=False):
     """ops.py:118-146 (NHWC): variables `beta` (zeros) and `gamma` (ones) of shape [C]; `relu` (extension) fuses the
     tf.nn.relu that follows every use in networks.py:318-322, 345-349, 391-396."""

@@ -140,4 +140,4 @@ class PitchClassifierStep(object):
                 self.accum[n].mul_(self.momentum).add_(g)
                 step = g + self.momentum * self.accum[n] if self.use_nesterov else self.accum[n]
                 self.params[n].sub_(lr * step)
-        return float(total), float(ce), logits.detach()
+        return float(total.detach()), float(ce.detach()), logits.detach()
