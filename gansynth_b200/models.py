@@ -509,10 +509,19 @@ class GANSynth(object):
         """Implicit restore of SingularMonitoredSession(checkpoint_dir=model_dir) (models.py:120)."""
         paths = sorted(glob.glob(os.path.join(model_dir, "model.ckpt-*.pt")),
                        key=lambda p: int(p.rsplit("-", 1)[1][:-3]))
-        if not paths:
-            # a model_dir written by the reference itself: TensorFlow Saver files + `checkpoint` state file
-            if os.path.exists(os.path.join(model_dir, "checkpoint")):
+        # a model_dir written by the reference itself (TensorFlow Saver files + `checkpoint` state file): used when there
+        # is no .pt file, or when the TF checkpoint is NEWER than the newest .pt (step parsed from `...ckpt-<step>`)
+        if os.path.exists(os.path.join(model_dir, "checkpoint")):
+            from . import tf_checkpoint as tfc
+            prefix = tfc.latest_checkpoint(model_dir)
+            tf_step = -1
+            if prefix is not None and os.path.exists(prefix + ".index"):
+                tail = prefix.rsplit("-", 1)[-1]
+                tf_step = int(tail) if tail.isdigit() else 0
+            pt_step = int(paths[-1].rsplit("-", 1)[1][:-3]) if paths else -1
+            if tf_step > pt_step:
                 return self.import_tf_checkpoint(model_dir, labels, latents)
+        if not paths:
             return None
         state = None
         while paths:

@@ -222,9 +222,23 @@ def save_bundle(prefix, tensors):
             items.append((name.encode("utf-8"), _entry_proto(arr, offset, _masked_crc(raw))))
             offset += len(raw)
     write_table(prefix + ".index", items)
+    # CheckpointState text proto, as tf.train.Saver maintains it: the new prefix becomes model_checkpoint_path and is
+    # appended to the all_model_checkpoint_paths already listed (an existing state file is extended, not overwritten)
     base = os.path.basename(prefix)
-    with open(os.path.join(os.path.dirname(os.path.abspath(prefix)), "checkpoint"), "w") as f:
-        f.write('model_checkpoint_path: "%s"\nall_model_checkpoint_paths: "%s"\n' % (base, base))
+    state_path = os.path.join(os.path.dirname(os.path.abspath(prefix)), "checkpoint")
+    older = []
+    if os.path.exists(state_path):
+        for line in open(state_path):
+            if line.startswith("all_model_checkpoint_paths:"):
+                name = line.split(":", 1)[1].strip().strip('"')
+                if name != base and name not in older:
+                    older.append(name)
+    tmp = state_path + ".tmp"
+    with open(tmp, "w") as f:
+        f.write('model_checkpoint_path: "%s"\n' % base)
+        for name in older + [base]:
+            f.write('all_model_checkpoint_paths: "%s"\n' % name)
+    os.replace(tmp, state_path)
 
 
 def load_bundle(prefix, verify=True):

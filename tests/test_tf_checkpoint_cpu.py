@@ -121,3 +121,17 @@ def test_model_export_then_import_into_a_fresh_model(emu, tmp_path):
     assert int(model2.global_step.value) == 17 and set(store2.vars) == set(want)
     for n, v in store2.state().items():
         assert torch.equal(v, want[n]), n
+
+
+def test_checkpoint_state_file_keeps_older_paths(tmp_path):
+    """save_bundle extends `<dir>/checkpoint` the way tf.train.Saver does: model_checkpoint_path is the newest prefix,
+    all_model_checkpoint_paths lists every prefix written so far (an existing state file is not clobbered)."""
+    import numpy as np
+    from gansynth_b200 import tf_checkpoint as tfc
+    for step in (1000, 2000, 3000):
+        tfc.save_bundle(str(tmp_path / ("model.ckpt-%d" % step)), {"v": np.full((2,), step, np.float32)})
+    lines = open(tmp_path / "checkpoint").read().splitlines()
+    assert lines[0] == 'model_checkpoint_path: "model.ckpt-3000"'
+    assert lines[1:] == ['all_model_checkpoint_paths: "model.ckpt-%d"' % s for s in (1000, 2000, 3000)]
+    assert tfc.latest_checkpoint(str(tmp_path)).endswith("model.ckpt-3000")
+    assert float(tfc.load_bundle(tfc.latest_checkpoint(str(tmp_path)))["v"][0]) == 3000.0
