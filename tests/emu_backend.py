@@ -146,6 +146,11 @@ class EmuBackend(object):
         hw = shape[1] * shape[2]
         return (dy / hw).view(shape[0], 1, 1, shape[3]).expand(*shape).contiguous()
 
+    def adam_slice(self, n, rank, world):
+        quads = n // 4
+        per = -(-quads // world)
+        return 4 * min(per * rank, quads), 4 * min(per * (rank + 1), quads)
+
     def momentum_step(self, p, g, accum, wd, lr, momentum, nesterov, grad_scale=1.0):
         with torch.no_grad():
             gi = g * grad_scale + (wd * p if wd is not None else 0.0)

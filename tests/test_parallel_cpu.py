@@ -97,3 +97,51 @@ def test_two_rank_step_equals_averaged_single_process(tmp_path):
     ops.set_default_store(None)
     from gansynth_b200.kernels import CudaBackend
     F.set_backend(CudaBackend())
+
+
+def _sync_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    model, store, latents, labels, images = _build(100)
+    model._ensure_optimizers(labels, latents)
+    import gansynth_b200.functional as F
+    from gansynth_b200.kernels import CudaBackend
+    slices = {}
+    for scope, st in model._opt.items():
+        n = st["flat"].numel()
+        lo, hi = CudaBackend().adam_slice(n, rank, world)            # host arithmetic of the C ABI (gs_adam_slice)
+        slices[scope] = (lo, hi)
+        # what the fused update leaves behind: only this rank's slice of the Adam slots is live, the rest is stale
+        ref = torch.arange(n, dtype=torch.float32)
+        for key, k in (("m", 1.0), ("v", 2.0)):
+            st[key].fill_(-7.0)
+            st[key][lo:hi] = k * ref[lo:hi]
+        st["fused"] = dict(rank=rank, world=world, synced=False)
+    try:
+        model._checkpoint_state()
+        guarded = False
+    except RuntimeError:
+        guarded = True
+    model._sync_optimizer_state()
+    ok = guarded
+    for scope, st in model._opt.items():
+        ref = torch.arange(st["flat"].numel(), dtype=torch.float32)
+        ok &= torch.equal(st["m"], ref) and torch.equal(st["v"], 2.0 * ref) and st["fused"]["synced"]
+    model._checkpoint_state()                                        # allowed again
+    torch.save(dict(ok=ok, slices=slices), os.path.join(out_dir, "sync%d.pt" % rank))
+    torch.distributed.destroy_process_group()
+
+
+def test_sharded_adam_slots_are_gathered_before_a_checkpoint(tmp_path):
+    """The fused all-reduce + Adam kernel leaves every rank with only its slice of m / v (models._update);
+    `_sync_optimizer_state` (collective) rebuilds the full slots on every rank, and `_checkpoint_state` refuses to run
+    before it.  World size 2 over gloo; the slices are those of gs_adam_slice."""
+    world, port = 2, 29500 + (os.getpid() + 7) % 500
+    mp.spawn(_sync_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    outs = [torch.load(os.path.join(tmp_path, "sync%d.pt" % r)) for r in range(world)]
+    assert all(o["ok"] for o in outs)
+    for scope in outs[0]["slices"]:
+        (a0, b0), (a1, b1) = outs[0]["slices"][scope], outs[1]["slices"][scope]
+        assert a0 == 0 and b0 == a1 and b0 % 4 == 0 and b1 > a1
