@@ -363,24 +363,46 @@ def spectral_secondary(device, pk):
                 algorithmic_bytes_per_clip=1304576)
 
 
-def inference_secondary(model, device):
-    """BASELINE config 5 at B = 8: labels + latents -> generator -> inverse spectral -> waveforms (models.py:232-250)."""
-    g = torch.Generator().manual_seed(2)
-    lab = torch.nn.functional.one_hot(torch.arange(BATCH) % 61, 61).float().to(device)
-    z = torch.randn(BATCH, 256, generator=g).to(device)
-    for _ in range(3):
-        out = model.generate_batch(lab, z)
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 10
-    torch.cuda.synchronize()
-    s.record()
-    for _ in range(reps):
-        out = model.generate_batch(lab, z)
-    e.record()
-    torch.cuda.synchronize()
-    ms = s.elapsed_time(e) / reps
-    return dict(workload="generate_batch at B=8 (CUDA-graph replay): G forward + convert_to_waveform -> [8, 64000]",
-                ms_per_batch=ms, clips_per_s=BATCH / ms * 1e3, output_shape=list(out.shape))
+def inference_secondary(model, device, pk):
+    """BASELINE config 5: labels + latents -> generator -> inverse spectral -> waveforms (models.py:232-250) at B = 8 and
+    B = 64, with the roofline of the path: F_G = 14.9 GFLOP of convolution / dense work per clip against the sustained bf16
+    peak (bf16x3 issues three MMA passes per algorithmic FLOP: 0.33 is a saturated pipe) and the bytes a clip must move
+    at least (its 1 304 576-byte spectrogram -> waveform transform plus the fp32 activations of the generator's top two
+    resolutions written once and read once) against the copy bandwidth."""
+    def timed(batch):
+        g = torch.Generator().manual_seed(2)
+        lab = torch.nn.functional.one_hot(torch.arange(batch) % 61, 61).float().to(device)
+        z = torch.randn(batch, 256, generator=g).to(device)
+        for _ in range(3):
+            out = model.generate_batch(lab, z)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        torch.cuda.synchronize()
+        s.record()
+        for _ in range(reps):
+            out = model.generate_batch(lab, z)
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / reps, out
+    ms, out = timed(BATCH)
+    res = dict(workload="generate_batch at B=8 (CUDA-graph replay): G forward + convert_to_waveform -> [8, 64000]",
+               ms_per_batch=ms, clips_per_s=BATCH / ms * 1e3, output_shape=list(out.shape))
+    try:
+        ms64, _ = timed(64)
+    except Exception as exc:                     # the B = 8 line above stands on its own
+        res["roofline"] = dict(error="%s: %s" % (type(exc).__name__, exc))
+        return res
+    clips64 = 64 / ms64 * 1e3
+    # per clip: top two resolutions (128x1024x32 and 64x512x64 fp32, two layers each, written + read) + the inverse transform
+    act_bytes = 2 * 2 * 4.0 * (128 * 1024 * 32 + 64 * 512 * 64) + 1304576.0
+    res["roofline"] = dict(batch=64, ms_per_batch=ms64, clips_per_s=clips64, flop_per_clip=F_G,
+                           tflops=F_G * clips64 / 1e12, tensor_frac=F_G * clips64 / 1e12 / pk["tf_sustained"],
+                           min_bytes_per_clip=act_bytes, hbm_gbs_at_min_bytes=act_bytes * clips64 / 1e9,
+                           hbm_frac_at_min_bytes=act_bytes * clips64 / 1e9 / pk["hbm"],
+                           bound="hbm" if F_G / act_bytes < pk["tf_sustained"] * 1e12 / (pk["hbm"] * 1e9) else "tensor",
+                           note="B = 8 is launch / latency bound (about 60 kernels in under a millisecond); batches above 64 run as "
+                                "64-clip chunks, so B = 64 is the saturated rate of config 5")
+    return res
 
 
 def oracle_iteration_time(batch, iters, threads=None):
@@ -620,7 +642,7 @@ def bench_ours(args):
                     r["mbytes_per_step"], r["flop_per_byte"], r["bound"], r["tflops"], r["gbs"], r["frac"]))
     if world == 1 and not args.no_spectral:
         line["secondary"] = spectral_secondary(device, pk)
-        line["secondary"]["inference"] = inference_secondary(model, device)
+        line["secondary"]["inference"] = inference_secondary(model, device, pk)
         if rank == 0 and not args.no_cpu_baseline:
             line["secondary"]["cpu_baseline"] = oracle_secondary_times(os.cpu_count())
     print(json.dumps(line), flush=True)
