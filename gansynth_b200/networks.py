@@ -288,9 +288,9 @@ class PGGAN(object):
 class ResNet(object):
     """The pitch classifier `GANSynth.evaluate` takes its features from (reference networks.py:293-413: pre-activation
     ResNet v2 blocks without bottleneck, group normalisation, weight-standardised convolutions; constructor arguments as
-    in pitch_classifier_main.py:42-53).  FORWARD ONLY: `__call__(images NCHW [B, 2, H, W]) -> (features [B, F],
-    logits [B, classes])` under torch.no_grad(); training it (models.PitchClassifier of the reference) is outside the hot
-    path.  Variables carry the reference's names (`resnet/conv/weight`, `resnet/residual_block_0_0/conv_1st/weight`,
+    in pitch_classifier_main.py:42-53).  `__call__(images NCHW [B, 2, H, W]) -> (features [B, F], logits [B, classes])`;
+    differentiable (every layer is an autograd Function over the CUDA kernels), trained by `models.PitchClassifier`.
+    Variables carry the reference's names (`resnet/conv/weight`, `resnet/residual_block_0_0/conv_1st/weight`,
     `.../group_normalization_1st/gamma`, `resnet/logits/weight` ...), so a checkpoint of the reference's classifier
     loads by name (GANSynth.import_tf_checkpoint / VariableStore.load)."""
 

@@ -1,0 +1,306 @@
+"""Golden vectors produced by the reference's OWN Python, run here.
+
+TensorFlow 1.13 cannot be installed in this image, but skmhrk1209/GANSynth is a composition of TensorFlow primitives.
+This script puts `oracle/tf1_eager/` (an eager PyTorch-CPU restatement of exactly those primitives) and `/root/reference`
+on sys.path and imports the reference's unmodified `networks.py`, `spectral_ops.py` and `models.py`: its scopes, variable
+names and shapes, weight scaling, block order, tf.cond growth logic, loss terms, tf.gradients penalties and optimizer calls
+execute as written.  What they compute goes into `tests/golden/reference_*.npz` / `.json` (float64 unless said otherwise,
+a few hundred kB in all); `tests/test_reference_pin_cpu.py` holds the oracle to these files on any box and, where
+`/root/reference` exists, re-runs this script's cases and checks that the committed files still say what the reference says.
+
+    python tests/golden/make_reference_vectors.py            # rewrites the fixtures (needs /root/reference)
+
+One construction of the reference's GANSynth / PitchClassifier object == one session.run of its graph (see the stand-in's
+header), so the training sequence `session.run(discriminator_train_op); session.run(generator_train_op)`
+(models.py:189-192) is: construct, run the D op; construct again on the next batch, run the G op.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REFERENCE = "/root/reference"
+
+# the fixture configurations: three doublings of a non-square 2x4 seed, like the reference's 2x16 -> 128x1024 in small
+TINY = dict(min_resolution=[2, 4], max_resolution=[16, 32], min_channels=4, max_channels=16)
+TINY_SPECTRAL = dict(waveform_length=300, sample_rate=16000, spectrogram_shape=[16, 32], overlap=0.75)
+FULL_SPECTRAL = dict(waveform_length=64000, sample_rate=16000, spectrogram_shape=[128, 1024], overlap=0.75)
+LATENT, LABELS, BATCH = 8, 5, 4
+HYPER = dict(generator_learning_rate=8e-4, generator_beta1=0.0, generator_beta2=0.99,
+             discriminator_learning_rate=8e-4, discriminator_beta1=0.0, discriminator_beta2=0.99,
+             mode_seeking_loss_weight=0.1, real_gradient_penalty_weight=5.0, fake_gradient_penalty_weight=0.0)
+TINY_RESNET = dict(conv_param=dict(filters=8, kernel_size=[7, 7], strides=[2, 2]),
+                   pool_param=dict(kernel_size=[3, 3], strides=[2, 2]),
+                   residual_params=[dict(filters=8, strides=[1, 1], blocks=2), dict(filters=16, strides=[2, 2], blocks=2)],
+                   groups=4, classes=LABELS)
+CLASSIFIER_HYPER = dict(weight_decay=1e-4, momentum=0.9, use_nesterov=True, base_learning_rate=0.05, decay_steps=3.0,
+                        decay_rate=0.1)
+GROWING_STEPS = 7                       # levels 0, 1/7, 2/7 over the three recorded iterations
+LEVELS = [0.0, 0.01, 0.3, 0.62, 1.0]    # forward-only cases: every tf.cond arm of networks.py:125-152 / 260-287
+
+
+def reference_modules():
+    """(tf stand-in, reference networks, spectral_ops, models, utils.Dict), imported from /root/reference."""
+    for p in (REFERENCE, os.path.join(ROOT, "oracle", "tf1_eager")):
+        if p in sys.path:
+            sys.path.remove(p)
+        sys.path.insert(0, p)
+    shadowed = {n: sys.modules.pop(n) for n in ("tensorflow", "tensorflow_probability", "tensorflow_hub", "networks", "ops",
+                                                "spectral_ops", "models", "metrics", "utils") if n in sys.modules}
+    try:
+        import tensorflow as tf
+        import networks
+        import spectral_ops
+        import models
+        from utils import Dict
+        for m in (networks, spectral_ops, models):
+            assert os.path.dirname(os.path.abspath(m.__file__)) == REFERENCE, m.__file__
+        return tf, networks, spectral_ops, models, Dict
+    finally:
+        for n in ("tensorflow", "tensorflow_probability", "tensorflow_hub", "networks", "ops", "spectral_ops", "models",
+                  "metrics", "utils"):
+            sys.modules.pop(n, None)
+        sys.modules.update(shadowed)
+        for p in (REFERENCE, os.path.join(ROOT, "oracle", "tf1_eager")):
+            sys.path.remove(p)
+
+
+def _np(t):
+    return t.detach().cpu().numpy().copy()
+
+
+def _values(tf, trainable_only=True):
+    return {n: _np(v.t) for n, v in tf.variables().items() if v.trainable or not trainable_only}
+
+
+def _perturb_biases(tf, seed):
+    """The reference starts biases / beta at 0 and gamma at 1; the fixtures move them so that they matter."""
+    gen = torch.Generator().manual_seed(seed)
+    for name, var in tf.variables().items():
+        if name.endswith(("/bias", "/beta")):
+            var.assign(0.1 * torch.randn(var.t.shape, generator=gen, dtype=torch.float64).to(var.t.dtype))
+        elif name.endswith("/gamma"):
+            var.assign(1.0 + 0.2 * torch.randn(var.t.shape, generator=gen, dtype=torch.float64).to(var.t.dtype))
+
+
+def _inputs(gen, waveform_length, dtype):
+    waves = (0.3 * torch.randn(BATCH, waveform_length, generator=gen, dtype=torch.float64)).to(dtype)
+    labels = torch.nn.functional.one_hot(torch.randint(0, LABELS, (BATCH,), generator=gen), LABELS).to(dtype)
+    return waves, labels
+
+
+# ------------------------------------------------------------------------------------------------ cases
+def pggan_forward(dtype=torch.float64):
+    """networks.py PGGAN.generator / .discriminator at every growth regime."""
+    tf, networks, _, _, _ = reference_modules()
+    tf.reset_default_graph()
+    tf.set_float_dtype(dtype)
+    tf.set_random_seed(0)
+    gen = torch.Generator().manual_seed(11)
+    latents = torch.randn(BATCH, LATENT, generator=gen, dtype=torch.float64).to(dtype)
+    labels = torch.nn.functional.one_hot(torch.tensor([0, 3, 1, 3]), LABELS).to(dtype)
+    images = (0.5 * torch.randn(BATCH, 2, *TINY["max_resolution"], generator=gen, dtype=torch.float64)).to(dtype)
+    out = dict(latents=_np(latents), labels=_np(labels), images=_np(images), levels=np.asarray(LEVELS))
+    level = tf.Tensor(torch.tensor(0.5, dtype=dtype))
+    pggan = networks.PGGAN(growing_level=level, **TINY)
+    tf.build_all_branches(True)                               # graph construction: every variable of every branch
+    pggan.generator(tf.Tensor(latents), tf.Tensor(labels))
+    pggan.discriminator(tf.Tensor(images), tf.Tensor(labels))
+    tf.build_all_branches(False)
+    _perturb_biases(tf, 12)
+    for name, value in _values(tf).items():
+        out["var:" + name] = value
+    for k, lv in enumerate(LEVELS):
+        level.t = torch.tensor(lv, dtype=dtype)
+        pggan = networks.PGGAN(growing_level=level, **TINY)   # growing_depth is computed in the constructor (networks.py:29)
+        fake = pggan.generator(tf.Tensor(latents), tf.Tensor(labels))
+        features, logits = pggan.discriminator(tf.Tensor(images), tf.Tensor(labels))
+        out["growing_depth_%d" % k] = _np(pggan.growing_depth.t)
+        out["fake_images_%d" % k] = _np(fake.t)
+        out["features_%d" % k] = _np(features.t)
+        out["logits_%d" % k] = _np(logits.t)
+    return out
+
+
+def variable_tables():
+    """Name -> shape of every variable the reference's two command lines create (gan_synth_main.py:43-54,
+    pitch_classifier_main.py:42-53), from building the graphs at full size with all tf.cond branches traced."""
+    tf, networks, _, _, D = reference_modules()
+    tables = {}
+    tf.reset_default_graph()
+    tf.set_float_dtype(torch.float32)
+    tf.build_all_branches(True)
+    with torch.no_grad():
+        pggan = networks.PGGAN(min_resolution=[2, 16], max_resolution=[128, 1024], min_channels=32, max_channels=256,
+                               growing_level=tf.Tensor(torch.tensor(0.5)))
+        labels = tf.Tensor(torch.nn.functional.one_hot(torch.tensor([0, 1, 2, 3]), 61).float())
+        pggan.generator(tf.Tensor(torch.zeros(4, 256)), labels)
+        pggan.discriminator(tf.Tensor(torch.zeros(4, 2, 128, 1024)), labels)
+        tables["gan_synth"] = {n: list(v.t.shape) for n, v in tf.variables().items()}
+        tf.reset_default_graph()
+        resnet = networks.ResNet(conv_param=D(filters=64, kernel_size=[7, 7], strides=[2, 2]),
+                                 pool_param=D(kernel_size=[3, 3], strides=[2, 2]),
+                                 residual_params=[D(filters=64, strides=[1, 1], blocks=3), D(filters=128, strides=[2, 2], blocks=4),
+                                                  D(filters=256, strides=[2, 2], blocks=6), D(filters=512, strides=[2, 2], blocks=3)],
+                                 groups=32, classes=61)
+        resnet(tf.Tensor(torch.zeros(1, 2, 64, 128)))
+        tables["pitch_classifier"] = {n: list(v.t.shape) for n, v in tf.variables().items()}
+    tf.build_all_branches(False)
+    return tables
+
+
+def spectral(dtype=torch.float64):
+    """spectral_ops.convert_to_spectrogram / convert_to_waveform at the reference's own size (sub-sampled) and at the
+    fixture size (whole)."""
+    import math
+    tf, _, spectral_ops, _, _ = reference_modules()
+    tf.set_float_dtype(dtype)
+    t = torch.arange(64000, dtype=torch.float64) / 16000.0
+    gen = torch.Generator().manual_seed(0)
+    wave = torch.stack([0.3 * torch.sin(2 * math.pi * 440.0 * t) * torch.exp(-3 * t)
+                        + 0.01 * torch.randn(64000, generator=gen, dtype=torch.float64),
+                        0.1 * torch.randn(64000, generator=gen, dtype=torch.float64)]).float().to(dtype)
+    logmel, inst = spectral_ops.convert_to_spectrogram(tf.Tensor(wave), **FULL_SPECTRAL)
+    back = spectral_ops.convert_to_waveform(logmel, inst, **FULL_SPECTRAL)
+    out = dict(full_wave=_np(wave).astype(np.float32), full_logmel_sub=_np(logmel.t)[:, ::8, ::16],
+               full_inst_sub=_np(inst.t)[:, ::8, ::16], full_back_sub=_np(back.t)[:, ::32])
+    small, _ = _inputs(torch.Generator().manual_seed(21), TINY_SPECTRAL["waveform_length"], dtype)
+    logmel, inst = spectral_ops.convert_to_spectrogram(tf.Tensor(small), **TINY_SPECTRAL)
+    back = spectral_ops.convert_to_waveform(logmel, inst, **TINY_SPECTRAL)
+    out.update(tiny_wave=_np(small), tiny_logmel=_np(logmel.t), tiny_inst=_np(inst.t), tiny_back=_np(back.t))
+    return out
+
+
+def gan_step(fake_penalty=0.0, iterations=3, dtype=torch.float64):
+    """models.py GANSynth under gan_synth_main.py's growth schedule (level = global_step / growing_steps) for
+    `iterations` x (D run, G run): inputs, both losses and the applied gradients of every run, variables after it."""
+    tf, networks, _, models, Dict = reference_modules()
+    tf.reset_default_graph()
+    tf.set_float_dtype(dtype)
+    tf.set_random_seed(0)
+    hyper = dict(HYPER, fake_gradient_penalty_weight=fake_penalty)
+    gen = torch.Generator().manual_seed(31 + int(fake_penalty * 10))
+    feed = {}
+
+    def real_input_fn():
+        waves, labels = _inputs(gen, TINY_SPECTRAL["waveform_length"], dtype)
+        feed["waveforms"], feed["labels"] = waves, labels
+        return tf.Tensor(waves.clone().requires_grad_(True)), tf.Tensor(labels)   # tf.gradients reaches real_images
+
+    def fake_input_fn():
+        z = tf.random.normal([BATCH, LATENT])
+        feed["latents"] = z.t.detach()
+        return z
+
+    def construct():
+        pggan = networks.PGGAN(growing_level=tf.cast(tf.divide(x=tf.train.get_or_create_global_step(), y=GROWING_STEPS),
+                                                     tf.float32), **TINY)       # gan_synth_main.py:48-53
+        return models.GANSynth(generator=pggan.generator, discriminator=pggan.discriminator, real_input_fn=real_input_fn,
+                               fake_input_fn=fake_input_fn, spectral_params=Dict(TINY_SPECTRAL), hyper_params=Dict(hyper))
+
+    tf.build_all_branches(True)
+    construct()                                               # graph construction; its draw of inputs is discarded
+    tf.build_all_branches(False)
+    _perturb_biases(tf, 32)
+    out = dict(fake_penalty=np.asarray(fake_penalty), iterations=np.asarray(iterations))
+    for name, value in _values(tf).items():
+        out["var0:" + name] = value
+    run = 0
+    for _ in range(iterations):
+        for which in ("discriminator", "generator"):
+            model = construct()
+            op = getattr(model, which + "_train_op")
+            tag = "run%d:" % run
+            out[tag + "which"] = np.asarray(which)
+            out[tag + "global_step"] = _np(tf.train.get_or_create_global_step().t)
+            for k in ("waveforms", "labels", "latents"):
+                out[tag + k] = _np(feed[k])
+            out[tag + "real_images"] = _np(model.real_images.t)
+            out[tag + "fake_images"] = _np(model.fake_images.t)
+            out[tag + "fake_waveforms"] = _np(model.fake_waveforms.t)
+            out[tag + "generator_loss"] = _np(model.generator_loss.t)
+            out[tag + "discriminator_loss"] = _np(model.discriminator_loss.t)
+            for grad, var in op.grads_and_vars:
+                out[tag + "grad:" + var.op.name] = np.zeros(var.t.shape) if grad is None else _np(grad)
+            op.run()
+            for name, value in _values(tf).items():
+                if name.startswith(which):
+                    out[tag + "var:" + name] = value
+            run += 1
+    out["final_global_step"] = _np(tf.train.get_or_create_global_step().t)
+    return out
+
+
+def classifier_step(iterations=2, dtype=torch.float64):
+    """networks.py ResNet + models.py PitchClassifier: loss (cross entropy + L2), Nesterov momentum under an
+    exponentially decaying learning rate, `iterations` train-op runs."""
+    tf, networks, _, models, Dict = reference_modules()
+    tf.reset_default_graph()
+    tf.set_float_dtype(dtype)
+    tf.set_random_seed(0)
+    gen = torch.Generator().manual_seed(41)
+    feed = {}
+
+    def input_fn():
+        waves, labels = _inputs(gen, TINY_SPECTRAL["waveform_length"], dtype)
+        feed["waveforms"], feed["labels"] = waves, labels
+        return tf.Tensor(waves), tf.Tensor(labels)
+
+    resnet = networks.ResNet(conv_param=Dict(TINY_RESNET["conv_param"]), pool_param=Dict(TINY_RESNET["pool_param"]),
+                             residual_params=[Dict(p) for p in TINY_RESNET["residual_params"]],
+                             groups=TINY_RESNET["groups"], classes=TINY_RESNET["classes"])
+    h = CLASSIFIER_HYPER
+    hyper = Dict(weight_decay=h["weight_decay"], momentum=h["momentum"], use_nesterov=h["use_nesterov"],
+                 learning_rate=lambda global_step: tf.train.exponential_decay(                   # pitch_classifier_main.py:69-74
+                     learning_rate=h["base_learning_rate"], global_step=global_step, decay_steps=h["decay_steps"],
+                     decay_rate=h["decay_rate"]))
+
+    def construct():
+        return models.PitchClassifier(network=resnet, input_fn=input_fn, spectral_params=Dict(TINY_SPECTRAL), hyper_params=hyper)
+
+    construct()                                               # graph construction
+    tf.local_variables_initializer()                          # the Scaffold's local_init_op (models.py:311-316)
+    _perturb_biases(tf, 42)
+    out = dict(iterations=np.asarray(iterations))
+    for name, value in _values(tf).items():
+        out["var0:" + name] = value
+    for run in range(iterations):
+        model = construct()
+        tag = "run%d:" % run
+        out[tag + "waveforms"], out[tag + "labels"] = _np(feed["waveforms"]), _np(feed["labels"])
+        out[tag + "loss"] = _np(model.loss.t)
+        out[tag + "accuracy"] = _np(model.update_op.t)       # what evaluate() returns (models.py:405-407): running
+        for grad, var in model.train_op.grads_and_vars:
+            out[tag + "grad:" + var.op.name] = _np(grad)
+        model.train_op.run()
+        for name, value in _values(tf).items():
+            out[tag + "var:" + name] = value
+    # the inference head the reference exports: features / logits of given images (models.py:300-304)
+    images = 0.5 * torch.randn(BATCH, 2, *TINY_SPECTRAL["spectrogram_shape"], generator=gen, dtype=torch.float64).to(dtype)
+    features, logits = resnet(tf.Tensor(images))
+    out.update(images=_np(images), features=_np(features.t), logits=_np(logits.t))
+    return out
+
+
+CASES = dict(reference_pggan=pggan_forward, reference_spectral=spectral, reference_step=gan_step,
+             reference_step_fake_penalty=lambda: gan_step(fake_penalty=2.0, iterations=1),
+             reference_classifier=classifier_step)
+
+
+def main():
+    for name, fn in CASES.items():
+        arrays = fn()
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **arrays)
+        print("%-32s %4d arrays %8.1f kB" % (name, len(arrays), os.path.getsize(path) / 1e3))
+    with open(os.path.join(HERE, "reference_variables.json"), "w") as f:
+        json.dump(variable_tables(), f, indent=0, sort_keys=False)
+    print("reference_variables.json written")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,169 @@
+"""The product (its real kernels on a GPU, or its host logic over tests/emu_backend.py on CPU) against the vectors the
+reference's own code produced (tests/golden/reference_*.npz, see tests/golden/make_reference_vectors.py): fp32 results
+against float64 reference values, 1e-3 relative (north_star's tolerance)."""
+import importlib.util
+import os
+
+import numpy as np
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+_spec = importlib.util.spec_from_file_location("make_reference_vectors", os.path.join(GOLDEN, "make_reference_vectors.py"))
+gen = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(gen)
+
+TOL = 1e-3
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def variables(z, prefix):
+    return {k[len(prefix):]: torch.from_numpy(z[k]).float() for k in z.files if k.startswith(prefix)}
+
+
+def rel(got, want):
+    got = got.detach().double().cpu().numpy()
+    want = np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    return float(np.abs(got - want).max() / (np.abs(want).max() + 1e-30))
+
+
+def product_pggan(store, level, device):
+    import gansynth_b200.networks as pnet
+    pg = pnet.PGGAN(growing_level=level, **gen.TINY)
+    pg._ensure_variables("generator", gen.LATENT, gen.LABELS)
+    pg._ensure_variables("discriminator", 0, gen.LABELS)
+    return pg
+
+
+def check_forward(store, device):
+    """networks.py generator / discriminator at the five growth levels of the fixture."""
+    z = load("reference_pggan")
+    dev = lambda k: torch.from_numpy(z[k]).float().to(device)
+    for k, level in enumerate(z["levels"]):
+        pg = product_pggan(store, float(level), device)
+        store.load(variables(z, "var:"))
+        with torch.no_grad():
+            fake = pg.generator(dev("latents"), dev("labels"))
+            features, logits = pg.discriminator(dev("images"), dev("labels"))
+        assert rel(fake, z["fake_images_%d" % k]) < TOL, (level, rel(fake, z["fake_images_%d" % k]))
+        assert rel(features, z["features_%d" % k]) < TOL and rel(logits, z["logits_%d" % k]) < TOL, level
+
+
+def check_spectral(device):
+    """spectral_ops.py both ways at the fixture size (generic kernels) and the reference's own size (fast kernels)."""
+    import gansynth_b200.spectral_ops as psp
+    z = load("reference_spectral")
+    for tag, params, sub in (("tiny", gen.TINY_SPECTRAL, None), ("full", gen.FULL_SPECTRAL, (8, 16, 32))):
+        wave = torch.from_numpy(z[tag + "_wave"]).float().to(device)
+        logmel, inst = psp.convert_to_spectrogram(wave, **params)
+        want_lm, want_if = (z["tiny_logmel"], z["tiny_inst"]) if sub is None else (z["full_logmel_sub"], z["full_inst_sub"])
+        got_lm, got_if = (logmel, inst) if sub is None else (logmel[:, ::sub[0], ::sub[1]], inst[:, ::sub[0], ::sub[1]])
+        assert rel(got_lm, want_lm) < TOL, (tag, rel(got_lm, want_lm))
+        # instantaneous frequency: a phase difference within rounding of +-pi may unwrap to the other side (2.0 apart,
+        # spectral_ops.py:23-25); everywhere else 1e-3 of the +-1 range.  Silent, rounding-dominated bins are the only
+        # place that happens: at most 0.5 % of them.
+        d = np.abs(got_if.detach().double().cpu().numpy() - want_if)
+        wrapped = np.abs(d - 2.0) < 2e-3
+        assert float(wrapped.mean()) < 5e-3 and float(d[~wrapped].max()) < 2e-3, (tag, float(wrapped.mean()), float(d[~wrapped].max()))
+        # the inverse from the REFERENCE's spectrogram, so both sides start from the same phases
+        if sub is None:
+            lm64, if64 = torch.from_numpy(z["tiny_logmel"]), torch.from_numpy(z["tiny_inst"])
+            back = psp.convert_to_waveform(lm64.float().to(device), if64.float().to(device), **params)
+            assert rel(back, z["tiny_back"]) < TOL, (tag, rel(back, z["tiny_back"]))
+
+
+def check_training_sequence(store, device, fixture="reference_step"):
+    """models.py GANSynth: D run, G run, ... under gan_synth_main.py's growth schedule, through the product's public
+    sub-step calls.  Losses and the applied gradient of every run against the reference's; after each run the
+    reference's variables are loaded, so every run starts from the reference's state (with beta1 = 0 an fp32 gradient
+    inside rounding of zero steps the other way, see tests/test_model_gpu.py::test_small_step_parity)."""
+    import gansynth_b200.models as pmodels
+    z = load(fixture)
+    hyper = dict(gen.HYPER, fake_gradient_penalty_weight=float(z["fake_penalty"]))
+    pmodels.reset_global_step()
+    level = pmodels.get_or_create_global_step() / gen.GROWING_STEPS                       # gan_synth_main.py:48-53
+    pg = product_pggan(store, level, device)
+    store.load(variables(z, "var0:"))
+    model = pmodels.GANSynth(pg.generator, pg.discriminator, None, None, gen.TINY_SPECTRAL, hyper, device=device)
+    model.use_cuda_graphs = False
+    dev = lambda a: torch.from_numpy(a).float().to(device)
+    for run in range(2 * int(z["iterations"])):
+        tag = "run%d:" % run
+        which = str(z[tag + "which"])
+        assert int(model.global_step.value) == int(z[tag + "global_step"])
+        waves, labels, latents = dev(z[tag + "waveforms"]), dev(z[tag + "labels"]), dev(z[tag + "latents"])
+        if which == "discriminator":
+            loss = model.discriminator_step(waves, labels, latents)
+        else:
+            loss = model.generator_step(labels, latents)
+        want = float(z[tag + which + "_loss"])
+        assert abs(float(loss) - want) < TOL * max(1.0, abs(want)), (run, float(loss), want)
+        flat = model._opt[which]["grad"]
+        for name, (a, k) in store.offsets[which].items():
+            want_g = z[tag + "grad:" + name]
+            got_g = flat[a:a + k].detach().double().cpu().numpy().reshape(want_g.shape)
+            scale = float(np.abs(want_g).max())
+            if scale == 0.0:
+                assert float(np.abs(got_g).max()) == 0.0, name
+            else:
+                assert float(np.abs(got_g - want_g).max()) <= TOL * scale, (run, name, float(np.abs(got_g - want_g).max()) / scale)
+        # tf.train.AdamOptimizer: where the gradient is resolved (above 1e-2 of the variable's largest) the updated
+        # weights meet the tolerance outright; elsewhere both sides moved by at most ~1.7 lr, possibly opposite ways
+        lr = hyper[which + "_learning_rate"]
+        for name, ref in variables(z, tag + "var:").items():
+            got = store.vars[name].detach().float().cpu()
+            g = np.abs(z[tag + "grad:" + name])
+            resolved = torch.from_numpy(g > 1e-2 * float(g.max())) if float(g.max()) > 0 else torch.zeros_like(ref, dtype=torch.bool)
+            diff = (got - ref).abs()
+            bound = TOL * float(ref.abs().max())
+            if bool(resolved.any()):
+                assert float(diff[resolved].max()) <= bound, (run, name, float(diff[resolved].max()), bound)
+            assert float(diff.max()) <= bound + 4.0 * lr, (run, name, float(diff.max()))
+        store.load(variables(z, tag + "var:"))
+    assert int(model.global_step.value) == int(z["final_global_step"])
+
+
+def check_classifier(store, device):
+    """networks.py ResNet + models.py PitchClassifier: two train-op runs (cross entropy + L2, Nesterov momentum under the
+    decaying learning rate of pitch_classifier_main.py:69-74), then the exported features / logits head."""
+    import gansynth_b200.models as pmodels
+    import gansynth_b200.networks as pnet
+    z = load("reference_classifier")
+    h = gen.CLASSIFIER_HYPER
+    pmodels.reset_global_step()
+    hyper = dict(weight_decay=h["weight_decay"], momentum=h["momentum"], use_nesterov=h["use_nesterov"],
+                 learning_rate=lambda step: pmodels.exponential_decay(h["base_learning_rate"], step, h["decay_steps"], h["decay_rate"]))
+    net = pnet.ResNet(**gen.TINY_RESNET)
+    model = pmodels.PitchClassifier(net, None, gen.TINY_SPECTRAL, hyper, device=device)
+    dev = lambda a: torch.from_numpy(a).float().to(device)
+    shaped = lambda d: {n: v.reshape(tuple(store.vars[n].shape)) for n, v in d.items()}    # gamma / beta: [1, C, 1, 1] there
+    for run in range(int(z["iterations"])):
+        tag = "run%d:" % run
+        waves, labels = dev(z[tag + "waveforms"]), dev(z[tag + "labels"])
+        if run == 0:
+            model._ensure_optimizer(model._images(waves))
+            store.load(shaped(variables(z, "var0:")))
+        before = {n: v.detach().clone() for n, v in store.vars.items()}
+        decay_loss = model.weight_decay_loss()
+        loss = float(model.train_step(waves, labels)) + decay_loss
+        want = float(z[tag + "loss"])
+        assert abs(loss - want) < TOL * max(1.0, abs(want)), (run, loss, want)
+        assert abs(model.accuracy - float(z[tag + "accuracy"])) < 1e-12
+        flat = model._opt["grad"]
+        for name, (a, k) in store.offsets[model.SCOPE].items():
+            want_g = z[tag + "grad:" + name].reshape(-1)
+            got_g = flat[a:a + k].detach().double().cpu().numpy()
+            if "normalization" not in name:                                              # models.py:267-271
+                got_g = got_g + h["weight_decay"] * before[name].detach().double().cpu().numpy().reshape(-1)
+            scale = float(np.abs(want_g).max())
+            assert float(np.abs(got_g - want_g).max()) <= TOL * scale, (run, name, float(np.abs(got_g - want_g).max()) / scale)
+        after = shaped(variables(z, tag + "var:"))
+        for name, ref in after.items():
+            assert rel(store.vars[name], ref.numpy()) < TOL, (run, name)
+        store.load(after)
+    with torch.no_grad():
+        features, logits = net(dev(z["images"]))
+    assert rel(features, z["features"]) < TOL and rel(logits, z["logits"]) < TOL

@@ -23,7 +23,7 @@ def conv_mode(request):
 
 
 def grad_ok(mode, got, want64, want32=None):
-    """Direction / size criterion against the UNPINNED fp64 oracle (kept as a coarse sanity bound only; the
+    """Direction / size criterion against the fp64 oracle run WITHOUT the product's leaky-relu masks (kept as a coarse sanity bound only; the
     gradient parity claim itself is `check_substep` below): cosine >= 0.9995 / 0.995, relative L2 <= 2e-2 / 1e-1."""
     g, w = got.detach().double().cpu().reshape(-1), want64.detach().double().reshape(-1)
     if float(w.abs().max()) == 0.0:

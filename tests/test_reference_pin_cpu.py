@@ -1,0 +1,215 @@
+"""CPU: the oracle against vectors the reference's OWN code produced.
+
+`tests/golden/reference_*.npz` were written by `tests/golden/make_reference_vectors.py`: the unmodified networks.py /
+spectral_ops.py / models.py of /root/reference executed op by op over `oracle/tf1_eager` (an eager restatement of the
+TensorFlow-1.13 primitives they call).  Everything above the primitives -- scopes and variable shapes, He constants, block
+order, the tf.cond growth arms and lerp weights, label conditioning, the three loss terms, both tf.gradients penalties,
+Adam / Nesterov-momentum updates, the D-run / G-run sequence with the growth level following global_step -- is therefore
+the reference's, and the oracle has to reproduce it to float64 round-off.  The last test re-runs the generator where
+/root/reference exists, so the committed files cannot drift away from what the reference says.
+"""
+import importlib.util
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import models as omodels
+from oracle import networks as onet
+from oracle import spectral_ops as osp
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+_spec = importlib.util.spec_from_file_location("make_reference_vectors", os.path.join(GOLDEN, "make_reference_vectors.py"))
+gen = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(gen)
+
+TIGHT = 1e-10      # float64 on both sides; the two differ only in the order of a few additions
+
+
+def _load(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def _close(got, want, tol=TIGHT):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    scale = max(1.0, float(np.abs(want).max()))
+    err = float(np.abs(got - want).max())
+    assert err <= tol * scale, (err, scale)
+
+
+def _grad_close(got, want, tol=1e-8):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64).reshape(np.shape(got))
+    scale = float(np.abs(want).max())
+    if scale == 0.0:
+        assert float(np.abs(got).max()) == 0.0
+    else:
+        assert float(np.abs(got - want).max()) <= tol * scale, (float(np.abs(got - want).max()), scale)
+
+
+def _variables(z, prefix):
+    return {k[len(prefix):]: _t(z[k]) for k in z.files if k.startswith(prefix)}
+
+
+# ------------------------------------------------------------------------------------------------ networks.py
+def test_generator_and_discriminator_at_every_growth_regime():
+    z = _load("reference_pggan")
+    params = _variables(z, "var:")
+    g_table, d_table = onet.PGGAN(growing_level=0.0, **gen.TINY).variable_shapes(gen.LATENT, gen.LABELS)
+    assert set(params) == set(g_table) | set(d_table)            # the reference's scopes give exactly the oracle's names
+    for name, (shape, _) in {**g_table, **d_table}.items():
+        assert tuple(params[name].shape) == tuple(shape), name
+    depths = []
+    for k, level in enumerate(z["levels"]):
+        pg = onet.PGGAN(growing_level=float(level), **gen.TINY)
+        _close(pg.growing_depth, z["growing_depth_%d" % k])
+        depths.append(pg.growing_depth)
+        _close(pg.generator(params, _t(z["latents"]), _t(z["labels"])), z["fake_images_%d" % k])
+        features, logits = pg.discriminator(params, _t(z["images"]), _t(z["labels"]))
+        _close(features, z["features_%d" % k])
+        _close(logits, z["logits_%d" % k])
+    # the five levels walk through every arm: nothing grown, first blend, middle blends, fully grown
+    assert depths[0] == 0.0 and 0.0 < depths[1] < 1.0 and 1.0 < depths[2] < 3.0 and depths[-1] > 3.0
+
+
+def test_variable_tables_of_both_command_lines():
+    with open(os.path.join(GOLDEN, "reference_variables.json")) as f:
+        tables = json.load(f)
+    g_table, d_table = onet.PGGAN(growing_level=0.0, min_resolution=[2, 16], max_resolution=[128, 1024], min_channels=32,
+                                  max_channels=256).variable_shapes(256, 61)
+    want = {n: list(s) for n, (s, _) in {**g_table, **d_table}.items()}
+    assert tables["gan_synth"] == want
+    resnet = onet.ResNet(conv_param=dict(filters=64, kernel_size=[7, 7], strides=[2, 2]), pool_param=dict(kernel_size=[3, 3], strides=[2, 2]),
+                         residual_params=[dict(filters=64, strides=[1, 1], blocks=3), dict(filters=128, strides=[2, 2], blocks=4),
+                                          dict(filters=256, strides=[2, 2], blocks=6), dict(filters=512, strides=[2, 2], blocks=3)],
+                         groups=32, classes=61)
+    ours = resnet.variable_shapes()
+    assert set(tables["pitch_classifier"]) == set(ours)
+    for name, shape in tables["pitch_classifier"].items():
+        if name.endswith(("/beta", "/gamma")):                   # the reference keeps these as [1, C, 1, 1] (ops.py:131-140)
+            assert shape == [1, ours[name][0], 1, 1], name
+        else:
+            assert shape == list(ours[name]), name
+
+
+# ------------------------------------------------------------------------------------------------ spectral_ops.py
+def test_spectral_round_trip():
+    z = _load("reference_spectral")
+    wave = _t(z["full_wave"]).double()
+    logmel, inst = osp.convert_to_spectrogram(wave, **gen.FULL_SPECTRAL)
+    _close(logmel[:, ::8, ::16], z["full_logmel_sub"])
+    _close(inst[:, ::8, ::16], z["full_inst_sub"])
+    _close(osp.convert_to_waveform(logmel, inst, **gen.FULL_SPECTRAL)[:, ::32], z["full_back_sub"])
+    logmel, inst = osp.convert_to_spectrogram(_t(z["tiny_wave"]), **gen.TINY_SPECTRAL)
+    _close(logmel, z["tiny_logmel"])
+    _close(inst, z["tiny_inst"])
+    _close(osp.convert_to_waveform(logmel, inst, **gen.TINY_SPECTRAL), z["tiny_back"])
+
+
+# ------------------------------------------------------------------------------------------------ models.py GANSynth
+@pytest.mark.parametrize("fixture", ["reference_step", "reference_step_fake_penalty"])
+def test_training_sequence(fixture):
+    z = _load(fixture)
+    hyper = dict(gen.HYPER, fake_gradient_penalty_weight=float(z["fake_penalty"]))
+    holder = {}
+    pg = onet.PGGAN(growing_level=lambda: holder["step"].global_step / gen.GROWING_STEPS, **gen.TINY)   # gan_synth_main.py:48-53
+    step = holder["step"] = omodels.GANSynthStep(pg, _variables(z, "var0:"), hyper)
+    for run in range(2 * int(z["iterations"])):
+        tag = "run%d:" % run
+        which = str(z[tag + "which"])
+        assert step.global_step == int(z[tag + "global_step"])
+        waves, labels, latents = _t(z[tag + "waveforms"]), _t(z[tag + "labels"]), _t(z[tag + "latents"])
+        real = omodels.real_images_from_waveforms(waves, gen.TINY_SPECTRAL)                 # models.py:27-28
+        _close(real, z[tag + "real_images"])
+        fake = pg.generator(step.params, latents, labels).detach()
+        _close(fake, z[tag + "fake_images"])
+        _close(osp.convert_to_waveform(fake[:, 0], fake[:, 1], **gen.TINY_SPECTRAL), z[tag + "fake_waveforms"])   # models.py:30-31
+        # every session.run evaluates both losses on its batch
+        _close(omodels.discriminator_loss(pg, step.params, real, labels, latents, hyper).detach(), z[tag + "discriminator_loss"])
+        _close(omodels.generator_loss(pg, step.params, labels, latents, hyper).detach(), z[tag + "generator_loss"])
+        if which == "discriminator":
+            _, grads = step.discriminator_update(real, labels, latents)
+        else:
+            _, grads = step.generator_update(labels, latents)
+        names = [k[len(tag) + 5:] for k in z.files if k.startswith(tag + "grad:")]
+        assert set(names) == set(grads)
+        for name in names:
+            _grad_close(grads[name].numpy(), z[tag + "grad:" + name])
+            _close(step.params[name].detach(), z[tag + "var:" + name])                      # tf.train.AdamOptimizer
+    assert step.global_step == int(z["final_global_step"]) == int(z["iterations"])          # only the G op counts steps
+
+
+# ------------------------------------------------------------------------------------------------ models.py PitchClassifier
+def test_classifier_training_and_export_head():
+    z = _load("reference_classifier")
+    flat = lambda d: {n: (v.reshape(-1) if n.endswith(("/beta", "/gamma")) else v) for n, v in d.items()}
+    resnet = onet.ResNet(**gen.TINY_RESNET)
+    h = gen.CLASSIFIER_HYPER
+    step = omodels.PitchClassifierStep(resnet, flat(_variables(z, "var0:")), h["weight_decay"], h["momentum"], h["use_nesterov"])
+    hits = seen = 0
+    for run in range(int(z["iterations"])):
+        tag = "run%d:" % run
+        waves, labels = _t(z[tag + "waveforms"]), _t(z[tag + "labels"])
+        images = omodels.real_images_from_waveforms(waves, gen.TINY_SPECTRAL)
+        before = {n: p.detach().clone() for n, p in step.params.items()}
+        lr = h["base_learning_rate"] * h["decay_rate"] ** (run / h["decay_steps"])          # pitch_classifier_main.py:69-74
+        total, _, logits = step.update(images, labels, lr)
+        _close(total, z[tag + "loss"])
+        hits += int((logits.argmax(dim=1) == labels.argmax(dim=1)).sum())
+        seen += labels.shape[0]
+        _close(hits / seen, z[tag + "accuracy"])                                            # tf.metrics.accuracy: running
+        for name in before:
+            _close(step.params[name].detach(), z[tag + "var:" + name].reshape(before[name].shape))
+    features, logits = resnet(step.params, _t(z["images"]))
+    _close(features.detach(), z["features"])
+    _close(logits.detach(), z["logits"])
+
+
+# ------------------------------------------------------------------------------------------------ the product's host logic
+def test_product_forward_on_reference_vectors(emu):
+    import reference_vectors as rv
+    rv.check_forward(emu, "cpu")
+
+
+def test_product_spectral_on_reference_vectors(emu):
+    import reference_vectors as rv
+    rv.check_spectral("cpu")
+
+
+@pytest.mark.parametrize("fixture", ["reference_step", "reference_step_fake_penalty"])
+def test_product_training_sequence_on_reference_vectors(emu, fixture):
+    import reference_vectors as rv
+    rv.check_training_sequence(emu, "cpu", fixture)
+
+
+def test_product_classifier_on_reference_vectors(emu):
+    import reference_vectors as rv
+    rv.check_classifier(emu, "cpu")
+
+
+# ------------------------------------------------------------------------------------------------ provenance
+@pytest.mark.skipif(not os.path.exists(gen.REFERENCE), reason="reference tree not present")
+def test_committed_vectors_are_what_the_reference_says():
+    """Re-runs the reference (every case of the generator) and compares with the committed files; then once more in
+    float32 -- the precision TensorFlow itself would use -- against the float32 oracle at fp32 round-off."""
+    for name, fn in gen.CASES.items():
+        fresh, committed = fn(), _load(name)
+        assert set(fresh) == set(committed.files), name
+        for key in committed.files:
+            if committed[key].dtype.kind in "fc":
+                _close(fresh[key], committed[key], 1e-12)
+            else:
+                assert np.array_equal(fresh[key], committed[key]), (name, key)
+    z32 = gen.pggan_forward(dtype=torch.float32)
+    params = {k[4:]: _t(v) for k, v in z32.items() if k.startswith("var:")}
+    for k, level in enumerate(z32["levels"]):
+        pg = onet.PGGAN(growing_level=float(level), **gen.TINY)
+        _close(pg.generator(params, _t(z32["latents"]), _t(z32["labels"])), z32["fake_images_%d" % k], 3e-5)
+        _, logits = pg.discriminator(params, _t(z32["images"]), _t(z32["labels"]))
+        _close(logits, z32["logits_%d" % k], 1e-4)
