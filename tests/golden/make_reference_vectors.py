@@ -286,7 +286,33 @@ def classifier_step(iterations=2, dtype=torch.float64):
     return out
 
 
-CASES = dict(reference_pggan=pggan_forward, reference_spectral=spectral, reference_step=gan_step,
+def metrics_case():
+    """metrics.py is plain numpy / scipy / sklearn: imported and called as it is."""
+    for name in ("metrics",):
+        sys.modules.pop(name, None)
+    sys.path.insert(0, REFERENCE)
+    try:
+        import metrics
+        assert os.path.dirname(os.path.abspath(metrics.__file__)) == REFERENCE
+    finally:
+        sys.path.remove(REFERENCE)
+        sys.modules.pop("metrics", None)
+    import scipy.linalg  # noqa: F401  (metrics.py reaches scipy.linalg / scipy.stats through the top-level package)
+    import scipy.stats  # noqa: F401
+    rng = np.random.default_rng(51)
+    logits = rng.normal(size=(64, LABELS)) * 3.0
+    real = rng.normal(size=(400, 6)) @ rng.normal(size=(6, 6))
+    fake = rng.normal(size=(300, 6)) @ rng.normal(size=(6, 6)) + 0.5
+    p, q = metrics.softmax(logits[:8]), metrics.softmax(logits[8:16])
+    props_p, props_q = rng.dirichlet(np.ones(10)), rng.dirichlet(np.ones(10))
+    return dict(logits=logits, real=real, fake=fake, softmax=metrics.softmax(logits), kl=metrics.kl_divergence(p, q),
+                inception_score=np.asarray(metrics.inception_score(logits)),
+                frechet_inception_distance=np.asarray(metrics.frechet_inception_distance(real, fake)),
+                props_p=props_p, props_q=props_q,
+                binomial=metrics.binomial_proportion_test(props_p, 400, props_q, 300, 0.05))
+
+
+CASES = dict(reference_metrics=metrics_case, reference_pggan=pggan_forward, reference_spectral=spectral, reference_step=gan_step,
              reference_step_fake_penalty=lambda: gan_step(fake_penalty=2.0, iterations=1),
              reference_classifier=classifier_step)
 

@@ -171,6 +171,18 @@ def test_classifier_training_and_export_head():
     _close(logits.detach(), z["logits"])
 
 
+# ------------------------------------------------------------------------------------------------ metrics.py
+def test_evaluation_statistics():
+    """gansynth_b200.metrics against values the reference's metrics.py (plain numpy / scipy) returned for the same inputs."""
+    from gansynth_b200 import metrics
+    z = _load("reference_metrics")
+    _close(metrics.softmax(z["logits"]), z["softmax"], 1e-14)
+    _close(metrics.kl_divergence(metrics.softmax(z["logits"][:8]), metrics.softmax(z["logits"][8:16])), z["kl"], 1e-13)
+    _close(metrics.inception_score(z["logits"]), z["inception_score"], 1e-13)
+    _close(metrics.frechet_inception_distance(z["real"], z["fake"]), z["frechet_inception_distance"], 1e-9)
+    assert np.array_equal(metrics.binomial_proportion_test(z["props_p"], 400, z["props_q"], 300, 0.05), z["binomial"])
+
+
 # ------------------------------------------------------------------------------------------------ the product's host logic
 def test_product_forward_on_reference_vectors(emu):
     import reference_vectors as rv
