@@ -286,6 +286,87 @@ def classifier_step(iterations=2, dtype=torch.float64):
     return out
 
 
+# ------------------------------------------------------------------------------------------------ the benchmark's own size
+FULL = dict(min_resolution=[2, 16], max_resolution=[128, 1024], min_channels=32, max_channels=256)   # gan_synth_main.py:43-47
+FULL_BATCH, FULL_LATENT, FULL_LABELS = 8, 256, 61
+GRAD_SAMPLES = 16
+
+
+def named_value(name, shape):
+    """Value of a full-size variable as a function of its NAME alone (64 MB of weights cannot be committed; both the
+    generator below and the tests rebuild them from this): truncated normal for weights, 0.1 N(0, 1) for biases, rounded
+    to float32 so that every precision starts from the same numbers."""
+    seed = sum((i + 1) * b for i, b in enumerate(name.encode())) % (2 ** 31)
+    rng = torch.Generator().manual_seed(seed)
+    if name.endswith("/bias"):
+        t = 0.1 * torch.randn(list(shape), generator=rng, dtype=torch.float64)
+    else:
+        t = torch.empty(list(shape), dtype=torch.float64)
+        torch.nn.init.trunc_normal_(t, 0.0, 1.0, -2.0, 2.0, generator=rng)
+    return t.float().double()
+
+
+def full_inputs():
+    rng = torch.Generator().manual_seed(61)
+    t = torch.arange(64000, dtype=torch.float64) / 16000.0
+    freqs = 110.0 * 2.0 ** (torch.arange(FULL_BATCH, dtype=torch.float64) / 2.0)
+    waves = 0.4 * torch.sin(2 * np.pi * freqs[:, None] * t[None, :]) * torch.exp(-2.0 * t)[None, :] \
+        + 0.02 * torch.randn(FULL_BATCH, 64000, generator=rng, dtype=torch.float64)
+    labels = torch.nn.functional.one_hot(torch.randint(0, FULL_LABELS, (FULL_BATCH,), generator=rng), FULL_LABELS).double()
+    latents = torch.randn(FULL_BATCH, FULL_LATENT, generator=rng, dtype=torch.float64)
+    return waves.float().double(), labels, latents.float().double()
+
+
+def grad_summary(grad):
+    """(L2 norm, largest magnitude, GRAD_SAMPLES evenly spaced elements of the flattened TF-layout gradient)."""
+    flat = grad.reshape(-1).double()
+    idx = torch.linspace(0, flat.numel() - 1, GRAD_SAMPLES).long()
+    return np.concatenate([[float(flat.norm()), float(flat.abs().max())], flat[idx].numpy()])
+
+
+def full_step(dtype=torch.float64):
+    """ONE session.run of models.GANSynth at the configuration of gan_synth_main.py (fully grown 128x1024 networks,
+    batch 8, the command line's hyper-parameters): images, logits-derived losses and a summary of every gradient.
+    About a minute and 20 GB in float64; not part of CASES (run with `--full`)."""
+    tf, networks, _, models, Dict = reference_modules()
+    tf.reset_default_graph()
+    tf.set_float_dtype(dtype)
+    waves, labels, latents = full_inputs()
+    holder = {}
+
+    def real_input_fn():
+        return tf.Tensor(waves.to(dtype).requires_grad_(True)), tf.Tensor(labels.to(dtype))
+
+    def fake_input_fn():
+        holder["z"] = tf.Tensor(latents.to(dtype).requires_grad_(True))
+        return holder["z"]
+
+    def construct():
+        pggan = networks.PGGAN(growing_level=tf.Tensor(torch.tensor(1.0, dtype=dtype)), **FULL)
+        return models.GANSynth(generator=pggan.generator, discriminator=pggan.discriminator, real_input_fn=real_input_fn,
+                               fake_input_fn=fake_input_fn, spectral_params=Dict(FULL_SPECTRAL), hyper_params=Dict(HYPER))
+
+    # graph construction on a small stand-in batch is not possible (shapes are the graph's), so the variables of the grown
+    # path are created by a first evaluation and then given their named values
+    with torch.no_grad():
+        pggan = networks.PGGAN(growing_level=tf.Tensor(torch.tensor(1.0, dtype=dtype)), **FULL)
+        fake = pggan.generator(tf.Tensor(latents.to(dtype)), tf.Tensor(labels.to(dtype)))
+        pggan.discriminator(fake, tf.Tensor(labels.to(dtype)))
+    for name, var in tf.variables().items():
+        var.assign(named_value(name, var.t.shape).to(dtype))
+    model = construct()
+    out = dict(variable_names=np.asarray(list(tf.variables())),
+               real_images_sub=_np(model.real_images.t)[:, :, ::4, ::16], fake_images_sub=_np(model.fake_images.t)[:, :, ::4, ::16],
+               fake_waveforms_sub=_np(model.fake_waveforms.t)[:, ::64],
+               real_logits=_np(model.real_logits.t), fake_logits=_np(model.fake_logits.t),
+               real_features=_np(model.real_features.t), fake_features=_np(model.fake_features.t),
+               generator_loss=_np(model.generator_loss.t), discriminator_loss=_np(model.discriminator_loss.t))
+    for which in ("discriminator", "generator"):
+        for grad, var in getattr(model, which + "_train_op").grads_and_vars:
+            out["grad:" + var.op.name] = grad_summary(torch.zeros_like(var.t) if grad is None else grad)
+    return out
+
+
 def metrics_case():
     """metrics.py is plain numpy / scipy / sklearn: imported and called as it is."""
     for name in ("metrics",):
@@ -318,6 +399,12 @@ CASES = dict(reference_metrics=metrics_case, reference_pggan=pggan_forward, refe
 
 
 def main():
+    if "--full" in sys.argv:
+        arrays = full_step()
+        path = os.path.join(HERE, "reference_full_step.npz")
+        np.savez_compressed(path, **arrays)
+        print("reference_full_step %d arrays %.1f kB" % (len(arrays), os.path.getsize(path) / 1e3))
+        return
     for name, fn in CASES.items():
         arrays = fn()
         path = os.path.join(HERE, name + ".npz")

@@ -167,3 +167,64 @@ def check_classifier(store, device):
     with torch.no_grad():
         features, logits = net(dev(z["images"]))
     assert rel(features, z["features"]) < TOL and rel(logits, z["logits"]) < TOL
+
+
+def check_full_step(store, device, sample_tol, norm_tol=5e-3):
+    """The benchmark's own configuration -- fully grown 128x1024 networks, batch 8, gan_synth_main.py's hyper-parameters --
+    against ONE session.run of the reference's models.GANSynth (tests/golden/reference_full_step.npz): images, features,
+    the selected logits, both losses at 1e-3; of every gradient the L2 norm (`norm_tol`) and 16 evenly spaced elements
+    (`sample_tol` of the variable's largest magnitude).  The weights are rebuilt from their names on both sides."""
+    import json
+    import gansynth_b200.models as pmodels
+    import gansynth_b200.networks as pnet
+    z = load("reference_full_step")
+    with open(os.path.join(GOLDEN, "reference_variables.json")) as f:
+        shapes = json.load(f)["gan_synth"]
+    pmodels.reset_global_step()
+    pg = pnet.PGGAN(growing_level=1.0, **gen.FULL)
+    pg._ensure_variables("generator", gen.FULL_LATENT, gen.FULL_LABELS)
+    pg._ensure_variables("discriminator", 0, gen.FULL_LABELS)
+    assert set(store.vars) == set(shapes)
+    store.load({n: gen.named_value(n, s).float() for n, s in shapes.items()})
+    model = pmodels.GANSynth(pg.generator, pg.discriminator, None, None, gen.FULL_SPECTRAL, gen.HYPER, device=device)
+    model.use_cuda_graphs = False
+    waves, labels, latents = (t.float().to(device) for t in gen.full_inputs())
+    real = model.real_images_from_waveforms(waves)
+    assert rel(real[:, 0, ::4, ::16], z["real_images_sub"][:, 0]) < TOL
+    d = np.abs(real[:, 1, ::4, ::16].detach().double().cpu().numpy() - z["real_images_sub"][:, 1])
+    wrapped = np.abs(d - 2.0) < 2e-3                         # a phase step within rounding of +-pi unwraps either way
+    assert float(wrapped.mean()) < 5e-3 and float(d[~wrapped].max()) < 2e-3, (float(wrapped.mean()), float(d[~wrapped].max()))
+    with torch.no_grad():
+        fake = pg.generator(latents, labels)
+        assert rel(fake[:, :, ::4, ::16], z["fake_images_sub"]) < TOL
+        features, logits = pg.discriminator(fake, labels)
+        assert rel(features, z["fake_features"]) < TOL
+        assert rel(pmodels._select_logits(logits, labels), z["fake_logits"]) < TOL
+        features, logits = pg.discriminator(real, labels)
+        assert rel(features, z["real_features"]) < TOL
+        assert rel(pmodels._select_logits(logits, labels), z["real_logits"]) < TOL
+    model._ensure_optimizers(labels, latents)
+    for which in ("discriminator", "generator"):
+        model._set_trainable(which)
+        if which == "discriminator":
+            loss = model.discriminator_loss_fn(real, labels, latents)
+        else:
+            loss = model.generator_loss_fn(labels, latents)
+        want = float(z[which + "_loss"])
+        assert abs(float(loss) - want) < TOL * max(1.0, abs(want)), (which, float(loss), want)
+        model._backward(which, loss)
+        flat = model._opt[which]["grad"]
+        worst, worst_norm, failures = (0.0, ""), (0.0, ""), []
+        for name, (a, k) in store.offsets[which].items():
+            if "grad:" + name not in z.files:                  # colour blocks of the lower resolutions: not on the grown path
+                assert float(flat[a:a + k].abs().max()) == 0.0, name
+                continue
+            want_s = z["grad:" + name]
+            got_s = gen.grad_summary(flat[a:a + k].detach().cpu())
+            nerr = abs(got_s[0] - want_s[0]) / want_s[0]
+            err = float(np.abs(got_s[2:] - want_s[2:]).max()) / want_s[1]
+            worst, worst_norm = max(worst, (err, name)), max(worst_norm, (nerr, name))
+            failures += [(name, nerr, err)] if (nerr > norm_tol or err > sample_tol) else []
+        print("%s: loss %.6f (reference %.6f); worst gradient norm error %.2e (%s); worst sampled element %.2e of its "
+              "variable's maximum (%s)" % (which, float(loss), want, worst_norm[0], worst_norm[1], worst[0], worst[1]))
+        assert not failures, failures[:6]

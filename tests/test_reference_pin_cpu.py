@@ -171,6 +171,46 @@ def test_classifier_training_and_export_head():
     _close(logits.detach(), z["logits"])
 
 
+# ------------------------------------------------------------------------------------------------ the benchmark's own size
+def _full_variables():
+    with open(os.path.join(GOLDEN, "reference_variables.json")) as f:
+        shapes = json.load(f)["gan_synth"]
+    return {n: gen.named_value(n, s) for n, s in shapes.items()}
+
+
+@pytest.mark.skipif(os.environ.get("GS_FULL_PIN", "0") != "1",
+                    reason="about two minutes and 25 GB of float64 on the CPU: GS_FULL_PIN=1 (profiles/full_pin_r2.txt has a run)")
+def test_full_size_step_oracle():
+    """One session.run of the reference's GANSynth at gan_synth_main.py's own configuration (fully grown 128x1024, batch 8)
+    against the oracle, float64: images, features, selected logits, both losses, every gradient's norm / maximum / samples."""
+    z = _load("reference_full_step")
+    params = _full_variables()
+    assert sorted(str(n) for n in z["variable_names"] if str(n) != "global_step") == sorted(n for n in params if "color_block" not in n or "128x1024" in n)
+    waves, labels, latents = gen.full_inputs()
+    pg = onet.PGGAN(growing_level=1.0, **gen.FULL)
+    step = omodels.GANSynthStep(pg, params, gen.HYPER)
+    real = omodels.real_images_from_waveforms(waves, gen.FULL_SPECTRAL)
+    _close(real[:, :, ::4, ::16], z["real_images_sub"])
+    with torch.no_grad():
+        fake = pg.generator(step.params, latents, labels)
+        _close(fake[:, :, ::4, ::16], z["fake_images_sub"])
+        _close(osp.convert_to_waveform(fake[:, 0], fake[:, 1], **gen.FULL_SPECTRAL)[:, ::64], z["fake_waveforms_sub"])
+        features, logits = pg.discriminator(step.params, fake, labels)
+        _close(features, z["fake_features"])
+        _close(omodels.select_logits(logits, labels), z["fake_logits"])
+        features, logits = pg.discriminator(step.params, real, labels)
+        _close(features, z["real_features"])
+        _close(omodels.select_logits(logits, labels), z["real_logits"])
+    d_loss, d_grads = step.discriminator_update(real, labels, latents, apply=False)
+    g_loss, g_grads = step.generator_update(labels, latents, apply=False)
+    _close(d_loss, z["discriminator_loss"])
+    _close(g_loss, z["generator_loss"])
+    for name, grad in {**d_grads, **g_grads}.items():
+        if "grad:" + name in z.files:
+            want = z["grad:" + name]
+            _grad_close(gen.grad_summary(grad.detach()), want, 1e-7 * max(1.0, want[1] and want[0] / want[1]))
+
+
 # ------------------------------------------------------------------------------------------------ metrics.py
 def test_evaluation_statistics():
     """gansynth_b200.metrics against values the reference's metrics.py (plain numpy / scipy) returned for the same inputs."""
@@ -198,6 +238,12 @@ def test_product_spectral_on_reference_vectors(emu):
 def test_product_training_sequence_on_reference_vectors(emu, fixture):
     import reference_vectors as rv
     rv.check_training_sequence(emu, "cpu", fixture)
+
+
+@pytest.mark.skipif(os.environ.get("GS_FULL_PIN", "0") != "1", reason="minutes of CPU: GS_FULL_PIN=1")
+def test_product_full_size_step_on_reference_vectors(emu):
+    import reference_vectors as rv
+    rv.check_full_step(emu, "cpu", 1e-2)
 
 
 def test_product_classifier_on_reference_vectors(emu):

@@ -34,3 +34,14 @@ def test_training_sequence(cuda_store, conv_mode, fixture):
 
 def test_classifier_training_and_export_head(cuda_store):
     rv.check_classifier(cuda_store, "cuda")
+
+
+def test_full_size_batch8_step(cuda_store, conv_mode):
+    """BASELINE config 2 itself against the reference's own code: see reference_vectors.check_full_step.  Forward values
+    and losses at 1e-3.  The sampled gradient elements are compared WITHOUT pinning the leaky-relu masks, so their bound is
+    the spread fp32 arithmetic itself shows against the float64 reference at this size (torch-CPU fp32: 3.9e-3 of a
+    variable's maximum), not north_star's 1e-3 -- that claim is test_model_gpu.py's mask-pinned criterion."""
+    if conv_mode == "fp32":
+        rv.check_full_step(cuda_store, "cuda", sample_tol=1e-2, norm_tol=5e-3)
+    else:
+        rv.check_full_step(cuda_store, "cuda", sample_tol=3e-2, norm_tol=3e-2)
