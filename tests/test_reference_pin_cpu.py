@@ -271,3 +271,65 @@ def test_committed_vectors_are_what_the_reference_says():
         _close(pg.generator(params, _t(z32["latents"]), _t(z32["labels"])), z32["fake_images_%d" % k], 3e-5)
         _, logits = pg.discriminator(params, _t(z32["images"]), _t(z32["labels"]))
         _close(logits, z32["logits_%d" % k], 1e-4)
+
+
+@pytest.mark.skipif(not os.path.exists(gen.REFERENCE), reason="reference tree not present")
+def test_oracle_follows_the_reference_over_configurations():
+    """Live, no fixture: seeded random architectures (seed resolution, number of doublings, channel clamp, latent size,
+    label count, growth level, batch) through the reference's networks.py and through the oracle with the same variables."""
+    tf, networks, _, _, _ = gen.reference_modules()
+    tf.set_float_dtype(torch.float64)
+    rng = np.random.default_rng(7)
+    for case in range(8):
+        tf.reset_default_graph()
+        tf.set_random_seed(case)
+        seed_res = [int(rng.choice([1, 2, 3, 4])), int(rng.choice([1, 2, 4, 5]))]
+        doublings = int(rng.integers(1, 4))      # the reference cannot build a graph without at least one doubling
+        cfg = dict(min_resolution=seed_res, max_resolution=[r << doublings for r in seed_res],
+                   min_channels=int(rng.choice([2, 4, 6])), max_channels=int(rng.choice([8, 12, 64])))
+        latent, classes, batch = int(rng.choice([3, 8])), int(rng.choice([2, 7])), 4 * int(rng.integers(1, 3))
+        level = float(rng.choice([0.0, rng.uniform(0.0, 1.0), 1.0]))
+        g = torch.Generator().manual_seed(100 + case)
+        latents = torch.randn(batch, latent, generator=g, dtype=torch.float64)
+        labels = torch.nn.functional.one_hot(torch.randint(0, classes, (batch,), generator=g), classes).double()
+        images = torch.randn(batch, 2, *cfg["max_resolution"], generator=g, dtype=torch.float64)
+        ref = networks.PGGAN(growing_level=tf.Tensor(torch.tensor(level, dtype=torch.float64)), **cfg)
+        tf.build_all_branches(True)
+        ref.generator(tf.Tensor(latents), tf.Tensor(labels))
+        ref.discriminator(tf.Tensor(images), tf.Tensor(labels))
+        tf.build_all_branches(False)
+        gen._perturb_biases(tf, 200 + case)
+        want_fake = ref.generator(tf.Tensor(latents), tf.Tensor(labels))
+        want_features, want_logits = ref.discriminator(tf.Tensor(images), tf.Tensor(labels))
+        params = {n: v.t.detach().clone() for n, v in tf.variables().items()}
+        ours = onet.PGGAN(growing_level=level, **cfg)
+        g_table, d_table = ours.variable_shapes(latent, classes)
+        assert {n: tuple(s) for n, (s, _) in {**g_table, **d_table}.items()} == {n: tuple(v.shape) for n, v in params.items()}, cfg
+        _close(ours.generator(params, latents, labels), want_fake.t.detach())
+        features, logits = ours.discriminator(params, images, labels)
+        _close(features, want_features.t.detach())
+        _close(logits, want_logits.t.detach())
+
+
+@pytest.mark.skipif(not os.path.exists(gen.REFERENCE), reason="reference tree not present")
+def test_oracle_spectral_follows_the_reference_over_configurations():
+    """Live: spectrogram shapes, overlaps, sample rates and waveform lengths (front padding 0 ... most of a frame) through
+    the reference's spectral_ops.py and through the oracle, both ways."""
+    tf, _, spectral_ops, _, _ = gen.reference_modules()
+    tf.set_float_dtype(torch.float64)
+    rng = np.random.default_rng(9)
+    for case in range(8):
+        bins = int(rng.choice([16, 32, 64, 256]))
+        steps = int(rng.choice([4, 9, 16, 33]))
+        overlap = float(rng.choice([0.5, 0.75, 0.875]))
+        frame_step = int((1.0 - overlap) * 2 * bins)
+        covered = frame_step * (steps - 1) + 2 * bins
+        params = dict(waveform_length=int(covered - rng.integers(0, 2 * bins - 1)), sample_rate=int(rng.choice([8000, 16000, 44100])),
+                      spectrogram_shape=[steps, bins], overlap=overlap)
+        g = torch.Generator().manual_seed(300 + case)
+        waves = 0.3 * torch.randn(3, params["waveform_length"], generator=g, dtype=torch.float64)
+        want_lm, want_if = spectral_ops.convert_to_spectrogram(tf.Tensor(waves), **params)
+        got_lm, got_if = osp.convert_to_spectrogram(waves, **params)
+        _close(got_lm, want_lm.t)
+        _close(got_if, want_if.t)
+        _close(osp.convert_to_waveform(got_lm, got_if, **params), spectral_ops.convert_to_waveform(want_lm, want_if, **params).t)
