@@ -17,7 +17,7 @@ at 1e-10 (forward at every growth regime, spectral both ways, the D-run / G-run 
 Adam update, the pitch classifier) and re-runs the generator wherever /root/reference exists.  What stays unpinned is the
 behaviour of the TensorFlow kernels under those primitives; that layer is covered by (a) analytic known-answer tests and
 independent numpy / scipy / torchaudio / torch.istft cross-checks in tests/test_oracle_cpu.py and (b) nothing else.
-tests/golden/small_step.npz and spectral.npz are older fixtures this package generated itself (tools/make_golden.py).
+tests/golden/small_step.npz and spectral.npz are older fixtures this package generated itself (tests/tools/make_golden.py).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
 this package.  The product package gansynth_b200/ never does.

@@ -235,7 +235,7 @@ def test_config1_plumbing(level):
 
 # ----------------------------------------------------------------------------- golden fixtures
 def test_golden_fixtures():
-    """tests/golden/*.npz were written by tools/make_golden.py from this oracle; they freeze its
+    """tests/golden/*.npz were written by tests/tools/make_golden.py from this oracle; they freeze its
     behaviour so later edits cannot drift silently."""
     path = os.path.join(GOLDEN, "small_step.npz")
     if not os.path.exists(path):

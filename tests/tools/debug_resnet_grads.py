@@ -1,7 +1,7 @@
 """Per-variable gradient parity of networks.ResNet (CUDA) against the oracle (debug helper)."""
 import os, sys
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import gansynth_b200.ops as ops, gansynth_b200.networks as pnet
 from oracle import networks as onet

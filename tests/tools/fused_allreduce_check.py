@@ -1,5 +1,5 @@
 """Multi-GPU check of the fused gradient all-reduce + Adam (gs_adam_step_allreduce over NVLink symmetric memory).
-Launch: python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 tools/fused_allreduce_check.py
+Launch: python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 tests/tools/fused_allreduce_check.py
 
 For each mode -- "0" (ncclAllReduce + gs_adam_step, the reference path), "p2p" (peer loads / stores), "1" (NVSwitch
 multimem) -- the same small model is trained for three iterations on rank-dependent data from identical weights.  Checks:
@@ -11,7 +11,7 @@ import sys
 import torch
 import torch.distributed as dist
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

@@ -1,11 +1,11 @@
 """Per-variable error of the full-size D / G sub-step gradients: CUDA path and fp32 oracle, both against
-the fp64 oracle.  Run on the GPU box: python tools/grad_diag.py [batch]"""
+the fp64 oracle.  Run on the GPU box: python tests/tools/grad_diag.py [batch]"""
 import os
 import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from common import FULL, HYPER, seeded_inputs  # noqa: E402

@@ -1,5 +1,5 @@
 """Writes tests/golden/*.npz from the oracle (the reference itself cannot run here: no TensorFlow).
-Run from the repo root:  python tools/make_golden.py"""
+Run from the repo root:  python tests/tools/make_golden.py"""
 import math
 import os
 import sys
@@ -7,7 +7,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from common import HYPER, SMALL, SPECTRAL, seeded_inputs  # noqa: E402
