@@ -273,14 +273,13 @@ def test_committed_vectors_are_what_the_reference_says():
         _close(logits, z32["logits_%d" % k], 1e-4)
 
 
-@pytest.mark.skipif(not os.path.exists(gen.REFERENCE), reason="reference tree not present")
-def test_oracle_follows_the_reference_over_configurations():
-    """Live, no fixture: seeded random architectures (seed resolution, number of doublings, channel clamp, latent size,
-    label count, growth level, batch) through the reference's networks.py and through the oracle with the same variables."""
+def _random_architectures(count=8):
+    """Seeded random architectures run through the reference's networks.py, live: yields (cfg, latent size, classes,
+    level, latents, labels, images, variables by name, the reference's fake images / features / logits)."""
     tf, networks, _, _, _ = gen.reference_modules()
     tf.set_float_dtype(torch.float64)
     rng = np.random.default_rng(7)
-    for case in range(8):
+    for case in range(count):
         tf.reset_default_graph()
         tf.set_random_seed(case)
         seed_res = [int(rng.choice([1, 2, 3, 4])), int(rng.choice([1, 2, 4, 5]))]
@@ -299,16 +298,45 @@ def test_oracle_follows_the_reference_over_configurations():
         ref.discriminator(tf.Tensor(images), tf.Tensor(labels))
         tf.build_all_branches(False)
         gen._perturb_biases(tf, 200 + case)
-        want_fake = ref.generator(tf.Tensor(latents), tf.Tensor(labels))
-        want_features, want_logits = ref.discriminator(tf.Tensor(images), tf.Tensor(labels))
+        fake = ref.generator(tf.Tensor(latents), tf.Tensor(labels))
+        features, logits = ref.discriminator(tf.Tensor(images), tf.Tensor(labels))
         params = {n: v.t.detach().clone() for n, v in tf.variables().items()}
+        yield cfg, latent, classes, level, latents, labels, images, params, fake.t.detach(), features.t.detach(), logits.t.detach()
+
+
+@pytest.mark.skipif(not os.path.exists(gen.REFERENCE), reason="reference tree not present")
+def test_oracle_follows_the_reference_over_configurations():
+    """Live, no fixture: seeded random architectures (seed resolution, number of doublings, channel clamp, latent size,
+    label count, growth level, batch) through the reference's networks.py and through the oracle with the same variables."""
+    for cfg, latent, classes, level, latents, labels, images, params, fake, features, logits in _random_architectures():
         ours = onet.PGGAN(growing_level=level, **cfg)
         g_table, d_table = ours.variable_shapes(latent, classes)
         assert {n: tuple(s) for n, (s, _) in {**g_table, **d_table}.items()} == {n: tuple(v.shape) for n, v in params.items()}, cfg
-        _close(ours.generator(params, latents, labels), want_fake.t.detach())
-        features, logits = ours.discriminator(params, images, labels)
-        _close(features, want_features.t.detach())
-        _close(logits, want_logits.t.detach())
+        _close(ours.generator(params, latents, labels), fake)
+        got_features, got_logits = ours.discriminator(params, images, labels)
+        _close(got_features, features)
+        _close(got_logits, logits)
+
+
+@pytest.mark.skipif(not os.path.exists(gen.REFERENCE), reason="reference tree not present")
+def test_product_host_logic_follows_the_reference_over_configurations(emu):
+    """The same architectures through the product's networks.py over emulated kernels (fp32): names, shapes, values."""
+    import gansynth_b200.models as pmodels
+    import gansynth_b200.networks as pnet
+    import gansynth_b200.ops as pops
+    for cfg, latent, classes, level, latents, labels, images, params, fake, features, logits in _random_architectures():
+        store = pops.set_default_store(pops.VariableStore(device="cpu", seed=0))
+        pmodels.reset_global_step()
+        pg = pnet.PGGAN(growing_level=level, **cfg)
+        pg._ensure_variables("generator", latent, classes)
+        pg._ensure_variables("discriminator", 0, classes)
+        assert {n: tuple(v.shape) for n, v in store.vars.items()} == {n: tuple(v.shape) for n, v in params.items()}, cfg
+        store.load({n: v.float() for n, v in params.items()})
+        with torch.no_grad():
+            _close(pg.generator(latents.float(), labels.float()), fake, 2e-4)
+            got_features, got_logits = pg.discriminator(images.float(), labels.float())
+        _close(got_features, features, 2e-4)
+        _close(got_logits, logits, 2e-4)
 
 
 @pytest.mark.skipif(not os.path.exists(gen.REFERENCE), reason="reference tree not present")
