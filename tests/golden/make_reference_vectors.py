@@ -367,6 +367,56 @@ def full_step(dtype=torch.float64):
     return out
 
 
+def random_architectures(count=8):
+    """Seeded random architectures run through the reference's networks.py, live: yields (cfg, latent size, classes,
+    level, latents, labels, images, variables by name, the reference's fake images / features / logits), float64."""
+    tf, networks, _, _, _ = reference_modules()
+    tf.set_float_dtype(torch.float64)
+    rng = np.random.default_rng(7)
+    for case in range(count):
+        tf.reset_default_graph()
+        tf.set_random_seed(case)
+        seed_res = [int(rng.choice([1, 2, 3, 4])), int(rng.choice([1, 2, 4, 5]))]
+        doublings = int(rng.integers(1, 4))      # the reference cannot build a graph without at least one doubling
+        cfg = dict(min_resolution=seed_res, max_resolution=[r << doublings for r in seed_res],
+                   min_channels=int(rng.choice([2, 4, 6])), max_channels=int(rng.choice([8, 12, 64])))
+        latent, classes, batch = int(rng.choice([3, 8])), int(rng.choice([2, 7])), 4 * int(rng.integers(1, 3))
+        level = float(rng.choice([0.0, rng.uniform(0.0, 1.0), 1.0]))
+        g = torch.Generator().manual_seed(100 + case)
+        latents = torch.randn(batch, latent, generator=g, dtype=torch.float64)
+        labels = torch.nn.functional.one_hot(torch.randint(0, classes, (batch,), generator=g), classes).double()
+        images = torch.randn(batch, 2, *cfg["max_resolution"], generator=g, dtype=torch.float64)
+        ref = networks.PGGAN(growing_level=tf.Tensor(torch.tensor(level, dtype=torch.float64)), **cfg)
+        tf.build_all_branches(True)
+        ref.generator(tf.Tensor(latents), tf.Tensor(labels))
+        ref.discriminator(tf.Tensor(images), tf.Tensor(labels))
+        tf.build_all_branches(False)
+        _perturb_biases(tf, 200 + case)
+        fake = ref.generator(tf.Tensor(latents), tf.Tensor(labels))
+        features, logits = ref.discriminator(tf.Tensor(images), tf.Tensor(labels))
+        params = {n: v.t.detach().clone() for n, v in tf.variables().items()}
+        yield cfg, latent, classes, level, latents, labels, images, params, fake.t.detach(), features.t.detach(), logits.t.detach()
+
+
+ODD_CASES = (1, 3, 6)      # 4x5 seed with 4..64 channels; 4x5 -> 32x40 with 6..12 channels; a 1x1 seed
+
+
+def odd_architectures():
+    """Three of `random_architectures` as a fixture (the others only run live)."""
+    out = dict(cases=np.asarray(ODD_CASES))
+    for case, (cfg, latent, classes, level, latents, labels, images, params, fake, features, logits) in enumerate(random_architectures()):
+        if case not in ODD_CASES:
+            continue
+        tag = "case%d:" % case
+        out[tag + "cfg"] = np.asarray(cfg["min_resolution"] + cfg["max_resolution"] + [cfg["min_channels"], cfg["max_channels"], latent, classes])
+        out[tag + "level"] = np.asarray(level)
+        for key, value in dict(latents=latents, labels=labels, images=images, fake_images=fake, features=features, logits=logits).items():
+            out[tag + key] = _np(value)
+        for name, value in params.items():
+            out[tag + "var:" + name] = _np(value)
+    return out
+
+
 def metrics_case():
     """metrics.py is plain numpy / scipy / sklearn: imported and called as it is."""
     for name in ("metrics",):
@@ -393,7 +443,7 @@ def metrics_case():
                 binomial=metrics.binomial_proportion_test(props_p, 400, props_q, 300, 0.05))
 
 
-CASES = dict(reference_metrics=metrics_case, reference_pggan=pggan_forward, reference_spectral=spectral, reference_step=gan_step,
+CASES = dict(reference_metrics=metrics_case, reference_architectures=odd_architectures, reference_pggan=pggan_forward, reference_spectral=spectral, reference_step=gan_step,
              reference_step_fake_penalty=lambda: gan_step(fake_penalty=2.0, iterations=1),
              reference_classifier=classifier_step)
 

@@ -228,3 +228,36 @@ def check_full_step(store, device, sample_tol, norm_tol=5e-3):
         print("%s: loss %.6f (reference %.6f); worst gradient norm error %.2e (%s); worst sampled element %.2e of its "
               "variable's maximum (%s)" % (which, float(loss), want, worst_norm[0], worst_norm[1], worst[0], worst[1]))
         assert not failures, failures[:6]
+
+
+def fixture_architectures():
+    """tests/golden/reference_architectures.npz in the shape of gen.random_architectures()."""
+    z = load("reference_architectures")
+    for case in z["cases"]:
+        tag = "case%d:" % int(case)
+        c = [int(v) for v in z[tag + "cfg"]]
+        cfg = dict(min_resolution=c[0:2], max_resolution=c[2:4], min_channels=c[4], max_channels=c[5])
+        t = lambda k: torch.from_numpy(z[tag + k])
+        params = {k[len(tag) + 4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith(tag + "var:")}
+        yield (cfg, c[6], c[7], float(z[tag + "level"]), t("latents"), t("labels"), t("images"), params, t("fake_images"),
+               t("features"), t("logits"))
+
+
+def check_architectures(device):
+    """Architectures off the benchmark's beaten path (non-square 4x5 and 1x1 seeds, channel counts 6 / 12, 2 or 7 classes)
+    through the product's networks.py: variable names and shapes, then values at 1e-3."""
+    import gansynth_b200.models as pmodels
+    import gansynth_b200.networks as pnet
+    import gansynth_b200.ops as pops
+    for cfg, latent, classes, level, latents, labels, images, params, fake, features, logits in fixture_architectures():
+        store = pops.set_default_store(pops.VariableStore(device=device, seed=0))
+        pmodels.reset_global_step()
+        pg = pnet.PGGAN(growing_level=level, **cfg)
+        pg._ensure_variables("generator", latent, classes)
+        pg._ensure_variables("discriminator", 0, classes)
+        assert {n: tuple(v.shape) for n, v in store.vars.items()} == {n: tuple(v.shape) for n, v in params.items()}, cfg
+        store.load({n: v.float() for n, v in params.items()})
+        with torch.no_grad():
+            got = pg.generator(latents.float().to(device), labels.float().to(device))
+            got_features, got_logits = pg.discriminator(images.float().to(device), labels.float().to(device))
+        assert rel(got, fake.numpy()) < TOL and rel(got_features, features.numpy()) < TOL and rel(got_logits, logits.numpy()) < TOL, cfg

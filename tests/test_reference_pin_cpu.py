@@ -98,6 +98,23 @@ def test_variable_tables_of_both_command_lines():
             assert shape == list(ours[name]), name
 
 
+def test_odd_architectures_from_fixture():
+    """Seed resolutions 4x5 and 1x1, channel counts that are not multiples of four, 2 / 7 classes, 3 / 8 latents
+    (tests/golden/reference_architectures.npz): the oracle on any box."""
+    import reference_vectors as rv
+    for cfg, latent, classes, level, latents, labels, images, params, fake, features, logits in rv.fixture_architectures():
+        ours = onet.PGGAN(growing_level=level, **cfg)
+        _close(ours.generator(params, latents, labels), fake)
+        got_features, got_logits = ours.discriminator(params, images, labels)
+        _close(got_features, features)
+        _close(got_logits, logits)
+
+
+def test_product_odd_architectures_from_fixture(emu):
+    import reference_vectors as rv
+    rv.check_architectures("cpu")
+
+
 # ------------------------------------------------------------------------------------------------ spectral_ops.py
 def test_spectral_round_trip():
     z = _load("reference_spectral")
@@ -273,42 +290,11 @@ def test_committed_vectors_are_what_the_reference_says():
         _close(logits, z32["logits_%d" % k], 1e-4)
 
 
-def _random_architectures(count=8):
-    """Seeded random architectures run through the reference's networks.py, live: yields (cfg, latent size, classes,
-    level, latents, labels, images, variables by name, the reference's fake images / features / logits)."""
-    tf, networks, _, _, _ = gen.reference_modules()
-    tf.set_float_dtype(torch.float64)
-    rng = np.random.default_rng(7)
-    for case in range(count):
-        tf.reset_default_graph()
-        tf.set_random_seed(case)
-        seed_res = [int(rng.choice([1, 2, 3, 4])), int(rng.choice([1, 2, 4, 5]))]
-        doublings = int(rng.integers(1, 4))      # the reference cannot build a graph without at least one doubling
-        cfg = dict(min_resolution=seed_res, max_resolution=[r << doublings for r in seed_res],
-                   min_channels=int(rng.choice([2, 4, 6])), max_channels=int(rng.choice([8, 12, 64])))
-        latent, classes, batch = int(rng.choice([3, 8])), int(rng.choice([2, 7])), 4 * int(rng.integers(1, 3))
-        level = float(rng.choice([0.0, rng.uniform(0.0, 1.0), 1.0]))
-        g = torch.Generator().manual_seed(100 + case)
-        latents = torch.randn(batch, latent, generator=g, dtype=torch.float64)
-        labels = torch.nn.functional.one_hot(torch.randint(0, classes, (batch,), generator=g), classes).double()
-        images = torch.randn(batch, 2, *cfg["max_resolution"], generator=g, dtype=torch.float64)
-        ref = networks.PGGAN(growing_level=tf.Tensor(torch.tensor(level, dtype=torch.float64)), **cfg)
-        tf.build_all_branches(True)
-        ref.generator(tf.Tensor(latents), tf.Tensor(labels))
-        ref.discriminator(tf.Tensor(images), tf.Tensor(labels))
-        tf.build_all_branches(False)
-        gen._perturb_biases(tf, 200 + case)
-        fake = ref.generator(tf.Tensor(latents), tf.Tensor(labels))
-        features, logits = ref.discriminator(tf.Tensor(images), tf.Tensor(labels))
-        params = {n: v.t.detach().clone() for n, v in tf.variables().items()}
-        yield cfg, latent, classes, level, latents, labels, images, params, fake.t.detach(), features.t.detach(), logits.t.detach()
-
-
 @pytest.mark.skipif(not os.path.exists(gen.REFERENCE), reason="reference tree not present")
 def test_oracle_follows_the_reference_over_configurations():
     """Live, no fixture: seeded random architectures (seed resolution, number of doublings, channel clamp, latent size,
     label count, growth level, batch) through the reference's networks.py and through the oracle with the same variables."""
-    for cfg, latent, classes, level, latents, labels, images, params, fake, features, logits in _random_architectures():
+    for cfg, latent, classes, level, latents, labels, images, params, fake, features, logits in gen.random_architectures():
         ours = onet.PGGAN(growing_level=level, **cfg)
         g_table, d_table = ours.variable_shapes(latent, classes)
         assert {n: tuple(s) for n, (s, _) in {**g_table, **d_table}.items()} == {n: tuple(v.shape) for n, v in params.items()}, cfg
@@ -324,7 +310,7 @@ def test_product_host_logic_follows_the_reference_over_configurations(emu):
     import gansynth_b200.models as pmodels
     import gansynth_b200.networks as pnet
     import gansynth_b200.ops as pops
-    for cfg, latent, classes, level, latents, labels, images, params, fake, features, logits in _random_architectures():
+    for cfg, latent, classes, level, latents, labels, images, params, fake, features, logits in gen.random_architectures():
         store = pops.set_default_store(pops.VariableStore(device="cpu", seed=0))
         pmodels.reset_global_step()
         pg = pnet.PGGAN(growing_level=level, **cfg)

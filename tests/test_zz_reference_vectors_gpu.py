@@ -45,3 +45,7 @@ def test_full_size_batch8_step(cuda_store, conv_mode):
         rv.check_full_step(cuda_store, "cuda", sample_tol=1e-2, norm_tol=5e-3)
     else:
         rv.check_full_step(cuda_store, "cuda", sample_tol=3e-2, norm_tol=3e-2)
+
+
+def test_odd_architectures(cuda_store, conv_mode):
+    rv.check_architectures("cuda")
