@@ -417,6 +417,40 @@ def odd_architectures():
     return out
 
 
+def random_spectral_configs(count=8):
+    """Seeded random spectral configurations through the reference's spectral_ops.py, live: yields (parameters, waveforms,
+    log-mel, IF, reconstructed waveforms), float64."""
+    tf, _, spectral_ops, _, _ = reference_modules()
+    tf.set_float_dtype(torch.float64)
+    rng = np.random.default_rng(9)
+    for case in range(count):
+        bins = int(rng.choice([16, 32, 64, 256]))
+        steps = int(rng.choice([4, 9, 16, 33]))
+        overlap = float(rng.choice([0.5, 0.75, 0.875]))
+        frame_step = int((1.0 - overlap) * 2 * bins)
+        covered = frame_step * (steps - 1) + 2 * bins
+        params = dict(waveform_length=int(covered - rng.integers(0, 2 * bins - 1)), sample_rate=int(rng.choice([8000, 16000, 44100])),
+                      spectrogram_shape=[steps, bins], overlap=overlap)
+        g = torch.Generator().manual_seed(300 + case)
+        waves = 0.3 * torch.randn(3, params["waveform_length"], generator=g, dtype=torch.float64)
+        logmel, inst = spectral_ops.convert_to_spectrogram(tf.Tensor(waves), **params)
+        back = spectral_ops.convert_to_waveform(logmel, inst, **params)
+        yield params, waves, logmel.t, inst.t, back.t
+
+
+def spectral_configs():
+    """All eight of `random_spectral_configs` as a fixture (they are small)."""
+    out = {}
+    for case, (params, waves, logmel, inst, back) in enumerate(random_spectral_configs()):
+        tag = "case%d:" % case
+        out[tag + "params"] = np.asarray([params["waveform_length"], params["sample_rate"], *params["spectrogram_shape"]])
+        out[tag + "overlap"] = np.asarray(params["overlap"])
+        for key, value in dict(waves=waves, logmel=logmel, inst=inst, back=back).items():
+            out[tag + key] = _np(value)
+    out["count"] = np.asarray(case + 1)
+    return out
+
+
 def metrics_case():
     """metrics.py is plain numpy / scipy / sklearn: imported and called as it is."""
     for name in ("metrics",):
@@ -443,7 +477,7 @@ def metrics_case():
                 binomial=metrics.binomial_proportion_test(props_p, 400, props_q, 300, 0.05))
 
 
-CASES = dict(reference_metrics=metrics_case, reference_architectures=odd_architectures, reference_pggan=pggan_forward, reference_spectral=spectral, reference_step=gan_step,
+CASES = dict(reference_metrics=metrics_case, reference_spectral_configs=spectral_configs, reference_architectures=odd_architectures, reference_pggan=pggan_forward, reference_spectral=spectral, reference_step=gan_step,
              reference_step_fake_penalty=lambda: gan_step(fake_penalty=2.0, iterations=1),
              reference_classifier=classifier_step)
 

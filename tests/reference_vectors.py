@@ -261,3 +261,25 @@ def check_architectures(device):
             got = pg.generator(latents.float().to(device), labels.float().to(device))
             got_features, got_logits = pg.discriminator(images.float().to(device), labels.float().to(device))
         assert rel(got, fake.numpy()) < TOL and rel(got_features, features.numpy()) < TOL and rel(got_logits, logits.numpy()) < TOL, cfg
+
+
+def fixture_spectral_configs():
+    z = load("reference_spectral_configs")
+    for case in range(int(z["count"])):
+        tag = "case%d:" % case
+        p = [int(v) for v in z[tag + "params"]]
+        params = dict(waveform_length=p[0], sample_rate=p[1], spectrogram_shape=p[2:4], overlap=float(z[tag + "overlap"]))
+        yield (params,) + tuple(torch.from_numpy(z[tag + k]) for k in ("waves", "logmel", "inst", "back"))
+
+
+def check_spectral_configs(device):
+    """The generic spectral kernels over eight configurations of the reference's spectral_ops.py (see the fixture)."""
+    import gansynth_b200.spectral_ops as psp
+    for params, waves, logmel, inst, back in fixture_spectral_configs():
+        got_lm, got_if = psp.convert_to_spectrogram(waves.float().to(device), **params)
+        assert rel(got_lm, logmel.numpy()) < TOL, (params, rel(got_lm, logmel.numpy()))
+        d = np.abs(got_if.detach().double().cpu().numpy() - inst.numpy())
+        wrapped = np.abs(d - 2.0) < 2e-3                     # a phase step within rounding of +-pi unwraps either way
+        assert float(wrapped.mean()) < 5e-3 and float(d[~wrapped].max()) < 2e-3, (params, float(wrapped.mean()), float(d[~wrapped].max()))
+        got_back = psp.convert_to_waveform(logmel.float().to(device), inst.float().to(device), **params)
+        assert rel(got_back, back.numpy()) < TOL, (params, rel(got_back, back.numpy()))

@@ -325,25 +325,17 @@ def test_product_host_logic_follows_the_reference_over_configurations(emu):
         _close(got_logits, logits, 2e-4)
 
 
-@pytest.mark.skipif(not os.path.exists(gen.REFERENCE), reason="reference tree not present")
-def test_oracle_spectral_follows_the_reference_over_configurations():
-    """Live: spectrogram shapes, overlaps, sample rates and waveform lengths (front padding 0 ... most of a frame) through
-    the reference's spectral_ops.py and through the oracle, both ways."""
-    tf, _, spectral_ops, _, _ = gen.reference_modules()
-    tf.set_float_dtype(torch.float64)
-    rng = np.random.default_rng(9)
-    for case in range(8):
-        bins = int(rng.choice([16, 32, 64, 256]))
-        steps = int(rng.choice([4, 9, 16, 33]))
-        overlap = float(rng.choice([0.5, 0.75, 0.875]))
-        frame_step = int((1.0 - overlap) * 2 * bins)
-        covered = frame_step * (steps - 1) + 2 * bins
-        params = dict(waveform_length=int(covered - rng.integers(0, 2 * bins - 1)), sample_rate=int(rng.choice([8000, 16000, 44100])),
-                      spectrogram_shape=[steps, bins], overlap=overlap)
-        g = torch.Generator().manual_seed(300 + case)
-        waves = 0.3 * torch.randn(3, params["waveform_length"], generator=g, dtype=torch.float64)
-        want_lm, want_if = spectral_ops.convert_to_spectrogram(tf.Tensor(waves), **params)
+def test_spectral_configurations_from_fixture():
+    """Spectrogram shapes, overlaps 0.5 / 0.75 / 0.875, three sample rates, waveform lengths with front padding from 0 to
+    most of a frame (tests/golden/reference_spectral_configs.npz): the oracle both ways."""
+    import reference_vectors as rv
+    for params, waves, logmel, inst, back in rv.fixture_spectral_configs():
         got_lm, got_if = osp.convert_to_spectrogram(waves, **params)
-        _close(got_lm, want_lm.t)
-        _close(got_if, want_if.t)
-        _close(osp.convert_to_waveform(got_lm, got_if, **params), spectral_ops.convert_to_waveform(want_lm, want_if, **params).t)
+        _close(got_lm, logmel)
+        _close(got_if, inst)
+        _close(osp.convert_to_waveform(got_lm, got_if, **params), back)
+
+
+def test_product_spectral_configurations_from_fixture(emu):
+    import reference_vectors as rv
+    rv.check_spectral_configs("cpu")

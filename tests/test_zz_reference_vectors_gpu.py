@@ -49,3 +49,7 @@ def test_full_size_batch8_step(cuda_store, conv_mode):
 
 def test_odd_architectures(cuda_store, conv_mode):
     rv.check_architectures("cuda")
+
+
+def test_spectral_configurations(cuda_store):
+    rv.check_spectral_configs("cuda")
