@@ -85,6 +85,9 @@ def test_variable_tables_of_both_command_lines():
                                   max_channels=256).variable_shapes(256, 61)
     want = {n: list(s) for n, (s, _) in {**g_table, **d_table}.items()}
     assert tables["gan_synth"] == want
+    count = lambda prefix: sum(int(np.prod(shape)) for name, shape in tables["gan_synth"].items() if name.startswith(prefix))
+    # the sizes of the two flat gradient buffers the data-parallel exchange moves: 35.7 MB and 27.3 MB
+    assert count("generator/") == 8932238 and count("discriminator/") == 6830973
     resnet = onet.ResNet(conv_param=dict(filters=64, kernel_size=[7, 7], strides=[2, 2]), pool_param=dict(kernel_size=[3, 3], strides=[2, 2]),
                          residual_params=[dict(filters=64, strides=[1, 1], blocks=3), dict(filters=128, strides=[2, 2], blocks=4),
                                           dict(filters=256, strides=[2, 2], blocks=6), dict(filters=512, strides=[2, 2], blocks=3)],
