@@ -100,7 +100,7 @@ def check_training_sequence(store, device, fixture="reference_step"):
         else:
             loss = model.generator_step(labels, latents)
         want = float(z[tag + which + "_loss"])
-        assert abs(float(loss) - want) < TOL * max(1.0, abs(want)), (run, float(loss), want)
+        assert abs(float(loss.detach()) - want) < TOL * max(1.0, abs(want)), (run, float(loss.detach()), want)
         flat = model._opt[which]["grad"]
         for name, (a, k) in store.offsets[which].items():
             want_g = z[tag + "grad:" + name]
@@ -211,7 +211,7 @@ def check_full_step(store, device, sample_tol, norm_tol=5e-3):
         else:
             loss = model.generator_loss_fn(labels, latents)
         want = float(z[which + "_loss"])
-        assert abs(float(loss) - want) < TOL * max(1.0, abs(want)), (which, float(loss), want)
+        assert abs(float(loss.detach()) - want) < TOL * max(1.0, abs(want)), (which, float(loss.detach()), want)
         model._backward(which, loss)
         flat = model._opt[which]["grad"]
         worst, worst_norm, failures = (0.0, ""), (0.0, ""), []
