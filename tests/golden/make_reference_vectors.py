@@ -367,6 +367,72 @@ def full_step(dtype=torch.float64):
     return out
 
 
+# ------------------------------------------------------------------------------------------------ BASELINE config 1
+CONFIG1 = dict(min_resolution=[4, 4], max_resolution=[16, 16], min_channels=32, max_channels=256)
+CONFIG1_SPECTRAL = dict(waveform_length=152, sample_rate=16000, spectrogram_shape=[16, 16], overlap=0.75)
+CONFIG1_BATCH, CONFIG1_GROWING_STEPS = 4, 4
+
+
+def config1_inputs(run):
+    rng = torch.Generator().manual_seed(71 + run)
+    waves = 0.3 * torch.randn(CONFIG1_BATCH, CONFIG1_SPECTRAL["waveform_length"], generator=rng, dtype=torch.float64)
+    labels = torch.nn.functional.one_hot(torch.randint(0, FULL_LABELS, (CONFIG1_BATCH,), generator=rng), FULL_LABELS).double()
+    latents = torch.randn(CONFIG1_BATCH, FULL_LATENT, generator=rng, dtype=torch.float64)
+    return waves.float().double(), labels, latents.float().double()
+
+
+def config1_sequence(iterations=3, dtype=torch.float64):
+    """BASELINE.json configs[0] -- `gan_synth_main.py --train` with the 2-stage PGGAN (4x4 -> 16x16), batch 4 -- as the
+    reference itself runs it: D run, G run, ... with the growth level following global_step (levels 0, 1/4, 2/4: nothing
+    grown, first blend, second blend).  The 8 MB of weights are `named_value`s and evolve by the reference's own Adam
+    updates, so the file keeps summaries only: both losses of every run, norm / maximum / samples of the applied
+    gradients and of the updated variables."""
+    tf, networks, _, models, Dict = reference_modules()
+    tf.reset_default_graph()
+    tf.set_float_dtype(dtype)
+    tf.set_random_seed(0)
+    state = dict(run=0)
+
+    def real_input_fn():
+        waves, labels, _ = config1_inputs(state["run"])
+        return tf.Tensor(waves.to(dtype).requires_grad_(True)), tf.Tensor(labels.to(dtype))
+
+    def fake_input_fn():
+        return tf.Tensor(config1_inputs(state["run"])[2].to(dtype).requires_grad_(True))
+
+    def construct():
+        pggan = networks.PGGAN(growing_level=tf.cast(tf.divide(x=tf.train.get_or_create_global_step(), y=CONFIG1_GROWING_STEPS),
+                                                     tf.float32), **CONFIG1)
+        return models.GANSynth(generator=pggan.generator, discriminator=pggan.discriminator, real_input_fn=real_input_fn,
+                               fake_input_fn=fake_input_fn, spectral_params=Dict(CONFIG1_SPECTRAL), hyper_params=Dict(HYPER))
+
+    tf.build_all_branches(True)
+    construct()
+    tf.build_all_branches(False)
+    for name, var in tf.variables().items():
+        if var.trainable:
+            var.assign(named_value(name, var.t.shape).to(dtype))
+    out = dict(iterations=np.asarray(iterations),
+               variable_names=np.asarray([n for n, v in tf.variables().items() if v.trainable]),
+               variable_sizes=np.asarray([v.t.numel() for n, v in tf.variables().items() if v.trainable]))
+    for run in range(2 * iterations):
+        which = ("discriminator", "generator")[run % 2]
+        state["run"] = run
+        model = construct()
+        op = getattr(model, which + "_train_op")
+        tag = "run%d:" % run
+        out[tag + "global_step"] = _np(tf.train.get_or_create_global_step().t)
+        out[tag + "generator_loss"] = _np(model.generator_loss.t)
+        out[tag + "discriminator_loss"] = _np(model.discriminator_loss.t)
+        out[tag + "fake_images"] = _np(model.fake_images.t)
+        for grad, var in op.grads_and_vars:
+            out[tag + "grad:" + var.op.name] = grad_summary(torch.zeros_like(var.t) if grad is None else grad)
+        op.run()
+        for grad, var in op.grads_and_vars:
+            out[tag + "var:" + var.op.name] = grad_summary(var.t.detach())
+    return out
+
+
 def random_architectures(count=8):
     """Seeded random architectures run through the reference's networks.py, live: yields (cfg, latent size, classes,
     level, latents, labels, images, variables by name, the reference's fake images / features / logits), float64."""
@@ -477,7 +543,7 @@ def metrics_case():
                 binomial=metrics.binomial_proportion_test(props_p, 400, props_q, 300, 0.05))
 
 
-CASES = dict(reference_metrics=metrics_case, reference_spectral_configs=spectral_configs, reference_architectures=odd_architectures, reference_pggan=pggan_forward, reference_spectral=spectral, reference_step=gan_step,
+CASES = dict(reference_metrics=metrics_case, reference_config1=config1_sequence, reference_spectral_configs=spectral_configs, reference_architectures=odd_architectures, reference_pggan=pggan_forward, reference_spectral=spectral, reference_step=gan_step,
              reference_step_fake_penalty=lambda: gan_step(fake_penalty=2.0, iterations=1),
              reference_classifier=classifier_step)
 

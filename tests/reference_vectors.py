@@ -283,3 +283,64 @@ def check_spectral_configs(device):
         assert float(wrapped.mean()) < 5e-3 and float(d[~wrapped].max()) < 2e-3, (params, float(wrapped.mean()), float(d[~wrapped].max()))
         got_back = psp.convert_to_waveform(logmel.float().to(device), inst.float().to(device), **params)
         assert rel(got_back, back.numpy()) < TOL, (params, rel(got_back, back.numpy()))
+
+
+def config1_oracle(z):
+    """The oracle stepping through tests/golden/reference_config1.npz: yields (run, which, inputs, oracle step) BEFORE the
+    run's update and applies the update afterwards, so callers can compare their own sub-step from the same state."""
+    from oracle import models as omodels
+    from oracle import networks as onet
+    holder = {}
+    pg = onet.PGGAN(growing_level=lambda: holder["step"].global_step / gen.CONFIG1_GROWING_STEPS, **gen.CONFIG1)
+    names = [str(n) for n in z["variable_names"]]
+    g_table, d_table = pg.variable_shapes(gen.FULL_LATENT, gen.FULL_LABELS)
+    shapes = {n: s for n, (s, _) in {**g_table, **d_table}.items()}
+    assert sorted(names) == sorted(shapes)
+    step = holder["step"] = omodels.GANSynthStep(pg, {n: gen.named_value(n, shapes[n]) for n in names}, gen.HYPER)
+    for run in range(2 * int(z["iterations"])):
+        which = ("discriminator", "generator")[run % 2]
+        assert step.global_step == int(z["run%d:global_step" % run])
+        waves, labels, latents = gen.config1_inputs(run)
+        yield run, which, waves, labels, latents, pg, step
+        real = omodels.real_images_from_waveforms(waves, gen.CONFIG1_SPECTRAL)
+        if which == "discriminator":
+            step.discriminator_update(real, labels, latents)
+        else:
+            step.generator_update(labels, latents)
+
+
+def check_config1(store, device, sample_tol=1e-2, norm_tol=5e-3):
+    """BASELINE configs[0] (2-stage PGGAN 4x4 -> 16x16, batch 4, the [16, 16] spectrogram) through the product's public
+    sub-step calls against the reference's own run of it: loss of every run at 1e-3, norm and samples of every applied
+    gradient.  Every run starts from the reference's state, carried by the oracle (which test_reference_pin_cpu.py holds
+    to the same file at 1e-10)."""
+    import gansynth_b200.models as pmodels
+    import gansynth_b200.networks as pnet
+    z = load("reference_config1")
+    pmodels.reset_global_step()
+    level = pmodels.get_or_create_global_step() / gen.CONFIG1_GROWING_STEPS
+    pg = pnet.PGGAN(growing_level=level, **gen.CONFIG1)
+    pg._ensure_variables("generator", gen.FULL_LATENT, gen.FULL_LABELS)
+    pg._ensure_variables("discriminator", 0, gen.FULL_LABELS)
+    model = pmodels.GANSynth(pg.generator, pg.discriminator, None, None, gen.CONFIG1_SPECTRAL, gen.HYPER, device=device)
+    model.use_cuda_graphs = False
+    for run, which, waves, labels, latents, _, ostep in config1_oracle(z):
+        store.load({n: p.detach().float() for n, p in ostep.params.items()})
+        model.global_step.value = ostep.global_step
+        tag = "run%d:" % run
+        dev = lambda t: t.float().to(device)
+        if which == "discriminator":
+            loss = model.discriminator_step(dev(waves), dev(labels), dev(latents))
+        else:
+            loss = model.generator_step(dev(labels), dev(latents))
+        want = float(z[tag + which + "_loss"])
+        assert abs(float(loss) - want) < TOL * max(1.0, abs(want)), (run, float(loss), want)
+        flat = model._opt[which]["grad"]
+        for name, (a, k) in store.offsets[which].items():
+            want_s = z[tag + "grad:" + name]
+            got_s = gen.grad_summary(flat[a:a + k].detach().cpu())
+            if want_s[1] == 0.0:                               # colour blocks the growth level has not reached
+                assert got_s[1] == 0.0, (run, name)
+                continue
+            assert abs(got_s[0] - want_s[0]) <= norm_tol * want_s[0], (run, name, got_s[0], want_s[0])
+            assert float(np.abs(got_s[2:] - want_s[2:]).max()) <= sample_tol * want_s[1], (run, name)

@@ -231,6 +231,40 @@ def test_full_size_step_oracle():
             _grad_close(gen.grad_summary(grad.detach()), want, 1e-7 * max(1.0, want[1] and want[0] / want[1]))
 
 
+# ------------------------------------------------------------------------------------------------ BASELINE configs[0]
+def test_baseline_config1_sequence():
+    """`gan_synth_main.py --train` with the 2-stage PGGAN at batch 4 as the reference runs it (three D-run / G-run
+    iterations, growth levels 0, 1/4, 2/4): the oracle reproduces both losses, every applied gradient and every updated
+    variable (norm, maximum, 16 samples each) from the same named weights."""
+    import reference_vectors as rv
+    z = _load("reference_config1")
+    for run, which, waves, labels, latents, pg, step in rv.config1_oracle(z):
+        tag = "run%d:" % run
+        real = omodels.real_images_from_waveforms(waves, gen.CONFIG1_SPECTRAL)
+        with torch.no_grad():
+            _close(pg.generator(step.params, latents, labels), z[tag + "fake_images"])
+        _close(omodels.discriminator_loss(pg, step.params, real, labels, latents, gen.HYPER).detach(), z[tag + "discriminator_loss"])
+        _close(omodels.generator_loss(pg, step.params, labels, latents, gen.HYPER).detach(), z[tag + "generator_loss"])
+        if run > 0:                                           # the variables the previous run's optimizer moved
+            prev, scope = "run%d:" % (run - 1), ("generator", "discriminator")[run % 2]
+            for name, p in step.params.items():
+                if name.startswith(scope + "/"):
+                    _grad_close(gen.grad_summary(p.detach()), z[prev + "var:" + name], 1e-9)
+        grads = (step.discriminator_update(real, labels, latents, apply=False) if which == "discriminator"
+                 else step.generator_update(labels, latents, apply=False))[1]
+        for name, grad in grads.items():
+            want = z[tag + "grad:" + name]
+            if want[1] == 0.0:
+                assert float(grad.abs().max()) == 0.0, name
+            else:
+                _grad_close(gen.grad_summary(grad), want, 1e-7 * want[0] / want[1])
+
+
+def test_product_baseline_config1_sequence(emu):
+    import reference_vectors as rv
+    rv.check_config1(emu, "cpu")
+
+
 # ------------------------------------------------------------------------------------------------ metrics.py
 def test_evaluation_statistics():
     """gansynth_b200.metrics against values the reference's metrics.py (plain numpy / scipy) returned for the same inputs."""

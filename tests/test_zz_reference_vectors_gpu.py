@@ -53,3 +53,11 @@ def test_odd_architectures(cuda_store, conv_mode):
 
 def test_spectral_configurations(cuda_store):
     rv.check_spectral_configs("cuda")
+
+
+def test_baseline_config1_sequence(cuda_store, conv_mode):
+    """BASELINE configs[0] as the reference itself runs it: reference_vectors.check_config1."""
+    if conv_mode == "fp32":
+        rv.check_config1(cuda_store, "cuda")
+    else:
+        rv.check_config1(cuda_store, "cuda", sample_tol=3e-2, norm_tol=3e-2)
