@@ -331,6 +331,18 @@ def kernel_table(conv, ew, cupti, cupti_total_us, steps_profiled, steps_eager, p
     return rows
 
 
+def cpu_model():
+    """Model name of the host CPU (reported beside every CPU-timed number)."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for row in f:
+                if row.lower().startswith("model name"):
+                    return row.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def spectral_secondary(device, pk):
     """BASELINE config 3: batch 256 round trip, GSamp/s and HBM roofline of the two spectral kernels."""
     import gansynth_b200.spectral_ops as sp
@@ -629,7 +641,7 @@ def bench_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count()
         times = oracle_iteration_time(BATCH, 3, cores)[1:]          # first iteration = warm-up (constants, allocator)
-        line["cpu_baseline"] = dict(value=1.0 / float(np.mean(times)), unit="steps/s", cores=cores, kind="port",
+        line["cpu_baseline"] = dict(value=1.0 / float(np.mean(times)), unit="steps/s", cores=cores, cpu=cpu_model(), kind="port",
                                     sample="two full iterations (D update + G update) of the oracle port at batch 8 after "
                                            "one warm-up iteration (%.1f s each)" % float(np.mean(times)))
     if args.kernel_table:
@@ -676,7 +688,7 @@ def bench_reference(args):
         vs_baseline=None, dtype="f32", data="synthetic",
         config=dict(workload="BASELINE configs[1] on host CPU cores via the oracle port (PyTorch-CPU fp32)",
                     global_batch=BATCH, parallelism="cpu"),
-        cpu_baseline=dict(value=value, unit="steps/s", cores=cores, kind="port", sample=sample),
+        cpu_baseline=dict(value=value, unit="steps/s", cores=cores, cpu=cpu_model(), kind="port", sample=sample),
         e2e=dict(value=value, unit="steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))), flush=True)
 
 
