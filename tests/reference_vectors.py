@@ -226,7 +226,7 @@ def check_full_step(store, device, sample_tol, norm_tol=5e-3):
             worst, worst_norm = max(worst, (err, name)), max(worst_norm, (nerr, name))
             failures += [(name, nerr, err)] if (nerr > norm_tol or err > sample_tol) else []
         print("%s: loss %.6f (reference %.6f); worst gradient norm error %.2e (%s); worst sampled element %.2e of its "
-              "variable's maximum (%s)" % (which, float(loss), want, worst_norm[0], worst_norm[1], worst[0], worst[1]))
+              "variable's maximum (%s)" % (which, float(loss.detach()), want, worst_norm[0], worst_norm[1], worst[0], worst[1]))
         assert not failures, failures[:6]
 
 
